@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — Mbases/s depth-counted on a synthetic 30x WGS-shaped alignment stream (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the depth hot path over one contig: zero the difference array, scatter the
+read intervals, one fused scan -> per-window sums/mins + callable-class runs.
+Workload at N=1 = BASELINE config[1]: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500.
+At N>1 every rank processes its own chr20-sized contig (contigs shard across GPUs with no
+data-path collective) -> weak scaling; value = N * bases / max-over-ranks device time.
+
+value  : inputs already resident in HBM (segments uploaded before the timed region).
+e2e    : the one-call C-ABI entry gl_depth_region with PINNED HOST buffers: H2D of the segments
+         and D2H of window sums + runs are inside the timed region, every step.
+roofline / cpu_baseline: see DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W = 500
+MINCOV = 4
+MAXMEAN = 0
+STEP = 10_000_000           # depth/depth.go:48 (a multiple of W=500)
+METRIC = "Mbases/s depth-counted (synth 30x WGS)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            t = [x.strip() for x in ln.split(",")]
+            if len(t) < 6:
+                continue
+            try:
+                sm.append(float(t[0])); mx.append(float(t[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_depth_pass(orc, s, e, L, threads, chunks):
+    """The reference's CPU path for one contig, chunk-parallel like `goleft depth -p`:
+    per 10 Mb chunk, per-base counting (the samtools child) + the callback's window/class walk + BED text."""
+    from concurrent.futures import ThreadPoolExecutor
+    order = np.argsort(s, kind="stable") if not (np.diff(s) >= 0).all() else None
+    if order is not None:
+        s, e = s[order], e[order]
+    maxlen = int((e - s).max()) if s.size else 0
+
+    def one(ch):
+        cs, ce = ch
+        lo = np.searchsorted(s, cs - maxlen, "left")
+        hi = np.searchsorted(s, ce, "left")
+        d = orc.pileup_diff(s[lo:hi], e[lo:hi], cs, ce)
+        hd, ca = orc.walk_chunk("chr20", cs, ce, W, MINCOV, MAXMEAN, d)
+        return len(hd) + len(ca)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        nbytes = sum(ex.map(one, chunks))
+    return time.perf_counter() - t0, nbytes
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; neither go nor samtools
+    exists in this image, so oracle/_ref cannot be built), all host threads, bounded sample."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from goleft_b200 import synth
+    from oracle import loader as orc
+    L = synth.CHR20_LEN
+    s, e = synth.chr20_like()
+    threads = os.cpu_count() or 1
+    chunks = orc.gen_chunks(L, W)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, _ = cpu_depth_pass(orc, s, e, L, threads, chunks)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    val = L / t / 1e6
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mbases/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+           "config": {"workload": "depth: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500, 1 sample",
+                      "window": W, "mincov": MINCOV, "segments": int(s.size)},
+           "cpu_baseline": {"value": val, "unit": "Mbases/s", "cores": threads, "kind": "port",
+                            "sample": "whole chr20 contig, 7 chunks of 10 Mb, chunk-parallel; per-base counting + "
+                                      "window/class walk + BED text (samtools text printing/parsing excluded)"},
+           "e2e": {"value": val, "unit": "Mbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = dist_env()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from goleft_b200 import capi, synth
+    if capi.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; goleft_b200 has no CPU fallback")
+
+    L = synth.CHR20_LEN
+    t0 = time.time()
+    s, e = synth.chr20_like(contig_index=19 + rank)
+    nseg = int(s.size)
+    log(f"[rank {rank}] synth: {nseg} segments over {L} bp in {time.time() - t0:.1f}s")
+
+    ctx = capi.Ctx(local)
+    d_s, d_e = ctx.dev_array(s), ctx.dev_array(e)
+    n_win = (L - 1) // W + 1
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def step_resident():
+        ctx.depth_begin(0, L)
+        ctx.depth_add_segments_device(d_s, d_e, nseg)
+        ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP)
+
+    # pinned host buffers for the end-to-end arm
+    h_s, h_e = ctx.pinned_empty(nseg, np.int32), ctx.pinned_empty(nseg, np.int32)
+    h_s[:] = s
+    h_e[:] = e
+    run_cap = L // 16 + 4096
+    o_sum, o_rs, o_rc = ctx.pinned_empty(n_win, np.int64), ctx.pinned_empty(run_cap, np.int32), ctx.pinned_empty(run_cap, np.uint8)
+
+    def step_e2e():
+        return ctx.depth_region(0, L, h_s, h_e, W, MINCOV, MAXMEAN, STEP, out=(o_sum, o_rs, o_rc))
+
+    # ---- warm-up (also sizes every grow-only buffer)
+    for _ in range(args.warmup):
+        step_resident()
+    ws, r0, rc = step_e2e()
+    n_runs = int(r0.size)
+    for _ in range(max(0, args.warmup - 1)):
+        step_e2e()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- timed: device-resident
+    barrier()
+    l0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_resident()
+    ms = ctx.timer_stop_ms()
+    launches = ctx.launch_count() - l0
+    barrier()
+
+    # ---- timed: end to end through the C ABI with host buffers
+    barrier()
+    ctx.timer_start()
+    te0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    ms_e2e = ctx.timer_stop_ms()
+    wall_e2e = (time.perf_counter() - te0) * 1e3
+    ms_e2e = max(ms_e2e, wall_e2e)          # the call is synchronous: host wall time bounds it from above
+    barrier()
+
+    # ---- per-kernel live timing for the roofline (same stream, CUDA events, L2-cold: 360 MB working set)
+    k_ms = {"memset": [], "scatter": [], "scan": []}
+    for _ in range(max(5, min(args.steps, 20))):
+        ctx.sync()
+        ctx.timer_start(); ctx.depth_begin(0, L); k_ms["memset"].append(ctx.timer_stop_ms())
+        ctx.timer_start(); ctx.depth_add_segments_device(d_s, d_e, nseg); k_ms["scatter"].append(ctx.timer_stop_ms())
+        ctx.timer_start(); ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP); k_ms["scan"].append(ctx.timer_stop_ms())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms_step = ms / args.steps
+        val = world * L / (ms_step * 1e-3) / 1e6
+        e2e_val = world * L / (ms_e2e / args.steps * 1e-3) / 1e6
+        kavg = {k: float(np.mean(v)) for k, v in k_ms.items()}
+        # algorithmic bytes: per launch
+        alg = {"scan": 4 * L + 12 * n_win + 5 * n_runs,          # read diff once; write int64 sum + int32 min; runs (4+1 B)
+               "scatter": 8 * nseg + 8 * nseg,                   # read (start,end); two int32 updates per segment
+               "memset": 4 * L}
+        dom = max(("scan", "scatter"), key=lambda k: kavg[k])
+        achieved = alg[dom] / (kavg[dom] * 1e-3) / 1e9
+        step_bytes = 8 * nseg + 8 * L + 12 * n_win + 5 * n_runs
+        out = {"metric": METRIC, "value": val, "unit": "Mbases/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+               "config": {"workload": "depth: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500, 1 sample per GPU",
+                          "window": W, "mincov": MINCOV, "run_break": STEP, "segments_per_gpu": nseg,
+                          "windows_per_gpu": n_win, "runs_per_gpu": n_runs, "contigs": world,
+                          "l2": "inputs larger than L2 (103 MB segments + 258 MB difference array per step)"},
+               "e2e": {"value": e2e_val, "unit": "Mbases/s", "h2d_bytes_per_step": 8 * nseg,
+                       "d2h_bytes_per_step": 8 * n_win + 5 * n_runs, "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "kernel": "depth_scan_kernel" if dom == "scan" else "depth_scatter_kernel",
+                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": alg[dom],
+                            "kernel_ms": kavg,
+                            "step": {"alg_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                                     "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}},
+               "clocks": clocks}
+        if not args.no_cpu_baseline:
+            from oracle import loader as orc       # cpu_baseline leg: the oracle port timed on this box's host cores
+            threads = os.cpu_count() or 1
+            chunks = orc.gen_chunks(L, W)
+            reps, tot = 0, 0.0
+            while reps < 3 and tot < 20.0:
+                dt, _ = cpu_depth_pass(orc, s, e, L, threads, chunks)
+                tot += dt; reps += 1
+            out["cpu_baseline"] = {"value": L / (tot / reps) / 1e6, "unit": "Mbases/s", "cores": threads, "kind": "port",
+                                   "sample": f"{reps} x whole chr20 contig (7 chunks of 10 Mb, chunk-parallel): per-base "
+                                             "counting + window/class walk + BED text; samtools text print/parse excluded"}
+        print(json.dumps(out), flush=True)
+
+    d_s.free(); d_e.free()
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,285 @@
+"""ctypes binding of libgoleft_b200.so (the C ABI in include/goleft_b200.h).
+
+This is what tests/ and bench.py call; it adds nothing but argument marshalling.  There is no
+CPU fallback: if the shared library is missing the import fails, and every call on a box
+without a CUDA device raises GlError (GL_ECUDA).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgoleft_b200.so")
+
+GL_OK, GL_EINVAL, GL_ECUDA, GL_ENOMEM, GL_ESTATE, GL_ERANGE, GL_ENCCL = 0, -1, -2, -3, -4, -5, -6
+CLASS_NAMES = ("NO_COVERAGE", "LOW_COVERAGE", "CALLABLE", "EXCESSIVE_COVERAGE")
+INDEXCOV_SLOTS = 70
+
+
+class GlError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"goleft_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make lib` (or __graft_entry__.build()); "
+            "goleft_b200 has no CPU fallback")
+    return C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+
+
+lib = _load()
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u8p = C.POINTER(C.c_uint8)
+_u64p = C.POINTER(C.c_uint64)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+
+def _proto(name, restype, *argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+_proto("gl_version", C.c_char_p)
+_proto("gl_device_count", C.c_int, C.POINTER(C.c_int))
+_proto("gl_ctx_create", C.c_int, C.c_int, C.POINTER(_vp))
+_proto("gl_ctx_destroy", C.c_int, _vp)
+_proto("gl_last_error", C.c_char_p, _vp)
+_proto("gl_sync", C.c_int, _vp)
+_proto("gl_launch_count", C.c_int, _vp, _i64p)
+_proto("gl_stream_handle", C.c_int, _vp, _u64p)
+_proto("gl_dev_alloc", C.c_int, _vp, C.c_int64, C.POINTER(_vp))
+_proto("gl_dev_free", C.c_int, _vp, _vp)
+_proto("gl_host_alloc_pinned", C.c_int, _vp, C.c_int64, C.POINTER(_vp))
+_proto("gl_host_free_pinned", C.c_int, _vp, _vp)
+_proto("gl_memcpy_h2d", C.c_int, _vp, _vp, _vp, C.c_int64)
+_proto("gl_memcpy_d2h", C.c_int, _vp, _vp, _vp, C.c_int64)
+_proto("gl_timer_start", C.c_int, _vp)
+_proto("gl_timer_stop_ms", C.c_int, _vp, C.POINTER(C.c_float))
+_proto("gl_flush_l2", C.c_int, _vp)
+
+_proto("gl_depth_begin", C.c_int, _vp, C.c_int64, C.c_int64)
+_proto("gl_depth_add_segments", C.c_int, _vp, _vp, _vp, C.c_int64)
+_proto("gl_depth_add_segments_device", C.c_int, _vp, _vp, _vp, C.c_int64)
+_proto("gl_depth_reduce", C.c_int, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64)
+_proto("gl_depth_result_sizes", C.c_int, _vp, _i64p, _i64p, _i32p)
+_proto("gl_depth_get_windows", C.c_int, _vp, _vp, _vp, C.c_int64)
+_proto("gl_depth_get_runs", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
+_proto("gl_depth_windows", C.c_int, _vp, C.c_int32, _vp, _vp, C.c_int64)
+_proto("gl_depth_classes", C.c_int, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_depth_perbase", C.c_int, _vp, _vp)
+_proto("gl_depth_region", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
+       C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_depth_format_chunk", C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int64, _vp, _vp,
+       C.c_int64, C.POINTER(_vp), _i64p, C.POINTER(_vp), _i64p)
+_proto("gl_free_text", None, _vp)
+
+
+def version() -> str:
+    return lib.gl_version().decode()
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = lib.gl_device_count(C.byref(n))
+    if rc != GL_OK:
+        return 0
+    return n.value
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _as(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def format_chunk(chrom: str, rs: int, re: int, W: int, win_sum: np.ndarray, run_start: np.ndarray,
+                 run_class: np.ndarray) -> Tuple[bytes, bytes]:
+    """Host-only: the reference's rows for one chunk (no GPU needed)."""
+    win_sum = _as(win_sum, np.int64)
+    run_start = _as(run_start, np.int32)
+    run_class = _as(run_class, np.uint8)
+    d, c = _vp(), _vp()
+    dl, cl = C.c_int64(0), C.c_int64(0)
+    rc = lib.gl_depth_format_chunk(chrom.encode(), rs, re, W, _ptr(win_sum), len(win_sum), _ptr(run_start),
+                                   _ptr(run_class), len(run_start), C.byref(d), C.byref(dl), C.byref(c), C.byref(cl))
+    if rc != GL_OK:
+        raise GlError(rc, "gl_depth_format_chunk: bad arguments")
+    try:
+        return C.string_at(d, dl.value), C.string_at(c, cl.value)
+    finally:
+        lib.gl_free_text(d)
+        lib.gl_free_text(c)
+
+
+class DevBuf:
+    """A device allocation owned by a Ctx."""
+
+    def __init__(self, ctx: "Ctx", nbytes: int):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = _vp()
+        ctx._ck(lib.gl_dev_alloc(ctx.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, a: np.ndarray) -> "DevBuf":
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        self.ctx._ck(lib.gl_memcpy_h2d(self.ctx.h, self.ptr, _ptr(a), a.nbytes))
+        return self
+
+    def download(self, dtype, count: int) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        self.ctx._ck(lib.gl_memcpy_d2h(self.ctx.h, _ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib.gl_dev_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+
+class Ctx:
+    """One GPU context (gl_ctx)."""
+
+    def __init__(self, device: int = 0):
+        h = _vp()
+        rc = lib.gl_ctx_create(device, C.byref(h))
+        if rc != GL_OK:
+            raise GlError(rc, lib.gl_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib.gl_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc: int):
+        if rc != GL_OK:
+            raise GlError(rc, lib.gl_last_error(self.h).decode())
+
+    # ---- plumbing
+    def sync(self):
+        self._ck(lib.gl_sync(self.h))
+
+    def launch_count(self) -> int:
+        n = C.c_int64(0)
+        self._ck(lib.gl_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def dev_array(self, a: np.ndarray) -> DevBuf:
+        a = np.ascontiguousarray(a)
+        return DevBuf(self, max(a.nbytes, 16)).upload(a)
+
+    def dev_empty(self, nbytes: int) -> DevBuf:
+        return DevBuf(self, nbytes)
+
+    def pinned_empty(self, count: int, dtype) -> np.ndarray:
+        dt = np.dtype(dtype)
+        p = _vp()
+        self._ck(lib.gl_host_alloc_pinned(self.h, max(count * dt.itemsize, 16), C.byref(p)))
+        buf = (C.c_char * (count * dt.itemsize)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dt, count=count)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p.value)
+        return arr
+
+    def timer_start(self):
+        self._ck(lib.gl_timer_start(self.h))
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float(0)
+        self._ck(lib.gl_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        self._ck(lib.gl_flush_l2(self.h))
+
+    # ---- depth
+    def depth_begin(self, rs: int, re: int):
+        self._ck(lib.gl_depth_begin(self.h, rs, re))
+
+    def depth_add_segments(self, start: np.ndarray, end: np.ndarray):
+        start, end = _as(start, np.int32), _as(end, np.int32)
+        assert start.shape == end.shape
+        self._ck(lib.gl_depth_add_segments(self.h, _ptr(start), _ptr(end), start.size))
+
+    def depth_add_segments_device(self, d_start: DevBuf, d_end: DevBuf, n: int, offset: int = 0):
+        self._ck(lib.gl_depth_add_segments_device(self.h, d_start.ptr + 4 * offset, d_end.ptr + 4 * offset, n))
+
+    def depth_reduce(self, W: int, mincov: int = 4, maxmean: int = 0, run_break: int = 0):
+        self._ck(lib.gl_depth_reduce(self.h, W, mincov, maxmean, run_break))
+
+    def depth_result_sizes(self) -> Tuple[int, int, int]:
+        nw, nr, md = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        self._ck(lib.gl_depth_result_sizes(self.h, C.byref(nw), C.byref(nr), C.byref(md)))
+        return nw.value, nr.value, md.value
+
+    def depth_get_windows(self, want_min: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        nw, _, _ = self.depth_result_sizes()
+        s = np.empty(nw, np.int64)
+        m = np.empty(nw, np.int32) if want_min else None
+        self._ck(lib.gl_depth_get_windows(self.h, _ptr(s), _ptr(m), nw))
+        return s, m
+
+    def depth_get_runs(self, want_end: bool = False):
+        _, nr, _ = self.depth_result_sizes()
+        rs_ = np.empty(nr, np.int32)
+        rc_ = np.empty(nr, np.uint8)
+        re_ = np.empty(nr, np.int32) if want_end else None
+        self._ck(lib.gl_depth_get_runs(self.h, _ptr(rs_), _ptr(re_), _ptr(rc_), nr))
+        return (rs_, re_, rc_) if want_end else (rs_, rc_)
+
+    def depth_windows(self, W: int, n_windows: int, want_min: bool = True):
+        s = np.empty(n_windows, np.int64)
+        m = np.empty(n_windows, np.int32) if want_min else None
+        self._ck(lib.gl_depth_windows(self.h, W, _ptr(s), _ptr(m), n_windows))
+        return s, m
+
+    def depth_classes(self, mincov: int, maxmean: int, cap: int):
+        rs_ = np.empty(cap, np.int32)
+        re_ = np.empty(cap, np.int32)
+        rc_ = np.empty(cap, np.uint8)
+        n = C.c_int64(0)
+        self._ck(lib.gl_depth_classes(self.h, mincov, maxmean, _ptr(rs_), _ptr(re_), _ptr(rc_), cap, C.byref(n)))
+        return rs_[: n.value], re_[: n.value], rc_[: n.value]
+
+    def depth_perbase(self, length: int) -> np.ndarray:
+        out = np.empty(length, np.int32)
+        self._ck(lib.gl_depth_perbase(self.h, _ptr(out)))
+        return out
+
+    def depth_region(self, rs: int, re: int, start: np.ndarray, end: np.ndarray, W: int, mincov: int = 4,
+                     maxmean: int = 0, run_break: int = 0, out=None):
+        """One call, host in / host out.  `out` = (sum, run_start, run_class) preallocated arrays."""
+        n_win = (re - 1) // W - rs // W + 1
+        if out is None:
+            out = (np.empty(n_win, np.int64), np.empty(max(1024, (re - rs) // 8), np.int32),
+                   np.empty(max(1024, (re - rs) // 8), np.uint8))
+        s, r0, rc_ = out
+        nw, nr = C.c_int64(0), C.c_int64(0)
+        self._ck(lib.gl_depth_region(self.h, rs, re, _ptr(start), _ptr(end), start.size, W, mincov, maxmean, run_break,
+                                     _ptr(s), s.size, C.byref(nw), _ptr(r0), _ptr(rc_), min(r0.size, rc_.size),
+                                     C.byref(nr)))
+        return s[: nw.value], r0[: nr.value], rc_[: nr.value]

@@ -1,0 +1,79 @@
+// gl_common.cuh — context object and error plumbing shared by every translation unit of
+// libgoleft_b200.so.  sm_100a only; there is no CPU fallback anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/goleft_b200.h"
+
+struct gl_buf {            // grow-only device buffer
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct gl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;       // compute stream
+    cudaStream_t copy_stream = nullptr;  // H2D staging stream
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;         // gl_timer_*
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};      // staging ring
+    cudaEvent_t ev_used[2] = {nullptr, nullptr};
+
+    // ---- depth state
+    bool depth_active = false, depth_reduced = false;
+    int64_t rs = 0, re = 0;
+    int32_t red_W = 0, red_mincov = 0, red_maxmean = 0; int64_t red_break = 0;
+    int64_t n_windows = 0, n_runs = 0; int32_t max_depth = 0;
+    gl_buf diff;          // int32[len+1 (+pad)]
+    gl_buf win_sum;       // u64[n_windows]
+    gl_buf win_min;       // i32[n_windows]
+    gl_buf run_start;     // i32[run_cap]
+    gl_buf run_class;     // u8[run_cap]
+    gl_buf scratch;       // header + 2 status words per tile
+    gl_buf seg[2];        // device staging for host segments: int32 start|end
+    void* pinned[2] = {nullptr, nullptr};
+    size_t pinned_bytes = 0;
+    gl_buf flush;         // L2 flush scratch
+    gl_buf misc;          // small outputs of other subsystems
+
+    void* nccl = nullptr; // ncclComm_t when gl_comm_init was called
+    int rank = 0, world = 1;
+};
+
+extern thread_local std::string g_gl_err;
+
+int gl_fail(gl_ctx* ctx, int code, const char* fmt, ...);
+int gl_buf_reserve(gl_ctx* ctx, gl_buf& b, size_t bytes);
+
+#define GL_CUDA(ctx, expr)                                                             \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess)                                                         \
+            return gl_fail((ctx), GL_ECUDA, "%s failed: %s (%s:%d)", #expr,            \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                \
+    } while (0)
+
+#define GL_CHECK(expr)                 \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != GL_OK) return _rc;  \
+    } while (0)
+
+#define GL_LAUNCHED(ctx, n)                                                            \
+    do {                                                                               \
+        (ctx)->launches += (n);                                                        \
+        GL_CUDA((ctx), cudaGetLastError());                                            \
+    } while (0)
+
+static inline int gl_use(gl_ctx* ctx) {
+    if (!ctx) return gl_fail(nullptr, GL_EINVAL, "null ctx");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return gl_fail(ctx, GL_ECUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    return GL_OK;
+}

@@ -1,0 +1,222 @@
+// gl_ctx.cu — context lifetime, device/pinned memory plumbing, timers.
+#include "gl_common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+thread_local std::string g_gl_err;
+
+int gl_fail(gl_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_gl_err = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+int gl_buf_reserve(gl_ctx* ctx, gl_buf& b, size_t bytes) {
+    if (bytes <= b.cap) return GL_OK;
+    if (b.p) {
+        GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GL_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = (bytes + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        cudaGetLastError();
+        return gl_fail(ctx, GL_ENOMEM, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return GL_OK;
+}
+
+static void buf_free(gl_buf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+extern "C" {
+
+const char* gl_version(void) { return "goleft_b200 0.1.0 sm_100a"; }
+
+int gl_device_count(int* n) {
+    if (!n) return gl_fail(nullptr, GL_EINVAL, "null out pointer");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        cudaGetLastError();
+        return gl_fail(nullptr, GL_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *n = c;
+    return GL_OK;
+}
+
+int gl_ctx_create(int device, gl_ctx** out) {
+    if (!out) return gl_fail(nullptr, GL_EINVAL, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    GL_CHECK(gl_device_count(&n));
+    if (n <= 0) return gl_fail(nullptr, GL_ECUDA, "no CUDA device visible: libgoleft_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return gl_fail(nullptr, GL_EINVAL, "device %d out of range [0,%d)", device, n);
+    gl_ctx* ctx = new gl_ctx();
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_used[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, device);
+        if (e == cudaSuccess) {
+            ctx->sm_count = prop.multiProcessorCount;
+            if (prop.major < 10) {
+                int rc = gl_fail(nullptr, GL_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                                 device, prop.major, prop.minor);
+                delete ctx;
+                return rc;
+            }
+        }
+    }
+    if (e != cudaSuccess) {
+        int rc = gl_fail(nullptr, GL_ECUDA, "gl_ctx_create: %s", cudaGetErrorString(e));
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return GL_OK;
+}
+
+int gl_comm_destroy(gl_ctx* ctx);
+
+int gl_ctx_destroy(gl_ctx* ctx) {
+    if (!ctx) return GL_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->nccl) gl_comm_destroy(ctx);
+    buf_free(ctx->diff); buf_free(ctx->win_sum); buf_free(ctx->win_min);
+    buf_free(ctx->run_start); buf_free(ctx->run_class); buf_free(ctx->scratch);
+    buf_free(ctx->seg[0]); buf_free(ctx->seg[1]); buf_free(ctx->flush); buf_free(ctx->misc);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+        if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);
+    }
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return GL_OK;
+}
+
+const char* gl_last_error(gl_ctx* ctx) { return ctx ? ctx->err.c_str() : g_gl_err.c_str(); }
+
+int gl_sync(gl_ctx* ctx) {
+    GL_CHECK(gl_use(ctx));
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+int gl_launch_count(gl_ctx* ctx, int64_t* n) {
+    if (!ctx || !n) return gl_fail(ctx, GL_EINVAL, "null argument");
+    *n = ctx->launches;
+    return GL_OK;
+}
+
+int gl_stream_handle(gl_ctx* ctx, uint64_t* stream) {
+    if (!ctx || !stream) return gl_fail(ctx, GL_EINVAL, "null argument");
+    *stream = (uint64_t)(uintptr_t)ctx->stream;
+    return GL_OK;
+}
+
+int gl_dev_alloc(gl_ctx* ctx, int64_t bytes, void** d_ptr) {
+    GL_CHECK(gl_use(ctx));
+    if (!d_ptr || bytes < 0) return gl_fail(ctx, GL_EINVAL, "gl_dev_alloc: bad argument");
+    *d_ptr = nullptr;
+    cudaError_t e = cudaMalloc(d_ptr, (size_t)(bytes > 0 ? bytes : 1));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return gl_fail(ctx, GL_ENOMEM, "cudaMalloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+    }
+    return GL_OK;
+}
+
+int gl_dev_free(gl_ctx* ctx, void* d_ptr) {
+    GL_CHECK(gl_use(ctx));
+    if (d_ptr) GL_CUDA(ctx, cudaFree(d_ptr));
+    return GL_OK;
+}
+
+int gl_host_alloc_pinned(gl_ctx* ctx, int64_t bytes, void** h_ptr) {
+    GL_CHECK(gl_use(ctx));
+    if (!h_ptr || bytes < 0) return gl_fail(ctx, GL_EINVAL, "gl_host_alloc_pinned: bad argument");
+    *h_ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(h_ptr, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return gl_fail(ctx, GL_ENOMEM, "cudaHostAlloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+    }
+    return GL_OK;
+}
+
+int gl_host_free_pinned(gl_ctx* ctx, void* h_ptr) {
+    GL_CHECK(gl_use(ctx));
+    if (h_ptr) GL_CUDA(ctx, cudaFreeHost(h_ptr));
+    return GL_OK;
+}
+
+int gl_memcpy_h2d(gl_ctx* ctx, void* d_dst, const void* h_src, int64_t bytes) {
+    GL_CHECK(gl_use(ctx));
+    if (bytes < 0) return gl_fail(ctx, GL_EINVAL, "negative size");
+    if (bytes == 0) return GL_OK;
+    GL_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+int gl_memcpy_d2h(gl_ctx* ctx, void* h_dst, const void* d_src, int64_t bytes) {
+    GL_CHECK(gl_use(ctx));
+    if (bytes < 0) return gl_fail(ctx, GL_EINVAL, "negative size");
+    if (bytes == 0) return GL_OK;
+    GL_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+int gl_timer_start(gl_ctx* ctx) {
+    GL_CHECK(gl_use(ctx));
+    GL_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return GL_OK;
+}
+
+int gl_timer_stop_ms(gl_ctx* ctx, float* ms) {
+    GL_CHECK(gl_use(ctx));
+    if (!ms) return gl_fail(ctx, GL_EINVAL, "null out pointer");
+    GL_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    GL_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    GL_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return GL_OK;
+}
+
+int gl_flush_l2(gl_ctx* ctx) {
+    GL_CHECK(gl_use(ctx));
+    const size_t bytes = size_t(256) << 20;   // 256 MiB > 126 MB L2
+    GL_CHECK(gl_buf_reserve(ctx, ctx->flush, bytes));
+    GL_CUDA(ctx, cudaMemsetAsync(ctx->flush.p, 0x5a, bytes, ctx->stream));
+    return GL_OK;
+}
+
+}  // extern "C"

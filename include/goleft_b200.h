@@ -1,0 +1,193 @@
+/*
+ * goleft_b200.h — C ABI of libgoleft_b200.so, the B200 (sm_100a) engine behind
+ * goleft's windowed-depth hot path (`depth`, `indexcov`, `covstats`, `depthwed`).
+ *
+ * The reference (brentp/goleft, pure Go) has no FFI for this path; each entry point
+ * below cites the reference code whose work it replaces (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the cgo binding a maintainer would add.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  No torch / C++ types.
+ *  - every call returns int: 0 = ok, <0 = error (GL_E*); text via gl_last_error().
+ *  - the caller owns every host buffer; the library owns device memory inside an
+ *    opaque gl_ctx (one ctx per GPU, one host thread at a time per ctx).
+ *  - coordinates are 0-based half-open, like the reference's internal ints.
+ *  - pointers named d_* are DEVICE pointers (from gl_dev_alloc); all others are
+ *    host pointers (pageable is fine, the library stages through pinned memory).
+ *  - calls are synchronous on the ctx's stream unless stated otherwise.
+ *  - there is NO CPU fallback: without a CUDA device every call fails with GL_ECUDA.
+ */
+#ifndef GOLEFT_B200_H
+#define GOLEFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GL_OK        0
+#define GL_EINVAL   -1   /* bad argument */
+#define GL_ECUDA    -2   /* CUDA runtime error (message has the cudaError string) */
+#define GL_ENOMEM   -3   /* device or pinned-host allocation failed */
+#define GL_ESTATE   -4   /* call out of order (e.g. add_segments before begin) */
+#define GL_ERANGE   -5   /* output capacity too small / value out of supported range */
+#define GL_ENCCL    -6   /* NCCL error */
+
+/* coverage classes of depth/depth.go:223-234 (getCovClass) */
+#define GL_NO_COVERAGE        0
+#define GL_LOW_COVERAGE       1
+#define GL_CALLABLE           2
+#define GL_EXCESSIVE_COVERAGE 3
+
+/* indexcov constants: indexcov/indexcov.go:153 (slots), indexcov/types.go:15 (TileWidth) */
+#define GL_INDEXCOV_SLOTS 70
+#define GL_TILE_WIDTH     16384
+
+typedef struct gl_ctx gl_ctx;
+
+/* ---------------------------------------------------------------- context */
+const char* gl_version(void);                       /* "goleft_b200 <semver> sm_100a" */
+int  gl_device_count(int* n);
+int  gl_ctx_create(int device, gl_ctx** out);
+int  gl_ctx_destroy(gl_ctx* ctx);
+const char* gl_last_error(gl_ctx* ctx);             /* ctx may be NULL: last global error */
+int  gl_sync(gl_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches claim) */
+int  gl_launch_count(gl_ctx* ctx, int64_t* n);
+/* raw cudaStream_t of the ctx, as an integer, so a caller can record events on it */
+int  gl_stream_handle(gl_ctx* ctx, uint64_t* stream);
+
+/* device memory owned by the ctx's device (plumbing for callers that keep inputs resident) */
+int  gl_dev_alloc(gl_ctx* ctx, int64_t bytes, void** d_ptr);
+int  gl_dev_free(gl_ctx* ctx, void* d_ptr);
+int  gl_host_alloc_pinned(gl_ctx* ctx, int64_t bytes, void** h_ptr);
+int  gl_host_free_pinned(gl_ctx* ctx, void* h_ptr);
+int  gl_memcpy_h2d(gl_ctx* ctx, void* d_dst, const void* h_src, int64_t bytes);
+int  gl_memcpy_d2h(gl_ctx* ctx, void* h_dst, const void* d_src, int64_t bytes);
+/* device-timed interval helpers (CUDA events on the ctx stream) */
+int  gl_timer_start(gl_ctx* ctx);
+int  gl_timer_stop_ms(gl_ctx* ctx, float* ms);      /* records, synchronizes, returns elapsed */
+/* write `bytes` of junk to a scratch buffer (> L2) so the next launch starts cold */
+int  gl_flush_l2(gl_ctx* ctx);
+
+/* ------------------------------------------------------------------ depth
+ * Replaces, per region [region_start, region_end) of one contig:
+ *   - the `samtools depth -Q q -d D -r chr:b-e` child of depth/depth.go:45,116,152
+ *     (per-base counting of the M/=/X blocks of records that pass the flag/MAPQ filter;
+ *      the filter itself is applied by the segment feeder, see gl_bam_* below),
+ *   - the per-line window accumulation of depth/depth.go:282-306,329-341 (Σ depth per
+ *     genome-aligned window, clipped to the region),
+ *   - the per-line class run-length encoding of depth/depth.go:307-327,343-350.
+ * Text formatting (%.4g of sum/len, BED rows, the Q2/Q3 chunk-edge quirks) stays on the
+ * host: gl_depth_format_chunk().
+ */
+
+/* Start a region: allocates (grow-only) and zeroes an int32 difference array of
+ * region_end-region_start+1 entries in HBM.  0 <= start < end, end-start < 2^30. */
+int  gl_depth_begin(gl_ctx* ctx, int64_t region_start, int64_t region_end);
+
+/* Scatter n segments [start[i], end[i]) (absolute contig coordinates, any order,
+ * end>start; clipped to the region by the kernel; segments outside are ignored).
+ * May be called repeatedly between begin and reduce.  Host-pointer variant copies
+ * through a pinned ring on the ctx stream; _device variant reads HBM-resident arrays. */
+int  gl_depth_add_segments(gl_ctx* ctx, const int32_t* start, const int32_t* end, int64_t n);
+int  gl_depth_add_segments_device(gl_ctx* ctx, const int32_t* d_start, const int32_t* d_end, int64_t n);
+
+/* One fused pass over the difference array: prefix scan -> per-base depth ->
+ *   (a) per-window int64 sums (+ int32 min) for genome-aligned windows of size W clipped
+ *       to the region: window k covers [max(rs,(rs/W+k)*W), min(re,(rs/W+k+1)*W)),
+ *   (b) class run starts: position x starts a run when x==rs, class(x)!=class(x-1), or
+ *       run_break>0 and x%run_break==0 (the reference never merges runs across its 10 Mb
+ *       chunks, depth/depth.go:132,150: pass run_break=step to reproduce that).
+ * mincov/maxmean as depth/depth.go:223-234.  Results stay on the device until fetched. */
+int  gl_depth_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break);
+
+/* Sizes of the results of the last gl_depth_reduce (synchronizes). */
+int  gl_depth_result_sizes(gl_ctx* ctx, int64_t* n_windows, int64_t* n_runs, int32_t* max_depth);
+
+/* Fetch results (host buffers).  min_out may be NULL.  run_end may be NULL
+ * (run i ends where run i+1 starts; the last ends at region_end). */
+int  gl_depth_get_windows(gl_ctx* ctx, int64_t* sum_out, int32_t* min_out, int64_t cap);
+int  gl_depth_get_runs(gl_ctx* ctx, int32_t* run_start, int32_t* run_end, uint8_t* run_class, int64_t cap);
+
+/* Convenience forms named in SURVEY.md §8(b): run the fused pass for one output only. */
+int  gl_depth_windows(gl_ctx* ctx, int32_t W, int64_t* sum_out, int32_t* min_out, int64_t n_windows);
+int  gl_depth_classes(gl_ctx* ctx, int32_t mincov, int32_t maxmean, int32_t* run_start, int32_t* run_end,
+                      uint8_t* run_class, int64_t cap, int64_t* n_runs);
+/* Per-base depth of the region (debug / parity): depth_out has region_end-region_start entries. */
+int  gl_depth_perbase(gl_ctx* ctx, int32_t* depth_out);
+
+/* One-call form used by the CLI and the end-to-end benchmark: host segments in, host
+ * results out, for one region; uploads are chunked and overlapped with the scatter. */
+int  gl_depth_region(gl_ctx* ctx, int64_t region_start, int64_t region_end,
+                     const int32_t* start, const int32_t* end, int64_t n,
+                     int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break,
+                     int64_t* sum_out, int64_t win_cap, int64_t* n_windows,
+                     int32_t* run_start, uint8_t* run_class, int64_t run_cap, int64_t* n_runs);
+
+/* Host-side text: reproduces the rows the reference callback writes for ONE chunk
+ * [rs,re) (depth/depth.go:293-305,326-358 incl. the chunk-edge quirks) from window sums
+ * and runs restricted to that chunk.  Appends to malloc'd buffers; free with gl_free_text. */
+int  gl_depth_format_chunk(const char* chrom, int64_t rs, int64_t re, int32_t W,
+                           const int64_t* win_sum /* windows of [rs,re) */, int64_t n_windows,
+                           const int32_t* run_start, const uint8_t* run_class, int64_t n_runs,
+                           char** depth_bed, int64_t* depth_len, char** callable_bed, int64_t* callable_len);
+void gl_free_text(char* p);
+
+/* ---------------------------------------------------------------- indexcov
+ * Replaces indexcov/types.go:45-82 (getSizes), indexcov/indexcov.go:83-125 (Index.init),
+ * :129-151 (NormalizedDepth), :170-177 (CountsAtDepth), :1050-1078 (counter.count),
+ * :549-597 (normalizeAcrossSamples) for a cohort laid out as S samples x T tiles. */
+
+/* I1: tile sizes from BAI linear-index virtual offsets.  voff: concatenated per-ref linear
+ * index entries of one sample; ref_ptr: CSR offsets (n_refs+1).  sizes gets, per ref with
+ * >=2 intervals, n_intv-1 deltas; size_ptr (n_refs+1) their CSR offsets.  Returns GL_ERANGE
+ * if any delta is negative (the reference panics, types.go:75-77). */
+int  gl_indexcov_sizes(gl_ctx* ctx, const uint64_t* voff, const int64_t* ref_ptr, int32_t n_refs,
+                       int64_t* sizes, int64_t* size_ptr);
+/* I2: the capped weighted median of Index.init: smallest v with sum_{s<=v} min(s,n98) > total/2. */
+int  gl_indexcov_scale(gl_ctx* ctx, const int64_t* sizes, int64_t n, int64_t* median_out);
+/* I3: depth[i] = min(float32(float64(sizes[i])/median), 50000). */
+int  gl_indexcov_normalize(gl_ctx* ctx, const int64_t* sizes, int64_t n, double median, float* depth_out);
+/* I4: 70-slot histogram (counts += ...). */
+int  gl_indexcov_counts(gl_ctx* ctx, const float* depth, int64_t n, int32_t counts[GL_INDEXCOV_SLOTS]);
+/* I5: counter.count over depth[0..n) with `longest` tiles expected; out4 += {out, low, hi, in}. */
+int  gl_indexcov_bins(gl_ctx* ctx, const float* depth, int64_t n, int64_t longest, int64_t out4[4]);
+/* I7: in-place cross-sample normalisation of one chromosome; depths is S rows of stride T,
+ * lens[i] valid entries in row i. */
+int  gl_indexcov_xnorm(gl_ctx* ctx, float* depths, const int32_t* lens, int32_t S, int32_t T);
+/* Cohort form (the fused kernel): S samples, per-sample tile sizes CSR (sample_ptr, S+1), all on
+ * the host; returns medians[S] and normalised depths in the same CSR layout. */
+int  gl_indexcov_cohort(gl_ctx* ctx, const int64_t* sizes, const int64_t* sample_ptr, int32_t S,
+                        double* medians, float* depth_out);
+int  gl_indexcov_cohort_device(gl_ctx* ctx, const int64_t* d_sizes, const int64_t* d_sample_ptr,
+                               const int64_t* h_sample_ptr, int32_t S, double* d_medians, float* d_depth_out);
+
+/* ---------------------------------------------------------------- covstats
+ * V2: histogram of int32 values in [lo,hi) -> hist[v-lo] (covstats/covstats.go:202-217 and the
+ * order statistics of :175-199, which the host derives from the histogram). */
+int  gl_bincount_i32(gl_ctx* ctx, const int32_t* v, int64_t n, int32_t lo, int32_t hi, uint64_t* hist);
+
+/* ---------------------------------------------------------------- depthwed
+ * W1: depthwed/depthwed.go:93-157.  means: S samples x R rows (row-major by sample) of the
+ * float64 4th BED column; starts/ends[R] of sample 0; chrom_id[R].  Computes
+ * int(0.5+mean) and aggregates consecutive rows of one chrom until end-start >= size.
+ * out: n_out rows x S ints (row-major by OUTPUT ROW, like the reference's TSV lines). */
+int  gl_depthwed_aggregate(gl_ctx* ctx, const double* means, int32_t S, int64_t R,
+                           const int32_t* starts, const int32_t* ends, const int32_t* chrom_id, int64_t size,
+                           int32_t* out_start, int32_t* out_end, int32_t* out_chrom, int64_t* out, int64_t out_cap,
+                           int64_t* n_out);
+
+/* ------------------------------------------------------------- multi-GPU
+ * One process per GPU.  The caller distributes a 128-byte NCCL unique id (rank 0 creates it). */
+int  gl_comm_unique_id(uint8_t id128[128]);
+int  gl_comm_init(gl_ctx* ctx, const uint8_t id128[128], int rank, int world);
+int  gl_comm_destroy(gl_ctx* ctx);
+/* all-gather equal-sized int32 blocks that live on the device: d_recv holds world*count ints */
+int  gl_allgather_i32_device(gl_ctx* ctx, const int32_t* d_send, int32_t* d_recv, int64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOLEFT_B200_H */

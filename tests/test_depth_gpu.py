@@ -1,0 +1,183 @@
+"""GPU parity: the CUDA depth path, called through the C ABI, against oracle/oracle_depth.c.
+Integer work -> bit-exact.  Every test here needs a B200 (`-m gpu`)."""
+import numpy as np
+import pytest
+
+from goleft_b200 import capi, synth
+from oracle import loader as orc
+
+pytestmark = pytest.mark.gpu
+
+FAI_WINDOWS = [100, 1000000000, 55, 60, 71, 13, 2001]          # depth/functional-test.sh:45-70
+BED_WINDOWS = [10, 1000000, 50, 55, 60, 71, 13, 2002]          # depth/functional-test.sh:73-97
+
+
+def rand_segments(rng, n, lo, hi, maxlen=300):
+    s = rng.integers(lo, hi, n).astype(np.int32)
+    e = (s + rng.integers(1, maxlen, n)).astype(np.int32)
+    return s, e
+
+
+def check_region(ctx, s, e, rs, re, W, mincov=4, maxmean=0, run_break=0, device=False):
+    exp_depth = orc.pileup_brute(s, e, rs, re) if s.size * 300 < 5e8 else orc.pileup_diff(s, e, rs, re)
+    ctx.depth_begin(rs, re)
+    bufs = []
+    if device:
+        ds, de = ctx.dev_array(s), ctx.dev_array(e)
+        bufs = [ds, de]
+        ctx.depth_add_segments_device(ds, de, s.size)
+    else:
+        ctx.depth_add_segments(s, e)
+    ctx.depth_reduce(W, mincov, maxmean, run_break)
+    nw, nr, md = ctx.depth_result_sizes()
+    ws, wm = ctx.depth_get_windows()
+    r0, r1, rc = ctx.depth_get_runs(want_end=True)
+    es, em = orc.window_sums(exp_depth, rs, re, W)
+    ea, ec = orc.class_runs(exp_depth, rs, re, mincov, maxmean, run_break)
+    assert nw == es.size
+    assert np.array_equal(ws, es)
+    assert np.array_equal(wm, em)
+    assert nr == ea.size
+    assert np.array_equal(r0, ea)
+    assert np.array_equal(rc, ec)
+    assert np.array_equal(r1, np.append(ea[1:], re).astype(np.int32))
+    assert md == int(exp_depth.max(initial=0))
+    got_depth = ctx.depth_perbase(re - rs)
+    assert np.array_equal(got_depth, exp_depth)
+    for b in bufs:
+        b.free()
+    return exp_depth, ws, r0, rc
+
+
+@pytest.mark.parametrize("W", FAI_WINDOWS)
+def test_small_region_all_fai_windows(ctx, W):
+    rng = np.random.default_rng(W)
+    s, e = rand_segments(rng, 20000, -100, 20100)
+    check_region(ctx, s, e, 0, 20001, W)
+
+
+@pytest.mark.parametrize("W", BED_WINDOWS)
+def test_bed_regions(ctx, W):
+    """the nine regions of depth/test/windows.bed, incl. 1- and 2-base regions"""
+    rng = np.random.default_rng(W + 1000)
+    s, e = rand_segments(rng, 5000, 0, 16000, maxlen=120)
+    for rs, re in [(14250, 15500), (1575, 15800), (100, 1000), (2000, 5000), (1, 3), (9, 13), (16, 17), (24, 29), (39, 43)]:
+        depth, ws, r0, rc = check_region(ctx, s, e, rs, re, W)
+        exp = orc.walk_chunk("chrM", rs, re, W, 4, 0, depth)
+        assert capi.format_chunk("chrM", rs, re, W, ws, r0, rc) == exp
+
+
+def test_empty_and_out_of_region_segments(ctx):
+    z = np.zeros(0, np.int32)
+    check_region(ctx, z, z, 0, 16571, 10)                      # t-empty.bam (functional-test.sh:102)
+    s = np.array([0, 50, 5000, 99, 100, 10], np.int32)
+    e = np.array([10, 101, 6000, 100, 101, 5000], np.int32)
+    check_region(ctx, s, e, 100, 1000, 10)                     # only clipped pieces count
+
+
+def test_tile_edges_and_run_break(ctx):
+    rng = np.random.default_rng(5)
+    for L in [4095, 4096, 4097, 8192, 12289]:
+        s, e = rand_segments(rng, 3000, -50, L + 50, maxlen=200)
+        check_region(ctx, s, e, 0, L, 500, run_break=4096)
+        check_region(ctx, s, e, 7, L + 7, 512, run_break=1000, device=True)
+
+
+def test_window_sizes_extreme(ctx):
+    rng = np.random.default_rng(6)
+    s, e = rand_segments(rng, 40000, 0, 100000, maxlen=151)
+    for W in [1, 2, 16, 17, 4096, 5000, 2 ** 30]:
+        check_region(ctx, s, e, 0, 100000, W, mincov=3, maxmean=25)
+
+
+def test_deep_pileup_int64_sums(ctx):
+    """500k identical reads: window sums exceed 2^32"""
+    s = np.full(500_000, 1000, np.int32)
+    e = np.full(500_000, 21000, np.int32)
+    depth, ws, _, _ = check_region(ctx, s, e, 0, 30000, 10000, maxmean=1000)
+    assert ws.max() > 2 ** 32
+
+
+def test_multiple_add_calls_and_unsorted(ctx):
+    rng = np.random.default_rng(8)
+    s, e = rand_segments(rng, 30001, 0, 50000)
+    p = rng.permutation(s.size)
+    s, e = s[p], e[p]
+    exp = orc.pileup_diff(s, e, 0, 50000)
+    ctx.depth_begin(0, 50000)
+    ctx.depth_add_segments(s[:7], e[:7])                       # unaligned tail path
+    ds, de = ctx.dev_array(s), ctx.dev_array(e)
+    ctx.depth_add_segments_device(ds, de, 10000 - 7, offset=7)  # misaligned device pointers -> scalar kernel
+    ctx.depth_add_segments(s[10000:], e[10000:])
+    assert np.array_equal(ctx.depth_perbase(50000), exp)
+    ws, wm = ctx.depth_windows(250, 200)
+    es, em = orc.window_sums(exp, 0, 50000, 250)
+    assert np.array_equal(ws, es) and np.array_equal(wm, em)
+    r0, r1, rc = ctx.depth_classes(4, 0, 50000)
+    ea, ec = orc.class_runs(exp, 0, 50000, 4, 0)
+    assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
+    ds.free(); de.free()
+
+
+def test_state_errors(ctx):
+    c2 = capi.Ctx(0)
+    with pytest.raises(capi.GlError) as ei:
+        c2.depth_add_segments(np.zeros(1, np.int32), np.ones(1, np.int32))
+    assert ei.value.code == capi.GL_ESTATE
+    with pytest.raises(capi.GlError) as ei:
+        c2.depth_begin(10, 10)
+    assert ei.value.code == capi.GL_EINVAL
+    c2.depth_begin(0, 100)
+    with pytest.raises(capi.GlError) as ei:
+        c2.depth_reduce(0)
+    assert ei.value.code == capi.GL_EINVAL
+    c2.close()
+
+
+def test_run_capacity_regrow(ctx):
+    """alternating covered/uncovered bases: one run per base, far above the initial capacity"""
+    L = 300_000
+    s = np.arange(0, L, 2, dtype=np.int32)
+    e = s + 1
+    check_region(ctx, s, e, 0, L, 1000, mincov=1)
+
+
+def test_fai_mode_whole_contig_text(ctx):
+    """25 Mb synthetic 30x contig, whole contig in one launch with run_break = step, then per-chunk text
+    == the oracle's per-chunk walker (what `goleft depth -w 500 --ordered` writes)."""
+    L, W = 25_000_000, 500
+    s, e = synth.segments(synth.reads(L, contig_index=3))
+    exp_depth = orc.pileup_diff(s, e, 0, L)
+    chunks = orc.gen_chunks(L, W)
+    step = chunks[0][1] - chunks[0][0]
+    ws, r0, rc = ctx.depth_region(0, L, s, e, W, 4, 0, run_break=step)
+    got_hd, got_ca, exp_hd, exp_ca = [], [], [], []
+    for cs, ce in chunks:
+        h, c = orc.walk_chunk("chr4", cs, ce, W, 4, 0, exp_depth[cs:ce])
+        exp_hd.append(h); exp_ca.append(c)
+        lo, hi = np.searchsorted(r0, cs), np.searchsorted(r0, ce)
+        h, c = capi.format_chunk("chr4", cs, ce, W, ws[cs // W:(ce - 1) // W + 1], r0[lo:hi], rc[lo:hi])
+        got_hd.append(h); got_ca.append(c)
+    assert b"".join(got_hd) == b"".join(exp_hd)
+    assert b"".join(got_ca) == b"".join(exp_ca)
+
+
+def test_full_size_chr20(ctx):
+    """BASELINE config 1 (chr20, 30x, W=500) at full size: bit-exact vs the oracle, plus the size-independent
+    properties: sum of window sums == total clipped segment length; runs tile the contig."""
+    L, W = synth.CHR20_LEN, 500
+    s, e = synth.chr20_like()
+    ds, de = ctx.dev_array(s), ctx.dev_array(e)
+    ctx.depth_begin(0, L)
+    ctx.depth_add_segments_device(ds, de, s.size)
+    ctx.depth_reduce(W, 4, 0, 10_000_000)
+    ws, wm = ctx.depth_get_windows()
+    r0, rc = ctx.depth_get_runs()
+    assert int(ws.sum()) == int((np.minimum(e, L).astype(np.int64) - np.maximum(s, 0)).clip(0).sum())
+    assert r0[0] == 0 and (np.diff(r0) > 0).all() and r0[-1] < L
+    exp = orc.pileup_diff(s, e, 0, L)
+    es, em = orc.window_sums(exp, 0, L, W)
+    ea, ec = orc.class_runs(exp, 0, L, 4, 0, 10_000_000)
+    assert np.array_equal(ws, es) and np.array_equal(wm, em)
+    assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
+    ds.free(); de.free()
