@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include "../../include/goleft_b200.h"
 
 struct gl_buf {            // grow-only device buffer
@@ -35,6 +36,8 @@ struct gl_ctx {
     gl_buf win_min;       // i32[n_windows]
     gl_buf run_start;     // i32[run_cap]
     gl_buf run_class;     // u8[run_cap]
+    gl_buf run_tmp_start; // claim-order staging of the runs
+    gl_buf run_tmp_class;
     gl_buf scratch;       // header + 2 status words per tile
     gl_buf seg[2];        // device staging for host segments: int32 start|end
     void* pinned[2] = {nullptr, nullptr};
