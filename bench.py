@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" = one pass of the depth hot path over one contig: zero the difference array, scatter the
-read intervals, one fused scan -> per-window sums/mins + callable-class runs.
+A "step" = one pass of the depth hot path over one contig: segments -> per-base depth (on chip only)
+-> per-window sums + callable-class runs (gl_depth_begin / add_segments / reduce).
 Workload at N=1 = BASELINE config[1]: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500.
 At N>1 every rank processes its own chr20-sized contig (contigs shard across GPUs with no
 data-path collective) -> weak scaling; value = N * bases / max-over-ranks device time.
@@ -191,6 +191,7 @@ def main():
     ctx = capi.Ctx(local)
     d_s, d_e = ctx.dev_array(s), ctx.dev_array(e)
     n_win = (L - 1) // W + 1
+    ctx.flush_l2()
 
     def barrier():
         ctx.sync()
@@ -224,34 +225,62 @@ def main():
     if rank == 0:
         sampler.start()
 
-    # ---- timed: device-resident
+    # ---- timed: device-resident.  The per-step working set (88 MB of segments) fits the 126 MB L2, so L2 is
+    #      flushed (256 MiB memset) before every timed step; each step is timed with CUDA events on the ctx
+    #      stream and the K step times are summed.
     barrier()
     l0 = ctx.launch_count()
-    ctx.timer_start()
+    ms = 0.0
     for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.timer_start()
         step_resident()
-    ms = ctx.timer_stop_ms()
+        ms += ctx.timer_stop_ms()
     launches = ctx.launch_count() - l0
     barrier()
 
-    # ---- timed: end to end through the C ABI with host buffers
+    # ---- timed: end to end through the C ABI with pinned host buffers (H2D + kernels + D2H inside)
     barrier()
-    ctx.timer_start()
-    te0 = time.perf_counter()
+    ms_e2e = 0.0
     for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.sync()
+        te0 = time.perf_counter()
+        ctx.timer_start()
         step_e2e()
-    ms_e2e = ctx.timer_stop_ms()
-    wall_e2e = (time.perf_counter() - te0) * 1e3
-    ms_e2e = max(ms_e2e, wall_e2e)          # the call is synchronous: host wall time bounds it from above
+        dev = ctx.timer_stop_ms()
+        ms_e2e += max(dev, (time.perf_counter() - te0) * 1e3)   # synchronous call: host wall time bounds it from above
     barrier()
 
-    # ---- per-kernel live timing for the roofline (same stream, CUDA events, L2-cold: 360 MB working set)
-    k_ms = {"memset": [], "scatter": [], "scan": []}
-    for _ in range(max(5, min(args.steps, 20))):
-        ctx.sync()
-        ctx.timer_start(); ctx.depth_begin(0, L); k_ms["memset"].append(ctx.timer_stop_ms())
-        ctx.timer_start(); ctx.depth_add_segments_device(d_s, d_e, nseg); k_ms["scatter"].append(ctx.timer_stop_ms())
-        ctx.timer_start(); ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP); k_ms["scan"].append(ctx.timer_stop_ms())
+    # ---- per-kernel live timing for the roofline: CUDA events on the launching stream around every
+    #      kernel of the same step (library-side, gl_profile_*), averaged over the repetitions
+    def kernel_times(reps):
+        ctx.profile_enable(True)
+        ctx.profile_read()
+        acc = {}
+        for _ in range(reps):
+            ctx.flush_l2()
+            step_resident()
+            for nm, t in ctx.profile_read():
+                acc.setdefault(nm, []).append(t)
+        ctx.profile_enable(False)
+        per_step = {k: float(np.sum(v)) / reps for k, v in acc.items()}
+        return per_step
+    reps = max(5, min(args.steps, 20))
+    k_ms = kernel_times(reps)
+    path = ctx.depth_last_path()
+    # the general (scatter) path on the same input, for the record
+    ctx.depth_set_path(2)
+    for _ in range(2):
+        step_resident()
+    ms_general = 0.0
+    for _ in range(reps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        step_resident()
+        ms_general += ctx.timer_stop_ms() / reps
+    k_ms_general = kernel_times(reps)
+    ctx.depth_set_path(0)
     clocks = sampler.stop() if rank == 0 else None
 
     if dist is not None:
@@ -265,30 +294,45 @@ def main():
         ms_step = ms / args.steps
         val = world * L / (ms_step * 1e-3) / 1e6
         e2e_val = world * L / (ms_e2e / args.steps * 1e-3) / 1e6
-        kavg = {k: float(np.mean(v)) for k, v in k_ms.items()}
-        # algorithmic bytes: per launch
-        alg = {"scan": 4 * L + 12 * n_win + 5 * n_runs,          # read diff once; write int64 sum + int32 min; runs (4+1 B)
-               "scatter": 8 * nseg + 8 * nseg,                   # read (start,end); two int32 updates per segment
-               "memset": 4 * L}
-        dom = max(("scan", "scatter"), key=lambda k: kavg[k])
-        achieved = alg[dom] / (kavg[dom] * 1e-3) / 1e9
-        step_bytes = 8 * nseg + 8 * L + 12 * n_win + 5 * n_runs
+        # ALGORITHMIC bytes per launch: what each kernel must move at minimum.
+        # fused path: K_fused reads every (start,end) once (8 B/segment) and writes sums (8 B/window) and
+        # runs (5 B/run); K_index reads the same 8 B/segment and writes the 4 B/cell offset table.
+        # general path: memset 4L, scatter 8 B/segment read + two int32 updates, scan 4L read.
+        ncells = L // 256 + 66
+        alg = {"depth_fused_kernel": 8 * nseg + 8 * n_win + 5 * n_runs,
+               "depth_index_kernel": 8 * nseg + 4 * ncells,
+               "depth_scan_kernel": 4 * L + 8 * n_win + 5 * n_runs,
+               "depth_scatter_kernel": 16 * nseg,
+               "memset_diff": 4 * L}
+        dom = max((k for k in k_ms if k in alg), key=lambda k: k_ms[k])
+        achieved = alg[dom] / (k_ms[dom] * 1e-3) / 1e9
+        step_bytes = sum(alg[k] for k in k_ms if k in alg)
+        survey_bytes = 8 * nseg + 8 * L + 12 * n_win + 9 * n_runs       # SURVEY.md §8(d) formula (HBM difference array)
+        gdom = max((k for k in k_ms_general if k in alg), key=lambda k: k_ms_general[k])
         out = {"metric": METRIC, "value": val, "unit": "Mbases/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                "config": {"workload": "depth: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500, 1 sample per GPU",
                           "window": W, "mincov": MINCOV, "run_break": STEP, "segments_per_gpu": nseg,
                           "windows_per_gpu": n_win, "runs_per_gpu": n_runs, "contigs": world,
-                          "l2": "inputs larger than L2 (103 MB segments + 258 MB difference array per step)"},
+                          "path": {1: "fused (sorted segments -> smem difference tiles)", 2: "general (HBM difference array)"}.get(path, str(path)),
+                          "l2": "L2 flushed (256 MiB memset) before every timed step; per-step CUDA-event times summed"},
                "e2e": {"value": e2e_val, "unit": "Mbases/s", "h2d_bytes_per_step": 8 * nseg,
                        "d2h_bytes_per_step": 8 * n_win + 5 * n_runs, "ms_per_step": ms_e2e / args.steps},
                "gpu_launches": int(launches),
-               "roofline": {"bound": "hbm", "kernel": "depth_scan_kernel" if dom == "scan" else "depth_scatter_kernel",
-                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": alg[dom],
-                            "kernel_ms": kavg,
+               "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "alg_bytes_per_launch": alg[dom], "kernel_ms": k_ms,
                             "step": {"alg_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
-                                     "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}},
+                                     "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+                            "survey_formula": {"alg_bytes": survey_bytes,
+                                               "achieved": survey_bytes / (ms_step * 1e-3) / 1e9,
+                                               "frac": survey_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                                               "note": "SURVEY.md §8(d) counts an 8 B/base HBM difference array the fused path never materialises"}},
+               "general_path": {"ms_per_step": ms_general, "value": world * L / (ms_general * 1e-3) / 1e6,
+                                "kernel_ms": k_ms_general, "dominant": gdom,
+                                "achieved": alg[gdom] / (k_ms_general[gdom] * 1e-3) / 1e9,
+                                "frac": alg[gdom] / (k_ms_general[gdom] * 1e-3) / 1e9 / peak},
                "clocks": clocks}
         if not args.no_cpu_baseline:
             from oracle import loader as orc       # cpu_baseline leg: the oracle port timed on this box's host cores

@@ -69,13 +69,17 @@ _proto("gl_memcpy_d2h", C.c_int, _vp, _vp, _vp, C.c_int64)
 _proto("gl_timer_start", C.c_int, _vp)
 _proto("gl_timer_stop_ms", C.c_int, _vp, C.POINTER(C.c_float))
 _proto("gl_flush_l2", C.c_int, _vp)
+_proto("gl_profile_enable", C.c_int, _vp, C.c_int)
+_proto("gl_profile_read", C.c_int, _vp, _vp, C.c_int64, _i64p)
 
 _proto("gl_depth_begin", C.c_int, _vp, C.c_int64, C.c_int64)
 _proto("gl_depth_add_segments", C.c_int, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_add_segments_device", C.c_int, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_reduce", C.c_int, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64)
 _proto("gl_depth_result_sizes", C.c_int, _vp, _i64p, _i64p, _i32p)
-_proto("gl_depth_get_windows", C.c_int, _vp, _vp, _vp, C.c_int64)
+_proto("gl_depth_get_windows", C.c_int, _vp, _vp, C.c_int64)
+_proto("gl_depth_last_path", C.c_int, _vp, _i32p)
+_proto("gl_depth_set_path", C.c_int, _vp, C.c_int32)
 _proto("gl_depth_get_runs", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_windows", C.c_int, _vp, C.c_int32, _vp, _vp, C.c_int64)
 _proto("gl_depth_classes", C.c_int, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int64, _i64p)
@@ -213,6 +217,20 @@ class Ctx:
         self._ck(lib.gl_timer_stop_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def profile_enable(self, on: bool):
+        self._ck(lib.gl_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """[(kernel name, ms), ...] for every kernel launched since the last read"""
+        buf = C.create_string_buffer(1 << 20)
+        need = C.c_int64(0)
+        self._ck(lib.gl_profile_read(self.h, C.cast(buf, _vp), len(buf), C.byref(need)))
+        out = []
+        for ln in buf.value.decode().splitlines():
+            nm, ms = ln.rsplit(" ", 1)
+            out.append((nm, float(ms)))
+        return out
+
     def flush_l2(self):
         self._ck(lib.gl_flush_l2(self.h))
 
@@ -236,12 +254,19 @@ class Ctx:
         self._ck(lib.gl_depth_result_sizes(self.h, C.byref(nw), C.byref(nr), C.byref(md)))
         return nw.value, nr.value, md.value
 
-    def depth_get_windows(self, want_min: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+    def depth_get_windows(self) -> np.ndarray:
         nw, _, _ = self.depth_result_sizes()
         s = np.empty(nw, np.int64)
-        m = np.empty(nw, np.int32) if want_min else None
-        self._ck(lib.gl_depth_get_windows(self.h, _ptr(s), _ptr(m), nw))
-        return s, m
+        self._ck(lib.gl_depth_get_windows(self.h, _ptr(s), nw))
+        return s
+
+    def depth_last_path(self) -> int:
+        p = C.c_int32(0)
+        self._ck(lib.gl_depth_last_path(self.h, C.byref(p)))
+        return p.value
+
+    def depth_set_path(self, path: int):
+        self._ck(lib.gl_depth_set_path(self.h, path))
 
     def depth_get_runs(self, want_end: bool = False):
         _, nr, _ = self.depth_result_sizes()

@@ -1,18 +1,30 @@
 // depth.cu — the `goleft depth` hot path on sm_100a.
 //
-//   segments (start,end) --K1 scatter (int32 red.global)--> difference array in HBM
-//                          + warp-aggregated net sums per 4096-base tile and per 64-tile super-tile
-//   difference array    --K2 ONE fused streaming pass----> per-base depth (registers/smem only)
-//                                        -> per-window int64 sum + int32 min   (depth/depth.go:293-306)
-//                                        -> coverage-class run starts          (depth/depth.go:307-327)
-//   run starts          --K3 gather----------------------> runs in position order
+// Work per region [rs,re) of one contig, replacing the `samtools depth` child + per-line Go callback
+// (depth/depth.go:45,238-364):   segments (start,end) -> per-base depth -> per-window sums (+min)
+//                                                                      -> coverage-class run starts
+// Per-base depth never exists in HBM: it is produced and consumed inside one 4096-base tile per CTA.
 //
-// Because the scatter already knows which tile every +1/-1 lands in, the depth carried into a tile
-// is the sum of <= tiles/64 super-tile sums plus <= 63 tile sums — ~300 coalesced L2 loads that
-// overlap the tile's own HBM loads — instead of a serial dependency through the 64M-element array.
-// K2 therefore has no inter-CTA dependency at all (no look-back chain, no ticket), reads the
-// difference array exactly once, and per-base depth never goes back to HBM.  Variable-length run
-// output is claimed per tile with one atomic and put into position order by K3 the same way.
+// Two ways to build a tile's difference array (+1 at a segment start, -1 at its end):
+//
+//  FUSED path (segments in BAM order: reads sorted by position, so segment starts are sorted up to the
+//  span of one read):                                              [K_index] -> [K_fused] -> [K_gather]
+//     K_index  one streaming pass over the segments: max segment length, and per 256-base cell the
+//              lowest / highest segment index that starts in it plus their count (run-aggregated atomics).
+//     K_fused  per tile: zero 16 KB of shared memory, shared-memory atomics for the ~800 segments in the
+//              index span of the cells that can reach the tile (look-back of max-length), tile core.
+//              A tile whose index span is far larger than its segment count (input not in BAM order)
+//              raises a flag and the host reruns the region on the general path.
+//              No difference array in HBM at all: shared-memory atomics run at ~2.7 T/s on B200,
+//              global reds at 0.17 T/s (tools/microbench/atomics_bench.cu).
+//  GENERAL path (any order; the fallback):
+//     memset -> [K_scatter] int32 red.global onto a difference array in HBM + warp-aggregated per-tile
+//     net sums -> [K_super] 64-tile sums -> [K_scan] per tile: coalesced load, carry from the two-level
+//     sums (no look-back chain, no inter-CTA dependency), tile core -> [K_gather].
+//
+// Tile core (both paths): 16 consecutive bases per thread (swizzled smem transpose), one thread-local
+// + one warp scan, REDUX-based window sums from registers, class runs detected on warp min/max with a
+// per-base slow path, runs claimed per tile with one atomic and put in position order by K_gather.
 // All arithmetic is integer; results are bit-exact against oracle/oracle_depth.c.
 #include "gl_common.cuh"
 #include <string.h>
@@ -21,14 +33,18 @@ namespace {
 
 constexpr int kScanThreads = 256;
 constexpr int kWarps = kScanThreads / 32;
-constexpr int kRounds = 4;                        // int4 per lane per round
-constexpr int kWarpElems = 32 * 4 * kRounds;      // 512 bases per warp
+constexpr int kWarpElems = 512;                   // bases per warp (16 per lane)
 constexpr int kTile = kWarps * kWarpElems;        // 4096 bases per tile
 constexpr int kTileShift = 12;
 static_assert((1 << kTileShift) == kTile, "tile shift");
+constexpr int kSuperShift = 6;                    // 64 tiles per super-tile
 constexpr int kHeaderWords = 8;                   // u64 words in front of the per-tile tables
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kSuperShift = 6;                    // 64 tiles per super-tile
+constexpr int kCellShift = 8;                     // fused path: segment-offset table granularity (256 bases)
+constexpr int kMaxLookback = 16384;               // fused path handles segments up to this long
+constexpr int kMaxBatches = 8;
+constexpr int kLenSlots = 1024;
+constexpr int kFlagWords = 16 + kLenSlots;
 
 __device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
     int4 r;
@@ -38,13 +54,18 @@ __device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
     return r;
 }
 
-// ------------------------------------------------------------------------------------------------
-// K1: scatter.  One thread = 4 segments (two 128-bit loads), 8 fire-and-forget int32 reductions.
+// 16-byte-chunk swizzle inside a tile (1024 chunks): conflict-free both for a warp touching 32
+// consecutive chunks and for a warp whose lane l touches chunks 4l..4l+3 (the blocked layout).
+__device__ __forceinline__ int swz_chunk(int c) { return c ^ ((c >> 2) & 7); }
+__device__ __forceinline__ int swz_elem(int e) { return (swz_chunk(e >> 2) << 2) | (e & 3); }
+
+// ================================================================================================
+// GENERAL path, K_scatter.  One thread = 4 segments (two 128-bit loads), 8 fire-and-forget reds.
 // Coordinates are clipped to the region exactly as `samtools depth -r` clips its output
 // (depth/depth.go:150-152): a read spanning a chunk edge counts on both sides.
-// The same events are summed per 4096-base tile; coordinate-sorted input puts a whole warp in one
-// or two tiles, so the warp reduces with REDUX and issues one red per distinct tile.
-// ------------------------------------------------------------------------------------------------
+// The same events are summed per 4096-base tile; a warp of sorted segments sits in one or two tiles,
+// so it reduces with REDUX and issues one red per distinct tile.
+// ================================================================================================
 __device__ __forceinline__ void warp_tile_add(int* __restrict__ tile_sum, int t, int c, int sign, int lane) {
     unsigned rem = __ballot_sync(kFull, c != 0);
 #pragma unroll 1
@@ -114,7 +135,7 @@ __global__ void __launch_bounds__(256) depth_scatter_kernel(const int* __restric
     warp_tile_add(tile_sum, tE, cE, -1, lane);
 }
 
-// K1b: super_sum[st] = sum of the 64 tile sums of super-tile st (one warp each).  Doing this in the
+// K_super: super_sum[st] = sum of the 64 tile sums of super-tile st (one warp each).  Doing this in the
 // scatter itself would put every warp's red on the same handful of addresses — measured 7x slower.
 __global__ void __launch_bounds__(256) depth_super_sum_kernel(const int* __restrict__ tile_sum, int* __restrict__ super_sum,
                                                              int tiles) {
@@ -128,25 +149,81 @@ __global__ void __launch_bounds__(256) depth_super_sum_kernel(const int* __restr
     if (lane == 0) super_sum[st] = v;
 }
 
-// ------------------------------------------------------------------------------------------------
-// K2: fused scan + window reduce + class runs.  One CTA per 4096-base tile, no inter-CTA dependency.
-// ------------------------------------------------------------------------------------------------
+// ================================================================================================
+// FUSED path, K_index.  For every 256-base cell from `origin`: cell_lo = lowest index of a segment that
+// starts in the cell, cell_hi = highest such index + 1, cell_cnt = how many.  Consecutive segments
+// mostly share a cell, so each run of equal cells inside a warp issues one atomicMin (its first lane),
+// one atomicMax (its last lane) and one atomicAdd (run length).  No ordering assumption is made here;
+// the fused kernel compares span and count.  Also: the longest segment, in 1024 slots (a single word
+// would serialise one atomic per warp on one address).
+// ================================================================================================
+__global__ void __launch_bounds__(256) depth_index_kernel(const int* __restrict__ start, const int* __restrict__ end,
+                                                         long long n, int origin, int re, int ncells,
+                                                         unsigned* __restrict__ cell_lo, unsigned* __restrict__ cell_hi,
+                                                         unsigned* __restrict__ cell_cnt, int* __restrict__ flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int len = 0, c = -1;
+    if (i < n) {
+        const int s = start[i];
+        len = end[i] - s;
+        // segments that start below a non-zero origin cannot reach the region (length <= look-back, else the
+        // fused path is rejected anyway); negative starts belong to cell 0 when origin is 0
+        if (len > 0 && s < re && (s >= origin || origin == 0)) c = min(max(s - origin, 0) >> kCellShift, ncells - 1);
+    }
+    const int wl = __reduce_max_sync(kFull, len);
+    if (lane == 0 && wl > 0) {
+        const int slot = (int)((i >> 5) & (kLenSlots - 1));
+        if (wl > flags[16 + slot]) atomicMax(flags + 16 + slot, wl);
+    }
+    const int pc = __shfl_up_sync(kFull, c, 1), nc = __shfl_down_sync(kFull, c, 1);
+    const bool first = lane == 0 || pc != c, last = lane == 31 || nc != c;
+    const unsigned firsts = __ballot_sync(kFull, first);
+    if (c >= 0) {
+        if (first) {
+            const unsigned after = firsts & ~((2u << lane) - 1u);          // run starts after this lane
+            const int run = (after ? __ffs(after) - 1 : 32) - lane;
+            atomicMin(cell_lo + c, (unsigned)i);
+            atomicAdd(cell_cnt + c, (unsigned)run);
+        }
+        if (last) atomicMax(cell_hi + c, (unsigned)i + 1u);
+    }
+}
+
+// ================================================================================================
+// Tile core
+// ================================================================================================
+struct BatchDesc {
+    const int* start;
+    const int* end;
+    const unsigned* cell_lo;   // [ncells] lowest segment index starting in the cell (0xffffffff: none)
+    const unsigned* cell_hi;   // [ncells] highest such index + 1
+    const unsigned* cell_cnt;  // [ncells] number of segments starting in the cell
+    int n;
+};
+
 struct ScanParams {
+    // general path inputs
     const int* diff;              // padded to a whole number of tiles, zero beyond len
     const int* tile_sum;          // [num_tiles+1] net (+starts -ends) inside each tile
     const int* super_sum;         // [num_tiles/64+1] the same per 64 tiles
+    // fused path inputs
+    const int* flags;             // K_index output: [16..16+1024) max segment length slots
+    int origin, ncells, n_batches;
+    BatchDesc batch[kMaxBatches];
+    // region and outputs
     int len;                      // bases in the region
-    int rs;                       // absolute start of the region
+    int rs, re;                   // absolute region
     int W;                        // window size
     long long w0;                 // rs / W  (index of the first window)
     int mincov, maxmean;
     unsigned run_break;           // 0 = never (host clamps values >= 2^32 to 0: no multiple in range)
     unsigned long long* win_sum;  // [n_windows], zero-initialised
-    int* win_min;                 // [n_windows], initialised to 0x7f7f7f7f (or null)
+    int* win_min;                 // [n_windows], initialised to 0x7f7f7f7f, or null (then not computed)
     int* tmp_start;               // [run_cap] run starts in claim order
     unsigned char* tmp_class;     // [run_cap]
     long long run_cap;
-    uint64_t* header;             // [0]=runs claimed (= n_runs) [2]=max_depth
+    uint64_t* header;             // [0]=runs claimed (= n_runs) [2]=max_depth [3]=fused path rejected
     uint64_t* tile_runs;          // [num_tiles] (claim offset << 32) | count
     unsigned* super_cnt;          // [num_tiles/64+1] run starts per super-tile
     int* depth_out;               // optional per-base output (debug/parity), else null
@@ -160,86 +237,76 @@ __device__ __forceinline__ int cov_class(int d, int mincov, int maxmean) {
                   : (d < mincov ? GL_LOW_COVERAGE : ((maxmean > 0 && d >= maxmean) ? GL_EXCESSIVE_COVERAGE : GL_CALLABLE));
 }
 
-// class(d) is monotone in d, so a set of depths is single-class iff class(min) == class(max).
-__global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanParams p) {
-    __shared__ __align__(16) int s_depth[kTile];
+// S[i] for a run-time i in [0,16) out of 16 registers: 4 bit tests + 15 selects
+__device__ __forceinline__ int select16(const int (&S)[16], int i) {
+    const bool b0 = i & 1, b1 = i & 2, b2 = i & 4, b3 = i & 8;
+    const int a0 = b0 ? S[1] : S[0], a1 = b0 ? S[3] : S[2], a2 = b0 ? S[5] : S[4], a3 = b0 ? S[7] : S[6];
+    const int a4 = b0 ? S[9] : S[8], a5 = b0 ? S[11] : S[10], a6 = b0 ? S[13] : S[12], a7 = b0 ? S[15] : S[14];
+    const int c0 = b1 ? a1 : a0, c1 = b1 ? a3 : a2, c2 = b1 ? a5 : a4, c3 = b1 ? a7 : a6;
+    const int e0 = b2 ? c1 : c0, e1 = b2 ? c3 : c2;
+    return b3 ? e1 : e0;
+}
+
+// s_tile: the tile's 4096 differences in swizzled layout.  s_carry[8]: partial sums of everything
+// before the tile (all zero on the fused path).  Requires all 256 threads; contains __syncthreads.
+__device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__ s_tile, const int* s_carry, int tile) {
     __shared__ int s_warp_tot[kWarps];
     __shared__ int s_warp_cnt[kWarps];
     __shared__ int s_warp_max[kWarps];
-    __shared__ int s_warp_carry[kWarps];
     __shared__ long long s_run_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
     const int tile_base = tile * kTile;                       // relative position of the tile
     const int warp_base = tile_base + warp * kWarpElems;
+    const int idx0 = tile_base + tid * 16;                    // relative position of this thread's first base
 
-    // ---- load 16 diffs per thread, warp-coalesced 512 B per instruction
-    int4 v[kRounds];
+    // ---- 16 consecutive differences per thread; thread-local inclusive scan; one warp scan
+    int x[16];
 #pragma unroll
-    for (int r = 0; r < kRounds; r++)
-        v[r] = ld_stream_int4(reinterpret_cast<const int4*>(p.diff + warp_base + r * 128) + lane);
-
-    // ---- depth carried into the tile = sum of everything before it (two-level, overlaps the loads above)
-    {
-        const int st = tile >> kSuperShift;
-        int part = 0;
-        for (int k = tid; k < st; k += kScanThreads) part += p.super_sum[k];
-        const int k2 = (st << kSuperShift) + tid;
-        if (tid < (1 << kSuperShift) && k2 < tile) part += p.tile_sum[k2];
-        part = __reduce_add_sync(kFull, part);
-        if (lane == 0) s_warp_carry[warp] = part;
+    for (int j = 0; j < 4; j++) {
+        const int4 q = reinterpret_cast<const int4*>(s_tile)[swz_chunk(tid * 4 + j)];
+        x[4 * j] = q.x; x[4 * j + 1] = q.y; x[4 * j + 2] = q.z; x[4 * j + 3] = q.w;
     }
-
-    // ---- warp-local exclusive prefix of each quad
-    int pre[kRounds];
-    int running = 0;
 #pragma unroll
-    for (int r = 0; r < kRounds; r++) {
-        int q = v[r].x + v[r].y + v[r].z + v[r].w;
-        int inc = q;
+    for (int k = 1; k < 16; k++) x[k] += x[k - 1];
+    int inc = x[15];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(kFull, inc, o);
-            if (lane >= o) inc += t;
-        }
-        pre[r] = running + inc - q;
-        running += __shfl_sync(kFull, inc, 31);
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
     }
-    if (lane == 0) s_warp_tot[warp] = running;
+    const int lane_excl = inc - x[15];
+    if (lane == 31) s_warp_tot[warp] = inc;
     __syncthreads();
 
     int wbase = 0;                                            // depth at the base before this warp's first
 #pragma unroll
-    for (int w = 0; w < kWarps; w++) wbase += s_warp_carry[w] + ((w < warp) ? s_warp_tot[w] : 0);
+    for (int w = 0; w < kWarps; w++) wbase += s_carry[w] + ((w < warp) ? s_warp_tot[w] : 0);
+    const int tbase = wbase + lane_excl;                      // depth at the base before this thread's first
 
-    // ---- per-base depth (registers + this warp's smem slice), per-round min / max / sum
-    int* sw = s_depth + warp * kWarpElems;
-    int4 d[kRounds];
+    // ---- per-base depth in registers
+    int d[16];
     int mn = 0x7fffffff, mx = 0;
 #pragma unroll
-    for (int r = 0; r < kRounds; r++) {
-        const int prev = wbase + pre[r];
-        d[r].x = prev + v[r].x;
-        d[r].y = d[r].x + v[r].y;
-        d[r].z = d[r].y + v[r].z;
-        d[r].w = d[r].z + v[r].w;
-        reinterpret_cast<int4*>(sw + r * 128)[lane] = d[r];
-        mn = min(mn, min(min(d[r].x, d[r].y), min(d[r].z, d[r].w)));
-        mx = max(mx, max(max(d[r].x, d[r].y), max(d[r].z, d[r].w)));
-        if (p.depth_out) {
-            const int idx = warp_base + r * 128 + lane * 4;
-            if (idx + 3 < p.len) reinterpret_cast<int4*>(p.depth_out + idx)[0] = d[r];
+    for (int k = 0; k < 16; k++) {
+        d[k] = tbase + x[k];
+        mn = min(mn, d[k]);
+        mx = max(mx, d[k]);
+    }
+    if (p.depth_out) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int idx = idx0 + 4 * j;
+            if (idx + 3 < p.len) reinterpret_cast<int4*>(p.depth_out + idx)[0] = make_int4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
             else {
-                if (idx < p.len) p.depth_out[idx] = d[r].x;
-                if (idx + 1 < p.len) p.depth_out[idx + 1] = d[r].y;
-                if (idx + 2 < p.len) p.depth_out[idx + 2] = d[r].z;
+                if (idx < p.len) p.depth_out[idx] = d[4 * j];
+                if (idx + 1 < p.len) p.depth_out[idx + 1] = d[4 * j + 1];
+                if (idx + 2 < p.len) p.depth_out[idx + 2] = d[4 * j + 2];
             }
         }
     }
     const bool full_warp = warp_base + kWarpElems <= p.len;   // false only at the region's ragged end
     const int wmin = __reduce_min_sync(kFull, mn), wmax = __reduce_max_sync(kFull, mx);
-    __syncwarp();
 
     // does a forced run break (multiple of run_break) fall inside this tile?
     bool tile_has_break = false;
@@ -249,120 +316,99 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanP
         tile_has_break = (rem ? p.run_break - rem : 0u) < (unsigned)kTile;
     }
 
-    // ---- class-change masks.  Fast path: the warp's 512 bases and the base before them are one class.
-    unsigned masks = 0;
-    int maxd = 0;
+    // class(d) is monotone in d: the warp's 512 bases plus the base before them are one class iff
+    // class(min) == class(max) — then no run starts here and all per-base class work is skipped.
     bool slow_runs = false;
-    if (full_warp) maxd = wmax;
-    if (p.do_runs) {
+    if (p.do_runs)
         slow_runs = !full_warp || tile_has_break || warp_base == 0 ||
                     cov_class(min(wmin, wbase), p.mincov, p.maxmean) != cov_class(max(wmax, wbase), p.mincov, p.maxmean);
-    }
-    if (slow_runs || !full_warp) {
+    const bool fast_win = p.do_windows && full_warp && p.W >= 16 && p.win_min == nullptr && wmax < (1 << 22);
+    const bool slow_win = p.do_windows && !fast_win;
+
+    // The slow paths index depth by position: put it back into this warp's smem slice (linear layout;
+    // a warp's swizzled chunks stay inside its own slice, and every lane has finished reading).
+    int* sw = s_tile + warp * kWarpElems;
+    if (slow_runs || slow_win) {
+        __syncwarp();
 #pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            const int idx = warp_base + r * 128 + lane * 4;   // relative position of element 0
-            if (idx < p.len) {
-                const int nv = min(4, p.len - idx);
-                maxd = max(maxd, d[r].x);
-                if (nv > 1) maxd = max(maxd, d[r].y);
-                if (nv > 2) maxd = max(maxd, d[r].z);
-                if (nv > 3) maxd = max(maxd, d[r].w);
-                if (slow_runs) {
-                    const int cp = cov_class(wbase + pre[r], p.mincov, p.maxmean);
-                    const int c0 = cov_class(d[r].x, p.mincov, p.maxmean);
-                    const int c1 = cov_class(d[r].y, p.mincov, p.maxmean);
-                    const int c2 = cov_class(d[r].z, p.mincov, p.maxmean);
-                    const int c3 = cov_class(d[r].w, p.mincov, p.maxmean);
-                    unsigned m = (c0 != cp ? 1u : 0u) | (c1 != c0 ? 2u : 0u) | (c2 != c1 ? 4u : 0u) | (c3 != c2 ? 8u : 0u);
-                    if (idx == 0) m |= 1u;                    // the region's first base always starts a run
-                    if (tile_has_break) {
-                        const unsigned a = (unsigned)p.rs + (unsigned)idx;
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if ((a + j) % p.run_break == 0) m |= (1u << j);
-                    }
-                    m &= (1u << nv) - 1u;
-                    masks |= m << (4 * r);
-                }
-            }
-        }
-        if (!full_warp) maxd = __reduce_max_sync(kFull, maxd);
+        for (int j = 0; j < 4; j++)
+            reinterpret_cast<int4*>(sw + lane * 16)[j] = make_int4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+        __syncwarp();
     }
 
-    // ---- rank of each run start inside the warp, in position order (round, lane, j)
-    int lane_rank[kRounds];
-    int round_tot[kRounds];
-    int warp_cnt = 0;
+    // ---- run starts (slow path): one mask bit per base, rank inside the warp in position order
+    unsigned mask = 0;
+    int lane_rank = 0, warp_cnt = 0;
+    int maxd = full_warp ? wmax : 0;
+    if (slow_runs || !full_warp) {
+        const int nv = max(0, min(16, p.len - idx0));
+        int cp = cov_class(tbase, p.mincov, p.maxmean);
 #pragma unroll
-    for (int r = 0; r < kRounds; r++) { lane_rank[r] = 0; round_tot[r] = 0; }
-    if (slow_runs) {
-        const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            unsigned m = (masks >> (4 * r)) & 15u;
-            if (__any_sync(kFull, m != 0)) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    unsigned b = __ballot_sync(kFull, (m >> j) & 1u);
-                    lane_rank[r] += __popc(b & lt);
-                    round_tot[r] += __popc(b);
+        for (int k = 0; k < 16; k++) {
+            if (k < nv) {
+                if (!full_warp) maxd = max(maxd, d[k]);
+                if (slow_runs) {
+                    const int c = cov_class(d[k], p.mincov, p.maxmean);
+                    if (c != cp) mask |= 1u << k;
+                    cp = c;
                 }
             }
-            warp_cnt += round_tot[r];
         }
+        if (slow_runs) {
+            if (idx0 == 0) mask |= 1u;                        // the region's first base always starts a run
+            if (tile_has_break) {
+                const unsigned a = (unsigned)p.rs + (unsigned)idx0;
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    if ((a + k) % p.run_break == 0) mask |= 1u << k;
+            }
+            mask &= (nv >= 16) ? 0xffffu : ((1u << nv) - 1u);
+            const int c = __popc(mask);
+            int ci = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, ci, o);
+                if (lane >= o) ci += t;
+            }
+            lane_rank = ci - c;
+            warp_cnt = __shfl_sync(kFull, ci, 31);
+        }
+        if (!full_warp) maxd = __reduce_max_sync(kFull, maxd);
     }
     if (lane == 0) { s_warp_cnt[warp] = warp_cnt; s_warp_max[warp] = maxd; }
 
     // ---- window partial sums of this warp's 512 bases
-    if (p.do_windows) {
-        const unsigned a0 = (unsigned)p.rs + (unsigned)warp_base;                        // absolute, < 2^32
+    if (fast_win) {
+        // From registers.  S[k] = sum of this thread's first k+1 depths (< 2^26).  For every window edge
+        // inside the warp, each lane contributes the part of its 16 bases left of the edge that was not
+        // counted yet; one REDUX adds the lanes (< 2^31), lane 0 issues one 64-bit red per window.
+        int S[16];
+        S[0] = d[0];
+#pragma unroll
+        for (int k = 1; k < 16; k++) S[k] = S[k - 1] + d[k];
+        const unsigned a0 = (unsigned)p.rs + (unsigned)warp_base;     // absolute, < 2^32
+        const unsigned uW = (unsigned)p.W;
+        unsigned iw = a0 / uW;
+        long long edge = (long long)(iw + 1) * uW - a0;               // offset of the next window edge in the warp
+        int counted = 0;
+#pragma unroll 1
+        while (true) {
+            const int c = (int)min(16ll, max(0ll, edge - lane * 16)); // my bases left of the edge
+            int cur = select16(S, (c - 1) & 15);
+            cur = c == 0 ? 0 : cur;
+            const unsigned tot = (unsigned)__reduce_add_sync(kFull, cur - counted);
+            counted = cur;
+            if (lane == 0) atomicAdd(p.win_sum + ((long long)iw - p.w0), (unsigned long long)tot);
+            if (edge >= kWarpElems) break;
+            iw++;
+            edge += uW;
+        }
+    } else if (slow_win) {
+        // General path from this warp's smem slice: any W, min, ragged end, depth up to 2^31.
+        const unsigned a0 = (unsigned)p.rs + (unsigned)warp_base;
         const unsigned a1 = (unsigned)p.rs + (unsigned)min(warp_base + kWarpElems, p.len);
         const unsigned uW = (unsigned)p.W;
-        if (full_warp && p.W >= 128 && wmax < (1 << 24)) {
-            // Fast path from registers: a 128-base round holds at most one window edge; whole rounds are
-            // summed with one REDUX (sums < 2^31 because depth < 2^24), the edge round is split by lane.
-            unsigned iw = a0 / uW;
-            long long next_b = (long long)(iw + 1) * uW - a0;         // offset of the next window edge in the warp
-            unsigned long long acc = 0;
-            int acc_min = 0x7fffffff;
-#pragma unroll
-            for (int r = 0; r < kRounds; r++) {
-                const int q = d[r].x + d[r].y + d[r].z + d[r].w;
-                const int qm = min(min(d[r].x, d[r].y), min(d[r].z, d[r].w));
-                if (next_b >= (r + 1) * 128) {
-                    acc += (unsigned)__reduce_add_sync(kFull, q);
-                    if (p.win_min) acc_min = min(acc_min, __reduce_min_sync(kFull, qm));
-                } else {
-                    const int b = (int)next_b - r * 128 - lane * 4;   // elements j < b of this lane lie left of the edge
-                    const int l = (b > 0 ? d[r].x : 0) + (b > 1 ? d[r].y : 0) + (b > 2 ? d[r].z : 0) + (b > 3 ? d[r].w : 0);
-                    const unsigned left = (unsigned)__reduce_add_sync(kFull, l);
-                    const unsigned right = (unsigned)__reduce_add_sync(kFull, q - l);
-                    int lmin = 0x7fffffff, rmin = 0x7fffffff;
-                    if (p.win_min) {
-                        lmin = min(min(b > 0 ? d[r].x : lmin, b > 1 ? d[r].y : lmin), min(b > 2 ? d[r].z : lmin, b > 3 ? d[r].w : lmin));
-                        rmin = min(min(b > 0 ? rmin : d[r].x, b > 1 ? rmin : d[r].y), min(b > 2 ? rmin : d[r].z, b > 3 ? rmin : d[r].w));
-                        lmin = __reduce_min_sync(kFull, lmin);
-                        rmin = __reduce_min_sync(kFull, rmin);
-                    }
-                    acc += left;
-                    acc_min = min(acc_min, lmin);
-                    if (lane == 0) {
-                        atomicAdd(p.win_sum + ((long long)iw - p.w0), acc);
-                        if (p.win_min) atomicMin(p.win_min + ((long long)iw - p.w0), acc_min);
-                    }
-                    iw++;
-                    next_b += uW;
-                    acc = right;
-                    acc_min = rmin;
-                }
-            }
-            if (lane == 0) {
-                atomicAdd(p.win_sum + ((long long)iw - p.w0), acc);
-                if (p.win_min) atomicMin(p.win_min + ((long long)iw - p.w0), acc_min);
-            }
-        } else if (a0 < a1) {
-            // General path from this warp's smem slice: any W, ragged end, depth up to 2^31.
+        if (a0 < a1) {
             const unsigned iw0 = a0 / uW, iw1 = (a1 - 1) / uW;
             if (p.W > 16) {
                 for (unsigned iw = iw0; iw <= iw1; iw++) {
@@ -370,8 +416,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanP
                     const int s = (int)(max((long long)a0, ws) - a0), e = (int)(min((long long)a1, we) - a0);
                     unsigned long long sum = 0;
                     int m = 0x7fffffff;
-                    for (int x = s + lane; x < e; x += 32) {
-                        int dd = sw[x];
+                    for (int xx = s + lane; xx < e; xx += 32) {
+                        const int dd = sw[xx];
                         sum += (unsigned long long)(unsigned)dd;
                         m = min(m, dd);
                     }
@@ -389,8 +435,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanP
                     const int s = (int)(max((long long)a0, ws) - a0), e = (int)(min((long long)a1, we) - a0);
                     unsigned long long sum = 0;
                     int m = 0x7fffffff;
-                    for (int x = s; x < e; x++) {
-                        int dd = sw[x];
+                    for (int xx = s; xx < e; xx++) {
+                        const int dd = sw[xx];
                         sum += (unsigned long long)(unsigned)dd;
                         m = min(m, dd);
                     }
@@ -422,38 +468,126 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanP
     if (!p.do_runs || tile_cnt == 0) return;
     __syncthreads();
 
-    if (masks) {
-        long long base = s_run_base;
+    if (mask) {
+        long long rank = s_run_base + lane_rank;
 #pragma unroll
-        for (int w = 0; w < kWarps; w++) base += (w < warp) ? s_warp_cnt[w] : 0;
-#pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            unsigned m = (masks >> (4 * r)) & 15u;
-            long long rank = base + lane_rank[r];
-            const int off = r * 128 + lane * 4;
-            while (m) {
-                int j = __ffs(m) - 1;
-                m &= m - 1;
-                if (rank < p.run_cap) {
-                    p.tmp_start[rank] = p.rs + warp_base + off + j;
-                    p.tmp_class[rank] = (unsigned char)cov_class(sw[off + j], p.mincov, p.maxmean);
-                }
-                rank++;
+        for (int w = 0; w < kWarps; w++) rank += (w < warp) ? s_warp_cnt[w] : 0;
+        unsigned m = mask;
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            if (rank < p.run_cap) {
+                p.tmp_start[rank] = p.rs + idx0 + k;
+                p.tmp_class[rank] = (unsigned char)cov_class(sw[lane * 16 + k], p.mincov, p.maxmean);
             }
-            base += round_tot[r];
+            rank++;
         }
     }
 }
 
-// K3: one warp per tile moves its runs from claim order to position order.  The ordered offset of a
-// tile is the number of runs that start before it: super-tile counts + the tile counts of its own
+// GENERAL path, K_scan: coalesced load of the tile's differences -> swizzled smem -> tile core.
+__global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanParams p) {
+    __shared__ __align__(16) int s_tile[kTile];
+    __shared__ int s_carry[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int4* src = reinterpret_cast<const int4*>(p.diff + (size_t)tile * kTile);
+    int4 v[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) v[r] = ld_stream_int4(src + warp * 128 + r * 32 + lane);   // 512 B per warp-instruction
+    {   // depth carried into the tile = sum of everything before it (two-level, overlaps the loads above)
+        const int st = tile >> kSuperShift;
+        int part = 0;
+        for (int k = tid; k < st; k += kScanThreads) part += p.super_sum[k];
+        const int k2 = (st << kSuperShift) + tid;
+        if (tid < (1 << kSuperShift) && k2 < tile) part += p.tile_sum[k2];
+        part = __reduce_add_sync(kFull, part);
+        if (lane == 0) s_carry[warp] = part;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) reinterpret_cast<int4*>(s_tile)[swz_chunk(warp * 128 + r * 32 + lane)] = v[r];
+    __syncwarp();                                                       // a warp only re-reads its own 128 chunks
+    tile_core(p, s_tile, s_carry, tile);
+}
+
+// FUSED path, K_fused: build the tile's difference array in shared memory straight from the segments.
+__global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const ScanParams p) {
+    __shared__ __align__(16) int s_tile[kTile];
+    __shared__ int s_carry[kWarps];
+    __shared__ int s_len[kWarps];
+    __shared__ unsigned s_lo[kMaxBatches][kWarps], s_hi[kMaxBatches][kWarps], s_cnt[kMaxBatches][kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+
+    int maxlen = 0;
+#pragma unroll
+    for (int k = 0; k < kLenSlots / kScanThreads; k++) maxlen = max(maxlen, p.flags[16 + tid + k * kScanThreads]);
+    maxlen = __reduce_max_sync(kFull, maxlen);
+    if (lane == 0) s_len[warp] = maxlen;
+#pragma unroll
+    for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    maxlen = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) maxlen = max(maxlen, s_len[w]);
+    if (maxlen > kMaxLookback) {                                        // the general path handles long segments
+        if (tile == 0 && tid == 0) p.header[3] = 1;
+        return;
+    }
+
+    // cells whose segments can cover base t0-1 or touch the tile: starts in [t0 - maxlen, t1)
+    const int t0 = p.rs + tile * kTile;                                 // absolute tile span [t0,t1)
+    const int t1 = min(t0 + kTile, p.re);
+    const int lo_cell = (max(t0 - maxlen, p.origin) - p.origin) >> kCellShift;
+    const int hi_cell = min(((t1 - 1 - p.origin) >> kCellShift) + 1, p.ncells);    // exclusive; <= 82 cells
+    for (int b = 0; b < p.n_batches; b++) {
+        unsigned l = 0xffffffffu, h = 0, k = 0;
+        const int cidx = lo_cell + tid;
+        if (cidx < hi_cell) { l = p.batch[b].cell_lo[cidx]; h = p.batch[b].cell_hi[cidx]; k = p.batch[b].cell_cnt[cidx]; }
+        l = __reduce_min_sync(kFull, l);
+        h = __reduce_max_sync(kFull, h);
+        k = __reduce_add_sync(kFull, k);
+        if (lane == 0) { s_lo[b][warp] = l; s_hi[b][warp] = h; s_cnt[b][warp] = k; }
+    }
+    __syncthreads();
+    int carry = 0;                       // segments covering base t0-1: the depth carried into the tile
+    for (int b = 0; b < p.n_batches; b++) {
+        unsigned lo = 0xffffffffu, hi = 0, cnt = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) { lo = min(lo, s_lo[b][w]); hi = max(hi, s_hi[b][w]); cnt += s_cnt[b][w]; }
+        if (hi <= lo) continue;                                         // no segment starts in these cells
+        if ((unsigned long long)(hi - lo) > 8ull * cnt + 4096ull) {      // not in BAM order: let the general path do it
+            if (tid == 0) p.header[3] = 1;
+            return;                                                     // uniform: every thread sees the same lo/hi/cnt
+        }
+        const int* __restrict__ bs = p.batch[b].start;
+        const int* __restrict__ be = p.batch[b].end;
+        for (unsigned i = lo + tid; i < hi; i += kScanThreads) {
+            const int sc = max(bs[i], p.rs), ec = min(be[i], p.re);     // clipped to the region like the general path
+            if (sc < ec && sc < t1 && ec >= t0) {
+                if (sc < t0) carry++;                                   // covers t0-1 (and the tile from its first base, if ec > t0)
+                else atomicAdd(s_tile + swz_elem(sc - t0), 1);
+                if (ec - t0 < kTile) atomicAdd(s_tile + swz_elem(ec - t0), -1);
+            }
+        }
+    }
+    carry = __reduce_add_sync(kFull, carry);
+    if (lane == 0) s_carry[warp] = carry;
+    __syncthreads();
+    tile_core(p, s_tile, s_carry, tile);
+}
+
+// K_gather: one warp per tile moves its runs from claim order to position order.  The ordered offset of
+// a tile is the number of runs that start before it: super-tile counts + the tile counts of its own
 // super-tile (only tiles that have runs pay for the sum).
-__global__ void __launch_bounds__(256) depth_gather_runs_kernel(const uint64_t* __restrict__ tile_runs,
+__global__ void __launch_bounds__(256) depth_gather_runs_kernel(const uint64_t* __restrict__ header,
+                                                               const uint64_t* __restrict__ tile_runs,
                                                                const unsigned* __restrict__ super_cnt, int tiles,
                                                                const int* __restrict__ tmp_start,
                                                                const unsigned char* __restrict__ tmp_class,
                                                                int* __restrict__ run_start, unsigned char* __restrict__ run_class,
                                                                long long cap) {
+    if (header[3] != 0) return;                                         // fused path was rejected
     const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (t >= tiles) return;
     const uint64_t w = tile_runs[t];
@@ -478,20 +612,29 @@ __global__ void run_ends_kernel(const int* run_start, int* run_end, long long n,
     if (i < n) run_end[i] = (i + 1 < n) ? run_start[i + 1] : re;
 }
 
+// ================================================================================================
+// host side
+// ================================================================================================
 inline int64_t num_tiles_for(int64_t len) { return (len + kTile - 1) / kTile; }
 inline size_t diff_entries_for(int64_t len) { return (size_t)num_tiles_for(len) * kTile + 4; }
 inline size_t tile_entries_for(int64_t len) { return ((size_t)num_tiles_for(len) + 1 + 3) & ~size_t(3); }
 inline size_t super_entries_for(int64_t len) { return (((size_t)num_tiles_for(len) >> kSuperShift) + 2 + 3) & ~size_t(3); }
-inline int* tile_sum_ptr(gl_ctx* ctx) {
-    return static_cast<int*>(ctx->diff.p) + diff_entries_for(ctx->re - ctx->rs);
-}
+inline int* tile_sum_ptr(gl_ctx* ctx) { return static_cast<int*>(ctx->diff.p) + diff_entries_for(ctx->re - ctx->rs); }
 inline int* super_sum_ptr(gl_ctx* ctx) { return tile_sum_ptr(ctx) + tile_entries_for(ctx->re - ctx->rs); }
+
+inline const int32_t* batch_start(gl_ctx* ctx, const gl_seg_batch& b) {
+    return b.s ? b.s : static_cast<const int32_t*>(ctx->store_s.p) + b.off;
+}
+inline const int32_t* batch_end(gl_ctx* ctx, const gl_seg_batch& b) {
+    return b.e ? b.e : static_cast<const int32_t*>(ctx->store_e.p) + b.off;
+}
 
 int launch_scatter(gl_ctx* ctx, const int32_t* d_start, const int32_t* d_end, int64_t n) {
     if (n <= 0) return GL_OK;
     bool vec = ((reinterpret_cast<uintptr_t>(d_start) | reinterpret_cast<uintptr_t>(d_end)) & 15) == 0;
     int* diff = static_cast<int*>(ctx->diff.p);
     int* tsum = tile_sum_ptr(ctx);
+    gl_prof_scope prof(ctx, "depth_scatter_kernel");
     if (vec) {
         long long threads = (n >> 2) + (n & 3);
         unsigned grid = (unsigned)((threads + 255) / 256);
@@ -504,7 +647,36 @@ int launch_scatter(gl_ctx* ctx, const int32_t* d_start, const int32_t* d_end, in
     return GL_OK;
 }
 
-// runs the fused pass; on run-capacity overflow grows the buffers and runs again
+// general path: (re)build the HBM difference array from every batch
+int accumulate_general(gl_ctx* ctx) {
+    if (ctx->g_valid) return GL_OK;
+    const int64_t len = ctx->re - ctx->rs;
+    const size_t entries = diff_entries_for(len) + tile_entries_for(len) + super_entries_for(len);
+    GL_CHECK(gl_buf_reserve(ctx, ctx->diff, entries * 4));
+    {
+        gl_prof_scope prof(ctx, "memset_diff");
+        GL_CUDA(ctx, cudaMemsetAsync(ctx->diff.p, 0, entries * 4, ctx->stream));
+    }
+    for (const gl_seg_batch& b : ctx->batches) GL_CHECK(launch_scatter(ctx, batch_start(ctx, b), batch_end(ctx, b), b.n));
+    const int64_t tiles = num_tiles_for(len);
+    const int n_super = (int)((tiles + (1 << kSuperShift) - 1) >> kSuperShift);
+    {
+        gl_prof_scope prof(ctx, "depth_super_sum_kernel");
+        depth_super_sum_kernel<<<(unsigned)((n_super + 7) / 8), 256, 0, ctx->stream>>>(tile_sum_ptr(ctx), super_sum_ptr(ctx), (int)tiles);
+    }
+    GL_LAUNCHED(ctx, 1);
+    ctx->g_valid = true;
+    return GL_OK;
+}
+
+int read_header(gl_ctx* ctx, uint64_t hdr[4]) {
+    GL_CUDA(ctx, cudaMemcpyAsync(hdr, ctx->scratch.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+// One fused pass over the region.  Tries the fused (sorted) path first; the device decides eligibility,
+// the host learns it from the header it has to read anyway, and reruns on the general path if needed.
 int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break, bool do_windows,
                bool do_runs, int32_t* d_depth_out, bool want_min) {
     const int64_t len = ctx->re - ctx->rs;
@@ -512,9 +684,14 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
     const int64_t w0 = ctx->rs / W;
     const int64_t n_windows = (ctx->re - 1) / W - w0 + 1;
 
+    if (ctx->copies_pending) {        // host segments still streaming into the store on the copy stream
+        GL_CUDA(ctx, cudaEventRecord(ctx->ev_copy[0], ctx->copy_stream));
+        GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[0], 0));
+        ctx->copies_pending = false;
+    }
     if (do_windows) {
         GL_CHECK(gl_buf_reserve(ctx, ctx->win_sum, (size_t)n_windows * 8));
-        GL_CHECK(gl_buf_reserve(ctx, ctx->win_min, (size_t)n_windows * 4));
+        if (want_min) GL_CHECK(gl_buf_reserve(ctx, ctx->win_min, (size_t)n_windows * 4));
     }
     // scratch: header u64[8] | super_cnt u32[supers] | tile_runs u64[tiles]
     const size_t supers = super_entries_for(len);
@@ -531,27 +708,70 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
     unsigned* super_cnt = reinterpret_cast<unsigned*>(header + kHeaderWords);
     uint64_t* tile_runs = reinterpret_cast<uint64_t*>(static_cast<char*>(ctx->scratch.p) + head_bytes);
 
-    {
-        const int n_super = (int)((tiles + (1 << kSuperShift) - 1) >> kSuperShift);
-        depth_super_sum_kernel<<<(unsigned)((n_super + 7) / 8), 256, 0, ctx->stream>>>(tile_sum_ptr(ctx), super_sum_ptr(ctx), (int)tiles);
-        GL_LAUNCHED(ctx, 1);
+    ScanParams p;
+    memset(&p, 0, sizeof p);
+    p.len = (int)len;
+    p.rs = (int)ctx->rs;
+    p.re = (int)ctx->re;
+    p.W = W;
+    p.w0 = w0;
+    p.mincov = mincov;
+    p.maxmean = maxmean;
+    p.run_break = (run_break >= (int64_t(1) << 32)) ? 0u : (unsigned)run_break;
+    p.header = header;
+    p.tile_runs = tile_runs;
+    p.super_cnt = super_cnt;
+    p.depth_out = d_depth_out;
+    p.num_tiles = (int)tiles;
+    p.do_windows = do_windows ? 1 : 0;
+    p.do_runs = do_runs ? 1 : 0;
+
+    // ---- fused path set-up: index every batch (flags decide eligibility on the device)
+    bool try_fused = ctx->force_path != 2 && !ctx->batches.empty() && (int)ctx->batches.size() <= kMaxBatches;
+    for (const gl_seg_batch& b : ctx->batches) if (b.n >= INT32_MAX) try_fused = false;
+    if (try_fused) {
+        const int origin = (int)(std::max<int64_t>(0, ctx->rs - kMaxLookback) & ~int64_t((1 << kCellShift) - 1));
+        const int ncells = (int)(((ctx->re - 1 - origin) >> kCellShift) + 1);
+        const size_t nb = ctx->batches.size();
+        // per batch: cell_lo[ncells] | cell_hi[ncells] | cell_cnt[ncells]; all lo tables first so one memset(0xff) covers them
+        GL_CHECK(gl_buf_reserve(ctx, ctx->fine_idx, (size_t)ncells * 4 * 3 * nb));
+        GL_CHECK(gl_buf_reserve(ctx, ctx->sflags, kFlagWords * 4));
+        unsigned* lo_all = static_cast<unsigned*>(ctx->fine_idx.p);
+        unsigned* hi_all = lo_all + (size_t)ncells * nb;
+        unsigned* cnt_all = hi_all + (size_t)ncells * nb;
+        GL_CUDA(ctx, cudaMemsetAsync(ctx->sflags.p, 0, kFlagWords * 4, ctx->stream));
+        GL_CUDA(ctx, cudaMemsetAsync(lo_all, 0xff, (size_t)ncells * 4 * nb, ctx->stream));
+        GL_CUDA(ctx, cudaMemsetAsync(hi_all, 0, (size_t)ncells * 4 * 2 * nb, ctx->stream));
+        p.flags = static_cast<const int*>(ctx->sflags.p);
+        p.origin = origin;
+        p.ncells = ncells;
+        p.n_batches = (int)nb;
+        for (size_t bi = 0; bi < nb; bi++) {
+            const gl_seg_batch& b = ctx->batches[bi];
+            p.batch[bi].start = batch_start(ctx, b);
+            p.batch[bi].end = batch_end(ctx, b);
+            p.batch[bi].cell_lo = lo_all + bi * (size_t)ncells;
+            p.batch[bi].cell_hi = hi_all + bi * (size_t)ncells;
+            p.batch[bi].cell_cnt = cnt_all + bi * (size_t)ncells;
+            p.batch[bi].n = (int)b.n;
+            gl_prof_scope prof(ctx, "depth_index_kernel");
+            depth_index_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, ctx->stream>>>(
+                p.batch[bi].start, p.batch[bi].end, b.n, origin, (int)ctx->re, ncells, lo_all + bi * (size_t)ncells,
+                hi_all + bi * (size_t)ncells, cnt_all + bi * (size_t)ncells, static_cast<int*>(ctx->sflags.p));
+            GL_LAUNCHED(ctx, 1);
+        }
     }
 
-    for (int attempt = 0; attempt < 2; attempt++) {
-        ScanParams p;
-        memset(&p, 0, sizeof p);
-        p.diff = static_cast<const int*>(ctx->diff.p);
-        p.tile_sum = tile_sum_ptr(ctx);
-        p.super_sum = super_sum_ptr(ctx);
-        p.len = (int)len;
-        p.rs = (int)ctx->rs;
-        p.W = W;
-        p.w0 = w0;
-        p.mincov = mincov;
-        p.maxmean = maxmean;
-        p.run_break = (run_break >= (int64_t(1) << 32)) ? 0u : (unsigned)run_break;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        const bool fused = try_fused;
+        if (!fused) {
+            GL_CHECK(accumulate_general(ctx));
+            p.diff = static_cast<const int*>(ctx->diff.p);
+            p.tile_sum = tile_sum_ptr(ctx);
+            p.super_sum = super_sum_ptr(ctx);
+        }
         p.win_sum = static_cast<unsigned long long*>(ctx->win_sum.p);
-        p.win_min = want_min ? static_cast<int*>(ctx->win_min.p) : nullptr;
+        p.win_min = (do_windows && want_min) ? static_cast<int*>(ctx->win_min.p) : nullptr;
         p.tmp_start = static_cast<int*>(ctx->run_tmp_start.p);
         p.tmp_class = static_cast<unsigned char*>(ctx->run_tmp_class.p);
         long long cap = 0;
@@ -562,70 +782,75 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
             cap = std::min<long long>(cap, (long long)(ctx->run_tmp_start.cap / 4));
         }
         p.run_cap = cap;
-        p.header = header;
-        p.tile_runs = tile_runs;
-        p.super_cnt = super_cnt;
-        p.depth_out = d_depth_out;
-        p.num_tiles = (int)tiles;
-        p.do_windows = do_windows ? 1 : 0;
-        p.do_runs = do_runs ? 1 : 0;
 
         GL_CUDA(ctx, cudaMemsetAsync(header, 0, head_bytes, ctx->stream));
         if (do_windows) {
             GL_CUDA(ctx, cudaMemsetAsync(ctx->win_sum.p, 0, (size_t)n_windows * 8, ctx->stream));
             if (want_min) GL_CUDA(ctx, cudaMemsetAsync(ctx->win_min.p, 0x7f, (size_t)n_windows * 4, ctx->stream));
         }
-        depth_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p);
+        {
+            gl_prof_scope prof(ctx, fused ? "depth_fused_kernel" : "depth_scan_kernel");
+            if (fused) depth_fused_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p);
+            else depth_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p);
+        }
         GL_LAUNCHED(ctx, 1);
         if (do_runs) {
+            gl_prof_scope prof(ctx, "depth_gather_runs_kernel");
             depth_gather_runs_kernel<<<(unsigned)((tiles + 7) / 8), 256, 0, ctx->stream>>>(
-                tile_runs, super_cnt, (int)tiles, p.tmp_start, p.tmp_class, static_cast<int*>(ctx->run_start.p),
+                header, tile_runs, super_cnt, (int)tiles, p.tmp_start, p.tmp_class, static_cast<int*>(ctx->run_start.p),
                 static_cast<unsigned char*>(ctx->run_class.p), cap);
             GL_LAUNCHED(ctx, 1);
         }
 
-        ctx->red_W = W; ctx->red_mincov = mincov; ctx->red_maxmean = maxmean; ctx->red_break = run_break;
-        ctx->n_windows = do_windows ? n_windows : 0;
-        ctx->n_runs = -1;            // fetched lazily
-        ctx->max_depth = -1;
-        if (!do_runs) { ctx->n_runs = 0; break; }
-        if (attempt == 0) {
-            // The run count decides whether the output fit; peek at it only when the capacity
-            // could be exceeded at all (cap < len), else defer the sync to the first getter.
-            if (cap >= len) break;
-            uint64_t hdr[3];
-            GL_CUDA(ctx, cudaMemcpyAsync(hdr, ctx->scratch.p, sizeof hdr, cudaMemcpyDeviceToHost, ctx->stream));
-            GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            ctx->n_runs = (int64_t)hdr[0];
-            ctx->max_depth = (int32_t)hdr[2];
-            if ((long long)hdr[0] <= cap) break;
+        uint64_t hdr[4];
+        GL_CHECK(read_header(ctx, hdr));
+        if (fused && hdr[3] != 0) { try_fused = false; continue; }        // not in BAM order / segments too long
+        ctx->last_path = fused ? 1 : 2;
+        ctx->n_runs = do_runs ? (int64_t)hdr[0] : 0;
+        ctx->max_depth = (int32_t)hdr[2];
+        if (do_runs && (long long)hdr[0] > cap) {                          // output did not fit: grow and rerun
             size_t ncap = (size_t)hdr[0] + 1024;
             GL_CHECK(gl_buf_reserve(ctx, ctx->run_start, ncap * 4));
             GL_CHECK(gl_buf_reserve(ctx, ctx->run_class, ncap));
             GL_CHECK(gl_buf_reserve(ctx, ctx->run_tmp_start, ncap * 4));
             GL_CHECK(gl_buf_reserve(ctx, ctx->run_tmp_class, ncap));
+            continue;
         }
+        break;
     }
+    ctx->red_W = W; ctx->red_mincov = mincov; ctx->red_maxmean = maxmean; ctx->red_break = run_break;
+    ctx->n_windows = do_windows ? n_windows : 0;
     ctx->depth_reduced = true;
     return GL_OK;
 }
 
-int fetch_header(gl_ctx* ctx) {
-    if (ctx->n_runs >= 0 && ctx->max_depth >= 0) return GL_OK;
-    uint64_t hdr[3];
-    GL_CUDA(ctx, cudaMemcpyAsync(hdr, ctx->scratch.p, sizeof hdr, cudaMemcpyDeviceToHost, ctx->stream));
-    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->n_runs < 0) ctx->n_runs = (int64_t)hdr[0];
-    ctx->max_depth = (int32_t)hdr[2];
-    return GL_OK;
-}
-
-constexpr int64_t kStageSegs = int64_t(1) << 22;      // segments per staging slot (2 x 16 MiB)
+constexpr int64_t kStageSegs = int64_t(1) << 22;      // segments per pinned staging slot (2 x 16 MiB)
 
 bool is_pinned_host(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
+}
+
+// grow the ctx segment store to hold `need` segments, keeping its contents
+int store_reserve(gl_ctx* ctx, int64_t need) {
+    const size_t bytes = (size_t)need * 4;
+    if (bytes <= ctx->store_s.cap && bytes <= ctx->store_e.cap) return GL_OK;
+    const size_t want = std::max(bytes, ctx->store_s.cap * 2);
+    gl_buf ns, ne;
+    GL_CHECK(gl_buf_reserve(ctx, ns, want));
+    GL_CHECK(gl_buf_reserve(ctx, ne, want));
+    if (ctx->store_n > 0) {
+        GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        GL_CUDA(ctx, cudaMemcpyAsync(ns.p, ctx->store_s.p, (size_t)ctx->store_n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        GL_CUDA(ctx, cudaMemcpyAsync(ne.p, ctx->store_e.p, (size_t)ctx->store_n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->store_s.p) cudaFree(ctx->store_s.p);
+    if (ctx->store_e.p) cudaFree(ctx->store_e.p);
+    ctx->store_s = ns;
+    ctx->store_e = ne;
+    return GL_OK;
 }
 
 }  // namespace
@@ -638,12 +863,12 @@ int gl_depth_begin(gl_ctx* ctx, int64_t region_start, int64_t region_end) {
         return gl_fail(ctx, GL_EINVAL, "gl_depth_begin: bad region [%lld,%lld)", (long long)region_start, (long long)region_end);
     const int64_t len = region_end - region_start;
     if (len >= (int64_t(1) << 30)) return gl_fail(ctx, GL_ERANGE, "gl_depth_begin: region longer than 2^30-1 bases");
-    // difference array (padded to whole tiles) followed by the per-tile net sums: one memset clears both
-    const size_t entries = diff_entries_for(len) + tile_entries_for(len) + super_entries_for(len);
-    GL_CHECK(gl_buf_reserve(ctx, ctx->diff, entries * 4));
-    GL_CUDA(ctx, cudaMemsetAsync(ctx->diff.p, 0, entries * 4, ctx->stream));
+    if (ctx->copies_pending) { GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream)); ctx->copies_pending = false; }
     ctx->rs = region_start;
     ctx->re = region_end;
+    ctx->batches.clear();
+    ctx->store_n = 0;
+    ctx->g_valid = false;
     ctx->depth_active = true;
     ctx->depth_reduced = false;
     ctx->n_windows = 0;
@@ -656,8 +881,13 @@ int gl_depth_add_segments_device(gl_ctx* ctx, const int32_t* d_start, const int3
     GL_CHECK(gl_use(ctx));
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_add_segments: no region open (call gl_depth_begin)");
     if (n < 0 || (n > 0 && (!d_start || !d_end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments: bad argument");
+    if (n == 0) return GL_OK;
+    gl_seg_batch b;
+    b.s = d_start; b.e = d_end; b.n = n;
+    ctx->batches.push_back(b);
+    ctx->g_valid = false;
     ctx->depth_reduced = false;
-    return launch_scatter(ctx, d_start, d_end, n);
+    return GL_OK;
 }
 
 int gl_depth_add_segments(gl_ctx* ctx, const int32_t* start, const int32_t* end, int64_t n) {
@@ -665,44 +895,50 @@ int gl_depth_add_segments(gl_ctx* ctx, const int32_t* start, const int32_t* end,
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_add_segments: no region open (call gl_depth_begin)");
     if (n < 0 || (n > 0 && (!start || !end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments: bad argument");
     if (n == 0) return GL_OK;
-    ctx->depth_reduced = false;
-    const bool pinned = is_pinned_host(start) && is_pinned_host(end);
-    const size_t slot_bytes = (size_t)kStageSegs * 8;
-    for (int i = 0; i < 2; i++) {
-        GL_CHECK(gl_buf_reserve(ctx, ctx->seg[i], slot_bytes));
-        if (!pinned && !ctx->pinned[i]) {
-            cudaError_t e = cudaHostAlloc(&ctx->pinned[i], slot_bytes, cudaHostAllocDefault);
-            if (e != cudaSuccess) { ctx->pinned[i] = nullptr; cudaGetLastError(); return gl_fail(ctx, GL_ENOMEM, "cudaHostAlloc staging: %s", cudaGetErrorString(e)); }
+    GL_CHECK(store_reserve(ctx, ctx->store_n + n));
+    int32_t* d_s = static_cast<int32_t*>(ctx->store_s.p) + ctx->store_n;
+    int32_t* d_e = static_cast<int32_t*>(ctx->store_e.p) + ctx->store_n;
+    if (is_pinned_host(start) && is_pinned_host(end)) {
+        GL_CUDA(ctx, cudaMemcpyAsync(d_s, start, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        GL_CUDA(ctx, cudaMemcpyAsync(d_e, end, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+        // pageable source: stage through two pinned slots so the CPU memcpy overlaps the DMA
+        const size_t slot_bytes = (size_t)kStageSegs * 8;
+        for (int i = 0; i < 2; i++) {
+            if (!ctx->pinned[i]) {
+                cudaError_t e = cudaHostAlloc(&ctx->pinned[i], slot_bytes, cudaHostAllocDefault);
+                if (e != cudaSuccess) { ctx->pinned[i] = nullptr; cudaGetLastError(); return gl_fail(ctx, GL_ENOMEM, "cudaHostAlloc staging: %s", cudaGetErrorString(e)); }
+            }
         }
-    }
-    int64_t done = 0;
-    int slot = 0;
-    while (done < n) {
-        const int64_t m = (n - done < kStageSegs) ? n - done : kStageSegs;
-        int32_t* d_s = static_cast<int32_t*>(ctx->seg[slot].p);
-        int32_t* d_e = d_s + kStageSegs;
-        // the scatter that last read this device slot must be finished before it is overwritten
-        GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[slot], 0));
-        if (pinned) {
-            GL_CUDA(ctx, cudaMemcpyAsync(d_s, start + done, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-            GL_CUDA(ctx, cudaMemcpyAsync(d_e, end + done, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-        } else {
-            // the previous H2D out of this pinned slot must have drained before we refill it
-            GL_CUDA(ctx, cudaEventSynchronize(ctx->ev_copy[slot]));
+        int64_t done = 0;
+        int slot = 0;
+        while (done < n) {
+            const int64_t m = (n - done < kStageSegs) ? n - done : kStageSegs;
+            GL_CUDA(ctx, cudaEventSynchronize(ctx->ev_used[slot]));       // previous DMA out of this slot has drained
             int32_t* h_s = static_cast<int32_t*>(ctx->pinned[slot]);
             int32_t* h_e = h_s + kStageSegs;
             memcpy(h_s, start + done, (size_t)m * 4);
             memcpy(h_e, end + done, (size_t)m * 4);
-            GL_CUDA(ctx, cudaMemcpyAsync(d_s, h_s, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-            GL_CUDA(ctx, cudaMemcpyAsync(d_e, h_e, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+            GL_CUDA(ctx, cudaMemcpyAsync(d_s + done, h_s, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+            GL_CUDA(ctx, cudaMemcpyAsync(d_e + done, h_e, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+            GL_CUDA(ctx, cudaEventRecord(ctx->ev_used[slot], ctx->copy_stream));
+            done += m;
+            slot ^= 1;
         }
-        GL_CUDA(ctx, cudaEventRecord(ctx->ev_copy[slot], ctx->copy_stream));
-        GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[slot], 0));
-        GL_CHECK(launch_scatter(ctx, d_s, d_e, m));
-        GL_CUDA(ctx, cudaEventRecord(ctx->ev_used[slot], ctx->stream));
-        done += m;
-        slot ^= 1;
     }
+    ctx->copies_pending = true;
+    // consecutive host calls extend one contiguous batch in the store
+    if (!ctx->batches.empty() && ctx->batches.back().s == nullptr &&
+        ctx->batches.back().off + ctx->batches.back().n == ctx->store_n) {
+        ctx->batches.back().n += n;
+    } else {
+        gl_seg_batch b;
+        b.off = ctx->store_n; b.n = n;
+        ctx->batches.push_back(b);
+    }
+    ctx->store_n += n;
+    ctx->g_valid = false;
+    ctx->depth_reduced = false;
     return GL_OK;
 }
 
@@ -710,26 +946,36 @@ int gl_depth_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int
     GL_CHECK(gl_use(ctx));
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_reduce: no region open");
     if (W <= 0 || run_break < 0) return gl_fail(ctx, GL_EINVAL, "gl_depth_reduce: W must be > 0 and run_break >= 0");
-    return run_reduce(ctx, W, mincov, maxmean, run_break, true, true, nullptr, true);
+    return run_reduce(ctx, W, mincov, maxmean, run_break, true, true, nullptr, false);
 }
 
 int gl_depth_result_sizes(gl_ctx* ctx, int64_t* n_windows, int64_t* n_runs, int32_t* max_depth) {
     GL_CHECK(gl_use(ctx));
     if (!ctx->depth_reduced) return gl_fail(ctx, GL_ESTATE, "gl_depth_result_sizes: call gl_depth_reduce first");
-    GL_CHECK(fetch_header(ctx));
     if (n_windows) *n_windows = ctx->n_windows;
     if (n_runs) *n_runs = ctx->n_runs;
     if (max_depth) *max_depth = ctx->max_depth;
     return GL_OK;
 }
 
-int gl_depth_get_windows(gl_ctx* ctx, int64_t* sum_out, int32_t* min_out, int64_t cap) {
+int gl_depth_last_path(gl_ctx* ctx, int32_t* path) {
+    if (!ctx || !path) return gl_fail(ctx, GL_EINVAL, "null argument");
+    *path = ctx->last_path;
+    return GL_OK;
+}
+
+int gl_depth_set_path(gl_ctx* ctx, int32_t path) {
+    if (!ctx || path < 0 || path > 2) return gl_fail(ctx, GL_EINVAL, "gl_depth_set_path: path must be 0 (auto), 1 or 2");
+    ctx->force_path = path;
+    return GL_OK;
+}
+
+int gl_depth_get_windows(gl_ctx* ctx, int64_t* sum_out, int64_t cap) {
     GL_CHECK(gl_use(ctx));
     if (!ctx->depth_reduced || ctx->n_windows == 0) return gl_fail(ctx, GL_ESTATE, "gl_depth_get_windows: no window results");
     if (!sum_out) return gl_fail(ctx, GL_EINVAL, "gl_depth_get_windows: null sum_out");
     if (cap < ctx->n_windows) return gl_fail(ctx, GL_ERANGE, "gl_depth_get_windows: cap %lld < %lld windows", (long long)cap, (long long)ctx->n_windows);
     GL_CUDA(ctx, cudaMemcpyAsync(sum_out, ctx->win_sum.p, (size_t)ctx->n_windows * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (min_out) GL_CUDA(ctx, cudaMemcpyAsync(min_out, ctx->win_min.p, (size_t)ctx->n_windows * 4, cudaMemcpyDeviceToHost, ctx->stream));
     GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GL_OK;
 }
@@ -737,7 +983,6 @@ int gl_depth_get_windows(gl_ctx* ctx, int64_t* sum_out, int32_t* min_out, int64_
 int gl_depth_get_runs(gl_ctx* ctx, int32_t* run_start, int32_t* run_end, uint8_t* run_class, int64_t cap) {
     GL_CHECK(gl_use(ctx));
     if (!ctx->depth_reduced) return gl_fail(ctx, GL_ESTATE, "gl_depth_get_runs: call gl_depth_reduce first");
-    GL_CHECK(fetch_header(ctx));
     const int64_t n = ctx->n_runs;
     if (cap < n) return gl_fail(ctx, GL_ERANGE, "gl_depth_get_runs: cap %lld < %lld runs", (long long)cap, (long long)n);
     if (n == 0) return GL_OK;
@@ -759,7 +1004,12 @@ int gl_depth_windows(gl_ctx* ctx, int32_t W, int64_t* sum_out, int32_t* min_out,
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_windows: no region open");
     if (W <= 0) return gl_fail(ctx, GL_EINVAL, "gl_depth_windows: W must be > 0");
     GL_CHECK(run_reduce(ctx, W, 0, 0, 0, true, false, nullptr, min_out != nullptr));
-    return gl_depth_get_windows(ctx, sum_out, min_out, n_windows);
+    GL_CHECK(gl_depth_get_windows(ctx, sum_out, n_windows));
+    if (min_out) {
+        GL_CUDA(ctx, cudaMemcpyAsync(min_out, ctx->win_min.p, (size_t)ctx->n_windows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GL_OK;
 }
 
 int gl_depth_classes(gl_ctx* ctx, int32_t mincov, int32_t maxmean, int32_t* run_start, int32_t* run_end,
@@ -767,7 +1017,6 @@ int gl_depth_classes(gl_ctx* ctx, int32_t mincov, int32_t maxmean, int32_t* run_
     GL_CHECK(gl_use(ctx));
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_classes: no region open");
     GL_CHECK(run_reduce(ctx, 1 << 30, mincov, maxmean, 0, false, true, nullptr, false));
-    GL_CHECK(fetch_header(ctx));
     if (n_runs) *n_runs = ctx->n_runs;
     return gl_depth_get_runs(ctx, run_start, run_end, run_class, cap);
 }
@@ -792,8 +1041,7 @@ int gl_depth_region(gl_ctx* ctx, int64_t region_start, int64_t region_end, const
     GL_CHECK(gl_depth_begin(ctx, region_start, region_end));
     GL_CHECK(gl_depth_add_segments(ctx, start, end, n));
     GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, run_break));
-    int64_t nw = 0, nr = 0;
-    GL_CHECK(gl_depth_result_sizes(ctx, &nw, &nr, nullptr));
+    const int64_t nw = ctx->n_windows, nr = ctx->n_runs;
     if (n_windows) *n_windows = nw;
     if (n_runs) *n_runs = nr;
     if (nw > win_cap) return gl_fail(ctx, GL_ERANGE, "gl_depth_region: %lld windows > cap %lld", (long long)nw, (long long)win_cap);

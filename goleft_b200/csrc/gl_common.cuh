@@ -14,6 +14,13 @@ struct gl_buf {            // grow-only device buffer
     size_t cap = 0;
 };
 
+struct gl_seg_batch {      // one gl_depth_add_segments* call
+    const int32_t* s = nullptr;   // device pointers (caller-owned), or null when the batch lives in the ctx store
+    const int32_t* e = nullptr;
+    int64_t off = 0;              // offset into the ctx store when s == nullptr
+    int64_t n = 0;
+};
+
 struct gl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;       // compute stream
@@ -31,7 +38,16 @@ struct gl_ctx {
     int64_t rs = 0, re = 0;
     int32_t red_W = 0, red_mincov = 0, red_maxmean = 0; int64_t red_break = 0;
     int64_t n_windows = 0, n_runs = 0; int32_t max_depth = 0;
-    gl_buf diff;          // int32[len+1 (+pad)]
+    std::vector<gl_seg_batch> batches;      // segments added since gl_depth_begin
+    gl_buf store_s, store_e;                // host-uploaded segments, contiguous
+    int64_t store_n = 0;
+    bool copies_pending = false;            // H2D into the store still in flight on copy_stream
+    bool g_valid = false;                   // the HBM difference array holds every batch (general path)
+    int last_path = 0;                      // 1 = fused sorted path, 2 = general scatter path
+    int force_path = 0;                     // 0 = auto, 2 = always general (tests / comparison arm)
+    gl_buf fine_idx;      // per-256-base segment offsets of every batch (fused path)
+    gl_buf sflags;        // [0]=unsorted, [16..16+1024) max segment length slots
+    gl_buf diff;          // int32[len+1 (+pad)] + tile sums (general path only)
     gl_buf win_sum;       // u64[n_windows]
     gl_buf win_min;       // i32[n_windows]
     gl_buf run_start;     // i32[run_cap]
@@ -44,6 +60,12 @@ struct gl_ctx {
     size_t pinned_bytes = 0;
     gl_buf flush;         // L2 flush scratch
     gl_buf misc;          // small outputs of other subsystems
+
+    // per-kernel CUDA-event profiling (gl_profile_*): (name, start, stop) per launch while enabled
+    bool prof_on = false;
+    struct prof_rec { const char* name; cudaEvent_t a, b; };
+    std::vector<prof_rec> prof;
+    std::vector<cudaEvent_t> prof_pool;
 
     void* nccl = nullptr; // ncclComm_t when gl_comm_init was called
     int rank = 0, world = 1;
@@ -73,6 +95,23 @@ int gl_buf_reserve(gl_ctx* ctx, gl_buf& b, size_t bytes);
         (ctx)->launches += (n);                                                        \
         GL_CUDA((ctx), cudaGetLastError());                                            \
     } while (0)
+
+// Bracket one kernel launch with events on the ctx stream when profiling is on.
+struct gl_prof_scope {
+    gl_ctx* ctx; cudaEvent_t b = nullptr;
+    gl_prof_scope(gl_ctx* c, const char* name) : ctx(c) {
+        if (!c->prof_on) return;
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; i++) {
+            if (!c->prof_pool.empty()) { ev[i] = c->prof_pool.back(); c->prof_pool.pop_back(); }
+            else cudaEventCreate(&ev[i]);
+        }
+        cudaEventRecord(ev[0], c->stream);
+        b = ev[1];
+        c->prof.push_back({name, ev[0], ev[1]});
+    }
+    ~gl_prof_scope() { if (b) cudaEventRecord(b, ctx->stream); }
+};
 
 static inline int gl_use(gl_ctx* ctx) {
     if (!ctx) return gl_fail(nullptr, GL_EINVAL, "null ctx");

@@ -108,12 +108,15 @@ int gl_ctx_destroy(gl_ctx* ctx) {
     buf_free(ctx->diff); buf_free(ctx->win_sum); buf_free(ctx->win_min);
     buf_free(ctx->run_start); buf_free(ctx->run_class); buf_free(ctx->scratch);
     buf_free(ctx->run_tmp_start); buf_free(ctx->run_tmp_class);
+    buf_free(ctx->store_s); buf_free(ctx->store_e); buf_free(ctx->fine_idx); buf_free(ctx->sflags);
     buf_free(ctx->seg[0]); buf_free(ctx->seg[1]); buf_free(ctx->flush); buf_free(ctx->misc);
     for (int i = 0; i < 2; i++) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
         if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);
     }
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -209,6 +212,36 @@ int gl_timer_stop_ms(gl_ctx* ctx, float* ms) {
     GL_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     GL_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     GL_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return GL_OK;
+}
+
+int gl_profile_enable(gl_ctx* ctx, int on) {
+    GL_CHECK(gl_use(ctx));
+    ctx->prof_on = on != 0;
+    return GL_OK;
+}
+
+// "name ms\n" per kernel launched since the last read; synchronizes the stream
+int gl_profile_read(gl_ctx* ctx, char* buf, int64_t cap, int64_t* needed) {
+    GL_CHECK(gl_use(ctx));
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::string out;
+    for (auto& r : ctx->prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        char line[128];
+        snprintf(line, sizeof line, "%s %.6f\n", r.name, ms);
+        out += line;
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    if (needed) *needed = (int64_t)out.size() + 1;
+    if (buf && cap > 0) {
+        size_t n = std::min<size_t>(out.size(), (size_t)cap - 1);
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
     return GL_OK;
 }
 

@@ -68,6 +68,10 @@ int  gl_memcpy_d2h(gl_ctx* ctx, void* h_dst, const void* d_src, int64_t bytes);
 /* device-timed interval helpers (CUDA events on the ctx stream) */
 int  gl_timer_start(gl_ctx* ctx);
 int  gl_timer_stop_ms(gl_ctx* ctx, float* ms);      /* records, synchronizes, returns elapsed */
+/* per-kernel CUDA-event timing on the ctx stream: enable, run, then read "name ms\n" lines
+ * (one per kernel launched since the last read; synchronizes).  Off by default. */
+int  gl_profile_enable(gl_ctx* ctx, int on);
+int  gl_profile_read(gl_ctx* ctx, char* buf, int64_t cap, int64_t* needed);
 /* write `bytes` of junk to a scratch buffer (> L2) so the next launch starts cold */
 int  gl_flush_l2(gl_ctx* ctx);
 
@@ -83,35 +87,44 @@ int  gl_flush_l2(gl_ctx* ctx);
  * host: gl_depth_format_chunk().
  */
 
-/* Start a region: allocates (grow-only) and zeroes an int32 difference array of
- * region_end-region_start+1 entries in HBM.  0 <= start < end, end-start < 2^30. */
+/* Start a region [region_start, region_end) of one contig.  0 <= start < end, end-start < 2^30. */
 int  gl_depth_begin(gl_ctx* ctx, int64_t region_start, int64_t region_end);
 
-/* Scatter n segments [start[i], end[i]) (absolute contig coordinates, any order,
- * end>start; clipped to the region by the kernel; segments outside are ignored).
- * May be called repeatedly between begin and reduce.  Host-pointer variant copies
- * through a pinned ring on the ctx stream; _device variant reads HBM-resident arrays. */
+/* Add n segments [start[i], end[i]) (absolute contig coordinates, end>start; clipped to the region
+ * by the kernels; segments outside are ignored).  May be called repeatedly between begin and reduce.
+ * Host-pointer variant copies into a ctx-owned device store on a copy stream (pinned sources DMA
+ * directly, pageable ones are staged); _device variant references HBM-resident arrays, which must
+ * stay valid until the results have been fetched.
+ * Any order is accepted.  Coordinate-sorted segments (non-decreasing start, what a BAM yields) of at
+ * most 16384 bases take the fused path: each 4096-base tile's difference array is built in shared
+ * memory straight from the segments.  Anything else takes the general path: int32 reds onto a
+ * difference array in HBM.  The device checks eligibility itself; results are identical. */
 int  gl_depth_add_segments(gl_ctx* ctx, const int32_t* start, const int32_t* end, int64_t n);
 int  gl_depth_add_segments_device(gl_ctx* ctx, const int32_t* d_start, const int32_t* d_end, int64_t n);
 
-/* One fused pass over the difference array: prefix scan -> per-base depth ->
- *   (a) per-window int64 sums (+ int32 min) for genome-aligned windows of size W clipped
- *       to the region: window k covers [max(rs,(rs/W+k)*W), min(re,(rs/W+k+1)*W)),
+/* One fused pass: prefix scan -> per-base depth (never written to HBM) ->
+ *   (a) per-window int64 sums for genome-aligned windows of size W clipped to the region:
+ *       window k covers [max(rs,(rs/W+k)*W), min(re,(rs/W+k+1)*W)),
  *   (b) class run starts: position x starts a run when x==rs, class(x)!=class(x-1), or
  *       run_break>0 and x%run_break==0 (the reference never merges runs across its 10 Mb
  *       chunks, depth/depth.go:132,150: pass run_break=step to reproduce that).
- * mincov/maxmean as depth/depth.go:223-234.  Results stay on the device until fetched. */
+ * mincov/maxmean as depth/depth.go:223-234.  Synchronous; results stay on the device until fetched. */
 int  gl_depth_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break);
 
-/* Sizes of the results of the last gl_depth_reduce (synchronizes). */
+/* Sizes of the results of the last gl_depth_reduce. */
 int  gl_depth_result_sizes(gl_ctx* ctx, int64_t* n_windows, int64_t* n_runs, int32_t* max_depth);
+/* Which path the last reduce took: 1 = fused (sorted), 2 = general (scatter). */
+int  gl_depth_last_path(gl_ctx* ctx, int32_t* path);
+/* 0 = choose automatically (default), 2 = always take the general path (tests, comparison runs). */
+int  gl_depth_set_path(gl_ctx* ctx, int32_t path);
 
-/* Fetch results (host buffers).  min_out may be NULL.  run_end may be NULL
- * (run i ends where run i+1 starts; the last ends at region_end). */
-int  gl_depth_get_windows(gl_ctx* ctx, int64_t* sum_out, int32_t* min_out, int64_t cap);
+/* Fetch results (host buffers).  run_end may be NULL (run i ends where run i+1 starts; the last
+ * ends at region_end). */
+int  gl_depth_get_windows(gl_ctx* ctx, int64_t* sum_out, int64_t cap);
 int  gl_depth_get_runs(gl_ctx* ctx, int32_t* run_start, int32_t* run_end, uint8_t* run_class, int64_t cap);
 
-/* Convenience forms named in SURVEY.md §8(b): run the fused pass for one output only. */
+/* Forms named in SURVEY.md §8(b): run the pass for one output only.  gl_depth_windows also gives the
+ * per-window minimum depth when min_out != NULL (an extra: the reference prints means only). */
 int  gl_depth_windows(gl_ctx* ctx, int32_t W, int64_t* sum_out, int32_t* min_out, int64_t n_windows);
 int  gl_depth_classes(gl_ctx* ctx, int32_t mincov, int32_t maxmean, int32_t* run_start, int32_t* run_end,
                       uint8_t* run_class, int64_t cap, int64_t* n_runs);

@@ -18,8 +18,8 @@ def rand_segments(rng, n, lo, hi, maxlen=300):
     return s, e
 
 
-def check_region(ctx, s, e, rs, re, W, mincov=4, maxmean=0, run_break=0, device=False):
-    exp_depth = orc.pileup_brute(s, e, rs, re) if s.size * 300 < 5e8 else orc.pileup_diff(s, e, rs, re)
+def _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device, expect_path, exp):
+    exp_depth, es, em, ea, ec = exp
     ctx.depth_begin(rs, re)
     bufs = []
     if device:
@@ -29,23 +29,49 @@ def check_region(ctx, s, e, rs, re, W, mincov=4, maxmean=0, run_break=0, device=
     else:
         ctx.depth_add_segments(s, e)
     ctx.depth_reduce(W, mincov, maxmean, run_break)
+    if expect_path is not None and s.size:
+        assert ctx.depth_last_path() == expect_path
     nw, nr, md = ctx.depth_result_sizes()
-    ws, wm = ctx.depth_get_windows()
+    ws = ctx.depth_get_windows()
     r0, r1, rc = ctx.depth_get_runs(want_end=True)
-    es, em = orc.window_sums(exp_depth, rs, re, W)
-    ea, ec = orc.class_runs(exp_depth, rs, re, mincov, maxmean, run_break)
     assert nw == es.size
     assert np.array_equal(ws, es)
-    assert np.array_equal(wm, em)
     assert nr == ea.size
     assert np.array_equal(r0, ea)
     assert np.array_equal(rc, ec)
     assert np.array_equal(r1, np.append(ea[1:], re).astype(np.int32))
     assert md == int(exp_depth.max(initial=0))
+    ws2, wm2 = ctx.depth_windows(W, nw)                      # sums + per-window minimum (general window path)
+    assert np.array_equal(ws2, es) and np.array_equal(wm2, em)
     got_depth = ctx.depth_perbase(re - rs)
     assert np.array_equal(got_depth, exp_depth)
     for b in bufs:
         b.free()
+    return ws, r0, rc
+
+
+def check_region(ctx, s, e, rs, re, W, mincov=4, maxmean=0, run_break=0, device=False):
+    """Both ways of building the difference array must give the oracle's integers:
+    as given (general scatter path unless already sorted), sorted (fused smem path), sorted + forced general."""
+    exp_depth = orc.pileup_brute(s, e, rs, re) if s.size * 300 < 5e8 else orc.pileup_diff(s, e, rs, re)
+    es, em = orc.window_sums(exp_depth, rs, re, W)
+    ea, ec = orc.class_runs(exp_depth, rs, re, mincov, maxmean, run_break)
+    exp = (exp_depth, es, em, ea, ec)
+    is_sorted = bool((np.diff(s) >= 0).all()) if s.size else True
+    short = bool(((e - s) <= 16384).all()) if s.size else True
+    # unsorted input is correct on either path (the fused kernel only bails out when its index span explodes)
+    out = _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device,
+                    (1 if short else 2) if is_sorted else (None if short else 2), exp)
+    if not is_sorted:
+        o = np.argsort(s, kind="stable")
+        _run_once(ctx, s[o], e[o], rs, re, W, mincov, maxmean, run_break, device, 1 if short else 2, exp)
+    else:
+        ctx.depth_set_path(2)
+        try:
+            _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device, 2, exp)
+        finally:
+            ctx.depth_set_path(0)
+    ws, r0, rc = out
     return exp_depth, ws, r0, rc
 
 
@@ -88,6 +114,50 @@ def test_window_sizes_extreme(ctx):
     s, e = rand_segments(rng, 40000, 0, 100000, maxlen=151)
     for W in [1, 2, 16, 17, 4096, 5000, 2 ** 30]:
         check_region(ctx, s, e, 0, 100000, W, mincov=3, maxmean=25)
+
+
+def test_bam_order_segments_take_fused_path(ctx):
+    """BAM order = reads sorted by position; the second block of a deletion read starts after the next reads
+    do, so segment starts are only nearly sorted.  That must still take the fused path."""
+    L = 3_000_000
+    s, e = synth.segments(synth.reads(L, contig_index=7))
+    assert not (np.diff(s) >= 0).all()
+    ctx.depth_begin(0, L)
+    ctx.depth_add_segments(s, e)
+    ctx.depth_reduce(500, 4, 0, 0)
+    assert ctx.depth_last_path() == 1
+    exp = orc.pileup_diff(s, e, 0, L)
+    es, _ = orc.window_sums(exp, 0, L, 500)
+    ea, ec = orc.class_runs(exp, 0, L, 4, 0, 0)
+    assert np.array_equal(ctx.depth_get_windows(), es)
+    r0, rc = ctx.depth_get_runs()
+    assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
+    # shuffled: the fused kernel notices the index span explosion and the general path takes over
+    rng = np.random.default_rng(3)
+    p = rng.permutation(s.size)
+    ctx.depth_begin(0, L)
+    ctx.depth_add_segments(s[p], e[p])
+    ctx.depth_reduce(500, 4, 0, 0)
+    assert ctx.depth_last_path() == 2
+    assert np.array_equal(ctx.depth_get_windows(), es)
+    r0, rc = ctx.depth_get_runs()
+    assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
+
+
+def test_long_segments_fall_back(ctx):
+    """segments longer than the fused path's look-back (16384) -> general path, same integers"""
+    rng = np.random.default_rng(11)
+    s = np.sort(rng.integers(0, 200000, 3000)).astype(np.int32)
+    e = (s + rng.integers(1, 60000, 3000)).astype(np.int32)
+    check_region(ctx, s, e, 1000, 180000, 500)
+
+
+def test_fused_lookback_edges(ctx):
+    """sorted segments whose length is exactly at / around tile and cell edges"""
+    s = np.array([0, 0, 255, 256, 4095, 4096, 4096, 8191, 12000, 16383, 20000], np.int32)
+    e = np.array([4096, 16384, 4097, 257, 4096, 4097, 20480, 8192, 28384, 16385, 20001], np.int32)
+    for rs, re in [(0, 30000), (100, 20000), (4096, 8192), (4095, 8193)]:
+        check_region(ctx, s, e, rs, re, 100, mincov=2)
 
 
 def test_deep_pileup_int64_sums(ctx):
@@ -134,6 +204,15 @@ def test_state_errors(ctx):
     c2.close()
 
 
+def test_sparse_region_far_from_origin(ctx):
+    """bed-style region deep inside a contig with a handful of reads (index table starts at rs-16384)"""
+    s = np.array([99_990_000, 100_000_100, 100_000_100, 100_004_000, 100_100_000], np.int32)
+    e = s + np.array([20000, 150, 151, 9000, 10], np.int32)
+    check_region(ctx, s, e, 100_000_000, 100_050_000, 250, mincov=1)
+    s2 = s[1:4]; e2 = (s2 + 150).astype(np.int32)
+    check_region(ctx, s2, e2, 100_000_000, 100_050_000, 250, mincov=1)
+
+
 def test_run_capacity_regrow(ctx):
     """alternating covered/uncovered bases: one run per base, far above the initial capacity"""
     L = 300_000
@@ -171,13 +250,26 @@ def test_full_size_chr20(ctx):
     ctx.depth_begin(0, L)
     ctx.depth_add_segments_device(ds, de, s.size)
     ctx.depth_reduce(W, 4, 0, 10_000_000)
-    ws, wm = ctx.depth_get_windows()
+    assert ctx.depth_last_path() == 1
+    ws = ctx.depth_get_windows()
     r0, rc = ctx.depth_get_runs()
     assert int(ws.sum()) == int((np.minimum(e, L).astype(np.int64) - np.maximum(s, 0)).clip(0).sum())
     assert r0[0] == 0 and (np.diff(r0) > 0).all() and r0[-1] < L
     exp = orc.pileup_diff(s, e, 0, L)
     es, em = orc.window_sums(exp, 0, L, W)
     ea, ec = orc.class_runs(exp, 0, L, 4, 0, 10_000_000)
-    assert np.array_equal(ws, es) and np.array_equal(wm, em)
+    assert np.array_equal(ws, es)
     assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
+    # the general (scatter) path at full size gives the same integers
+    ctx.depth_set_path(2)
+    ctx.depth_begin(0, L)
+    ctx.depth_add_segments_device(ds, de, s.size)
+    ctx.depth_reduce(W, 4, 0, 10_000_000)
+    assert ctx.depth_last_path() == 2
+    assert np.array_equal(ctx.depth_get_windows(), es)
+    r0, rc = ctx.depth_get_runs()
+    assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
+    ws2, wm2 = ctx.depth_windows(W, es.size)
+    assert np.array_equal(ws2, es) and np.array_equal(wm2, em)
+    ctx.depth_set_path(0)
     ds.free(); de.free()
