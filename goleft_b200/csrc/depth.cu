@@ -157,36 +157,83 @@ __global__ void __launch_bounds__(256) depth_super_sum_kernel(const int* __restr
 // the fused kernel compares span and count.  Also: the longest segment, in 1024 slots (a single word
 // would serialise one atomic per warp on one address).
 // ================================================================================================
+__device__ __forceinline__ int index_cell(int s, int len, int origin, int re, int ncells) {
+    // segments that start below a non-zero origin cannot reach the region (length <= look-back, else the
+    // fused path is rejected anyway); negative starts belong to cell 0 when origin is 0
+    return (len > 0 && s < re && (s >= origin || origin == 0)) ? min(max(s - origin, 0) >> kCellShift, ncells - 1) : -1;
+}
+
+// 4 segments per thread (128-bit loads keep enough bytes in flight); runs of equal cells are found over
+// the warp's 128 consecutive segments.
 __global__ void __launch_bounds__(256) depth_index_kernel(const int* __restrict__ start, const int* __restrict__ end,
                                                          long long n, int origin, int re, int ncells,
                                                          unsigned* __restrict__ cell_lo, unsigned* __restrict__ cell_hi,
                                                          unsigned* __restrict__ cell_cnt, int* __restrict__ flags) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long base = t * 4;
     const int lane = threadIdx.x & 31;
-    int len = 0, c = -1;
-    if (i < n) {
-        const int s = start[i];
-        len = end[i] - s;
-        // segments that start below a non-zero origin cannot reach the region (length <= look-back, else the
-        // fused path is rejected anyway); negative starts belong to cell 0 when origin is 0
-        if (len > 0 && s < re && (s >= origin || origin == 0)) c = min(max(s - origin, 0) >> kCellShift, ncells - 1);
+    int c[4] = {-1, -1, -1, -1};
+    int len = 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(start) | reinterpret_cast<uintptr_t>(end)) & 15) == 0;
+    if (base + 3 < n && vec) {
+        const int4 s4 = ld_stream_int4(reinterpret_cast<const int4*>(start) + t);
+        const int4 e4 = ld_stream_int4(reinterpret_cast<const int4*>(end) + t);
+        const int l0 = e4.x - s4.x, l1 = e4.y - s4.y, l2 = e4.z - s4.z, l3 = e4.w - s4.w;
+        c[0] = index_cell(s4.x, l0, origin, re, ncells);
+        c[1] = index_cell(s4.y, l1, origin, re, ncells);
+        c[2] = index_cell(s4.z, l2, origin, re, ncells);
+        c[3] = index_cell(s4.w, l3, origin, re, ncells);
+        len = max(max(l0, l1), max(l2, l3));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (base + j < n) {
+                const int sv = start[base + j], l = end[base + j] - sv;
+                c[j] = index_cell(sv, l, origin, re, ncells);
+                len = max(len, l);
+            }
+        }
     }
     const int wl = __reduce_max_sync(kFull, len);
     if (lane == 0 && wl > 0) {
-        const int slot = (int)((i >> 5) & (kLenSlots - 1));
+        const int slot = (int)((t >> 5) & (kLenSlots - 1));
         if (wl > flags[16 + slot]) atomicMax(flags + 16 + slot, wl);
     }
-    const int pc = __shfl_up_sync(kFull, c, 1), nc = __shfl_down_sync(kFull, c, 1);
-    const bool first = lane == 0 || pc != c, last = lane == 31 || nc != c;
-    const unsigned firsts = __ballot_sync(kFull, first);
-    if (c >= 0) {
-        if (first) {
-            const unsigned after = firsts & ~((2u << lane) - 1u);          // run starts after this lane
-            const int run = (after ? __ffs(after) - 1 : 32) - lane;
-            atomicMin(cell_lo + c, (unsigned)i);
-            atomicAdd(cell_cnt + c, (unsigned)run);
+    const int pc = __shfl_up_sync(kFull, c[3], 1), nc = __shfl_down_sync(kFull, c[0], 1);
+    bool first[4], last[4];
+    first[0] = lane == 0 || pc != c[0];
+    first[1] = c[1] != c[0];
+    first[2] = c[2] != c[1];
+    first[3] = c[3] != c[2];
+    last[0] = first[1];
+    last[1] = first[2];
+    last[2] = first[3];
+    last[3] = lane == 31 || nc != c[3];
+    unsigned F[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) F[j] = __ballot_sync(kFull, first[j]);
+    if (first[0] | first[1] | first[2] | first[3] | last[3]) {
+        const unsigned later = (F[0] | F[1] | F[2] | F[3]) & ~((2u << lane) - 1u);     // lanes after mine that start a run
+        int q_next = 128;                                                              // position of the first run start after my lane
+        if (later) {
+            const int l2 = __ffs(later) - 1;
+            const int j2 = ((F[0] >> l2) & 1u) ? 0 : ((F[1] >> l2) & 1u) ? 1 : ((F[2] >> l2) & 1u) ? 2 : 3;
+            q_next = 4 * l2 + j2;
         }
-        if (last) atomicMax(cell_hi + c, (unsigned)i + 1u);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (c[j] >= 0) {
+                if (first[j]) {
+                    int q = q_next;
+#pragma unroll
+                    for (int jj = 3; jj > j; jj--)
+                        if (first[jj]) q = 4 * lane + jj;
+                    atomicMin(cell_lo + c[j], (unsigned)(base + j));
+                    atomicAdd(cell_cnt + c[j], (unsigned)(q - (4 * lane + j)));
+                }
+                if (last[j]) atomicMax(cell_hi + c[j], (unsigned)(base + j) + 1u);
+            }
+        }
     }
 }
 
@@ -510,71 +557,145 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanP
     tile_core(p, s_tile, s_carry, tile);
 }
 
-// FUSED path, K_fused: build the tile's difference array in shared memory straight from the segments.
-__global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const ScanParams p) {
+// FUSED path, K_fused: build each tile's difference array in shared memory straight from the segments.
+// Persistent CTAs (tile += gridDim.x), software-pipelined two tiles deep so that no CTA ever waits on
+// a dependent global load chain: while tile n runs its core, the segments of tile n+1 are already in
+// flight into registers (4 per thread) and so are the cell-table entries of tile n+2.
+constexpr int kSegRegs = 4;
+
+struct CellRegs { unsigned lo, hi, cnt; };
+struct SegRange { unsigned lo, hi, cnt; };
+
+__device__ __forceinline__ void fused_cells_of(const ScanParams& p, int tile, int maxlen, int& lo_cell, int& hi_cell) {
+    // cells whose segments can cover base t0-1 or touch the tile: starts in [t0 - maxlen, t1)
+    const int t0 = p.rs + tile * kTile;
+    const int t1 = min(t0 + kTile, p.re);
+    lo_cell = (max(t0 - maxlen, p.origin) - p.origin) >> kCellShift;
+    hi_cell = min(((t1 - 1 - p.origin) >> kCellShift) + 1, p.ncells);   // exclusive; at most 82 cells
+}
+
+__device__ __forceinline__ CellRegs fused_load_cells(const ScanParams& p, const BatchDesc& bd, int tile, int maxlen) {
+    CellRegs r = {0xffffffffu, 0u, 0u};
+    if (tile < p.num_tiles) {
+        int lo_cell, hi_cell;
+        fused_cells_of(p, tile, maxlen, lo_cell, hi_cell);
+        const int c = lo_cell + (int)threadIdx.x;
+        if (c < hi_cell) { r.lo = bd.cell_lo[c]; r.hi = bd.cell_hi[c]; r.cnt = bd.cell_cnt[c]; }
+    }
+    return r;
+}
+
+__device__ __forceinline__ void fused_reduce_cells(const CellRegs& r, unsigned (*s_rng)[kWarps]) {
+    const unsigned l = __reduce_min_sync(kFull, r.lo), h = __reduce_max_sync(kFull, r.hi), k = __reduce_add_sync(kFull, r.cnt);
+    if ((threadIdx.x & 31) == 0) { const int w = threadIdx.x >> 5; s_rng[0][w] = l; s_rng[1][w] = h; s_rng[2][w] = k; }
+}
+
+__device__ __forceinline__ SegRange fused_combine(unsigned (*s_rng)[kWarps]) {
+    SegRange g = {0xffffffffu, 0u, 0u};
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) { g.lo = min(g.lo, s_rng[0][w]); g.hi = max(g.hi, s_rng[1][w]); g.cnt += s_rng[2][w]; }
+    return g;
+}
+
+__device__ __forceinline__ bool fused_out_of_order(const SegRange& g) {
+    return g.hi > g.lo && (unsigned long long)(g.hi - g.lo) > 8ull * g.cnt + 4096ull;
+}
+
+// one segment into the tile [t0,t1): +1/-1 in shared memory, or +1 carried in when it covers base t0-1
+__device__ __forceinline__ void fused_apply(const ScanParams& p, int* s_tile, int t0, int t1, int s, int e, int& carry) {
+    const int sc = max(s, p.rs), ec = min(e, p.re);                    // clipped to the region like the general path
+    if (sc < ec && sc < t1 && ec >= t0) {
+        if (sc < t0) carry++;
+        else atomicAdd(s_tile + swz_elem(sc - t0), 1);
+        if (ec - t0 < kTile) atomicAdd(s_tile + swz_elem(ec - t0), -1);
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads, 3) depth_fused_kernel(const ScanParams p) {
     __shared__ __align__(16) int s_tile[kTile];
     __shared__ int s_carry[kWarps];
-    __shared__ int s_len[kWarps];
-    __shared__ unsigned s_lo[kMaxBatches][kWarps], s_hi[kMaxBatches][kWarps], s_cnt[kMaxBatches][kWarps];
+    __shared__ unsigned s_rng[3][kWarps];
+    __shared__ unsigned s_rng2[3][kWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
+    const int G = gridDim.x;
 
+    // longest segment (1024 slots written by K_index); segments longer than the look-back go the general way
     int maxlen = 0;
 #pragma unroll
     for (int k = 0; k < kLenSlots / kScanThreads; k++) maxlen = max(maxlen, p.flags[16 + tid + k * kScanThreads]);
     maxlen = __reduce_max_sync(kFull, maxlen);
-    if (lane == 0) s_len[warp] = maxlen;
-#pragma unroll
-    for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);
+    if (lane == 0) s_carry[warp] = maxlen;
     __syncthreads();
     maxlen = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; w++) maxlen = max(maxlen, s_len[w]);
-    if (maxlen > kMaxLookback) {                                        // the general path handles long segments
-        if (tile == 0 && tid == 0) p.header[3] = 1;
+    for (int w = 0; w < kWarps; w++) maxlen = max(maxlen, s_carry[w]);
+    __syncthreads();
+    if (maxlen > kMaxLookback) {
+        if (blockIdx.x == 0 && tid == 0) p.header[3] = 1;
         return;
     }
 
-    // cells whose segments can cover base t0-1 or touch the tile: starts in [t0 - maxlen, t1)
-    const int t0 = p.rs + tile * kTile;                                 // absolute tile span [t0,t1)
-    const int t1 = min(t0 + kTile, p.re);
-    const int lo_cell = (max(t0 - maxlen, p.origin) - p.origin) >> kCellShift;
-    const int hi_cell = min(((t1 - 1 - p.origin) >> kCellShift) + 1, p.ncells);    // exclusive; <= 82 cells
-    for (int b = 0; b < p.n_batches; b++) {
-        unsigned l = 0xffffffffu, h = 0, k = 0;
-        const int cidx = lo_cell + tid;
-        if (cidx < hi_cell) { l = p.batch[b].cell_lo[cidx]; h = p.batch[b].cell_hi[cidx]; k = p.batch[b].cell_cnt[cidx]; }
-        l = __reduce_min_sync(kFull, l);
-        h = __reduce_max_sync(kFull, h);
-        k = __reduce_add_sync(kFull, k);
-        if (lane == 0) { s_lo[b][warp] = l; s_hi[b][warp] = h; s_cnt[b][warp] = k; }
-    }
+    const BatchDesc& b0 = p.batch[0];
+    const int* __restrict__ bs = b0.start;
+    const int* __restrict__ be = b0.end;
+    int tile = blockIdx.x;
+
+    // ---- pipeline prologue: range and segments of the first tile, cell entries of the second
+    CellRegs cells = fused_load_cells(p, b0, tile, maxlen);
+    fused_reduce_cells(cells, s_rng);
     __syncthreads();
-    int carry = 0;                       // segments covering base t0-1: the depth carried into the tile
-    for (int b = 0; b < p.n_batches; b++) {
-        unsigned lo = 0xffffffffu, hi = 0, cnt = 0;
+    SegRange cur = fused_combine(s_rng);
+    int ss[kSegRegs], se[kSegRegs];
 #pragma unroll
-        for (int w = 0; w < kWarps; w++) { lo = min(lo, s_lo[b][w]); hi = max(hi, s_hi[b][w]); cnt += s_cnt[b][w]; }
-        if (hi <= lo) continue;                                         // no segment starts in these cells
-        if ((unsigned long long)(hi - lo) > 8ull * cnt + 4096ull) {      // not in BAM order: let the general path do it
-            if (tid == 0) p.header[3] = 1;
-            return;                                                     // uniform: every thread sees the same lo/hi/cnt
-        }
-        const int* __restrict__ bs = p.batch[b].start;
-        const int* __restrict__ be = p.batch[b].end;
-        for (unsigned i = lo + tid; i < hi; i += kScanThreads) {
-            const int sc = max(bs[i], p.rs), ec = min(be[i], p.re);     // clipped to the region like the general path
-            if (sc < ec && sc < t1 && ec >= t0) {
-                if (sc < t0) carry++;                                   // covers t0-1 (and the tile from its first base, if ec > t0)
-                else atomicAdd(s_tile + swz_elem(sc - t0), 1);
-                if (ec - t0 < kTile) atomicAdd(s_tile + swz_elem(ec - t0), -1);
-            }
-        }
+    for (int j = 0; j < kSegRegs; j++) {
+        const unsigned i = cur.lo + tid + j * kScanThreads;
+        const bool ok = i < cur.hi;
+        ss[j] = ok ? bs[i] : 0;
+        se[j] = ok ? be[i] : 0;
     }
-    carry = __reduce_add_sync(kFull, carry);
-    if (lane == 0) s_carry[warp] = carry;
-    __syncthreads();
-    tile_core(p, s_tile, s_carry, tile);
+    cells = fused_load_cells(p, b0, tile + G, maxlen);
+
+    for (; tile < p.num_tiles; tile += G) {
+        const int t0 = p.rs + tile * kTile, t1 = min(t0 + kTile, p.re);
+#pragma unroll
+        for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);
+        __syncthreads();                                                // previous core finished everywhere; tile is zero
+        if (fused_out_of_order(cur)) {                                  // uniform: every thread holds the same range
+            if (tid == 0) p.header[3] = 1;
+            return;
+        }
+        int carry = 0;
+#pragma unroll
+        for (int j = 0; j < kSegRegs; j++) fused_apply(p, s_tile, t0, t1, ss[j], se[j], carry);
+        for (unsigned i = cur.lo + tid + kSegRegs * kScanThreads; i < cur.hi; i += kScanThreads)   // deep tiles only
+            fused_apply(p, s_tile, t0, t1, bs[i], be[i], carry);
+        for (int b = 1; b < p.n_batches; b++) {                         // further batches: not pipelined
+            const BatchDesc& bd = p.batch[b];
+            fused_reduce_cells(fused_load_cells(p, bd, tile, maxlen), s_rng2);
+            __syncthreads();
+            const SegRange g = fused_combine(s_rng2);
+            __syncthreads();
+            if (fused_out_of_order(g)) {
+                if (tid == 0) p.header[3] = 1;
+                return;
+            }
+            for (unsigned i = g.lo + tid; i < g.hi; i += kScanThreads) fused_apply(p, s_tile, t0, t1, bd.start[i], bd.end[i], carry);
+        }
+        carry = __reduce_add_sync(kFull, carry);
+        if (lane == 0) s_carry[warp] = carry;
+        fused_reduce_cells(cells, s_rng);                               // range of the next tile
+        __syncthreads();
+        cur = fused_combine(s_rng);
+#pragma unroll
+        for (int j = 0; j < kSegRegs; j++) {                            // next tile's segments: in flight during the core
+            const unsigned i = cur.lo + tid + j * kScanThreads;
+            const bool ok = i < cur.hi;
+            ss[j] = ok ? bs[i] : 0;
+            se[j] = ok ? be[i] : 0;
+        }
+        cells = fused_load_cells(p, b0, tile + 2 * G, maxlen);          // and the tile after that one's cell entries
+        tile_core(p, s_tile, s_carry, tile);
+    }
 }
 
 // K_gather: one warp per tile moves its runs from claim order to position order.  The ordered offset of
@@ -755,7 +876,7 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
             p.batch[bi].cell_cnt = cnt_all + bi * (size_t)ncells;
             p.batch[bi].n = (int)b.n;
             gl_prof_scope prof(ctx, "depth_index_kernel");
-            depth_index_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, ctx->stream>>>(
+            depth_index_kernel<<<(unsigned)(((b.n + 3) / 4 + 255) / 256), 256, 0, ctx->stream>>>(
                 p.batch[bi].start, p.batch[bi].end, b.n, origin, (int)ctx->re, ncells, lo_all + bi * (size_t)ncells,
                 hi_all + bi * (size_t)ncells, cnt_all + bi * (size_t)ncells, static_cast<int*>(ctx->sflags.p));
             GL_LAUNCHED(ctx, 1);
@@ -790,7 +911,8 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
         }
         {
             gl_prof_scope prof(ctx, fused ? "depth_fused_kernel" : "depth_scan_kernel");
-            if (fused) depth_fused_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p);
+            const unsigned fused_grid = (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 3);
+            if (fused) depth_fused_kernel<<<fused_grid, kScanThreads, 0, ctx->stream>>>(p);
             else depth_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p);
         }
         GL_LAUNCHED(ctx, 1);
