@@ -86,6 +86,24 @@ _proto("gl_depth_classes", C.c_int, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.
 _proto("gl_depth_perbase", C.c_int, _vp, _vp)
 _proto("gl_depth_region", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_indexcov_sizes", C.c_int, _vp, _vp, _vp, C.c_int32, _vp, _vp)
+_proto("gl_indexcov_scale", C.c_int, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_indexcov_normalize", C.c_int, _vp, _vp, C.c_int64, C.c_double, _vp)
+_proto("gl_indexcov_cohort", C.c_int, _vp, _vp, _vp, C.c_int32, _vp, _vp)
+_proto("gl_indexcov_cohort_device", C.c_int, _vp, _vp, _vp, C.c_int32, _vp, _vp)
+_proto("gl_indexcov_counts", C.c_int, _vp, _vp, C.c_int64, _vp)
+_proto("gl_indexcov_bins", C.c_int, _vp, _vp, C.c_int64, C.c_int64, _vp)
+_proto("gl_indexcov_counts_batch", C.c_int, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp)
+_proto("gl_indexcov_counts_batch_device", C.c_int, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp)
+_proto("gl_indexcov_xnorm", C.c_int, _vp, _vp, _vp, C.c_int32, C.c_int32)
+_proto("gl_bincount_i32", C.c_int, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp)
+_proto("gl_depthwed_aggregate", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp,
+       C.c_int64, _i64p)
+_proto("gl_depthwed_aggregate_device", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp)
+_proto("gl_comm_unique_id", C.c_int, _vp)
+_proto("gl_comm_init", C.c_int, _vp, _vp, C.c_int, C.c_int)
+_proto("gl_comm_destroy", C.c_int, _vp)
+_proto("gl_allgather_device", C.c_int, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_format_chunk", C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int64, _vp, _vp,
        C.c_int64, C.POINTER(_vp), _i64p, C.POINTER(_vp), _i64p)
 _proto("gl_free_text", None, _vp)
@@ -308,3 +326,98 @@ class Ctx:
                                      _ptr(s), s.size, C.byref(nw), _ptr(r0), _ptr(rc_), min(r0.size, rc_.size),
                                      C.byref(nr)))
         return s[: nw.value], r0[: nr.value], rc_[: nr.value]
+
+    # ---- indexcov
+    def indexcov_sizes(self, voff: np.ndarray, ref_ptr: np.ndarray):
+        voff, ref_ptr = _as(voff, np.uint64), _as(ref_ptr, np.int64)
+        n_refs = ref_ptr.size - 1
+        size_ptr = np.zeros(n_refs + 1, np.int64)
+        sizes = np.empty(max(int(voff.size), 1), np.int64)
+        self._ck(lib.gl_indexcov_sizes(self.h, _ptr(voff), _ptr(ref_ptr), n_refs, _ptr(sizes), _ptr(size_ptr)))
+        return sizes[: size_ptr[-1]], size_ptr
+
+    def indexcov_scale(self, sizes: np.ndarray) -> int:
+        sizes = _as(sizes, np.int64)
+        m = C.c_int64(0)
+        self._ck(lib.gl_indexcov_scale(self.h, _ptr(sizes), sizes.size, C.byref(m)))
+        return m.value
+
+    def indexcov_normalize(self, sizes: np.ndarray, median: float) -> np.ndarray:
+        sizes = _as(sizes, np.int64)
+        out = np.empty(sizes.size, np.float32)
+        self._ck(lib.gl_indexcov_normalize(self.h, _ptr(sizes), sizes.size, float(median), _ptr(out)))
+        return out
+
+    def indexcov_cohort(self, sizes: np.ndarray, sample_ptr: np.ndarray, want_depth: bool = True):
+        sizes, sample_ptr = _as(sizes, np.int64), _as(sample_ptr, np.int64)
+        S = sample_ptr.size - 1
+        med = np.empty(S, np.float64)
+        dep = np.empty(sizes.size, np.float32) if want_depth else None
+        self._ck(lib.gl_indexcov_cohort(self.h, _ptr(sizes), _ptr(sample_ptr), S, _ptr(med), _ptr(dep)))
+        return med, dep
+
+    def indexcov_counts(self, depth: np.ndarray, counts: Optional[np.ndarray] = None) -> np.ndarray:
+        depth = _as(depth, np.float32)
+        if counts is None:
+            counts = np.zeros(INDEXCOV_SLOTS, np.int32)
+        self._ck(lib.gl_indexcov_counts(self.h, _ptr(depth), depth.size, _ptr(counts)))
+        return counts
+
+    def indexcov_bins(self, depth: np.ndarray, longest: int, out4: Optional[np.ndarray] = None) -> np.ndarray:
+        depth = _as(depth, np.float32)
+        if out4 is None:
+            out4 = np.zeros(4, np.int64)
+        self._ck(lib.gl_indexcov_bins(self.h, _ptr(depth), depth.size, longest, _ptr(out4)))
+        return out4
+
+    def indexcov_counts_batch(self, depth: np.ndarray, seg_ptr: np.ndarray, longest: Optional[np.ndarray] = None):
+        depth, seg_ptr = _as(depth, np.float32), _as(seg_ptr, np.int64)
+        n = seg_ptr.size - 1
+        lg = None if longest is None else _as(longest, np.int64)
+        counts = np.empty((n, INDEXCOV_SLOTS), np.int32)
+        bins = np.empty((n, 4), np.int64)
+        self._ck(lib.gl_indexcov_counts_batch(self.h, _ptr(depth), _ptr(seg_ptr), _ptr(lg), n, _ptr(counts), _ptr(bins)))
+        return counts, bins
+
+    def indexcov_xnorm(self, depths: np.ndarray, lens: np.ndarray) -> np.ndarray:
+        d = np.ascontiguousarray(depths, np.float32).copy()
+        lens = _as(lens, np.int32)
+        S, T = d.shape
+        self._ck(lib.gl_indexcov_xnorm(self.h, _ptr(d), _ptr(lens), S, T))
+        return d
+
+    # ---- covstats / depthwed
+    def bincount(self, v: np.ndarray, lo: int, hi: int) -> np.ndarray:
+        v = _as(v, np.int32)
+        h = np.empty(hi - lo, np.uint64)
+        self._ck(lib.gl_bincount_i32(self.h, _ptr(v), v.size, lo, hi, _ptr(h)))
+        return h
+
+    def depthwed_aggregate(self, means: np.ndarray, starts, ends, chrom_id, size: int):
+        means = np.ascontiguousarray(means, np.float64)
+        S, R = means.shape
+        starts, ends, chrom_id = _as(starts, np.int32), _as(ends, np.int32), _as(chrom_id, np.int32)
+        cap = max(R, 1)
+        o_s, o_e, o_c = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32)
+        out = np.empty((cap, S), np.int64)
+        n = C.c_int64(0)
+        self._ck(lib.gl_depthwed_aggregate(self.h, _ptr(means), S, R, _ptr(starts), _ptr(ends), _ptr(chrom_id), size,
+                                           _ptr(o_s), _ptr(o_e), _ptr(o_c), _ptr(out), cap, C.byref(n)))
+        k = n.value
+        return o_s[:k], o_e[:k], o_c[:k], out[:k]
+
+    # ---- multi-GPU
+    def comm_init(self, id128: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(id128)
+        self._ck(lib.gl_comm_init(self.h, C.cast(buf, _vp), rank, world))
+
+    def allgather_device(self, d_send: DevBuf, d_recv: DevBuf, nbytes: int):
+        self._ck(lib.gl_allgather_device(self.h, d_send.ptr, d_recv.ptr, nbytes))
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    rc = lib.gl_comm_unique_id(C.cast(buf, _vp))
+    if rc != GL_OK:
+        raise GlError(rc, lib.gl_last_error(None).decode())
+    return bytes(buf)

@@ -13,7 +13,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;     // ncclSuccess == 0
-enum { kNcclInt32 = 2 };      // ncclInt32 / ncclInt in nccl.h's ncclDataType_t
+enum { kNcclInt8 = 0 };       // ncclInt8 / ncclChar in nccl.h's ncclDataType_t
 
 struct NcclApi {
     void* handle = nullptr;
@@ -92,11 +92,11 @@ int gl_comm_destroy(gl_ctx* ctx) {
     return GL_OK;
 }
 
-int gl_allgather_i32_device(gl_ctx* ctx, const int32_t* d_send, int32_t* d_recv, int64_t count) {
+int gl_allgather_device(gl_ctx* ctx, const void* d_send, void* d_recv, int64_t bytes) {
     GL_CHECK(gl_use(ctx));
-    if (!ctx->nccl) return gl_fail(ctx, GL_ESTATE, "gl_allgather_i32_device: call gl_comm_init first");
-    if (count < 0 || !d_send || !d_recv) return gl_fail(ctx, GL_EINVAL, "gl_allgather_i32_device: bad argument");
-    GL_NCCL(ctx, g_nccl.AllGather(d_send, d_recv, (size_t)count, kNcclInt32, static_cast<ncclComm_t>(ctx->nccl), ctx->stream));
+    if (!ctx->nccl) return gl_fail(ctx, GL_ESTATE, "gl_allgather_device: call gl_comm_init first");
+    if (bytes < 0 || !d_send || !d_recv) return gl_fail(ctx, GL_EINVAL, "gl_allgather_device: bad argument");
+    GL_NCCL(ctx, g_nccl.AllGather(d_send, d_recv, (size_t)bytes, kNcclInt8, static_cast<ncclComm_t>(ctx->nccl), ctx->stream));
     GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GL_OK;
 }

@@ -1,0 +1,661 @@
+// indexcov.cu — `goleft indexcov` arithmetic on sm_100a, plus the small covstats / depthwed kernels.
+//
+//   I1  ic_sizes_kernel     BAI linear-index virtual offsets -> per-tile sizes   (indexcov/types.go:45-82)
+//   I2+I3 ic_cohort_kernel  ONE kernel, one CTA per sample: capped weighted median by two radix selects
+//                           over the sample's tiles (no sort), then normalised depth  (indexcov.go:83-151)
+//   I4+I5 ic_counts_kernel  per (sample, chromosome) segment: 70-slot histogram + in/out/hi/low counters
+//                                                                            (indexcov.go:170-177,1050-1078)
+//   I7  ic_xnorm_kernel     cross-sample normalisation, sequential in tile j, parallel over samples, with the
+//                           float64 mean reproduced bit-exactly (order-free when provably exact, else ordered)
+//   V2  bincount_kernel     shared-memory privatised histogram (covstats/covstats.go:202-217)
+//   W1  depthwed_kernel     int(0.5+mean), group-sum, sample-major -> row-major transpose (depthwed.go:93-157)
+//
+// Floating point follows Go on amd64: no fused multiply-add (the library is compiled with --fmad=false and
+// the hot expressions use the explicit _rn intrinsics), float64 division rounded to float32 exactly once.
+#include "gl_common.cuh"
+#include <string.h>
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------ I1
+__global__ void __launch_bounds__(256) ic_sizes_kernel(const unsigned long long* __restrict__ voff,
+                                                      const long long* __restrict__ ref_ptr,
+                                                      const long long* __restrict__ size_ptr, int n_refs,
+                                                      long long* __restrict__ sizes, int* __restrict__ neg_flag) {
+    const int r = blockIdx.x;
+    if (r >= n_refs) return;
+    const long long a = ref_ptr[r], b = ref_ptr[r + 1], o = size_ptr[r];
+    for (long long k = threadIdx.x; k + 1 < b - a; k += blockDim.x) {
+        const long long d = (long long)voff[a + k + 1] - (long long)voff[a + k];   // vOffset = File<<16|Block = raw u64
+        if (d < 0) *neg_flag = 1;
+        sizes[o + k] = d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ I2 + I3
+constexpr int kCohortThreads = 512;
+
+// k-th smallest (0-based) of n non-negative int64 by MSB-first radix descent, 8 bits a pass
+__device__ long long block_select_kth(const long long* __restrict__ v, long long n, long long k, unsigned* s_hist,
+                                      unsigned long long* s_bcast) {
+    unsigned long long prefix = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long x = (unsigned long long)v[i];
+            if ((x & himask) == prefix) atomicAdd(&s_hist[(x >> shift) & 255], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long acc = 0;
+            int d = 0;
+            for (; d < 256; d++) {
+                if (acc + (long long)s_hist[d] > k) break;
+                acc += s_hist[d];
+            }
+            s_bcast[0] = (unsigned long long)d;
+            s_bcast[1] = (unsigned long long)acc;
+        }
+        __syncthreads();
+        prefix |= s_bcast[0] << shift;
+        k -= (long long)s_bcast[1];
+        __syncthreads();
+    }
+    return (long long)prefix;
+}
+
+// smallest value x with  sum_{v<=x} min(v,cap)  >  half   (weights = capped values); total > half guaranteed
+__device__ long long block_select_weighted(const long long* __restrict__ v, long long n, long long cap, long long half,
+                                           unsigned long long* s_w, unsigned long long* s_bcast) {
+    unsigned long long prefix = 0;
+    long long below = 0;                       // weight of everything smaller than the current prefix range
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_w[i] = 0;
+        __syncthreads();
+        const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long x = (unsigned long long)v[i];
+            if ((x & himask) == prefix) {
+                const long long w = min((long long)x, cap);
+                if (w) atomicAdd(&s_w[(x >> shift) & 255], (unsigned long long)w);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long acc = below;
+            int d = 0;
+            for (; d < 255; d++) {
+                if (acc + (long long)s_w[d] > half) break;
+                acc += (long long)s_w[d];
+            }
+            s_bcast[0] = (unsigned long long)d;
+            s_bcast[1] = (unsigned long long)acc;
+        }
+        __syncthreads();
+        prefix |= s_bcast[0] << shift;
+        below = (long long)s_bcast[1];
+        __syncthreads();
+    }
+    return (long long)prefix;
+}
+
+__global__ void __launch_bounds__(kCohortThreads) ic_cohort_kernel(const long long* __restrict__ sizes,
+                                                                   const long long* __restrict__ sample_ptr, int S,
+                                                                   double* __restrict__ medians, float* __restrict__ depth_out) {
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_w[256];
+    __shared__ unsigned long long s_bcast[2];
+    __shared__ long long s_red[kCohortThreads / 32];
+    const int smp = blockIdx.x;
+    if (smp >= S) return;
+    const long long a = sample_ptr[smp], n = sample_ptr[smp + 1] - a;
+    const long long* v = sizes + a;
+    if (n <= 0) { if (threadIdx.x == 0) medians[smp] = 0.0; return; }
+
+    // n98 = sorted[int(0.98*n)]                                              (indexcov.go:111)
+    const long long k98 = (long long)(0.98 * (double)n);
+    const long long n98 = block_select_kth(v, n, k98, s_hist, s_bcast);
+
+    // total = sum min(s, n98)                                                (:112-118)
+    long long part = 0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) part += min(v[i], n98);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    long long total = 0;
+    for (int w = 0; w < kCohortThreads / 32; w++) total += s_red[w];
+    __syncthreads();
+
+    // first sorted position whose capped cumulative sum exceeds total/2      (:119-124)
+    long long med;
+    if (total == 0) {
+        // cumsum never exceeds 0: sort.Search returns len, the clamp picks the largest element
+        long long mx = 0;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) mx = max(mx, v[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        med = 0;
+        for (int w = 0; w < kCohortThreads / 32; w++) med = max(med, s_red[w]);
+    } else {
+        med = block_select_weighted(v, n, n98, total / 2, s_w, s_bcast);
+    }
+    const double dm = (double)med;
+    if (threadIdx.x == 0) medians[smp] = dm;
+
+    // depth = float32(float64(o)/median), capped at 50000                    (:129-151)
+    if (depth_out) {
+        float* out = depth_out + a;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            float d = (med == 0) ? 0.0f : __double2float_rn(__ddiv_rn((double)v[i], dm));
+            if (d > 50000.0f) d = 50000.0f;
+            out[i] = d;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ic_normalize_kernel(const long long* __restrict__ sizes, long long n, double median,
+                                                          float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d = __double2float_rn(__ddiv_rn((double)sizes[i], median));
+    if (d > 50000.0f) d = 50000.0f;
+    out[i] = d;
+}
+
+// ------------------------------------------------------------------------------------------------ I4 + I5
+// one CTA per segment (a sample's tiles on one chromosome)
+__global__ void __launch_bounds__(256) ic_counts_kernel(const float* __restrict__ depth, const long long* __restrict__ seg_ptr,
+                                                       const long long* __restrict__ longest, int n_seg,
+                                                       int* __restrict__ counts70, long long* __restrict__ bins4) {
+    __shared__ int s_cnt[GL_INDEXCOV_SLOTS];
+    __shared__ int s_bin[4];
+    const int seg = blockIdx.x;
+    if (seg >= n_seg) return;
+    for (int i = threadIdx.x; i < GL_INDEXCOV_SLOTS; i += blockDim.x) s_cnt[i] = 0;
+    if (threadIdx.x < 4) s_bin[threadIdx.x] = 0;
+    __syncthreads();
+    const long long a = seg_ptr[seg], n = seg_ptr[seg + 1] - a;
+    const float K = 46.66666793823242f;                      // float32(70 * float32(2/3)), indexcov.go:153-157,175
+    int b_out = 0, b_low = 0, b_hi = 0, b_in = 0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float d = depth[a + i];
+        const float v = __fadd_rn(__fmul_rn(d, K), 0.5f);
+        int slot = __float2int_rz(v);                       // Go int(f): truncation
+        slot = slot < GL_INDEXCOV_SLOTS ? (slot < 0 ? 0 : slot) : GL_INDEXCOV_SLOTS - 1;
+        atomicAdd(&s_cnt[slot], 1);
+        const float c = d > 8.0f ? 8.0f : d;                // MaxCN clip, :694-697
+        if (c < 0.85f || c > 1.15f) {                       // counter.count, :1053-1066
+            b_out++;
+            if (c > 1.15f) b_hi++;
+            else if (c < 0.15f) b_low++;
+        } else {
+            b_in++;
+        }
+    }
+    b_out = __reduce_add_sync(kFull, b_out); b_low = __reduce_add_sync(kFull, b_low);
+    b_hi = __reduce_add_sync(kFull, b_hi); b_in = __reduce_add_sync(kFull, b_in);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_bin[0], b_out); atomicAdd(&s_bin[1], b_low); atomicAdd(&s_bin[2], b_hi); atomicAdd(&s_bin[3], b_in);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < GL_INDEXCOV_SLOTS; i += blockDim.x) counts70[(size_t)seg * GL_INDEXCOV_SLOTS + i] = s_cnt[i];
+    if (threadIdx.x == 0) {
+        const long long miss = longest ? max(0ll, longest[seg] - n) : 0;   // c.out += n - i; c.low += n - i  (:1076-1077)
+        bins4[(size_t)seg * 4 + 0] = s_bin[0] + miss;
+        bins4[(size_t)seg * 4 + 1] = s_bin[1] + miss;
+        bins4[(size_t)seg * 4 + 2] = s_bin[2];
+        bins4[(size_t)seg * 4 + 3] = s_bin[3];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ I7
+// One CTA; threads own samples (i = tid, tid+blockDim, ...).  For every tile j the float64 mean over
+// samples of d[j], d[j-1], d[j+1] must equal the reference's sequential sum bit for bit.  A float64 sum of
+// float32 addends is exact — hence order-free — when (max exponent + log2(count) + 1) - (min ulp exponent)
+// <= 52; the block checks that per tile and otherwise thread 0 redoes the sum in the reference's order.
+constexpr int kXnThreads = 1024;
+
+__device__ __forceinline__ int f32_ulp_exp(float v) {       // exponent of the unit in the last place
+    int e = (int)((__float_as_uint(v) >> 23) & 0xff);
+    return (e == 0 ? 1 : e) - 127 - 23;
+}
+
+__global__ void __launch_bounds__(kXnThreads) ic_xnorm_kernel(float* __restrict__ depths, const int* __restrict__ lens, int S, int T,
+                                                             int max_len) {
+    __shared__ double s_sum[kXnThreads / 32];
+    __shared__ int s_cnt[kXnThreads / 32], s_emax[kXnThreads / 32], s_emin[kXnThreads / 32];
+    __shared__ double s_m;
+    __shared__ int s_skip;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = 0; j < max_len; j++) {
+        double part = 0;
+        int cnt = 0, emax = -1000, emin = 1000;
+        for (int i = tid; i < S; i += kXnThreads) {
+            const int len = lens[i];
+            if (len > j) {
+                const float* d = depths + (size_t)i * T;
+                float a = d[j];
+                part += (double)a; cnt++;
+                if (a != 0) { emax = max(emax, f32_ulp_exp(a) + 24); emin = min(emin, f32_ulp_exp(a)); }
+                if (j > 0) { a = d[j - 1]; part += (double)a; cnt++; if (a != 0) { emax = max(emax, f32_ulp_exp(a) + 24); emin = min(emin, f32_ulp_exp(a)); } }
+                if (j < len - 1) { a = d[j + 1]; part += (double)a; cnt++; if (a != 0) { emax = max(emax, f32_ulp_exp(a) + 24); emin = min(emin, f32_ulp_exp(a)); } }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+        cnt = __reduce_add_sync(kFull, cnt);
+        emax = __reduce_max_sync(kFull, emax);
+        emin = __reduce_min_sync(kFull, emin);
+        if (lane == 0) { s_sum[warp] = part; s_cnt[warp] = cnt; s_emax[warp] = emax; s_emin[warp] = emin; }
+        __syncthreads();
+        if (tid == 0) {
+            double m = 0; int n = 0, ex = -1000, en = 1000;
+            for (int w = 0; w < kXnThreads / 32; w++) { m += s_sum[w]; n += s_cnt[w]; ex = max(ex, s_emax[w]); en = min(en, s_emin[w]); }
+            int lg = 0;
+            while ((1 << lg) < n) lg++;
+            const bool exact = (en == 1000) || (ex + lg + 1 - en <= 52);
+            if (!exact) {                                   // reproduce the reference's order (indexcov.go:566-574)
+                m = 0;
+                for (int i = 0; i < S; i++) {
+                    const int len = lens[i];
+                    if (len > j) {
+                        const float* d = depths + (size_t)i * T;
+                        m += (double)d[j];
+                        if (j > 0) m += (double)d[j - 1];
+                        if (j < len - 1) m += (double)d[j + 1];
+                    }
+                }
+            }
+            int skip = n < 3 * S - 4;                       // :577
+            if (!skip) {
+                m = __ddiv_rn(m, (double)n);
+                if (m < 0.1) skip = 1;
+            }
+            s_m = m;
+            s_skip = skip;
+        }
+        __syncthreads();
+        if (!s_skip) {
+            const float m32 = __double2float_rn(s_m);
+            for (int i = tid; i < S; i += kXnThreads) {
+                const int len = lens[i];
+                if (len > j) {
+                    float* d = depths + (size_t)i * T;
+                    float x = __fdiv_rn(d[j], m32);
+                    if (j > 2 && j < len - 3) {
+                        float a = __fadd_rn(d[j - 3], d[j - 2]);
+                        a = __fadd_rn(a, d[j - 1]);
+                        a = __fadd_rn(a, x);
+                        a = __fadd_rn(a, __fdiv_rn(d[j + 1], m32));
+                        a = __fadd_rn(a, __fdiv_rn(d[j + 2], m32));
+                        a = __fadd_rn(a, __fdiv_rn(d[j + 3], m32));
+                        x = __fmul_rn(0.14285714924335479736328125f, a);
+                    }
+                    d[j] = x;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ V2
+constexpr int kBinSmem = 8192;
+__global__ void __launch_bounds__(256) bincount_kernel(const int* __restrict__ v, long long n, int lo, int hi,
+                                                      unsigned long long* __restrict__ hist) {
+    __shared__ unsigned s_h[kBinSmem];
+    const int nb = hi - lo;
+    const bool priv = nb <= kBinSmem;
+    if (priv) {
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) s_h[i] = 0;
+        __syncthreads();
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = v[i];
+        if (x >= lo && x < hi) {
+            if (priv) atomicAdd(&s_h[x - lo], 1u);
+            else atomicAdd(&hist[x - lo], 1ull);
+        }
+    }
+    if (priv) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb; i += blockDim.x)
+            if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ W1
+// means: S x R sample-major.  Group g sums rows [grp[g], grp[g+1]) of int(0.5+mean); out is n_out x S
+// row-major.  A 32x32 tile goes through shared memory so both the reads and the writes are coalesced.
+__global__ void __launch_bounds__(256) depthwed_kernel(const double* __restrict__ means, int S, long long R,
+                                                      const long long* __restrict__ grp, long long n_out, int simple,
+                                                      long long* __restrict__ out) {
+    __shared__ long long s_t[32][33];
+    const long long g0 = (long long)blockIdx.x * 32;
+    const int s0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    for (int k = ty; k < 32; k += 8) {                             // k: sample inside the tile, tx: group
+        const int s = s0 + k;
+        const long long g = g0 + tx;
+        long long acc = 0;
+        if (s < S && g < n_out) {
+            const long long a = simple ? g : grp[g], b = simple ? g + 1 : grp[g + 1];
+            for (long long r = a; r < b; r++) acc += (long long)__double2ll_rz(__dadd_rn(0.5, means[(size_t)s * R + r]));
+        }
+        s_t[k][tx] = acc;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {                             // k: group inside the tile, tx: sample
+        const long long g = g0 + k;
+        const int s = s0 + tx;
+        if (s < S && g < n_out) out[(size_t)g * S + s] = s_t[tx][k];
+    }
+}
+
+// small helper: a scratch device buffer per call site
+int dev_tmp(gl_ctx* ctx, gl_buf& b, size_t bytes) { return gl_buf_reserve(ctx, b, bytes ? bytes : 16); }
+
+}  // namespace
+
+extern "C" {
+
+int gl_indexcov_sizes(gl_ctx* ctx, const uint64_t* voff, const int64_t* ref_ptr, int32_t n_refs, int64_t* sizes,
+                      int64_t* size_ptr) {
+    GL_CHECK(gl_use(ctx));
+    if (n_refs < 0 || !ref_ptr || !size_ptr || (n_refs > 0 && !voff)) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_sizes: bad argument");
+    size_ptr[0] = 0;
+    for (int32_t r = 0; r < n_refs; r++) {
+        const int64_t ni = ref_ptr[r + 1] - ref_ptr[r];
+        if (ni < 0) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_sizes: ref_ptr not monotone");
+        size_ptr[r + 1] = size_ptr[r] + (ni >= 2 ? ni - 1 : 0);     // types.go:68-72
+    }
+    const int64_t total_v = ref_ptr[n_refs], total_s = size_ptr[n_refs];
+    if (total_s == 0) return GL_OK;
+    if (!sizes) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_sizes: null sizes");
+    gl_buf bv, bp, bs, bo;
+    const size_t pb = (size_t)(n_refs + 1) * 8;
+    GL_CHECK(dev_tmp(ctx, bv, (size_t)total_v * 8));
+    GL_CHECK(dev_tmp(ctx, bp, pb * 2 + 16));
+    GL_CHECK(dev_tmp(ctx, bs, (size_t)total_s * 8));
+    (void)bo;
+    char* dp = static_cast<char*>(bp.p);
+    int rc = GL_OK;
+    do {
+        if (cudaMemcpyAsync(bv.p, voff, (size_t)total_v * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(dp, ref_ptr, pb, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(dp + pb, size_ptr, pb, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemsetAsync(dp + 2 * pb, 0, 16, ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexcov_sizes: copy failed"); break; }
+        ic_sizes_kernel<<<(unsigned)n_refs, 256, 0, ctx->stream>>>(static_cast<const unsigned long long*>(bv.p),
+                                                                   reinterpret_cast<const long long*>(dp),
+                                                                   reinterpret_cast<const long long*>(dp + pb), n_refs,
+                                                                   static_cast<long long*>(bs.p), reinterpret_cast<int*>(dp + 2 * pb));
+        ctx->launches++;
+        int neg = 0;
+        if (cudaMemcpyAsync(sizes, bs.p, (size_t)total_s * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(&neg, dp + 2 * pb, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexcov_sizes: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        if (neg) rc = gl_fail(ctx, GL_ERANGE, "gl_indexcov_sizes: expected positive change in vOffset");   // types.go:75-77
+    } while (0);
+    cudaFree(bv.p); cudaFree(bp.p); cudaFree(bs.p);
+    return rc;
+}
+
+int gl_indexcov_cohort_device(gl_ctx* ctx, const int64_t* d_sizes, const int64_t* d_sample_ptr, int32_t S,
+                              double* d_medians, float* d_depth_out) {
+    GL_CHECK(gl_use(ctx));
+    if (S < 0 || !d_sizes || !d_sample_ptr || !d_medians) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_cohort_device: bad argument");
+    if (S == 0) return GL_OK;
+    {
+        gl_prof_scope prof(ctx, "ic_cohort_kernel");
+        ic_cohort_kernel<<<(unsigned)S, kCohortThreads, 0, ctx->stream>>>(reinterpret_cast<const long long*>(d_sizes),
+                                                                          reinterpret_cast<const long long*>(d_sample_ptr), S,
+                                                                          d_medians, d_depth_out);
+    }
+    GL_LAUNCHED(ctx, 1);
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+int gl_indexcov_cohort(gl_ctx* ctx, const int64_t* sizes, const int64_t* sample_ptr, int32_t S, double* medians,
+                       float* depth_out) {
+    GL_CHECK(gl_use(ctx));
+    if (S < 0 || !sample_ptr || !medians) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_cohort: bad argument");
+    if (S == 0) return GL_OK;
+    const int64_t total = sample_ptr[S];
+    if (total > 0 && !sizes) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_cohort: null sizes");
+    gl_buf bs, bp, bm, bd;
+    GL_CHECK(dev_tmp(ctx, bs, (size_t)total * 8));
+    GL_CHECK(dev_tmp(ctx, bp, (size_t)(S + 1) * 8));
+    GL_CHECK(dev_tmp(ctx, bm, (size_t)S * 8));
+    if (depth_out) GL_CHECK(dev_tmp(ctx, bd, (size_t)total * 4));
+    int rc = GL_OK;
+    do {
+        if ((total && cudaMemcpyAsync(bs.p, sizes, (size_t)total * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) ||
+            cudaMemcpyAsync(bp.p, sample_ptr, (size_t)(S + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexcov_cohort: H2D failed"); break; }
+        rc = gl_indexcov_cohort_device(ctx, static_cast<const int64_t*>(bs.p), static_cast<const int64_t*>(bp.p), S,
+                                       static_cast<double*>(bm.p), depth_out ? static_cast<float*>(bd.p) : nullptr);
+        if (rc != GL_OK) break;
+        if (cudaMemcpyAsync(medians, bm.p, (size_t)S * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            (depth_out && total && cudaMemcpyAsync(depth_out, bd.p, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexcov_cohort: D2H failed"); break; }
+    } while (0);
+    cudaFree(bs.p); cudaFree(bp.p); cudaFree(bm.p); if (bd.p) cudaFree(bd.p);
+    return rc;
+}
+
+int gl_indexcov_scale(gl_ctx* ctx, const int64_t* sizes, int64_t n, int64_t* median_out) {
+    if (n <= 0 || !sizes || !median_out) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_scale: needs at least one tile (indexcov.go:100-102)");
+    const int64_t ptr[2] = {0, n};
+    double m = 0;
+    GL_CHECK(gl_indexcov_cohort(ctx, sizes, ptr, 1, &m, nullptr));
+    *median_out = (int64_t)m;
+    return GL_OK;
+}
+
+int gl_indexcov_normalize(gl_ctx* ctx, const int64_t* sizes, int64_t n, double median, float* depth_out) {
+    GL_CHECK(gl_use(ctx));
+    if (n < 0 || (n > 0 && (!sizes || !depth_out))) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_normalize: bad argument");
+    if (n == 0) return GL_OK;
+    if (median == 0.0) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_normalize: median is 0 (the reference returns no depths, indexcov.go:140-142)");
+    gl_buf bs, bd;
+    GL_CHECK(dev_tmp(ctx, bs, (size_t)n * 8));
+    GL_CHECK(dev_tmp(ctx, bd, (size_t)n * 4));
+    int rc = GL_OK;
+    do {
+        if (cudaMemcpyAsync(bs.p, sizes, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "H2D failed"); break; }
+        ic_normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(static_cast<const long long*>(bs.p), n, median, static_cast<float*>(bd.p));
+        ctx->launches++;
+        if (cudaMemcpyAsync(depth_out, bd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexcov_normalize: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    cudaFree(bs.p); cudaFree(bd.p);
+    return rc;
+}
+
+int gl_indexcov_counts_batch_device(gl_ctx* ctx, const float* d_depth, const int64_t* d_seg_ptr, const int64_t* d_longest,
+                                    int32_t n_seg, int32_t* d_counts70, int64_t* d_bins4) {
+    GL_CHECK(gl_use(ctx));
+    if (n_seg < 0 || !d_seg_ptr || !d_counts70 || !d_bins4) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_counts_batch_device: bad argument");
+    if (n_seg == 0) return GL_OK;
+    {
+        gl_prof_scope prof(ctx, "ic_counts_kernel");
+        ic_counts_kernel<<<(unsigned)n_seg, 256, 0, ctx->stream>>>(d_depth, reinterpret_cast<const long long*>(d_seg_ptr),
+                                                                   reinterpret_cast<const long long*>(d_longest), n_seg, d_counts70,
+                                                                   reinterpret_cast<long long*>(d_bins4));
+    }
+    GL_LAUNCHED(ctx, 1);
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+int gl_indexcov_counts_batch(gl_ctx* ctx, const float* depth, const int64_t* seg_ptr, const int64_t* longest, int32_t n_seg,
+                             int32_t* counts70, int64_t* bins4) {
+    GL_CHECK(gl_use(ctx));
+    if (n_seg < 0 || !seg_ptr || !counts70 || !bins4) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_counts_batch: bad argument");
+    if (n_seg == 0) return GL_OK;
+    const int64_t total = seg_ptr[n_seg];
+    gl_buf bd, bp, bl, bc, bb;
+    GL_CHECK(dev_tmp(ctx, bd, (size_t)total * 4));
+    GL_CHECK(dev_tmp(ctx, bp, (size_t)(n_seg + 1) * 8));
+    GL_CHECK(dev_tmp(ctx, bl, (size_t)n_seg * 8));
+    GL_CHECK(dev_tmp(ctx, bc, (size_t)n_seg * GL_INDEXCOV_SLOTS * 4));
+    GL_CHECK(dev_tmp(ctx, bb, (size_t)n_seg * 32));
+    int rc = GL_OK;
+    do {
+        if ((total && cudaMemcpyAsync(bd.p, depth, (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) ||
+            cudaMemcpyAsync(bp.p, seg_ptr, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            (longest && cudaMemcpyAsync(bl.p, longest, (size_t)n_seg * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexcov_counts_batch: H2D failed"); break; }
+        rc = gl_indexcov_counts_batch_device(ctx, static_cast<const float*>(bd.p), static_cast<const int64_t*>(bp.p),
+                                             longest ? static_cast<const int64_t*>(bl.p) : nullptr, n_seg,
+                                             static_cast<int32_t*>(bc.p), static_cast<int64_t*>(bb.p));
+        if (rc != GL_OK) break;
+        if (cudaMemcpyAsync(counts70, bc.p, (size_t)n_seg * GL_INDEXCOV_SLOTS * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(bins4, bb.p, (size_t)n_seg * 32, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexcov_counts_batch: D2H failed"); break; }
+    } while (0);
+    cudaFree(bd.p); cudaFree(bp.p); cudaFree(bl.p); cudaFree(bc.p); cudaFree(bb.p);
+    return rc;
+}
+
+int gl_indexcov_counts(gl_ctx* ctx, const float* depth, int64_t n, int32_t counts[GL_INDEXCOV_SLOTS]) {
+    if (n < 0 || !counts) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_counts: bad argument");
+    const int64_t ptr[2] = {0, n};
+    int32_t c[GL_INDEXCOV_SLOTS];
+    int64_t b[4];
+    GL_CHECK(gl_indexcov_counts_batch(ctx, depth, ptr, nullptr, 1, c, b));
+    for (int i = 0; i < GL_INDEXCOV_SLOTS; i++) counts[i] += c[i];            // counts[...]++ accumulates, indexcov.go:175
+    return GL_OK;
+}
+
+int gl_indexcov_bins(gl_ctx* ctx, const float* depth, int64_t n, int64_t longest, int64_t out4[4]) {
+    if (n < 0 || !out4) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_bins: bad argument");
+    const int64_t ptr[2] = {0, n};
+    int32_t c[GL_INDEXCOV_SLOTS];
+    int64_t b[4];
+    GL_CHECK(gl_indexcov_counts_batch(ctx, depth, ptr, &longest, 1, c, b));
+    for (int i = 0; i < 4; i++) out4[i] += b[i];
+    return GL_OK;
+}
+
+int gl_indexcov_xnorm(gl_ctx* ctx, float* depths, const int32_t* lens, int32_t S, int32_t T) {
+    GL_CHECK(gl_use(ctx));
+    if (S < 0 || T < 0 || (S > 0 && (!depths || !lens))) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_xnorm: bad argument");
+    if (S < 5 || T == 0) return GL_OK;                                          // indexcov.go:551
+    int32_t max_len = 0;
+    for (int32_t i = 0; i < S; i++) {
+        if (lens[i] < 0 || lens[i] > T) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_xnorm: lens[%d] out of range", i);
+        if (lens[i] > max_len) max_len = lens[i];
+    }
+    gl_buf bd, bl;
+    GL_CHECK(dev_tmp(ctx, bd, (size_t)S * T * 4));
+    GL_CHECK(dev_tmp(ctx, bl, (size_t)S * 4));
+    int rc = GL_OK;
+    do {
+        if (cudaMemcpyAsync(bd.p, depths, (size_t)S * T * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(bl.p, lens, (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexcov_xnorm: H2D failed"); break; }
+        ic_xnorm_kernel<<<1, kXnThreads, 0, ctx->stream>>>(static_cast<float*>(bd.p), static_cast<const int*>(bl.p), S, T, max_len);
+        ctx->launches++;
+        if (cudaMemcpyAsync(depths, bd.p, (size_t)S * T * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexcov_xnorm: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    cudaFree(bd.p); cudaFree(bl.p);
+    return rc;
+}
+
+int gl_bincount_i32(gl_ctx* ctx, const int32_t* v, int64_t n, int32_t lo, int32_t hi, uint64_t* hist) {
+    GL_CHECK(gl_use(ctx));
+    if (n < 0 || hi <= lo || !hist || (n > 0 && !v)) return gl_fail(ctx, GL_EINVAL, "gl_bincount_i32: bad argument");
+    const int64_t nb = (int64_t)hi - lo;
+    gl_buf bv, bh;
+    GL_CHECK(dev_tmp(ctx, bv, (size_t)n * 4));
+    GL_CHECK(dev_tmp(ctx, bh, (size_t)nb * 8));
+    int rc = GL_OK;
+    do {
+        if ((n && cudaMemcpyAsync(bv.p, v, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) ||
+            cudaMemsetAsync(bh.p, 0, (size_t)nb * 8, ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_bincount_i32: H2D failed"); break; }
+        if (n) {
+            const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+            gl_prof_scope prof(ctx, "bincount_kernel");
+            bincount_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const int*>(bv.p), n, lo, hi, static_cast<unsigned long long*>(bh.p));
+            ctx->launches++;
+        }
+        if (cudaMemcpyAsync(hist, bh.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_bincount_i32: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    cudaFree(bv.p); cudaFree(bh.p);
+    return rc;
+}
+
+// groups of consecutive rows per output line (depthwed.go:117-157): sequential in the row order, O(R) on the host
+static int64_t depthwed_groups(int64_t R, const int32_t* starts, const int32_t* ends, const int32_t* chrom_id, int64_t size,
+                               std::vector<int64_t>& grp) {
+    grp.clear();
+    int64_t r = 0;
+    while (r < R) {
+        grp.push_back(r);
+        const int32_t chrom = chrom_id[r], st = starts[r];
+        int32_t en = ends[r];
+        r++;
+        while (r < R && (int64_t)en - st < size && chrom_id[r] == chrom) { en = ends[r]; r++; }
+    }
+    grp.push_back(R);
+    return (int64_t)grp.size() - 1;
+}
+
+int gl_depthwed_aggregate_device(gl_ctx* ctx, const double* d_means, int32_t S, int64_t R, const int64_t* d_grp, int64_t n_out,
+                                 int64_t* d_out) {
+    GL_CHECK(gl_use(ctx));
+    if (S <= 0 || R < 0 || n_out < 0 || !d_means || !d_out) return gl_fail(ctx, GL_EINVAL, "gl_depthwed_aggregate_device: bad argument");
+    if (n_out == 0) return GL_OK;
+    dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((S + 31) / 32));
+    {
+        gl_prof_scope prof(ctx, "depthwed_kernel");
+        depthwed_kernel<<<grid, 256, 0, ctx->stream>>>(d_means, S, R, reinterpret_cast<const long long*>(d_grp), n_out, d_grp ? 0 : 1,
+                                                       reinterpret_cast<long long*>(d_out));
+    }
+    GL_LAUNCHED(ctx, 1);
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+int gl_depthwed_aggregate(gl_ctx* ctx, const double* means, int32_t S, int64_t R, const int32_t* starts, const int32_t* ends,
+                          const int32_t* chrom_id, int64_t size, int32_t* out_start, int32_t* out_end, int32_t* out_chrom,
+                          int64_t* out, int64_t out_cap, int64_t* n_out) {
+    GL_CHECK(gl_use(ctx));
+    if (S <= 0 || R < 0 || !means || !starts || !ends || !chrom_id || !n_out || size <= 0)
+        return gl_fail(ctx, GL_EINVAL, "gl_depthwed_aggregate: bad argument");
+    std::vector<int64_t> grp;
+    const int64_t ng = depthwed_groups(R, starts, ends, chrom_id, size, grp);
+    *n_out = ng;
+    if (ng > out_cap) return gl_fail(ctx, GL_ERANGE, "gl_depthwed_aggregate: %lld rows > cap %lld", (long long)ng, (long long)out_cap);
+    if (ng == 0) return GL_OK;
+    for (int64_t g = 0; g < ng; g++) {
+        out_start[g] = starts[grp[g]];
+        out_end[g] = ends[grp[g + 1] - 1];
+        out_chrom[g] = chrom_id[grp[g]];
+    }
+    gl_buf bm, bg, bo;
+    GL_CHECK(dev_tmp(ctx, bm, (size_t)S * R * 8));
+    GL_CHECK(dev_tmp(ctx, bg, (size_t)(ng + 1) * 8));
+    GL_CHECK(dev_tmp(ctx, bo, (size_t)ng * S * 8));
+    int rc = GL_OK;
+    do {
+        if (cudaMemcpyAsync(bm.p, means, (size_t)S * R * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(bg.p, grp.data(), (size_t)(ng + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_depthwed_aggregate: H2D failed"); break; }
+        rc = gl_depthwed_aggregate_device(ctx, static_cast<const double*>(bm.p), S, R, static_cast<const int64_t*>(bg.p), ng, static_cast<int64_t*>(bo.p));
+        if (rc != GL_OK) break;
+        if (cudaMemcpyAsync(out, bo.p, (size_t)ng * S * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_depthwed_aggregate: D2H failed"); break; }
+    } while (0);
+    cudaFree(bm.p); cudaFree(bg.p); cudaFree(bo.p);
+    return rc;
+}
+
+}  // extern "C"

@@ -151,7 +151,8 @@ void gl_free_text(char* p);
 /* ---------------------------------------------------------------- indexcov
  * Replaces indexcov/types.go:45-82 (getSizes), indexcov/indexcov.go:83-125 (Index.init),
  * :129-151 (NormalizedDepth), :170-177 (CountsAtDepth), :1050-1078 (counter.count),
- * :549-597 (normalizeAcrossSamples) for a cohort laid out as S samples x T tiles. */
+ * :549-597 (normalizeAcrossSamples).  float32/float64 results are bit-exact (no FMA contraction,
+ * same rounding points as Go on amd64). */
 
 /* I1: tile sizes from BAI linear-index virtual offsets.  voff: concatenated per-ref linear
  * index entries of one sample; ref_ptr: CSR offsets (n_refs+1).  sizes gets, per ref with
@@ -159,23 +160,30 @@ void gl_free_text(char* p);
  * if any delta is negative (the reference panics, types.go:75-77). */
 int  gl_indexcov_sizes(gl_ctx* ctx, const uint64_t* voff, const int64_t* ref_ptr, int32_t n_refs,
                        int64_t* sizes, int64_t* size_ptr);
-/* I2: the capped weighted median of Index.init: smallest v with sum_{s<=v} min(s,n98) > total/2. */
+/* I2: the capped weighted median of Index.init: sorted[first i with cumsum(min(s,n98))[i] > total/2]. */
 int  gl_indexcov_scale(gl_ctx* ctx, const int64_t* sizes, int64_t n, int64_t* median_out);
 /* I3: depth[i] = min(float32(float64(sizes[i])/median), 50000). */
 int  gl_indexcov_normalize(gl_ctx* ctx, const int64_t* sizes, int64_t n, double median, float* depth_out);
-/* I4: 70-slot histogram (counts += ...). */
+/* I2+I3 for a cohort in one kernel (one CTA per sample, radix selects instead of a sort):
+ * S samples, tile sizes in CSR layout (sample_ptr, S+1); medians[S]; depths in the same layout
+ * (depth_out may be NULL).  A sample with median 0 gets zero depths (the reference returns none). */
+int  gl_indexcov_cohort(gl_ctx* ctx, const int64_t* sizes, const int64_t* sample_ptr, int32_t S,
+                        double* medians, float* depth_out);
+int  gl_indexcov_cohort_device(gl_ctx* ctx, const int64_t* d_sizes, const int64_t* d_sample_ptr, int32_t S,
+                               double* d_medians, float* d_depth_out);
+/* I4: 70-slot histogram of one depth array (counts += ..., like the reference's counts[...]++). */
 int  gl_indexcov_counts(gl_ctx* ctx, const float* depth, int64_t n, int32_t counts[GL_INDEXCOV_SLOTS]);
 /* I5: counter.count over depth[0..n) with `longest` tiles expected; out4 += {out, low, hi, in}. */
 int  gl_indexcov_bins(gl_ctx* ctx, const float* depth, int64_t n, int64_t longest, int64_t out4[4]);
+/* I4+I5 for many (sample, chromosome) segments at once: seg_ptr CSR (n_seg+1) into depth,
+ * longest[n_seg] (may be NULL); counts70[n_seg*70] and bins4[n_seg*4] are overwritten. */
+int  gl_indexcov_counts_batch(gl_ctx* ctx, const float* depth, const int64_t* seg_ptr, const int64_t* longest,
+                              int32_t n_seg, int32_t* counts70, int64_t* bins4);
+int  gl_indexcov_counts_batch_device(gl_ctx* ctx, const float* d_depth, const int64_t* d_seg_ptr,
+                                     const int64_t* d_longest, int32_t n_seg, int32_t* d_counts70, int64_t* d_bins4);
 /* I7: in-place cross-sample normalisation of one chromosome; depths is S rows of stride T,
- * lens[i] valid entries in row i. */
+ * lens[i] valid entries in row i.  No-op for S < 5 (indexcov.go:551). */
 int  gl_indexcov_xnorm(gl_ctx* ctx, float* depths, const int32_t* lens, int32_t S, int32_t T);
-/* Cohort form (the fused kernel): S samples, per-sample tile sizes CSR (sample_ptr, S+1), all on
- * the host; returns medians[S] and normalised depths in the same CSR layout. */
-int  gl_indexcov_cohort(gl_ctx* ctx, const int64_t* sizes, const int64_t* sample_ptr, int32_t S,
-                        double* medians, float* depth_out);
-int  gl_indexcov_cohort_device(gl_ctx* ctx, const int64_t* d_sizes, const int64_t* d_sample_ptr,
-                               const int64_t* h_sample_ptr, int32_t S, double* d_medians, float* d_depth_out);
 
 /* ---------------------------------------------------------------- covstats
  * V2: histogram of int32 values in [lo,hi) -> hist[v-lo] (covstats/covstats.go:202-217 and the
@@ -183,22 +191,27 @@ int  gl_indexcov_cohort_device(gl_ctx* ctx, const int64_t* d_sizes, const int64_
 int  gl_bincount_i32(gl_ctx* ctx, const int32_t* v, int64_t n, int32_t lo, int32_t hi, uint64_t* hist);
 
 /* ---------------------------------------------------------------- depthwed
- * W1: depthwed/depthwed.go:93-157.  means: S samples x R rows (row-major by sample) of the
- * float64 4th BED column; starts/ends[R] of sample 0; chrom_id[R].  Computes
- * int(0.5+mean) and aggregates consecutive rows of one chrom until end-start >= size.
- * out: n_out rows x S ints (row-major by OUTPUT ROW, like the reference's TSV lines). */
+ * W1: depthwed/depthwed.go:93-157.  means: S samples x R rows (sample-major) of the float64 4th BED
+ * column; starts/ends/chrom_id[R] of the rows.  Computes int(0.5+mean) and sums consecutive rows of
+ * one chrom until end-start >= size.  out: n_out rows x S (row-major by OUTPUT ROW, like the
+ * reference's TSV lines). */
 int  gl_depthwed_aggregate(gl_ctx* ctx, const double* means, int32_t S, int64_t R,
                            const int32_t* starts, const int32_t* ends, const int32_t* chrom_id, int64_t size,
                            int32_t* out_start, int32_t* out_end, int32_t* out_chrom, int64_t* out, int64_t out_cap,
                            int64_t* n_out);
+/* device form: d_grp[n_out+1] row groups (NULL: one row per output line); d_out n_out x S */
+int  gl_depthwed_aggregate_device(gl_ctx* ctx, const double* d_means, int32_t S, int64_t R, const int64_t* d_grp,
+                                  int64_t n_out, int64_t* d_out);
 
 /* ------------------------------------------------------------- multi-GPU
- * One process per GPU.  The caller distributes a 128-byte NCCL unique id (rank 0 creates it). */
+ * One process per GPU.  The caller distributes a 128-byte NCCL unique id (rank 0 creates it).
+ * The one collective on this path: an all-gather over NVLink that assembles the depthwed
+ * n-sites x n-samples matrix (or the indexcov cohort) from per-GPU sample shards. */
 int  gl_comm_unique_id(uint8_t id128[128]);
 int  gl_comm_init(gl_ctx* ctx, const uint8_t id128[128], int rank, int world);
 int  gl_comm_destroy(gl_ctx* ctx);
-/* all-gather equal-sized int32 blocks that live on the device: d_recv holds world*count ints */
-int  gl_allgather_i32_device(gl_ctx* ctx, const int32_t* d_send, int32_t* d_recv, int64_t count);
+/* all-gather equal-sized blocks that live on the device: d_recv holds world*bytes */
+int  gl_allgather_device(gl_ctx* ctx, const void* d_send, void* d_recv, int64_t bytes);
 
 #ifdef __cplusplus
 }

@@ -137,3 +137,108 @@ def class_runs(depth: np.ndarray, rs: int, re: int, mincov: int, maxmean: int, r
     c = np.empty(n, np.uint8)
     lib.orc_class_runs(_ptr(depth), rs, re, mincov, maxmean, run_break, _ptr(a), _ptr(c), n)
     return a, c
+
+
+# ------------------------------------------------------------------ indexcov / covstats / depthwed
+_proto("orc_ic_sizes", C.c_int64, _vp, _vp, C.c_int32, _vp, _vp)
+_proto("orc_ic_median", C.c_int64, _vp, C.c_int64)
+_proto("orc_ic_normalize", None, _vp, C.c_int64, C.c_double, _vp)
+_proto("orc_ic_counts", None, _vp, C.c_int64, _vp)
+_proto("orc_ic_roc", None, _vp, _vp)
+_proto("orc_ic_bins", None, _vp, C.c_int64, C.c_int64, _vp)
+_proto("orc_ic_xnorm", None, _vp, _vp, C.c_int32, C.c_int32)
+_proto("orc_ic_getcn", C.c_double, _vp, C.c_int64)
+_proto("orc_cs_mean_std", None, _vp, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double))
+_proto("orc_cs_mad_filter", C.c_int64, _vp, C.c_int64, C.c_int)
+_proto("orc_cs_tail", C.c_int64, _vp, C.c_int64, _vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int64)
+_proto("orc_bincount", None, _vp, C.c_int64, C.c_int32, C.c_int32, _vp)
+_proto("orc_depthwed", C.c_int64, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64)
+
+
+def ic_sizes(voff, ref_ptr):
+    voff = np.ascontiguousarray(voff, np.uint64)
+    ref_ptr = np.ascontiguousarray(ref_ptr, np.int64)
+    n_refs = ref_ptr.size - 1
+    sizes = np.empty(max(voff.size, 1), np.int64)
+    size_ptr = np.zeros(n_refs + 1, np.int64)
+    k = lib.orc_ic_sizes(_ptr(voff), _ptr(ref_ptr), n_refs, _ptr(sizes), _ptr(size_ptr))
+    if k < 0:
+        raise ValueError("expected positive change in vOffset")
+    return sizes[:k], size_ptr
+
+
+def ic_median(sizes) -> int:
+    sizes = np.ascontiguousarray(sizes, np.int64)
+    return int(lib.orc_ic_median(_ptr(sizes), sizes.size))
+
+
+def ic_normalize(sizes, median: float) -> np.ndarray:
+    sizes = np.ascontiguousarray(sizes, np.int64)
+    out = np.empty(sizes.size, np.float32)
+    lib.orc_ic_normalize(_ptr(sizes), sizes.size, float(median), _ptr(out))
+    return out
+
+
+def ic_counts(depth, counts=None) -> np.ndarray:
+    depth = np.ascontiguousarray(depth, np.float32)
+    if counts is None:
+        counts = np.zeros(70, np.int32)
+    lib.orc_ic_counts(_ptr(depth), depth.size, _ptr(counts))
+    return counts
+
+
+def ic_roc(counts) -> np.ndarray:
+    counts = np.ascontiguousarray(counts, np.int32)
+    roc = np.empty(70, np.float32)
+    lib.orc_ic_roc(_ptr(counts), _ptr(roc))
+    return roc
+
+
+def ic_bins(depth, longest: int, out4=None) -> np.ndarray:
+    depth = np.ascontiguousarray(depth, np.float32)
+    if out4 is None:
+        out4 = np.zeros(4, np.int64)
+    lib.orc_ic_bins(_ptr(depth), depth.size, longest, _ptr(out4))
+    return out4
+
+
+def ic_xnorm(depths, lens) -> np.ndarray:
+    d = np.ascontiguousarray(depths, np.float32).copy()
+    lens = np.ascontiguousarray(lens, np.int32)
+    lib.orc_ic_xnorm(_ptr(d), _ptr(lens), d.shape[0], d.shape[1])
+    return d
+
+
+def ic_getcn(depth) -> float:
+    depth = np.ascontiguousarray(depth, np.float32)
+    return float(lib.orc_ic_getcn(_ptr(depth), depth.size))
+
+
+def bincount(v, lo: int, hi: int) -> np.ndarray:
+    v = np.ascontiguousarray(v, np.int32)
+    h = np.empty(hi - lo, np.uint64)
+    lib.orc_bincount(_ptr(v), v.size, lo, hi, _ptr(h))
+    return h
+
+
+def cs_tail(insert, tmpl, max_read_len: int):
+    insert = np.ascontiguousarray(insert, np.int32).copy()
+    tmpl = np.ascontiguousarray(tmpl, np.int32).copy()
+    out6 = np.zeros(6, np.float64)
+    H = np.zeros(1 << 16, np.float64)
+    hn = lib.orc_cs_tail(_ptr(insert), insert.size, _ptr(tmpl), tmpl.size, max_read_len, _ptr(out6), _ptr(H), H.size)
+    return out6, H[:hn]
+
+
+def depthwed(means, starts, ends, chrom_id, size: int):
+    means = np.ascontiguousarray(means, np.float64)
+    S, R = means.shape
+    starts = np.ascontiguousarray(starts, np.int32)
+    ends = np.ascontiguousarray(ends, np.int32)
+    chrom_id = np.ascontiguousarray(chrom_id, np.int32)
+    cap = max(R, 1)
+    o_s, o_e, o_c = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32)
+    out = np.empty((cap, S), np.int64)
+    k = lib.orc_depthwed(_ptr(means), S, R, _ptr(starts), _ptr(ends), _ptr(chrom_id), size, _ptr(o_s), _ptr(o_e), _ptr(o_c),
+                         _ptr(out), cap)
+    return o_s[:k], o_e[:k], o_c[:k], out[:k]

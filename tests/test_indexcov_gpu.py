@@ -1,0 +1,134 @@
+"""GPU parity for the indexcov / covstats / depthwed kernels against oracle/oracle_indexcov.c.
+Integers bit-exact; float32/float64 results bit-exact too (same rounding points, no FMA)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import loader as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def fixture():
+    j = json.load(open(os.path.join(ROOT, "tests", "golden", "sample_issue_27_bai_linear_index.json")))
+    refs = j["ioffsets"]
+    voff = np.array([v for r in refs for v in r], np.uint64)
+    ptr = np.concatenate([[0], np.cumsum([len(r) for r in refs])]).astype(np.int64)
+    return voff, ptr
+
+
+def synth_cohort(rng, S, T):
+    """per-sample tile sizes shaped like SURVEY.md §8d C4: lognormal * copy-number blocks, some zeros"""
+    base = rng.lognormal(np.log(1.6e9), 0.25, (S, T))
+    cn = rng.choice([1.0, 0.5, 1.5, 0.0], p=[0.94, 0.02, 0.02, 0.02], size=(S, T // 64 + 1)).repeat(64, 1)[:, :T]
+    return np.round(base * cn).astype(np.int64)
+
+
+def test_fixture_through_gpu(ctx):
+    voff, ptr = fixture()
+    sizes, sptr = ctx.indexcov_sizes(voff, ptr)
+    es, eptr = orc.ic_sizes(voff, ptr)
+    assert np.array_equal(sizes, es) and np.array_equal(sptr, eptr)
+    med = ctx.indexcov_scale(sizes)
+    assert med == orc.ic_median(es) == 1484454039397
+    d = ctx.indexcov_normalize(sizes, float(med))
+    assert np.array_equal(d.view(np.uint32), orc.ic_normalize(es, float(med)).view(np.uint32))
+    assert np.array_equal(ctx.indexcov_counts(d), orc.ic_counts(d))
+    assert np.array_equal(ctx.indexcov_bins(d, d.size + 5), orc.ic_bins(d, d.size + 5))
+    assert ctx.indexcov_bins(d, d.size).tolist() == [312, 304, 6, 1]
+
+
+def test_negative_delta_is_an_error(ctx):
+    from goleft_b200 import capi
+    voff = np.array([100, 50, 70], np.uint64)
+    with pytest.raises(capi.GlError) as ei:
+        ctx.indexcov_sizes(voff, np.array([0, 3], np.int64))
+    assert ei.value.code == capi.GL_ERANGE                      # the reference panics (types.go:75-77)
+    with pytest.raises(ValueError):
+        orc.ic_sizes(voff, np.array([0, 3], np.int64))
+
+
+def test_cohort_medians_and_depths(ctx):
+    rng = np.random.default_rng(4)
+    S = 37
+    lens = rng.integers(1, 5000, S)
+    lens[0], lens[1], lens[2] = 1, 2, 50
+    rows = [synth_cohort(rng, 1, int(n))[0] for n in lens]
+    rows[3][:] = 0                                              # all-zero sample: median 0
+    rows[4][:] = 7                                              # all ties
+    sizes = np.concatenate(rows)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    med, dep = ctx.indexcov_cohort(sizes, ptr)
+    for i in range(S):
+        m = orc.ic_median(rows[i])
+        assert med[i] == float(m), i
+        if m != 0:
+            exp = orc.ic_normalize(rows[i], float(m))
+            assert np.array_equal(dep[ptr[i]:ptr[i + 1]].view(np.uint32), exp.view(np.uint32)), i
+        else:
+            assert (dep[ptr[i]:ptr[i + 1]] == 0).all()
+
+
+def test_counts_batch(ctx):
+    rng = np.random.default_rng(5)
+    n_seg = 40
+    lens = rng.integers(0, 3000, n_seg)
+    d = np.abs(rng.normal(1.0, 0.4, int(lens.sum()))).astype(np.float32)
+    d[rng.random(d.size) < 0.02] = 0
+    d[rng.random(d.size) < 0.01] = 60000.0
+    d[:4] = [0.85, 1.15, 0.15, 8.0]                             # threshold values themselves
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    longest = lens + rng.integers(0, 50, n_seg)
+    counts, bins = ctx.indexcov_counts_batch(d, ptr, longest)
+    for s in range(n_seg):
+        seg = d[ptr[s]:ptr[s + 1]]
+        assert np.array_equal(counts[s], orc.ic_counts(seg)), s
+        assert np.array_equal(bins[s], orc.ic_bins(seg, int(longest[s]))), s
+
+
+def test_xnorm(ctx):
+    rng = np.random.default_rng(6)
+    for S, T in [(5, 40), (23, 300), (64, 1000)]:
+        d = np.abs(rng.normal(1.0, 0.3, (S, T))).astype(np.float32)
+        d[rng.random((S, T)) < 0.03] = 0
+        d[0, 5] = 1e-7                                          # forces the ordered (non order-free) summation path
+        d[1, 7] = 3e4
+        lens = rng.integers(T - 20, T + 1, S).astype(np.int32)
+        lens[0] = T
+        got = ctx.indexcov_xnorm(d, lens)
+        exp = orc.ic_xnorm(d, lens)
+        for i in range(S):
+            n = lens[i]
+            assert np.array_equal(got[i, :n].view(np.uint32), exp[i, :n].view(np.uint32)), (S, T, i)
+
+
+def test_bincount(ctx):
+    rng = np.random.default_rng(7)
+    v = rng.normal(450, 80, 1_000_000).astype(np.int32)
+    for lo, hi in [(150, 900), (0, 20000), (-100, 5)]:
+        assert np.array_equal(ctx.bincount(v, lo, hi), orc.bincount(v, lo, hi))
+    assert ctx.bincount(np.zeros(0, np.int32), 0, 10).sum() == 0
+
+
+def test_depthwed(ctx):
+    rng = np.random.default_rng(8)
+    S = 45
+    rows = []
+    for chrom, L in enumerate([10_050, 3_000, 777]):
+        st = np.arange(0, L, 100)
+        rows += [(chrom, int(a), int(min(a + 100, L))) for a in st]
+    chrom_id = np.array([r[0] for r in rows], np.int32)
+    starts = np.array([r[1] for r in rows], np.int32)
+    ends = np.array([r[2] for r in rows], np.int32)
+    R = len(rows)
+    # values as the reference would parse them back from "%.4g" text
+    means = np.array([[float("%.4g" % x) for x in rng.gamma(9, 3.3, R)] for _ in range(S)])
+    means[0, :5] = [0.5, 1.5, 2.4999, 0.49, 1e5]
+    for size in [100, 500, 1000, 100000]:
+        g = ctx.depthwed_aggregate(means, starts, ends, chrom_id, size)
+        e = orc.depthwed(means, starts, ends, chrom_id, size)
+        for a, b in zip(g, e):
+            assert np.array_equal(a, b), size
