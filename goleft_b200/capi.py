@@ -104,6 +104,14 @@ _proto("gl_comm_unique_id", C.c_int, _vp)
 _proto("gl_comm_init", C.c_int, _vp, _vp, C.c_int, C.c_int)
 _proto("gl_comm_destroy", C.c_int, _vp)
 _proto("gl_allgather_device", C.c_int, _vp, _vp, _vp, C.c_int64)
+_proto("gl_bam_decode_segments", C.c_int, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp), _vp, C.c_int64)
+_proto("gl_segset_n_refs", C.c_int, _vp, _i32p, _i64p, _i64p)
+_proto("gl_segset_ref", C.c_int, _vp, C.c_int32, C.POINTER(C.c_char_p), _i64p, C.POINTER(_vp), C.POINTER(_vp), _i64p)
+_proto("gl_segset_free", None, _vp)
+_proto("gl_bai_read", C.c_int, C.c_char_p, C.POINTER(_vp), _vp, C.c_int64)
+_proto("gl_bai_n_refs", C.c_int, _vp, _i32p, _u64p)
+_proto("gl_bai_ref", C.c_int, _vp, C.c_int32, C.POINTER(_vp), _i64p, _u64p, _u64p, _i32p)
+_proto("gl_bai_free", None, _vp)
 _proto("gl_depth_format_chunk", C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int64, _vp, _vp,
        C.c_int64, C.POINTER(_vp), _i64p, C.POINTER(_vp), _i64p)
 _proto("gl_free_text", None, _vp)
@@ -146,6 +154,50 @@ def format_chunk(chrom: str, rs: int, re: int, W: int, win_sum: np.ndarray, run_
     finally:
         lib.gl_free_text(d)
         lib.gl_free_text(c)
+
+
+def bam_segments(path: str, min_mapq: int = 1, threads: int = 4, only_tid: int = -1):
+    """Host-only feeder: {"refs": [(name, length)], "segments": {tid: (start, end)}, "n_records", "n_pass"}."""
+    h = _vp()
+    err = C.create_string_buffer(512)
+    rc = lib.gl_bam_decode_segments(path.encode(), min_mapq, threads, only_tid, C.byref(h), C.cast(err, _vp), 512)
+    if rc != GL_OK:
+        raise GlError(rc, err.value.decode())
+    try:
+        n, nrec, npass = C.c_int32(0), C.c_int64(0), C.c_int64(0)
+        lib.gl_segset_n_refs(h, C.byref(n), C.byref(nrec), C.byref(npass))
+        refs, segs = [], {}
+        for tid in range(n.value):
+            name, ln, ps, pe, k = C.c_char_p(), C.c_int64(0), _vp(), _vp(), C.c_int64(0)
+            lib.gl_segset_ref(h, tid, C.byref(name), C.byref(ln), C.byref(ps), C.byref(pe), C.byref(k))
+            refs.append((name.value.decode(), ln.value))
+            if k.value:
+                s_ = np.ctypeslib.as_array(C.cast(ps, _i32p), (k.value,)).copy()
+                e_ = np.ctypeslib.as_array(C.cast(pe, _i32p), (k.value,)).copy()
+                segs[tid] = (s_, e_)
+        return {"refs": refs, "segments": segs, "n_records": nrec.value, "n_pass": npass.value}
+    finally:
+        lib.gl_segset_free(h)
+
+
+def bai_read(path: str):
+    h = _vp()
+    err = C.create_string_buffer(512)
+    rc = lib.gl_bai_read(path.encode(), C.byref(h), C.cast(err, _vp), 512)
+    if rc != GL_OK:
+        raise GlError(rc, err.value.decode())
+    try:
+        n, nc = C.c_int32(0), C.c_uint64(0)
+        lib.gl_bai_n_refs(h, C.byref(n), C.byref(nc))
+        out = {"ioffsets": [], "mapped": [], "unmapped": [], "n_no_coor": nc.value}
+        for tid in range(n.value):
+            p, k, m, u, hs = _vp(), C.c_int64(0), C.c_uint64(0), C.c_uint64(0), C.c_int32(0)
+            lib.gl_bai_ref(h, tid, C.byref(p), C.byref(k), C.byref(m), C.byref(u), C.byref(hs))
+            out["ioffsets"].append(np.ctypeslib.as_array(C.cast(p, _u64p), (k.value,)).copy() if k.value else np.zeros(0, np.uint64))
+            out["mapped"].append(m.value); out["unmapped"].append(u.value)
+        return out
+    finally:
+        lib.gl_bai_free(h)
 
 
 class DevBuf:

@@ -148,6 +148,27 @@ int  gl_depth_format_chunk(const char* chrom, int64_t rs, int64_t re, int32_t W,
                            char** depth_bed, int64_t* depth_len, char** callable_bed, int64_t* callable_len);
 void gl_free_text(char* p);
 
+/* ---------------------------------------------------------------- feeder (host-only, no GPU needed)
+ * BGZF (multi-threaded inflate) + BAM decode + the `samtools depth` record filter: records with
+ * (flag & 0x704) == 0 and MAPQ >= min_mapq contribute their M/=/X blocks (D and N advance without
+ * counting; blocks separated only by I/S/H/P are merged), per reference, in record order.
+ * Replaces the decode half of the `samtools depth` child (depth/depth.go:45).  only_tid < 0: all refs. */
+typedef struct gl_segset gl_segset;
+int  gl_bam_decode_segments(const char* path, int32_t min_mapq, int32_t threads, int32_t only_tid, gl_segset** out,
+                            char* err, int64_t err_cap);
+int  gl_segset_n_refs(const gl_segset* s, int32_t* n_refs, int64_t* n_records, int64_t* n_pass);
+int  gl_segset_ref(const gl_segset* s, int32_t tid, const char** name, int64_t* length, const int32_t** start,
+                   const int32_t** end, int64_t* n);
+void gl_segset_free(gl_segset* s);
+/* BAI: per-reference linear index (16 KB tiles) + the 0x924a stats bin (indexcov/types.go:19,45-58),
+ * what indexcov takes from biogo's bam.ReadIndex (indexcov/indexcov.go:514). */
+typedef struct gl_bai gl_bai;
+int  gl_bai_read(const char* path, gl_bai** out, char* err, int64_t err_cap);
+int  gl_bai_n_refs(const gl_bai* b, int32_t* n_refs, uint64_t* n_no_coor);
+int  gl_bai_ref(const gl_bai* b, int32_t tid, const uint64_t** ioffsets, int64_t* n_intv, uint64_t* mapped,
+                uint64_t* unmapped, int32_t* has_stats);
+void gl_bai_free(gl_bai* b);
+
 /* ---------------------------------------------------------------- indexcov
  * Replaces indexcov/types.go:45-82 (getSizes), indexcov/indexcov.go:83-125 (Index.init),
  * :129-151 (NormalizedDepth), :170-177 (CountsAtDepth), :1050-1078 (counter.count),
