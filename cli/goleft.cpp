@@ -1,0 +1,687 @@
+// goleft — C++ host for the B200 engine, keeping the `goleft depth|indexcov|covstats|depthwed` command-line
+// and BED/TSV output surface of brentp/goleft v0.2.6 (cmd/goleft/goleft.go:24-69).  Every number it prints is
+// computed by libgoleft_b200.so (CUDA, sm_100a) through the C ABI in include/goleft_b200.h; there is no CPU
+// fallback: without a GPU the subcommands fail with the library's error.
+//
+// Out of scope here: HTML/PNG plots, PCA columns of the .ped, CRAM/.crai, --stats GC columns.
+#include <errno.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <algorithm>
+#include <map>
+#include <regex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <zlib.h>
+
+#include "../goleft_b200/csrc/host/hts_io.h"
+#include "goleft_b200.h"
+
+static const char* kVersion = "0.2.6";          // goleft.go:3 (the surface this build mirrors)
+
+// ------------------------------------------------------------------------------------------------ util
+[[noreturn]] static void fatal(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    fputc('\n', stderr);
+    exit(code);
+}
+
+static void glck(gl_ctx* ctx, int rc, const char* what) {
+    if (rc != GL_OK) fatal(1, "%s: %s", what, gl_last_error(ctx));
+}
+
+static bool ends_with(const std::string& s, const std::string& suf) {
+    return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+
+static bool file_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+
+// lines of a (possibly gzipped) text file; like Go's ReadString('\n') loops that break on io.EOF, a final
+// line WITHOUT a trailing newline is dropped when drop_unterminated is set (depth.go:106-110,137-141)
+static std::vector<std::string> read_lines(const std::string& path, bool drop_unterminated) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) fatal(1, "open %s: %s", path.c_str(), strerror(errno));
+    std::vector<std::string> out;
+    std::string cur;
+    char buf[1 << 16];
+    int n;
+    while ((n = gzread(f, buf, sizeof buf)) > 0) {
+        for (int i = 0; i < n; i++) {
+            if (buf[i] == '\n') { out.push_back(cur); cur.clear(); }
+            else cur.push_back(buf[i]);
+        }
+    }
+    gzclose(f);
+    if (!cur.empty() && !drop_unterminated) out.push_back(cur);
+    return out;
+}
+
+// go-arg style parser (alexflint/go-arg v1.4.3): -x v, --long v, --long=v, -long v; bool flags take no value
+struct Spec { std::string lng; char sht; bool is_bool; std::string* sval; bool* bval; bool required; bool seen; };
+struct ArgParser {
+    std::string prog;
+    std::vector<Spec> specs;
+    std::vector<std::string> positional;
+    void add(const std::string& lng, char sht, std::string* v, bool required = false) { specs.push_back({lng, sht, false, v, nullptr, required, false}); }
+    void addb(const std::string& lng, char sht, bool* v) { specs.push_back({lng, sht, true, nullptr, v, false, false}); }
+    [[noreturn]] void fail(const std::string& msg) const {
+        fprintf(stderr, "Usage: %s [options] ...\nerror: %s\n", prog.c_str(), msg.c_str());
+        exit(255);                                         // functional-tests.sh:40-42
+    }
+    void parse(int argc, char** argv) {
+        for (int i = 1; i < argc; i++) {
+            std::string a = argv[i];
+            if (a == "-h" || a == "--help") {
+                printf("Usage: %s", prog.c_str());
+                for (auto& s : specs) printf(" [--%s%s]", s.lng.c_str(), s.is_bool ? "" : " VALUE");
+                printf(" ...\n");
+                exit(0);
+            }
+            if (a.size() > 1 && a[0] == '-' && !(a.size() > 1 && isdigit((unsigned char)a[1]))) {
+                std::string name = a.substr(a[1] == '-' ? 2 : 1), val;
+                bool has_val = false;
+                size_t eq = name.find('=');
+                if (eq != std::string::npos) { val = name.substr(eq + 1); name = name.substr(0, eq); has_val = true; }
+                Spec* sp = nullptr;
+                for (auto& s : specs) if (s.lng == name || (name.size() == 1 && s.sht && s.sht == name[0])) sp = &s;
+                if (!sp) fail("unknown argument " + a);
+                sp->seen = true;
+                if (sp->is_bool) { *sp->bval = has_val ? (val == "true" || val == "1") : true; continue; }
+                if (!has_val) {
+                    if (i + 1 >= argc) fail("missing value for " + a);
+                    val = argv[++i];
+                }
+                *sp->sval = val;
+            } else {
+                positional.push_back(a);
+            }
+        }
+        for (auto& s : specs) if (s.required && !s.seen) fail(s.lng + " is required");
+    }
+};
+
+// depth.go:73-94: regexp "(.+?)[:\t](\d+)([\-\t])(\d+).*?" — leftmost match, lazy first group
+static bool chrom_start_end(const std::string& line, std::string& chrom, long long& start, long long& end) {
+    const size_t n = line.size();
+    for (size_t m0 = 0; m0 < n; m0++) {
+        for (size_t k = m0 + 1; k < n; k++) {
+            if (line[k] != ':' && line[k] != '\t') continue;
+            size_t b = k + 1;
+            while (b < n && isdigit((unsigned char)line[b])) b++;
+            if (b == k + 1 || b >= n || (line[b] != '-' && line[b] != '\t')) continue;
+            size_t d = b + 1;
+            while (d < n && isdigit((unsigned char)line[d])) d++;
+            if (d == b + 1) continue;
+            chrom = line.substr(m0, k - m0);
+            long long s = atoll(line.c_str() + k + 1);
+            if (line[b] == '-') s--;
+            start = s < 0 ? 0 : s;
+            end = atoll(line.c_str() + b + 1);
+            return true;
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------ depth
+static int cmd_depth(int argc, char** argv) {
+    std::string w = "250", m = "0", q = "1", chrom, mincov = "4", reference, procs = "0", bed, prefix;
+    bool ordered = false, stats = false;
+    ArgParser ap;
+    ap.prog = "goleft depth";
+    ap.add("windowsize", 'w', &w); ap.add("maxmeandepth", 'm', &m); ap.addb("ordered", 'o', &ordered);
+    ap.add("q", 'Q', &q); ap.add("chrom", 'c', &chrom); ap.add("mincov", 0, &mincov); ap.addb("stats", 's', &stats);
+    ap.add("reference", 'r', &reference); ap.add("processes", 'p', &procs); ap.add("bed", 'b', &bed);
+    ap.add("prefix", 0, &prefix, true);
+    ap.parse(argc, argv);
+    if (ap.positional.empty()) ap.fail("bam is required");
+    const std::string bam = ap.positional[0];
+    const int W = atoi(w.c_str()), maxmean = atoi(m.c_str()), Q = atoi(q.c_str()), mcov = atoi(mincov.c_str());
+    if (W <= 0) ap.fail("windowsize must be > 0");
+    if (stats) fprintf(stderr, "goleft depth: --stats (GC/CpG/masked columns) is not built in this engine; columns omitted\n");
+    int threads = atoi(procs.c_str());
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+
+    // work list (depth.go:103-159)
+    struct Region { std::string chrom; long long s, e; };
+    std::vector<Region> regions;
+    long long step = std::max(1LL, 10000000LL / W) * W;                    // depth.go:132
+    if (!bed.empty()) {
+        for (const std::string& ln : read_lines(bed, true)) {
+            if (ln.empty()) continue;
+            Region r;
+            if (!chrom_start_end(ln, r.chrom, r.s, r.e)) fatal(1, "couldn't get region from line%s", ln.c_str());
+            regions.push_back(r);
+        }
+    } else {
+        for (const std::string& ln : read_lines(reference + ".fai", true)) {
+            size_t t1 = ln.find('\t');
+            if (t1 == std::string::npos) continue;
+            std::string c = ln.substr(0, t1);
+            if (!chrom.empty() && c != chrom) continue;
+            long long len = atoll(ln.c_str() + t1 + 1);
+            for (long long i = 0; i < len; i += step) regions.push_back({c, i, std::min(i + step, len)});
+        }
+    }
+
+    glhts::SegmentSet segs;
+    std::string err = glhts::bam_decode_segments(bam, Q, threads, -1, segs);
+    if (!err.empty()) fatal(1, "%s", err.c_str());
+    std::map<std::string, int> tid_of;
+    for (size_t i = 0; i < segs.header.refs.size(); i++) tid_of[segs.header.refs[i].name] = (int)i;
+
+    gl_ctx* ctx = nullptr;
+    if (gl_ctx_create(0, &ctx) != GL_OK) fatal(1, "goleft depth: %s", gl_last_error(nullptr));
+    const std::string sfx = chrom.empty() ? "" : "." + chrom;               // depth.go:378-389
+    FILE* fca = fopen((prefix + sfx + ".callable.bed").c_str(), "w");
+    FILE* fhd = fopen((prefix + sfx + ".depth.bed").c_str(), "w");
+    if (!fca || !fhd) fatal(1, "cannot create output files with prefix %s", prefix.c_str());
+
+    std::vector<int64_t> sums;
+    std::vector<int32_t> rstart;
+    std::vector<uint8_t> rclass;
+    auto run_region = [&](const std::string& c, long long rs, long long re, long long run_break, int64_t& nw, int64_t& nr) {
+        static const int32_t none = 0;
+        const int32_t *ps = &none, *pe = &none;
+        int64_t n = 0;
+        auto it = tid_of.find(c);
+        if (it != tid_of.end()) { ps = segs.start[it->second].data(); pe = segs.end[it->second].data(); n = (int64_t)segs.start[it->second].size(); }
+        sums.resize((size_t)((re - 1) / W - rs / W + 1));
+        for (;;) {
+            int rc = gl_depth_region(ctx, rs, re, n ? ps : nullptr, n ? pe : nullptr, n, W, mcov, maxmean, run_break, sums.data(),
+                                     (int64_t)sums.size(), &nw, rstart.data(), rclass.data(), (int64_t)rstart.size(), &nr);
+            if (rc == GL_ERANGE && nr > (int64_t)rstart.size()) { rstart.resize((size_t)nr + 1024); rclass.resize((size_t)nr + 1024); continue; }
+            glck(ctx, rc, "gl_depth_region");
+            break;
+        }
+    };
+    rstart.resize(1 << 16); rclass.resize(1 << 16);
+
+    if (!bed.empty()) {
+        for (const Region& r : regions) {                                   // one chunk per BED line
+            if (r.e <= r.s) continue;
+            int64_t nw = 0, nr = 0;
+            run_region(r.chrom, r.s, r.e, 0, nw, nr);
+            char *hd = nullptr, *ca = nullptr;
+            int64_t hl = 0, cl = 0;
+            if (gl_depth_format_chunk(r.chrom.c_str(), r.s, r.e, W, sums.data(), nw, rstart.data(), rclass.data(), nr, &hd, &hl, &ca, &cl) != GL_OK)
+                fatal(1, "gl_depth_format_chunk failed");
+            fwrite(hd, 1, (size_t)hl, fhd); fwrite(ca, 1, (size_t)cl, fca);
+            gl_free_text(hd); gl_free_text(ca);
+        }
+    } else {
+        // whole contig in one pass (run_break = step reproduces the reference's per-chunk run boundaries),
+        // then the reference's rows chunk by chunk, always in order (a valid -o/--ordered output)
+        size_t i = 0;
+        while (i < regions.size()) {
+            size_t j = i;
+            while (j < regions.size() && regions[j].chrom == regions[i].chrom) j++;
+            const long long len = regions[j - 1].e;
+            int64_t nw = 0, nr = 0;
+            run_region(regions[i].chrom, 0, len, step, nw, nr);
+            for (size_t k = i; k < j; k++) {
+                const long long cs = regions[k].s, ce = regions[k].e;
+                const int32_t* lo = std::lower_bound(rstart.data(), rstart.data() + nr, (int32_t)cs);
+                const int32_t* hi = std::lower_bound(rstart.data(), rstart.data() + nr, (int32_t)ce);
+                char *hd = nullptr, *ca = nullptr;
+                int64_t hl = 0, cl = 0;
+                if (gl_depth_format_chunk(regions[k].chrom.c_str(), cs, ce, W, sums.data() + cs / W, (ce - 1) / W - cs / W + 1, lo,
+                                          rclass.data() + (lo - rstart.data()), hi - lo, &hd, &hl, &ca, &cl) != GL_OK)
+                    fatal(1, "gl_depth_format_chunk failed");
+                fwrite(hd, 1, (size_t)hl, fhd); fwrite(ca, 1, (size_t)cl, fca);
+                gl_free_text(hd); gl_free_text(ca);
+            }
+            i = j;
+        }
+    }
+    fclose(fca); fclose(fhd);
+    gl_ctx_destroy(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ indexcov
+// indexcov.go:213-246
+static std::string short_name(const std::string& b, bool from_filename, const glhts::BamHeader* hdr) {
+    if (!from_filename && hdr) {
+        std::vector<std::string> sm = hdr->sample_names();
+        if (sm.size() > 1) fatal(1, "bam reagroup: more than one RG for %s", b.c_str());
+        if (sm.size() == 1) return sm[0];
+    }
+    std::string v = b.substr(b.find_last_of('/') == std::string::npos ? 0 : b.find_last_of('/') + 1);
+    std::vector<std::string> parts;
+    size_t p = 0;
+    for (;;) { size_t d = v.find('.', p); parts.push_back(v.substr(p, d == std::string::npos ? std::string::npos : d - p)); if (d == std::string::npos) break; p = d + 1; }
+    if (parts.size() <= 2) return parts[0];
+    std::string out = parts[0];
+    for (size_t i = 1; i + 1 < parts.size(); i++) out += "-" + parts[i];
+    return out;
+}
+
+// indexcov.go:530-547
+static bool same_chrom(const std::vector<std::string>& as, const std::string& b) {
+    for (const std::string& a : as) {
+        if (a == b) return true;
+        std::string na = a;
+        if (a.compare(0, 3, "chr") == 0) na = a.substr(3);
+        else if (b.compare(0, 3, "chr") == 0) na = "chr" + a;
+        if (na == b) return true;
+    }
+    return false;
+}
+
+// indexcov.go:957-991 for one sample
+static double get_cn(const float* d, size_t n) {
+    std::vector<float> tmp;
+    size_t lows = 0;
+    for (size_t i = 0; i < n; i++) if (d[i] != 0) { tmp.push_back(d[i]); if (d[i] < 0.02f) lows++; }
+    if (tmp.empty()) return -0.1;
+    std::sort(tmp.begin(), tmp.end());
+    const double pLo = (double)lows / (double)n;
+    const float* t = tmp.data();
+    size_t tk = tmp.size();
+    if (pLo > 0.3) { t += lows; tk -= lows; }
+    if (tk == 0) return 0;
+    return (double)(2.0f * t[(size_t)((double)tk * 0.4)]);
+}
+
+struct IcRef { std::string name; long long len; int id; };
+
+static int cmd_indexcov(int argc, char** argv) {
+    std::string dir, exclude = "^chrEBV$|^NC|_random$|Un_|^HLA\\-|_alt$|hap\\d$", sex = "X,Y", chrom, fai;
+    bool includegl = false, extranorm = false;
+    ArgParser ap;
+    ap.prog = "goleft indexcov";
+    ap.add("directory", 'd', &dir, true); ap.addb("includegl", 'e', &includegl); ap.add("excludepatt", 0, &exclude);
+    ap.add("sex", 'X', &sex); ap.add("chrom", 'c', &chrom); ap.add("fai", 'f', &fai); ap.addb("extranormalize", 'n', &extranorm);
+    ap.parse(argc, argv);
+    std::vector<std::string> bams = ap.positional;
+    if (bams.empty()) ap.fail("bam is required");
+    std::vector<std::string> sexes_wanted;
+    { size_t p = 0; for (;;) { size_t c = sex.find(',', p); std::string t = sex.substr(p, c == std::string::npos ? std::string::npos : c - p); if (!t.empty()) sexes_wanted.push_back(t); if (c == std::string::npos) break; p = c + 1; } }
+    std::regex excl(exclude);
+    mkdir(dir.c_str(), 0755);
+
+    // references (indexcov.go:344-374): BAM header of the first input, or the .fai
+    std::vector<IcRef> refs;
+    if (ends_with(bams[0], ".bam")) {
+        glhts::BamHeader h;
+        std::string e = glhts::bam_read_header(bams[0], h);
+        if (!e.empty()) fatal(1, "%s", e.c_str());
+        for (size_t i = 0; i < h.refs.size(); i++) refs.push_back({h.refs[i].name, h.refs[i].length, (int)i});
+        if (!chrom.empty()) {                                               // RefsFromBam appends the named chrom (:336-338)
+            std::string c = chrom.compare(0, 3, "chr") == 0 ? chrom.substr(3) : chrom;
+            bool found = false;
+            for (size_t i = 0; i < h.refs.size() && !found; i++) {
+                const std::string& n = h.refs[i].name;
+                if (c == n || (n.compare(0, 3, "chr") == 0 && c == n.substr(3))) { refs.push_back({n, h.refs[i].length, (int)i}); found = true; }
+            }
+            if (!found) fatal(1, "indexcov: chromosome: %s not found", chrom.c_str());
+        }
+    } else if (!fai.empty()) {
+        std::vector<glhts::RefInfo> r;
+        std::string e = glhts::fai_read(fai, r);
+        if (!e.empty()) fatal(1, "error opening fai: %s. Is is present?", fai.c_str());
+        for (auto& x : r) if (chrom.empty() || x.name == chrom) refs.push_back({x.name, x.length, (int)refs.size()});
+        if (refs.empty()) fatal(1, "ERROR: didn't find any usable chromosomes in %s", fai.c_str());
+    } else {
+        fatal(1, "indexcov: since no .fai was specified, expected input to be a list of bams");
+    }
+
+    // indexes (indexcov.go:471-525)
+    const size_t S = bams.size();
+    std::vector<std::string> names(S);
+    std::vector<glhts::BaiIndex> idx(S);
+    for (size_t i = 0; i < S; i++) {
+        const std::string& b = bams[i];
+        if (ends_with(b, ".crai")) fatal(1, "indexcov: .crai input is not built in this engine");
+        std::string p = ends_with(b, ".bai") ? b : b + ".bai";
+        if (!file_exists(p)) p = b.substr(0, b.size() - 4) + (ends_with(b, ".bai") ? "" : ".bai");
+        std::string e = glhts::bai_read(p, idx[i]);
+        if (!e.empty()) fatal(1, "%s", e.c_str());
+        if (ends_with(b, ".bai")) names[i] = short_name(b, true, nullptr);
+        else { glhts::BamHeader h; std::string he = glhts::bam_read_header(b, h); if (!he.empty()) fatal(1, "%s", he.c_str()); names[i] = short_name(b, false, &h); }
+    }
+
+    gl_ctx* ctx = nullptr;
+    if (gl_ctx_create(0, &ctx) != GL_OK) fatal(1, "goleft indexcov: %s", gl_last_error(nullptr));
+    fprintf(stderr, "indexcov: running on %zu indexes\n", S);
+
+    // tile sizes per sample (I1), then medians + normalised depths for the cohort in one kernel (I2+I3)
+    std::vector<int64_t> all_sizes, sample_ptr(1, 0);
+    std::vector<std::vector<int64_t>> size_ptr(S);                          // per sample: CSR over its refs
+    std::vector<uint64_t> mapped(S, 0), unmapped(S, 0);
+    for (size_t i = 0; i < S; i++) {
+        const size_t nr = idx[i].ioffsets.size();
+        std::vector<uint64_t> voff;
+        std::vector<int64_t> rp(nr + 1, 0);
+        for (size_t r = 0; r < nr; r++) { voff.insert(voff.end(), idx[i].ioffsets[r].begin(), idx[i].ioffsets[r].end()); rp[r + 1] = (int64_t)voff.size(); mapped[i] += idx[i].mapped[r]; unmapped[i] += idx[i].unmapped[r]; }
+        std::vector<int64_t> sz(voff.size() + 1), sp(nr + 1, 0);
+        glck(ctx, gl_indexcov_sizes(ctx, voff.data(), rp.data(), (int32_t)nr, sz.data(), sp.data()), "gl_indexcov_sizes");
+        if (sp[nr] < 1) fatal(1, "indexcov: no usable chromsomes in bam: %s", bams[i].c_str());   // indexcov.go:100-102
+        all_sizes.insert(all_sizes.end(), sz.begin(), sz.begin() + sp[nr]);
+        sample_ptr.push_back((int64_t)all_sizes.size());
+        size_ptr[i] = sp;
+    }
+    std::vector<double> med(S);
+    std::vector<float> dep(all_sizes.size());
+    glck(ctx, gl_indexcov_cohort(ctx, all_sizes.data(), sample_ptr.data(), (int32_t)S, med.data(), dep.data()), "gl_indexcov_cohort");
+
+    const std::string base = dir + "/" + dir.substr(dir.find_last_of('/') == std::string::npos ? 0 : dir.find_last_of('/') + 1) + "-indexcov";
+    glhts::BgzfWriter bgz(base + ".bed.gz");
+    FILE* roc = fopen((base + ".roc").c_str(), "w");
+    if (!bgz.ok() || !roc) fatal(1, "cannot create outputs in %s", dir.c_str());
+    { std::string h = "#chrom\tstart\tend"; for (auto& n : names) h += "\t" + n; h += "\n"; bgz.write(h.data(), h.size()); }
+
+    std::map<std::string, std::vector<double>> sexes;
+    std::vector<int64_t> bins(S * 4, 0);
+    std::vector<float> slopes(S, 0);
+    int n_slopes = 0, n_reported = 0;
+    for (const IcRef& ref : refs) {
+        if (!exclude.empty() && std::regex_search(ref.name, excl)) {
+            if (n_reported < 10) { fprintf(stderr, "indexcv: excluding chromosome: %s because of exclude-pattern: %s\n", ref.name.c_str(), exclude.c_str()); if (++n_reported == 10) fprintf(stderr, "not reporting further skipped chromosomes\n"); }
+            continue;
+        }
+        // per-sample slices of this reference (ref.ID() indexes the index's reference array, indexcov.go:656)
+        std::vector<const float*> dptr(S, nullptr);
+        std::vector<int32_t> lens(S, 0);
+        size_t longest = 0;
+        for (size_t k = 0; k < S; k++) {
+            if (ref.id + 1 < (int)size_ptr[k].size() && med[k] != 0) {
+                const int64_t a = size_ptr[k][ref.id], b = size_ptr[k][ref.id + 1];
+                dptr[k] = dep.data() + sample_ptr[k] + a;
+                lens[k] = (int32_t)(b - a);
+            }
+            longest = std::max(longest, (size_t)lens[k]);
+        }
+        const bool is_sex = same_chrom(sexes_wanted, ref.name);
+        std::vector<float> mat;                                             // S x longest, used when values are rewritten
+        if (extranorm && !is_sex && longest > 0) {
+            mat.assign(S * longest, 0.f);
+            for (size_t k = 0; k < S; k++) if (lens[k]) memcpy(&mat[k * longest], dptr[k], (size_t)lens[k] * 4);
+            glck(ctx, gl_indexcov_xnorm(ctx, mat.data(), lens.data(), (int32_t)S, (int32_t)longest), "gl_indexcov_xnorm");
+            for (size_t k = 0; k < S; k++) dptr[k] = &mat[k * longest];
+        }
+        // slot histograms + in/out counters for every sample on this reference (I4+I5)
+        std::vector<float> flat;
+        std::vector<int64_t> seg_ptr(1, 0), lg(S, (int64_t)longest);
+        for (size_t k = 0; k < S; k++) { flat.insert(flat.end(), dptr[k], dptr[k] + lens[k]); seg_ptr.push_back((int64_t)flat.size()); }
+        std::vector<int32_t> counts(S * GL_INDEXCOV_SLOTS);
+        std::vector<int64_t> b4(S * 4);
+        glck(ctx, gl_indexcov_counts_batch(ctx, flat.data(), seg_ptr.data(), lg.data(), (int32_t)S, counts.data(), b4.data()), "gl_indexcov_counts_batch");
+
+        // bed.gz rows (indexcov.go:678-680,1038-1048)
+        std::string row;
+        char num[48];
+        for (size_t i = 0; i < longest; i++) {
+            row = ref.name;
+            snprintf(num, sizeof num, "\t%zu\t%zu", i * 16384, (i + 1) * 16384);
+            row += num;
+            for (size_t k = 0; k < S; k++) {
+                if (i >= (size_t)lens[k]) row += "\t0";
+                else { snprintf(num, sizeof num, "\t%.3g", (double)dptr[k][i]); row += num; }
+            }
+            row += "\n";
+            bgz.write(row.data(), row.size());
+        }
+        if (is_sex) {
+            if (longest > 0) { std::vector<double> cn(S); for (size_t k = 0; k < S; k++) cn[k] = get_cn(dptr[k], (size_t)lens[k]); sexes[ref.name] = cn; }
+        } else {
+            for (size_t k = 0; k < S * 4; k++) bins[k] += b4[k];
+        }
+        if (longest > 0) {                                                  // writeROCs (indexcov.go:1018-1036)
+            std::string h = "#chrom\tcov"; for (auto& n : names) h += "\t" + n; h += "\n";
+            fputs(h.c_str(), roc);
+            std::vector<float> rocs(S * GL_INDEXCOV_SLOTS);
+            for (size_t k = 0; k < S; k++) {
+                int tot[GL_INDEXCOV_SLOTS];
+                const int32_t* c = &counts[k * GL_INDEXCOV_SLOTS];
+                tot[GL_INDEXCOV_SLOTS - 1] = c[GL_INDEXCOV_SLOTS - 1];
+                for (int i = GL_INDEXCOV_SLOTS - 2; i >= 0; i--) tot[i] = tot[i + 1] + c[i];
+                const float mx = (float)tot[0];
+                for (int i = 0; i < GL_INDEXCOV_SLOTS; i++) rocs[k * GL_INDEXCOV_SLOTS + i] = (float)tot[i] / mx;
+            }
+            for (int i = 0; i < GL_INDEXCOV_SLOTS; i++) {
+                fprintf(roc, "%s\t%.2f", ref.name.c_str(), (double)i / (70.0 * (2.0 / 3.0)));
+                for (size_t k = 0; k < S; k++) fprintf(roc, "\t%.2f", (double)rocs[k * GL_INDEXCOV_SLOTS + i]);
+                fputc('\n', roc);
+            }
+            if ((includegl || ref.name.compare(0, 2, "GL") != 0) && longest > 2 && !is_sex && longest > 100) {
+                const double sm = 2.0 / 3.0;                                // updateSlopes (indexcov.go:739-750)
+                const int ilo = (int)(0.5 + (sm - 0.1) * 70), ihi = (int)(0.5 + (sm + 0.1) * 70);
+                const float scalar = (float)ref.len / 1e6f;
+                for (size_t k = 0; k < S; k++) slopes[k] += (rocs[k * 70 + ilo] - rocs[k * 70 + ihi]) * scalar;
+                n_slopes++;
+            }
+        }
+    }
+    bgz.close();
+    fclose(roc);
+    for (size_t k = 0; k < S; k++) slopes[k] = slopes[k] / (float)n_slopes;
+    if (sexes.size() != sexes_wanted.size()) {                              // checkSexes (indexcov.go:760-770)
+        std::string keys; for (auto& kv : sexes) keys += (keys.empty() ? "" : ",") + kv.first;
+        if (sexes.empty() && sex != "X,Y") fatal(1, "(FATAL) indexcov: expected %zu sex chromosomes, found: %zu.", sexes_wanted.size(), sexes.size());
+        fprintf(stderr, "(WARNING) indexcov: expected %zu sex chromosomes, found: %zu.\nyou can set the expected with --sex '%s'\n", sexes_wanted.size(), sexes.size(), keys.c_str());
+    }
+    // .ped (indexcov.go:815-894), without the PCA columns
+    if (sexes.empty()) fprintf(stderr, "sex chromosomes not found.\n");
+    FILE* ped = fopen((base + ".ped").c_str(), "w");
+    if (!ped) fatal(1, "cannot create %s.ped", base.c_str());
+    bool anygt = false;
+    for (size_t k = 0; k < S; k++) if (mapped[k] > 0 || unmapped[k] > 0) anygt = true;
+    fprintf(ped, "#family_id\tsample_id\tpaternal_id\tmaternal_id\tsex\tphenotype");
+    for (auto& kv : sexes) fprintf(ped, "\tCN%s", kv.first.c_str());
+    fprintf(ped, "\tbins.out\tbins.lo\tbins.hi\tbins.in\tslope\tp.out");
+    if (anygt) fprintf(ped, "\tmapped\tunmapped");
+    fputc('\n', ped);
+    for (size_t k = 0; k < S; k++) {
+        const int inferred = sexes.empty() ? -9 : (int)(0.5 + sexes.begin()->second[k]);
+        fprintf(ped, "unknown\t%s\t-9\t-9\t%d\t-9", names[k].c_str(), inferred);
+        for (auto& kv : sexes) fprintf(ped, "\t%.2f", kv.second[k]);
+        fprintf(ped, "\t%lld\t%lld\t%lld\t%lld\t%.3f\t%.2f", (long long)bins[k * 4 + 0], (long long)bins[k * 4 + 1], (long long)bins[k * 4 + 2],
+                (long long)bins[k * 4 + 3], (double)slopes[k], (double)bins[k * 4 + 0] / (double)bins[k * 4 + 3]);
+        if (anygt) fprintf(ped, "\t%llu\t%llu", (unsigned long long)mapped[k], (unsigned long long)unmapped[k]);
+        fputc('\n', ped);
+    }
+    fclose(ped);
+    fprintf(stderr, "indexcov finished: see %s.bed.gz, .roc and .ped for output (no index.html: plots are not built)\n", base.c_str());
+    gl_ctx_destroy(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ covstats
+static void mean_std(const int32_t* a, size_t n, double& mean, double& sd) {         // covstats.go:78-89
+    const double l = (double)n;
+    mean = 0; sd = 0;
+    for (size_t i = 0; i < n; i++) mean += (double)a[i] / l;
+    for (size_t i = 0; i < n; i++) sd += pow((double)a[i] - mean, 2) / l;
+    sd = sqrt(sd);
+}
+static size_t mad_filter(std::vector<int32_t>& arr, int nmads) {                    // covstats.go:57-76
+    if (!std::is_sorted(arr.begin(), arr.end())) std::sort(arr.begin(), arr.end());
+    const size_t n = arr.size();
+    const int32_t med = arr[n / 2];
+    std::vector<int32_t> um;
+    for (size_t i = n / 2 + 1; i < n; i++) um.push_back(arr[i] - med);
+    std::sort(um.begin(), um.end());
+    const long long upper = (long long)med + (long long)nmads * um[um.size() / 2];
+    size_t i = 0;
+    for (i = 0; i < n; i++) if (arr[i] > upper) break;
+    if (i == n) i = n - 1;                                                          // Go's range loop leaves i at the last index
+    return i;
+}
+
+static int cmd_covstats(int argc, char** argv) {
+    // the header is printed before the arguments are parsed (covstats.go:224-226)
+    printf("coverage\tinsert_mean\tinsert_sd\tinsert_5th\tinsert_95th\ttemplate_mean\ttemplate_sd\tpct_unmapped\tpct_bad_reads\tpct_duplicate\tpct_proper_pair\tread_length\tbam\tsample\n");
+    std::string nstr = "1000000", regions, fasta;
+    ArgParser ap;
+    ap.prog = "goleft covstats";
+    ap.add("n", 'n', &nstr); ap.add("regions", 'r', &regions); ap.add("fasta", 'f', &fasta);
+    ap.parse(argc, argv);
+    if (ap.positional.empty()) ap.fail("bams is required");
+    const int N = atoi(nstr.c_str());
+    gl_ctx* ctx = nullptr;
+    if (gl_ctx_create(0, &ctx) != GL_OK) fatal(1, "goleft covstats: %s", gl_last_error(nullptr));
+    for (const std::string& bam : ap.positional) {
+        glhts::BamHeader hdr;
+        glhts::CovstatsSample cs;
+        std::string e = glhts::bam_covstats_sample(bam, N, 100000, hdr, cs);
+        if (!e.empty()) fatal(1, "%s", e.c_str());
+        std::string names;
+        for (auto& s : hdr.sample_names()) names += (names.empty() ? "" : ",") + s;
+        if (names.empty()) names = "<no-read-groups>";
+        glhts::BaiIndex bai;
+        bool have_idx = false;
+        if (ends_with(bam, ".bam")) {
+            std::string p = bam + ".bai";
+            if (!file_exists(p)) p = bam.substr(0, bam.size() - 4) + ".bai";
+            std::string be = glhts::bai_read(p, bai);
+            if (!be.empty()) fatal(1, "%s", be.c_str());
+            have_idx = true;
+        }
+        double pBad = 0, pDup = 0, pProper = 0, pUnmapped = 0, rlMean = 0, insMean = 0, insSd = 0, tMean = 0, tSd = 0;
+        int pct5 = 0, pct95 = 0, maxRead = 0;
+        if (!cs.read_len.empty()) {                                                 // covstats.go:177-186
+            const double den = (double)(cs.k + cs.n_unmapped);
+            pBad = cs.n_bad / den; pDup = cs.n_dup / den; pProper = cs.n_proper / den; pUnmapped = cs.n_unmapped / den;
+            std::sort(cs.read_len.begin(), cs.read_len.end());
+            double sd;
+            mean_std(cs.read_len.data(), cs.read_len.size(), rlMean, sd);
+            maxRead = cs.read_len.back();
+        }
+        if (!cs.insert.empty()) {                                                   // covstats.go:188-218
+            std::sort(cs.insert.begin(), cs.insert.end());
+            const double l = (double)(cs.insert.size() - 1);
+            pct5 = cs.insert[(size_t)(0.05 * l + 0.5)];
+            pct95 = cs.insert[(size_t)(0.95 * l + 0.5)];
+            const size_t ki = mad_filter(cs.insert, 10);
+            mean_std(cs.insert.data(), ki, insMean, insSd);
+            const size_t kt = mad_filter(cs.tmpl, 10);
+            mean_std(cs.tmpl.data(), kt, tMean, tSd);
+            // template-length histogram H over [MaxReadLength, mean + 4 sd] on the GPU (covstats.go:202-217);
+            // H is part of the reference's Stats struct (consumed by smoove), not of the TSV row
+            const int lo = maxRead, hi = (int)(tMean + tSd * 4) + 1;
+            if (hi > lo && kt > 0) {
+                std::vector<uint64_t> H((size_t)(hi - lo));
+                glck(ctx, gl_bincount_i32(ctx, cs.tmpl.data(), (int64_t)kt, lo, hi, H.data()), "gl_bincount_i32");
+            }
+        }
+        long long genome = 0;
+        unsigned long long mapped = 0;
+        std::string not_found;
+        for (size_t r = 0; r < hdr.refs.size(); r++) {                              // covstats.go:256-267
+            genome += hdr.refs[r].length;
+            if (have_idx) {
+                if (r >= bai.has_stats.size() || !bai.has_stats[r]) {
+                    if (hdr.refs[r].name.find("random") == std::string::npos && hdr.refs[r].length > 10000) not_found += (not_found.empty() ? "" : ",") + hdr.refs[r].name;
+                    continue;
+                }
+                mapped += bai.mapped[r];
+            }
+        }
+        if (!not_found.empty()) fprintf(stderr, "chromosomes: %s not found in %s\n", not_found.c_str(), bam.c_str());
+        if (!regions.empty()) {                                                     // covstats.go:36-55
+            genome = 0;
+            for (const std::string& ln : read_lines(regions, true)) {
+                size_t t1 = ln.find('\t');
+                if (t1 == std::string::npos) continue;
+                size_t t2 = ln.find('\t', t1 + 1);
+                genome += atoll(ln.c_str() + t2 + 1) - atoll(ln.c_str() + t1 + 1);
+            }
+        }
+        const double coverage = (1 - pBad) * (double)mapped * rlMean / (double)genome;     // covstats.go:277
+        printf("%.2f\t%.2f\t%.2f\t%d\t%d\t%.2f\t%.2f\t%.2f\t%.1f\t%.1f\t%.1f\t%d\t%s\t%s\n", coverage, insMean, insSd, pct5, pct95, tMean, tSd,
+               100 * pUnmapped, 100 * pBad, 100 * pDup, 100 * pProper, maxRead, bam.c_str(), names.c_str());
+    }
+    gl_ctx_destroy(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ depthwed
+static int cmd_depthwed(int argc, char** argv) {
+    std::string size;
+    ArgParser ap;
+    ap.prog = "goleft depthwed";
+    ap.add("size", 's', &size, true);
+    ap.parse(argc, argv);
+    if (ap.positional.empty()) ap.fail("beds is required");
+    const long long sz = atoll(size.c_str());
+    const size_t S = ap.positional.size();
+    std::vector<std::string> chroms;
+    std::map<std::string, int> chrom_id;
+    std::vector<int32_t> starts, ends, cid;
+    std::vector<double> means;
+    size_t R = 0;
+    std::string header = "#chrom\tstart\tend";
+    for (size_t f = 0; f < S; f++) {
+        std::string nm = ap.positional[f];                                          // getNameFromFile (depthwed.go:37-46)
+        nm = nm.substr(nm.find_last_of('/') == std::string::npos ? 0 : nm.find_last_of('/') + 1);
+        for (const char* suf : {".gz", ".bed", ".depth"}) if (ends_with(nm, suf)) nm = nm.substr(0, nm.size() - strlen(suf));
+        header += "\t" + nm;
+        std::vector<std::string> lines = read_lines(ap.positional[f], true);
+        if (f == 0) { R = lines.size(); means.resize(S * R); }
+        else if (lines.size() != R) fatal(2, "panic: not all files have same number of records");
+        for (size_t r = 0; r < R; r++) {
+            const std::string& ln = lines[r];
+            size_t t1 = ln.find('\t'), t2 = ln.find('\t', t1 + 1), t3 = ln.find('\t', t2 + 1);
+            if (t1 == std::string::npos || t2 == std::string::npos || t3 == std::string::npos) fatal(1, "bad line in %s: %s", ap.positional[f].c_str(), ln.c_str());
+            means[f * R + r] = strtod(ln.c_str() + t3 + 1, nullptr);
+            if (f == 0) {
+                std::string c = ln.substr(0, t1);
+                auto it = chrom_id.find(c);
+                if (it == chrom_id.end()) { it = chrom_id.emplace(c, (int)chroms.size()).first; chroms.push_back(c); }
+                cid.push_back(it->second);
+                starts.push_back(atoi(ln.c_str() + t1 + 1));
+                ends.push_back(atoi(ln.c_str() + t2 + 1));
+            }
+        }
+    }
+    printf("%s\n", header.c_str());
+    if (R == 0) return 0;
+    gl_ctx* ctx = nullptr;
+    if (gl_ctx_create(0, &ctx) != GL_OK) fatal(1, "goleft depthwed: %s", gl_last_error(nullptr));
+    std::vector<int32_t> os(R), oe(R), oc(R);
+    std::vector<int64_t> out(R * S);
+    int64_t n_out = 0;
+    glck(ctx, gl_depthwed_aggregate(ctx, means.data(), (int32_t)S, (int64_t)R, starts.data(), ends.data(), cid.data(), sz, os.data(), oe.data(),
+                                    oc.data(), out.data(), (int64_t)R, &n_out), "gl_depthwed_aggregate");
+    std::string row;
+    char num[32];
+    for (int64_t g = 0; g < n_out; g++) {
+        row = chroms[oc[g]];
+        snprintf(num, sizeof num, "\t%d\t%d", os[g], oe[g]); row += num;
+        for (size_t s = 0; s < S; s++) { snprintf(num, sizeof num, "\t%lld", (long long)out[(size_t)g * S + s]); row += num; }
+        row += "\n";
+        fwrite(row.data(), 1, row.size(), stdout);
+    }
+    gl_ctx_destroy(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ dispatcher
+static void print_progs() {                                                          // cmd/goleft/goleft.go:33-53
+    fprintf(stderr, "goleft Version: %s (B200 engine: %s)\n\n", kVersion, gl_version());
+    fprintf(stderr, "covstats    : coverage and insert-size statistics on bams by sampling\n");
+    fprintf(stderr, "depth       : parallelize calls to samtools in user-defined windows\n");
+    fprintf(stderr, "depthwed    : matricize output from depth to n-sites * n-samples\n");
+    fprintf(stderr, "indexcov    : quick coverage estimate using only the bam index\n");
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) { print_progs(); return 0; }
+    const std::string prog = argv[1];
+    if (prog == "depth") return cmd_depth(argc - 1, argv + 1);
+    if (prog == "indexcov") return cmd_indexcov(argc - 1, argv + 1);
+    if (prog == "covstats") return cmd_covstats(argc - 1, argv + 1);
+    if (prog == "depthwed") return cmd_depthwed(argc - 1, argv + 1);
+    print_progs();
+    return 1;
+}

@@ -1,0 +1,289 @@
+"""End-to-end: the C++ `goleft` CLI (bin/goleft over libgoleft_b200.so) on files written here, compared with the
+oracle.  Mirrors the reference's functional tests (depth/functional-test.sh, indexcov/functional-tests.sh) in
+shape: exit codes, file names, exact tiling, and — beyond the reference — exact text."""
+import gzip
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from bamutil import make_bai, make_bam  # noqa: E402
+from goleft_b200 import capi  # noqa: E402
+from oracle import loader as orc  # noqa: E402
+
+GOLEFT = os.path.join(ROOT, "bin", "goleft")
+
+
+def run(*args, check=True):
+    p = subprocess.run([GOLEFT, *args], capture_output=True, text=True)
+    if check:
+        assert p.returncode == 0, p.stderr
+    return p
+
+
+def test_dispatcher_and_arg_errors():
+    """no GPU needed for these: cmd/goleft/goleft.go:55-69 and go-arg's exit code 255"""
+    if not os.path.exists(GOLEFT):
+        pytest.skip("bin/goleft not built")
+    assert run().returncode == 0
+    p = run("nosuchprog", check=False)
+    assert p.returncode == 1 and "goleft Version: 0.2.6" in p.stderr
+    p = run("indexcov", "-d", "/tmp/tt", check=False)                       # functional-tests.sh:39-42
+    assert p.returncode == 255 and "error: bam is required" in p.stderr
+    p = run("depth", "x.bam", check=False)
+    assert p.returncode == 255 and "prefix is required" in p.stderr
+    p = run("depthwed", "a.bed", check=False)
+    assert p.returncode == 255 and "size is required" in p.stderr
+
+
+def _make_bam(tmp_path, seed=0, n=40000):
+    rng = np.random.default_rng(seed)
+    refs = [("chrM", 16571), ("chr22", 20001), ("HLA-A*01:01:01:01", 3000)]
+    recs, mates = [], []
+    for tid, (name, L) in enumerate(refs):
+        m = n if tid == 0 else n // 20
+        pos = np.sort(rng.integers(0, max(1, L - 160), m))
+        for p0 in pos:
+            flag = int(rng.choice([99, 147, 0, 16, 0x400 | 99, 0x100, 0x200, 0x800]))
+            mapq = int(rng.choice([0, 1, 20, 60, 60, 60]))
+            kind = int(rng.integers(0, 5))
+            cigar = [[(100, "M")], [(100, "M")], [(45, "M"), (7, "D"), (55, "M")], [(30, "M"), (2, "I"), (68, "M")], [(12, "S"), (88, "M")]][kind]
+            recs.append((tid, int(p0), mapq, flag, cigar))
+            ins = int(rng.normal(350, 40))
+            mates.append((int(p0) + ins - 100, ins) if flag & 1 and not flag & 16 else (max(0, int(p0) - 250), -ins))
+    for _ in range(50):
+        recs.append((-1, -1, 0, 4, [(100, "M")])); mates.append((-1, 0))
+    bam = tmp_path / "s.bam"
+    bam.write_bytes(make_bam(refs, recs, sample="S1", mates=mates))
+    fai = tmp_path / "ref.fa.fai"
+    fai.write_text("".join("%s\t%d\t6\t60\t61\n" % r for r in refs))
+    n_mapped = [sum(1 for r in recs if r[0] == t) for t in range(len(refs))]
+    (tmp_path / "s.bam.bai").write_bytes(make_bai([[0] for _ in refs], [(n_mapped[t], 0) for t in range(len(refs))]))
+    return str(bam), str(tmp_path / "ref.fa"), refs, recs, mates
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W", [100, 250, 13, 2001, 1000000000])
+def test_depth_fai_mode(tmp_path, W):
+    bam, ref, refs, _, _ = _make_bam(tmp_path)
+    prefix = str(tmp_path / "x")
+    run("depth", "-Q", "1", "--ordered", "--windowsize", str(W), "--prefix", prefix, "--reference", ref, bam)
+    seg = capi.bam_segments(bam, 1, 2)
+    exp_hd, exp_ca = b"", b""
+    for tid, (name, L) in enumerate(refs):
+        s, e = seg["segments"][tid]
+        d = orc.pileup_brute(s, e, 0, L)
+        for cs, ce in orc.gen_chunks(L, W):
+            h, c = orc.walk_chunk(name, cs, ce, W, 4, 0, d[cs:ce])
+            exp_hd += h; exp_ca += c
+    assert open(prefix + ".depth.bed", "rb").read() == exp_hd
+    assert open(prefix + ".callable.bed", "rb").read() == exp_ca
+
+
+@pytest.mark.gpu
+def test_depth_chrom_and_flags(tmp_path):
+    bam, ref, refs, _, _ = _make_bam(tmp_path, seed=1)
+    prefix = str(tmp_path / "y")
+    run("depth", "-c", "chr22", "-w", "71", "--mincov", "2", "-m", "9", "--q", "20", "--prefix", prefix, "-r", ref, bam)
+    s, e = capi.bam_segments(bam, 20, 2)["segments"][1]
+    d = orc.pileup_brute(s, e, 0, 20001)
+    exp = orc.walk_chunk("chr22", 0, 20001, 71, 2, 9, d)
+    assert open(prefix + ".chr22.depth.bed", "rb").read() == exp[0]            # depth.go:378-389 file naming
+    assert open(prefix + ".chr22.callable.bed", "rb").read() == exp[1]
+    assert b"EXCESSIVE_COVERAGE" in exp[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W", [10, 50, 1000000])
+def test_depth_bed_mode(tmp_path, W):
+    bam, ref, refs, _, _ = _make_bam(tmp_path, seed=2)
+    bed = tmp_path / "w.bed"
+    regions = [("chr22", 14250, 15500), ("chr22", 1575, 15800), ("chrM", 100, 1000), ("chrM", 2000, 5000), ("chrM", 1, 3),
+               ("chrM", 9, 13), ("chrM", 16, 17), ("chrM", 24, 29), ("chrM", 39, 43)]
+    bed.write_text("".join("%s\t%d\t%d\n" % r for r in regions) + "chrM\t50\t60")     # last line unterminated: dropped like Go's ReadBytes loop
+    prefix = str(tmp_path / "z")
+    run("depth", "--bed", str(bed), "-Q", "1", "--windowsize", str(W), "--prefix", prefix, "--reference", ref, bam)
+    seg = capi.bam_segments(bam, 1, 2)
+    tid_of = {n: i for i, (n, _) in enumerate(refs)}
+    exp_hd, exp_ca = b"", b""
+    for name, rs, re in regions:
+        s, e = seg["segments"][tid_of[name]]
+        h, c = orc.walk_chunk(name, rs, re, W, 4, 0, orc.pileup_brute(s, e, rs, re))
+        exp_hd += h; exp_ca += c
+    assert open(prefix + ".depth.bed", "rb").read() == exp_hd
+    assert open(prefix + ".callable.bed", "rb").read() == exp_ca
+
+
+@pytest.mark.gpu
+def test_depth_empty_bam(tmp_path):
+    """check_empty (functional-test.sh:102-109)"""
+    refs = [("chrM", 16571), ("chr22", 20001)]
+    (tmp_path / "e.bam").write_bytes(make_bam(refs, []))
+    (tmp_path / "r.fa.fai").write_text("".join("%s\t%d\t6\t60\t61\n" % r for r in refs))
+    prefix = str(tmp_path / "e")
+    run("depth", "--windowsize", "10", "--q", "1", "--mincov", "4", "--reference", str(tmp_path / "r.fa"), "--processes", "1",
+        "--prefix", prefix, str(tmp_path / "e.bam"))
+    ca = open(prefix + ".callable.bed").read().splitlines()
+    assert ca == ["chrM\t0\t16571\tNO_COVERAGE", "chr22\t0\t20001\tNO_COVERAGE"]
+    hd = [ln.split("\t") for ln in open(prefix + ".depth.bed").read().splitlines()]
+    assert len(hd) == 1658 + 2001 and all(r[3] == "0" for r in hd)
+
+
+def _cohort_bais(tmp_path, S=7, seed=3):
+    rng = np.random.default_rng(seed)
+    refs = [("1", 3_000_000), ("2", 2_000_000), ("GL000207.1", 4262), ("X", 1_500_000), ("Y", 600_000), ("NC_007605", 171823)]
+    fai = tmp_path / "g.fa.fai"
+    fai.write_text("".join("%s\t%d\t6\t60\t61\n" % r for r in refs))
+    paths, lin = [], []
+    for k in range(S):
+        male = k % 2 == 0
+        per_ref = []
+        v = 100000
+        for name, L in refs:
+            nt = L // 16384 + 1
+            if k == 3 and name == "2":
+                nt -= 5                                            # a shorter sample: "0" columns
+            scale = {"X": 0.5 if male else 1.0, "Y": 0.5 if male else 0.01}.get(name, 1.0)
+            sizes = np.maximum(0, rng.normal(1.6e9 * scale, 1.5e8, nt)).astype(np.int64)
+            iv = [v]
+            for sz in sizes:
+                v += int(sz); iv.append(v)
+            per_ref.append(iv if nt > 0 else [])
+        p = tmp_path / ("smp%d.rest.bai" % k)
+        p.write_bytes(make_bai(per_ref, [(1000 * (k + 1), 10 + k) for _ in refs]))
+        paths.append(str(p)); lin.append(per_ref)
+    return refs, str(fai), paths, lin
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extranorm", [False, True])
+def test_indexcov_cohort(tmp_path, extranorm):
+    refs, fai, paths, lin = _cohort_bais(tmp_path)
+    out = tmp_path / "tt"
+    args = ["indexcov", "-d", str(out), "--fai", fai] + (["-n"] if extranorm else []) + paths
+    p = run(*args)
+    assert "indexcov finished" in p.stderr
+    S = len(paths)
+    # oracle
+    med, depths = [], []
+    for k in range(S):
+        voff = np.array([v for r in lin[k] for v in r], np.uint64)
+        ptr = np.concatenate([[0], np.cumsum([len(r) for r in lin[k]])]).astype(np.int64)
+        sizes, sptr = orc.ic_sizes(voff, ptr)
+        m = orc.ic_median(sizes)
+        med.append(m)
+        d = orc.ic_normalize(sizes, float(m))
+        depths.append([d[sptr[r]:sptr[r + 1]] for r in range(len(refs))])
+    names = ["smp%d-rest" % k for k in range(S)]                  # GetShortName for .bai (indexcov.go:238-245)
+    exp_rows = ["#chrom\tstart\tend\t" + "\t".join(names)]
+    bins = np.zeros((S, 4), np.int64)
+    roc_txt = ""
+    for r, (name, L) in enumerate(refs):
+        if name.startswith("NC"):
+            continue                                                # default --excludepatt
+        ds = [depths[k][r] for k in range(S)]
+        longest = max(len(d) for d in ds)
+        is_sex = name in ("X", "Y")
+        if extranorm and not is_sex:
+            mat = np.zeros((S, longest), np.float32)
+            for k in range(S):
+                mat[k, :len(ds[k])] = ds[k]
+            mat = orc.ic_xnorm(mat, np.array([len(d) for d in ds], np.int32))
+            ds = [mat[k, :len(ds[k])] for k in range(S)]
+        for i in range(longest):
+            exp_rows.append("%s\t%d\t%d\t" % (name, i * 16384, (i + 1) * 16384) +
+                            "\t".join("0" if i >= len(ds[k]) else "%.3g" % ds[k][i] for k in range(S)))
+        if not is_sex:
+            for k in range(S):
+                bins[k] += orc.ic_bins(ds[k], longest)
+        rocs = [orc.ic_roc(orc.ic_counts(ds[k])) for k in range(S)]
+        roc_txt += "#chrom\tcov\t" + "\t".join(names) + "\n"
+        for i in range(70):
+            roc_txt += "%s\t%.2f\t" % (name, i / (70 * (2.0 / 3.0))) + "\t".join("%.2f" % rocs[k][i] for k in range(S)) + "\n"
+    got = gzip.open(str(out / "tt-indexcov.bed.gz"), "rt").read().splitlines()
+    assert got == exp_rows
+    assert open(str(out / "tt-indexcov.roc")).read() == roc_txt
+    ped = [ln.split("\t") for ln in open(str(out / "tt-indexcov.ped")).read().splitlines()]
+    assert ped[0][:8] == ["#family_id", "sample_id", "paternal_id", "maternal_id", "sex", "phenotype", "CNX", "CNY"]
+    assert len({len(r) for r in ped}) == 1                        # num_colcounts == 1 (functional-tests.sh:26-30,50)
+    col = ped[0].index("bins.out")
+    for k in range(S):
+        assert [int(x) for x in ped[k + 1][col:col + 4]] == bins[k].tolist()
+        assert ped[k + 1][ped[0].index("CNX")] == "%.2f" % orc.ic_getcn(depths[k][3])
+        assert ped[k + 1][4] == str(int(0.5 + orc.ic_getcn(depths[k][3])))
+        assert ped[k + 1][-2:] == [str(1000 * (k + 1) * len(refs)), str((10 + k) * len(refs))]
+
+
+@pytest.mark.gpu
+def test_indexcov_no_usable_chromosomes(tmp_path):
+    refs = [("1", 100000)]
+    (tmp_path / "g.fa.fai").write_text("1\t100000\t6\t60\t61\n")
+    p = tmp_path / "a.bai"
+    p.write_bytes(make_bai([[5]], [None]))                          # one interval -> no tiles
+    r = run("indexcov", "-d", str(tmp_path / "o"), "--fai", str(tmp_path / "g.fa.fai"), str(p), check=False)
+    assert r.returncode == 1 and "no usable chromsomes in bam" in r.stderr     # functional-tests.sh:58-62
+
+
+@pytest.mark.gpu
+def test_covstats(tmp_path):
+    bam, ref, refs, recs, mates = _make_bam(tmp_path, seed=4, n=150000)
+    p = run("covstats", "-n", "20000", bam)
+    lines = p.stdout.splitlines()
+    assert lines[0].startswith("coverage\tinsert_mean\tinsert_sd\tinsert_5th")
+    t = lines[1].split("\t")
+    # restate BamStats (covstats.go:122-220) on the records written above
+    sizes, ins, tm = [], [], []
+    k = nbad = ndup = nproper = nun = 0
+    for i, (tid, pos, mapq, flag, cigar) in enumerate(recs):
+        if i < 100000:
+            continue
+        if len(ins) >= 20000:
+            break
+        if flag & 4:
+            nun += 1; continue
+        k += 1
+        if flag & (0x400 | 0x200):
+            ndup += 1 if flag & 0x400 else 0
+            nbad += 1; continue
+        if flag & 2:
+            nproper += 1
+        if len(sizes) < 40000:
+            sizes.append(sum(l for l, op in cigar if op in "MIS=X"))
+        elif not ins:
+            break
+        mp, tl = mates[i]
+        if pos < mp and flag & 2 and len(cigar) == 1 and cigar[0][1] == "M":
+            ins.append(mp - (pos + cigar[0][0])); tm.append(tl)
+    out6, H = orc.cs_tail(np.array(ins, np.int32), np.array(tm, np.int32), max(sizes))
+    rl = np.sort(np.array(sizes))
+    rl_mean = 0.0
+    for a in rl:
+        rl_mean += float(a) / len(rl)
+    mapped = sum(1 for r in recs if r[0] >= 0)
+    cov = (1 - nbad / (k + nun)) * mapped * rl_mean / sum(L for _, L in refs)
+    exp = ["%.2f" % cov, "%.2f" % out6[2], "%.2f" % out6[3], "%d" % out6[0], "%d" % out6[1], "%.2f" % out6[4], "%.2f" % out6[5],
+           "%.2f" % (100 * nun / (k + nun)), "%.1f" % (100 * nbad / (k + nun)), "%.1f" % (100 * ndup / (k + nun)),
+           "%.1f" % (100 * nproper / (k + nun)), "%d" % max(sizes), bam, "S1"]
+    assert t == exp
+
+
+@pytest.mark.gpu
+def test_depthwed(tmp_path):
+    rng = np.random.default_rng(5)
+    rows = [("chr1", a, min(a + 250, 10100)) for a in range(0, 10100, 250)] + [("chrX", a, min(a + 250, 1300)) for a in range(0, 1300, 250)]
+    files, means = [], []
+    for k in range(4):
+        vals = [float("%.4g" % x) for x in rng.gamma(8, 4, len(rows))]
+        p = tmp_path / ("s%d.depth.bed" % k)
+        p.write_text("".join("%s\t%d\t%d\t%.4g\n" % (c, s, e, v) for (c, s, e), v in zip(rows, vals)))
+        files.append(str(p)); means.append(vals)
+    out = run("depthwed", "-s", "1000", *files).stdout.splitlines()
+    cid = {"chr1": 0, "chrX": 1}
+    s_, e_, c_, m_ = orc.depthwed(np.array(means), [r[1] for r in rows], [r[2] for r in rows], [cid[r[0]] for r in rows], 1000)
+    assert out[0] == "#chrom\tstart\tend\ts0\ts1\ts2\ts3"
+    exp = ["%s\t%d\t%d\t" % (["chr1", "chrX"][c], s, e) + "\t".join(str(int(v)) for v in row) for s, e, c, row in zip(s_, e_, c_, m_)]
+    assert out[1:] == exp

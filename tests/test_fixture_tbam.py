@@ -1,8 +1,7 @@
 """The reference's own fixture depth/test/t.bam (as tests/golden/t_bam_segments.npz, see make_tbam_fixture.py)
 through the oracle (CPU) and through the CUDA path (GPU), in the configurations of depth/functional-test.sh."""
 import os
-import struct
-import zlib
+import sys
 
 import numpy as np
 import pytest
@@ -11,6 +10,7 @@ from goleft_b200 import capi
 from oracle import loader as orc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 FAI_WINDOWS = [100, 1000000000, 55, 60, 71, 13, 2001]          # functional-test.sh:45-70
 BED_WINDOWS = [10, 1000000, 50, 55, 60, 71, 13, 2002]          # functional-test.sh:73-97
 WINDOWS_BED = [("chr22", 14250, 15500), ("chr22", 1575, 15800), ("chrM", 100, 1000), ("chrM", 2000, 5000), ("chrM", 1, 3),
@@ -73,32 +73,7 @@ def test_oracle_w250_row_counts():
 
 
 # ------------------------------------------------------------------ the feeder on a BAM written here
-def _bgzf(payload: bytes) -> bytes:
-    out = b""
-    for i in range(0, len(payload), 60000):
-        chunk = payload[i:i + 60000]
-        c = zlib.compressobj(6, zlib.DEFLATED, -15)
-        comp = c.compress(chunk) + c.flush()
-        bsize = 18 + len(comp) + 8
-        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize - 1) + comp
-        out += struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk))
-    return out + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
-
-
-def _bam(refs, records) -> bytes:
-    text = b"@HD\tVN:1.6\tSO:coordinate\n@RG\tID:a\tSM:sampleA\n"
-    b = b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
-    for n, l in refs:
-        b += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
-    ops = "MIDNSHP=X"
-    for tid, pos, mapq, flag, cigar in records:
-        name = b"r\0"
-        cig = b"".join(struct.pack("<I", (ln << 4) | ops.index(op)) for ln, op in cigar)
-        lseq = sum(ln for ln, op in cigar if op in "MIS=X")
-        body = struct.pack("<iiBBHHHiiii", tid, pos, len(name), mapq, 0, len(cigar), flag, lseq, -1, -1, 0)
-        body += name + cig + b"\0" * ((lseq + 1) // 2) + b"\xff" * lseq
-        b += struct.pack("<i", len(body)) + body
-    return _bgzf(b)
+from bamutil import make_bam as _bam
 
 
 def test_feeder_on_synthetic_bam(tmp_path):
