@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -94,6 +94,15 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read+write per launch of `kernel` from the committed ncu --set full capture (profiles/), or None"""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))
+        return int(j[kernel]["traffic_bytes"])
+    except Exception:
+        return None
 
 
 def dist_env():
@@ -150,9 +159,10 @@ def run_reference(args):
            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
            "config": {"workload": "depth: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500, 1 sample",
                       "window": W, "mincov": MINCOV, "segments": int(s.size)},
-           "cpu_baseline": {"value": val, "unit": "Mbases/s", "cores": threads, "kind": "port",
-                            "sample": "whole chr20 contig, 7 chunks of 10 Mb, chunk-parallel; per-base counting + "
-                                      "window/class walk + BED text (samtools text printing/parsing excluded)"},
+           "cpu_baseline": {"value": val, "unit": "Mbases/s", "cores": min(threads, len(chunks)), "kind": "port",
+                            "sample": "whole chr20 contig, 7 chunks of 10 Mb, one thread per chunk (the reference's own unit of "
+                                      "parallelism, depth.go:132,392); per-base counting + window/class walk + BED text "
+                                      "(samtools text printing/parsing excluded)"},
            "e2e": {"value": val, "unit": "Mbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -321,7 +331,7 @@ def main():
                        "d2h_bytes_per_step": 8 * n_win + 5 * n_runs, "ms_per_step": ms_e2e / args.steps},
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
                             "alg_bytes_per_launch": alg[dom], "kernel_ms": k_ms,
                             "step": {"alg_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                                      "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
@@ -342,9 +352,10 @@ def main():
             while reps < 3 and tot < 20.0:
                 dt, _ = cpu_depth_pass(orc, s, e, L, threads, chunks)
                 tot += dt; reps += 1
-            out["cpu_baseline"] = {"value": L / (tot / reps) / 1e6, "unit": "Mbases/s", "cores": threads, "kind": "port",
-                                   "sample": f"{reps} x whole chr20 contig (7 chunks of 10 Mb, chunk-parallel): per-base "
-                                             "counting + window/class walk + BED text; samtools text print/parse excluded"}
+            out["cpu_baseline"] = {"value": L / (tot / reps) / 1e6, "unit": "Mbases/s", "cores": min(threads, len(chunks)), "kind": "port",
+                                   "sample": f"{reps} x whole chr20 contig (7 chunks of 10 Mb, one thread per chunk = the reference's "
+                                             "unit of parallelism): per-base counting + window/class walk + BED text; "
+                                             "samtools text print/parse excluded"}
         print(json.dumps(out), flush=True)
 
     d_s.free(); d_e.free()
