@@ -112,6 +112,11 @@ _proto("gl_bai_read", C.c_int, C.c_char_p, C.POINTER(_vp), _vp, C.c_int64)
 _proto("gl_bai_n_refs", C.c_int, _vp, _i32p, _u64p)
 _proto("gl_bai_ref", C.c_int, _vp, C.c_int32, C.POINTER(_vp), _i64p, _u64p, _u64p, _i32p)
 _proto("gl_bai_free", None, _vp)
+_proto("gl_pack_segments16_bound", C.c_int64, C.c_int64)
+_proto("gl_pack_segments16", C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_depth_add_segments_packed16", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
+_proto("gl_depth_region_packed16", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
+       C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_depth_format_chunk", C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int64, _vp, _vp,
        C.c_int64, C.POINTER(_vp), _i64p, C.POINTER(_vp), _i64p)
 _proto("gl_free_text", None, _vp)
@@ -154,6 +159,24 @@ def format_chunk(chrom: str, rs: int, re: int, W: int, win_sum: np.ndarray, run_
     finally:
         lib.gl_free_text(d)
         lib.gl_free_text(c)
+
+
+def pack_segments16(start: np.ndarray, end: np.ndarray):
+    """Host-only: (anchors int32[nb], off uint16[nb*256], len uint16[nb*256]) — the feeder's compact format."""
+    start, end = _as(start, np.int32), _as(end, np.int32)
+    nb = C.c_int64(0)
+    cap = max(1, int(lib.gl_pack_segments16_bound(start.size)) // 8 + start.size // 256 + 2)
+    while True:
+        a = np.empty(cap, np.int32)
+        o = np.empty(cap * 256, np.uint16)
+        ln = np.empty(cap * 256, np.uint16)
+        rc = lib.gl_pack_segments16(_ptr(start), _ptr(end), start.size, _ptr(a), _ptr(o), _ptr(ln), cap, C.byref(nb))
+        if rc == GL_OK:
+            k = nb.value
+            return a[:k], o[: k * 256], ln[: k * 256]
+        if rc != GL_ERANGE:
+            raise GlError(rc, "gl_pack_segments16: bad arguments")
+        cap = nb.value + 1
 
 
 def bam_segments(path: str, min_mapq: int = 1, threads: int = 4, only_tid: int = -1):
@@ -315,6 +338,22 @@ class Ctx:
 
     def depth_add_segments_device(self, d_start: DevBuf, d_end: DevBuf, n: int, offset: int = 0):
         self._ck(lib.gl_depth_add_segments_device(self.h, d_start.ptr + 4 * offset, d_end.ptr + 4 * offset, n))
+
+    def depth_add_segments_packed16(self, anchors: np.ndarray, off: np.ndarray, ln: np.ndarray):
+        self._ck(lib.gl_depth_add_segments_packed16(self.h, _ptr(anchors), _ptr(off), _ptr(ln), anchors.size))
+
+    def depth_region_packed16(self, rs: int, re: int, anchors, off, ln, W: int, mincov: int = 4, maxmean: int = 0,
+                              run_break: int = 0, out=None):
+        n_win = (re - 1) // W - rs // W + 1
+        if out is None:
+            out = (np.empty(n_win, np.int64), np.empty(max(1024, (re - rs) // 8), np.int32),
+                   np.empty(max(1024, (re - rs) // 8), np.uint8))
+        s, r0, rc_ = out
+        nw, nr = C.c_int64(0), C.c_int64(0)
+        self._ck(lib.gl_depth_region_packed16(self.h, rs, re, _ptr(anchors), _ptr(off), _ptr(ln), anchors.size, W, mincov,
+                                              maxmean, run_break, _ptr(s), s.size, C.byref(nw), _ptr(r0), _ptr(rc_),
+                                              min(r0.size, rc_.size), C.byref(nr)))
+        return s[: nw.value], r0[: nr.value], rc_[: nr.value]
 
     def depth_reduce(self, W: int, mincov: int = 4, maxmean: int = 0, run_break: int = 0):
         self._ck(lib.gl_depth_reduce(self.h, W, mincov, maxmean, run_break))

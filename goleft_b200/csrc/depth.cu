@@ -135,6 +135,16 @@ __global__ void __launch_bounds__(256) depth_scatter_kernel(const int* __restric
     warp_tile_add(tile_sum, tE, cE, -1, lane);
 }
 
+// packed16 -> (start,end): one CTA per 256-slot block (host/seg_pack.cpp); empty slots become empty segments
+__global__ void __launch_bounds__(256) depth_unpack16_kernel(const int* __restrict__ anchors, const unsigned short* __restrict__ off,
+                                                            const unsigned short* __restrict__ len, int* __restrict__ start,
+                                                            int* __restrict__ end) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int s = anchors[blockIdx.x] + (int)off[i];
+    start[i] = s;
+    end[i] = s + (int)len[i];
+}
+
 // K_super: super_sum[st] = sum of the 64 tile sums of super-tile st (one warp each).  Doing this in the
 // scatter itself would put every warp's red on the same handful of addresses — measured 7x slower.
 __global__ void __launch_bounds__(256) depth_super_sum_kernel(const int* __restrict__ tile_sum, int* __restrict__ super_sum,
@@ -1064,6 +1074,54 @@ int gl_depth_add_segments(gl_ctx* ctx, const int32_t* start, const int32_t* end,
     return GL_OK;
 }
 
+int gl_depth_add_segments_packed16(gl_ctx* ctx, const int32_t* anchors, const uint16_t* off, const uint16_t* len, int64_t n_blocks) {
+    GL_CHECK(gl_use(ctx));
+    if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_add_segments_packed16: no region open (call gl_depth_begin)");
+    if (n_blocks < 0 || (n_blocks > 0 && (!anchors || !off || !len))) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments_packed16: bad argument");
+    if (n_blocks == 0) return GL_OK;
+    const int64_t n = n_blocks * 256;
+    GL_CHECK(store_reserve(ctx, ctx->store_n + n));
+    // staging for the packed bytes: anchors | off | len
+    const size_t b_anchor = (size_t)n_blocks * 4, b_u16 = (size_t)n * 2;
+    GL_CHECK(gl_buf_reserve(ctx, ctx->packed, ((b_anchor + 255) & ~size_t(255)) + 2 * ((b_u16 + 255) & ~size_t(255))));
+    char* d_anchor = static_cast<char*>(ctx->packed.p);
+    char* d_off = d_anchor + ((b_anchor + 255) & ~size_t(255));
+    char* d_len = d_off + ((b_u16 + 255) & ~size_t(255));
+    const bool pinned = is_pinned_host(anchors) && is_pinned_host(off) && is_pinned_host(len);
+    if (!pinned) {       // pageable: let the runtime stage it (the fast path is pinned feeder buffers)
+        GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    }
+    // the previous unpack must be done with the staging buffer before it is overwritten
+    GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
+    GL_CUDA(ctx, cudaMemcpyAsync(d_anchor, anchors, b_anchor, cudaMemcpyHostToDevice, ctx->copy_stream));
+    GL_CUDA(ctx, cudaMemcpyAsync(d_off, off, b_u16, cudaMemcpyHostToDevice, ctx->copy_stream));
+    GL_CUDA(ctx, cudaMemcpyAsync(d_len, len, b_u16, cudaMemcpyHostToDevice, ctx->copy_stream));
+    GL_CUDA(ctx, cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
+    GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
+    {
+        gl_prof_scope prof(ctx, "depth_unpack16_kernel");
+        depth_unpack16_kernel<<<(unsigned)n_blocks, 256, 0, ctx->stream>>>(
+            reinterpret_cast<const int*>(d_anchor), reinterpret_cast<const unsigned short*>(d_off),
+            reinterpret_cast<const unsigned short*>(d_len), static_cast<int*>(ctx->store_s.p) + ctx->store_n,
+            static_cast<int*>(ctx->store_e.p) + ctx->store_n);
+    }
+    GL_LAUNCHED(ctx, 1);
+    GL_CUDA(ctx, cudaEventRecord(ctx->ev_used[0], ctx->stream));
+    if (!pinned) GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    if (!ctx->batches.empty() && ctx->batches.back().s == nullptr &&
+        ctx->batches.back().off + ctx->batches.back().n == ctx->store_n) {
+        ctx->batches.back().n += n;
+    } else {
+        gl_seg_batch b;
+        b.off = ctx->store_n; b.n = n;
+        ctx->batches.push_back(b);
+    }
+    ctx->store_n += n;
+    ctx->g_valid = false;
+    ctx->depth_reduced = false;
+    return GL_OK;
+}
+
 int gl_depth_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break) {
     GL_CHECK(gl_use(ctx));
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_reduce: no region open");
@@ -1156,6 +1214,19 @@ int gl_depth_perbase(gl_ctx* ctx, int32_t* depth_out) {
     return GL_OK;
 }
 
+static int region_fetch(gl_ctx* ctx, int64_t* sum_out, int64_t win_cap, int64_t* n_windows, int32_t* run_start, uint8_t* run_class,
+                        int64_t run_cap, int64_t* n_runs);
+
+int gl_depth_region_packed16(gl_ctx* ctx, int64_t region_start, int64_t region_end, const int32_t* anchors, const uint16_t* off,
+                             const uint16_t* len, int64_t n_blocks, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break,
+                             int64_t* sum_out, int64_t win_cap, int64_t* n_windows, int32_t* run_start, uint8_t* run_class,
+                             int64_t run_cap, int64_t* n_runs) {
+    GL_CHECK(gl_depth_begin(ctx, region_start, region_end));
+    GL_CHECK(gl_depth_add_segments_packed16(ctx, anchors, off, len, n_blocks));
+    GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, run_break));
+    return region_fetch(ctx, sum_out, win_cap, n_windows, run_start, run_class, run_cap, n_runs);
+}
+
 int gl_depth_region(gl_ctx* ctx, int64_t region_start, int64_t region_end, const int32_t* start, const int32_t* end,
                     int64_t n, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break, int64_t* sum_out,
                     int64_t win_cap, int64_t* n_windows, int32_t* run_start, uint8_t* run_class, int64_t run_cap,
@@ -1163,6 +1234,11 @@ int gl_depth_region(gl_ctx* ctx, int64_t region_start, int64_t region_end, const
     GL_CHECK(gl_depth_begin(ctx, region_start, region_end));
     GL_CHECK(gl_depth_add_segments(ctx, start, end, n));
     GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, run_break));
+    return region_fetch(ctx, sum_out, win_cap, n_windows, run_start, run_class, run_cap, n_runs);
+}
+
+static int region_fetch(gl_ctx* ctx, int64_t* sum_out, int64_t win_cap, int64_t* n_windows, int32_t* run_start, uint8_t* run_class,
+                        int64_t run_cap, int64_t* n_runs) {
     const int64_t nw = ctx->n_windows, nr = ctx->n_runs;
     if (n_windows) *n_windows = nw;
     if (n_runs) *n_runs = nr;

@@ -40,6 +40,7 @@ struct gl_ctx {
     int64_t n_windows = 0, n_runs = 0; int32_t max_depth = 0;
     std::vector<gl_seg_batch> batches;      // segments added since gl_depth_begin
     gl_buf store_s, store_e;                // host-uploaded segments, contiguous
+    gl_buf packed;                          // staging for packed16 uploads
     int64_t store_n = 0;
     bool copies_pending = false;            // H2D into the store still in flight on copy_stream
     bool g_valid = false;                   // the HBM difference array holds every batch (general path)

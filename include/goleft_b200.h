@@ -102,6 +102,17 @@ int  gl_depth_begin(gl_ctx* ctx, int64_t region_start, int64_t region_end);
 int  gl_depth_add_segments(gl_ctx* ctx, const int32_t* start, const int32_t* end, int64_t n);
 int  gl_depth_add_segments_device(gl_ctx* ctx, const int32_t* d_start, const int32_t* d_end, int64_t n);
 
+/* The feeder's compact format ("packed16", half the PCIe bytes): blocks of 256 slots, one int32 anchor per
+ * block, slot k = [anchor+off[k], anchor+off[k]+len[k]) with uint16 off/len (len 0 = empty slot).
+ * gl_pack_segments16 builds it on the host from plain arrays (splitting segments longer than 65535, opening
+ * a new block when a start does not fit 16 bits); returns GL_ERANGE with the needed *n_blocks when
+ * cap_blocks is too small (pass NULL outputs to only count).  The GPU unpacks into its segment store. */
+int64_t gl_pack_segments16_bound(int64_t n);
+int  gl_pack_segments16(const int32_t* start, const int32_t* end, int64_t n, int32_t* anchors, uint16_t* off,
+                        uint16_t* len, int64_t cap_blocks, int64_t* n_blocks);
+int  gl_depth_add_segments_packed16(gl_ctx* ctx, const int32_t* anchors, const uint16_t* off, const uint16_t* len,
+                                    int64_t n_blocks);
+
 /* One fused pass: prefix scan -> per-base depth (never written to HBM) ->
  *   (a) per-window int64 sums for genome-aligned windows of size W clipped to the region:
  *       window k covers [max(rs,(rs/W+k)*W), min(re,(rs/W+k+1)*W)),
@@ -138,6 +149,12 @@ int  gl_depth_region(gl_ctx* ctx, int64_t region_start, int64_t region_end,
                      int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break,
                      int64_t* sum_out, int64_t win_cap, int64_t* n_windows,
                      int32_t* run_start, uint8_t* run_class, int64_t run_cap, int64_t* n_runs);
+
+int  gl_depth_region_packed16(gl_ctx* ctx, int64_t region_start, int64_t region_end, const int32_t* anchors,
+                              const uint16_t* off, const uint16_t* len, int64_t n_blocks,
+                              int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break,
+                              int64_t* sum_out, int64_t win_cap, int64_t* n_windows,
+                              int32_t* run_start, uint8_t* run_class, int64_t run_cap, int64_t* n_runs);
 
 /* Host-side text: reproduces the rows the reference callback writes for ONE chunk
  * [rs,re) (depth/depth.go:293-305,326-358 incl. the chunk-edge quirks) from window sums

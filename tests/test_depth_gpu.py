@@ -273,3 +273,30 @@ def test_full_size_chr20(ctx):
     assert np.array_equal(ws2, es) and np.array_equal(wm2, em)
     ctx.depth_set_path(0)
     ds.free(); de.free()
+
+
+def test_packed16_path(ctx):
+    """the feeder's compact format (half the PCIe bytes) gives the same integers as plain int32 arrays"""
+    L = 5_000_000
+    s, e = synth.segments(synth.reads(L, contig_index=9))
+    a, o, ln = capi.pack_segments16(s, e)
+    exp = orc.pileup_diff(s, e, 0, L)
+    es, _ = orc.window_sums(exp, 0, L, 500)
+    ea, ec = orc.class_runs(exp, 0, L, 4, 0, 1_000_000)
+    ws, r0, rc = ctx.depth_region_packed16(0, L, a, o, ln, 500, 4, 0, run_break=1_000_000)
+    assert ctx.depth_last_path() == 1
+    assert np.array_equal(ws, es) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
+    # two packed batches + one plain batch in one region, sub-region with clipping
+    h = s.size // 3
+    a1, o1, l1 = capi.pack_segments16(s[:h], e[:h])
+    a2, o2, l2 = capi.pack_segments16(s[h:2 * h], e[h:2 * h])
+    ctx.depth_begin(1234, 4_000_000)
+    ctx.depth_add_segments_packed16(a1, o1, l1)
+    ctx.depth_add_segments_packed16(a2, o2, l2)
+    ctx.depth_add_segments(s[2 * h:], e[2 * h:])
+    ctx.depth_reduce(250, 4, 0, 0)
+    exp = orc.pileup_diff(s, e, 1234, 4_000_000)
+    assert np.array_equal(ctx.depth_get_windows(), orc.window_sums(exp, 1234, 4_000_000, 250)[0])
+    r0, rc = ctx.depth_get_runs()
+    ea, ec = orc.class_runs(exp, 1234, 4_000_000, 4, 0, 0)
+    assert np.array_equal(r0, ea) and np.array_equal(rc, ec)

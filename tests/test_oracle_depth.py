@@ -244,3 +244,31 @@ def test_go_g_format_table():
              0.5: "0.5", 2.0 / 3.0: "0.6667", 99995.0: "9.999e+04" if "%.4g" % 99995.0 == "9.999e+04" else "1e+05"}
     for v, exp in table.items():
         assert "%.4g" % v == exp, v
+
+
+# ------------------------------------------------------------------ the feeder's packed16 format (host-only)
+def _unpack16(a, o, ln):
+    st = np.repeat(a.astype(np.int64), 256) + o
+    en = st + ln
+    keep = ln > 0
+    return st[keep], en[keep]
+
+
+def test_pack_segments16_roundtrip():
+    rng = np.random.default_rng(9)
+    # BAM-like: nearly sorted, a sparse stretch, long segments that must be split, empties that are dropped
+    s = np.sort(rng.integers(0, 3_000_000, 50_000)).astype(np.int32)
+    s[20_000:] += 50_000_000
+    e = (s + rng.integers(1, 300, s.size)).astype(np.int32)
+    s[1000], e[1000] = s[1000], s[1000] + 200_000            # split into 65535-base pieces
+    e[2000] = s[2000]                                        # empty
+    s[3000] = s[2999] - 9000                                 # starts earlier than its predecessor (fits below the anchor)
+    e[3000] = s[3000] + 100
+    a, o, ln = capi.pack_segments16(s, e)
+    assert o.size == a.size * 256 and ln.dtype == np.uint16
+    st, en = _unpack16(a, o, ln)
+    # same multiset of covered bases: compare per-base depth over a window that contains everything interesting
+    for lo, hi in [(0, 3_100_000), (50_000_000, 53_100_000)]:
+        assert np.array_equal(orc.pileup_diff(st.astype(np.int32), en.astype(np.int32), lo, hi), orc.pileup_diff(s, e, lo, hi))
+    assert a.size <= s.size // 256 + 8                       # nearly every block is full
+    assert capi.pack_segments16(np.zeros(0, np.int32), np.zeros(0, np.int32))[0].size == 0
