@@ -477,6 +477,14 @@ class Ctx:
         self._ck(lib.gl_indexcov_xnorm(self.h, _ptr(d), _ptr(lens), S, T))
         return d
 
+    def indexcov_cohort_device(self, d_sizes: DevBuf, d_sample_ptr: DevBuf, S: int, d_medians: DevBuf, d_depth: Optional[DevBuf]):
+        self._ck(lib.gl_indexcov_cohort_device(self.h, d_sizes.ptr, d_sample_ptr.ptr, S, d_medians.ptr,
+                                               d_depth.ptr if d_depth is not None else None))
+
+    def depthwed_aggregate_device(self, d_means: DevBuf, S: int, R: int, d_grp: Optional[DevBuf], n_out: int, d_out: DevBuf):
+        self._ck(lib.gl_depthwed_aggregate_device(self.h, d_means.ptr, S, R, d_grp.ptr if d_grp is not None else None, n_out,
+                                                  d_out.ptr))
+
     # ---- covstats / depthwed
     def bincount(self, v: np.ndarray, lo: int, hi: int) -> np.ndarray:
         v = _as(v, np.int32)

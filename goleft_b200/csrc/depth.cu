@@ -57,7 +57,7 @@ __device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
 // 16-byte-chunk swizzle inside a tile (1024 chunks): conflict-free both for a warp touching 32
 // consecutive chunks and for a warp whose lane l touches chunks 4l..4l+3 (the blocked layout).
 __device__ __forceinline__ int swz_chunk(int c) { return c ^ ((c >> 2) & 7); }
-__device__ __forceinline__ int swz_elem(int e) { return (swz_chunk(e >> 2) << 2) | (e & 3); }
+__device__ __forceinline__ int swz_elem(int e) { return e ^ (((e >> 4) & 7) << 2); }   // == (swz_chunk(e>>2)<<2) | (e&3)
 
 // ================================================================================================
 // GENERAL path, K_scatter.  One thread = 4 segments (two 128-bit loads), 8 fire-and-forget reds.
@@ -310,6 +310,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     __shared__ int s_warp_tot[kWarps];
     __shared__ int s_warp_cnt[kWarps];
     __shared__ int s_warp_max[kWarps];
+    __shared__ int s_has_break;
     __shared__ long long s_run_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -334,11 +335,20 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     }
     const int lane_excl = inc - x[15];
     if (lane == 31) s_warp_tot[warp] = inc;
+    if (tid == 0) {
+        // does a forced run break (multiple of run_break) fall inside this tile?  (absolute positions are < 2^32)
+        int hb = 0;
+        if (p.do_runs && p.run_break > 0) {
+            const unsigned a = (unsigned)p.rs + (unsigned)tile_base;
+            const unsigned rem = a % p.run_break;
+            hb = (rem ? p.run_break - rem : 0u) < (unsigned)kTile;
+        }
+        s_has_break = hb;
+    }
     __syncthreads();
 
-    int wbase = 0;                                            // depth at the base before this warp's first
-#pragma unroll
-    for (int w = 0; w < kWarps; w++) wbase += s_carry[w] + ((w < warp) ? s_warp_tot[w] : 0);
+    // depth at the base before this warp's first: everything carried into the tile + the warps before this one
+    const int wbase = __reduce_add_sync(kFull, lane < kWarps ? s_carry[lane] + (lane < warp ? s_warp_tot[lane] : 0) : 0);
     const int tbase = wbase + lane_excl;                      // depth at the base before this thread's first
 
     // ---- per-base depth in registers
@@ -365,13 +375,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     const bool full_warp = warp_base + kWarpElems <= p.len;   // false only at the region's ragged end
     const int wmin = __reduce_min_sync(kFull, mn), wmax = __reduce_max_sync(kFull, mx);
 
-    // does a forced run break (multiple of run_break) fall inside this tile?
-    bool tile_has_break = false;
-    if (p.do_runs && p.run_break > 0) {
-        const unsigned a = (unsigned)p.rs + (unsigned)tile_base;      // absolute positions are < 2^32
-        const unsigned rem = a % p.run_break;
-        tile_has_break = (rem ? p.run_break - rem : 0u) < (unsigned)kTile;
-    }
+    const bool tile_has_break = s_has_break != 0;
 
     // class(d) is monotone in d: the warp's 512 bases plus the base before them are one class iff
     // class(min) == class(max) — then no run starts here and all per-base class work is skipped.
@@ -506,9 +510,8 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     __syncthreads();
 
     // ---- per-tile summary; claim output slots for this tile's run starts
-    int tile_cnt = 0, tile_mx = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; w++) { tile_cnt += s_warp_cnt[w]; tile_mx = max(tile_mx, s_warp_max[w]); }
+    const int tile_cnt = __reduce_add_sync(kFull, lane < kWarps ? s_warp_cnt[lane] : 0);
+    const int tile_mx = __reduce_max_sync(kFull, lane < kWarps ? s_warp_max[lane] : 0);
     if (tid == 0) {
         if (tile_mx > 0 && (unsigned long long)tile_mx > *reinterpret_cast<volatile unsigned long long*>(p.header + 2))
             atomicMax(reinterpret_cast<unsigned long long*>(p.header + 2), (unsigned long long)tile_mx);
@@ -527,8 +530,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
 
     if (mask) {
         long long rank = s_run_base + lane_rank;
-#pragma unroll
-        for (int w = 0; w < kWarps; w++) rank += (w < warp) ? s_warp_cnt[w] : 0;
+        for (int w = 0; w < warp; w++) rank += s_warp_cnt[w];
         unsigned m = mask;
         while (m) {
             const int k = __ffs(m) - 1;
@@ -612,16 +614,18 @@ __device__ __forceinline__ bool fused_out_of_order(const SegRange& g) {
 }
 
 // one segment into the tile [t0,t1): +1/-1 in shared memory, or +1 carried in when it covers base t0-1
-__device__ __forceinline__ void fused_apply(const ScanParams& p, int* s_tile, int t0, int t1, int s, int e, int& carry) {
-    const int sc = max(s, p.rs), ec = min(e, p.re);                    // clipped to the region like the general path
-    if (sc < ec && sc < t1 && ec >= t0) {
-        if (sc < t0) carry++;
+// Region clipping: rs <= t0 and t1 <= re, so only tile 0 can see starts below rs (they count from its first base)
+// and an end beyond re only lands in the masked tail of the last tile: neither needs an explicit clip.
+__device__ __forceinline__ void fused_apply(int* s_tile, int t0, int t1, bool first_tile, int s, int e, int& carry) {
+    const int sc = first_tile ? max(s, t0) : s;                         // t0 == rs on the first tile
+    if (sc < e && sc < t1 && e >= t0) {
+        if (sc < t0) carry++;                                           // covers base t0-1: carried in
         else atomicAdd(s_tile + swz_elem(sc - t0), 1);
-        if (ec - t0 < kTile) atomicAdd(s_tile + swz_elem(ec - t0), -1);
+        if (e - t0 < kTile) atomicAdd(s_tile + swz_elem(e - t0), -1);
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads, 3) depth_fused_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const ScanParams p) {
     __shared__ __align__(16) int s_tile[kTile];
     __shared__ int s_carry[kWarps];
     __shared__ unsigned s_rng[3][kWarps];
@@ -667,6 +671,7 @@ __global__ void __launch_bounds__(kScanThreads, 3) depth_fused_kernel(const Scan
 
     for (; tile < p.num_tiles; tile += G) {
         const int t0 = p.rs + tile * kTile, t1 = min(t0 + kTile, p.re);
+        const bool first_tile = tile == 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);
         __syncthreads();                                                // previous core finished everywhere; tile is zero
@@ -676,9 +681,9 @@ __global__ void __launch_bounds__(kScanThreads, 3) depth_fused_kernel(const Scan
         }
         int carry = 0;
 #pragma unroll
-        for (int j = 0; j < kSegRegs; j++) fused_apply(p, s_tile, t0, t1, ss[j], se[j], carry);
+        for (int j = 0; j < kSegRegs; j++) fused_apply(s_tile, t0, t1, first_tile, ss[j], se[j], carry);
         for (unsigned i = cur.lo + tid + kSegRegs * kScanThreads; i < cur.hi; i += kScanThreads)   // deep tiles only
-            fused_apply(p, s_tile, t0, t1, bs[i], be[i], carry);
+            fused_apply(s_tile, t0, t1, first_tile, bs[i], be[i], carry);
         for (int b = 1; b < p.n_batches; b++) {                         // further batches: not pipelined
             const BatchDesc& bd = p.batch[b];
             fused_reduce_cells(fused_load_cells(p, bd, tile, maxlen), s_rng2);
@@ -689,7 +694,7 @@ __global__ void __launch_bounds__(kScanThreads, 3) depth_fused_kernel(const Scan
                 if (tid == 0) p.header[3] = 1;
                 return;
             }
-            for (unsigned i = g.lo + tid; i < g.hi; i += kScanThreads) fused_apply(p, s_tile, t0, t1, bd.start[i], bd.end[i], carry);
+            for (unsigned i = g.lo + tid; i < g.hi; i += kScanThreads) fused_apply(s_tile, t0, t1, first_tile, bd.start[i], bd.end[i], carry);
         }
         carry = __reduce_add_sync(kFull, carry);
         if (lane == 0) s_carry[warp] = carry;
@@ -921,7 +926,7 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
         }
         {
             gl_prof_scope prof(ctx, fused ? "depth_fused_kernel" : "depth_scan_kernel");
-            const unsigned fused_grid = (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 3);
+            const unsigned fused_grid = (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 4);
             if (fused) depth_fused_kernel<<<fused_grid, kScanThreads, 0, ctx->stream>>>(p);
             else depth_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p);
         }

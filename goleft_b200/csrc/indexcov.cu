@@ -1,8 +1,9 @@
 // indexcov.cu — `goleft indexcov` arithmetic on sm_100a, plus the small covstats / depthwed kernels.
 //
 //   I1  ic_sizes_kernel     BAI linear-index virtual offsets -> per-tile sizes   (indexcov/types.go:45-82)
-//   I2+I3 ic_cohort_kernel  ONE kernel, one CTA per sample: capped weighted median by two radix selects
-//                           over the sample's tiles (no sort), then normalised depth  (indexcov.go:83-151)
+//   I2+I3 ic_cohort_kernel  ONE kernel, one CTA per sample: capped weighted median by two range-adaptive
+//                           histogram selects over the sample's tiles (no sort), then normalised depth
+//                                                                                      (indexcov.go:83-151)
 //   I4+I5 ic_counts_kernel  per (sample, chromosome) segment: 70-slot histogram + in/out/hi/low counters
 //                                                                            (indexcov.go:170-177,1050-1078)
 //   I7  ic_xnorm_kernel     cross-sample normalisation, sequential in tile j, parallel over samples, with the
@@ -37,78 +38,90 @@ __global__ void __launch_bounds__(256) ic_sizes_kernel(const unsigned long long*
 // ------------------------------------------------------------------------------------------------ I2 + I3
 constexpr int kCohortThreads = 512;
 
-// k-th smallest (0-based) of n non-negative int64 by MSB-first radix descent, 8 bits a pass
-__device__ long long block_select_kth(const long long* __restrict__ v, long long n, long long k, unsigned* s_hist,
-                                      unsigned long long* s_bcast) {
-    unsigned long long prefix = 0;
-    for (int shift = 56; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
-        __syncthreads();
-        const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
-        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned long long x = (unsigned long long)v[i];
-            if ((x & himask) == prefix) atomicAdd(&s_hist[(x >> shift) & 255], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long acc = 0;
-            int d = 0;
-            for (; d < 256; d++) {
-                if (acc + (long long)s_hist[d] > k) break;
-                acc += s_hist[d];
-            }
-            s_bcast[0] = (unsigned long long)d;
-            s_bcast[1] = (unsigned long long)acc;
-        }
-        __syncthreads();
-        prefix |= s_bcast[0] << shift;
-        k -= (long long)s_bcast[1];
-        __syncthreads();
-    }
-    return (long long)prefix;
+// Selection without a sort.  Both selects of Index.init are "smallest value v with F(v) > target", where
+// F(v) = sum over x <= v of w(x):  w = 1 gives the k-th smallest (target = k), w = min(x, cap) gives the capped
+// weighted median (target = total/2).  The answer is bracketed by [lo,hi]; each level histograms the candidates
+// into kSelBins equal-width bins over the CURRENT range (not over radix digits: tile sizes of one sample share
+// their leading bytes, a digit histogram would put every shared-memory atomic on one bin), picks the bin where
+// the running weight crosses the target, and shrinks [lo,hi] to the min/max of that bin's members.  The width
+// drops by >= kSelBins per level, so 64-bit values need at most 7 levels; real data takes 3.
+constexpr int kSelBins = 1024;
+
+struct SelSmem {
+    unsigned long long w[kSelBins];
+    long long red_lo[kCohortThreads / 32], red_hi[kCohortThreads / 32];
+    long long bcast[3];
+};
+
+__device__ __forceinline__ int sel_bin(long long x, long long lo, double scale) {
+    const int b = (int)((double)(unsigned long long)(x - lo) * scale);      // monotone in x
+    return b < kSelBins - 1 ? b : kSelBins - 1;
 }
 
-// smallest value x with  sum_{v<=x} min(v,cap)  >  half   (weights = capped values); total > half guaranteed
-__device__ long long block_select_weighted(const long long* __restrict__ v, long long n, long long cap, long long half,
-                                           unsigned long long* s_w, unsigned long long* s_bcast) {
-    unsigned long long prefix = 0;
-    long long below = 0;                       // weight of everything smaller than the current prefix range
-    for (int shift = 56; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_w[i] = 0;
+// block-wide min / max of the values in [flo,fhi] whose bin at (lo,scale) equals `bin` (bin < 0: every value in range)
+__device__ void block_minmax(const long long* __restrict__ v, long long n, long long flo, long long fhi, long long lo, double scale,
+                             int bin, SelSmem& sm, long long& out_lo, long long& out_hi) {
+    long long mn = 0x7fffffffffffffffll, mx = -0x7fffffffffffffffll - 1;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long x = v[i];
+        if (x >= flo && x <= fhi && (bin < 0 || sel_bin(x, lo, scale) == bin)) { mn = min(mn, x); mx = max(mx, x); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(kFull, mn, o)); mx = max(mx, __shfl_xor_sync(kFull, mx, o)); }
+    if ((threadIdx.x & 31) == 0) { sm.red_lo[threadIdx.x >> 5] = mn; sm.red_hi[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    mn = 0x7fffffffffffffffll; mx = -0x7fffffffffffffffll - 1;
+    for (int w = 0; w < kCohortThreads / 32; w++) { mn = min(mn, sm.red_lo[w]); mx = max(mx, sm.red_hi[w]); }
+    __syncthreads();
+    out_lo = mn; out_hi = mx;
+}
+
+template <bool kWeighted>
+__device__ long long block_select(const long long* __restrict__ v, long long n, long long cap, long long target, long long lo,
+                                  long long hi, SelSmem& sm) {
+    long long below = 0;                                   // F just below lo
+    while (lo < hi) {
+        const double scale = (double)kSelBins / ((double)(unsigned long long)(hi - lo) + 1.0);
+        for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) sm.w[i] = 0;
         __syncthreads();
-        const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
         for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned long long x = (unsigned long long)v[i];
-            if ((x & himask) == prefix) {
-                const long long w = min((long long)x, cap);
-                if (w) atomicAdd(&s_w[(x >> shift) & 255], (unsigned long long)w);
+            const long long x = v[i];
+            if (x >= lo && x <= hi) {
+                const unsigned long long w = kWeighted ? (unsigned long long)min(x, cap) : 1ull;
+                if (w) atomicAdd(&sm.w[sel_bin(x, lo, scale)], w);
             }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             long long acc = below;
-            int d = 0;
-            for (; d < 255; d++) {
-                if (acc + (long long)s_w[d] > half) break;
-                acc += (long long)s_w[d];
+            int b = 0;
+            for (; b < kSelBins - 1; b++) {
+                if (acc + (long long)sm.w[b] > target) break;
+                acc += (long long)sm.w[b];
             }
-            s_bcast[0] = (unsigned long long)d;
-            s_bcast[1] = (unsigned long long)acc;
+            sm.bcast[0] = b;
+            sm.bcast[1] = acc;
         }
         __syncthreads();
-        prefix |= s_bcast[0] << shift;
-        below = (long long)s_bcast[1];
+        const int bin = (int)sm.bcast[0];
+        below = sm.bcast[1];
         __syncthreads();
+        long long nlo, nhi;
+        block_minmax(v, n, lo, hi, lo, scale, bin, sm, nlo, nhi);
+        if (nlo > nhi) return lo;                          // cannot happen when F(max) > target; keeps the loop finite
+        lo = nlo;
+        hi = nhi;
+        if (kWeighted && lo < hi) {
+            // zero-weight members (x == 0) never move the running weight: with lo == 0 the crossing value is > 0
+        }
     }
-    return (long long)prefix;
+    return lo;
 }
 
 __global__ void __launch_bounds__(kCohortThreads) ic_cohort_kernel(const long long* __restrict__ sizes,
                                                                    const long long* __restrict__ sample_ptr, int S,
                                                                    double* __restrict__ medians, float* __restrict__ depth_out) {
-    __shared__ unsigned s_hist[256];
-    __shared__ unsigned long long s_w[256];
-    __shared__ unsigned long long s_bcast[2];
+    __shared__ SelSmem sm;
     __shared__ long long s_red[kCohortThreads / 32];
     const int smp = blockIdx.x;
     if (smp >= S) return;
@@ -116,9 +129,12 @@ __global__ void __launch_bounds__(kCohortThreads) ic_cohort_kernel(const long lo
     const long long* v = sizes + a;
     if (n <= 0) { if (threadIdx.x == 0) medians[smp] = 0.0; return; }
 
+    long long vmin, vmax;
+    block_minmax(v, n, -0x7fffffffffffffffll - 1, 0x7fffffffffffffffll, 0, 0.0, -1, sm, vmin, vmax);
+
     // n98 = sorted[int(0.98*n)]                                              (indexcov.go:111)
     const long long k98 = (long long)(0.98 * (double)n);
-    const long long n98 = block_select_kth(v, n, k98, s_hist, s_bcast);
+    const long long n98 = block_select<false>(v, n, 0, k98, vmin, vmax, sm);
 
     // total = sum min(s, n98)                                                (:112-118)
     long long part = 0;
@@ -131,21 +147,9 @@ __global__ void __launch_bounds__(kCohortThreads) ic_cohort_kernel(const long lo
     for (int w = 0; w < kCohortThreads / 32; w++) total += s_red[w];
     __syncthreads();
 
-    // first sorted position whose capped cumulative sum exceeds total/2      (:119-124)
-    long long med;
-    if (total == 0) {
-        // cumsum never exceeds 0: sort.Search returns len, the clamp picks the largest element
-        long long mx = 0;
-        for (long long i = threadIdx.x; i < n; i += blockDim.x) mx = max(mx, v[i]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, o));
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
-        __syncthreads();
-        med = 0;
-        for (int w = 0; w < kCohortThreads / 32; w++) med = max(med, s_red[w]);
-    } else {
-        med = block_select_weighted(v, n, n98, total / 2, s_w, s_bcast);
-    }
+    // first sorted position whose capped cumulative sum exceeds total/2      (:119-124).  When total == 0 the
+    // cumsum never exceeds 0: sort.Search returns len and the clamp picks the largest element.
+    const long long med = (total == 0) ? vmax : block_select<true>(v, n, n98, total / 2, vmin, vmax, sm);
     const double dm = (double)med;
     if (threadIdx.x == 0) medians[smp] = dm;
 
