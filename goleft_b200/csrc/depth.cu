@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(256) depth_super_sum_kernel(const int* __restr
 }
 
 // ================================================================================================
-// FUSED path, K_index.  For every 256-base cell from `origin`: cell_lo = lowest index of a segment that
-// starts in the cell, cell_hi = highest such index + 1, cell_cnt = how many.  Consecutive segments
+// FUSED path, K_index.  For every 256-base cell from `origin`: cell_lo = ~(lowest index of a segment that
+// starts in the cell), cell_hi = highest such index + 1, cell_cnt = how many.  Consecutive segments
 // mostly share a cell, so each run of equal cells inside a warp issues one atomicMin (its first lane),
 // one atomicMax (its last lane) and one atomicAdd (run length).  No ordering assumption is made here;
 // the fused kernel compares span and count.  Also: the longest segment, in 1024 slots (a single word
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) depth_index_kernel(const int* __restrict_
 #pragma unroll
                     for (int jj = 3; jj > j; jj--)
                         if (first[jj]) q = 4 * lane + jj;
-                    atomicMin(cell_lo + c[j], (unsigned)(base + j));
+                    atomicMax(cell_lo + c[j], ~(unsigned)(base + j));        // table holds ~min so it can be zero-initialised
                     atomicAdd(cell_cnt + c[j], (unsigned)(q - (4 * lane + j)));
                 }
                 if (last[j]) atomicMax(cell_hi + c[j], (unsigned)(base + j) + 1u);
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) depth_index_kernel(const int* __restrict_
 struct BatchDesc {
     const int* start;
     const int* end;
-    const unsigned* cell_lo;   // [ncells] lowest segment index starting in the cell (0xffffffff: none)
+    const unsigned* cell_lo;   // [ncells] bitwise NOT of the lowest segment index starting in the cell (0: none)
     const unsigned* cell_hi;   // [ncells] highest such index + 1
     const unsigned* cell_cnt;  // [ncells] number of segments starting in the cell
     int n;
@@ -592,7 +592,7 @@ __device__ __forceinline__ CellRegs fused_load_cells(const ScanParams& p, const 
         int lo_cell, hi_cell;
         fused_cells_of(p, tile, maxlen, lo_cell, hi_cell);
         const int c = lo_cell + (int)threadIdx.x;
-        if (c < hi_cell) { r.lo = bd.cell_lo[c]; r.hi = bd.cell_hi[c]; r.cnt = bd.cell_cnt[c]; }
+        if (c < hi_cell) { r.lo = ~bd.cell_lo[c]; r.hi = bd.cell_hi[c]; r.cnt = bd.cell_cnt[c]; }
     }
     return r;
 }
@@ -825,14 +825,22 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
         GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[0], 0));
         ctx->copies_pending = false;
     }
-    if (do_windows) {
-        GL_CHECK(gl_buf_reserve(ctx, ctx->win_sum, (size_t)n_windows * 8));
-        if (want_min) GL_CHECK(gl_buf_reserve(ctx, ctx->win_min, (size_t)n_windows * 4));
-    }
-    // scratch: header u64[8] | super_cnt u32[supers] | tile_runs u64[tiles]
+    if (do_windows && want_min) GL_CHECK(gl_buf_reserve(ctx, ctx->win_min, (size_t)n_windows * 4));
+    // One scratch buffer; everything that must start at zero is contiguous so a single memset clears it:
+    //   [header u64[8] | super_cnt u32[supers]] [win_sum u64[n_windows]] [flags] [cell_hi|cell_cnt|cell_lo per batch]  | tile_runs
+    bool try_fused = ctx->force_path != 2 && !ctx->batches.empty() && (int)ctx->batches.size() <= kMaxBatches;
+    for (const gl_seg_batch& b : ctx->batches) if (b.n >= INT32_MAX) try_fused = false;
+    const int origin = (int)(std::max<int64_t>(0, ctx->rs - kMaxLookback) & ~int64_t((1 << kCellShift) - 1));
+    const int ncells = (int)(((ctx->re - 1 - origin) >> kCellShift) + 1);
+    const size_t nb = ctx->batches.size();
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t supers = super_entries_for(len);
-    const size_t head_bytes = kHeaderWords * 8 + ((supers * 4 + 7) & ~size_t(7));
-    GL_CHECK(gl_buf_reserve(ctx, ctx->scratch, head_bytes + (size_t)tiles * 8));
+    const size_t head_bytes = al(kHeaderWords * 8 + supers * 4);
+    const size_t win_bytes = al(do_windows ? (size_t)n_windows * 8 : 0);
+    const size_t flag_bytes = try_fused ? al(kFlagWords * 4) : 0;
+    const size_t cell_bytes = try_fused ? al((size_t)ncells * 4 * 3 * nb) : 0;
+    const size_t zero_bytes = head_bytes + win_bytes + flag_bytes + cell_bytes;
+    GL_CHECK(gl_buf_reserve(ctx, ctx->scratch, zero_bytes + (size_t)tiles * 8));
     if (do_runs && ctx->run_start.cap == 0) {
         size_t cap = (size_t)(len / 16 + 4096);
         GL_CHECK(gl_buf_reserve(ctx, ctx->run_start, cap * 4));
@@ -840,9 +848,14 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
         GL_CHECK(gl_buf_reserve(ctx, ctx->run_tmp_start, cap * 4));
         GL_CHECK(gl_buf_reserve(ctx, ctx->run_tmp_class, cap));
     }
-    uint64_t* header = static_cast<uint64_t*>(ctx->scratch.p);
+    char* sbase = static_cast<char*>(ctx->scratch.p);
+    uint64_t* header = reinterpret_cast<uint64_t*>(sbase);
     unsigned* super_cnt = reinterpret_cast<unsigned*>(header + kHeaderWords);
-    uint64_t* tile_runs = reinterpret_cast<uint64_t*>(static_cast<char*>(ctx->scratch.p) + head_bytes);
+    ctx->win_sum_p = sbase + head_bytes;
+    int* flags = reinterpret_cast<int*>(sbase + head_bytes + win_bytes);
+    unsigned* cells = reinterpret_cast<unsigned*>(sbase + head_bytes + win_bytes + flag_bytes);
+    uint64_t* tile_runs = reinterpret_cast<uint64_t*>(sbase + zero_bytes);
+    GL_CUDA(ctx, cudaMemsetAsync(sbase, 0, zero_bytes, ctx->stream));
 
     ScanParams p;
     memset(&p, 0, sizeof p);
@@ -862,23 +875,12 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
     p.do_windows = do_windows ? 1 : 0;
     p.do_runs = do_runs ? 1 : 0;
 
-    // ---- fused path set-up: index every batch (flags decide eligibility on the device)
-    bool try_fused = ctx->force_path != 2 && !ctx->batches.empty() && (int)ctx->batches.size() <= kMaxBatches;
-    for (const gl_seg_batch& b : ctx->batches) if (b.n >= INT32_MAX) try_fused = false;
+    // ---- fused path set-up: index every batch (the device decides eligibility)
     if (try_fused) {
-        const int origin = (int)(std::max<int64_t>(0, ctx->rs - kMaxLookback) & ~int64_t((1 << kCellShift) - 1));
-        const int ncells = (int)(((ctx->re - 1 - origin) >> kCellShift) + 1);
-        const size_t nb = ctx->batches.size();
-        // per batch: cell_lo[ncells] | cell_hi[ncells] | cell_cnt[ncells]; all lo tables first so one memset(0xff) covers them
-        GL_CHECK(gl_buf_reserve(ctx, ctx->fine_idx, (size_t)ncells * 4 * 3 * nb));
-        GL_CHECK(gl_buf_reserve(ctx, ctx->sflags, kFlagWords * 4));
-        unsigned* lo_all = static_cast<unsigned*>(ctx->fine_idx.p);
-        unsigned* hi_all = lo_all + (size_t)ncells * nb;
+        unsigned* hi_all = cells;
         unsigned* cnt_all = hi_all + (size_t)ncells * nb;
-        GL_CUDA(ctx, cudaMemsetAsync(ctx->sflags.p, 0, kFlagWords * 4, ctx->stream));
-        GL_CUDA(ctx, cudaMemsetAsync(lo_all, 0xff, (size_t)ncells * 4 * nb, ctx->stream));
-        GL_CUDA(ctx, cudaMemsetAsync(hi_all, 0, (size_t)ncells * 4 * 2 * nb, ctx->stream));
-        p.flags = static_cast<const int*>(ctx->sflags.p);
+        unsigned* lo_all = cnt_all + (size_t)ncells * nb;
+        p.flags = flags;
         p.origin = origin;
         p.ncells = ncells;
         p.n_batches = (int)nb;
@@ -893,7 +895,7 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
             gl_prof_scope prof(ctx, "depth_index_kernel");
             depth_index_kernel<<<(unsigned)(((b.n + 3) / 4 + 255) / 256), 256, 0, ctx->stream>>>(
                 p.batch[bi].start, p.batch[bi].end, b.n, origin, (int)ctx->re, ncells, lo_all + bi * (size_t)ncells,
-                hi_all + bi * (size_t)ncells, cnt_all + bi * (size_t)ncells, static_cast<int*>(ctx->sflags.p));
+                hi_all + bi * (size_t)ncells, cnt_all + bi * (size_t)ncells, flags);
             GL_LAUNCHED(ctx, 1);
         }
     }
@@ -906,7 +908,7 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
             p.tile_sum = tile_sum_ptr(ctx);
             p.super_sum = super_sum_ptr(ctx);
         }
-        p.win_sum = static_cast<unsigned long long*>(ctx->win_sum.p);
+        p.win_sum = static_cast<unsigned long long*>(ctx->win_sum_p);
         p.win_min = (do_windows && want_min) ? static_cast<int*>(ctx->win_min.p) : nullptr;
         p.tmp_start = static_cast<int*>(ctx->run_tmp_start.p);
         p.tmp_class = static_cast<unsigned char*>(ctx->run_tmp_class.p);
@@ -919,11 +921,8 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
         }
         p.run_cap = cap;
 
-        GL_CUDA(ctx, cudaMemsetAsync(header, 0, head_bytes, ctx->stream));
-        if (do_windows) {
-            GL_CUDA(ctx, cudaMemsetAsync(ctx->win_sum.p, 0, (size_t)n_windows * 8, ctx->stream));
-            if (want_min) GL_CUDA(ctx, cudaMemsetAsync(ctx->win_min.p, 0x7f, (size_t)n_windows * 4, ctx->stream));
-        }
+        if (attempt > 0) GL_CUDA(ctx, cudaMemsetAsync(sbase, 0, head_bytes + win_bytes, ctx->stream));   // header + window sums again
+        if (do_windows && want_min) GL_CUDA(ctx, cudaMemsetAsync(ctx->win_min.p, 0x7f, (size_t)n_windows * 4, ctx->stream));
         {
             gl_prof_scope prof(ctx, fused ? "depth_fused_kernel" : "depth_scan_kernel");
             const unsigned fused_grid = (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 4);
@@ -1160,7 +1159,7 @@ int gl_depth_get_windows(gl_ctx* ctx, int64_t* sum_out, int64_t cap) {
     if (!ctx->depth_reduced || ctx->n_windows == 0) return gl_fail(ctx, GL_ESTATE, "gl_depth_get_windows: no window results");
     if (!sum_out) return gl_fail(ctx, GL_EINVAL, "gl_depth_get_windows: null sum_out");
     if (cap < ctx->n_windows) return gl_fail(ctx, GL_ERANGE, "gl_depth_get_windows: cap %lld < %lld windows", (long long)cap, (long long)ctx->n_windows);
-    GL_CUDA(ctx, cudaMemcpyAsync(sum_out, ctx->win_sum.p, (size_t)ctx->n_windows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA(ctx, cudaMemcpyAsync(sum_out, ctx->win_sum_p, (size_t)ctx->n_windows * 8, cudaMemcpyDeviceToHost, ctx->stream));
     GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GL_OK;
 }
@@ -1249,7 +1248,7 @@ static int region_fetch(gl_ctx* ctx, int64_t* sum_out, int64_t win_cap, int64_t*
     if (n_runs) *n_runs = nr;
     if (nw > win_cap) return gl_fail(ctx, GL_ERANGE, "gl_depth_region: %lld windows > cap %lld", (long long)nw, (long long)win_cap);
     if (nr > run_cap) return gl_fail(ctx, GL_ERANGE, "gl_depth_region: %lld runs > cap %lld", (long long)nr, (long long)run_cap);
-    GL_CUDA(ctx, cudaMemcpyAsync(sum_out, ctx->win_sum.p, (size_t)nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA(ctx, cudaMemcpyAsync(sum_out, ctx->win_sum_p, (size_t)nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (nr > 0) {
         GL_CUDA(ctx, cudaMemcpyAsync(run_start, ctx->run_start.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, ctx->stream));
         GL_CUDA(ctx, cudaMemcpyAsync(run_class, ctx->run_class.p, (size_t)nr, cudaMemcpyDeviceToHost, ctx->stream));

@@ -46,16 +46,14 @@ struct gl_ctx {
     bool g_valid = false;                   // the HBM difference array holds every batch (general path)
     int last_path = 0;                      // 1 = fused sorted path, 2 = general scatter path
     int force_path = 0;                     // 0 = auto, 2 = always general (tests / comparison arm)
-    gl_buf fine_idx;      // per-256-base segment offsets of every batch (fused path)
-    gl_buf sflags;        // [0]=unsorted, [16..16+1024) max segment length slots
     gl_buf diff;          // int32[len+1 (+pad)] + tile sums (general path only)
-    gl_buf win_sum;       // u64[n_windows]
+    void* win_sum_p = nullptr;   // u64[n_windows], inside `scratch`
     gl_buf win_min;       // i32[n_windows]
     gl_buf run_start;     // i32[run_cap]
     gl_buf run_class;     // u8[run_cap]
     gl_buf run_tmp_start; // claim-order staging of the runs
     gl_buf run_tmp_class;
-    gl_buf scratch;       // header + 2 status words per tile
+    gl_buf scratch;       // header | window sums | index flags + cell tables | per-tile run table
     gl_buf seg[2];        // device staging for host segments: int32 start|end
     void* pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;

@@ -105,10 +105,10 @@ int gl_ctx_destroy(gl_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->nccl) gl_comm_destroy(ctx);
-    buf_free(ctx->diff); buf_free(ctx->win_sum); buf_free(ctx->win_min);
+    buf_free(ctx->diff); buf_free(ctx->win_min);
     buf_free(ctx->run_start); buf_free(ctx->run_class); buf_free(ctx->scratch);
     buf_free(ctx->run_tmp_start); buf_free(ctx->run_tmp_class);
-    buf_free(ctx->store_s); buf_free(ctx->store_e); buf_free(ctx->packed); buf_free(ctx->fine_idx); buf_free(ctx->sflags);
+    buf_free(ctx->store_s); buf_free(ctx->store_e); buf_free(ctx->packed);
     buf_free(ctx->seg[0]); buf_free(ctx->seg[1]); buf_free(ctx->flush); buf_free(ctx->misc);
     for (int i = 0; i < 2; i++) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
