@@ -281,8 +281,8 @@ struct ScanParams {
     unsigned char* tmp_class;     // [run_cap]
     long long run_cap;
     uint64_t* header;             // [0]=runs claimed (= n_runs) [2]=max_depth [3]=fused path rejected
-    uint64_t* tile_runs;          // [num_tiles] (claim offset << 32) | count
-    unsigned* super_cnt;          // [num_tiles/64+1] run starts per super-tile
+    uint64_t* chunk_runs;         // [num_tiles*8] per 512-base warp chunk: (claim offset << 32) | count
+    unsigned* super_cnt;          // [num_tiles*8/64+1] run starts per 64 chunks
     int* depth_out;               // optional per-base output (debug/parity), else null
     int num_tiles;
     int do_windows, do_runs;
@@ -304,14 +304,16 @@ __device__ __forceinline__ int select16(const int (&S)[16], int i) {
     return b3 ? e1 : e0;
 }
 
-// s_tile: the tile's 4096 differences in swizzled layout.  s_carry[8]: partial sums of everything
-// before the tile (all zero on the fused path).  Requires all 256 threads; contains __syncthreads.
-__device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__ s_tile, const int* s_carry, int tile) {
+// s_tile: the tile's 4096 differences in swizzled layout (kZeroAfterRead: each warp clears its own slice as soon
+// as it has read it, so a persistent CTA can accumulate the next tile without a clearing pass + barrier).
+// s_depth: 4096 ints, per-warp private scratch of the slow paths.  s_carry[8]: partial sums of everything before
+// the tile.  Requires all 256 threads; contains exactly ONE __syncthreads (the 8 warp totals); after it every warp
+// is independent: runs are claimed per 512-base warp chunk, not per tile.
+template <bool kZeroAfterRead>
+__device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__ s_tile, int* __restrict__ s_depth,
+                                          const int* s_carry, int tile) {
     __shared__ int s_warp_tot[kWarps];
-    __shared__ int s_warp_cnt[kWarps];
-    __shared__ int s_warp_max[kWarps];
     __shared__ int s_has_break;
-    __shared__ long long s_run_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_base = tile * kTile;                       // relative position of the tile
@@ -324,6 +326,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     for (int j = 0; j < 4; j++) {
         const int4 q = reinterpret_cast<const int4*>(s_tile)[swz_chunk(tid * 4 + j)];
         x[4 * j] = q.x; x[4 * j + 1] = q.y; x[4 * j + 2] = q.z; x[4 * j + 3] = q.w;
+        if (kZeroAfterRead) reinterpret_cast<int4*>(s_tile)[swz_chunk(tid * 4 + j)] = make_int4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int k = 1; k < 16; k++) x[k] += x[k - 1];
@@ -386,9 +389,8 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     const bool fast_win = p.do_windows && full_warp && p.W >= 16 && p.win_min == nullptr && wmax < (1 << 22);
     const bool slow_win = p.do_windows && !fast_win;
 
-    // The slow paths index depth by position: put it back into this warp's smem slice (linear layout;
-    // a warp's swizzled chunks stay inside its own slice, and every lane has finished reading).
-    int* sw = s_tile + warp * kWarpElems;
+    // The slow paths index depth by position: this warp's private slice of s_depth (linear layout).
+    int* sw = s_depth + warp * kWarpElems;
     if (slow_runs || slow_win) {
         __syncwarp();
 #pragma unroll
@@ -436,7 +438,8 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
         }
         if (!full_warp) maxd = __reduce_max_sync(kFull, maxd);
     }
-    if (lane == 0) { s_warp_cnt[warp] = warp_cnt; s_warp_max[warp] = maxd; }
+    if (lane == 0 && maxd > 0 && (unsigned long long)maxd > *reinterpret_cast<volatile unsigned long long*>(p.header + 2))
+        atomicMax(reinterpret_cast<unsigned long long*>(p.header + 2), (unsigned long long)maxd);
 
     // ---- window partial sums of this warp's 512 bases
     if (fast_win) {
@@ -507,39 +510,31 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
             }
         }
     }
-    __syncthreads();
 
-    // ---- per-tile summary; claim output slots for this tile's run starts
-    const int tile_cnt = __reduce_add_sync(kFull, lane < kWarps ? s_warp_cnt[lane] : 0);
-    const int tile_mx = __reduce_max_sync(kFull, lane < kWarps ? s_warp_max[lane] : 0);
-    if (tid == 0) {
-        if (tile_mx > 0 && (unsigned long long)tile_mx > *reinterpret_cast<volatile unsigned long long*>(p.header + 2))
-            atomicMax(reinterpret_cast<unsigned long long*>(p.header + 2), (unsigned long long)tile_mx);
-        if (p.do_runs) {
-            unsigned long long off = 0;
-            if (tile_cnt) {
-                off = atomicAdd(reinterpret_cast<unsigned long long*>(p.header), (unsigned long long)tile_cnt);
-                atomicAdd(p.super_cnt + (tile >> kSuperShift), (unsigned)tile_cnt);
+    // ---- claim output slots for this warp chunk's run starts (claim order; K_gather puts them in position order)
+    if (p.do_runs) {
+        const int chunk = tile * kWarps + warp;
+        unsigned long long off = 0;
+        if (lane == 0) {
+            if (warp_cnt) {
+                off = atomicAdd(reinterpret_cast<unsigned long long*>(p.header), (unsigned long long)warp_cnt);
+                atomicAdd(p.super_cnt + (chunk >> kSuperShift), (unsigned)warp_cnt);
             }
-            p.tile_runs[tile] = ((uint64_t)off << 32) | (unsigned)tile_cnt;
-            s_run_base = (long long)off;
+            p.chunk_runs[chunk] = ((uint64_t)off << 32) | (unsigned)warp_cnt;
         }
-    }
-    if (!p.do_runs || tile_cnt == 0) return;
-    __syncthreads();
-
-    if (mask) {
-        long long rank = s_run_base + lane_rank;
-        for (int w = 0; w < warp; w++) rank += s_warp_cnt[w];
-        unsigned m = mask;
-        while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            if (rank < p.run_cap) {
-                p.tmp_start[rank] = p.rs + idx0 + k;
-                p.tmp_class[rank] = (unsigned char)cov_class(sw[lane * 16 + k], p.mincov, p.maxmean);
+        if (warp_cnt) {                                       // warp-uniform
+            off = __shfl_sync(kFull, off, 0);
+            long long rank = (long long)off + lane_rank;
+            unsigned m = mask;
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                if (rank < p.run_cap) {
+                    p.tmp_start[rank] = p.rs + idx0 + k;
+                    p.tmp_class[rank] = (unsigned char)cov_class(sw[lane * 16 + k], p.mincov, p.maxmean);
+                }
+                rank++;
             }
-            rank++;
         }
     }
 }
@@ -547,6 +542,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
 // GENERAL path, K_scan: coalesced load of the tile's differences -> swizzled smem -> tile core.
 __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanParams p) {
     __shared__ __align__(16) int s_tile[kTile];
+    __shared__ __align__(16) int s_depth[kTile];
     __shared__ int s_carry[kWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -566,7 +562,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanP
 #pragma unroll
     for (int r = 0; r < 4; r++) reinterpret_cast<int4*>(s_tile)[swz_chunk(warp * 128 + r * 32 + lane)] = v[r];
     __syncwarp();                                                       // a warp only re-reads its own 128 chunks
-    tile_core(p, s_tile, s_carry, tile);
+    tile_core<false>(p, s_tile, s_depth, s_carry, tile);
 }
 
 // FUSED path, K_fused: build each tile's difference array in shared memory straight from the segments.
@@ -627,7 +623,8 @@ __device__ __forceinline__ void fused_apply(int* s_tile, int t0, int t1, bool fi
 
 __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const ScanParams p) {
     __shared__ __align__(16) int s_tile[kTile];
-    __shared__ int s_carry[kWarps];
+    __shared__ __align__(16) int s_depth[kTile];
+    __shared__ int s_carry2[2][kWarps];      // double-buffered: a fast warp writes tile n+1's carry while a slow one still reads tile n's
     __shared__ unsigned s_rng[3][kWarps];
     __shared__ unsigned s_rng2[3][kWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -638,11 +635,13 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const Scan
 #pragma unroll
     for (int k = 0; k < kLenSlots / kScanThreads; k++) maxlen = max(maxlen, p.flags[16 + tid + k * kScanThreads]);
     maxlen = __reduce_max_sync(kFull, maxlen);
-    if (lane == 0) s_carry[warp] = maxlen;
+    if (lane == 0) s_carry2[0][warp] = maxlen;
+#pragma unroll
+    for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);   // later tiles: cleared by the core
     __syncthreads();
     maxlen = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; w++) maxlen = max(maxlen, s_carry[w]);
+    for (int w = 0; w < kWarps; w++) maxlen = max(maxlen, s_carry2[0][w]);
     __syncthreads();
     if (maxlen > kMaxLookback) {
         if (blockIdx.x == 0 && tid == 0) p.header[3] = 1;
@@ -669,12 +668,11 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const Scan
     }
     cells = fused_load_cells(p, b0, tile + G, maxlen);
 
-    for (; tile < p.num_tiles; tile += G) {
+    for (int it = 0; tile < p.num_tiles; tile += G, it ^= 1) {
+        int* s_carry = s_carry2[it];
         const int t0 = p.rs + tile * kTile, t1 = min(t0 + kTile, p.re);
         const bool first_tile = tile == 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);
-        __syncthreads();                                                // previous core finished everywhere; tile is zero
+        // (the previous core's barrier guarantees every warp has read + cleared its slice of the tile)
         if (fused_out_of_order(cur)) {                                  // uniform: every thread holds the same range
             if (tid == 0) p.header[3] = 1;
             return;
@@ -709,36 +707,43 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const Scan
             se[j] = ok ? be[i] : 0;
         }
         cells = fused_load_cells(p, b0, tile + 2 * G, maxlen);          // and the tile after that one's cell entries
-        tile_core(p, s_tile, s_carry, tile);
+        tile_core<true>(p, s_tile, s_depth, s_carry, tile);
     }
 }
 
-// K_gather: one warp per tile moves its runs from claim order to position order.  The ordered offset of
-// a tile is the number of runs that start before it: super-tile counts + the tile counts of its own
-// super-tile (only tiles that have runs pay for the sum).
+// K_gather: one warp per 512-base chunk moves its runs from claim order to position order.  The ordered offset
+// of a chunk is the number of runs that start before it: counts per 64 chunks + the chunk counts of its own group
+// (only chunks that have runs pay for the sum).
 __global__ void __launch_bounds__(256) depth_gather_runs_kernel(const uint64_t* __restrict__ header,
-                                                               const uint64_t* __restrict__ tile_runs,
-                                                               const unsigned* __restrict__ super_cnt, int tiles,
+                                                               const uint64_t* __restrict__ chunk_runs,
+                                                               const unsigned* __restrict__ super_cnt, int chunks,
                                                                const int* __restrict__ tmp_start,
                                                                const unsigned char* __restrict__ tmp_class,
                                                                int* __restrict__ run_start, unsigned char* __restrict__ run_class,
                                                                long long cap) {
     if (header[3] != 0) return;                                         // fused path was rejected
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (t >= tiles) return;
-    const uint64_t w = tile_runs[t];
-    const unsigned cnt = (unsigned)w;
-    if (cnt == 0) return;
-    const int st = t >> kSuperShift;
-    unsigned part = 0;
-    for (int k = lane; k < st; k += 32) part += super_cnt[k];
-    for (int k = (st << kSuperShift) + lane; k < t; k += 32) part += (unsigned)tile_runs[k];
-    const long long dst = (long long)__reduce_add_sync(kFull, part);
-    const long long src = (long long)(w >> 32);
-    for (unsigned i = lane; i < cnt; i += 32) {
-        if (src + i < cap && dst + i < cap) {
-            run_start[dst + i] = tmp_start[src + i];
-            run_class[dst + i] = tmp_class[src + i];
+    const int lane = threadIdx.x & 31;
+    const int base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;        // each warp looks at 32 chunks (one coalesced load)
+    if (base >= chunks) return;
+    const uint64_t mine = (base + lane < chunks) ? chunk_runs[base + lane] : 0;
+    unsigned nz = __ballot_sync(kFull, (unsigned)mine != 0);
+    while (nz) {                                                        // warp-uniform: chunks that have runs
+        const int l = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const int t = base + l;
+        const uint64_t w = __shfl_sync(kFull, mine, l);
+        const unsigned cnt = (unsigned)w;
+        const int st = t >> kSuperShift;
+        unsigned part = 0;
+        for (int k = lane; k < st; k += 32) part += super_cnt[k];
+        for (int k = (st << kSuperShift) + lane; k < t; k += 32) part += (unsigned)chunk_runs[k];
+        const long long dst = (long long)__reduce_add_sync(kFull, part);
+        const long long src = (long long)(w >> 32);
+        for (unsigned i = lane; i < cnt; i += 32) {
+            if (src + i < cap && dst + i < cap) {
+                run_start[dst + i] = tmp_start[src + i];
+                run_class[dst + i] = tmp_class[src + i];
+            }
         }
     }
 }
@@ -827,20 +832,21 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
     }
     if (do_windows && want_min) GL_CHECK(gl_buf_reserve(ctx, ctx->win_min, (size_t)n_windows * 4));
     // One scratch buffer; everything that must start at zero is contiguous so a single memset clears it:
-    //   [header u64[8] | super_cnt u32[supers]] [win_sum u64[n_windows]] [flags] [cell_hi|cell_cnt|cell_lo per batch]  | tile_runs
+    //   [header u64[8] | super_cnt u32[supers]] [win_sum u64[n_windows]] [flags] [cell_hi|cell_cnt|cell_lo per batch]  | chunk_runs
     bool try_fused = ctx->force_path != 2 && !ctx->batches.empty() && (int)ctx->batches.size() <= kMaxBatches;
     for (const gl_seg_batch& b : ctx->batches) if (b.n >= INT32_MAX) try_fused = false;
     const int origin = (int)(std::max<int64_t>(0, ctx->rs - kMaxLookback) & ~int64_t((1 << kCellShift) - 1));
     const int ncells = (int)(((ctx->re - 1 - origin) >> kCellShift) + 1);
     const size_t nb = ctx->batches.size();
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t supers = super_entries_for(len);
+    const int64_t chunks = tiles * kWarps;
+    const size_t supers = (size_t)(chunks >> kSuperShift) + 2;
     const size_t head_bytes = al(kHeaderWords * 8 + supers * 4);
     const size_t win_bytes = al(do_windows ? (size_t)n_windows * 8 : 0);
     const size_t flag_bytes = try_fused ? al(kFlagWords * 4) : 0;
     const size_t cell_bytes = try_fused ? al((size_t)ncells * 4 * 3 * nb) : 0;
     const size_t zero_bytes = head_bytes + win_bytes + flag_bytes + cell_bytes;
-    GL_CHECK(gl_buf_reserve(ctx, ctx->scratch, zero_bytes + (size_t)tiles * 8));
+    GL_CHECK(gl_buf_reserve(ctx, ctx->scratch, zero_bytes + (size_t)chunks * 8));
     if (do_runs && ctx->run_start.cap == 0) {
         size_t cap = (size_t)(len / 16 + 4096);
         GL_CHECK(gl_buf_reserve(ctx, ctx->run_start, cap * 4));
@@ -854,7 +860,7 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
     ctx->win_sum_p = sbase + head_bytes;
     int* flags = reinterpret_cast<int*>(sbase + head_bytes + win_bytes);
     unsigned* cells = reinterpret_cast<unsigned*>(sbase + head_bytes + win_bytes + flag_bytes);
-    uint64_t* tile_runs = reinterpret_cast<uint64_t*>(sbase + zero_bytes);
+    uint64_t* chunk_runs = reinterpret_cast<uint64_t*>(sbase + zero_bytes);
     GL_CUDA(ctx, cudaMemsetAsync(sbase, 0, zero_bytes, ctx->stream));
 
     ScanParams p;
@@ -868,7 +874,7 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
     p.maxmean = maxmean;
     p.run_break = (run_break >= (int64_t(1) << 32)) ? 0u : (unsigned)run_break;
     p.header = header;
-    p.tile_runs = tile_runs;
+    p.chunk_runs = chunk_runs;
     p.super_cnt = super_cnt;
     p.depth_out = d_depth_out;
     p.num_tiles = (int)tiles;
@@ -932,8 +938,8 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
         GL_LAUNCHED(ctx, 1);
         if (do_runs) {
             gl_prof_scope prof(ctx, "depth_gather_runs_kernel");
-            depth_gather_runs_kernel<<<(unsigned)((tiles + 7) / 8), 256, 0, ctx->stream>>>(
-                header, tile_runs, super_cnt, (int)tiles, p.tmp_start, p.tmp_class, static_cast<int*>(ctx->run_start.p),
+            depth_gather_runs_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, ctx->stream>>>(
+                header, chunk_runs, super_cnt, (int)chunks, p.tmp_start, p.tmp_class, static_cast<int*>(ctx->run_start.p),
                 static_cast<unsigned char*>(ctx->run_class.p), cap);
             GL_LAUNCHED(ctx, 1);
         }
