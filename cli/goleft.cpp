@@ -3,7 +3,7 @@
 // computed by libgoleft_b200.so (CUDA, sm_100a) through the C ABI in include/goleft_b200.h; there is no CPU
 // fallback: without a GPU the subcommands fail with the library's error.
 //
-// Out of scope here: HTML/PNG plots, PCA columns of the .ped, CRAM/.crai, --stats GC columns.
+// Out of scope here: HTML/PNG plots, PCA columns of the .ped, --stats GC columns.  .crai input needs --fai.
 #include <errno.h>
 #include <math.h>
 #include <stdarg.h>
@@ -339,9 +339,15 @@ static int cmd_indexcov(int argc, char** argv) {
     const size_t S = bams.size();
     std::vector<std::string> names(S);
     std::vector<glhts::BaiIndex> idx(S);
+    std::vector<std::vector<glhts::CraiSlices>> crai(S);
     for (size_t i = 0; i < S; i++) {
         const std::string& b = bams[i];
-        if (ends_with(b, ".crai")) fatal(1, "indexcov: .crai input is not built in this engine");
+        if (ends_with(b, ".crai")) {                                       // indexcov.go:474-496
+            std::string e = glhts::crai_read(b, crai[i]);
+            if (!e.empty()) fatal(1, "%s", e.c_str());
+            names[i] = short_name(b, true, nullptr);
+            continue;
+        }
         std::string p = ends_with(b, ".bai") ? b : b + ".bai";
         if (!file_exists(p)) p = b.substr(0, b.size() - 4) + (ends_with(b, ".bai") ? "" : ".bai");
         std::string e = glhts::bai_read(p, idx[i]);
@@ -359,6 +365,21 @@ static int cmd_indexcov(int argc, char** argv) {
     std::vector<std::vector<int64_t>> size_ptr(S);                          // per sample: CSR over its refs
     std::vector<uint64_t> mapped(S, 0), unmapped(S, 0);
     for (size_t i = 0; i < S; i++) {
+        if (ends_with(bams[i], ".crai")) {                                  // CRAM: interpolated pseudo-tiles (crai.go:56-127)
+            const size_t nr = crai[i].size();
+            std::vector<int64_t> sp(nr + 1, 0), sz;
+            for (size_t r = 0; r < nr; r++) {
+                std::vector<int64_t> one;
+                if (!glhts::crai_make_sizes(crai[i][r].start.data(), crai[i][r].span.data(), crai[i][r].bytes.data(),
+                                            (int64_t)crai[i][r].start.size(), one)) fatal(2, "panic: tilewidth logic error");
+                all_sizes.insert(all_sizes.end(), one.begin(), one.end());
+                sp[r + 1] = sp[r] + (int64_t)one.size();
+            }
+            if (sp[nr] < 1) fatal(1, "indexcov: no usable chromsomes in bam: %s", bams[i].c_str());
+            sample_ptr.push_back((int64_t)all_sizes.size());
+            size_ptr[i] = sp;
+            continue;
+        }
         const size_t nr = idx[i].ioffsets.size();
         std::vector<uint64_t> voff;
         std::vector<int64_t> rp(nr + 1, 0);

@@ -117,6 +117,7 @@ _proto("gl_pack_segments16", C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_in
 _proto("gl_depth_add_segments_packed16", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_region_packed16", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_crai_make_sizes", C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _i64p)
 _proto("gl_depth_format_chunk", C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int64, _vp, _vp,
        C.c_int64, C.POINTER(_vp), _i64p, C.POINTER(_vp), _i64p)
 _proto("gl_free_text", None, _vp)
@@ -201,6 +202,18 @@ def bam_segments(path: str, min_mapq: int = 1, threads: int = 4, only_tid: int =
         return {"refs": refs, "segments": segs, "n_records": nrec.value, "n_pass": npass.value}
     finally:
         lib.gl_segset_free(h)
+
+
+def crai_make_sizes(start, span, nbytes) -> np.ndarray:
+    """Host-only: 16 KB pseudo-tile sizes of one reference from its CRAM slices (crai.go:56-127)."""
+    start, span, nbytes = _as(start, np.int64), _as(span, np.int64), _as(nbytes, np.int32)
+    cap = int((start[-1] + max(int(span[-1]), 0)) // 16384 + 64) if start.size else 1
+    out = np.empty(cap, np.int64)
+    n = C.c_int64(0)
+    rc = lib.gl_crai_make_sizes(_ptr(start), _ptr(span), _ptr(nbytes), start.size, _ptr(out), cap, C.byref(n))
+    if rc != GL_OK:
+        raise GlError(rc, "gl_crai_make_sizes: tile-width logic error (the reference panics) or capacity")
+    return out[: n.value].copy()
 
 
 def bai_read(path: str):

@@ -2,6 +2,7 @@
 // `samtools depth` child's decode + filter (depth/depth.go:45) and biogo's BAI reader (indexcov.go:514).
 #include <string.h>
 #include <string>
+#include <vector>
 #include "../../../include/goleft_b200.h"
 #include "hts_io.h"
 
@@ -76,5 +77,16 @@ int gl_bai_ref(const gl_bai* b, int32_t tid, const uint64_t** ioffsets, int64_t*
 }
 
 void gl_bai_free(gl_bai* b) { delete b; }
+
+int gl_crai_make_sizes(const int64_t* aln_start, const int64_t* aln_span, const int32_t* slice_len, int64_t n, int64_t* sizes,
+                       int64_t cap, int64_t* n_sizes) {
+    if (n < 0 || !n_sizes || (n > 0 && (!aln_start || !aln_span || !slice_len))) return GL_EINVAL;
+    std::vector<int64_t> v;
+    if (!glhts::crai_make_sizes(aln_start, aln_span, slice_len, n, v)) return GL_ERANGE;    // the reference panics here
+    *n_sizes = (int64_t)v.size();
+    if ((int64_t)v.size() > cap) return GL_ERANGE;
+    if (!v.empty()) memcpy(sizes, v.data(), v.size() * sizeof(int64_t));
+    return GL_OK;
+}
 
 }  // extern "C"

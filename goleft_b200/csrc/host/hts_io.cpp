@@ -425,6 +425,84 @@ std::string bai_read(const std::string& path, BaiIndex& out) {
     return "";
 }
 
+// ---------------------------------------------------------------------------------------------- CRAI
+std::string crai_read(const std::string& path, std::vector<CraiSlices>& out) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) return "cannot open " + path;
+    std::string text;
+    char buf[1 << 16];
+    int n;
+    while ((n = gzread(f, buf, sizeof buf)) > 0) text.append(buf, (size_t)n);
+    gzclose(f);
+    size_t p = 0;
+    int iline = 1;
+    while (p < text.size()) {
+        size_t e = text.find('\n', p);
+        if (e == std::string::npos) break;                      // ReadString returns io.EOF: an unterminated last line is dropped
+        std::string line = text.substr(p, e - p);
+        p = e + 1;
+        while (!line.empty() && isspace((unsigned char)line.back())) line.pop_back();
+        size_t b = 0;
+        while (b < line.size() && isspace((unsigned char)line[b])) b++;
+        line = line.substr(b);
+        long long v[6];
+        int nf = 0;
+        size_t q = 0;
+        bool bad = false;
+        while (true) {
+            size_t t = line.find('\t', q);
+            std::string tok = line.substr(q, t == std::string::npos ? std::string::npos : t - q);
+            if (nf < 6) {
+                char* endp = nullptr;
+                v[nf] = strtoll(tok.c_str(), &endp, 10);
+                if (tok.empty() || *endp) bad = true;
+            }
+            nf++;
+            if (t == std::string::npos) break;
+            q = t + 1;
+        }
+        if (nf != 6) return "crai: expected 6 fields in index, got " + std::to_string(nf) + " at line " + std::to_string(iline);
+        if (bad) return "crai: unable to parse line " + std::to_string(iline);
+        if (v[0] == -1) continue;                               // unmapped (crai.go:147-150)
+        if (v[0] < 0) return "crai: bad seqID at line " + std::to_string(iline);
+        if ((size_t)v[0] >= out.size()) out.resize((size_t)v[0] + 1);
+        if (v[2] < 0) break;                                    // negative alnSpan: "breaking early" (crai.go:164-167)
+        out[(size_t)v[0]].start.push_back(v[1]);
+        out[(size_t)v[0]].span.push_back(v[2]);
+        out[(size_t)v[0]].bytes.push_back((int32_t)v[5]);
+        iline++;
+    }
+    return "";
+}
+
+bool crai_make_sizes(const int64_t* start_in, const int64_t* span_in, const int32_t* bytes, int64_t n, std::vector<int64_t>& sizes) {
+    const int64_t TW = 16384;
+    sizes.clear();
+    int64_t last_start = 0, last_val = 0;
+    for (int64_t s = 0; s < n; s++) {
+        int64_t st = start_in[s], sp = span_in[s];
+        bool first = true;
+        while (last_start < st - TW) {                          // back-fill the gap before this slice
+            sizes.push_back(first ? last_val : 0);
+            if (first) last_val = 0;
+            first = false;
+            last_start += TW;
+        }
+        if (st - last_start > TW) return false;                 // "tilewidth logic error"
+        while (st - last_start < -TW) { st += TW; sp -= TW; }   // a long read of the previous slice reached into this one
+        if (sp <= 0) continue;
+        const int64_t per_base = (int64_t)(100000 * (double)bytes[s] / (double)sp);
+        const int64_t n_tiles = (int64_t)((double)sp / (double)TW);
+        if (n_tiles == 0 && st - last_start < TW) { last_val = per_base; continue; }
+        sizes.insert(sizes.end(), (size_t)n_tiles, per_base);
+        const int64_t cmp = (st + sp) / TW;
+        if ((int64_t)sizes.size() > cmp + 1 || cmp < (int64_t)sizes.size() - 1) return false;   // "logic error"
+        last_start += TW * n_tiles;
+        last_val = per_base;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------- FAI
 std::string fai_read(const std::string& path, std::vector<RefInfo>& out) {
     FILE* f = fopen(path.c_str(), "r");

@@ -67,6 +67,13 @@ struct BaiIndex {
 };
 std::string bai_read(const std::string& path, BaiIndex& out);
 
+// ---------------------------------------------------------------------------------------------- CRAI
+// .crai (gzip'd text, 6 tab columns) -> per reference slices; sizes = the 16 KB pseudo-tiles indexcov uses for
+// CRAM (indexcov/crai/crai.go:56-192).  crai_make_sizes returns false where the reference panics.
+struct CraiSlices { std::vector<int64_t> start, span; std::vector<int32_t> bytes; };
+std::string crai_read(const std::string& path, std::vector<CraiSlices>& out);
+bool crai_make_sizes(const int64_t* start, const int64_t* span, const int32_t* bytes, int64_t n, std::vector<int64_t>& sizes);
+
 // ---------------------------------------------------------------------------------------------- FAI
 std::string fai_read(const std::string& path, std::vector<RefInfo>& out);
 

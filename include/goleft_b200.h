@@ -186,6 +186,12 @@ int  gl_bai_ref(const gl_bai* b, int32_t tid, const uint64_t** ioffsets, int64_t
                 uint64_t* unmapped, int32_t* has_stats);
 void gl_bai_free(gl_bai* b);
 
+/* CRAM index: one reference's slices (alignment start, span, slice bytes) -> 16 KB pseudo-tile sizes
+ * (indexcov/crai/crai.go:56-127).  GL_ERANGE where the reference panics, or when cap is too small
+ * (*n_sizes then holds the needed count). */
+int  gl_crai_make_sizes(const int64_t* aln_start, const int64_t* aln_span, const int32_t* slice_len, int64_t n,
+                        int64_t* sizes, int64_t cap, int64_t* n_sizes);
+
 /* ---------------------------------------------------------------- indexcov
  * Replaces indexcov/types.go:45-82 (getSizes), indexcov/indexcov.go:83-125 (Index.init),
  * :129-151 (NormalizedDepth), :170-177 (CountsAtDepth), :1050-1078 (counter.count),

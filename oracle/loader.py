@@ -242,3 +242,18 @@ def depthwed(means, starts, ends, chrom_id, size: int):
     k = lib.orc_depthwed(_ptr(means), S, R, _ptr(starts), _ptr(ends), _ptr(chrom_id), size, _ptr(o_s), _ptr(o_e), _ptr(o_c),
                          _ptr(out), cap)
     return o_s[:k], o_e[:k], o_c[:k], out[:k]
+
+
+_proto("orc_crai_sizes", C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, C.c_int64)
+
+
+def crai_sizes(start, span, nbytes) -> np.ndarray:
+    start = np.ascontiguousarray(start, np.int64)
+    span = np.ascontiguousarray(span, np.int64)
+    nbytes = np.ascontiguousarray(nbytes, np.int32)
+    n = lib.orc_crai_sizes(_ptr(start), _ptr(span), _ptr(nbytes), start.size, None, 0)
+    if n < 0:
+        raise ValueError("tilewidth logic error")
+    out = np.empty(n, np.int64)
+    lib.orc_crai_sizes(_ptr(start), _ptr(span), _ptr(nbytes), start.size, _ptr(out), n)
+    return out

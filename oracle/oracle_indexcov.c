@@ -269,3 +269,39 @@ int64_t orc_depthwed(const double* means, int32_t S, int64_t R, const int32_t* s
     }
     return n_out;
 }
+
+/* ---------------------------------------------------------------- N4: indexcov/crai/crai.go:56-127 (makeSizes)
+ * One reference's CRAM slices (alignment start, span, slice bytes) -> 16 KB pseudo-tile sizes.
+ * Returns the number of tiles, -1 where the reference panics ("tilewidth logic error" / "logic error"). */
+int64_t orc_crai_sizes(const int64_t* aln_start, const int64_t* aln_span, const int32_t* slice_len, int64_t n,
+                       int64_t* sizes, int64_t cap) {
+    const int64_t TW = 16384;
+    int64_t k_out = 0, lastStart = 0, lastVal = 0;
+    if (n == 0) return 0;
+    for (int64_t s = 0; s < n; s++) {
+        int64_t start = aln_start[s], span = aln_span[s];
+        int k = 0;
+        for (; lastStart < start - TW; lastStart += TW) {           /* :78-86 back fill gaps */
+            if (k_out < cap) sizes[k_out] = (k == 0) ? lastVal : 0;
+            k_out++;
+            if (k == 0) lastVal = 0;
+            k++;
+        }
+        int64_t overhang = start - lastStart;
+        if (overhang > TW) return -1;                               /* :88-90 */
+        while (overhang < -TW) {                                    /* :91-99 */
+            start += TW; span -= TW;
+            overhang = start - lastStart;
+        }
+        if (span <= 0) continue;                                    /* :100-104 */
+        int64_t perBase = (int64_t)(100000 * (double)slice_len[s] / (double)span);   /* :106 */
+        int64_t nTiles = (int64_t)((double)span / (double)TW);      /* :108 */
+        if (nTiles == 0 && start - lastStart < TW) { lastVal = perBase; continue; }
+        for (int64_t i = 0; i < nTiles; i++) { if (k_out < cap) sizes[k_out] = perBase; k_out++; }
+        int64_t cmp = (start + span) / TW;
+        if (k_out > cmp + 1 || cmp < k_out - 1) return -1;          /* :118-121 */
+        lastStart += TW * nTiles;
+        lastVal = perBase;
+    }
+    return k_out;
+}

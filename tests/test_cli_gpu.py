@@ -287,3 +287,41 @@ def test_depthwed(tmp_path):
     assert out[0] == "#chrom\tstart\tend\ts0\ts1\ts2\ts3"
     exp = ["%s\t%d\t%d\t" % (["chr1", "chrX"][c], s, e) + "\t".join(str(int(v)) for v in row) for s, e, c, row in zip(s_, e_, c_, m_)]
     assert out[1:] == exp
+
+
+@pytest.mark.gpu
+def test_indexcov_crai_cohort(tmp_path):
+    """CRAM indexes (.crai): interpolated 16 KB pseudo-tiles (indexcov/crai/crai.go:56-127) through the same cohort path"""
+    rng = np.random.default_rng(9)
+    refs = [("1", 4_000_000), ("2", 2_500_000)]
+    fai = tmp_path / "g.fa.fai"
+    fai.write_text("".join("%s\t%d\t6\t60\t61\n" % r for r in refs))
+    paths, slices = [], []
+    for k in range(5):
+        per = []
+        lines = []
+        for si, (name, L) in enumerate(refs):
+            st = np.cumsum(rng.integers(150_000, 400_000, 9)).astype(np.int64) + 1
+            st = st[st < L - 10]
+            sp = rng.integers(200_000, 420_000, st.size).astype(np.int64)
+            by = rng.integers(2_000_000, 4_000_000, st.size).astype(np.int32)
+            per.append((st, sp, by))
+            lines += ["%d\t%d\t%d\t%d\t%d\t%d\n" % (si, a, b, 1000 + i, 10, c) for i, (a, b, c) in enumerate(zip(st, sp, by))]
+        lines.append("-1\t0\t0\t99\t10\t500\n")
+        p = tmp_path / ("cram%d.crai" % k)
+        p.write_bytes(gzip.compress("".join(lines).encode()))
+        paths.append(str(p)); slices.append(per)
+    out = tmp_path / "cc"
+    run("indexcov", "-d", str(out), "--fai", str(fai), *paths)
+    exp_rows = ["#chrom\tstart\tend\t" + "\t".join("cram%d" % k for k in range(5))]
+    depths = []
+    for k in range(5):
+        sz = [orc.crai_sizes(*slices[k][r]) for r in range(2)]
+        m = orc.ic_median(np.concatenate(sz))
+        depths.append([orc.ic_normalize(x, float(m)) for x in sz])
+    for r, (name, L) in enumerate(refs):
+        longest = max(len(depths[k][r]) for k in range(5))
+        for i in range(longest):
+            exp_rows.append("%s\t%d\t%d\t" % (name, i * 16384, (i + 1) * 16384) +
+                            "\t".join("0" if i >= len(depths[k][r]) else "%.3g" % depths[k][r][i] for k in range(5)))
+    assert gzip.open(str(out / "cc-indexcov.bed.gz"), "rt").read().splitlines() == exp_rows

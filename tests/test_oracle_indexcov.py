@@ -124,6 +124,45 @@ def test_depthwed_groups():
     assert out.shape == (6, 2) and out[:, 0].tolist() == [1, 3, 3, 1, 10, 0]
 
 
+def test_crai_sizes_reference_test_vector():
+    """the index embedded in indexcov/crai/crai_test.go:1030-1036 (TestSizes only prints it; these pins are
+    restatement-derived): gaps are back-filled with the previous value then zeros, spans become whole tiles"""
+    from goleft_b200 import capi
+    rows = [(10000, 98379, 376975), (108293, 223811, 340259), (332008, 216930, 339687), (149775203, 134825, 357798),
+            (149909940, 135166, 313541)]
+    st, sp, by = zip(*rows)
+    a = orc.crai_sizes(st, sp, by)
+    assert a.size == 9157 and a[:6].tolist() == [383186] * 6 and a[6] == 152029
+    assert a[-8:].tolist() == [231967] * 8 and int((a == 0).sum()) > 9000
+    assert np.array_equal(capi.crai_make_sizes(st, sp, by), a)             # the product's host code agrees
+    assert orc.crai_sizes([], [], []).size == 0
+
+
+def test_crai_sizes_viral_fixture_and_random():
+    from goleft_b200 import capi
+    z = np.load(os.path.join(ROOT, "tests", "golden", "viral_crai_slices.npz"))
+    total = 0
+    for si in np.unique(z["seq"]):
+        m = z["seq"] == si
+        a = orc.crai_sizes(z["start"][m], z["span"][m], z["nbytes"][m])
+        assert np.array_equal(capi.crai_make_sizes(z["start"][m], z["span"][m], z["nbytes"][m]), a)
+        total += a.size
+    assert total == 191442
+    rng = np.random.default_rng(12)
+    for _ in range(200):                                                    # long-read style overlapping slices
+        n = int(rng.integers(1, 40))
+        st = np.cumsum(rng.integers(1, 400000, n)).astype(np.int64)
+        sp = rng.integers(1, 600000, n).astype(np.int64)
+        by = rng.integers(1, 4_000_000, n).astype(np.int32)
+        try:
+            a = orc.crai_sizes(st, sp, by)
+        except ValueError:
+            with pytest.raises(capi.GlError):
+                capi.crai_make_sizes(st, sp, by)
+            continue
+        assert np.array_equal(capi.crai_make_sizes(st, sp, by), a)
+
+
 def test_library_exports_every_declared_symbol():
     """-m 'not gpu': the C-ABI library loads and exports every entry point include/goleft_b200.h declares."""
     from goleft_b200 import capi
