@@ -438,7 +438,9 @@ static int cmd_indexcov(int argc, char** argv) {
         std::vector<int64_t> b4(S * 4);
         glck(ctx, gl_indexcov_counts_batch(ctx, flat.data(), seg_ptr.data(), lg.data(), (int32_t)S, counts.data(), b4.data()), "gl_indexcov_counts_batch");
 
-        // bed.gz rows (indexcov.go:678-680,1038-1048)
+        // bed.gz rows (indexcov.go:678-680,1038-1048): every "%.3g" comes from the GPU formatter as a 10-byte token
+        std::vector<uint8_t> tok(flat.size() * 10 + 10);
+        glck(ctx, gl_format_g3(ctx, flat.data(), (int64_t)flat.size(), tok.data()), "gl_format_g3");
         std::string row;
         char num[48];
         for (size_t i = 0; i < longest; i++) {
@@ -446,8 +448,11 @@ static int cmd_indexcov(int argc, char** argv) {
             snprintf(num, sizeof num, "\t%zu\t%zu", i * 16384, (i + 1) * 16384);
             row += num;
             for (size_t k = 0; k < S; k++) {
-                if (i >= (size_t)lens[k]) row += "\t0";
-                else { snprintf(num, sizeof num, "\t%.3g", (double)dptr[k][i]); row += num; }
+                row.push_back('\t');
+                if (i >= (size_t)lens[k]) { row.push_back('0'); continue; }
+                const uint8_t* t = &tok[((size_t)seg_ptr[k] + i) * 10];
+                if (t[9]) row.append(reinterpret_cast<const char*>(t), t[9]);
+                else { snprintf(num, sizeof num, "%.3g", (double)dptr[k][i]); row += num; }   // magnitude outside the kernel's range
             }
             row += "\n";
             bgz.write(row.data(), row.size());

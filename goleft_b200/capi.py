@@ -96,6 +96,8 @@ _proto("gl_indexcov_bins", C.c_int, _vp, _vp, C.c_int64, C.c_int64, _vp)
 _proto("gl_indexcov_counts_batch", C.c_int, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp)
 _proto("gl_indexcov_counts_batch_device", C.c_int, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp)
 _proto("gl_indexcov_xnorm", C.c_int, _vp, _vp, _vp, C.c_int32, C.c_int32)
+_proto("gl_format_g3", C.c_int, _vp, _vp, C.c_int64, _vp)
+_proto("gl_format_g3_device", C.c_int, _vp, _vp, C.c_int64, _vp)
 _proto("gl_bincount_i32", C.c_int, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp)
 _proto("gl_depthwed_aggregate", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp,
        C.c_int64, _i64p)
@@ -497,6 +499,13 @@ class Ctx:
     def depthwed_aggregate_device(self, d_means: DevBuf, S: int, R: int, d_grp: Optional[DevBuf], n_out: int, d_out: DevBuf):
         self._ck(lib.gl_depthwed_aggregate_device(self.h, d_means.ptr, S, R, d_grp.ptr if d_grp is not None else None, n_out,
                                                   d_out.ptr))
+
+    def format_g3(self, vals: np.ndarray) -> np.ndarray:
+        """(n,10) uint8 tokens: text in [0:len), len in byte 9"""
+        vals = _as(vals, np.float32)
+        tok = np.empty((vals.size, 10), np.uint8)
+        self._ck(lib.gl_format_g3(self.h, _ptr(vals), vals.size, _ptr(tok)))
+        return tok
 
     # ---- covstats / depthwed
     def bincount(self, v: np.ndarray, lo: int, hi: int) -> np.ndarray:

@@ -6,6 +6,8 @@
 //                                                                                      (indexcov.go:83-151)
 //   I4+I5 ic_counts_kernel  per (sample, chromosome) segment: 70-slot histogram + in/out/hi/low counters
 //                                                                            (indexcov.go:170-177,1050-1078)
+//   I6  fmt_g3_kernel       float32 -> the bytes of "%.3g", exact (integer arithmetic), 10-byte tokens
+//                                                                              (indexcov.go:678-680,1038-1048)
 //   I7  ic_xnorm_kernel     cross-sample normalisation, sequential in tile j, parallel over samples, with the
 //                           float64 mean reproduced bit-exactly (order-free when provably exact, else ordered)
 //   V2  bincount_kernel     shared-memory privatised histogram (covstats/covstats.go:202-217)
@@ -363,6 +365,88 @@ __global__ void __launch_bounds__(256) depthwed_kernel(const double* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ I6
+// float32 -> the bytes of Go's fmt "%.3g" (== C printf "%.3g" of the same value), exactly: the three significant
+// digits come from integer arithmetic on mantissa * 10^k (128-bit), rounded half-to-even on the exact binary
+// value, never from floating-point scaling.  Output: 10-byte tokens, bytes [0..len) = text, byte 9 = len
+// (len 0 = "format this one on the host": magnitudes outside [1e-15, 1e15), not seen in normalised depths).
+__device__ __forceinline__ unsigned __int128 pow10_u128(int k) {
+    unsigned __int128 r = 1;
+    for (int i = 0; i < k; i++) r *= 10;
+    return r;
+}
+
+// round_half_even( m * 2^e2 * 10^k ) for 0 <= result < 2^63
+__device__ __forceinline__ unsigned long long scaled_round(unsigned m, int e2, int k) {
+    unsigned __int128 num = m, den = 1;
+    if (k >= 0) num *= pow10_u128(k); else den *= pow10_u128(-k);
+    if (e2 >= 0) num <<= e2; else den <<= -e2;
+    unsigned __int128 q = num / den, r = num % den;
+    const unsigned __int128 twice = r * 2;
+    if (twice > den || (twice == den && (q & 1))) q++;
+    return (unsigned long long)q;
+}
+
+__global__ void __launch_bounds__(256) fmt_g3_kernel(const float* __restrict__ v, long long n, unsigned char* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned char t[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) t[k] = 0;
+    const float f = v[i];
+    const unsigned bits = __float_as_uint(f);
+    const bool neg = bits >> 31;
+    const unsigned ex = (bits >> 23) & 0xff, frac = bits & 0x7fffff;
+    int len = 0;
+    if (ex == 0xff) {                                            // Go: "+Inf" "-Inf" "NaN"
+        if (frac) { t[0] = 'N'; t[1] = 'a'; t[2] = 'N'; len = 3; }
+        else { t[0] = neg ? '-' : '+'; t[1] = 'I'; t[2] = 'n'; t[3] = 'f'; len = 4; }
+    } else if (ex == 0 && frac == 0) {
+        if (neg) t[len++] = '-';
+        t[len++] = '0';
+    } else {
+        const unsigned m = ex ? (frac | 0x800000u) : frac;
+        const int e2 = ex ? (int)ex - 150 : -149;
+        int e10 = (int)floor(log10((double)fabsf(f)));
+        if (e10 < -15 || e10 >= 15) {
+            len = 0;                                             // host formats it
+        } else {
+            unsigned long long N = scaled_round(m, e2, 2 - e10);
+            if (N < 100) { e10--; N = scaled_round(m, e2, 2 - e10); }          // log10 estimate one too high
+            else if (N > 1000) { e10++; N = scaled_round(m, e2, 2 - e10); }    // one too low
+            if (N >= 1000) { N = 100; e10++; }                                 // 999.5.. rounds up to the next decade
+            const int d1 = (int)(N / 100), d2 = (int)(N / 10 % 10), d3 = (int)(N % 10);
+            const int nd = d3 ? 3 : (d2 ? 2 : 1);                // significant digits after stripping zeros
+            const int dig[3] = {d1, d2, d3};
+            if (neg) t[len++] = '-';
+            if (e10 < -4 || e10 >= 3) {                          // %e form, exponent at least two digits
+                t[len++] = (unsigned char)('0' + d1);
+                if (nd > 1) { t[len++] = '.'; t[len++] = (unsigned char)('0' + d2); if (nd > 2) t[len++] = (unsigned char)('0' + d3); }
+                t[len++] = 'e';
+                t[len++] = e10 < 0 ? '-' : '+';
+                const int ae = e10 < 0 ? -e10 : e10;
+                t[len++] = (unsigned char)('0' + ae / 10);
+                t[len++] = (unsigned char)('0' + ae % 10);
+            } else if (e10 >= 0) {                               // d[.d[d]] with the point after e10+1 digits
+                for (int k = 0; k < 3; k++) {
+                    if (k <= e10 || k < nd) {
+                        if (k == e10 + 1) t[len++] = '.';
+                        t[len++] = (unsigned char)('0' + dig[k]);
+                    }
+                }
+            } else {                                             // 0.000ddd
+                t[len++] = '0'; t[len++] = '.';
+                for (int z = 0; z < -e10 - 1; z++) t[len++] = '0';
+                for (int k = 0; k < nd; k++) t[len++] = (unsigned char)('0' + dig[k]);
+            }
+        }
+    }
+    t[9] = (unsigned char)len;
+    unsigned char* o = out + i * 10;
+#pragma unroll
+    for (int k = 0; k < 10; k++) o[k] = t[k];
+}
+
 // small helper: a scratch device buffer per call site
 int dev_tmp(gl_ctx* ctx, gl_buf& b, size_t bytes) { return gl_buf_reserve(ctx, b, bytes ? bytes : 16); }
 
@@ -570,6 +654,38 @@ int gl_indexcov_xnorm(gl_ctx* ctx, float* depths, const int32_t* lens, int32_t S
             cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexcov_xnorm: %s", cudaGetErrorString(cudaGetLastError())); break; }
     } while (0);
     cudaFree(bd.p); cudaFree(bl.p);
+    return rc;
+}
+
+int gl_format_g3_device(gl_ctx* ctx, const float* d_vals, int64_t n, uint8_t* d_tokens) {
+    GL_CHECK(gl_use(ctx));
+    if (n < 0 || (n > 0 && (!d_vals || !d_tokens))) return gl_fail(ctx, GL_EINVAL, "gl_format_g3_device: bad argument");
+    if (n == 0) return GL_OK;
+    {
+        gl_prof_scope prof(ctx, "fmt_g3_kernel");
+        fmt_g3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_vals, n, d_tokens);
+    }
+    GL_LAUNCHED(ctx, 1);
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+int gl_format_g3(gl_ctx* ctx, const float* vals, int64_t n, uint8_t* tokens) {
+    GL_CHECK(gl_use(ctx));
+    if (n < 0 || (n > 0 && (!vals || !tokens))) return gl_fail(ctx, GL_EINVAL, "gl_format_g3: bad argument");
+    if (n == 0) return GL_OK;
+    gl_buf bv, bt;
+    GL_CHECK(dev_tmp(ctx, bv, (size_t)n * 4));
+    GL_CHECK(dev_tmp(ctx, bt, (size_t)n * 10));
+    int rc = GL_OK;
+    do {
+        if (cudaMemcpyAsync(bv.p, vals, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_format_g3: H2D failed"); break; }
+        rc = gl_format_g3_device(ctx, static_cast<const float*>(bv.p), n, static_cast<uint8_t*>(bt.p));
+        if (rc != GL_OK) break;
+        if (cudaMemcpyAsync(tokens, bt.p, (size_t)n * 10, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_format_g3: D2H failed"); break; }
+    } while (0);
+    cudaFree(bv.p); cudaFree(bt.p);
     return rc;
 }
 

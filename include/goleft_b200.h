@@ -225,6 +225,10 @@ int  gl_indexcov_counts_batch(gl_ctx* ctx, const float* depth, const int64_t* se
                               int32_t n_seg, int32_t* counts70, int64_t* bins4);
 int  gl_indexcov_counts_batch_device(gl_ctx* ctx, const float* d_depth, const int64_t* d_seg_ptr,
                                      const int64_t* d_longest, int32_t n_seg, int32_t* d_counts70, int64_t* d_bins4);
+/* I6: the "%.3g" of every value (the bed.gz row writer, indexcov.go:678-680,1038-1048): 10-byte tokens,
+ * bytes [0..len) = text, byte 9 = len; len 0 means the magnitude is outside [1e-15,1e15) and the host formats it. */
+int  gl_format_g3(gl_ctx* ctx, const float* vals, int64_t n, uint8_t* tokens);
+int  gl_format_g3_device(gl_ctx* ctx, const float* d_vals, int64_t n, uint8_t* d_tokens);
 /* I7: in-place cross-sample normalisation of one chromosome; depths is S rows of stride T,
  * lens[i] valid entries in row i.  No-op for S < 5 (indexcov.go:551). */
 int  gl_indexcov_xnorm(gl_ctx* ctx, float* depths, const int32_t* lens, int32_t S, int32_t T);

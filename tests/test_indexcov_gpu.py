@@ -132,3 +132,36 @@ def test_depthwed(ctx):
         e = orc.depthwed(means, starts, ends, chrom_id, size)
         for a, b in zip(g, e):
             assert np.array_equal(a, b), size
+
+
+def test_format_g3_exact(ctx):
+    """I6: the GPU "%.3g" tokens equal printf's for every value tried: random magnitudes, the half-way cases of
+    3-digit rounding, powers of ten, denormals/huge values (host fallback), zero, inf, nan"""
+    rng = np.random.default_rng(10)
+    vals = [np.float32(x) for x in (0.0, -0.0, 1.0, 0.5, 999.5, 999.4999, 99.95, 9.995, 0.9995, 0.09995, 1000.0, 1000.5, 1005.0,
+                                      9995.0, 99950.0, 1e-4, 9.9949e-5, 9.995e-5, 1e-5, 1.2345e-7, 50000.0, 0.125, 0.375, 2.5,
+                                      1.005, 1.015, 1.025, 100.5, 101.5, 1e15, 9.99e14, 1e-15, 9.9e-16, 1e-30, 3e38, 1e-45,
+                                      np.inf, -np.inf, np.nan, -3.14159, 123456.0, 12.25, 12.35, 12.45)]
+    a = np.concatenate([np.array(vals, np.float32),
+                        np.exp(rng.uniform(np.log(1e-16), np.log(1e16), 400_000)).astype(np.float32),
+                        np.abs(rng.normal(1.0, 0.4, 400_000)).astype(np.float32),
+                        (rng.integers(1, 10000, 200_000) / np.float32(8.0)).astype(np.float32),       # many exact ties
+                        (rng.integers(100, 100000, 200_000).astype(np.float32) * np.float32(0.005)),
+                        -np.abs(rng.normal(3, 5, 1000)).astype(np.float32)])
+    tok = ctx.format_g3(a)
+    n_host = 0
+    for v, t in zip(a, tok):
+        ln = int(t[9])
+        if ln == 0:
+            n_host += 1
+            assert not (1e-15 <= abs(float(v)) < 1e15)
+            continue
+        got = bytes(t[:ln]).decode()
+        if np.isnan(v):
+            exp = "NaN"
+        elif np.isinf(v):
+            exp = "+Inf" if v > 0 else "-Inf"
+        else:
+            exp = "%.3g" % float(v)
+        assert got == exp, (float(v), got, exp)
+    assert n_host < 60_000
