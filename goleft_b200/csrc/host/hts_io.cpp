@@ -121,20 +121,19 @@ std::string bgzf_inflate_stream(const std::string& path, int threads, bgzf_sink_
 }
 
 // ---------------------------------------------------------------------------------------------- writer
-BgzfWriter::BgzfWriter(const std::string& path) { f_ = fopen(path.c_str(), "wb"); buf_.reserve(0xff00); }
-BgzfWriter::~BgzfWriter() { close(); }
+namespace {
+constexpr size_t kBlockIn = 0xff00;                  // uncompressed bytes per BGZF block
+constexpr size_t kBatchBlocks = 256;                 // 16 MB of text per parallel deflate round
 
-void BgzfWriter::flush_block() {
-    FILE* f = static_cast<FILE*>(f_);
-    if (!f) return;
-    uint8_t out[0x10000 + 64];
+// one BGZF member (indexcov.go:248-257: ModTime 0, OS 0xff); out must hold 64 KB + 64
+size_t bgzf_deflate_block(const uint8_t* in, size_t n, uint8_t* out) {
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
-    zs.next_in = buf_.data();
-    zs.avail_in = (uInt)buf_.size();
+    zs.next_in = const_cast<Bytef*>(in);
+    zs.avail_in = (uInt)n;
     zs.next_out = out + 18;
-    zs.avail_out = sizeof(out) - 18 - 8;
+    zs.avail_out = 0x10000 + 64 - 18 - 8;
     deflate(&zs, Z_FINISH);
     const size_t clen = zs.total_out;
     deflateEnd(&zs);
@@ -143,28 +142,58 @@ void BgzfWriter::flush_block() {
     const size_t bsize = 18 + clen + 8;
     out[16] = (uint8_t)((bsize - 1) & 0xff);
     out[17] = (uint8_t)((bsize - 1) >> 8);
-    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf_.data(), (uInt)buf_.size());
-    const uint32_t isz = (uint32_t)buf_.size();
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), in, (uInt)n);
+    const uint32_t isz = (uint32_t)n;
     for (int i = 0; i < 4; i++) { out[18 + clen + i] = (uint8_t)(crc >> (8 * i)); out[22 + clen + i] = (uint8_t)(isz >> (8 * i)); }
-    fwrite(out, 1, bsize, f);
+    return bsize;
+}
+}  // namespace
+
+BgzfWriter::BgzfWriter(const std::string& path) { f_ = fopen(path.c_str(), "wb"); buf_.reserve(kBlockIn * kBatchBlocks); }
+BgzfWriter::~BgzfWriter() { close(); }
+
+void BgzfWriter::flush_batch() {
+    FILE* f = static_cast<FILE*>(f_);
+    if (!f || buf_.empty()) return;
+    const size_t nblk = (buf_.size() + kBlockIn - 1) / kBlockIn;
+    std::vector<std::vector<uint8_t>> outs(nblk);
+    std::vector<size_t> lens(nblk, 0);
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= nblk) break;
+            const size_t off = i * kBlockIn, n = std::min(kBlockIn, buf_.size() - off);
+            outs[i].resize(0x10000 + 64);
+            lens[i] = bgzf_deflate_block(buf_.data() + off, n, outs[i].data());
+        }
+    };
+    const size_t nt = std::min<size_t>(nblk, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    for (size_t i = 0; i < nblk; i++) fwrite(outs[i].data(), 1, lens[i], f);
     buf_.clear();
 }
 
 void BgzfWriter::write(const char* p, size_t n) {
     while (n) {
-        const size_t room = 0xff00 - buf_.size();
+        const size_t room = kBlockIn * kBatchBlocks - buf_.size();
         const size_t k = std::min(room, n);
         buf_.insert(buf_.end(), p, p + k);
         p += k; n -= k;
-        if (buf_.size() == 0xff00) flush_block();
+        if (buf_.size() == kBlockIn * kBatchBlocks) flush_batch();
     }
 }
 
 void BgzfWriter::close() {
     FILE* f = static_cast<FILE*>(f_);
     if (!f) return;
-    if (!buf_.empty()) flush_block();
-    flush_block();                                   // empty block = BGZF EOF marker
+    flush_batch();
+    uint8_t eof_block[0x10000 + 64];
+    const size_t n = bgzf_deflate_block(nullptr, 0, eof_block);      // empty block = BGZF EOF marker
+    fwrite(eof_block, 1, n, f);
     fclose(f);
     f_ = nullptr;
 }

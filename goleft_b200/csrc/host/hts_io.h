@@ -29,9 +29,9 @@ public:
     void write(const char* p, size_t n);
     void close();
 private:
-    void flush_block();
+    void flush_batch();                              // deflates the pending 64 KB blocks on all cores, writes them in order
     void* f_ = nullptr;
-    std::vector<uint8_t> buf_;
+    std::vector<uint8_t> buf_;                       // pending uncompressed bytes (up to kBatchBlocks blocks)
 };
 
 // ---------------------------------------------------------------------------------------------- BAM
