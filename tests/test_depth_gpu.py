@@ -300,3 +300,25 @@ def test_packed16_path(ctx):
     r0, rc = ctx.depth_get_runs()
     ea, ec = orc.class_runs(exp, 1234, 4_000_000, 4, 0, 0)
     assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
+
+
+def test_chr1_sized_contig(ctx):
+    """BASELINE config[2]'s largest shard unit: a 248,956,422 bp contig at 30x (41 M reads), one launch per kernel.
+    Checks the size-independent properties (sum of window sums == total clipped segment length; runs strictly
+    increasing from 0; packed16 path == int32 path) and then the full oracle comparison."""
+    L, W = 248_956_422, 500
+    s, e = synth.segments(synth.reads(L, contig_index=0))
+    step = 10_000_000
+    ws, r0, rc = ctx.depth_region(0, L, s, e, W, 4, 0, run_break=step,
+                                  out=(np.empty((L - 1) // W + 1, np.int64), np.empty(1 << 22, np.int32), np.empty(1 << 22, np.uint8)))
+    assert ctx.depth_last_path() == 1
+    assert int(ws.sum()) == int((np.minimum(e, L).astype(np.int64) - np.maximum(s, 0)).clip(0).sum())
+    assert r0[0] == 0 and (np.diff(r0) > 0).all() and r0[-1] < L
+    a, o, ln = capi.pack_segments16(s, e)
+    ws2, r02, rc2 = ctx.depth_region_packed16(0, L, a, o, ln, W, 4, 0, run_break=step,
+                                              out=(np.empty(ws.size, np.int64), np.empty(1 << 22, np.int32), np.empty(1 << 22, np.uint8)))
+    assert np.array_equal(ws, ws2) and np.array_equal(r0, r02) and np.array_equal(rc, rc2)
+    exp = orc.pileup_diff(s, e, 0, L)
+    es, _ = orc.window_sums(exp, 0, L, W)
+    ea, ec = orc.class_runs(exp, 0, L, 4, 0, step)
+    assert np.array_equal(ws, es) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
