@@ -667,6 +667,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const Scan
         se[j] = ok ? be[i] : 0;
     }
     cells = fused_load_cells(p, b0, tile + G, maxlen);
+    __syncthreads();          // every warp has read s_rng before iteration 0 rewrites it (found by compute-sanitizer racecheck)
 
     for (int it = 0; tile < p.num_tiles; tile += G, it ^= 1) {
         int* s_carry = s_carry2[it];
