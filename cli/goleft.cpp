@@ -206,16 +206,76 @@ static int cmd_depth(int argc, char** argv) {
     rstart.resize(1 << 16); rclass.resize(1 << 16);
 
     if (!bed.empty()) {
-        for (const Region& r : regions) {                                   // one chunk per BED line
-            if (r.e <= r.s) continue;
-            int64_t nw = 0, nr = 0;
-            run_region(r.chrom, r.s, r.e, 0, nw, nr);
+        // One pass per contig instead of one per BED line: window sums + class runs of the span the contig's regions
+        // cover (run_break 0), the clipped first/last window of every region from gl_depth_interval_sums, then the
+        // reference's rows region by region in BED order (depth.go:293-358 sees each line as its own chunk).
+        std::vector<std::string> out_hd(regions.size()), out_ca(regions.size());
+        auto format_one = [&](size_t k, const int64_t* ws, int64_t nw, const int32_t* rs_, const uint8_t* rc_, int64_t nr) {
             char *hd = nullptr, *ca = nullptr;
             int64_t hl = 0, cl = 0;
-            if (gl_depth_format_chunk(r.chrom.c_str(), r.s, r.e, W, sums.data(), nw, rstart.data(), rclass.data(), nr, &hd, &hl, &ca, &cl) != GL_OK)
+            if (gl_depth_format_chunk(regions[k].chrom.c_str(), regions[k].s, regions[k].e, W, ws, nw, rs_, rc_, nr, &hd, &hl, &ca, &cl) != GL_OK)
                 fatal(1, "gl_depth_format_chunk failed");
-            fwrite(hd, 1, (size_t)hl, fhd); fwrite(ca, 1, (size_t)cl, fca);
+            out_hd[k].assign(hd, (size_t)hl); out_ca[k].assign(ca, (size_t)cl);
             gl_free_text(hd); gl_free_text(ca);
+        };
+        std::map<std::string, std::vector<size_t>> by_chrom;
+        std::vector<std::string> chrom_order;
+        for (size_t k = 0; k < regions.size(); k++) {
+            if (regions[k].e <= regions[k].s) continue;
+            auto ins = by_chrom.emplace(regions[k].chrom, std::vector<size_t>());
+            if (ins.second) chrom_order.push_back(regions[k].chrom);
+            ins.first->second.push_back(k);
+        }
+        std::vector<int64_t> rsum, edge;
+        std::vector<int32_t> ia, ib, rrs;
+        std::vector<uint8_t> rrc;
+        for (const std::string& c : chrom_order) {
+            const std::vector<size_t>& ks = by_chrom[c];
+            long long lo = regions[ks[0]].s, hi = regions[ks[0]].e;
+            for (size_t k : ks) { lo = std::min(lo, regions[k].s); hi = std::max(hi, regions[k].e); }
+            const long long span_s = lo / W * W;
+            int64_t nw = 0, nr = 0;
+            bool batched = tid_of.count(c) != 0 && ks.size() > 1 && hi - span_s < (1LL << 31) - 2 * (long long)W;
+            if (batched) {
+                run_region(c, span_s, hi, 0, nw, nr);
+                int32_t path = 0;
+                batched = gl_depth_last_path(ctx, &path) == GL_OK && path == 1;                     // the interval sums want the fused path's cell index
+            }
+            if (!batched) {
+                for (size_t k : ks) {
+                    run_region(c, regions[k].s, regions[k].e, 0, nw, nr);
+                    format_one(k, sums.data(), nw, rstart.data(), rclass.data(), nr);
+                }
+                continue;
+            }
+            ia.clear(); ib.clear();
+            for (size_t k : ks) {                                            // clipped edge windows
+                const long long s = regions[k].s, e = regions[k].e, w0 = s / W, w1 = (e - 1) / W;
+                if (s % W != 0 || (w0 == w1 && e != (w0 + 1) * W)) { ia.push_back((int32_t)s); ib.push_back((int32_t)std::min(e, (w0 + 1) * W)); }
+                if (w1 > w0 && e != (w1 + 1) * W) { ia.push_back((int32_t)(w1 * W)); ib.push_back((int32_t)e); }
+            }
+            edge.resize(ia.size());
+            if (!ia.empty()) glck(ctx, gl_depth_interval_sums(ctx, ia.data(), ib.data(), (int64_t)ia.size(), edge.data()), "gl_depth_interval_sums");
+            size_t ei = 0;
+            const long long sw0 = span_s / W;
+            for (size_t k : ks) {
+                const long long s = regions[k].s, e = regions[k].e, w0 = s / W, w1 = (e - 1) / W;
+                rsum.assign(sums.begin() + (w0 - sw0), sums.begin() + (w1 - sw0) + 1);
+                if (s % W != 0 || (w0 == w1 && e != (w0 + 1) * W)) rsum[0] = edge[ei++];
+                if (w1 > w0 && e != (w1 + 1) * W) rsum.back() = edge[ei++];
+                const int32_t* rb = rstart.data();
+                const int32_t* first = std::upper_bound(rb, rb + nr, (int32_t)s);          // first run starting after s
+                const int32_t* last = std::lower_bound(rb, rb + nr, (int32_t)e);
+                rrs.assign(1, (int32_t)s);
+                rrc.assign(1, rclass[(size_t)(first - rb) - 1]);                           // run_start[0] == span_s <= s
+                rrs.insert(rrs.end(), first, last);
+                rrc.insert(rrc.end(), rclass.data() + (first - rb), rclass.data() + (last - rb));
+                format_one(k, rsum.data(), (int64_t)rsum.size(), rrs.data(), rrc.data(), (int64_t)rrs.size());
+            }
+        }
+        for (size_t k = 0; k < regions.size(); k++) {
+            fwrite(out_hd[k].data(), 1, out_hd[k].size(), fhd);
+            fwrite(out_ca[k].data(), 1, out_ca[k].size(), fca);
         }
     } else {
         // whole contig in one pass (run_break = step reproduces the reference's per-chunk run boundaries),

@@ -84,6 +84,7 @@ _proto("gl_depth_get_runs", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_windows", C.c_int, _vp, C.c_int32, _vp, _vp, C.c_int64)
 _proto("gl_depth_classes", C.c_int, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_depth_perbase", C.c_int, _vp, _vp)
+_proto("gl_depth_interval_sums", C.c_int, _vp, _vp, _vp, C.c_int64, _vp)
 _proto("gl_depth_region", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_indexcov_sizes", C.c_int, _vp, _vp, _vp, C.c_int32, _vp, _vp)
@@ -413,6 +414,12 @@ class Ctx:
         n = C.c_int64(0)
         self._ck(lib.gl_depth_classes(self.h, mincov, maxmean, _ptr(rs_), _ptr(re_), _ptr(rc_), cap, C.byref(n)))
         return rs_[: n.value], re_[: n.value], rc_[: n.value]
+
+    def depth_interval_sums(self, a, b) -> np.ndarray:
+        a, b = _as(a, np.int32), _as(b, np.int32)
+        out = np.empty(a.size, np.int64)
+        self._ck(lib.gl_depth_interval_sums(self.h, _ptr(a), _ptr(b), a.size, _ptr(out)))
+        return out
 
     def depth_perbase(self, length: int) -> np.ndarray:
         out = np.empty(length, np.int32)

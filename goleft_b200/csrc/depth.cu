@@ -749,6 +749,45 @@ __global__ void __launch_bounds__(256) depth_gather_runs_kernel(const uint64_t* 
     }
 }
 
+// Sum of per-base depth over arbitrary intervals [a,b) of the open region, straight from the segments:
+// sum_x depth(x) = sum over segments of |segment ∩ [a,b)|.  One warp per interval.  With the cell index of the last
+// fused reduce only the segments that can reach the interval are visited; without it (general path) every segment is.
+// Used for the clipped edge windows of BED regions (depth/depth.go:293-305 with regionStart/regionEnd inside a window).
+__global__ void __launch_bounds__(256) depth_interval_sum_kernel(const ScanParams p, const int* __restrict__ ia, const int* __restrict__ ib,
+                                                                long long n_iv, int use_index, long long* __restrict__ out) {
+    const long long iv = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (iv >= n_iv) return;
+    const int a = max(ia[iv], p.rs), b = min(ib[iv], p.re);
+    unsigned long long sum = 0;
+    if (a < b) {
+        int maxlen = 0;
+        if (use_index) {
+            for (int k = lane; k < kLenSlots; k += 32) maxlen = max(maxlen, p.flags[16 + k]);
+            maxlen = __reduce_max_sync(kFull, maxlen);
+        }
+        for (int bi = 0; bi < p.n_batches; bi++) {
+            const BatchDesc& bd = p.batch[bi];
+            unsigned lo = 0, hi = (unsigned)bd.n;
+            if (use_index) {
+                const int lo_cell = (max(a - maxlen, p.origin) - p.origin) >> kCellShift;
+                const int hi_cell = min(((b - 1 - p.origin) >> kCellShift) + 1, p.ncells);
+                unsigned l = 0xffffffffu, h = 0;
+                for (int c = lo_cell + lane; c < hi_cell; c += 32) { l = min(l, ~bd.cell_lo[c]); h = max(h, bd.cell_hi[c]); }
+                lo = __reduce_min_sync(kFull, l);
+                hi = __reduce_max_sync(kFull, h);
+            }
+            for (unsigned i = lo + lane; i < hi; i += 32) {
+                const int s = max(bd.start[i], a), e = min(bd.end[i], b);
+                if (s < e) sum += (unsigned)(e - s);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+    if (lane == 0) out[iv] = (long long)sum;
+}
+
 __global__ void run_ends_kernel(const int* run_start, int* run_end, long long n, int re) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) run_end[i] = (i + 1 < n) ? run_start[i + 1] : re;
@@ -949,6 +988,10 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
         GL_CHECK(read_header(ctx, hdr));
         if (fused && hdr[3] != 0) { try_fused = false; continue; }        // not in BAM order / segments too long
         ctx->last_path = fused ? 1 : 2;
+        ctx->idx_flags = fused ? flags : nullptr;
+        ctx->idx_cells = fused ? cells : nullptr;
+        ctx->idx_origin = origin;
+        ctx->idx_ncells = ncells;
         ctx->n_runs = do_runs ? (int64_t)hdr[0] : 0;
         ctx->max_depth = (int32_t)hdr[2];
         if (do_runs && (long long)hdr[0] > cap) {                          // output did not fit: grow and rerun
@@ -1210,6 +1253,60 @@ int gl_depth_classes(gl_ctx* ctx, int32_t mincov, int32_t maxmean, int32_t* run_
     GL_CHECK(run_reduce(ctx, 1 << 30, mincov, maxmean, 0, false, true, nullptr, false));
     if (n_runs) *n_runs = ctx->n_runs;
     return gl_depth_get_runs(ctx, run_start, run_end, run_class, cap);
+}
+
+int gl_depth_interval_sums(gl_ctx* ctx, const int32_t* a, const int32_t* b, int64_t n, int64_t* sums) {
+    GL_CHECK(gl_use(ctx));
+    if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_interval_sums: no region open");
+    if (n < 0 || (n > 0 && (!a || !b || !sums))) return gl_fail(ctx, GL_EINVAL, "gl_depth_interval_sums: bad argument");
+    if (n == 0) return GL_OK;
+    if (ctx->copies_pending) {
+        GL_CUDA(ctx, cudaEventRecord(ctx->ev_copy[0], ctx->copy_stream));
+        GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[0], 0));
+        ctx->copies_pending = false;
+    }
+    if ((int)ctx->batches.size() > kMaxBatches) return gl_fail(ctx, GL_ERANGE, "gl_depth_interval_sums: more than %d segment batches", kMaxBatches);
+    ScanParams p;
+    memset(&p, 0, sizeof p);
+    p.rs = (int)ctx->rs;
+    p.re = (int)ctx->re;
+    const bool use_index = ctx->depth_reduced && ctx->last_path == 1 && ctx->idx_cells != nullptr;
+    p.n_batches = (int)ctx->batches.size();
+    p.flags = ctx->idx_flags;
+    p.origin = ctx->idx_origin;
+    p.ncells = ctx->idx_ncells;
+    const size_t nb = ctx->batches.size();
+    for (size_t bi = 0; bi < nb; bi++) {
+        const gl_seg_batch& bt = ctx->batches[bi];
+        p.batch[bi].start = batch_start(ctx, bt);
+        p.batch[bi].end = batch_end(ctx, bt);
+        p.batch[bi].n = (int)std::min<int64_t>(bt.n, INT32_MAX - 1);
+        if (use_index) {                                           // same layout as run_reduce: hi | cnt | lo
+            const unsigned* hi_all = ctx->idx_cells;
+            const unsigned* cnt_all = hi_all + (size_t)ctx->idx_ncells * nb;
+            const unsigned* lo_all = cnt_all + (size_t)ctx->idx_ncells * nb;
+            p.batch[bi].cell_hi = hi_all + bi * (size_t)ctx->idx_ncells;
+            p.batch[bi].cell_cnt = cnt_all + bi * (size_t)ctx->idx_ncells;
+            p.batch[bi].cell_lo = lo_all + bi * (size_t)ctx->idx_ncells;
+        }
+    }
+    GL_CHECK(gl_buf_reserve(ctx, ctx->misc, (size_t)n * 16));
+    long long* d_out = static_cast<long long*>(ctx->misc.p);
+    int* d_a = reinterpret_cast<int*>(d_out + n);
+    int* d_b = d_a + n;
+    int rc = GL_OK;
+    do {
+        if (cudaMemcpyAsync(d_a, a, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_b, b, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_depth_interval_sums: H2D failed"); break; }
+        {
+            gl_prof_scope prof(ctx, "depth_interval_sum_kernel");
+            depth_interval_sum_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(p, d_a, d_b, n, use_index ? 1 : 0, d_out);
+        }
+        ctx->launches++;
+        if (cudaMemcpyAsync(sums, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_depth_interval_sums: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    return rc;
 }
 
 int gl_depth_perbase(gl_ctx* ctx, int32_t* depth_out) {

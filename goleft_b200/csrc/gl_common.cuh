@@ -45,6 +45,8 @@ struct gl_ctx {
     bool copies_pending = false;            // H2D into the store still in flight on copy_stream
     bool g_valid = false;                   // the HBM difference array holds every batch (general path)
     int last_path = 0;                      // 1 = fused sorted path, 2 = general scatter path
+    // index tables of the last fused reduce (valid until the next reduce): used by gl_depth_interval_sums
+    const int* idx_flags = nullptr; const unsigned* idx_cells = nullptr; int idx_origin = 0, idx_ncells = 0, idx_maxlen = -1;
     int force_path = 0;                     // 0 = auto, 2 = always general (tests / comparison arm)
     gl_buf diff;          // int32[len+1 (+pad)] + tile sums (general path only)
     void* win_sum_p = nullptr;   // u64[n_windows], inside `scratch`

@@ -139,6 +139,10 @@ int  gl_depth_get_runs(gl_ctx* ctx, int32_t* run_start, int32_t* run_end, uint8_
 int  gl_depth_windows(gl_ctx* ctx, int32_t W, int64_t* sum_out, int32_t* min_out, int64_t n_windows);
 int  gl_depth_classes(gl_ctx* ctx, int32_t mincov, int32_t maxmean, int32_t* run_start, int32_t* run_end,
                       uint8_t* run_class, int64_t cap, int64_t* n_runs);
+/* Sum of per-base depth over n arbitrary intervals [a[i], b[i]) of the open region (clipped to it), computed straight
+ * from the segments (sum of overlaps); uses the cell index of the last gl_depth_reduce when that took the fused path.
+ * This is what BED mode needs for the clipped first/last window of every region (depth/depth.go:293-305,329-341). */
+int  gl_depth_interval_sums(gl_ctx* ctx, const int32_t* a, const int32_t* b, int64_t n, int64_t* sums);
 /* Per-base depth of the region (debug / parity): depth_out has region_end-region_start entries. */
 int  gl_depth_perbase(gl_ctx* ctx, int32_t* depth_out);
 

@@ -119,6 +119,43 @@ def test_depth_bed_mode(tmp_path, W):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("W", [7, 100, 250])
+def test_depth_bed_mode_many_regions(tmp_path, W):
+    """Batched BED mode (one pass per contig + gl_depth_interval_sums for the clipped edge windows) against the
+    per-line walk of the oracle: random, overlapping, unsorted, window-aligned and out-of-contig regions."""
+    bam, ref, refs, _, _ = _make_bam(tmp_path, seed=3)
+    rng = np.random.default_rng(W)
+    regions = []
+    for _ in range(300):
+        name, L = refs[int(rng.integers(0, 3))]
+        a = int(rng.integers(0, L))
+        ln = int(rng.choice([1, 2, W - 1, W, W + 1, 3 * W, int(rng.integers(1, 2000))]))
+        if rng.random() < 0.3:
+            a = a // W * W                                                        # aligned start
+        regions.append((name, a, max(a + 1, a + ln)))
+    regions += [("chr22", 19990, 20500), ("chrUn_absent", 10, 700), ("chr22", 0, 20001), ("chrM", 3 * W, 5 * W)]
+    bed = tmp_path / "many.bed"
+    bed.write_text("".join("%s\t%d\t%d\n" % r for r in regions))
+    prefix = str(tmp_path / "m")
+    run("depth", "--bed", str(bed), "-Q", "1", "--windowsize", str(W), "--prefix", prefix, "--reference", ref, bam)
+    seg = capi.bam_segments(bam, 1, 2)
+    tid_of = {n: i for i, (n, _) in enumerate(refs)}
+    exp_hd, exp_ca = b"", b""
+    for line in regions:
+        name, rs, re = orc.chrom_start_end("%s\t%d\t%d" % line)      # HLA names: the lazy regex mis-splits them (depth.go:34-43,143)
+        if re <= rs:
+            continue
+        if name in tid_of:
+            s, e = seg["segments"][tid_of[name]]
+        else:
+            s = e = np.zeros(0, np.int32)
+        h, c = orc.walk_chunk(name, rs, re, W, 4, 0, orc.pileup_brute(s, e, rs, re))
+        exp_hd += h; exp_ca += c
+    assert open(prefix + ".depth.bed", "rb").read() == exp_hd
+    assert open(prefix + ".callable.bed", "rb").read() == exp_ca
+
+
+@pytest.mark.gpu
 def test_depth_empty_bam(tmp_path):
     """check_empty (functional-test.sh:102-109)"""
     refs = [("chrM", 16571), ("chr22", 20001)]

@@ -322,3 +322,35 @@ def test_chr1_sized_contig(ctx):
     es, _ = orc.window_sums(exp, 0, L, W)
     ea, ec = orc.class_runs(exp, 0, L, 4, 0, step)
     assert np.array_equal(ws, es) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
+
+
+def test_interval_sums(ctx):
+    """gl_depth_interval_sums = sum of per-base depth over arbitrary [a,b): with the fused path's cell index,
+    after the general path (no index: every segment visited), before any reduce, with several batches, and clipped
+    to the open region."""
+    L = 600_000
+    s, e = synth.segments(synth.reads(L, contig_index=5))
+    rs, re = 1234, L - 777
+    depth = orc.pileup_diff(s, e, rs, re).astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(depth)])
+    rng = np.random.default_rng(9)
+    a = rng.integers(rs - 500, re + 500, 5000).astype(np.int32)
+    b = (a + rng.choice([0, 1, 2, 99, 100, 250, 4096, 4097, 70000], 5000)).astype(np.int32)
+    a[:3] = [rs, rs - 50, re - 1]
+    b[:3] = [re, rs + 1, re + 100]
+    ac, bc = np.clip(a, rs, re), np.clip(b, rs, re)
+    exp = np.where(bc > ac, cs[np.maximum(bc, ac) - rs] - cs[ac - rs], 0)
+    half = s.size // 2
+    for path in (0, 2):
+        ctx.depth_set_path(path)
+        ctx.depth_begin(rs, re)
+        ctx.depth_add_segments(s[:half], e[:half])
+        ctx.depth_add_segments(s[half:], e[half:])
+        if path == 2:
+            assert np.array_equal(ctx.depth_interval_sums(a[:200], b[:200]), exp[:200])      # before any reduce
+        ctx.depth_reduce(500, 4, 0, 0)
+        assert ctx.depth_last_path() == (1 if path == 0 else 2)
+        n = a.size if path == 0 else 300                     # no index -> brute force over all segments: keep it small
+        assert np.array_equal(ctx.depth_interval_sums(a[:n], b[:n]), exp[:n])
+        assert ctx.depth_interval_sums(a[:0], b[:0]).size == 0
+    ctx.depth_set_path(0)
