@@ -10,7 +10,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
 #include <map>
 #include <regex>
@@ -146,7 +149,6 @@ static int cmd_depth(int argc, char** argv) {
     const std::string bam = ap.positional[0];
     const int W = atoi(w.c_str()), maxmean = atoi(m.c_str()), Q = atoi(q.c_str()), mcov = atoi(mincov.c_str());
     if (W <= 0) ap.fail("windowsize must be > 0");
-    if (stats) fprintf(stderr, "goleft depth: --stats (GC/CpG/masked columns) is not built in this engine; columns omitted\n");
     int threads = atoi(procs.c_str());
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
 
@@ -205,18 +207,97 @@ static int cmd_depth(int argc, char** argv) {
     };
     rstart.resize(1 << 16); rclass.resize(1 << 16);
 
+    // ---- row text.  Without --stats a chunk is formatted at once; with it (depth.go:191-200,246-252) the chunks of a
+    // contig are parked, their window rows listed, one gl_fasta_stats launch counts GC/CpG/masked for all of them from
+    // the contig's raw FASTA bytes, and only then is the text made.
+    std::vector<glhts::RefInfo> fa_index;
+    const uint8_t* fa_map = nullptr;
+    size_t fa_len = 0;
+    if (stats) {
+        if (reference.empty()) fatal(1, "goleft depth: --stats needs --reference");
+        std::string e2 = glhts::fai_read(reference + ".fai", fa_index);
+        if (!e2.empty()) fatal(1, "%s", e2.c_str());
+        int fd = open(reference.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd < 0 || fstat(fd, &st) != 0) fatal(1, "cannot open %s", reference.c_str());
+        fa_len = (size_t)st.st_size;
+        if (fa_len) {
+            void* m = mmap(nullptr, fa_len, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) fatal(1, "cannot mmap %s", reference.c_str());
+            fa_map = static_cast<const uint8_t*>(m);
+        }
+        close(fd);
+    }
+    struct Pending {
+        std::string chrom; long long rs, re;
+        std::vector<int64_t> sums; std::vector<int32_t> rs_; std::vector<uint8_t> rc_;
+        std::string *hd, *ca;                               // null: straight to the output files
+        int64_t row0, nrows;
+    };
+    std::vector<Pending> pending;
+    std::vector<int64_t> row_s, row_e;
+    auto put_text = [&](std::string* hd_to, std::string* ca_to, char* hd, int64_t hl, char* ca, int64_t cl) {
+        if (hd_to) { hd_to->assign(hd, (size_t)hl); ca_to->assign(ca, (size_t)cl); }
+        else { fwrite(hd, 1, (size_t)hl, fhd); fwrite(ca, 1, (size_t)cl, fca); }
+        gl_free_text(hd); gl_free_text(ca);
+    };
+    auto emit = [&](const std::string& c, long long rs, long long re, const int64_t* ws, int64_t nw, const int32_t* rs_, const uint8_t* rc_,
+                    int64_t nr, std::string* hd_to, std::string* ca_to) {
+        if (!stats) {
+            char *hd = nullptr, *ca = nullptr;
+            int64_t hl = 0, cl = 0;
+            if (gl_depth_format_chunk(c.c_str(), rs, re, W, ws, nw, rs_, rc_, nr, &hd, &hl, &ca, &cl) != GL_OK) fatal(1, "gl_depth_format_chunk failed");
+            put_text(hd_to, ca_to, hd, hl, ca, cl);
+            return;
+        }
+        Pending pc{c, rs, re, std::vector<int64_t>(ws, ws + nw), std::vector<int32_t>(rs_, rs_ + nr), std::vector<uint8_t>(rc_, rc_ + nr), hd_to, ca_to,
+                   (int64_t)row_s.size(), 0};
+        int64_t n = 0;
+        gl_depth_chunk_rows(rs, re, W, rs_, rc_, nr, nullptr, nullptr, 0, &n);
+        row_s.resize(row_s.size() + (size_t)n); row_e.resize(row_s.size());
+        if (gl_depth_chunk_rows(rs, re, W, rs_, rc_, nr, row_s.data() + pc.row0, row_e.data() + pc.row0, n, &n) != GL_OK) fatal(1, "gl_depth_chunk_rows failed");
+        pc.nrows = n;
+        pending.push_back(std::move(pc));
+    };
+    auto flush_stats = [&]() {                              // all parked chunks belong to one contig
+        if (pending.empty()) return;
+        const std::string& c = pending[0].chrom;
+        std::vector<double> st3(row_s.size() * 3, 0.0);
+        const glhts::RefInfo* ri = nullptr;
+        for (const glhts::RefInfo& r : fa_index) if (r.name == c) { ri = &r; break; }
+        if (!ri) fprintf(stderr, "GC: unknown sequence %s\n", c.c_str());                 // faidx error text; zeros are printed (depth.go:195-199)
+        else if (!row_s.empty()) {
+            const int64_t rec_bytes = std::min<int64_t>((int64_t)fa_len - ri->offset, glhts::fasta_position(*ri, ri->length) + 1);
+            if (ri->offset < 0 || rec_bytes < 0) fatal(1, "bad .fai entry for %s", c.c_str());
+            glck(ctx, gl_fasta_load(ctx, fa_map + ri->offset, rec_bytes), "gl_fasta_load");
+            std::vector<int64_t> ba(row_s.size()), bb(row_s.size());
+            for (size_t i = 0; i < row_s.size(); i++) {
+                // faidx panics on coordinates past the contig; rows are clipped to it here instead
+                const int64_t s = std::min<int64_t>(std::max<int64_t>(row_s[i], 0), ri->length), e = std::min<int64_t>(std::max<int64_t>(row_e[i], s), ri->length);
+                const int64_t ps = glhts::fasta_position(*ri, s), pe = glhts::fasta_position(*ri, e);
+                ba[i] = std::min(ps, rec_bytes);
+                bb[i] = std::max(ba[i], std::min<int64_t>(pe + ((ri->offset + pe < (int64_t)fa_len) ? 1 : 0), rec_bytes));
+            }
+            glck(ctx, gl_fasta_stats(ctx, ba.data(), bb.data(), (int64_t)ba.size(), nullptr, st3.data()), "gl_fasta_stats");
+        }
+        for (const Pending& pc : pending) {
+            char *hd = nullptr, *ca = nullptr;
+            int64_t hl = 0, cl = 0;
+            if (gl_depth_format_chunk_stats(pc.chrom.c_str(), pc.rs, pc.re, W, pc.sums.data(), (int64_t)pc.sums.size(), pc.rs_.data(), pc.rc_.data(),
+                                            (int64_t)pc.rs_.size(), st3.data() + pc.row0 * 3, pc.nrows, &hd, &hl, &ca, &cl) != GL_OK)
+                fatal(1, "gl_depth_format_chunk_stats failed");
+            put_text(pc.hd, pc.ca, hd, hl, ca, cl);
+        }
+        pending.clear(); row_s.clear(); row_e.clear();
+    };
+
     if (!bed.empty()) {
         // One pass per contig instead of one per BED line: window sums + class runs of the span the contig's regions
         // cover (run_break 0), the clipped first/last window of every region from gl_depth_interval_sums, then the
         // reference's rows region by region in BED order (depth.go:293-358 sees each line as its own chunk).
         std::vector<std::string> out_hd(regions.size()), out_ca(regions.size());
         auto format_one = [&](size_t k, const int64_t* ws, int64_t nw, const int32_t* rs_, const uint8_t* rc_, int64_t nr) {
-            char *hd = nullptr, *ca = nullptr;
-            int64_t hl = 0, cl = 0;
-            if (gl_depth_format_chunk(regions[k].chrom.c_str(), regions[k].s, regions[k].e, W, ws, nw, rs_, rc_, nr, &hd, &hl, &ca, &cl) != GL_OK)
-                fatal(1, "gl_depth_format_chunk failed");
-            out_hd[k].assign(hd, (size_t)hl); out_ca[k].assign(ca, (size_t)cl);
-            gl_free_text(hd); gl_free_text(ca);
+            emit(regions[k].chrom, regions[k].s, regions[k].e, ws, nw, rs_, rc_, nr, &out_hd[k], &out_ca[k]);
         };
         std::map<std::string, std::vector<size_t>> by_chrom;
         std::vector<std::string> chrom_order;
@@ -246,6 +327,7 @@ static int cmd_depth(int argc, char** argv) {
                     run_region(c, regions[k].s, regions[k].e, 0, nw, nr);
                     format_one(k, sums.data(), nw, rstart.data(), rclass.data(), nr);
                 }
+                flush_stats();
                 continue;
             }
             ia.clear(); ib.clear();
@@ -272,6 +354,7 @@ static int cmd_depth(int argc, char** argv) {
                 rrc.insert(rrc.end(), rclass.data() + (first - rb), rclass.data() + (last - rb));
                 format_one(k, rsum.data(), (int64_t)rsum.size(), rrs.data(), rrc.data(), (int64_t)rrs.size());
             }
+            flush_stats();
         }
         for (size_t k = 0; k < regions.size(); k++) {
             fwrite(out_hd[k].data(), 1, out_hd[k].size(), fhd);
@@ -291,18 +374,14 @@ static int cmd_depth(int argc, char** argv) {
                 const long long cs = regions[k].s, ce = regions[k].e;
                 const int32_t* lo = std::lower_bound(rstart.data(), rstart.data() + nr, (int32_t)cs);
                 const int32_t* hi = std::lower_bound(rstart.data(), rstart.data() + nr, (int32_t)ce);
-                char *hd = nullptr, *ca = nullptr;
-                int64_t hl = 0, cl = 0;
-                if (gl_depth_format_chunk(regions[k].chrom.c_str(), cs, ce, W, sums.data() + cs / W, (ce - 1) / W - cs / W + 1, lo,
-                                          rclass.data() + (lo - rstart.data()), hi - lo, &hd, &hl, &ca, &cl) != GL_OK)
-                    fatal(1, "gl_depth_format_chunk failed");
-                fwrite(hd, 1, (size_t)hl, fhd); fwrite(ca, 1, (size_t)cl, fca);
-                gl_free_text(hd); gl_free_text(ca);
+                emit(regions[k].chrom, cs, ce, sums.data() + cs / W, (ce - 1) / W - cs / W + 1, lo, rclass.data() + (lo - rstart.data()), hi - lo, nullptr, nullptr);
             }
+            flush_stats();
             i = j;
         }
     }
     fclose(fca); fclose(fhd);
+    if (fa_map) munmap(const_cast<uint8_t*>(fa_map), fa_len);
     gl_ctx_destroy(ctx);
     return 0;
 }

@@ -85,6 +85,9 @@ _proto("gl_depth_windows", C.c_int, _vp, C.c_int32, _vp, _vp, C.c_int64)
 _proto("gl_depth_classes", C.c_int, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_depth_perbase", C.c_int, _vp, _vp)
 _proto("gl_depth_interval_sums", C.c_int, _vp, _vp, _vp, C.c_int64, _vp)
+_proto("gl_fasta_load", C.c_int, _vp, _vp, C.c_int64)
+_proto("gl_fasta_stats", C.c_int, _vp, _vp, _vp, C.c_int64, _vp, _vp)
+_proto("gl_depth_chunk_rows", C.c_int, C.c_int64, C.c_int64, C.c_int32, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_depth_region", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_indexcov_sizes", C.c_int, _vp, _vp, _vp, C.c_int32, _vp, _vp)
@@ -420,6 +423,18 @@ class Ctx:
         out = np.empty(a.size, np.int64)
         self._ck(lib.gl_depth_interval_sums(self.h, _ptr(a), _ptr(b), a.size, _ptr(out)))
         return out
+
+    def fasta_load(self, record_bytes):
+        a = np.frombuffer(record_bytes, np.uint8) if not isinstance(record_bytes, np.ndarray) else _as(record_bytes, np.uint8)
+        self._ck(lib.gl_fasta_load(self.h, _ptr(a), a.size))
+
+    def fasta_stats(self, byte_start, byte_end):
+        """-> (counts[n,4] = G+C, lower, ACGT, CpG ; stats[n,3] = GC, CpG, Masked)"""
+        a, b = _as(byte_start, np.int64), _as(byte_end, np.int64)
+        counts = np.zeros((a.size, 4), np.int64)
+        stats = np.zeros((a.size, 3), np.float64)
+        self._ck(lib.gl_fasta_stats(self.h, _ptr(a), _ptr(b), a.size, _ptr(counts), _ptr(stats)))
+        return counts, stats
 
     def depth_perbase(self, length: int) -> np.ndarray:
         out = np.empty(length, np.int32)

@@ -61,6 +61,8 @@ struct gl_ctx {
     size_t pinned_bytes = 0;
     gl_buf flush;         // L2 flush scratch
     gl_buf misc;          // small outputs of other subsystems
+    gl_buf fasta;         // raw FASTA bytes of one record (gl_fasta_load), newlines included
+    int64_t fasta_n = 0;
 
     // per-kernel CUDA-event profiling (gl_profile_*): (name, start, stop) per launch while enabled
     bool prof_on = false;

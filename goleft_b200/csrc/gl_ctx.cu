@@ -109,7 +109,7 @@ int gl_ctx_destroy(gl_ctx* ctx) {
     buf_free(ctx->run_start); buf_free(ctx->run_class); buf_free(ctx->scratch);
     buf_free(ctx->run_tmp_start); buf_free(ctx->run_tmp_class);
     buf_free(ctx->store_s); buf_free(ctx->store_e); buf_free(ctx->packed);
-    buf_free(ctx->seg[0]); buf_free(ctx->seg[1]); buf_free(ctx->flush); buf_free(ctx->misc);
+    buf_free(ctx->seg[0]); buf_free(ctx->seg[1]); buf_free(ctx->flush); buf_free(ctx->misc); buf_free(ctx->fasta);
     for (int i = 0; i < 2; i++) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);

@@ -543,6 +543,8 @@ std::string fai_read(const std::string& path, std::vector<RefInfo>& out) {
         RefInfo ri;
         ri.name.assign(line, (size_t)(t1 - line));
         ri.length = atoll(t1 + 1);
+        long long off = 0, lb = 0, lw = 0;
+        if (sscanf(t1 + 1, "%*d\t%lld\t%lld\t%lld", &off, &lb, &lw) == 3) { ri.offset = off; ri.line_bases = lb; ri.line_width = lw; }
         out.push_back(ri);
     }
     fclose(f);

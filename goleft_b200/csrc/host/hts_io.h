@@ -12,7 +12,11 @@ namespace glhts {
 struct RefInfo {
     std::string name;
     int64_t length = 0;
+    int64_t offset = 0, line_bases = 0, line_width = 0;   // .fai columns 3-5 (0 when the source has none, e.g. a BAM header)
 };
+
+// byte offset of 0-based base p of a FASTA record, relative to the record's first base (faidx `position`)
+inline int64_t fasta_position(const RefInfo& r, int64_t p) { return r.line_bases > 0 ? p / r.line_bases * r.line_width + p % r.line_bases : p; }
 
 // ---------------------------------------------------------------------------------------------- BGZF
 // Inflates a whole BGZF stream with `threads` workers, in batches of blocks, handing every batch's

@@ -169,6 +169,26 @@ int  gl_depth_format_chunk(const char* chrom, int64_t rs, int64_t re, int32_t W,
                            char** depth_bed, int64_t* depth_len, char** callable_bed, int64_t* callable_len);
 void gl_free_text(char* p);
 
+/* ---- `goleft depth --stats` (depth/depth.go:191-200 getStats, :246-252): GC / CpG / masked fraction per window row.
+ * The arithmetic is github.com/brentp/faidx Faidx.Stats (go.mod:11, not vendored; parity unpinned), which scans the raw
+ * bytes of the FASTA record, newlines included.
+ * gl_depth_chunk_rows lists the (s,e) of the window rows gl_depth_format_chunk writes for a chunk, in order (including
+ *   the misaligned / re-emitted rows of depth.go:329-358); returns GL_ERANGE with *n_rows set when cap is too small.
+ * gl_fasta_load uploads the bytes of one FASTA record (from the .fai offset to the end of its last line, plus the one
+ *   byte after it when the file has one), gl_fasta_stats counts, for row r, the slice [byte_start[r], byte_end[r]) of it
+ *   the way Faidx.Stats does (every byte but the slice's last is classified, the next byte decides CpG):
+ *   counts4[r] = {G+C, lower-case, A+C+G+T, CpG} and/or stats3[r] = {GC, CpG, Masked} as float64 (0 when no ACGT).
+ *   byte_start = position(s), byte_end = min(position(e)+1, file length) relative to the loaded record.
+ * gl_depth_format_chunk_stats = gl_depth_format_chunk with the three "%.3g" columns appended to every window row. */
+int  gl_depth_chunk_rows(int64_t rs, int64_t re, int32_t W, const int32_t* run_start, const uint8_t* run_class, int64_t n_runs,
+                         int64_t* row_s, int64_t* row_e, int64_t cap, int64_t* n_rows);
+int  gl_fasta_load(gl_ctx* ctx, const uint8_t* bytes, int64_t n);
+int  gl_fasta_stats(gl_ctx* ctx, const int64_t* byte_start, const int64_t* byte_end, int64_t n_rows, int64_t* counts4, double* stats3);
+int  gl_depth_format_chunk_stats(const char* chrom, int64_t rs, int64_t re, int32_t W, const int64_t* win_sum, int64_t n_windows,
+                                 const int32_t* run_start, const uint8_t* run_class, int64_t n_runs,
+                                 const double* stats3, int64_t n_stat_rows,
+                                 char** depth_bed, int64_t* depth_len, char** callable_bed, int64_t* callable_len);
+
 /* ---------------------------------------------------------------- feeder (host-only, no GPU needed)
  * BGZF (multi-threaded inflate) + BAM decode + the `samtools depth` record filter: records with
  * (flag & 0x704) == 0 and MAPQ >= min_mapq contribute their M/=/X blocks (D and N advance without

@@ -47,6 +47,23 @@ _proto("orc_walk_text", C.c_int, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64
        C.POINTER(_vp), _i64p)
 _proto("orc_window_sums", C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int64)
 _proto("orc_class_runs", C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int64)
+_proto("orc_faidx_stats", C.c_int, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp)
+_proto("orc_stats_text", C.c_int, _vp, C.c_char_p, C.c_int64)
+
+
+def faidx_stats(fasta: bytes, rec, start: int, end: int):
+    """Faidx.Stats restatement: rec = (offset, length, line_bases, line_width) from the .fai; -> (GC, CpG, Masked) or None
+    where faidx panics."""
+    buf = np.frombuffer(fasta, np.uint8)
+    out = np.zeros(3, np.float64)
+    rc = lib.orc_faidx_stats(_ptr(buf), buf.size, rec[0], rec[1], rec[2], rec[3], start, end, _ptr(out))
+    return None if rc < 0 else out
+
+
+def stats_text(st3) -> bytes:
+    b = C.create_string_buffer(128)
+    n = lib.orc_stats_text(_ptr(np.ascontiguousarray(st3, np.float64)), b, 128)
+    return b.raw[:n]
 
 
 def pileup_brute(start, end, rs: int, re: int) -> np.ndarray:

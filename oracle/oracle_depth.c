@@ -351,3 +351,54 @@ int64_t orc_class_runs(const int32_t* depth, int64_t rs, int64_t re, int64_t min
     }
     return k;
 }
+
+/* ------------------------------------------------------------------ --stats (depth/depth.go:191-200)
+ * getStats -> github.com/brentp/faidx Faidx.Stats (go.mod:11 v0.0.0-20200301150453-c39eb85760d8, NOT under the
+ * reference tree; restated from that package's published source — PARITY UNPINNED, nothing in the reference's
+ * tests asserts a --stats value).  `position` maps a 0-based base to a file offset through the .fai columns;
+ * Stats walks the raw bytes mmap[position(start) : position(end) (+1 if inside the file)), skipping the slice's last
+ * byte, so newlines are stepped over and a C whose next BYTE is G/g counts as CpG.
+ * out3 = {GC, CpG, Masked} (the order depth.go:199 prints).  Returns -1 where faidx panics (coordinate > length). */
+static int64_t orc_fa_position(int64_t rec_start, int64_t lbases, int64_t lbytes, int64_t p) {
+    return rec_start + p / lbases * lbytes + p % lbases;
+}
+
+int orc_faidx_stats(const uint8_t* map, int64_t map_len, int64_t rec_start, int64_t rec_len, int64_t lbases, int64_t lbytes,
+                    int64_t start, int64_t end, double* out3) {
+    out3[0] = out3[1] = out3[2] = 0.0;
+    if (start < 0 || end < 0 || start > rec_len || end > rec_len || lbases <= 0) return -1;
+    int64_t pstart = orc_fa_position(rec_start, lbases, lbytes, start);
+    int64_t pend = orc_fa_position(rec_start, lbases, lbytes, end);
+    int64_t oend = pend;
+    if (oend < map_len) oend++;
+    if (pstart > oend || oend > map_len) return -1;              /* Go slice bounds panic */
+    int64_t gc_up = 0, gc_lo = 0, at_up = 0, at_lo = 0, cpg = 0;
+    int64_t n = oend - pstart;
+    const uint8_t* buf = map + pstart;
+    for (int64_t i = 0; i < n; i++) {
+        if (i == n - 1) break;                                   /* "we added 1 to do the GC content" */
+        uint8_t v = buf[i];
+        if (v == 'G' || v == 'C') {
+            if (v == 'C' && (buf[i + 1] == 'G' || buf[i + 1] == 'g')) cpg++;
+            gc_up++;
+        } else if (v == 'g' || v == 'c') {
+            if (v == 'c' && (buf[i + 1] == 'G' || buf[i + 1] == 'g')) cpg++;
+            gc_lo++;
+        } else if (v == 'A' || v == 'T') {
+            at_up++;
+        } else if (v == 'a' || v == 't') {
+            at_lo++;
+        }
+    }
+    double tot = (double)(gc_up + gc_lo + at_up + at_lo);
+    if (tot == 0.0) return 0;
+    out3[0] = (double)(gc_lo + gc_up) / tot;
+    out3[1] = (double)(2 * cpg) / tot;
+    out3[2] = (double)(at_lo + gc_lo) / tot;
+    return 0;
+}
+
+/* the "%s" tail of a window row (depth.go:199) */
+int orc_stats_text(const double* st3, char* out, int64_t cap) {
+    return snprintf(out, (size_t)cap, "\t%.3g\t%.3g\t%.3g", st3[0], st3[1], st3[2]);
+}

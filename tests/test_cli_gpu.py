@@ -155,6 +155,55 @@ def test_depth_bed_mode_many_regions(tmp_path, W):
     assert open(prefix + ".callable.bed", "rb").read() == exp_ca
 
 
+def _with_stats(hd: bytes, fa: bytes, recs) -> bytes:
+    """append getStats(chrom, s, e) to every window row (depth.go:299,334,355 call it with the printed s and e)"""
+    out = []
+    for ln in hd.decode().splitlines():
+        c, s, e, _ = ln.split("\t")
+        st = orc.faidx_stats(fa, recs[c], int(s), int(e)) if c in recs else np.zeros(3)
+        out.append(ln.encode() + orc.stats_text(st) + b"\n")
+    return b"".join(out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W", [100, 333])
+def test_depth_stats_columns(tmp_path, W):
+    """--stats: GC / CpG / masked columns in fai mode and BED mode (every functional test of the reference passes
+    --stats, depth/functional-test.sh; values follow the Faidx.Stats restatement — parity unpinned)."""
+    from fautil import make_fasta
+    bam, ref, refs, _, _ = _make_bam(tmp_path, seed=5)
+    fa, fai, recs = make_fasta(refs, seed=W, line=60)
+    open(ref, "wb").write(fa)
+    open(ref + ".fai", "w").write(fai)
+    seg = capi.bam_segments(bam, 1, 2)
+    prefix = str(tmp_path / "st")
+    run("depth", "--stats", "-Q", "1", "--ordered", "--windowsize", str(W), "--prefix", prefix, "--reference", ref, bam)
+    exp_hd, exp_ca = b"", b""
+    for tid, (name, L) in enumerate(refs):
+        s, e = seg["segments"][tid]
+        d = orc.pileup_brute(s, e, 0, L)
+        for cs, ce in orc.gen_chunks(L, W):
+            h, c = orc.walk_chunk(name, cs, ce, W, 4, 0, d[cs:ce])
+            exp_hd += _with_stats(h, fa, recs); exp_ca += c
+    assert open(prefix + ".depth.bed", "rb").read() == exp_hd
+    assert open(prefix + ".callable.bed", "rb").read() == exp_ca
+    assert len({ln.split(b"\t")[4] for ln in exp_hd.splitlines()}) > 10          # the columns are not constant
+    # BED mode, incl. misaligned regions and a contig the FASTA index does not know (zeros, like faidx's error path)
+    regions = [("chr22", 14250, 15500), ("chrM", 101, 1000), ("chr22", 1575, 15800), ("chrM", 16000, 16571), ("chrQ", 5, 700), ("chrM", 24, 29)]
+    bed = tmp_path / "st.bed"
+    bed.write_text("".join("%s\t%d\t%d\n" % r for r in regions))
+    prefix = str(tmp_path / "stb")
+    run("depth", "-s", "--bed", str(bed), "-Q", "1", "--windowsize", str(W), "--prefix", prefix, "--reference", ref, bam)
+    tid_of = {n: i for i, (n, _) in enumerate(refs)}
+    exp_hd, exp_ca = b"", b""
+    for name, rs, re in regions:
+        s, e = seg["segments"][tid_of[name]] if name in tid_of else (np.zeros(0, np.int32),) * 2
+        h, c = orc.walk_chunk(name, rs, re, W, 4, 0, orc.pileup_brute(s, e, rs, re))
+        exp_hd += _with_stats(h, fa, recs); exp_ca += c
+    assert open(prefix + ".depth.bed", "rb").read() == exp_hd
+    assert open(prefix + ".callable.bed", "rb").read() == exp_ca
+
+
 @pytest.mark.gpu
 def test_depth_empty_bam(tmp_path):
     """check_empty (functional-test.sh:102-109)"""

@@ -354,3 +354,33 @@ def test_interval_sums(ctx):
         assert np.array_equal(ctx.depth_interval_sums(a[:n], b[:n]), exp[:n])
         assert ctx.depth_interval_sums(a[:0], b[:0]).size == 0
     ctx.depth_set_path(0)
+
+
+@pytest.mark.parametrize("line,crlf", [(60, False), (7, False), (50, True)])
+def test_fasta_stats_kernel(ctx, line, crlf):
+    """gl_fasta_stats (--stats columns, depth.go:191-200) against the Faidx.Stats restatement: windows of every size
+    incl. empty, single-base, line-straddling, > 64 KB (several pieces) and the contig's very end, for the last record
+    of the file (no byte after it) and an inner one."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fautil import make_fasta, position
+    refs = [("a", 5000), ("big", 300_001), ("last", 1234)]
+    fa, _, recs = make_fasta(refs, seed=line, line=line, crlf=crlf)
+    if line == 7:
+        fa = fa.rstrip(b"\n")                                  # file ends with the last base itself
+    rng = np.random.default_rng(1)
+    for name, L in refs:
+        rec = recs[name]
+        off = rec[0]
+        nbytes = min(len(fa) - off, position(rec, L) + 1)
+        ctx.fasta_load(fa[off:off + nbytes])
+        s = rng.integers(0, L + 1, 400)
+        e = np.minimum(L, s + rng.choice([0, 1, 2, line - 1, line, line + 1, 500, 70_000, 200_000], 400))
+        s[:4] = [0, L - 1, L, 0]
+        e[:4] = [L, L, L, 1]
+        ba = np.array([position(rec, int(x)) for x in s], np.int64)
+        bb = np.array([min(position(rec, int(x)) + (1 if off + position(rec, int(x)) < len(fa) else 0), nbytes) for x in e], np.int64)
+        counts, stats = ctx.fasta_stats(ba, bb)
+        exp = np.array([orc.faidx_stats(fa, rec, int(a), int(b)) for a, b in zip(s, e)])
+        assert np.array_equal(stats, exp), name
+        assert (counts[:, 2] >= counts[:, 0]).all() and counts[0, 2] > 0

@@ -272,3 +272,29 @@ def test_pack_segments16_roundtrip():
         assert np.array_equal(orc.pileup_diff(st.astype(np.int32), en.astype(np.int32), lo, hi), orc.pileup_diff(s, e, lo, hi))
     assert a.size <= s.size // 256 + 8                       # nearly every block is full
     assert capi.pack_segments16(np.zeros(0, np.int32), np.zeros(0, np.int32))[0].size == 0
+
+
+def test_faidx_stats_restatement_hand_cases():
+    """Faidx.Stats as restated (un-vendored brentp/faidx, parity unpinned): hand-computed cases incl. its edge
+    behaviours — newline between C and G is not a CpG, the byte after the window decides the last CpG, the very last base
+    of a file with no trailing byte is dropped."""
+    fa = b">c\nACGT\nCGcg\nNNNN\nccgC\nG"
+    rec = (3, 17, 4, 5)                                       # offset, length, bases/line, bytes/line
+    st = orc.faidx_stats(fa, rec, 0, 4)                       # ACGT, next byte '\n': A,C(G follows ->cpg),G,T
+    assert np.allclose(st, [0.5, 2 * 1 / 4, 0.0])
+    st = orc.faidx_stats(fa, rec, 2, 6)                       # G T \n C G: T|C line break; CG inside line 2
+    assert np.allclose(st, [3 / 4, 2 * 1 / 4, 0.0])
+    st = orc.faidx_stats(fa, rec, 3, 5)                       # T \n C + lookahead G -> cpg
+    assert np.allclose(st, [1 / 2, 2 * 1 / 2, 0.0])
+    st = orc.faidx_stats(fa, rec, 4, 8)                       # CGcg: C-G, c-g; masked 2/4; last g followed by \n
+    assert np.allclose(st, [1.0, 2 * 2 / 4, 0.5])
+    st = orc.faidx_stats(fa, rec, 8, 12)                      # NNNN: nothing counted
+    assert np.allclose(st, [0, 0, 0])
+    st = orc.faidx_stats(fa, rec, 12, 16)                     # ccgC then '\n': C at line end, G on next line: not a CpG
+    assert np.allclose(st, [1.0, 2 * 1 / 4, 3 / 4])
+    st = orc.faidx_stats(fa, rec, 16, 17)                     # last base, no byte after it in the file: dropped
+    assert np.allclose(st, [0, 0, 0])
+    st = orc.faidx_stats(fa, rec, 12, 17)                     # ... but it still is the look-ahead of the byte before
+    assert np.allclose(st, [1.0, 2 * 1 / 4, 3 / 4])
+    assert orc.faidx_stats(fa, rec, 0, 18) is None            # faidx panics past the contig
+    assert orc.stats_text(np.array([0.5, 0.04166, 1.0])) == b"\t0.5\t0.0417\t1"
