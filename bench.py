@@ -11,8 +11,9 @@ At N>1 every rank processes its own chr20-sized contig (contigs shard across GPU
 data-path collective) -> weak scaling; value = N * bases / max-over-ranks device time.
 
 value  : inputs already resident in HBM (segments uploaded before the timed region).
-e2e    : the one-call C-ABI entry gl_depth_region with PINNED HOST buffers: H2D of the segments
-         and D2H of window sums + runs are inside the timed region, every step.
+e2e    : the one-call C-ABI entry gl_depth_region_packed8 (the feeder's short-read format, 2 B/segment) with
+         PINNED HOST buffers: H2D of the segments, unpack, all kernels and D2H of window sums + runs are inside the
+         timed region, every step.  e2e_packed16 / e2e_int32: the same through the 4 B and 8 B/segment entries.
 roofline / cpu_baseline: see DESIGN.md §Measurement.
 """
 import argparse
@@ -232,8 +233,19 @@ def main():
     h_l[:] = pl
     packed_bytes = int(pa.nbytes + po.nbytes + pl.nbytes)
 
-    def step_e2e():
+    def step_e2e_p16():
         return ctx.depth_region_packed16(0, L, h_a, h_o, h_l, W, MINCOV, MAXMEAN, STEP, out=(o_sum, o_rs, o_rc))
+
+    # the feeder's densest format for short reads (packed8: uint8 start delta + uint8 length = 2 B/segment)
+    qa, qd, ql = capi.pack_segments8(s, e)
+    h8_a, h8_d, h8_l = ctx.pinned_empty(qa.size, np.int32), ctx.pinned_empty(qd.size, np.uint8), ctx.pinned_empty(ql.size, np.uint8)
+    h8_a[:] = qa
+    h8_d[:] = qd
+    h8_l[:] = ql
+    packed8_bytes = int(qa.nbytes + qd.nbytes + ql.nbytes)
+
+    def step_e2e():
+        return ctx.depth_region_packed8(0, L, h8_a, h8_d, h8_l, W, MINCOV, MAXMEAN, STEP, out=(o_sum, o_rs, o_rc))
 
     # ---- warm-up (also sizes every grow-only buffer)
     for _ in range(args.warmup):
@@ -244,6 +256,7 @@ def main():
         step_e2e()
     for _ in range(args.warmup):
         step_e2e_int32()
+        step_e2e_p16()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -285,6 +298,16 @@ def main():
         dev = ctx.timer_stop_ms()
         ms_e2e_int32 += max(dev, (time.perf_counter() - te0) * 1e3)
     barrier()
+    ms_e2e_p16 = 0.0
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.sync()
+        te0 = time.perf_counter()
+        ctx.timer_start()
+        step_e2e_p16()
+        dev = ctx.timer_stop_ms()
+        ms_e2e_p16 += max(dev, (time.perf_counter() - te0) * 1e3)
+    barrier()
 
     # ---- per-kernel live timing for the roofline: CUDA events on the launching stream around every
     #      kernel of the same step (library-side, gl_profile_*), averaged over the repetitions
@@ -320,9 +343,9 @@ def main():
     os.environ.setdefault("NCCL_DEBUG", "WARN")
     if dist is not None:
         import torch
-        t = torch.tensor([ms, ms_e2e, ms_e2e_int32], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, ms_e2e, ms_e2e_int32, ms_e2e_p16], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_e2e_int32 = float(t[0]), float(t[1]), float(t[2])
+        ms, ms_e2e, ms_e2e_int32, ms_e2e_p16 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -352,9 +375,13 @@ def main():
                           "windows_per_gpu": n_win, "runs_per_gpu": n_runs, "contigs": world,
                           "path": {1: "fused (sorted segments -> smem difference tiles)", 2: "general (HBM difference array)"}.get(path, str(path)),
                           "l2": "L2 flushed (256 MiB memset) before every timed step; per-step CUDA-event times summed"},
-               "e2e": {"value": e2e_val, "unit": "Mbases/s", "h2d_bytes_per_step": packed_bytes,
+               "e2e": {"value": e2e_val, "unit": "Mbases/s", "h2d_bytes_per_step": packed8_bytes,
                        "d2h_bytes_per_step": 8 * n_win + 5 * n_runs, "ms_per_step": ms_e2e / args.steps,
-                       "call": "gl_depth_region_packed16 (the feeder's compact segment format, pinned host buffers)"},
+                       "call": "gl_depth_region_packed8 (the feeder's short-read segment format: uint8 start delta + uint8 length, pinned host buffers)"},
+               "e2e_packed16": {"value": world * L / (ms_e2e_p16 / args.steps * 1e-3) / 1e6, "unit": "Mbases/s",
+                                "h2d_bytes_per_step": packed_bytes, "d2h_bytes_per_step": 8 * n_win + 5 * n_runs,
+                                "ms_per_step": ms_e2e_p16 / args.steps,
+                                "call": "gl_depth_region_packed16 (uint16 offset + uint16 length per segment, any read length)"},
                "e2e_int32": {"value": world * L / (ms_e2e_int32 / args.steps * 1e-3) / 1e6, "unit": "Mbases/s",
                              "h2d_bytes_per_step": 8 * nseg, "d2h_bytes_per_step": 8 * n_win + 5 * n_runs,
                              "ms_per_step": ms_e2e_int32 / args.steps,

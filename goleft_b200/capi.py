@@ -123,6 +123,11 @@ _proto("gl_pack_segments16", C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_in
 _proto("gl_depth_add_segments_packed16", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_region_packed16", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_pack_segments8_bound", C.c_int64, C.c_int64)
+_proto("gl_pack_segments8", C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_depth_add_segments_packed8", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
+_proto("gl_depth_region_packed8", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
+       C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_crai_make_sizes", C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _i64p)
 _proto("gl_depth_format_chunk", C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int64, _vp, _vp,
        C.c_int64, C.POINTER(_vp), _i64p, C.POINTER(_vp), _i64p)
@@ -184,6 +189,34 @@ def pack_segments16(start: np.ndarray, end: np.ndarray):
         if rc != GL_ERANGE:
             raise GlError(rc, "gl_pack_segments16: bad arguments")
         cap = nb.value + 1
+
+
+def pack_segments8(start: np.ndarray, end: np.ndarray):
+    """Host-only: (anchors int32[nb], dstart uint8[nb*64], len uint8[nb*64]) — the feeder's densest format (short reads)."""
+    start, end = _as(start, np.int32), _as(end, np.int32)
+    nb = C.c_int64(0)
+    cap = max(1, start.size // 48 + 64)
+    while True:
+        a = np.empty(cap, np.int32)
+        d = np.empty(cap * 64, np.uint8)
+        ln = np.empty(cap * 64, np.uint8)
+        rc = lib.gl_pack_segments8(_ptr(start), _ptr(end), start.size, _ptr(a), _ptr(d), _ptr(ln), cap, C.byref(nb))
+        if rc == GL_OK:
+            k = nb.value
+            return a[:k], d[: k * 64], ln[: k * 64]
+        if rc != GL_ERANGE:
+            raise GlError(rc, "gl_pack_segments8: bad arguments")
+        cap = nb.value + 1
+
+
+def unpack_segments8(anchors, dstart, ln):
+    """numpy decode of packed8 (what depth_unpack8_kernel computes): -> (start, end) int64, empty slots dropped"""
+    nb = anchors.size
+    d = dstart.reshape(nb, 64).astype(np.int64)
+    s = anchors.astype(np.int64)[:, None] + np.cumsum(d, axis=1)
+    l = ln.reshape(nb, 64).astype(np.int64)
+    keep = l > 0
+    return s[keep], (s + l)[keep]
 
 
 def bam_segments(path: str, min_mapq: int = 1, threads: int = 4, only_tid: int = -1):
@@ -360,6 +393,22 @@ class Ctx:
 
     def depth_add_segments_packed16(self, anchors: np.ndarray, off: np.ndarray, ln: np.ndarray):
         self._ck(lib.gl_depth_add_segments_packed16(self.h, _ptr(anchors), _ptr(off), _ptr(ln), anchors.size))
+
+    def depth_add_segments_packed8(self, anchors: np.ndarray, dstart: np.ndarray, ln: np.ndarray):
+        self._ck(lib.gl_depth_add_segments_packed8(self.h, _ptr(anchors), _ptr(dstart), _ptr(ln), anchors.size))
+
+    def depth_region_packed8(self, rs: int, re: int, anchors, dstart, ln, W: int, mincov: int = 4, maxmean: int = 0,
+                             run_break: int = 0, out=None):
+        n_win = (re - 1) // W - rs // W + 1
+        if out is None:
+            out = (np.empty(n_win, np.int64), np.empty(max(1024, (re - rs) // 8), np.int32),
+                   np.empty(max(1024, (re - rs) // 8), np.uint8))
+        s, r0, rc_ = out
+        nw, nr = C.c_int64(0), C.c_int64(0)
+        self._ck(lib.gl_depth_region_packed8(self.h, rs, re, _ptr(anchors), _ptr(dstart), _ptr(ln), anchors.size, W, mincov,
+                                             maxmean, run_break, _ptr(s), s.size, C.byref(nw), _ptr(r0), _ptr(rc_),
+                                             min(r0.size, rc_.size), C.byref(nr)))
+        return s[: nw.value], r0[: nr.value], rc_[: nr.value]
 
     def depth_region_packed16(self, rs: int, re: int, anchors, off, ln, W: int, mincov: int = 4, maxmean: int = 0,
                               run_break: int = 0, out=None):

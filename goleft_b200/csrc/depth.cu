@@ -145,6 +145,44 @@ __global__ void __launch_bounds__(256) depth_unpack16_kernel(const int* __restri
     end[i] = s + (int)len[i];
 }
 
+// packed8 -> (start,end): 64-slot blocks, 8 consecutive slots per lane, so 8 lanes per block and 4 blocks per warp;
+// starts are the anchor plus the running sum of the uint8 deltas (thread-local sum + an 8-lane segmented scan).
+// A warp writes 1 KB of contiguous starts.
+__global__ void __launch_bounds__(256) depth_unpack8_kernel(const int* __restrict__ anchors, const uint2* __restrict__ dstart,
+                                                           const uint2* __restrict__ len, long long n_blocks,
+                                                           int* __restrict__ start, int* __restrict__ end) {
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;      // one thread per 8 slots
+    const long long b = t >> 3;
+    const int sub = threadIdx.x & 7;
+    const bool live = b < n_blocks;
+    uint2 d = make_uint2(0, 0), l = make_uint2(0, 0);
+    if (live) { d = dstart[t]; l = len[t]; }
+    int ds[8], ln[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        ds[k] = (d.x >> (8 * k)) & 0xff; ds[4 + k] = (d.y >> (8 * k)) & 0xff;
+        ln[k] = (l.x >> (8 * k)) & 0xff; ln[4 + k] = (l.y >> (8 * k)) & 0xff;
+    }
+#pragma unroll
+    for (int k = 1; k < 8; k++) ds[k] += ds[k - 1];
+    int inc = ds[7];
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o, 8);
+        if (sub >= o) inc += v;
+    }
+    if (!live) return;
+    const int base = anchors[b] + inc - ds[7];
+    int4* so = reinterpret_cast<int4*>(start + t * 8);
+    int4* eo = reinterpret_cast<int4*>(end + t * 8);
+    const int s0 = base + ds[0], s1 = base + ds[1], s2 = base + ds[2], s3 = base + ds[3];
+    const int s4 = base + ds[4], s5 = base + ds[5], s6 = base + ds[6], s7 = base + ds[7];
+    so[0] = make_int4(s0, s1, s2, s3);
+    so[1] = make_int4(s4, s5, s6, s7);
+    eo[0] = make_int4(s0 + ln[0], s1 + ln[1], s2 + ln[2], s3 + ln[3]);
+    eo[1] = make_int4(s4 + ln[4], s5 + ln[5], s6 + ln[6], s7 + ln[7]);
+}
+
 // K_super: super_sum[st] = sum of the 64 tile sums of super-tile st (one warp each).  Doing this in the
 // scatter itself would put every warp's red on the same handful of addresses — measured 7x slower.
 __global__ void __launch_bounds__(256) depth_super_sum_kernel(const int* __restrict__ tile_sum, int* __restrict__ super_sum,
@@ -1176,6 +1214,50 @@ int gl_depth_add_segments_packed16(gl_ctx* ctx, const int32_t* anchors, const ui
     return GL_OK;
 }
 
+int gl_depth_add_segments_packed8(gl_ctx* ctx, const int32_t* anchors, const uint8_t* dstart, const uint8_t* len, int64_t n_blocks) {
+    GL_CHECK(gl_use(ctx));
+    if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_add_segments_packed8: no region open (call gl_depth_begin)");
+    if (n_blocks < 0 || (n_blocks > 0 && (!anchors || !dstart || !len))) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments_packed8: bad argument");
+    if (n_blocks == 0) return GL_OK;
+    const int64_t n = n_blocks * 64;
+    const int64_t base = (ctx->store_n + 3) & ~int64_t(3);        // the unpack kernel stores int4
+    GL_CHECK(store_reserve(ctx, base + n));
+    const size_t b_anchor = (size_t)n_blocks * 4, b_u8 = (size_t)n;
+    GL_CHECK(gl_buf_reserve(ctx, ctx->packed, ((b_anchor + 255) & ~size_t(255)) + 2 * ((b_u8 + 255) & ~size_t(255))));
+    char* d_anchor = static_cast<char*>(ctx->packed.p);
+    char* d_ds = d_anchor + ((b_anchor + 255) & ~size_t(255));
+    char* d_len = d_ds + ((b_u8 + 255) & ~size_t(255));
+    const bool pinned = is_pinned_host(anchors) && is_pinned_host(dstart) && is_pinned_host(len);
+    if (!pinned) GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));   // previous unpack done with the staging buffer
+    GL_CUDA(ctx, cudaMemcpyAsync(d_anchor, anchors, b_anchor, cudaMemcpyHostToDevice, ctx->copy_stream));
+    GL_CUDA(ctx, cudaMemcpyAsync(d_ds, dstart, b_u8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    GL_CUDA(ctx, cudaMemcpyAsync(d_len, len, b_u8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    GL_CUDA(ctx, cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
+    GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
+    {
+        gl_prof_scope prof(ctx, "depth_unpack8_kernel");
+        depth_unpack8_kernel<<<(unsigned)((n_blocks + 31) / 32), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const int*>(d_anchor), reinterpret_cast<const uint2*>(d_ds), reinterpret_cast<const uint2*>(d_len), n_blocks,
+            static_cast<int*>(ctx->store_s.p) + base, static_cast<int*>(ctx->store_e.p) + base);
+    }
+    GL_LAUNCHED(ctx, 1);
+    GL_CUDA(ctx, cudaEventRecord(ctx->ev_used[0], ctx->stream));
+    if (!pinned) GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    if (!ctx->batches.empty() && ctx->batches.back().s == nullptr &&
+        ctx->batches.back().off + ctx->batches.back().n == base) {
+        ctx->batches.back().n += n;
+    } else {
+        gl_seg_batch b;
+        b.off = base; b.n = n;
+        ctx->batches.push_back(b);
+    }
+    ctx->store_n = base + n;
+    ctx->g_valid = false;
+    ctx->depth_reduced = false;
+    return GL_OK;
+}
+
 int gl_depth_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break) {
     GL_CHECK(gl_use(ctx));
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_reduce: no region open");
@@ -1331,6 +1413,16 @@ int gl_depth_region_packed16(gl_ctx* ctx, int64_t region_start, int64_t region_e
                              int64_t run_cap, int64_t* n_runs) {
     GL_CHECK(gl_depth_begin(ctx, region_start, region_end));
     GL_CHECK(gl_depth_add_segments_packed16(ctx, anchors, off, len, n_blocks));
+    GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, run_break));
+    return region_fetch(ctx, sum_out, win_cap, n_windows, run_start, run_class, run_cap, n_runs);
+}
+
+int gl_depth_region_packed8(gl_ctx* ctx, int64_t region_start, int64_t region_end, const int32_t* anchors, const uint8_t* dstart,
+                            const uint8_t* len, int64_t n_blocks, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break,
+                            int64_t* sum_out, int64_t win_cap, int64_t* n_windows, int32_t* run_start, uint8_t* run_class,
+                            int64_t run_cap, int64_t* n_runs) {
+    GL_CHECK(gl_depth_begin(ctx, region_start, region_end));
+    GL_CHECK(gl_depth_add_segments_packed8(ctx, anchors, dstart, len, n_blocks));
     GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, run_break));
     return region_fetch(ctx, sum_out, win_cap, n_windows, run_start, run_class, run_cap, n_runs);
 }

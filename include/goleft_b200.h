@@ -112,6 +112,15 @@ int  gl_pack_segments16(const int32_t* start, const int32_t* end, int64_t n, int
                         uint16_t* len, int64_t cap_blocks, int64_t* n_blocks);
 int  gl_depth_add_segments_packed16(gl_ctx* ctx, const int32_t* anchors, const uint16_t* off, const uint16_t* len,
                                     int64_t n_blocks);
+/* "packed8": a quarter of the bytes, for short-read data.  Blocks of 64 slots: int32 anchor (start of slot 0) +
+ * per slot uint8 dstart (start - previous slot's start) and uint8 len (0 = empty/filler).  gl_pack_segments8 puts the
+ * segments in start order (depth is order-independent), cuts segments longer than 255 into pieces and bridges gaps
+ * > 255 bases with filler slots or a new block, whichever is smaller; same return convention as gl_pack_segments16.
+ * Use it when 132 * n_blocks < 8 * n (always for 100-250 bp reads at >= 1x). */
+int64_t gl_pack_segments8_bound(int64_t n);
+int  gl_pack_segments8(const int32_t* start, const int32_t* end, int64_t n, int32_t* anchors, uint8_t* dstart, uint8_t* len,
+                       int64_t cap_blocks, int64_t* n_blocks);
+int  gl_depth_add_segments_packed8(gl_ctx* ctx, const int32_t* anchors, const uint8_t* dstart, const uint8_t* len, int64_t n_blocks);
 
 /* One fused pass: prefix scan -> per-base depth (never written to HBM) ->
  *   (a) per-window int64 sums for genome-aligned windows of size W clipped to the region:
@@ -159,6 +168,10 @@ int  gl_depth_region_packed16(gl_ctx* ctx, int64_t region_start, int64_t region_
                               int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break,
                               int64_t* sum_out, int64_t win_cap, int64_t* n_windows,
                               int32_t* run_start, uint8_t* run_class, int64_t run_cap, int64_t* n_runs);
+int  gl_depth_region_packed8(gl_ctx* ctx, int64_t region_start, int64_t region_end, const int32_t* anchors,
+                             const uint8_t* dstart, const uint8_t* len, int64_t n_blocks, int32_t W, int32_t mincov, int32_t maxmean,
+                             int64_t run_break, int64_t* sum_out, int64_t win_cap, int64_t* n_windows, int32_t* run_start,
+                             uint8_t* run_class, int64_t run_cap, int64_t* n_runs);
 
 /* Host-side text: reproduces the rows the reference callback writes for ONE chunk
  * [rs,re) (depth/depth.go:293-305,326-358 incl. the chunk-edge quirks) from window sums

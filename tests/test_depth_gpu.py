@@ -302,6 +302,42 @@ def test_packed16_path(ctx):
     assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
 
 
+def test_packed8_path(ctx):
+    """the feeder's densest format (a quarter of the PCIe bytes; short reads) gives the same integers"""
+    L = 5_000_000
+    s, e = synth.segments(synth.reads(L, contig_index=9))
+    a, d, ln = capi.pack_segments8(s, e)
+    exp = orc.pileup_diff(s, e, 0, L)
+    es, _ = orc.window_sums(exp, 0, L, 500)
+    ea, ec = orc.class_runs(exp, 0, L, 4, 0, 1_000_000)
+    ws, r0, rc = ctx.depth_region_packed8(0, L, a, d, ln, 500, 4, 0, run_break=1_000_000)
+    assert ctx.depth_last_path() == 1
+    assert np.array_equal(ws, es) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
+    # an int32 batch of odd length first (the packed8 unpack realigns the store), then packed8 + packed16 batches; clipping
+    h = s.size // 3 | 1
+    a1, d1, l1 = capi.pack_segments8(s[h:2 * h], e[h:2 * h])
+    a2, o2, l2 = capi.pack_segments16(s[2 * h:], e[2 * h:])
+    ctx.depth_begin(1234, 4_000_000)
+    ctx.depth_add_segments(s[:h], e[:h])
+    ctx.depth_add_segments_packed8(a1, d1, l1)
+    ctx.depth_add_segments_packed16(a2, o2, l2)
+    ctx.depth_reduce(250, 4, 0, 0)
+    exp = orc.pileup_diff(s, e, 1234, 4_000_000)
+    assert np.array_equal(ctx.depth_get_windows(), orc.window_sums(exp, 1234, 4_000_000, 250)[0])
+    r0, rc = ctx.depth_get_runs()
+    ea, ec = orc.class_runs(exp, 1234, 4_000_000, 4, 0, 0)
+    assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
+    # long segments and gaps: pieces + fillers, general path
+    rng = np.random.default_rng(5)
+    s = np.sort(rng.integers(0, 3_000_000, 20000)).astype(np.int32)
+    e = (s + rng.choice([1, 100, 255, 256, 3000, 40000], s.size)).astype(np.int32)
+    a, d, ln = capi.pack_segments8(s, e)
+    exp = orc.pileup_diff(s, e, 500, 2_900_000)
+    ws, r0, rc = ctx.depth_region_packed8(500, 2_900_000, a, d, ln, 333, 4, 0)
+    ea, ec = orc.class_runs(exp, 500, 2_900_000, 4, 0, 0)
+    assert np.array_equal(ws, orc.window_sums(exp, 500, 2_900_000, 333)[0]) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
+
+
 def test_chr1_sized_contig(ctx):
     """BASELINE config[2]'s largest shard unit: a 248,956,422 bp contig at 30x (41 M reads), one launch per kernel.
     Checks the size-independent properties (sum of window sums == total clipped segment length; runs strictly

@@ -298,3 +298,30 @@ def test_faidx_stats_restatement_hand_cases():
     assert np.allclose(st, [1.0, 2 * 1 / 4, 3 / 4])
     assert orc.faidx_stats(fa, rec, 0, 18) is None            # faidx panics past the contig
     assert orc.stats_text(np.array([0.5, 0.04166, 1.0])) == b"\t0.5\t0.0417\t1"
+
+
+def test_pack_segments8_roundtrip():
+    """packed8 (uint8 start delta + uint8 length per slot): the decoded pieces are in start order and give the
+    oracle's per-base depth — short reads in BAM order (a quarter of the int32 bytes), and the awkward inputs: long
+    segments (cut in 255-base pieces), gaps (filler slots / new blocks), negative starts, shuffled order, empties."""
+    L = 1_000_000
+    s, e = synth.segments(synth.reads(L, contig_index=4))
+    a, d, ln = capi.pack_segments8(s, e)
+    assert a.size * 132 < 0.27 * s.size * 8
+    s2, e2 = capi.unpack_segments8(a, d, ln)
+    assert (np.diff(s2) >= 0).all() and s2.size == s.size
+    assert np.array_equal(orc.pileup_diff(s, e, 0, L), orc.pileup_diff(s2.astype(np.int32), e2.astype(np.int32), 0, L))
+    rng = np.random.default_rng(0)
+    s = np.concatenate([rng.integers(-300, 5000, 300), rng.integers(10_000_000, 10_001_000, 50), [2_000_000_000]]).astype(np.int32)
+    e = (s + rng.choice([0, 1, 5, 150, 255, 256, 1000, 70000], s.size)).astype(np.int32)
+    e[-1] = s[-1] + 100
+    a, d, ln = capi.pack_segments8(s, e)
+    s2, e2 = capi.unpack_segments8(a, d, ln)
+    assert (e2 - s2).max() <= 255 and (np.diff(s2) >= 0).all()
+    for rs, re in [(0, 100000), (9_990_000, 10_100_000), (1_999_999_000, 2_000_001_000)]:
+        assert np.array_equal(orc.pileup_brute(s, e, rs, re), orc.pileup_brute(s2.astype(np.int32), e2.astype(np.int32), rs, re))
+    p = rng.permutation(s.size)                                   # order does not matter
+    a3, d3, l3 = capi.pack_segments8(s[p], e[p])
+    s3, e3 = capi.unpack_segments8(a3, d3, l3)
+    assert np.array_equal(np.sort(s3), np.sort(s2)) and (e3 - s3).sum() == (e2 - s2).sum()
+    assert capi.pack_segments8(np.zeros(0, np.int32), np.zeros(0, np.int32))[0].size == 0
