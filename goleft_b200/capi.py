@@ -126,6 +126,7 @@ _proto("gl_depth_region_packed16", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp,
 _proto("gl_pack_segments8_bound", C.c_int64, C.c_int64)
 _proto("gl_pack_segments8", C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_depth_add_segments_packed8", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
+_proto("gl_depth_add_segments_packed8_device", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_region_packed8", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_crai_make_sizes", C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _i64p)
@@ -396,6 +397,9 @@ class Ctx:
 
     def depth_add_segments_packed8(self, anchors: np.ndarray, dstart: np.ndarray, ln: np.ndarray):
         self._ck(lib.gl_depth_add_segments_packed8(self.h, _ptr(anchors), _ptr(dstart), _ptr(ln), anchors.size))
+
+    def depth_add_segments_packed8_device(self, d_anchors: "DevBuf", d_dstart: "DevBuf", d_len: "DevBuf", n_blocks: int):
+        self._ck(lib.gl_depth_add_segments_packed8_device(self.h, d_anchors.ptr, d_dstart.ptr, d_len.ptr, n_blocks))
 
     def depth_region_packed8(self, rs: int, re: int, anchors, dstart, ln, W: int, mincov: int = 4, maxmean: int = 0,
                              run_break: int = 0, out=None):

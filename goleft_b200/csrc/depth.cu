@@ -324,6 +324,13 @@ struct ScanParams {
     int* depth_out;               // optional per-base output (debug/parity), else null
     int num_tiles;
     int do_windows, do_runs;
+    // packed8 path (K_tileidx8 + K_fused8)
+    const int* p8_anchors;        // [p8_nblocks] non-decreasing
+    const unsigned* p8_ds;        // [p8_nblocks*16] 4 uint8 start deltas per word
+    const unsigned* p8_len;       // [p8_nblocks*16] 4 uint8 lengths per word
+    int p8_nblocks;
+    int* tile_lo;                 // [num_tiles] first / one-past-last block that can touch the tile
+    int* tile_hi;
 };
 
 __device__ __forceinline__ int cov_class(int d, int mincov, int maxmean) {
@@ -750,6 +757,102 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const Scan
     }
 }
 
+// ================================================================================================
+// packed8 path.  The segments arrive sorted by start in 64-slot blocks with sorted anchors and lengths <= 255,
+// so the blocks a tile needs follow from the anchors alone: no per-segment index pass, no int32 copy of the
+// segments in HBM, a quarter of the segment bytes read.
+// K_tileidx8: per tile the block range [lo,hi): blocks that may hold a start in [t0-255, t1).  Block b's starts lie in
+// [anchor[b], anchor[b+1]], so lo = (#anchors < t0-255) - 1 and hi = #anchors < t1.  Also verifies the anchors' order.
+// ================================================================================================
+__global__ void __launch_bounds__(256) depth_tileidx8_kernel(const ScanParams p) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int nb = p.p8_nblocks;
+    for (int i = t; i + 1 < nb; i += gridDim.x * 256)
+        if (p.p8_anchors[i] > p.p8_anchors[i + 1]) p.header[3] = 1;
+    if (t >= p.num_tiles) return;
+    const long long t0 = (long long)p.rs + (long long)t * kTile;
+    const long long t1 = min(t0 + kTile, (long long)p.re);
+    auto count_less = [&](long long x) {                    // number of anchors < x
+        int lo = 0, hi = nb;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((long long)p.p8_anchors[mid] < x) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    p.tile_lo[t] = max(0, count_less(t0 - 255) - 1);
+    p.tile_hi[t] = count_less(t1);
+}
+
+struct P8Regs { unsigned d, l; int anchor; };
+
+// thread (tid) takes slots 4*(tid&15)..+3 of block lo + (tid>>4) + 16*pass
+__device__ __forceinline__ P8Regs fused8_load(const ScanParams& p, int lo, int hi, int pass) {
+    P8Regs r = {0u, 0u, 0};
+    const int b = lo + (int)(threadIdx.x >> 4) + 16 * pass;
+    if (b < hi) {
+        r.d = p.p8_ds[(size_t)b * 16 + (threadIdx.x & 15)];
+        r.l = p.p8_len[(size_t)b * 16 + (threadIdx.x & 15)];
+        r.anchor = p.p8_anchors[b];
+    }
+    return r;
+}
+
+__device__ __forceinline__ void fused8_apply(const P8Regs& r, int* s_tile, int t0, int t1, bool first_tile, int& carry) {
+    const int sub = threadIdx.x & 15;
+    const int d0 = r.d & 0xff, d1 = d0 + ((r.d >> 8) & 0xff), d2 = d1 + ((r.d >> 16) & 0xff), d3 = d2 + (r.d >> 24);
+    int inc = d3;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, inc, o, 16);
+        if (sub >= o) inc += v;
+    }
+    if (r.l == 0) return;                                   // four empty slots (or no block): nothing to add
+    const int base = r.anchor + inc - d3;
+    const int s0 = base + d0, s1 = base + d1, s2 = base + d2, s3 = base + d3;
+    fused_apply(s_tile, t0, t1, first_tile, s0, s0 + (int)(r.l & 0xff), carry);
+    fused_apply(s_tile, t0, t1, first_tile, s1, s1 + (int)((r.l >> 8) & 0xff), carry);
+    fused_apply(s_tile, t0, t1, first_tile, s2, s2 + (int)((r.l >> 16) & 0xff), carry);
+    fused_apply(s_tile, t0, t1, first_tile, s3, s3 + (int)(r.l >> 24), carry);
+}
+
+// K_fused8: persistent, software-pipelined like K_fused: while tile n runs its core, the packed words of tile n+1 and
+// the block range of tile n+2 are in flight.
+__global__ void __launch_bounds__(kScanThreads, 4) depth_fused8_kernel(const ScanParams p) {
+    __shared__ __align__(16) int s_tile[kTile];
+    __shared__ __align__(16) int s_depth[kTile];
+    __shared__ int s_carry2[2][kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    if (p.header[3] != 0) return;                           // K_tileidx8 found unsorted anchors: the host falls back
+#pragma unroll
+    for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);   // later tiles: cleared by the core
+    int tile = blockIdx.x;
+    int lo = 0, hi = 0, lo2 = 0, hi2 = 0;
+    if (tile < p.num_tiles) { lo = p.tile_lo[tile]; hi = p.tile_hi[tile]; }
+    if (tile + G < p.num_tiles) { lo2 = p.tile_lo[tile + G]; hi2 = p.tile_hi[tile + G]; }
+    P8Regs regs = fused8_load(p, lo, hi, 0);
+    __syncthreads();
+
+    for (int it = 0; tile < p.num_tiles; tile += G, it ^= 1) {
+        int* s_carry = s_carry2[it];
+        const int t0 = p.rs + tile * kTile, t1 = min(t0 + kTile, p.re);
+        const bool first_tile = tile == 0;
+        int carry = 0;
+        fused8_apply(regs, s_tile, t0, t1, first_tile, carry);
+        for (int pass = 1; lo + 16 * pass < hi; pass++)     // deep tiles only (uniform trip count)
+            fused8_apply(fused8_load(p, lo, hi, pass), s_tile, t0, t1, first_tile, carry);
+        carry = __reduce_add_sync(kFull, carry);
+        if (lane == 0) s_carry[warp] = carry;
+        __syncthreads();
+        lo = lo2; hi = hi2;
+        regs = fused8_load(p, lo, hi, 0);                   // next tile's packed words: in flight during the core
+        lo2 = hi2 = 0;
+        if (tile + 2 * G < p.num_tiles) { lo2 = p.tile_lo[tile + 2 * G]; hi2 = p.tile_hi[tile + 2 * G]; }
+        tile_core<true>(p, s_tile, s_depth, s_carry, tile);
+    }
+}
+
 // K_gather: one warp per 512-base chunk moves its runs from claim order to position order.  The ordered offset
 // of a chunk is the number of runs that start before it: counts per 64 chunks + the chunk counts of its own group
 // (only chunks that have runs pay for the sum).
@@ -894,6 +997,134 @@ int read_header(gl_ctx* ctx, uint64_t hdr[4]) {
     return GL_OK;
 }
 
+// packed8 batch -> int32 arrays in the store (only when something needs them: another batch, a forced path, ...)
+int p8_materialize(gl_ctx* ctx) {
+    if (!ctx->p8.pending) return GL_OK;
+    {
+        gl_prof_scope prof(ctx, "depth_unpack8_kernel");
+        depth_unpack8_kernel<<<(unsigned)((ctx->p8.n_blocks + 31) / 32), 256, 0, ctx->stream>>>(
+            ctx->p8.anchors, static_cast<const uint2*>(ctx->p8.ds), static_cast<const uint2*>(ctx->p8.len), ctx->p8.n_blocks,
+            static_cast<int*>(ctx->store_s.p) + ctx->p8.store_off, static_cast<int*>(ctx->store_e.p) + ctx->p8.store_off);
+    }
+    GL_LAUNCHED(ctx, 1);
+    GL_CUDA(ctx, cudaEventRecord(ctx->ev_used[0], ctx->stream));
+    ctx->p8.pending = false;
+    return GL_OK;
+}
+
+// The region's only batch is packed8: K_tileidx8 + K_fused8 + K_gather straight from the packed words.
+// *accepted = false when the anchors turn out unsorted (hand-made input): the caller unpacks and takes the other paths.
+int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break, bool do_windows, bool do_runs,
+                  int32_t* d_depth_out, bool want_min, bool* accepted) {
+    *accepted = false;
+    const int64_t len = ctx->re - ctx->rs;
+    const int64_t tiles = num_tiles_for(len);
+    const int64_t w0 = ctx->rs / W;
+    const int64_t n_windows = (ctx->re - 1) / W - w0 + 1;
+    if (do_windows && want_min) GL_CHECK(gl_buf_reserve(ctx, ctx->win_min, (size_t)n_windows * 4));
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const int64_t chunks = tiles * kWarps;
+    const size_t supers = (size_t)(chunks >> kSuperShift) + 2;
+    const size_t head_bytes = al(kHeaderWords * 8 + supers * 4);
+    const size_t win_bytes = al(do_windows ? (size_t)n_windows * 8 : 0);
+    const size_t zero_bytes = head_bytes + win_bytes;
+    const size_t run_bytes = al((size_t)chunks * 8);
+    GL_CHECK(gl_buf_reserve(ctx, ctx->scratch, zero_bytes + run_bytes + 2 * al((size_t)tiles * 4)));
+    if (do_runs && ctx->run_start.cap == 0) {
+        size_t cap = (size_t)(len / 16 + 4096);
+        GL_CHECK(gl_buf_reserve(ctx, ctx->run_start, cap * 4));
+        GL_CHECK(gl_buf_reserve(ctx, ctx->run_class, cap));
+        GL_CHECK(gl_buf_reserve(ctx, ctx->run_tmp_start, cap * 4));
+        GL_CHECK(gl_buf_reserve(ctx, ctx->run_tmp_class, cap));
+    }
+    char* sbase = static_cast<char*>(ctx->scratch.p);
+    uint64_t* header = reinterpret_cast<uint64_t*>(sbase);
+    unsigned* super_cnt = reinterpret_cast<unsigned*>(header + kHeaderWords);
+    ctx->win_sum_p = sbase + head_bytes;
+    uint64_t* chunk_runs = reinterpret_cast<uint64_t*>(sbase + zero_bytes);
+
+    ScanParams p;
+    memset(&p, 0, sizeof p);
+    p.len = (int)len;
+    p.rs = (int)ctx->rs;
+    p.re = (int)ctx->re;
+    p.W = W;
+    p.w0 = w0;
+    p.mincov = mincov;
+    p.maxmean = maxmean;
+    p.run_break = (run_break >= (int64_t(1) << 32)) ? 0u : (unsigned)run_break;
+    p.header = header;
+    p.chunk_runs = chunk_runs;
+    p.super_cnt = super_cnt;
+    p.depth_out = d_depth_out;
+    p.num_tiles = (int)tiles;
+    p.do_windows = do_windows ? 1 : 0;
+    p.do_runs = do_runs ? 1 : 0;
+    p.p8_anchors = ctx->p8.anchors;
+    p.p8_ds = static_cast<const unsigned*>(ctx->p8.ds);
+    p.p8_len = static_cast<const unsigned*>(ctx->p8.len);
+    p.p8_nblocks = (int)ctx->p8.n_blocks;
+    p.tile_lo = reinterpret_cast<int*>(sbase + zero_bytes + run_bytes);
+    p.tile_hi = reinterpret_cast<int*>(sbase + zero_bytes + run_bytes + al((size_t)tiles * 4));
+    p.win_sum = static_cast<unsigned long long*>(ctx->win_sum_p);
+    p.win_min = (do_windows && want_min) ? static_cast<int*>(ctx->win_min.p) : nullptr;
+
+    for (int attempt = 0; attempt < 2; attempt++) {
+        p.tmp_start = static_cast<int*>(ctx->run_tmp_start.p);
+        p.tmp_class = static_cast<unsigned char*>(ctx->run_tmp_class.p);
+        long long cap = 0;
+        if (do_runs) {
+            cap = (long long)ctx->run_class.cap;
+            cap = std::min<long long>(cap, (long long)(ctx->run_start.cap / 4));
+            cap = std::min<long long>(cap, (long long)ctx->run_tmp_class.cap);
+            cap = std::min<long long>(cap, (long long)(ctx->run_tmp_start.cap / 4));
+        }
+        p.run_cap = cap;
+        GL_CUDA(ctx, cudaMemsetAsync(sbase, 0, zero_bytes, ctx->stream));
+        if (do_windows && want_min) GL_CUDA(ctx, cudaMemsetAsync(ctx->win_min.p, 0x7f, (size_t)n_windows * 4, ctx->stream));
+        {
+            gl_prof_scope prof(ctx, "depth_tileidx8_kernel");
+            depth_tileidx8_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, ctx->stream>>>(p);
+        }
+        GL_LAUNCHED(ctx, 1);
+        {
+            gl_prof_scope prof(ctx, "depth_fused8_kernel");
+            depth_fused8_kernel<<<(unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 4), kScanThreads, 0, ctx->stream>>>(p);
+        }
+        GL_LAUNCHED(ctx, 1);
+        GL_CUDA(ctx, cudaEventRecord(ctx->ev_used[0], ctx->stream));      // the packed staging buffer may be overwritten after this
+        if (do_runs) {
+            gl_prof_scope prof(ctx, "depth_gather_runs_kernel");
+            depth_gather_runs_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, ctx->stream>>>(
+                header, chunk_runs, super_cnt, (int)chunks, p.tmp_start, p.tmp_class, static_cast<int*>(ctx->run_start.p),
+                static_cast<unsigned char*>(ctx->run_class.p), cap);
+            GL_LAUNCHED(ctx, 1);
+        }
+        uint64_t hdr[4];
+        GL_CHECK(read_header(ctx, hdr));
+        if (hdr[3] != 0) return GL_OK;                                     // anchors not sorted: not accepted
+        ctx->n_runs = do_runs ? (int64_t)hdr[0] : 0;
+        ctx->max_depth = (int32_t)hdr[2];
+        if (do_runs && (long long)hdr[0] > cap) {                          // output did not fit: grow and rerun
+            size_t ncap = (size_t)hdr[0] + 1024;
+            GL_CHECK(gl_buf_reserve(ctx, ctx->run_start, ncap * 4));
+            GL_CHECK(gl_buf_reserve(ctx, ctx->run_class, ncap));
+            GL_CHECK(gl_buf_reserve(ctx, ctx->run_tmp_start, ncap * 4));
+            GL_CHECK(gl_buf_reserve(ctx, ctx->run_tmp_class, ncap));
+            continue;
+        }
+        break;
+    }
+    ctx->last_path = 3;
+    ctx->idx_flags = nullptr;
+    ctx->idx_cells = nullptr;
+    ctx->red_W = W; ctx->red_mincov = mincov; ctx->red_maxmean = maxmean; ctx->red_break = run_break;
+    ctx->n_windows = do_windows ? n_windows : 0;
+    ctx->depth_reduced = true;
+    *accepted = true;
+    return GL_OK;
+}
+
 // One fused pass over the region.  Tries the fused (sorted) path first; the device decides eligibility,
 // the host learns it from the header it has to read anyway, and reruns on the general path if needed.
 int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break, bool do_windows,
@@ -907,6 +1138,14 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
         GL_CUDA(ctx, cudaEventRecord(ctx->ev_copy[0], ctx->copy_stream));
         GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[0], 0));
         ctx->copies_pending = false;
+    }
+    if (ctx->p8.pending) {
+        if (ctx->force_path == 0 && ctx->batches.size() == 1 && tiles < (int64_t(1) << 30) && ctx->p8.n_blocks < INT32_MAX) {
+            bool accepted = false;
+            GL_CHECK(run_reduce_f8(ctx, W, mincov, maxmean, run_break, do_windows, do_runs, d_depth_out, want_min, &accepted));
+            if (accepted) return GL_OK;
+        }
+        GL_CHECK(p8_materialize(ctx));
     }
     if (do_windows && want_min) GL_CHECK(gl_buf_reserve(ctx, ctx->win_min, (size_t)n_windows * 4));
     // One scratch buffer; everything that must start at zero is contiguous so a single memset clears it:
@@ -1092,6 +1331,7 @@ int gl_depth_begin(gl_ctx* ctx, int64_t region_start, int64_t region_end) {
     ctx->re = region_end;
     ctx->batches.clear();
     ctx->store_n = 0;
+    ctx->p8.pending = false;
     ctx->g_valid = false;
     ctx->depth_active = true;
     ctx->depth_reduced = false;
@@ -1106,6 +1346,7 @@ int gl_depth_add_segments_device(gl_ctx* ctx, const int32_t* d_start, const int3
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_add_segments: no region open (call gl_depth_begin)");
     if (n < 0 || (n > 0 && (!d_start || !d_end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments: bad argument");
     if (n == 0) return GL_OK;
+    GL_CHECK(p8_materialize(ctx));
     gl_seg_batch b;
     b.s = d_start; b.e = d_end; b.n = n;
     ctx->batches.push_back(b);
@@ -1119,6 +1360,7 @@ int gl_depth_add_segments(gl_ctx* ctx, const int32_t* start, const int32_t* end,
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_add_segments: no region open (call gl_depth_begin)");
     if (n < 0 || (n > 0 && (!start || !end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments: bad argument");
     if (n == 0) return GL_OK;
+    GL_CHECK(p8_materialize(ctx));
     GL_CHECK(store_reserve(ctx, ctx->store_n + n));
     int32_t* d_s = static_cast<int32_t*>(ctx->store_s.p) + ctx->store_n;
     int32_t* d_e = static_cast<int32_t*>(ctx->store_e.p) + ctx->store_n;
@@ -1171,6 +1413,7 @@ int gl_depth_add_segments_packed16(gl_ctx* ctx, const int32_t* anchors, const ui
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_add_segments_packed16: no region open (call gl_depth_begin)");
     if (n_blocks < 0 || (n_blocks > 0 && (!anchors || !off || !len))) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments_packed16: bad argument");
     if (n_blocks == 0) return GL_OK;
+    GL_CHECK(p8_materialize(ctx));
     const int64_t n = n_blocks * 256;
     GL_CHECK(store_reserve(ctx, ctx->store_n + n));
     // staging for the packed bytes: anchors | off | len
@@ -1214,48 +1457,54 @@ int gl_depth_add_segments_packed16(gl_ctx* ctx, const int32_t* anchors, const ui
     return GL_OK;
 }
 
+// registers a packed8 batch whose words are already on the device (stream-ordered after ctx->stream's wait)
+static int p8_register(gl_ctx* ctx, const int* d_anchor, const void* d_ds, const void* d_len, int64_t n_blocks) {
+    const int64_t n = n_blocks * 64;
+    const int64_t base = (ctx->store_n + 3) & ~int64_t(3);        // the unpack kernel stores int4
+    GL_CHECK(store_reserve(ctx, base + n));
+    gl_seg_batch b;
+    b.off = base; b.n = n;
+    ctx->batches.push_back(b);
+    ctx->store_n = base + n;
+    ctx->p8.anchors = d_anchor; ctx->p8.ds = d_ds; ctx->p8.len = d_len; ctx->p8.n_blocks = n_blocks; ctx->p8.store_off = base;
+    ctx->p8.pending = true;
+    if (ctx->batches.size() > 1) GL_CHECK(p8_materialize(ctx));   // not the only batch: the int32 paths take it
+    ctx->g_valid = false;
+    ctx->depth_reduced = false;
+    return GL_OK;
+}
+
+int gl_depth_add_segments_packed8_device(gl_ctx* ctx, const int32_t* d_anchors, const uint8_t* d_dstart, const uint8_t* d_len, int64_t n_blocks) {
+    GL_CHECK(gl_use(ctx));
+    if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_add_segments_packed8_device: no region open (call gl_depth_begin)");
+    if (n_blocks < 0 || (n_blocks > 0 && (!d_anchors || !d_dstart || !d_len))) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments_packed8_device: bad argument");
+    if (((uintptr_t)d_dstart | (uintptr_t)d_len) & 7) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments_packed8_device: dstart/len must be 8-byte aligned");
+    if (n_blocks == 0) return GL_OK;
+    GL_CHECK(p8_materialize(ctx));
+    return p8_register(ctx, d_anchors, d_dstart, d_len, n_blocks);
+}
+
 int gl_depth_add_segments_packed8(gl_ctx* ctx, const int32_t* anchors, const uint8_t* dstart, const uint8_t* len, int64_t n_blocks) {
     GL_CHECK(gl_use(ctx));
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_add_segments_packed8: no region open (call gl_depth_begin)");
     if (n_blocks < 0 || (n_blocks > 0 && (!anchors || !dstart || !len))) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments_packed8: bad argument");
     if (n_blocks == 0) return GL_OK;
-    const int64_t n = n_blocks * 64;
-    const int64_t base = (ctx->store_n + 3) & ~int64_t(3);        // the unpack kernel stores int4
-    GL_CHECK(store_reserve(ctx, base + n));
-    const size_t b_anchor = (size_t)n_blocks * 4, b_u8 = (size_t)n;
+    GL_CHECK(p8_materialize(ctx));                                  // an earlier packed8 batch still lives in the staging buffer
+    const size_t b_anchor = (size_t)n_blocks * 4, b_u8 = (size_t)n_blocks * 64;
     GL_CHECK(gl_buf_reserve(ctx, ctx->packed, ((b_anchor + 255) & ~size_t(255)) + 2 * ((b_u8 + 255) & ~size_t(255))));
     char* d_anchor = static_cast<char*>(ctx->packed.p);
     char* d_ds = d_anchor + ((b_anchor + 255) & ~size_t(255));
     char* d_len = d_ds + ((b_u8 + 255) & ~size_t(255));
     const bool pinned = is_pinned_host(anchors) && is_pinned_host(dstart) && is_pinned_host(len);
     if (!pinned) GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));   // previous unpack done with the staging buffer
+    GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));   // previous consumer done with the staging buffer
     GL_CUDA(ctx, cudaMemcpyAsync(d_anchor, anchors, b_anchor, cudaMemcpyHostToDevice, ctx->copy_stream));
     GL_CUDA(ctx, cudaMemcpyAsync(d_ds, dstart, b_u8, cudaMemcpyHostToDevice, ctx->copy_stream));
     GL_CUDA(ctx, cudaMemcpyAsync(d_len, len, b_u8, cudaMemcpyHostToDevice, ctx->copy_stream));
     GL_CUDA(ctx, cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
     GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
-    {
-        gl_prof_scope prof(ctx, "depth_unpack8_kernel");
-        depth_unpack8_kernel<<<(unsigned)((n_blocks + 31) / 32), 256, 0, ctx->stream>>>(
-            reinterpret_cast<const int*>(d_anchor), reinterpret_cast<const uint2*>(d_ds), reinterpret_cast<const uint2*>(d_len), n_blocks,
-            static_cast<int*>(ctx->store_s.p) + base, static_cast<int*>(ctx->store_e.p) + base);
-    }
-    GL_LAUNCHED(ctx, 1);
-    GL_CUDA(ctx, cudaEventRecord(ctx->ev_used[0], ctx->stream));
     if (!pinned) GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    if (!ctx->batches.empty() && ctx->batches.back().s == nullptr &&
-        ctx->batches.back().off + ctx->batches.back().n == base) {
-        ctx->batches.back().n += n;
-    } else {
-        gl_seg_batch b;
-        b.off = base; b.n = n;
-        ctx->batches.push_back(b);
-    }
-    ctx->store_n = base + n;
-    ctx->g_valid = false;
-    ctx->depth_reduced = false;
-    return GL_OK;
+    return p8_register(ctx, reinterpret_cast<const int*>(d_anchor), d_ds, d_len, n_blocks);
 }
 
 int gl_depth_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t run_break) {
@@ -1281,7 +1530,7 @@ int gl_depth_last_path(gl_ctx* ctx, int32_t* path) {
 }
 
 int gl_depth_set_path(gl_ctx* ctx, int32_t path) {
-    if (!ctx || path < 0 || path > 2) return gl_fail(ctx, GL_EINVAL, "gl_depth_set_path: path must be 0 (auto), 1 or 2");
+    if (!ctx || path < 0 || path > 2) return gl_fail(ctx, GL_EINVAL, "gl_depth_set_path: path must be 0 (auto), 1 (no packed8 kernel) or 2 (general only)");
     ctx->force_path = path;
     return GL_OK;
 }
@@ -1348,6 +1597,7 @@ int gl_depth_interval_sums(gl_ctx* ctx, const int32_t* a, const int32_t* b, int6
         ctx->copies_pending = false;
     }
     if ((int)ctx->batches.size() > kMaxBatches) return gl_fail(ctx, GL_ERANGE, "gl_depth_interval_sums: more than %d segment batches", kMaxBatches);
+    GL_CHECK(p8_materialize(ctx));
     ScanParams p;
     memset(&p, 0, sizeof p);
     p.rs = (int)ctx->rs;

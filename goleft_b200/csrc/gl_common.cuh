@@ -47,7 +47,11 @@ struct gl_ctx {
     int last_path = 0;                      // 1 = fused sorted path, 2 = general scatter path
     // index tables of the last fused reduce (valid until the next reduce): used by gl_depth_interval_sums
     const int* idx_flags = nullptr; const unsigned* idx_cells = nullptr; int idx_origin = 0, idx_ncells = 0, idx_maxlen = -1;
-    int force_path = 0;                     // 0 = auto, 2 = always general (tests / comparison arm)
+    int force_path = 0;                     // 0 = auto, 1 = no packed8 kernel (int32 fused, else general), 2 = always general
+    // a packed8 batch that is the region's only batch stays packed: K_fused8 reads it as it is (last_path 3); it is
+    // unpacked into the store (its batch descriptor already points there) only when something needs int32 arrays
+    struct { const int* anchors = nullptr; const void* ds = nullptr; const void* len = nullptr; int64_t n_blocks = 0, store_off = 0;
+             bool pending = false; } p8;
     gl_buf diff;          // int32[len+1 (+pad)] + tile sums (general path only)
     void* win_sum_p = nullptr;   // u64[n_windows], inside `scratch`
     gl_buf win_min;       // i32[n_windows]

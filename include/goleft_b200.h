@@ -121,6 +121,10 @@ int64_t gl_pack_segments8_bound(int64_t n);
 int  gl_pack_segments8(const int32_t* start, const int32_t* end, int64_t n, int32_t* anchors, uint8_t* dstart, uint8_t* len,
                        int64_t cap_blocks, int64_t* n_blocks);
 int  gl_depth_add_segments_packed8(gl_ctx* ctx, const int32_t* anchors, const uint8_t* dstart, const uint8_t* len, int64_t n_blocks);
+/* same with the three arrays already in device memory (caller-owned, 8-byte aligned, must stay valid until the region's
+ * last reduce): nothing is copied; a region whose only batch is packed8 is reduced straight from these words. */
+int  gl_depth_add_segments_packed8_device(gl_ctx* ctx, const int32_t* d_anchors, const uint8_t* d_dstart, const uint8_t* d_len,
+                                          int64_t n_blocks);
 
 /* One fused pass: prefix scan -> per-base depth (never written to HBM) ->
  *   (a) per-window int64 sums for genome-aligned windows of size W clipped to the region:
@@ -133,9 +137,10 @@ int  gl_depth_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, in
 
 /* Sizes of the results of the last gl_depth_reduce. */
 int  gl_depth_result_sizes(gl_ctx* ctx, int64_t* n_windows, int64_t* n_runs, int32_t* max_depth);
-/* Which path the last reduce took: 1 = fused (sorted), 2 = general (scatter). */
+/* Which path the last reduce took: 1 = fused (nearly sorted int32 segments), 2 = general (scatter into an HBM difference
+ * array), 3 = packed8 (the region's only batch is packed8: read as it is, no int32 copy, no per-segment index). */
 int  gl_depth_last_path(gl_ctx* ctx, int32_t* path);
-/* 0 = choose automatically (default), 2 = always take the general path (tests, comparison runs). */
+/* 0 = choose automatically (default), 1 = never the packed8 kernel, 2 = always the general path (tests, comparison runs). */
 int  gl_depth_set_path(gl_ctx* ctx, int32_t path);
 
 /* Fetch results (host buffers).  run_end may be NULL (run i ends where run i+1 starts; the last

@@ -18,11 +18,20 @@ def rand_segments(rng, n, lo, hi, maxlen=300):
     return s, e
 
 
-def _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device, expect_path, exp):
+def _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device, expect_path, exp, packed8=False):
     exp_depth, es, em, ea, ec = exp
     ctx.depth_begin(rs, re)
     bufs = []
-    if device:
+    if packed8:
+        a, d, ln = capi.pack_segments8(s, e)
+        if device and a.size:
+            bufs = [ctx.dev_array(a), ctx.dev_array(d), ctx.dev_array(ln)]
+            ctx.depth_add_segments_packed8_device(bufs[0], bufs[1], bufs[2], a.size)
+        else:
+            ctx.depth_add_segments_packed8(a, d, ln)
+        if a.size == 0:
+            expect_path = None
+    elif device:
         ds, de = ctx.dev_array(s), ctx.dev_array(e)
         bufs = [ds, de]
         ctx.depth_add_segments_device(ds, de, s.size)
@@ -71,6 +80,14 @@ def check_region(ctx, s, e, rs, re, W, mincov=4, maxmean=0, run_break=0, device=
             _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device, 2, exp)
         finally:
             ctx.depth_set_path(0)
+    # the packed8 kernel (any input packs: long segments are cut, order does not matter), then the same packed batch
+    # unpacked and taken through the int32 paths
+    _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device, 3, exp, packed8=True)
+    ctx.depth_set_path(1)
+    try:
+        _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device, None, exp, packed8=True)
+    finally:
+        ctx.depth_set_path(0)
     ws, r0, rc = out
     return exp_depth, ws, r0, rc
 
@@ -273,6 +290,18 @@ def test_full_size_chr20(ctx):
     assert np.array_equal(ws2, es) and np.array_equal(wm2, em)
     ctx.depth_set_path(0)
     ds.free(); de.free()
+    # the packed8 kernel at full size, packed words resident on the device
+    a, d, ln = capi.pack_segments8(s, e)
+    bufs = [ctx.dev_array(a), ctx.dev_array(d), ctx.dev_array(ln)]
+    ctx.depth_begin(0, L)
+    ctx.depth_add_segments_packed8_device(bufs[0], bufs[1], bufs[2], a.size)
+    ctx.depth_reduce(W, 4, 0, 10_000_000)
+    assert ctx.depth_last_path() == 3
+    assert np.array_equal(ctx.depth_get_windows(), es)
+    r0, rc = ctx.depth_get_runs()
+    assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
+    for b in bufs:
+        b.free()
 
 
 def test_packed16_path(ctx):
@@ -311,7 +340,7 @@ def test_packed8_path(ctx):
     es, _ = orc.window_sums(exp, 0, L, 500)
     ea, ec = orc.class_runs(exp, 0, L, 4, 0, 1_000_000)
     ws, r0, rc = ctx.depth_region_packed8(0, L, a, d, ln, 500, 4, 0, run_break=1_000_000)
-    assert ctx.depth_last_path() == 1
+    assert ctx.depth_last_path() == 3
     assert np.array_equal(ws, es) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
     # an int32 batch of odd length first (the packed8 unpack realigns the store), then packed8 + packed16 batches; clipping
     h = s.size // 3 | 1
@@ -334,8 +363,27 @@ def test_packed8_path(ctx):
     a, d, ln = capi.pack_segments8(s, e)
     exp = orc.pileup_diff(s, e, 500, 2_900_000)
     ws, r0, rc = ctx.depth_region_packed8(500, 2_900_000, a, d, ln, 333, 4, 0)
+    assert ctx.depth_last_path() == 3
     ea, ec = orc.class_runs(exp, 500, 2_900_000, 4, 0, 0)
     assert np.array_equal(ws, orc.window_sums(exp, 500, 2_900_000, 333)[0]) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
+
+
+def test_packed8_unsorted_anchors_fall_back(ctx):
+    """hand-made packed8 blocks whose anchors are not sorted: K_tileidx8 notices, the batch is unpacked and the int32
+    paths give the right integers"""
+    L = 400_000
+    s, e = synth.segments(synth.reads(L, contig_index=2))
+    a, d, ln = capi.pack_segments8(s, e)
+    nb = a.size
+    perm = np.random.default_rng(0).permutation(nb)
+    a2 = np.ascontiguousarray(a[perm])
+    d2 = np.ascontiguousarray(d.reshape(nb, 64)[perm]).reshape(-1)
+    l2 = np.ascontiguousarray(ln.reshape(nb, 64)[perm]).reshape(-1)
+    exp = orc.pileup_diff(s, e, 0, L)
+    ws, r0, rc = ctx.depth_region_packed8(0, L, a2, d2, l2, 500, 4, 0)
+    assert ctx.depth_last_path() in (1, 2)
+    ea, ec = orc.class_runs(exp, 0, L, 4, 0, 0)
+    assert np.array_equal(ws, orc.window_sums(exp, 0, L, 500)[0]) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
 
 
 def test_chr1_sized_contig(ctx):
