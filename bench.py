@@ -10,9 +10,10 @@ Workload at N=1 = BASELINE config[1]: synthetic 30x chr20 (64,444,167 bp, 150 bp
 At N>1 every rank processes its own chr20-sized contig (contigs shard across GPUs with no
 data-path collective) -> weak scaling; value = N * bases / max-over-ranks device time.
 
-value  : inputs already resident in HBM (segments uploaded before the timed region).
+value  : inputs already resident in HBM in the engine's segment format (packed8) before the timed region;
+         int32_resident: the same from plain int32 (start,end) device arrays.
 e2e    : the one-call C-ABI entry gl_depth_region_packed8 (the feeder's short-read format, 2 B/segment) with
-         PINNED HOST buffers: H2D of the segments, unpack, all kernels and D2H of window sums + runs are inside the
+         PINNED HOST buffers: H2D of the segments, all kernels and D2H of window sums + runs are inside the
          timed region, every step.  e2e_packed16 / e2e_int32: the same through the 4 B and 8 B/segment entries.
 roofline / cpu_baseline: see DESIGN.md §Measurement.
 """
@@ -210,9 +211,18 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    def step_resident():
+    def step_resident_int32():
         ctx.depth_begin(0, L)
         ctx.depth_add_segments_device(d_s, d_e, nseg)
+        ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP)
+
+    # the engine's native segment format (packed8: 64-slot blocks, uint8 start delta + uint8 length), resident in HBM
+    qa, qd, ql = capi.pack_segments8(s, e)
+    d_qa, d_qd, d_ql = ctx.dev_array(qa), ctx.dev_array(qd), ctx.dev_array(ql)
+
+    def step_resident():
+        ctx.depth_begin(0, L)
+        ctx.depth_add_segments_packed8_device(d_qa, d_qd, d_ql, qa.size)
         ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP)
 
     # pinned host buffers for the end-to-end arm
@@ -236,8 +246,7 @@ def main():
     def step_e2e_p16():
         return ctx.depth_region_packed16(0, L, h_a, h_o, h_l, W, MINCOV, MAXMEAN, STEP, out=(o_sum, o_rs, o_rc))
 
-    # the feeder's densest format for short reads (packed8: uint8 start delta + uint8 length = 2 B/segment)
-    qa, qd, ql = capi.pack_segments8(s, e)
+    # the same packed8 words in pinned host memory for the end-to-end arm
     h8_a, h8_d, h8_l = ctx.pinned_empty(qa.size, np.int32), ctx.pinned_empty(qd.size, np.uint8), ctx.pinned_empty(ql.size, np.uint8)
     h8_a[:] = qa
     h8_d[:] = qd
@@ -250,6 +259,7 @@ def main():
     # ---- warm-up (also sizes every grow-only buffer)
     for _ in range(args.warmup):
         step_resident()
+        step_resident_int32()
     ws, r0, rc = step_e2e()
     n_runs = int(r0.size)
     for _ in range(max(0, args.warmup - 1)):
@@ -274,6 +284,13 @@ def main():
         step_resident()
         ms += ctx.timer_stop_ms()
     launches = ctx.launch_count() - l0
+    barrier()
+    ms_int32 = 0.0
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        step_resident_int32()
+        ms_int32 += ctx.timer_stop_ms()
     barrier()
 
     # ---- timed: end to end through the C ABI with pinned host buffers (H2D + kernels + D2H inside)
@@ -311,13 +328,14 @@ def main():
 
     # ---- per-kernel live timing for the roofline: CUDA events on the launching stream around every
     #      kernel of the same step (library-side, gl_profile_*), averaged over the repetitions
-    def kernel_times(reps):
+    def kernel_times(reps, step=None):
+        step = step or step_resident
         ctx.profile_enable(True)
         ctx.profile_read()
         acc = {}
         for _ in range(reps):
             ctx.flush_l2()
-            step_resident()
+            step()
             for nm, t in ctx.profile_read():
                 acc.setdefault(nm, []).append(t)
         ctx.profile_enable(False)
@@ -326,26 +344,27 @@ def main():
     reps = max(5, min(args.steps, 20))
     k_ms = kernel_times(reps)
     path = ctx.depth_last_path()
+    k_ms_int32 = kernel_times(reps, step_resident_int32)
     # the general (scatter) path on the same input, for the record
     ctx.depth_set_path(2)
     for _ in range(2):
-        step_resident()
+        step_resident_int32()
     ms_general = 0.0
     for _ in range(reps):
         ctx.flush_l2()
         ctx.timer_start()
-        step_resident()
+        step_resident_int32()
         ms_general += ctx.timer_stop_ms() / reps
-    k_ms_general = kernel_times(reps)
+    k_ms_general = kernel_times(reps, step_resident_int32)
     ctx.depth_set_path(0)
     clocks = sampler.stop() if rank == 0 else None
 
     os.environ.setdefault("NCCL_DEBUG", "WARN")
     if dist is not None:
         import torch
-        t = torch.tensor([ms, ms_e2e, ms_e2e_int32, ms_e2e_p16], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, ms_e2e, ms_e2e_int32, ms_e2e_p16, ms_int32], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_e2e_int32, ms_e2e_p16 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        ms, ms_e2e, ms_e2e_int32, ms_e2e_p16, ms_int32 = (float(x) for x in t)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -357,7 +376,10 @@ def main():
         # runs (5 B/run); K_index reads the same 8 B/segment and writes the 4 B/cell offset table.
         # general path: memset 4L, scatter 8 B/segment read + two int32 updates, scan 4L read.
         ncells = L // 256 + 66
-        alg = {"depth_fused_kernel": 8 * nseg + 8 * n_win + 5 * n_runs,
+        p8_bytes = int(qa.nbytes + qd.nbytes + ql.nbytes)
+        alg = {"depth_fused8_kernel": p8_bytes + 8 * n_win + 5 * n_runs,
+               "depth_tileidx8_kernel": int(qa.nbytes) + 8 * ((L - 1) // 4096 + 1),
+               "depth_fused_kernel": 8 * nseg + 8 * n_win + 5 * n_runs,
                "depth_index_kernel": 8 * nseg + 4 * ncells,
                "depth_scan_kernel": 4 * L + 8 * n_win + 5 * n_runs,
                "depth_scatter_kernel": 16 * nseg,
@@ -373,7 +395,9 @@ def main():
                "config": {"workload": "depth: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500, 1 sample per GPU",
                           "window": W, "mincov": MINCOV, "run_break": STEP, "segments_per_gpu": nseg,
                           "windows_per_gpu": n_win, "runs_per_gpu": n_runs, "contigs": world,
-                          "path": {1: "fused (sorted segments -> smem difference tiles)", 2: "general (HBM difference array)"}.get(path, str(path)),
+                          "resident_format": "packed8 (64-slot blocks: int32 anchor + uint8 start delta + uint8 length per segment), %d bytes" % p8_bytes,
+                          "path": {1: "fused (sorted int32 segments -> smem difference tiles)", 2: "general (HBM difference array)",
+                                   3: "packed8 (packed words -> smem difference tiles)"}.get(path, str(path)),
                           "l2": "L2 flushed (256 MiB memset) before every timed step; per-step CUDA-event times summed"},
                "e2e": {"value": e2e_val, "unit": "Mbases/s", "h2d_bytes_per_step": packed8_bytes,
                        "d2h_bytes_per_step": 8 * n_win + 5 * n_runs, "ms_per_step": ms_e2e / args.steps,
@@ -391,20 +415,23 @@ def main():
                             # contract definition: SURVEY.md §8(d)'s algorithmic bytes x the units one launch processes.
                             # The dominant kernel (K_fused) performs that whole per-base pipeline (difference array, scan,
                             # window reduce, class runs) on chip, so this is its EFFECTIVE bandwidth ...
-                            "achieved": survey_bytes / (k_ms[dom] * 1e-3) / 1e9 if dom == "depth_fused_kernel" else achieved,
-                            "frac": (survey_bytes / (k_ms[dom] * 1e-3) / 1e9 if dom == "depth_fused_kernel" else achieved) / peak,
-                            "alg_bytes_per_launch": survey_bytes if dom == "depth_fused_kernel" else alg[dom],
+                            "achieved": survey_bytes / (k_ms[dom] * 1e-3) / 1e9 if dom in ("depth_fused_kernel", "depth_fused8_kernel") else achieved,
+                            "frac": (survey_bytes / (k_ms[dom] * 1e-3) / 1e9 if dom in ("depth_fused_kernel", "depth_fused8_kernel") else achieved) / peak,
+                            "alg_bytes_per_launch": survey_bytes if dom in ("depth_fused_kernel", "depth_fused8_kernel") else alg[dom],
                             "basis": "SURVEY.md 8(d): 8*N_seg + 8*L + 12*ceil(L/W) + 9*runs (HBM difference-array pipeline); "
                                      "effective bandwidth of the kernel that does that pipeline's work",
                             # ... and these are the bytes the kernel itself has to move, with the ncu DRAM traffic beside them:
                             "own": {"alg_bytes_per_launch": alg[dom], "achieved": achieved, "frac": achieved / peak,
-                                    "note": "8 B/segment in + 8 B/window + 5 B/run out: the 8 B/base difference array never "
+                                    "note": "packed segment words in + 8 B/window + 5 B/run out: the 8 B/base difference array never "
                                             "exists in HBM, so the kernel is latency/issue-bound, not HBM-bound "
                                             "(ncu: profiles/r01_ncu_full_summary.json)"},
                             "traffic": ncu_traffic(dom), "kernel_ms": k_ms,
                             "step": {"survey_alg_bytes": survey_bytes, "achieved": survey_bytes / (ms_step * 1e-3) / 1e9,
                                      "frac": survey_bytes / (ms_step * 1e-3) / 1e9 / peak,
                                      "own_alg_bytes": step_bytes, "own_achieved": step_bytes / (ms_step * 1e-3) / 1e9}},
+               "int32_resident": {"ms_per_step": ms_int32 / args.steps, "value": world * L / (ms_int32 / args.steps * 1e-3) / 1e6,
+                                  "kernel_ms": k_ms_int32,
+                                  "note": "same region from plain int32 (start,end) device arrays: K_index + K_fused + K_gather"},
                "general_path": {"ms_per_step": ms_general, "value": world * L / (ms_general * 1e-3) / 1e6,
                                 "kernel_ms": k_ms_general, "dominant": gdom,
                                 "achieved": alg[gdom] / (k_ms_general[gdom] * 1e-3) / 1e9,
@@ -424,7 +451,7 @@ def main():
                                              "samtools text print/parse excluded"}
         print(json.dumps(out), flush=True)
 
-    d_s.free(); d_e.free()
+    d_s.free(); d_e.free(); d_qa.free(); d_qd.free(); d_ql.free()
     ctx.close()
     if dist is not None:
         dist.barrier()

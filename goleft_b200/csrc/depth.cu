@@ -329,8 +329,10 @@ struct ScanParams {
     const unsigned* p8_ds;        // [p8_nblocks*16] 4 uint8 start deltas per word
     const unsigned* p8_len;       // [p8_nblocks*16] 4 uint8 lengths per word
     int p8_nblocks;
-    int* tile_lo;                 // [num_tiles] first / one-past-last block that can touch the tile
-    int* tile_hi;
+    int* tile_lo;                 // [num_tiles+1] number of anchors < x_k - 255, x_k = rs + k*4096
+    int* tile_hi;                 // [num_tiles+1] number of anchors < x_k
+    int tile_begin, tile_end;     // K_fused8 processes these tiles (a streamed upload launches it once per arrived chunk)
+    int idx_begin, idx_end;       // K_tileidx8 handles the anchor gaps i in [idx_begin, idx_end), i = -1 .. nb-1
 };
 
 __device__ __forceinline__ int cov_class(int d, int mincov, int maxmean) {
@@ -761,27 +763,47 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const Scan
 // packed8 path.  The segments arrive sorted by start in 64-slot blocks with sorted anchors and lengths <= 255,
 // so the blocks a tile needs follow from the anchors alone: no per-segment index pass, no int32 copy of the
 // segments in HBM, a quarter of the segment bytes read.
-// K_tileidx8: per tile the block range [lo,hi): blocks that may hold a start in [t0-255, t1).  Block b's starts lie in
-// [anchor[b], anchor[b+1]], so lo = (#anchors < t0-255) - 1 and hi = #anchors < t1.  Also verifies the anchors' order.
+// K_tileidx8: for every tile boundary x_k = rs + k*4096 (k = 0..T) the number of anchors < x_k (cnt_hi[k]) and the number
+// of anchors < x_k - 255 (cnt_lo[k]).  Block b's starts lie in [anchor[b], anchor[b+1]] and lengths are <= 255, so tile k
+// needs the blocks [max(0, cnt_lo[k] - 1), cnt_hi[k+1]).  No search: thread i owns the gap (anchor[i], anchor[i+1]]
+// (i = -1 and nb-1 own the open ends) and writes i+1 for every boundary inside it — usually none, one in ~13 threads
+// writes one.  Also verifies that the anchors are sorted.
 // ================================================================================================
+__device__ __forceinline__ long long floordiv_tile(long long x) { return x >> kTileShift; }   // arithmetic shift = floor
+
 __global__ void __launch_bounds__(256) depth_tileidx8_kernel(const ScanParams p) {
-    const int t = blockIdx.x * 256 + threadIdx.x;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x + p.idx_begin;
+    const int lane = threadIdx.x & 31;
     const int nb = p.p8_nblocks;
-    for (int i = t; i + 1 < nb; i += gridDim.x * 256)
-        if (p.p8_anchors[i] > p.p8_anchors[i + 1]) p.header[3] = 1;
-    if (t >= p.num_tiles) return;
-    const long long t0 = (long long)p.rs + (long long)t * kTile;
-    const long long t1 = min(t0 + kTile, (long long)p.re);
-    auto count_less = [&](long long x) {                    // number of anchors < x
-        int lo = 0, hi = nb;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((long long)p.p8_anchors[mid] < x) lo = mid + 1; else hi = mid;
+    const int T = p.num_tiles;
+    long long h0 = 1, h1 = 0, l0 = 1, l1 = 0;                               // empty ranges
+    if (i < p.idx_end) {
+        const long long lo_x = i >= 0 ? (long long)p.p8_anchors[i] : LLONG_MIN / 2;
+        const long long hi_x = i + 1 < nb ? (long long)p.p8_anchors[i + 1] : LLONG_MAX / 2;
+        if (lo_x > hi_x) p.header[3] = 1;                                   // unsorted anchors: the host falls back
+        else {
+            // boundaries x_k with lo_x < x_k <= hi_x, and the same for x_k - 255
+            h0 = max(0ll, floordiv_tile(lo_x - p.rs) + 1); h1 = min((long long)T, floordiv_tile(hi_x - p.rs));
+            l0 = max(0ll, floordiv_tile(lo_x - p.rs + 255) + 1); l1 = min((long long)T, floordiv_tile(hi_x - p.rs + 255));
         }
-        return lo;
-    };
-    p.tile_lo[t] = max(0, count_less(t0 - 255) - 1);
-    p.tile_hi[t] = count_less(t1);
+    }
+    const int v = (int)(i + 1);
+    // a gap without coverage (centromere, contig ends) spans many boundaries: the warp writes those together
+    const bool longr = (h1 - h0 > 2) || (l1 - l0 > 2);
+    unsigned m = __ballot_sync(kFull, longr);
+    if (!longr) {
+        for (long long k = h0; k <= h1; k++) p.tile_hi[k] = v;
+        for (long long k = l0; k <= l1; k++) p.tile_lo[k] = v;
+    }
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const long long a0 = __shfl_sync(kFull, h0, src), a1 = __shfl_sync(kFull, h1, src);
+        const long long b0 = __shfl_sync(kFull, l0, src), b1 = __shfl_sync(kFull, l1, src);
+        const int vv = __shfl_sync(kFull, v, src);
+        for (long long k = a0 + lane; k <= a1; k += 32) p.tile_hi[k] = vv;
+        for (long long k = b0 + lane; k <= b1; k += 32) p.tile_lo[k] = vv;
+    }
 }
 
 struct P8Regs { unsigned d, l; int anchor; };
@@ -827,14 +849,15 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused8_kernel(const Sca
     if (p.header[3] != 0) return;                           // K_tileidx8 found unsorted anchors: the host falls back
 #pragma unroll
     for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);   // later tiles: cleared by the core
-    int tile = blockIdx.x;
+    int tile = p.tile_begin + blockIdx.x;
+    const int nb = p.p8_nblocks;                            // (clamps: garbage ranges of a rejected input stay in bounds)
     int lo = 0, hi = 0, lo2 = 0, hi2 = 0;
-    if (tile < p.num_tiles) { lo = p.tile_lo[tile]; hi = p.tile_hi[tile]; }
-    if (tile + G < p.num_tiles) { lo2 = p.tile_lo[tile + G]; hi2 = p.tile_hi[tile + G]; }
+    if (tile < p.tile_end) { lo = max(0, p.tile_lo[tile] - 1); hi = min(nb, p.tile_hi[tile + 1]); }
+    if (tile + G < p.tile_end) { lo2 = max(0, p.tile_lo[tile + G] - 1); hi2 = min(nb, p.tile_hi[tile + G + 1]); }
     P8Regs regs = fused8_load(p, lo, hi, 0);
     __syncthreads();
 
-    for (int it = 0; tile < p.num_tiles; tile += G, it ^= 1) {
+    for (int it = 0; tile < p.tile_end; tile += G, it ^= 1) {
         int* s_carry = s_carry2[it];
         const int t0 = p.rs + tile * kTile, t1 = min(t0 + kTile, p.re);
         const bool first_tile = tile == 0;
@@ -848,7 +871,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused8_kernel(const Sca
         lo = lo2; hi = hi2;
         regs = fused8_load(p, lo, hi, 0);                   // next tile's packed words: in flight during the core
         lo2 = hi2 = 0;
-        if (tile + 2 * G < p.num_tiles) { lo2 = p.tile_lo[tile + 2 * G]; hi2 = p.tile_hi[tile + 2 * G]; }
+        if (tile + 2 * G < p.tile_end) { lo2 = max(0, p.tile_lo[tile + 2 * G] - 1); hi2 = min(nb, p.tile_hi[tile + 2 * G + 1]); }
         tile_core<true>(p, s_tile, s_depth, s_carry, tile);
     }
 }
@@ -997,9 +1020,39 @@ int read_header(gl_ctx* ctx, uint64_t hdr[4]) {
     return GL_OK;
 }
 
+constexpr int kP8ChunksMax = 32;
+static int p8_chunks() {                                       // streamed upload: chunks per region (GL_P8_CHUNKS=1 turns streaming off)
+    static int k = [] { const char* e = getenv("GL_P8_CHUNKS"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > kP8ChunksMax ? kP8ChunksMax : v); }();
+    return k;
+}
+// Chunk c of K ends at this block.  Every copy costs ~10 us of DMA set-up, and only the LAST chunk's reduce is exposed
+// (the others hide behind the next copy), so the chunks halve in size: 8/15, 4/15, 2/15, 1/15 for K = 4.
+static int64_t p8_chunk_end(int64_t nb, int c, int K) {
+    if (c >= K - 1) return nb;
+    const double total = (double)((1ll << K) - 1);
+    double acc = 0;
+    for (int j = 0; j <= c; j++) acc += (double)(1ll << (K - 1 - j));
+    return std::min<int64_t>(nb, (int64_t)((double)nb * acc / total));
+}
+
+// a packed8 batch whose upload was deferred (gl_depth_region_packed8): copy all of it now, in one piece
+int p8_finish_upload(gl_ctx* ctx) {
+    if (!ctx->p8.upload_pending) return GL_OK;
+    const size_t nb = (size_t)ctx->p8.n_blocks;
+    GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
+    GL_CUDA(ctx, cudaMemcpyAsync(const_cast<int*>(ctx->p8.anchors), ctx->p8.h_anchors, nb * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    GL_CUDA(ctx, cudaMemcpyAsync(const_cast<void*>(ctx->p8.ds), ctx->p8.h_ds, nb * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+    GL_CUDA(ctx, cudaMemcpyAsync(const_cast<void*>(ctx->p8.len), ctx->p8.h_len, nb * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+    GL_CUDA(ctx, cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
+    GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
+    ctx->p8.upload_pending = false;
+    return GL_OK;
+}
+
 // packed8 batch -> int32 arrays in the store (only when something needs them: another batch, a forced path, ...)
 int p8_materialize(gl_ctx* ctx) {
     if (!ctx->p8.pending) return GL_OK;
+    GL_CHECK(p8_finish_upload(ctx));
     {
         gl_prof_scope prof(ctx, "depth_unpack8_kernel");
         depth_unpack8_kernel<<<(unsigned)((ctx->p8.n_blocks + 31) / 32), 256, 0, ctx->stream>>>(
@@ -1029,7 +1082,7 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
     const size_t win_bytes = al(do_windows ? (size_t)n_windows * 8 : 0);
     const size_t zero_bytes = head_bytes + win_bytes;
     const size_t run_bytes = al((size_t)chunks * 8);
-    GL_CHECK(gl_buf_reserve(ctx, ctx->scratch, zero_bytes + run_bytes + 2 * al((size_t)tiles * 4)));
+    GL_CHECK(gl_buf_reserve(ctx, ctx->scratch, zero_bytes + run_bytes + 2 * al((size_t)(tiles + 1) * 4)));
     if (do_runs && ctx->run_start.cap == 0) {
         size_t cap = (size_t)(len / 16 + 4096);
         GL_CHECK(gl_buf_reserve(ctx, ctx->run_start, cap * 4));
@@ -1065,7 +1118,7 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
     p.p8_len = static_cast<const unsigned*>(ctx->p8.len);
     p.p8_nblocks = (int)ctx->p8.n_blocks;
     p.tile_lo = reinterpret_cast<int*>(sbase + zero_bytes + run_bytes);
-    p.tile_hi = reinterpret_cast<int*>(sbase + zero_bytes + run_bytes + al((size_t)tiles * 4));
+    p.tile_hi = reinterpret_cast<int*>(sbase + zero_bytes + run_bytes + al((size_t)(tiles + 1) * 4));
     p.win_sum = static_cast<unsigned long long*>(ctx->win_sum_p);
     p.win_min = (do_windows && want_min) ? static_cast<int*>(ctx->win_min.p) : nullptr;
 
@@ -1082,16 +1135,60 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
         p.run_cap = cap;
         GL_CUDA(ctx, cudaMemsetAsync(sbase, 0, zero_bytes, ctx->stream));
         if (do_windows && want_min) GL_CUDA(ctx, cudaMemsetAsync(ctx->win_min.p, 0x7f, (size_t)n_windows * 4, ctx->stream));
-        {
-            gl_prof_scope prof(ctx, "depth_tileidx8_kernel");
-            depth_tileidx8_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, ctx->stream>>>(p);
+        // One pass over everything that is on the device — or, when the upload was deferred, chunk by chunk: the words
+        // are sorted by position, so once a chunk has landed every tile that ends before its last anchor can be reduced
+        // while the next chunk is still on the wire.
+        const int64_t nb = ctx->p8.n_blocks;
+        const bool streamed = ctx->p8.upload_pending;
+        const int n_chunks = streamed ? p8_chunks() : 1;
+        if (streamed) {
+            while ((int)ctx->ev_chunk.size() < n_chunks) {
+                cudaEvent_t ev;
+                GL_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                ctx->ev_chunk.push_back(ev);
+            }
+            GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));   // previous consumer done with the staging buffer
         }
-        GL_LAUNCHED(ctx, 1);
-        {
-            gl_prof_scope prof(ctx, "depth_fused8_kernel");
-            depth_fused8_kernel<<<(unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 4), kScanThreads, 0, ctx->stream>>>(p);
+        int64_t b0 = 0, t_prev = 0;
+        for (int c = 0; c < n_chunks; c++) {
+            const bool last = c == n_chunks - 1;
+            const int64_t b1 = p8_chunk_end(nb, c, n_chunks);
+            if (b1 <= b0 && !last) continue;
+            if (streamed && b1 > b0) {
+                const size_t nbk = (size_t)(b1 - b0);
+                GL_CUDA(ctx, cudaMemcpyAsync(const_cast<int*>(ctx->p8.anchors) + b0, ctx->p8.h_anchors + b0, nbk * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+                GL_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(const_cast<void*>(ctx->p8.ds)) + b0 * 64, static_cast<const char*>(ctx->p8.h_ds) + b0 * 64,
+                                             nbk * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+                GL_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(const_cast<void*>(ctx->p8.len)) + b0 * 64, static_cast<const char*>(ctx->p8.h_len) + b0 * 64,
+                                             nbk * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+                GL_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+                GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0));
+            }
+            // anchor gaps this chunk completes: (a[i], a[i+1]] for i in [b0-1, b1-1), plus the open end after the last anchor
+            p.idx_begin = (int)(b0 - 1);
+            p.idx_end = (int)(last ? nb : b1 - 1);
+            if (p.idx_end > p.idx_begin) {
+                gl_prof_scope prof(ctx, "depth_tileidx8_kernel");
+                depth_tileidx8_kernel<<<(unsigned)((p.idx_end - p.idx_begin + 255) / 256), 256, 0, ctx->stream>>>(p);
+                GL_LAUNCHED(ctx, 1);
+            }
+            // tiles whose end boundary is not beyond the last anchor on the device are complete
+            int64_t t_ready = tiles;
+            if (!last) {
+                const int64_t a_last = streamed ? (int64_t)ctx->p8.h_anchors[b1 - 1] : 0;
+                t_ready = std::min<int64_t>(tiles, std::max<int64_t>(t_prev, (a_last - ctx->rs) >> kTileShift));
+            }
+            if (t_ready > t_prev) {
+                p.tile_begin = (int)t_prev;
+                p.tile_end = (int)t_ready;
+                gl_prof_scope prof(ctx, "depth_fused8_kernel");
+                depth_fused8_kernel<<<(unsigned)std::min<int64_t>(t_ready - t_prev, (int64_t)ctx->sm_count * 4), kScanThreads, 0, ctx->stream>>>(p);
+                GL_LAUNCHED(ctx, 1);
+            }
+            t_prev = t_ready;
+            b0 = b1;
         }
-        GL_LAUNCHED(ctx, 1);
+        ctx->p8.upload_pending = false;
         GL_CUDA(ctx, cudaEventRecord(ctx->ev_used[0], ctx->stream));      // the packed staging buffer may be overwritten after this
         if (do_runs) {
             gl_prof_scope prof(ctx, "depth_gather_runs_kernel");
@@ -1100,9 +1197,23 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
                 static_cast<unsigned char*>(ctx->run_class.p), cap);
             GL_LAUNCHED(ctx, 1);
         }
+        ctx->prefetched = false;
+        if (ctx->prefetch_sums && do_windows && n_windows <= ctx->prefetch_cap) {   // sums travel while the header is read
+            GL_CUDA(ctx, cudaMemcpyAsync(ctx->prefetch_sums, ctx->win_sum_p, (size_t)n_windows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->prefetched = true;
+        }
+        ctx->prefetched_runs = 0;
+        if (ctx->prefetch_run_start && ctx->prefetch_run_class && do_runs) {       // ... and so do the first runs (usually all of them)
+            const int64_t k = std::min<int64_t>(std::min<int64_t>(ctx->prefetch_run_cap, 16384), (int64_t)cap);
+            if (k > 0) {
+                GL_CUDA(ctx, cudaMemcpyAsync(ctx->prefetch_run_start, ctx->run_start.p, (size_t)k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                GL_CUDA(ctx, cudaMemcpyAsync(ctx->prefetch_run_class, ctx->run_class.p, (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+                ctx->prefetched_runs = k;
+            }
+        }
         uint64_t hdr[4];
         GL_CHECK(read_header(ctx, hdr));
-        if (hdr[3] != 0) return GL_OK;                                     // anchors not sorted: not accepted
+        if (hdr[3] != 0) { ctx->prefetched = false; ctx->prefetched_runs = 0; return GL_OK; }        // anchors not sorted: not accepted
         ctx->n_runs = do_runs ? (int64_t)hdr[0] : 0;
         ctx->max_depth = (int32_t)hdr[2];
         if (do_runs && (long long)hdr[0] > cap) {                          // output did not fit: grow and rerun
@@ -1261,9 +1372,23 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
             GL_LAUNCHED(ctx, 1);
         }
 
+        ctx->prefetched = false;
+        if (ctx->prefetch_sums && do_windows && n_windows <= ctx->prefetch_cap) {   // sums travel while the header is read
+            GL_CUDA(ctx, cudaMemcpyAsync(ctx->prefetch_sums, ctx->win_sum_p, (size_t)n_windows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->prefetched = true;
+        }
+        ctx->prefetched_runs = 0;
+        if (ctx->prefetch_run_start && ctx->prefetch_run_class && do_runs) {       // ... and so do the first runs (usually all of them)
+            const int64_t k = std::min<int64_t>(std::min<int64_t>(ctx->prefetch_run_cap, 16384), (int64_t)cap);
+            if (k > 0) {
+                GL_CUDA(ctx, cudaMemcpyAsync(ctx->prefetch_run_start, ctx->run_start.p, (size_t)k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                GL_CUDA(ctx, cudaMemcpyAsync(ctx->prefetch_run_class, ctx->run_class.p, (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+                ctx->prefetched_runs = k;
+            }
+        }
         uint64_t hdr[4];
         GL_CHECK(read_header(ctx, hdr));
-        if (fused && hdr[3] != 0) { try_fused = false; continue; }        // not in BAM order / segments too long
+        if (fused && hdr[3] != 0) { try_fused = false; ctx->prefetched = false; ctx->prefetched_runs = 0; continue; }        // not in BAM order / segments too long
         ctx->last_path = fused ? 1 : 2;
         ctx->idx_flags = fused ? flags : nullptr;
         ctx->idx_cells = fused ? cells : nullptr;
@@ -1332,6 +1457,7 @@ int gl_depth_begin(gl_ctx* ctx, int64_t region_start, int64_t region_end) {
     ctx->batches.clear();
     ctx->store_n = 0;
     ctx->p8.pending = false;
+    ctx->p8.upload_pending = false;
     ctx->g_valid = false;
     ctx->depth_active = true;
     ctx->depth_reduced = false;
@@ -1484,7 +1610,13 @@ int gl_depth_add_segments_packed8_device(gl_ctx* ctx, const int32_t* d_anchors, 
     return p8_register(ctx, d_anchors, d_dstart, d_len, n_blocks);
 }
 
+static int add_packed8_host(gl_ctx* ctx, const int32_t* anchors, const uint8_t* dstart, const uint8_t* len, int64_t n_blocks, bool may_defer);
+
 int gl_depth_add_segments_packed8(gl_ctx* ctx, const int32_t* anchors, const uint8_t* dstart, const uint8_t* len, int64_t n_blocks) {
+    return add_packed8_host(ctx, anchors, dstart, len, n_blocks, false);
+}
+
+static int add_packed8_host(gl_ctx* ctx, const int32_t* anchors, const uint8_t* dstart, const uint8_t* len, int64_t n_blocks, bool may_defer) {
     GL_CHECK(gl_use(ctx));
     if (!ctx->depth_active) return gl_fail(ctx, GL_ESTATE, "gl_depth_add_segments_packed8: no region open (call gl_depth_begin)");
     if (n_blocks < 0 || (n_blocks > 0 && (!anchors || !dstart || !len))) return gl_fail(ctx, GL_EINVAL, "gl_depth_add_segments_packed8: bad argument");
@@ -1496,6 +1628,14 @@ int gl_depth_add_segments_packed8(gl_ctx* ctx, const int32_t* anchors, const uin
     char* d_ds = d_anchor + ((b_anchor + 255) & ~size_t(255));
     char* d_len = d_ds + ((b_u8 + 255) & ~size_t(255));
     const bool pinned = is_pinned_host(anchors) && is_pinned_host(dstart) && is_pinned_host(len);
+    if (may_defer && pinned && ctx->batches.empty() && ctx->force_path == 0 && n_blocks >= 4096) {
+        // one-call entry: the reduce follows at once, so let it stream the words in (chunk k+1 on the wire while chunk k's
+        // tiles are reduced)
+        GL_CHECK(p8_register(ctx, reinterpret_cast<const int*>(d_anchor), d_ds, d_len, n_blocks));
+        ctx->p8.h_anchors = anchors; ctx->p8.h_ds = dstart; ctx->p8.h_len = len;
+        ctx->p8.upload_pending = true;
+        return GL_OK;
+    }
     if (!pinned) GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));   // previous consumer done with the staging buffer
     GL_CUDA(ctx, cudaMemcpyAsync(d_anchor, anchors, b_anchor, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -1663,7 +1803,12 @@ int gl_depth_region_packed16(gl_ctx* ctx, int64_t region_start, int64_t region_e
                              int64_t run_cap, int64_t* n_runs) {
     GL_CHECK(gl_depth_begin(ctx, region_start, region_end));
     GL_CHECK(gl_depth_add_segments_packed16(ctx, anchors, off, len, n_blocks));
-    GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, run_break));
+    ctx->prefetch_sums = sum_out; ctx->prefetch_cap = sum_out ? win_cap : 0;
+    ctx->prefetch_run_start = run_start; ctx->prefetch_run_class = run_class; ctx->prefetch_run_cap = (run_start && run_class) ? run_cap : 0;
+    const int rc_reduce = gl_depth_reduce(ctx, W, mincov, maxmean, run_break);
+    ctx->prefetch_sums = nullptr; ctx->prefetch_cap = 0;
+    ctx->prefetch_run_start = nullptr; ctx->prefetch_run_class = nullptr; ctx->prefetch_run_cap = 0;
+    GL_CHECK(rc_reduce);
     return region_fetch(ctx, sum_out, win_cap, n_windows, run_start, run_class, run_cap, n_runs);
 }
 
@@ -1672,8 +1817,13 @@ int gl_depth_region_packed8(gl_ctx* ctx, int64_t region_start, int64_t region_en
                             int64_t* sum_out, int64_t win_cap, int64_t* n_windows, int32_t* run_start, uint8_t* run_class,
                             int64_t run_cap, int64_t* n_runs) {
     GL_CHECK(gl_depth_begin(ctx, region_start, region_end));
-    GL_CHECK(gl_depth_add_segments_packed8(ctx, anchors, dstart, len, n_blocks));
-    GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, run_break));
+    GL_CHECK(add_packed8_host(ctx, anchors, dstart, len, n_blocks, true));
+    ctx->prefetch_sums = sum_out; ctx->prefetch_cap = sum_out ? win_cap : 0;
+    ctx->prefetch_run_start = run_start; ctx->prefetch_run_class = run_class; ctx->prefetch_run_cap = (run_start && run_class) ? run_cap : 0;
+    const int rc_reduce = gl_depth_reduce(ctx, W, mincov, maxmean, run_break);
+    ctx->prefetch_sums = nullptr; ctx->prefetch_cap = 0;
+    ctx->prefetch_run_start = nullptr; ctx->prefetch_run_class = nullptr; ctx->prefetch_run_cap = 0;
+    GL_CHECK(rc_reduce);
     return region_fetch(ctx, sum_out, win_cap, n_windows, run_start, run_class, run_cap, n_runs);
 }
 
@@ -1683,7 +1833,12 @@ int gl_depth_region(gl_ctx* ctx, int64_t region_start, int64_t region_end, const
                     int64_t* n_runs) {
     GL_CHECK(gl_depth_begin(ctx, region_start, region_end));
     GL_CHECK(gl_depth_add_segments(ctx, start, end, n));
-    GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, run_break));
+    ctx->prefetch_sums = sum_out; ctx->prefetch_cap = sum_out ? win_cap : 0;
+    ctx->prefetch_run_start = run_start; ctx->prefetch_run_class = run_class; ctx->prefetch_run_cap = (run_start && run_class) ? run_cap : 0;
+    const int rc_reduce = gl_depth_reduce(ctx, W, mincov, maxmean, run_break);
+    ctx->prefetch_sums = nullptr; ctx->prefetch_cap = 0;
+    ctx->prefetch_run_start = nullptr; ctx->prefetch_run_class = nullptr; ctx->prefetch_run_cap = 0;
+    GL_CHECK(rc_reduce);
     return region_fetch(ctx, sum_out, win_cap, n_windows, run_start, run_class, run_cap, n_runs);
 }
 
@@ -1694,8 +1849,12 @@ static int region_fetch(gl_ctx* ctx, int64_t* sum_out, int64_t win_cap, int64_t*
     if (n_runs) *n_runs = nr;
     if (nw > win_cap) return gl_fail(ctx, GL_ERANGE, "gl_depth_region: %lld windows > cap %lld", (long long)nw, (long long)win_cap);
     if (nr > run_cap) return gl_fail(ctx, GL_ERANGE, "gl_depth_region: %lld runs > cap %lld", (long long)nr, (long long)run_cap);
-    GL_CUDA(ctx, cudaMemcpyAsync(sum_out, ctx->win_sum_p, (size_t)nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (nr > 0) {
+    const bool have_sums = ctx->prefetched, have_runs = ctx->prefetched_runs >= nr;
+    ctx->prefetched = false;
+    ctx->prefetched_runs = 0;
+    if (have_sums && have_runs) return GL_OK;                  // everything came home with the header (the reduce has synchronised)
+    if (!have_sums) GL_CUDA(ctx, cudaMemcpyAsync(sum_out, ctx->win_sum_p, (size_t)nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nr > 0 && !have_runs) {
         GL_CUDA(ctx, cudaMemcpyAsync(run_start, ctx->run_start.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, ctx->stream));
         GL_CUDA(ctx, cudaMemcpyAsync(run_class, ctx->run_class.p, (size_t)nr, cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -32,6 +32,7 @@ struct gl_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;         // gl_timer_*
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};      // staging ring
     cudaEvent_t ev_used[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_chunk;                // streamed packed8 upload: one per chunk
 
     // ---- depth state
     bool depth_active = false, depth_reduced = false;
@@ -51,9 +52,14 @@ struct gl_ctx {
     // a packed8 batch that is the region's only batch stays packed: K_fused8 reads it as it is (last_path 3); it is
     // unpacked into the store (its batch descriptor already points there) only when something needs int32 arrays
     struct { const int* anchors = nullptr; const void* ds = nullptr; const void* len = nullptr; int64_t n_blocks = 0, store_off = 0;
-             bool pending = false; } p8;
+             bool pending = false;
+             // upload deferred to the reduce (one-call entry with pinned host words): streamed in chunks, each chunk's
+             // tiles reduced while the next chunk is on the wire
+             const int* h_anchors = nullptr; const void* h_ds = nullptr; const void* h_len = nullptr; bool upload_pending = false; } p8;
     gl_buf diff;          // int32[len+1 (+pad)] + tile sums (general path only)
     void* win_sum_p = nullptr;   // u64[n_windows], inside `scratch`
+    int64_t* prefetch_sums = nullptr; int64_t prefetch_cap = 0; bool prefetched = false;   // one-call entries: window sums go home while the header is read
+    int32_t* prefetch_run_start = nullptr; uint8_t* prefetch_run_class = nullptr; int64_t prefetch_run_cap = 0, prefetched_runs = 0;   // and the first runs
     gl_buf win_min;       // i32[n_windows]
     gl_buf run_start;     // i32[run_cap]
     gl_buf run_class;     // u8[run_cap]

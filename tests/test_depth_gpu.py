@@ -368,6 +368,55 @@ def test_packed8_path(ctx):
     assert np.array_equal(ws, orc.window_sums(exp, 500, 2_900_000, 333)[0]) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
 
 
+def _pinned(ctx, *arrays):
+    out = []
+    for a in arrays:
+        h = ctx.pinned_empty(a.size, a.dtype)
+        h[:] = a
+        out.append(h)
+    return out
+
+
+def test_packed8_streamed_upload(ctx):
+    """one-call entry with pinned host words: the upload is streamed in chunks and every chunk's tiles are reduced while
+    the next chunk is on the wire — same integers; also a sparse region (few anchors per chunk), a region that starts
+    after the first chunks' data, and hand-shuffled blocks (rejected after streaming, unpacked, int32 paths)"""
+    L = 6_000_000
+    s, e = synth.segments(synth.reads(L, contig_index=11))
+    a, d, ln = capi.pack_segments8(s, e)
+    assert a.size >= 4096
+    ha, hd, hl = _pinned(ctx, a, d, ln)
+    for rs, re, W, brk in [(0, L, 500, 1_000_000), (4_500_000, L - 3, 333, 0), (0, 70_000, 100, 0)]:
+        exp = orc.pileup_diff(s, e, rs, re)
+        ws, r0, rc = ctx.depth_region_packed8(rs, re, ha, hd, hl, W, 4, 0, run_break=brk)
+        assert ctx.depth_last_path() == 3
+        ea, ec = orc.class_runs(exp, rs, re, 4, 0, brk)
+        assert np.array_equal(ws, orc.window_sums(exp, rs, re, W)[0]) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
+        got = ctx.depth_perbase(re - rs)                      # a second reduce of the same (now resident) batch
+        assert np.array_equal(got, exp)
+    # sparse: 1x coverage with long empty stretches
+    rng = np.random.default_rng(8)
+    s2 = np.sort(np.concatenate([rng.integers(0, 2_000_000, 300_000), rng.integers(40_000_000, 41_000_000, 100_000)])).astype(np.int32)
+    e2 = (s2 + rng.integers(30, 151, s2.size)).astype(np.int32)
+    a2, d2, l2 = capi.pack_segments8(s2, e2)
+    h2 = _pinned(ctx, a2, d2, l2)
+    exp = orc.pileup_diff(s2, e2, 0, 45_000_000)
+    ws, r0, rc = ctx.depth_region_packed8(0, 45_000_000, h2[0], h2[1], h2[2], 1000, 4, 0)
+    assert ctx.depth_last_path() == 3
+    ea, ec = orc.class_runs(exp, 0, 45_000_000, 4, 0, 0)
+    assert np.array_equal(ws, orc.window_sums(exp, 0, 45_000_000, 1000)[0]) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
+    # shuffled blocks through the streamed entry
+    nb = a.size
+    perm = rng.permutation(nb)
+    hs = _pinned(ctx, np.ascontiguousarray(a[perm]), np.ascontiguousarray(d.reshape(nb, 64)[perm]).reshape(-1),
+                 np.ascontiguousarray(ln.reshape(nb, 64)[perm]).reshape(-1))
+    exp = orc.pileup_diff(s, e, 0, L)
+    ws, r0, rc = ctx.depth_region_packed8(0, L, hs[0], hs[1], hs[2], 500, 4, 0)
+    assert ctx.depth_last_path() in (1, 2)
+    ea, ec = orc.class_runs(exp, 0, L, 4, 0, 0)
+    assert np.array_equal(ws, orc.window_sums(exp, 0, L, 500)[0]) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
+
+
 def test_packed8_unsorted_anchors_fall_back(ctx):
     """hand-made packed8 blocks whose anchors are not sorted: K_tileidx8 notices, the batch is unpacked and the int32
     paths give the right integers"""
