@@ -832,12 +832,111 @@ static int cmd_depthwed(int argc, char** argv) {
 }
 
 // ------------------------------------------------------------------------------------------------ dispatcher
+// ------------------------------------------------------------------------------------------------ indexsplit
+// indexsplit/indexsplit.go:24-30,197-216: N regions of about equal amounts of data across the cohort, from the indexes alone
+static int cmd_indexsplit(int argc, char** argv) {
+    std::string n, fai, problematic;
+    ArgParser ap;
+    ap.prog = "goleft indexsplit";
+    ap.add("n", 'n', &n, true); ap.add("fai", 0, &fai); ap.add("problematic", 'p', &problematic);
+    ap.parse(argc, argv);
+    if (ap.positional.empty()) ap.fail("indexes is required");
+    const std::vector<std::string>& paths = ap.positional;
+    const int N = atoi(n.c_str());
+
+    // references: from the first BAM's header, else from the .fai (the reference's ReadFai references carry ID -1 and
+    // Split indexes a slice with it; here a .fai reference's id is its position in the file)
+    struct Ref { std::string name; int64_t len; int id; };
+    std::vector<Ref> refs;
+    if (ends_with(paths[0], ".bam")) {
+        glhts::BamHeader h;
+        std::string e = glhts::bam_read_header(paths[0], h);
+        if (!e.empty()) fatal(1, "%s", e.c_str());
+        for (size_t i = 0; i < h.refs.size(); i++) refs.push_back({h.refs[i].name, h.refs[i].length, (int)i});
+    } else {
+        std::vector<glhts::RefInfo> r;
+        std::string e = glhts::fai_read(fai, r);
+        if (!e.empty()) fatal(1, "error opening fai: %s. Is is present?", fai.c_str());
+        std::stable_sort(r.begin(), r.end(), [](const glhts::RefInfo& a, const glhts::RefInfo& b) { return a.offset < b.offset; });   // indexcov.go:293
+        for (auto& x : r) refs.push_back({x.name, x.length, (int)refs.size()});
+    }
+    const int32_t R = (int32_t)refs.size();
+
+    gl_ctx* ctx = nullptr;
+    if (gl_ctx_create(0, &ctx) != GL_OK) fatal(1, "goleft indexsplit: %s", gl_last_error(nullptr));
+    const size_t S = paths.size();
+    std::vector<int64_t> all_sizes, ptr(S * (size_t)(R + 1), 0), max_len((size_t)R, 0);
+    for (size_t i = 0; i < S; i++) {                                        // indexcov.ReadIndex(path).Sizes(), indexsplit.go:92-93
+        const std::string& b = paths[i];
+        std::vector<int64_t> sz, sp;
+        if (ends_with(b, ".crai")) {
+            std::vector<glhts::CraiSlices> cr;
+            std::string e = glhts::crai_read(b, cr);
+            if (!e.empty()) fatal(1, "%s", e.c_str());
+            sp.assign(cr.size() + 1, 0);
+            for (size_t r = 0; r < cr.size(); r++) {
+                std::vector<int64_t> one;
+                if (!glhts::crai_make_sizes(cr[r].start.data(), cr[r].span.data(), cr[r].bytes.data(), (int64_t)cr[r].start.size(), one)) fatal(2, "panic: tilewidth logic error");
+                sz.insert(sz.end(), one.begin(), one.end());
+                sp[r + 1] = (int64_t)sz.size();
+            }
+        } else {
+            std::string p = ends_with(b, ".bai") ? b : b + ".bai";
+            if (!file_exists(p)) p = b.substr(0, b.size() - 4) + (ends_with(b, ".bai") ? "" : ".bai");
+            glhts::BaiIndex bai;
+            std::string e = glhts::bai_read(p, bai);
+            if (!e.empty()) fatal(1, "%s", e.c_str());
+            const size_t nr = bai.ioffsets.size();
+            std::vector<uint64_t> voff;
+            std::vector<int64_t> rp(nr + 1, 0);
+            for (size_t r = 0; r < nr; r++) { voff.insert(voff.end(), bai.ioffsets[r].begin(), bai.ioffsets[r].end()); rp[r + 1] = (int64_t)voff.size(); }
+            sz.resize(voff.size() + 1); sp.assign(nr + 1, 0);
+            glck(ctx, gl_indexcov_sizes(ctx, voff.data(), rp.data(), (int32_t)nr, sz.data(), sp.data()), "gl_indexcov_sizes");
+            sz.resize((size_t)sp[nr]);
+        }
+        if (sp.back() < 1) fatal(1, "indexcov: no usable chromsomes in bam: %s", b.c_str());     // Index.init, indexcov.go:100-102
+        const int64_t base = (int64_t)all_sizes.size();
+        const int32_t nr = (int32_t)sp.size() - 1;
+        for (int32_t r = 0; r <= R; r++) ptr[i * (size_t)(R + 1) + r] = base + sp[(size_t)std::min(r, nr)];
+        for (int32_t r = 0; r < R && r < nr; r++) max_len[(size_t)r] = std::max(max_len[(size_t)r], sp[(size_t)r + 1] - sp[(size_t)r]);
+        all_sizes.insert(all_sizes.end(), sz.begin(), sz.begin() + sp[(size_t)std::min(R, nr)]);
+    }
+    std::vector<int64_t> out_ptr((size_t)R + 1, 0);
+    for (int32_t r = 0; r < R; r++) out_ptr[(size_t)r + 1] = out_ptr[(size_t)r] + max_len[(size_t)r];
+    std::vector<double> tile_sum((size_t)out_ptr[(size_t)R] + 1, 0.0);
+    glck(ctx, gl_indexsplit_accumulate(ctx, all_sizes.data(), ptr.data(), (int32_t)S, R, out_ptr.data(), tile_sum.data()), "gl_indexsplit_accumulate");
+
+    // -p: BED of problematic regions (depth.ReadTree, depth/intervals.go:42-82)
+    std::vector<int32_t> pr; std::vector<int64_t> ps, pe;
+    if (!problematic.empty()) {
+        std::map<std::string, int> num;
+        for (int32_t q = 0; q < R; q++) num.emplace(refs[(size_t)q].name, q);
+        for (const std::string& ln : read_lines(problematic, true)) {
+            std::string c; long long s0, e0;
+            if (!chrom_start_end(ln, c, s0, e0)) fatal(2, "panic: couldn't get region from line %s", ln.c_str());
+            if (s0 >= e0) continue;
+            auto it = num.find(c);
+            if (it != num.end()) { pr.push_back(it->second); ps.push_back(s0); pe.push_back(e0); }
+        }
+    }
+    std::vector<const char*> nm; std::vector<int64_t> ln_; std::vector<int32_t> ids;
+    for (const Ref& r : refs) { nm.push_back(r.name.c_str()); ln_.push_back(r.len); ids.push_back(r.id); }
+    char* text = nullptr; int64_t tl = 0;
+    if (gl_indexsplit_chunks(tile_sum.data(), out_ptr.data(), R, nm.data(), ln_.data(), ids.data(), R, N, pr.data(), ps.data(), pe.data(),
+                             (int64_t)pr.size(), &text, &tl) != GL_OK) fatal(1, "gl_indexsplit_chunks failed");
+    fwrite(text, 1, (size_t)tl, stdout);
+    gl_free_text(text);
+    gl_ctx_destroy(ctx);
+    return 0;
+}
+
 static void print_progs() {                                                          // cmd/goleft/goleft.go:33-53
     fprintf(stderr, "goleft Version: %s (B200 engine: %s)\n\n", kVersion, gl_version());
     fprintf(stderr, "covstats    : coverage and insert-size statistics on bams by sampling\n");
     fprintf(stderr, "depth       : parallelize calls to samtools in user-defined windows\n");
     fprintf(stderr, "depthwed    : matricize output from depth to n-sites * n-samples\n");
     fprintf(stderr, "indexcov    : quick coverage estimate using only the bam index\n");
+    fprintf(stderr, "indexsplit  : create regions of even coverage across bams/crams\n");
 }
 
 int main(int argc, char** argv) {
@@ -847,6 +946,7 @@ int main(int argc, char** argv) {
     if (prog == "indexcov") return cmd_indexcov(argc - 1, argv + 1);
     if (prog == "covstats") return cmd_covstats(argc - 1, argv + 1);
     if (prog == "depthwed") return cmd_depthwed(argc - 1, argv + 1);
+    if (prog == "indexsplit") return cmd_indexsplit(argc - 1, argv + 1);
     print_progs();
     return 1;
 }

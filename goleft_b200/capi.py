@@ -129,6 +129,9 @@ _proto("gl_depth_add_segments_packed8", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_add_segments_packed8_device", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_region_packed8", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_indexsplit_accumulate", C.c_int, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp)
+_proto("gl_indexsplit_chunks", C.c_int, _vp, _vp, C.c_int32, C.POINTER(C.c_char_p), _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int64,
+       C.POINTER(_vp), _i64p)
 _proto("gl_crai_make_sizes", C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _i64p)
 _proto("gl_depth_format_chunk", C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int64, _vp, _vp,
        C.c_int64, C.POINTER(_vp), _i64p, C.POINTER(_vp), _i64p)
@@ -190,6 +193,43 @@ def pack_segments16(start: np.ndarray, end: np.ndarray):
         if rc != GL_ERANGE:
             raise GlError(rc, "gl_pack_segments16: bad arguments")
         cap = nb.value + 1
+
+
+def indexsplit_layout(sample_sizes, R: int):
+    """CSR layout gl_indexsplit_accumulate wants: (sizes int64, ptr int64[S*(R+1)], out_ptr int64[R+1])"""
+    S = len(sample_sizes)
+    flat, ptr, maxlen = [], np.zeros(S * (R + 1), np.int64), np.zeros(R, np.int64)
+    off = 0
+    for s, per_ref in enumerate(sample_sizes):
+        for r in range(R):
+            ptr[s * (R + 1) + r] = off
+            if r < len(per_ref):
+                a = np.asarray(per_ref[r], np.int64)
+                flat.append(a); off += a.size
+                maxlen[r] = max(maxlen[r], a.size)
+        ptr[s * (R + 1) + R] = off
+    sizes = np.concatenate(flat) if flat else np.zeros(0, np.int64)
+    return sizes, ptr, np.concatenate([[0], np.cumsum(maxlen)]).astype(np.int64)
+
+
+def indexsplit_chunks(tile_sum, out_ptr, names, ref_lens, ref_ids, N: int, problems=()) -> bytes:
+    """Host-only: gl_indexsplit_chunks -> the output lines."""
+    tile_sum = _as(tile_sum, np.float64)
+    out_ptr = _as(out_ptr, np.int64)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    lens, ids = _as(np.asarray(ref_lens), np.int64), _as(np.asarray(ref_ids), np.int32)
+    pr = _as(np.asarray([p[0] for p in problems]), np.int32)
+    ps = _as(np.asarray([p[1] for p in problems]), np.int64)
+    pe = _as(np.asarray([p[2] for p in problems]), np.int64)
+    t, n = _vp(), C.c_int64(0)
+    rc = lib.gl_indexsplit_chunks(_ptr(tile_sum), _ptr(out_ptr), out_ptr.size - 1, arr, _ptr(lens), _ptr(ids), len(names), N,
+                                  _ptr(pr), _ptr(ps), _ptr(pe), len(problems), C.byref(t), C.byref(n))
+    if rc != GL_OK:
+        raise GlError(rc, "gl_indexsplit_chunks: bad arguments")
+    try:
+        return C.string_at(t, n.value)
+    finally:
+        lib.gl_free_text(t)
 
 
 def pack_segments8(start: np.ndarray, end: np.ndarray):
@@ -470,6 +510,12 @@ class Ctx:
         n = C.c_int64(0)
         self._ck(lib.gl_depth_classes(self.h, mincov, maxmean, _ptr(rs_), _ptr(re_), _ptr(rc_), cap, C.byref(n)))
         return rs_[: n.value], re_[: n.value], rc_[: n.value]
+
+    def indexsplit_accumulate(self, sizes, ptr, S: int, R: int, out_ptr) -> np.ndarray:
+        sizes, ptr, out_ptr = _as(sizes, np.int64), _as(ptr, np.int64), _as(out_ptr, np.int64)
+        out = np.zeros(int(out_ptr[-1]), np.float64)
+        self._ck(lib.gl_indexsplit_accumulate(self.h, _ptr(sizes), _ptr(ptr), S, R, _ptr(out_ptr), _ptr(out)))
+        return out
 
     def depth_interval_sums(self, a, b) -> np.ndarray:
         a, b = _as(a, np.int32), _as(b, np.int32)

@@ -447,6 +447,24 @@ __global__ void __launch_bounds__(256) fmt_g3_kernel(const float* __restrict__ v
     for (int k = 0; k < 10; k++) o[k] = t[k];
 }
 
+// indexsplit (indexsplit/indexsplit.go:92-115): cohort data per 16 KB tile = sum over the samples, IN PATH ORDER, of
+// float64(size)/1e9.  One thread per (reference, tile): the float64 adds run in the reference's order, so the result is
+// bit-identical; consecutive tiles of one sample are consecutive in memory, so every pass over the samples is coalesced.
+// ptr[s*(R+1)+r] = offset of sample s's tiles of reference r in `sizes` (a sample with fewer references repeats its end).
+__global__ void __launch_bounds__(256) indexsplit_sum_kernel(const long long* __restrict__ sizes, const long long* __restrict__ ptr,
+                                                            int S, int R, const long long* __restrict__ out_ptr, double* __restrict__ out) {
+    const int r = blockIdx.y;
+    const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long n = out_ptr[r + 1] - out_ptr[r];
+    if (j >= n) return;
+    double acc = 0.0;
+    for (int s = 0; s < S; s++) {
+        const long long a = ptr[(size_t)s * (R + 1) + r], b = ptr[(size_t)s * (R + 1) + r + 1];
+        if (j < b - a) acc += (double)sizes[a + j] / 1000000000.0;
+    }
+    out[out_ptr[r] + j] = acc;
+}
+
 // small helper: a scratch device buffer per call site
 int dev_tmp(gl_ctx* ctx, gl_buf& b, size_t bytes) { return gl_buf_reserve(ctx, b, bytes ? bytes : 16); }
 
@@ -686,6 +704,46 @@ int gl_format_g3(gl_ctx* ctx, const float* vals, int64_t n, uint8_t* tokens) {
             cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_format_g3: D2H failed"); break; }
     } while (0);
     cudaFree(bv.p); cudaFree(bt.p);
+    return rc;
+}
+
+int gl_indexsplit_accumulate(gl_ctx* ctx, const int64_t* sizes, const int64_t* ptr, int32_t S, int32_t R, const int64_t* out_ptr, double* out) {
+    GL_CHECK(gl_use(ctx));
+    if (S < 0 || R < 0 || !out_ptr || (S > 0 && R > 0 && !ptr)) return gl_fail(ctx, GL_EINVAL, "gl_indexsplit_accumulate: bad argument");
+    if (R == 0) return GL_OK;
+    const int64_t n_out = out_ptr[R] - out_ptr[0];
+    int64_t max_len = 0;
+    for (int32_t r = 0; r < R; r++) {
+        if (out_ptr[r + 1] < out_ptr[r]) return gl_fail(ctx, GL_EINVAL, "gl_indexsplit_accumulate: out_ptr not monotone");
+        max_len = std::max<int64_t>(max_len, out_ptr[r + 1] - out_ptr[r]);
+    }
+    if (n_out == 0 || out_ptr[0] != 0) return n_out == 0 ? GL_OK : gl_fail(ctx, GL_EINVAL, "gl_indexsplit_accumulate: out_ptr[0] must be 0");
+    if (!out || (S > 0 && !sizes)) return gl_fail(ctx, GL_EINVAL, "gl_indexsplit_accumulate: bad argument");
+    const int64_t n_in = S > 0 ? ptr[(size_t)(S - 1) * (R + 1) + R] : 0;
+    for (int32_t s = 0; s < S; s++)
+        for (int32_t r = 0; r < R; r++) {
+            const int64_t a = ptr[(size_t)s * (R + 1) + r], b = ptr[(size_t)s * (R + 1) + r + 1];
+            if (a < 0 || b < a || b > n_in || b - a > out_ptr[r + 1] - out_ptr[r]) return gl_fail(ctx, GL_EINVAL, "gl_indexsplit_accumulate: ptr out of range (sample %d, ref %d)", s, r);
+        }
+    if (R > 65535) return gl_fail(ctx, GL_ERANGE, "gl_indexsplit_accumulate: more than 65535 references");
+    gl_buf bs, bp, bo, bq;
+    int rc = GL_OK;
+    do {
+        if (dev_tmp(ctx, bs, (size_t)n_in * 8) != GL_OK || dev_tmp(ctx, bp, (size_t)std::max(S, 1) * (R + 1) * 8) != GL_OK ||
+            dev_tmp(ctx, bo, (size_t)n_out * 8) != GL_OK || dev_tmp(ctx, bq, (size_t)(R + 1) * 8) != GL_OK) { rc = GL_ENOMEM; break; }
+        if ((n_in && cudaMemcpyAsync(bs.p, sizes, (size_t)n_in * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) ||
+            (S && cudaMemcpyAsync(bp.p, ptr, (size_t)S * (R + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) ||
+            cudaMemcpyAsync(bq.p, out_ptr, (size_t)(R + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexsplit_accumulate: H2D failed"); break; }
+        {
+            gl_prof_scope prof(ctx, "indexsplit_sum_kernel");
+            indexsplit_sum_kernel<<<dim3((unsigned)((max_len + 255) / 256), (unsigned)R), 256, 0, ctx->stream>>>(
+                static_cast<const long long*>(bs.p), static_cast<const long long*>(bp.p), S, R, static_cast<const long long*>(bq.p), static_cast<double*>(bo.p));
+        }
+        ctx->launches++;
+        if (cudaMemcpyAsync(out, bo.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_indexsplit_accumulate: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    cudaFree(bs.p); cudaFree(bp.p); cudaFree(bo.p); cudaFree(bq.p);
     return rc;
 }
 

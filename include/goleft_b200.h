@@ -275,6 +275,22 @@ int  gl_format_g3_device(gl_ctx* ctx, const float* d_vals, int64_t n, uint8_t* d
  * lens[i] valid entries in row i.  No-op for S < 5 (indexcov.go:551). */
 int  gl_indexcov_xnorm(gl_ctx* ctx, float* depths, const int32_t* lens, int32_t S, int32_t T);
 
+/* indexsplit (indexsplit/indexsplit.go:92-115): amount of cohort data per 16 KB tile = sum over the S samples, in path
+ * order, of float64(size)/1e9 — bit-identical to the reference's sequential adds.  sizes: every sample's tile sizes
+ * (gl_indexcov_sizes / gl_crai_make_sizes) concatenated; ptr[s*(R+1)+r] = offset of sample s's tiles of reference r
+ * (a sample whose index has fewer references repeats its end offset); out_ptr[r] = prefix sum of max_s(len) per
+ * reference; out[out_ptr[r] + j] = the tile's sum. */
+int  gl_indexsplit_accumulate(gl_ctx* ctx, const int64_t* sizes, const int64_t* ptr, int32_t S, int32_t R, const int64_t* out_ptr,
+                              double* out);
+/* Host-only: the rest of indexsplit.Split (indexsplit.go:37-65,119-188): chop outliers, share N regions over the
+ * references by their data, walk the tiles and cut.  tile_sum/out_ptr as filled by gl_indexsplit_accumulate (R index
+ * references); the n_refs listed references (name, length, id into the index references or -1) are reported in order;
+ * problematic intervals (-p) are (listed-reference number, start, end).  Returns the lines "chrom\tstart\tend\t%.2f\t%d\n"
+ * in *text (release with gl_free_text). */
+int  gl_indexsplit_chunks(const double* tile_sum, const int64_t* out_ptr, int32_t R, const char* const* ref_names, const int64_t* ref_lens,
+                          const int32_t* ref_ids, int32_t n_refs, int32_t N, const int32_t* prob_ref, const int64_t* prob_start,
+                          const int64_t* prob_end, int64_t n_prob, char** text, int64_t* text_len);
+
 /* ---------------------------------------------------------------- covstats
  * V2: histogram of int32 values in [lo,hi) -> hist[v-lo] (covstats/covstats.go:202-217 and the
  * order statistics of :175-199, which the host derives from the histogram). */

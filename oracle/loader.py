@@ -264,6 +264,34 @@ def depthwed(means, starts, ends, chrom_id, size: int):
 _proto("orc_crai_sizes", C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, C.c_int64)
 
 
+_proto("orc_indexsplit", C.c_int64, _vp, _vp, C.c_int, C.c_int, C.POINTER(C.c_char_p), _vp, C.c_int, _vp, _vp, _vp, C.c_int64, C.c_char_p, C.c_int64)
+
+
+def indexsplit(sample_sizes, names, ref_lens, N: int, problems=()) -> bytes:
+    """indexsplit.Split restatement.  sample_sizes: per sample a list (per reference) of int64 tile-size arrays."""
+    S, R = len(sample_sizes), len(names)
+    flat, ptr = [], np.zeros(S * (R + 1), np.int64)
+    off = 0
+    for s, per_ref in enumerate(sample_sizes):
+        for r in range(R):
+            ptr[s * (R + 1) + r] = off
+            if r < len(per_ref):
+                flat.append(np.asarray(per_ref[r], np.int64)); off += flat[-1].size
+        ptr[s * (R + 1) + R] = off
+    sizes = np.concatenate(flat) if flat else np.zeros(0, np.int64)
+    arr = (C.c_char_p * R)(*[n.encode() for n in names])
+    lens = np.asarray(ref_lens, np.int64)
+    pr = np.asarray([p[0] for p in problems], np.int32)
+    ps = np.asarray([p[1] for p in problems], np.int64)
+    pe = np.asarray([p[2] for p in problems], np.int64)
+    cap = 1 << 24
+    out = C.create_string_buffer(cap)
+    n = lib.orc_indexsplit(_ptr(sizes), _ptr(ptr), S, R, arr, _ptr(lens), N, _ptr(pr), _ptr(ps), _ptr(pe), len(problems), out, cap)
+    if n < 0:
+        raise RuntimeError("orc_indexsplit: output buffer too small")
+    return out.raw[:n]
+
+
 def crai_sizes(start, span, nbytes) -> np.ndarray:
     start = np.ascontiguousarray(start, np.int64)
     span = np.ascontiguousarray(span, np.int64)

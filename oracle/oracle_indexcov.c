@@ -11,6 +11,7 @@
  * Citations are relative to the reference checkout (brentp/goleft @ v0.2.6).
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -304,4 +305,108 @@ int64_t orc_crai_sizes(const int64_t* aln_start, const int64_t* aln_span, const 
         lastVal = perBase;
     }
     return k_out;
+}
+
+/* ------------------------------------------------------------------ indexsplit (indexsplit/indexsplit.go)
+ * orc_indexsplit restates Split (:82-194) with getPercents/chop (:37-65) and Chunk.String (:77-79) for references whose
+ * ID is their position (RefsFromBam).  sizes/ptr: as gl_indexsplit_accumulate (ptr[s*(R+1)+r]).  Problematic intervals
+ * (-p): (reference number, start, end), half-open overlap like depth.Overlaps (depth/intervals.go:16-40).
+ * Third-party: gonum v0.14.0 stat.MeanStdDev (corrected two-pass) and floats.Sum (amd64 SIMD kernel, alignment-dependent
+ * order — restated as left-to-right; PARITY UNPINNED), biogo/store interval tree (overlap query only).
+ * Returns the number of bytes written to out (0-terminated), or -1 if cap is too small. */
+static int os_overlaps(const int32_t* pr, const int64_t* ps, const int64_t* pe, int64_t np, int ref, int64_t a, int64_t b) {
+    for (int64_t k = 0; k < np; k++)
+        if (pr[k] == ref && pe[k] > a && ps[k] < b) return 1;
+    return 0;
+}
+
+int64_t orc_indexsplit(const int64_t* sizes_in, const int64_t* ptr, int S, int R, const char** names, const int64_t* ref_lens, int N,
+                       const int32_t* pr, const int64_t* ps, const int64_t* pe, int64_t np, char* out, int64_t cap) {
+    const int64_t TW = 16384;
+    const double scalar = 1000000000.0;
+    double** sizes = (double**)calloc((size_t)(R > 0 ? R : 1), sizeof(double*));
+    int64_t* lens = (int64_t*)calloc((size_t)(R > 0 ? R : 1), sizeof(int64_t));
+    for (int s = 0; s < S; s++) {                                    /* :92-115 */
+        for (int i = 0; i < R; i++) {
+            const int64_t a = ptr[(size_t)s * (R + 1) + i], b = ptr[(size_t)s * (R + 1) + i + 1];
+            const int64_t olen = b - a;
+            if (olen > lens[i]) {
+                sizes[i] = (double*)realloc(sizes[i], (size_t)olen * sizeof(double));
+                for (int64_t j = lens[i]; j < olen; j++) sizes[i][j] = 0.0;
+            }
+            const int64_t m = lens[i] < olen ? lens[i] : olen;
+            int64_t j = 0;
+            for (; j < m; j++) sizes[i][j] += (double)sizes_in[a + j] / scalar;
+            for (; j < olen; j++) sizes[i][j] = (double)sizes_in[a + j] / scalar;   /* append */
+            if (olen > lens[i]) lens[i] = olen;
+        }
+    }
+    double* sums = (double*)calloc((size_t)(R > 0 ? R : 1), sizeof(double));
+    double* pcts = (double*)calloc((size_t)(R > 0 ? R : 1), sizeof(double));
+    double tot = 0.0;
+    for (int k = 0; k < R; k++) {                                    /* chop :37-48, then sums :55-58 */
+        const int64_t n = lens[k];
+        double sum = 0.0;
+        for (int64_t i = 0; i < n; i++) sum += sizes[k][i];
+        const double m = sum / (double)n;
+        double ss = 0.0, comp = 0.0;
+        for (int64_t i = 0; i < n; i++) { double d = sizes[k][i] - m; ss += d * d; comp += d; }
+        const double sd = sqrt((ss - comp * comp / (double)n) / (double)(n - 1));
+        const double max = m + 3 * sd;
+        for (int64_t i = 0; i < n; i++) if (sizes[k][i] > max) sizes[k][i] = 8 * m;
+        double t = 0.0;
+        for (int64_t i = 0; i < n; i++) t += sizes[k][i];
+        sums[k] = t;
+        tot += t;
+    }
+    for (int k = 0; k < R; k++) pcts[k] = sums[k] / tot;
+    int64_t w = 0;
+    int overflow = 0;
+#define EMIT(nm, st, en, sm, sp) do { char b_[256]; int n_ = snprintf(b_, sizeof b_, "%s\t%lld\t%lld\t%.2f\t%d\n", nm, (long long)(st), (long long)(en), (double)(sm), (int)(sp)); \
+        if (w + n_ + 1 > cap) overflow = 1; else { memcpy(out + w, b_, (size_t)n_); w += n_; } } while (0)
+    for (int ri = 0; ri < R; ri++) {                                 /* :119-188 */
+        const char* name = names[ri];
+        const int64_t rlen = ref_lens[ri];
+        if (lens[ri] == 0) { EMIT(name, 0, rlen, 0.0, 0); continue; }
+        const double share = pcts[ri] * (double)N;
+        int n = (share == share) ? (int)share : 0;
+        if (n == 0 && pcts[ri] > 0) n = 1;
+        else if (n == 0) { EMIT(name, 0, rlen, 0.0, 0); continue; }
+        const double chunk = sums[ri] / (double)n;
+        const double* size = sizes[ri];
+        const int64_t len = lens[ri];
+        double sum = 0.0;
+        int64_t lasti = 0;
+        for (int64_t i = 0; i < len; i++) {
+            const int ovl = os_overlaps(pr, ps, pe, np, ri, i * TW, (i + 1) * TW);
+            if (size[i] > chunk || (size[i] >= 0.05 * chunk && ovl)) {
+                if (i > lasti) EMIT(name, lasti * TW, i * TW, sum, 1);
+                sum = size[i];
+                int nsplits = (int)(0.5 + (sum / (chunk / 2)));
+                if (nsplits > 8) nsplits = 8;
+                else if (nsplits < 1) { nsplits = 1; if (ovl) nsplits = 3; }
+                int64_t start = i * TW;
+                const int64_t l = (int64_t)((double)TW / (double)nsplits + 1);
+                for (int k = 0; k < nsplits; k++) {
+                    if (i + k == len + 1) EMIT(name, start, rlen, sum / (double)nsplits, nsplits);
+                    else { int64_t en = start + l < (i + 1) * TW ? start + l : (i + 1) * TW; EMIT(name, start, en, sum / (double)nsplits, nsplits); }
+                    start += l;
+                }
+                lasti = i + 1; sum = 0.0;
+                continue;
+            }
+            sum += size[i];
+            if (sum >= chunk || i == len - 1 || (sum >= 0.2 * chunk && ovl)) {
+                if (i == len - 1) EMIT(name, lasti * TW, rlen, sum, 1);
+                else EMIT(name, lasti * TW, (i + 1) * TW, sum, 1);
+                lasti = i + 1; sum = 0.0;
+            }
+        }
+    }
+#undef EMIT
+    for (int k = 0; k < R; k++) free(sizes[k]);
+    free(sizes); free(lens); free(sums); free(pcts);
+    if (overflow) return -1;
+    out[w] = 0;
+    return w;
 }

@@ -246,6 +246,33 @@ def _cohort_bais(tmp_path, S=7, seed=3):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N", [10, 200])
+def test_indexsplit(tmp_path, N):
+    """goleft indexsplit (indexsplit/indexsplit.go): regions of about equal cohort data.  Text equals the oracle's
+    restatement of Split; the regions tile every chromosome exactly once (indexsplit/functional-tests.sh:33-36)."""
+    refs, fai, paths, lin = _cohort_bais(tmp_path, S=9, seed=N)
+    bed = tmp_path / "prob.bed"
+    bed.write_text("1\t1000000\t1100000\nX\t5\t10\n2\t7\t3\n")
+    p = run("indexsplit", "-n", str(N), "--fai", fai, "-p", str(bed), *paths)
+    per_sample = []
+    for k in range(len(paths)):
+        voff = np.array([v for r in lin[k] for v in r], np.uint64)
+        ptr = np.concatenate([[0], np.cumsum([len(r) for r in lin[k]])]).astype(np.int64)
+        sizes, sptr = orc.ic_sizes(voff, ptr)
+        per_sample.append([sizes[sptr[r]:sptr[r + 1]] for r in range(len(refs))])
+    exp = orc.indexsplit(per_sample, [n for n, _ in refs], [L for _, L in refs], N, problems=[(0, 1000000, 1100000), (3, 5, 10)])
+    assert p.stdout.encode() == exp
+    rows = [ln.split("\t") for ln in p.stdout.splitlines()]
+    if N == 10:                                     # regions of many tiles: exact tiling (with regions near one tile the
+        for name, L in refs:                        # reference's own heavy-tile rows overlap at chromosome ends)
+            iv = [(int(r[1]), int(r[2])) for r in rows if r[0] == name]
+            assert iv[0][0] == 0 and iv[-1][1] == L
+            assert all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
+    assert len(rows) >= min(N, 5)
+    assert run("indexsplit", "--fai", fai, *paths, check=False).returncode == 255           # -n is required
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("extranorm", [False, True])
 def test_indexcov_cohort(tmp_path, extranorm):
     refs, fai, paths, lin = _cohort_bais(tmp_path)

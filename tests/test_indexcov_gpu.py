@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+from goleft_b200 import capi
 from oracle import loader as orc
 
 pytestmark = pytest.mark.gpu
@@ -165,3 +166,30 @@ def test_format_g3_exact(ctx):
             exp = "%.3g" % float(v)
         assert got == exp, (float(v), got, exp)
     assert n_host < 60_000
+
+
+def test_indexsplit_accumulate_bit_exact(ctx):
+    """gl_indexsplit_accumulate: per-tile float64 sums over the samples in path order — bit-identical to the sequential
+    adds of indexsplit.go:92-115 (ragged samples, a sample with fewer references, an empty reference)."""
+    rng = np.random.default_rng(4)
+    R = 6
+    lens = [900, 1, 0, 4000, 37, 12000]
+    samples = []
+    for k in range(23):
+        nref = R if k % 5 else R - 2
+        per = []
+        for r in range(nref):
+            n = max(0, lens[r] - int(rng.integers(0, 3)) * (k % 3 == 0))
+            per.append(rng.integers(0, 4_000_000_000, n).astype(np.int64))
+        samples.append(per)
+    sizes, ptr, out_ptr = capi.indexsplit_layout(samples, R)
+    got = ctx.indexsplit_accumulate(sizes, ptr, len(samples), R, out_ptr)
+    exp = np.zeros(int(out_ptr[-1]))
+    for s in range(len(samples)):
+        for r in range(R):
+            a, b = ptr[s * (R + 1) + r], ptr[s * (R + 1) + r + 1]
+            exp[out_ptr[r]:out_ptr[r] + (b - a)] += sizes[a:b].astype(np.float64) / 1e9
+    assert np.array_equal(got.view(np.uint64), exp.view(np.uint64))
+    names = ["r%d" % r for r in range(R)]
+    ref_lens = [max(1, n) * 16384 + 5 for n in lens]
+    assert capi.indexsplit_chunks(got, out_ptr, names, ref_lens, list(range(R)), 50) == orc.indexsplit(samples, names, ref_lens, 50)

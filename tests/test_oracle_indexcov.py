@@ -182,3 +182,47 @@ def test_no_cuda_device_fails_loudly():
     with pytest.raises(capi.GlError) as ei:
         capi.Ctx(0)
     assert ei.value.code == capi.GL_ECUDA
+
+
+def test_indexsplit_restatement_tiles_every_chromosome():
+    """indexsplit/functional-tests.sh:33-36: the regions cover every chromosome exactly once (no gap, no overlap), also
+    with heavy tiles (cut in up to 8 pieces), problematic regions (cut in 3) and an empty chromosome; the host chunker
+    of the library (no GPU needed) prints the same lines as the oracle."""
+    from goleft_b200 import capi
+    rng = np.random.default_rng(1)
+    names = ["1", "2", "X", "MT", "empty"]
+    lens = [3_000_000, 2_000_000, 1_500_000, 16571, 5000]
+    samples = []
+    for k in range(6):
+        per = []
+        for r, L in enumerate(lens[:4]):
+            n = max(0, L // 16384 - (k % 2 if r == 1 else 0))
+            v = rng.lognormal(np.log(1.6e9), 0.25, n)
+            if r == 0:
+                v[50] *= 30
+            per.append(v.astype(np.int64))
+        samples.append(per)
+    problems = [(0, 1_000_000, 1_100_000), (1, 5, 10)]
+    for N in (5, 40, 1000):
+        txt = orc.indexsplit(samples, names, lens, N, problems)
+        rows = [ln.split("\t") for ln in txt.decode().splitlines()]
+        for name, L in zip(names, lens):
+            if N == 1000:
+                break           # regions smaller than a tile: every tile is cut in pieces and indexsplit.go:159-165 emits
+                                # overlapping rows near a chromosome's end — restated as is, only compared with the host code
+            iv = [(int(r[1]), int(r[2])) for r in rows if r[0] == name]
+            assert iv[0][0] == 0 and iv[-1][1] == L, (name, iv[:2], iv[-2:])
+            assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(iv, iv[1:]))
+        assert [r for r in rows if r[0] == "empty"] == [["empty", "0", "5000", "0.00", "0"]]
+        if N >= 40:                                     # small enough regions: problematic tiles are cut in 3, the heavy tile in more
+            assert any(r[4] == "3" for r in rows)
+        if N == 1000:
+            assert any(int(r[4]) > 3 for r in rows)
+        sizes, ptr, out_ptr = capi.indexsplit_layout(samples, len(names))
+        acc = np.zeros(int(out_ptr[-1]))
+        R = len(names)
+        for s in range(len(samples)):
+            for r in range(R):
+                a, b = ptr[s * (R + 1) + r], ptr[s * (R + 1) + r + 1]
+                acc[out_ptr[r]:out_ptr[r] + (b - a)] += sizes[a:b].astype(np.float64) / 1e9
+        assert capi.indexsplit_chunks(acc, out_ptr, names, lens, list(range(R)), N, problems) == txt
