@@ -331,6 +331,7 @@ struct ScanParams {
     int p8_nblocks;
     int* tile_lo;                 // [num_tiles+1] number of anchors < x_k - 255, x_k = rs + k*4096
     int* tile_hi;                 // [num_tiles+1] number of anchors < x_k
+    unsigned W_inv;               // floor(2^32 / W): window index by multiplication (fast window path, W >= 16)
     int tile_begin, tile_end;     // K_fused8 processes these tiles (a streamed upload launches it once per arrived chunk)
     int idx_begin, idx_end;       // K_tileidx8 handles the anchor gaps i in [idx_begin, idx_end), i = -1 .. nb-1
 };
@@ -356,9 +357,16 @@ __device__ __forceinline__ int select16(const int (&S)[16], int i) {
 // s_depth: 4096 ints, per-warp private scratch of the slow paths.  s_carry[8]: partial sums of everything before
 // the tile.  Requires all 256 threads; contains exactly ONE __syncthreads (the 8 warp totals); after it every warp
 // is independent: runs are claimed per 512-base warp chunk, not per tile.
+// deepest base seen by this warp -> header[2]; the plain read first keeps most warps off the atomic
+__device__ __forceinline__ void flush_max(const ScanParams& p, int acc_max) {
+    if ((threadIdx.x & 31) == 0 && acc_max > 0 &&
+        (unsigned long long)acc_max > *reinterpret_cast<volatile unsigned long long*>(p.header + 2))
+        atomicMax(reinterpret_cast<unsigned long long*>(p.header + 2), (unsigned long long)acc_max);
+}
+
 template <bool kZeroAfterRead>
 __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__ s_tile, int* __restrict__ s_depth,
-                                          const int* s_carry, int tile) {
+                                          const int* s_carry, int tile, int& acc_max) {
     __shared__ int s_warp_tot[kWarps];
     __shared__ int s_has_break;
 
@@ -485,8 +493,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
         }
         if (!full_warp) maxd = __reduce_max_sync(kFull, maxd);
     }
-    if (lane == 0 && maxd > 0 && (unsigned long long)maxd > *reinterpret_cast<volatile unsigned long long*>(p.header + 2))
-        atomicMax(reinterpret_cast<unsigned long long*>(p.header + 2), (unsigned long long)maxd);
+    acc_max = max(acc_max, maxd);                             // warp-uniform; the kernel publishes it once (flush_max)
 
     // ---- window partial sums of this warp's 512 bases
     if (fast_win) {
@@ -499,12 +506,16 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
         for (int k = 1; k < 16; k++) S[k] = S[k - 1] + d[k];
         const unsigned a0 = (unsigned)p.rs + (unsigned)warp_base;     // absolute, < 2^32
         const unsigned uW = (unsigned)p.W;
-        unsigned iw = a0 / uW;
-        long long edge = (long long)(iw + 1) * uW - a0;               // offset of the next window edge in the warp
+        // iw = a0 / W without a division: q = hi32(a0 * floor(2^32/W)) is the quotient or one less
+        unsigned iw = __umulhi(a0, p.W_inv);
+        unsigned rem = a0 - iw * uW;
+        if (rem >= uW) { iw++; rem -= uW; }
+        if (rem >= uW) { iw++; rem -= uW; }
+        unsigned edge = uW - rem;                                     // offset of the next window edge in the warp, in (0, W]
         int counted = 0;
 #pragma unroll 1
         while (true) {
-            const int c = (int)min(16ll, max(0ll, edge - lane * 16)); // my bases left of the edge
+            const int c = min(16, max(0, (int)edge - lane * 16));     // my bases left of the edge
             int cur = select16(S, (c - 1) & 15);
             cur = c == 0 ? 0 : cur;
             const unsigned tot = (unsigned)__reduce_add_sync(kFull, cur - counted);
@@ -609,7 +620,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanP
 #pragma unroll
     for (int r = 0; r < 4; r++) reinterpret_cast<int4*>(s_tile)[swz_chunk(warp * 128 + r * 32 + lane)] = v[r];
     __syncwarp();                                                       // a warp only re-reads its own 128 chunks
-    tile_core<false>(p, s_tile, s_depth, s_carry, tile);
+    int acc_max = 0;
+    tile_core<false>(p, s_tile, s_depth, s_carry, tile, acc_max);
+    flush_max(p, acc_max);
 }
 
 // FUSED path, K_fused: build each tile's difference array in shared memory straight from the segments.
@@ -716,6 +729,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const Scan
     cells = fused_load_cells(p, b0, tile + G, maxlen);
     __syncthreads();          // every warp has read s_rng before iteration 0 rewrites it (found by compute-sanitizer racecheck)
 
+    int acc_max = 0;
     for (int it = 0; tile < p.num_tiles; tile += G, it ^= 1) {
         int* s_carry = s_carry2[it];
         const int t0 = p.rs + tile * kTile, t1 = min(t0 + kTile, p.re);
@@ -755,8 +769,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const Scan
             se[j] = ok ? be[i] : 0;
         }
         cells = fused_load_cells(p, b0, tile + 2 * G, maxlen);          // and the tile after that one's cell entries
-        tile_core<true>(p, s_tile, s_depth, s_carry, tile);
+        tile_core<true>(p, s_tile, s_depth, s_carry, tile, acc_max);
     }
+    flush_max(p, acc_max);
 }
 
 // ================================================================================================
@@ -857,6 +872,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused8_kernel(const Sca
     P8Regs regs = fused8_load(p, lo, hi, 0);
     __syncthreads();
 
+    int acc_max = 0;
     for (int it = 0; tile < p.tile_end; tile += G, it ^= 1) {
         int* s_carry = s_carry2[it];
         const int t0 = p.rs + tile * kTile, t1 = min(t0 + kTile, p.re);
@@ -872,8 +888,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused8_kernel(const Sca
         regs = fused8_load(p, lo, hi, 0);                   // next tile's packed words: in flight during the core
         lo2 = hi2 = 0;
         if (tile + 2 * G < p.tile_end) { lo2 = max(0, p.tile_lo[tile + 2 * G] - 1); hi2 = min(nb, p.tile_hi[tile + 2 * G + 1]); }
-        tile_core<true>(p, s_tile, s_depth, s_carry, tile);
+        tile_core<true>(p, s_tile, s_depth, s_carry, tile, acc_max);
     }
+    flush_max(p, acc_max);
 }
 
 // K_gather: one warp per 512-base chunk moves its runs from claim order to position order.  The ordered offset
@@ -1102,6 +1119,7 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
     p.rs = (int)ctx->rs;
     p.re = (int)ctx->re;
     p.W = W;
+    p.W_inv = W >= 2 ? (unsigned)((uint64_t(1) << 32) / (uint64_t)W) : 0u;
     p.w0 = w0;
     p.mincov = mincov;
     p.maxmean = maxmean;
@@ -1297,6 +1315,7 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
     p.rs = (int)ctx->rs;
     p.re = (int)ctx->re;
     p.W = W;
+    p.W_inv = W >= 2 ? (unsigned)((uint64_t(1) << 32) / (uint64_t)W) : 0u;
     p.w0 = w0;
     p.mincov = mincov;
     p.maxmean = maxmean;
