@@ -342,21 +342,6 @@ __device__ __forceinline__ int cov_class(int d, int mincov, int maxmean) {
                   : (d < mincov ? GL_LOW_COVERAGE : ((maxmean > 0 && d >= maxmean) ? GL_EXCESSIVE_COVERAGE : GL_CALLABLE));
 }
 
-// S[i] for a run-time i in [0,16) out of 16 registers: 4 bit tests + 15 selects
-__device__ __forceinline__ int select16(const int (&S)[16], int i) {
-    const bool b0 = i & 1, b1 = i & 2, b2 = i & 4, b3 = i & 8;
-    const int a0 = b0 ? S[1] : S[0], a1 = b0 ? S[3] : S[2], a2 = b0 ? S[5] : S[4], a3 = b0 ? S[7] : S[6];
-    const int a4 = b0 ? S[9] : S[8], a5 = b0 ? S[11] : S[10], a6 = b0 ? S[13] : S[12], a7 = b0 ? S[15] : S[14];
-    const int c0 = b1 ? a1 : a0, c1 = b1 ? a3 : a2, c2 = b1 ? a5 : a4, c3 = b1 ? a7 : a6;
-    const int e0 = b2 ? c1 : c0, e1 = b2 ? c3 : c2;
-    return b3 ? e1 : e0;
-}
-
-// s_tile: the tile's 4096 differences in swizzled layout (kZeroAfterRead: each warp clears its own slice as soon
-// as it has read it, so a persistent CTA can accumulate the next tile without a clearing pass + barrier).
-// s_depth: 4096 ints, per-warp private scratch of the slow paths.  s_carry[8]: partial sums of everything before
-// the tile.  Requires all 256 threads; contains exactly ONE __syncthreads (the 8 warp totals); after it every warp
-// is independent: runs are claimed per 512-base warp chunk, not per tile.
 // deepest base seen by this warp -> header[2]; the plain read first keeps most warps off the atomic
 __device__ __forceinline__ void flush_max(const ScanParams& p, int acc_max) {
     if ((threadIdx.x & 31) == 0 && acc_max > 0 &&
@@ -497,13 +482,14 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
 
     // ---- window partial sums of this warp's 512 bases
     if (fast_win) {
-        // From registers.  S[k] = sum of this thread's first k+1 depths (< 2^26).  For every window edge
-        // inside the warp, each lane contributes the part of its 16 bases left of the edge that was not
-        // counted yet; one REDUX adds the lanes (< 2^31), lane 0 issues one 64-bit red per window.
-        int S[16];
-        S[0] = d[0];
+        // From registers.  For every window edge inside the warp each lane contributes the part of its 16 bases left
+        // of the edge that was not counted yet: all 16 (s16) for lanes left of the edge's lane, the first `cu` for the
+        // edge's lane, nothing right of it; one REDUX adds the lanes (< 2^31), lane 0 issues one 64-bit red per window.
+        // cu = edge % 16 is the same for the whole warp, so the partial sum is a jump into a fall-through chain
+        // (cu adds, no divergence) instead of a 16-way register select per lane.
+        int s16 = 0;
 #pragma unroll
-        for (int k = 1; k < 16; k++) S[k] = S[k - 1] + d[k];
+        for (int k = 0; k < 16; k++) s16 += d[k];
         const unsigned a0 = (unsigned)p.rs + (unsigned)warp_base;     // absolute, < 2^32
         const unsigned uW = (unsigned)p.W;
         // iw = a0 / W without a division: q = hi32(a0 * floor(2^32/W)) is the quotient or one less
@@ -515,9 +501,27 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
         int counted = 0;
 #pragma unroll 1
         while (true) {
-            const int c = min(16, max(0, (int)edge - lane * 16));     // my bases left of the edge
-            int cur = select16(S, (c - 1) & 15);
-            cur = c == 0 ? 0 : cur;
+            const int el = (int)(edge >> 4);                          // lane holding the edge (>= 32: beyond the warp)
+            int part = 0;
+            switch (edge & 15u) {                                     // warp-uniform
+                case 15: part += d[14]; [[fallthrough]];
+                case 14: part += d[13]; [[fallthrough]];
+                case 13: part += d[12]; [[fallthrough]];
+                case 12: part += d[11]; [[fallthrough]];
+                case 11: part += d[10]; [[fallthrough]];
+                case 10: part += d[9]; [[fallthrough]];
+                case 9: part += d[8]; [[fallthrough]];
+                case 8: part += d[7]; [[fallthrough]];
+                case 7: part += d[6]; [[fallthrough]];
+                case 6: part += d[5]; [[fallthrough]];
+                case 5: part += d[4]; [[fallthrough]];
+                case 4: part += d[3]; [[fallthrough]];
+                case 3: part += d[2]; [[fallthrough]];
+                case 2: part += d[1]; [[fallthrough]];
+                case 1: part += d[0]; [[fallthrough]];
+                default: break;
+            }
+            const int cur = lane < el ? s16 : (lane == el ? part : 0);
             const unsigned tot = (unsigned)__reduce_add_sync(kFull, cur - counted);
             counted = cur;
             if (lane == 0) atomicAdd(p.win_sum + ((long long)iw - p.w0), (unsigned long long)tot);
