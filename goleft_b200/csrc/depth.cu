@@ -1164,14 +1164,15 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
         const bool streamed = ctx->p8.upload_pending;
         const int n_chunks = streamed ? p8_chunks() : 1;
         if (streamed) {
-            while ((int)ctx->ev_chunk.size() < n_chunks) {
+            while ((int)ctx->ev_chunk.size() < 2 * n_chunks) {
                 cudaEvent_t ev;
                 GL_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
                 ctx->ev_chunk.push_back(ev);
             }
             GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));   // previous consumer done with the staging buffer
         }
-        int64_t b0 = 0, t_prev = 0;
+        int64_t b0 = 0, t_prev = 0, w_sent = 0;             // w_sent: window sums already on their way home
+        const bool early_sums = streamed && ctx->prefetch_sums && do_windows && n_windows <= ctx->prefetch_cap;
         for (int c = 0; c < n_chunks; c++) {
             const bool last = c == n_chunks - 1;
             const int64_t b1 = p8_chunk_end(nb, c, n_chunks);
@@ -1207,6 +1208,18 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
                 depth_fused8_kernel<<<(unsigned)std::min<int64_t>(t_ready - t_prev, (int64_t)ctx->sm_count * 4), kScanThreads, 0, ctx->stream>>>(p);
                 GL_LAUNCHED(ctx, 1);
             }
+            if (early_sums && !last && t_ready > t_prev) {
+                // windows that end at or before the last reduced tile's end are final: send them home on their own stream
+                const int64_t w_done = std::min<int64_t>(n_windows, std::max<int64_t>(w_sent, (ctx->rs + t_ready * kTile) / W - w0));
+                if (w_done > w_sent) {
+                    cudaEvent_t ev = ctx->ev_chunk[(size_t)n_chunks + c];
+                    GL_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+                    GL_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev, 0));
+                    GL_CUDA(ctx, cudaMemcpyAsync(ctx->prefetch_sums + w_sent, static_cast<const char*>(ctx->win_sum_p) + w_sent * 8,
+                                                 (size_t)(w_done - w_sent) * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                    w_sent = w_done;
+                }
+            }
             t_prev = t_ready;
             b0 = b1;
         }
@@ -1220,8 +1233,10 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
             GL_LAUNCHED(ctx, 1);
         }
         ctx->prefetched = false;
-        if (ctx->prefetch_sums && do_windows && n_windows <= ctx->prefetch_cap) {   // sums travel while the header is read
-            GL_CUDA(ctx, cudaMemcpyAsync(ctx->prefetch_sums, ctx->win_sum_p, (size_t)n_windows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->prefetch_sums && do_windows && n_windows <= ctx->prefetch_cap) {   // (the rest of the) sums travel while the header is read
+            if (n_windows > w_sent)
+                GL_CUDA(ctx, cudaMemcpyAsync(ctx->prefetch_sums + w_sent, static_cast<const char*>(ctx->win_sum_p) + w_sent * 8,
+                                             (size_t)(n_windows - w_sent) * 8, cudaMemcpyDeviceToHost, ctx->stream));
             ctx->prefetched = true;
         }
         ctx->prefetched_runs = 0;
@@ -1235,6 +1250,7 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
         }
         uint64_t hdr[4];
         GL_CHECK(read_header(ctx, hdr));
+        if (w_sent > 0) GL_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
         if (hdr[3] != 0) { ctx->prefetched = false; ctx->prefetched_runs = 0; return GL_OK; }        // anchors not sorted: not accepted
         ctx->n_runs = do_runs ? (int64_t)hdr[0] : 0;
         ctx->max_depth = (int32_t)hdr[2];

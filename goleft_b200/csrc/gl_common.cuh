@@ -25,6 +25,7 @@ struct gl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;       // compute stream
     cudaStream_t copy_stream = nullptr;  // H2D staging stream
+    cudaStream_t d2h_stream = nullptr;   // streamed packed8 reduce: finished window sums leave while later chunks arrive
     std::string err;
     int64_t launches = 0;
     int sm_count = 148;
