@@ -378,6 +378,15 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     }
     const int lane_excl = inc - x[15];
     if (lane == 31) s_warp_tot[warp] = inc;
+    // depth[k] = tbase + x[k], tbase known only after the barrier: take min / max / sum of the x[k] now, while other
+    // warps are still arriving, and add tbase afterwards (the per-base depths are formed only where a slow path needs them)
+    int xmn = x[0], xmx = x[0], xsum = x[0];
+#pragma unroll
+    for (int k = 1; k < 16; k++) {
+        xmn = min(xmn, x[k]);
+        xmx = max(xmx, x[k]);
+        xsum += x[k];
+    }
     if (tid == 0) {
         // does a forced run break (multiple of run_break) fall inside this tile?  (absolute positions are < 2^32)
         int hb = 0;
@@ -394,24 +403,17 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     const int wbase = __reduce_add_sync(kFull, lane < kWarps ? s_carry[lane] + (lane < warp ? s_warp_tot[lane] : 0) : 0);
     const int tbase = wbase + lane_excl;                      // depth at the base before this thread's first
 
-    // ---- per-base depth in registers
-    int d[16];
-    int mn = 0x7fffffff, mx = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        d[k] = tbase + x[k];
-        mn = min(mn, d[k]);
-        mx = max(mx, d[k]);
-    }
+    const int mn = tbase + xmn, mx = tbase + xmx;
+#define GL_D(k) (tbase + x[k])                                 /* depth of this thread's k-th base */
     if (p.depth_out) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int idx = idx0 + 4 * j;
-            if (idx + 3 < p.len) reinterpret_cast<int4*>(p.depth_out + idx)[0] = make_int4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+            if (idx + 3 < p.len) reinterpret_cast<int4*>(p.depth_out + idx)[0] = make_int4(GL_D(4 * j), GL_D(4 * j + 1), GL_D(4 * j + 2), GL_D(4 * j + 3));
             else {
-                if (idx < p.len) p.depth_out[idx] = d[4 * j];
-                if (idx + 1 < p.len) p.depth_out[idx + 1] = d[4 * j + 1];
-                if (idx + 2 < p.len) p.depth_out[idx + 2] = d[4 * j + 2];
+                if (idx < p.len) p.depth_out[idx] = GL_D(4 * j);
+                if (idx + 1 < p.len) p.depth_out[idx + 1] = GL_D(4 * j + 1);
+                if (idx + 2 < p.len) p.depth_out[idx + 2] = GL_D(4 * j + 2);
             }
         }
     }
@@ -435,7 +437,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            reinterpret_cast<int4*>(sw + lane * 16)[j] = make_int4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+            reinterpret_cast<int4*>(sw + lane * 16)[j] = make_int4(GL_D(4 * j), GL_D(4 * j + 1), GL_D(4 * j + 2), GL_D(4 * j + 3));
         __syncwarp();
     }
 
@@ -449,9 +451,9 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             if (k < nv) {
-                if (!full_warp) maxd = max(maxd, d[k]);
+                if (!full_warp) maxd = max(maxd, GL_D(k));
                 if (slow_runs) {
-                    const int c = cov_class(d[k], p.mincov, p.maxmean);
+                    const int c = cov_class(GL_D(k), p.mincov, p.maxmean);
                     if (c != cp) mask |= 1u << k;
                     cp = c;
                 }
@@ -487,9 +489,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
         // edge's lane, nothing right of it; one REDUX adds the lanes (< 2^31), lane 0 issues one 64-bit red per window.
         // cu = edge % 16 is the same for the whole warp, so the partial sum is a jump into a fall-through chain
         // (cu adds, no divergence) instead of a 16-way register select per lane.
-        int s16 = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) s16 += d[k];
+        const int s16 = 16 * tbase + xsum;
         const unsigned a0 = (unsigned)p.rs + (unsigned)warp_base;     // absolute, < 2^32
         const unsigned uW = (unsigned)p.W;
         // iw = a0 / W without a division: q = hi32(a0 * floor(2^32/W)) is the quotient or one less
@@ -504,23 +504,24 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
             const int el = (int)(edge >> 4);                          // lane holding the edge (>= 32: beyond the warp)
             int part = 0;
             switch (edge & 15u) {                                     // warp-uniform
-                case 15: part += d[14]; [[fallthrough]];
-                case 14: part += d[13]; [[fallthrough]];
-                case 13: part += d[12]; [[fallthrough]];
-                case 12: part += d[11]; [[fallthrough]];
-                case 11: part += d[10]; [[fallthrough]];
-                case 10: part += d[9]; [[fallthrough]];
-                case 9: part += d[8]; [[fallthrough]];
-                case 8: part += d[7]; [[fallthrough]];
-                case 7: part += d[6]; [[fallthrough]];
-                case 6: part += d[5]; [[fallthrough]];
-                case 5: part += d[4]; [[fallthrough]];
-                case 4: part += d[3]; [[fallthrough]];
-                case 3: part += d[2]; [[fallthrough]];
-                case 2: part += d[1]; [[fallthrough]];
-                case 1: part += d[0]; [[fallthrough]];
+                case 15: part += x[14]; [[fallthrough]];
+                case 14: part += x[13]; [[fallthrough]];
+                case 13: part += x[12]; [[fallthrough]];
+                case 12: part += x[11]; [[fallthrough]];
+                case 11: part += x[10]; [[fallthrough]];
+                case 10: part += x[9]; [[fallthrough]];
+                case 9: part += x[8]; [[fallthrough]];
+                case 8: part += x[7]; [[fallthrough]];
+                case 7: part += x[6]; [[fallthrough]];
+                case 6: part += x[5]; [[fallthrough]];
+                case 5: part += x[4]; [[fallthrough]];
+                case 4: part += x[3]; [[fallthrough]];
+                case 3: part += x[2]; [[fallthrough]];
+                case 2: part += x[1]; [[fallthrough]];
+                case 1: part += x[0]; [[fallthrough]];
                 default: break;
             }
+            part += (int)(edge & 15u) * tbase;
             const int cur = lane < el ? s16 : (lane == el ? part : 0);
             const unsigned tot = (unsigned)__reduce_add_sync(kFull, cur - counted);
             counted = cur;
@@ -600,6 +601,8 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
         }
     }
 }
+
+#undef GL_D
 
 // GENERAL path, K_scan: coalesced load of the tile's differences -> swizzled smem -> tile core.
 __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanParams p) {
