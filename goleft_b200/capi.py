@@ -177,6 +177,19 @@ def format_chunk(chrom: str, rs: int, re: int, W: int, win_sum: np.ndarray, run_
         lib.gl_free_text(c)
 
 
+def chunk_rows(rs: int, re: int, W: int, run_start: np.ndarray, run_class: np.ndarray):
+    """Host-only: (s, e) of the window rows gl_depth_format_chunk writes for a chunk, in order."""
+    run_start = _as(run_start, np.int32)
+    run_class = _as(run_class, np.uint8)
+    n = C.c_int64(0)
+    lib.gl_depth_chunk_rows(rs, re, W, _ptr(run_start), _ptr(run_class), run_start.size, None, None, 0, C.byref(n))
+    s, e = np.empty(n.value, np.int64), np.empty(n.value, np.int64)
+    rc = lib.gl_depth_chunk_rows(rs, re, W, _ptr(run_start), _ptr(run_class), run_start.size, _ptr(s), _ptr(e), n.value, C.byref(n))
+    if rc != GL_OK:
+        raise GlError(rc, "gl_depth_chunk_rows: bad arguments")
+    return s, e
+
+
 def pack_segments16(start: np.ndarray, end: np.ndarray):
     """Host-only: (anchors int32[nb], off uint16[nb*256], len uint16[nb*256]) — the feeder's compact format."""
     start, end = _as(start, np.int32), _as(end, np.int32)

@@ -325,3 +325,24 @@ def test_pack_segments8_roundtrip():
     s3, e3 = capi.unpack_segments8(a3, d3, l3)
     assert np.array_equal(np.sort(s3), np.sort(s2)) and (e3 - s3).sum() == (e2 - s2).sum()
     assert capi.pack_segments8(np.zeros(0, np.int32), np.zeros(0, np.int32))[0].size == 0
+
+
+def test_chunk_rows_match_the_formatted_text():
+    """gl_depth_chunk_rows (what --stats computes GC/CpG/masked for) lists exactly the (s, e) of the rows
+    gl_depth_format_chunk prints, quirk rows included (misaligned last window, re-emitted window: depth.go:329-358)."""
+    rng = np.random.default_rng(21)
+    for _ in range(400):
+        W = int(rng.choice([1, 7, 10, 50, 100, 1000]))
+        rs = int(rng.integers(0, 3000))
+        re = rs + int(rng.integers(1, 2500))
+        depth = np.zeros(re - rs, np.int32)
+        for _ in range(int(rng.integers(0, 4))):                    # a few covered stretches, often ending early
+            a = int(rng.integers(0, re - rs)); b = min(re - rs, a + int(rng.integers(1, 600)))
+            depth[a:b] += int(rng.integers(1, 9))
+        es, _ = orc.window_sums(depth, rs, re, W)
+        ea, ec = orc.class_runs(depth, rs, re, 4, 0, 0)
+        hd, _ = capi.format_chunk("c", rs, re, W, es, ea, ec)
+        s, e = capi.chunk_rows(rs, re, W, ea, ec)
+        rows = [ln.split(b"\t") for ln in hd.splitlines()]
+        assert [int(r[1]) for r in rows] == s.tolist() and [int(r[2]) for r in rows] == e.tolist()
+        assert hd == orc.walk_chunk("c", rs, re, W, 4, 0, depth)[0]
