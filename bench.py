@@ -437,7 +437,7 @@ def main():
                                 "achieved": alg[gdom] / (k_ms_general[gdom] * 1e-3) / 1e9,
                                 "frac": alg[gdom] / (k_ms_general[gdom] * 1e-3) / 1e9 / peak},
                "clocks": clocks}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:         # rank 0 at N=1 only (the other ranks' feeders share the host cores at N>1)
             from oracle import loader as orc       # cpu_baseline leg: the oracle port timed on this box's host cores
             threads = os.cpu_count() or 1
             chunks = orc.gen_chunks(L, W)
