@@ -125,10 +125,18 @@ _proto("gl_depth_region_packed16", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_pack_segments8_bound", C.c_int64, C.c_int64)
 _proto("gl_pack_segments8", C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_pack_segments8_mt", C.c_int, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_depth_add_segments_packed8", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_add_segments_packed8_device", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_region_packed8", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_depth_text", C.c_int, _vp, C.c_char_p, _vp, C.c_int64, _i64p, _vp, C.c_int64, _i64p)
+_proto("gl_depth_text_bound", C.c_int64, C.c_char_p, C.c_int64)
+_proto("gl_depth_format_rows", C.c_int, _vp, C.c_char_p, _vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _i64p)
+_proto("gl_depth_bed_contig", C.c_int, _vp, C.c_char_p, C.c_int64, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+       C.c_int32, _vp, C.c_int64, _i64p, _vp, C.c_int64, _i64p)
+_proto("gl_depth_bed_contig_packed8", C.c_int, _vp, C.c_char_p, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+       C.c_int64, _vp, C.c_int64, _i64p, _vp, C.c_int64, _i64p)
 _proto("gl_indexsplit_accumulate", C.c_int, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp)
 _proto("gl_indexsplit_chunks", C.c_int, _vp, _vp, C.c_int32, C.POINTER(C.c_char_p), _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int64,
        C.POINTER(_vp), _i64p)
@@ -245,8 +253,9 @@ def indexsplit_chunks(tile_sum, out_ptr, names, ref_lens, ref_ids, N: int, probl
         lib.gl_free_text(t)
 
 
-def pack_segments8(start: np.ndarray, end: np.ndarray):
-    """Host-only: (anchors int32[nb], dstart uint8[nb*64], len uint8[nb*64]) — the feeder's densest format (short reads)."""
+def pack_segments8(start: np.ndarray, end: np.ndarray, threads: Optional[int] = None):
+    """Host-only: (anchors int32[nb], dstart uint8[nb*64], len uint8[nb*64]) — the feeder's densest format (short reads).
+    threads=None: the single-threaded packer; an int: gl_pack_segments8_mt (0 = all pool threads)."""
     start, end = _as(start, np.int32), _as(end, np.int32)
     nb = C.c_int64(0)
     cap = max(1, start.size // 48 + 64)
@@ -254,7 +263,10 @@ def pack_segments8(start: np.ndarray, end: np.ndarray):
         a = np.empty(cap, np.int32)
         d = np.empty(cap * 64, np.uint8)
         ln = np.empty(cap * 64, np.uint8)
-        rc = lib.gl_pack_segments8(_ptr(start), _ptr(end), start.size, _ptr(a), _ptr(d), _ptr(ln), cap, C.byref(nb))
+        if threads is None:
+            rc = lib.gl_pack_segments8(_ptr(start), _ptr(end), start.size, _ptr(a), _ptr(d), _ptr(ln), cap, C.byref(nb))
+        else:
+            rc = lib.gl_pack_segments8_mt(_ptr(start), _ptr(end), start.size, threads, _ptr(a), _ptr(d), _ptr(ln), cap, C.byref(nb))
         if rc == GL_OK:
             k = nb.value
             return a[:k], d[: k * 64], ln[: k * 64]
@@ -566,6 +578,69 @@ class Ctx:
                                      _ptr(s), s.size, C.byref(nw), _ptr(r0), _ptr(rc_), min(r0.size, rc_.size),
                                      C.byref(nr)))
         return s[: nw.value], r0[: nr.value], rc_[: nr.value]
+
+    # ---- depth text (device formatter)
+    def _text_bufs(self, chrom: str, n_win: int, out):
+        if out is None:
+            out = (np.empty(int(lib.gl_depth_text_bound(chrom.encode(), n_win)), np.uint8), np.empty(1 << 16, np.uint8))
+        return out
+
+    def depth_text(self, chrom: str, out=None) -> Tuple[bytes, bytes]:
+        """(depth.bed bytes, callable.bed bytes) of the last reduce, formatted on the device."""
+        nw, _, _ = self.depth_result_sizes()
+        hd, ca = self._text_bufs(chrom, nw, out)
+        hl, cl = C.c_int64(0), C.c_int64(0)
+        rc = lib.gl_depth_text(self.h, chrom.encode(), _ptr(hd), hd.size, C.byref(hl), _ptr(ca), ca.size, C.byref(cl))
+        if rc == GL_ERANGE and out is None:
+            hd, ca = np.empty(hl.value + 16, np.uint8), np.empty(cl.value + 16, np.uint8)
+            rc = lib.gl_depth_text(self.h, chrom.encode(), _ptr(hd), hd.size, C.byref(hl), _ptr(ca), ca.size, C.byref(cl))
+        self._ck(rc)
+        return hd[: hl.value].tobytes(), ca[: cl.value].tobytes()
+
+    def depth_format_rows(self, chrom: str, row_s, row_e, row_sum) -> bytes:
+        row_s, row_e, row_sum = _as(row_s, np.int32), _as(row_e, np.int32), _as(row_sum, np.int64)
+        out = np.empty(row_s.size * (len(chrom) + 33) + 16, np.uint8)
+        ln = C.c_int64(0)
+        self._ck(lib.gl_depth_format_rows(self.h, chrom.encode(), _ptr(row_s), _ptr(row_e), _ptr(row_sum), row_s.size, _ptr(out),
+                                          out.size, C.byref(ln)))
+        return out[: ln.value].tobytes()
+
+    def depth_bed_contig(self, chrom: str, length: int, start, end, W: int, mincov: int = 4, maxmean: int = 0,
+                         step: int = 10_000_000, threads: int = 0, out=None, raw: bool = False):
+        """One call: host int32 segments in -> (depth.bed, callable.bed) bytes out.  raw=True returns the two lengths only
+        (the bytes are in `out`)."""
+        n_win = (length - 1) // W + 1
+        keep = out is not None
+        hd, ca = self._text_bufs(chrom, n_win, out)
+        hl, cl = C.c_int64(0), C.c_int64(0)
+        cb = chrom.encode()
+        rc = lib.gl_depth_bed_contig(self.h, cb, length, _ptr(start), _ptr(end), start.size, W, mincov, maxmean, step, threads,
+                                     _ptr(hd), hd.size, C.byref(hl), _ptr(ca), ca.size, C.byref(cl))
+        if rc == GL_ERANGE and not keep:
+            hd, ca = np.empty(hl.value + 16, np.uint8), np.empty(cl.value + 16, np.uint8)
+            rc = lib.gl_depth_bed_contig(self.h, cb, length, _ptr(start), _ptr(end), start.size, W, mincov, maxmean, step, threads,
+                                         _ptr(hd), hd.size, C.byref(hl), _ptr(ca), ca.size, C.byref(cl))
+        self._ck(rc)
+        if raw:
+            return hl.value, cl.value
+        return hd[: hl.value].tobytes(), ca[: cl.value].tobytes()
+
+    def depth_bed_contig_packed8(self, chrom: str, length: int, anchors, dstart, ln, W: int, mincov: int = 4, maxmean: int = 0,
+                                 step: int = 10_000_000, out=None, raw: bool = False):
+        n_win = (length - 1) // W + 1
+        keep = out is not None
+        hd, ca = self._text_bufs(chrom, n_win, out)
+        hl, cl = C.c_int64(0), C.c_int64(0)
+        cb = chrom.encode()
+        args = (self.h, cb, length, _ptr(anchors), _ptr(dstart), _ptr(ln), anchors.size, W, mincov, maxmean, step)
+        rc = lib.gl_depth_bed_contig_packed8(*args, _ptr(hd), hd.size, C.byref(hl), _ptr(ca), ca.size, C.byref(cl))
+        if rc == GL_ERANGE and not keep:
+            hd, ca = np.empty(hl.value + 16, np.uint8), np.empty(cl.value + 16, np.uint8)
+            rc = lib.gl_depth_bed_contig_packed8(*args, _ptr(hd), hd.size, C.byref(hl), _ptr(ca), ca.size, C.byref(cl))
+        self._ck(rc)
+        if raw:
+            return hl.value, cl.value
+        return hd[: hl.value].tobytes(), ca[: cl.value].tobytes()
 
     # ---- indexcov
     def indexcov_sizes(self, voff: np.ndarray, ref_ptr: np.ndarray):

@@ -1884,6 +1884,66 @@ int gl_depth_region(gl_ctx* ctx, int64_t region_start, int64_t region_end, const
     return region_fetch(ctx, sum_out, win_cap, n_windows, run_start, run_class, run_cap, n_runs);
 }
 
+// ---- one contig, segments in, BED text out (depth/depth.go:238-364 for every 10 Mb chunk of the contig, in order)
+int gl_depth_bed_contig_packed8(gl_ctx* ctx, const char* chrom, int64_t contig_len, const int32_t* anchors, const uint8_t* dstart,
+                                const uint8_t* len, int64_t n_blocks, int32_t W, int32_t mincov, int32_t maxmean, int64_t step,
+                                char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed, int64_t callable_cap,
+                                int64_t* callable_len) {
+    if (W <= 0 || step <= 0 || step % W != 0) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_contig: step must be a positive multiple of W (depth.go:132)");
+    GL_CHECK(gl_depth_begin(ctx, 0, contig_len));
+    GL_CHECK(add_packed8_host(ctx, anchors, dstart, len, n_blocks, true));
+    GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, step));
+    return gl_depth_text(ctx, chrom, depth_bed, depth_cap, depth_len, callable_bed, callable_cap, callable_len);
+}
+
+int gl_depth_bed_contig(gl_ctx* ctx, const char* chrom, int64_t contig_len, const int32_t* start, const int32_t* end, int64_t n,
+                        int32_t W, int32_t mincov, int32_t maxmean, int64_t step, int32_t threads,
+                        char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed, int64_t callable_cap,
+                        int64_t* callable_len) {
+    GL_CHECK(gl_use(ctx));
+    if (W <= 0 || step <= 0 || step % W != 0) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_contig: step must be a positive multiple of W (depth.go:132)");
+    if (n < 0 || (n > 0 && (!start || !end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_contig: bad segments");
+    // short reads (what a 30x WGS BAM holds): pack to 2 B/segment on the host threads, a quarter of the PCIe bytes;
+    // long segments would be cut into many 255-base pieces, so they go up as plain int32.  Judged on a sample.
+    static const int force = [] { const char* e = getenv("GL_BED_PACK"); return e ? atoi(e) : -1; }();   // 0: never pack, 1: always
+    bool pack = n >= 4096;
+    if (pack && force < 0) {
+        int64_t tot = 0, cnt = 0;
+        for (int part = 0; part < 4; part++)
+            for (int64_t i = (n - 1024) * part / 3, j = 0; j < 1024; j++, i++) { tot += std::max<int64_t>(0, (int64_t)end[i] - start[i]); cnt++; }
+        pack = tot <= 400 * cnt;
+    } else if (force >= 0) pack = force != 0 && n > 0;
+    if (!pack) {
+        GL_CHECK(gl_depth_begin(ctx, 0, contig_len));
+        GL_CHECK(gl_depth_add_segments(ctx, start, end, n));
+        GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, step));
+        return gl_depth_text(ctx, chrom, depth_bed, depth_cap, depth_len, callable_bed, callable_cap, callable_len);
+    }
+    int64_t cap = n / 40 + 1024, nb = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const size_t bytes = (size_t)cap * 132 + 256;
+        if (ctx->pack_pinned_bytes < bytes) {
+            GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            if (ctx->pack_pinned) cudaFreeHost(ctx->pack_pinned);
+            ctx->pack_pinned = nullptr; ctx->pack_pinned_bytes = 0;
+            cudaError_t e = cudaHostAlloc(&ctx->pack_pinned, bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) { ctx->pack_pinned = nullptr; cudaGetLastError(); return gl_fail(ctx, GL_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+            ctx->pack_pinned_bytes = bytes;
+        }
+        const int64_t cap_now = (int64_t)((ctx->pack_pinned_bytes - 256) / 132);
+        int32_t* a = static_cast<int32_t*>(ctx->pack_pinned);
+        uint8_t* d = reinterpret_cast<uint8_t*>(a + ((cap_now + 3) & ~int64_t(3)));
+        uint8_t* l = d + (size_t)cap_now * 64;
+        // (an earlier call's upload out of this buffer has finished: every entry point synchronises before it returns)
+        const int rc = gl_pack_segments8_mt(start, end, n, threads, a, d, l, cap_now, &nb);
+        if (rc == GL_ERANGE) { cap = nb + 16; continue; }
+        if (rc != GL_OK) return gl_fail(ctx, rc, "gl_pack_segments8_mt failed");
+        return gl_depth_bed_contig_packed8(ctx, chrom, contig_len, a, d, l, nb, W, mincov, maxmean, step, depth_bed, depth_cap, depth_len,
+                                           callable_bed, callable_cap, callable_len);
+    }
+    return gl_fail(ctx, GL_ERANGE, "gl_depth_bed_contig: packing did not converge");
+}
+
 static int region_fetch(gl_ctx* ctx, int64_t* sum_out, int64_t win_cap, int64_t* n_windows, int32_t* run_start, uint8_t* run_class,
                         int64_t run_cap, int64_t* n_runs) {
     const int64_t nw = ctx->n_windows, nr = ctx->n_runs;

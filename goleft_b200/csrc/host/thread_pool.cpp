@@ -1,0 +1,109 @@
+// thread_pool.cpp — see thread_pool.h
+#include "thread_pool.h"
+#include <stdlib.h>
+#include <chrono>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define GL_CPU_PAUSE() _mm_pause()
+#else
+#define GL_CPU_PAUSE() ((void)0)
+#endif
+
+namespace glhost {
+
+namespace {
+constexpr int kLimitBits = 16;                         // gen word = (generation << 16) | participating threads
+constexpr auto kSpin = std::chrono::microseconds(200); // how long an idle worker spins before it sleeps
+}  // namespace
+
+int ThreadPool::default_threads() {
+    if (const char* e = getenv("GL_THREADS")) {
+        const int v = atoi(e);
+        if (v > 0) return v > 1024 ? 1024 : v;
+    }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? (int)hc : 1;
+}
+
+ThreadPool& ThreadPool::global() {
+    static ThreadPool pool(default_threads());
+    return pool;
+}
+
+ThreadPool::ThreadPool(int threads) {
+    if (threads < 1) threads = 1;
+    for (int i = 1; i < threads; i++) workers_.emplace_back([this, i] { worker_main(i); });
+}
+
+ThreadPool::~ThreadPool() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+}
+
+void ThreadPool::work(int id) {
+    const std::function<void(int64_t, int)>& fn = *fn_;
+    const int64_t n = n_tasks_;
+    for (;;) {
+        const int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
+        if (i >= n) break;
+        fn(i, id);
+    }
+}
+
+void ThreadPool::worker_main(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+        uint64_t g = gen_.load(std::memory_order_acquire);
+        if (g == seen) {
+            const auto t0 = std::chrono::steady_clock::now();
+            while ((g = gen_.load(std::memory_order_acquire)) == seen && !stop_.load(std::memory_order_relaxed)) {
+                GL_CPU_PAUSE();
+                if (std::chrono::steady_clock::now() - t0 > kSpin) {
+                    std::unique_lock<std::mutex> lk(mu_);
+                    cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen || stop_.load(); });
+                    g = gen_.load(std::memory_order_acquire);
+                    break;
+                }
+            }
+        }
+        if (stop_.load()) return;
+        if (g == seen) continue;
+        seen = g;
+        const int limit = (int)(g & ((1u << kLimitBits) - 1));
+        if (id < limit) {
+            work(id);
+            active_.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+}
+
+void ThreadPool::run(int64_t n_tasks, const std::function<void(int64_t, int)>& fn, int max_threads) {
+    if (n_tasks <= 0) return;
+    std::lock_guard<std::mutex> run_lk(run_mu_);
+    int limit = size();
+    if (max_threads > 0 && max_threads < limit) limit = max_threads;
+    if ((int64_t)limit > n_tasks) limit = (int)n_tasks;
+    if (limit <= 1) {
+        for (int64_t i = 0; i < n_tasks; i++) fn(i, 0);
+        return;
+    }
+    fn_ = &fn;
+    n_tasks_ = n_tasks;
+    next_.store(0, std::memory_order_relaxed);
+    active_.store(limit - 1, std::memory_order_relaxed);
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        const uint64_t generation = (gen_.load(std::memory_order_relaxed) >> kLimitBits) + 1;
+        gen_.store((generation << kLimitBits) | (uint64_t)limit, std::memory_order_release);
+    }
+    cv_.notify_all();
+    work(0);
+    while (active_.load(std::memory_order_acquire) != 0) GL_CPU_PAUSE();
+    fn_ = nullptr;
+}
+
+}  // namespace glhost

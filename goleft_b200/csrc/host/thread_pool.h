@@ -1,0 +1,41 @@
+// thread_pool.h — a small persistent worker pool for the host side of the feeder (segment packing, BGZF inflate,
+// record parsing, row assembly).  Work is a counted loop: run(n, fn) calls fn(i, worker) for i in [0, n), tasks claimed
+// in index order (so a task may wait for lower-numbered tasks without deadlock), the calling thread takes part.
+// Workers spin briefly after a job before they sleep, so back-to-back calls (one per contig) do not pay a futex wake-up.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace glhost {
+
+class ThreadPool {
+public:
+    explicit ThreadPool(int threads);
+    ~ThreadPool();
+    int size() const { return (int)workers_.size() + 1; }                    // workers + the caller
+    // fn(task, worker): worker in [0, size()).  Uses at most max_threads threads (0 = all).  Not re-entrant.
+    void run(int64_t n_tasks, const std::function<void(int64_t, int)>& fn, int max_threads = 0);
+    static ThreadPool& global();                                             // sized by GL_THREADS or hardware_concurrency
+    static int default_threads();
+
+private:
+    void worker_main(int id);
+    void work(int id);
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<int64_t> next_{0};
+    std::atomic<int> active_{0};
+    std::atomic<bool> stop_{false};
+    int64_t n_tasks_ = 0;
+    int limit_ = 0;
+    const std::function<void(int64_t, int)>* fn_ = nullptr;
+    std::mutex run_mu_;
+};
+
+}  // namespace glhost

@@ -120,6 +120,11 @@ int  gl_depth_add_segments_packed16(gl_ctx* ctx, const int32_t* anchors, const u
 int64_t gl_pack_segments8_bound(int64_t n);
 int  gl_pack_segments8(const int32_t* start, const int32_t* end, int64_t n, int32_t* anchors, uint8_t* dstart, uint8_t* len,
                        int64_t cap_blocks, int64_t* n_blocks);
+/* The same format from `threads` host threads (0 = all of the library's pool; GL_THREADS sets its size): the input is cut
+ * into position ranges that are packed independently and concatenated, so the blocks differ from gl_pack_segments8's at the
+ * range edges (a block may end early) but decode to the same multiset of pieces.  Host-only. */
+int  gl_pack_segments8_mt(const int32_t* start, const int32_t* end, int64_t n, int32_t threads, int32_t* anchors, uint8_t* dstart,
+                          uint8_t* len, int64_t cap_blocks, int64_t* n_blocks);
 int  gl_depth_add_segments_packed8(gl_ctx* ctx, const int32_t* anchors, const uint8_t* dstart, const uint8_t* len, int64_t n_blocks);
 /* same with the three arrays already in device memory (caller-owned, 8-byte aligned, must stay valid until the region's
  * last reduce): nothing is copied; a region whose only batch is packed8 is reduced straight from these words. */
@@ -177,6 +182,33 @@ int  gl_depth_region_packed8(gl_ctx* ctx, int64_t region_start, int64_t region_e
                              const uint8_t* dstart, const uint8_t* len, int64_t n_blocks, int32_t W, int32_t mincov, int32_t maxmean,
                              int64_t run_break, int64_t* sum_out, int64_t win_cap, int64_t* n_windows, int32_t* run_start,
                              uint8_t* run_class, int64_t run_cap, int64_t* n_runs);
+
+/* BED text of the last gl_depth_reduce, formatted ON THE DEVICE (depth_text.cu): only finished bytes cross PCIe.
+ *   depth_bed    : "chrom\tstart\tend\t%.4g\n" per window (depth/depth.go:301,337,357; mean = float64(sum)/float64(e-s),
+ *                  depth.go:181-189; the four digits are rounded half-even on the exact binary value, like strconv),
+ *   callable_bed : "chrom\tstart\tend\tCLASS\n" per class run (depth.go:312-349).
+ * Needs region_start % W == 0 and run_break % W == 0: then the reference's per-chunk rows (incl. its tail rows,
+ * depth.go:329-358) are exactly the genome-aligned windows of the region, each once.  BED-mode regions with unaligned
+ * starts go through gl_depth_chunk_rows + gl_depth_format_rows (explicit rows) or gl_depth_format_chunk (host).
+ * GL_ERANGE with both lengths set when a buffer is too small; gl_depth_text_bound() is always enough for depth_bed. */
+int  gl_depth_text(gl_ctx* ctx, const char* chrom, char* depth_bed, int64_t depth_cap, int64_t* depth_len,
+                   char* callable_bed, int64_t callable_cap, int64_t* callable_len);
+int64_t gl_depth_text_bound(const char* chrom, int64_t n_windows);
+/* n explicit window rows (s, e, sum) -> the same row text (the misaligned / re-emitted rows of depth.go:329-358) */
+int  gl_depth_format_rows(gl_ctx* ctx, const char* chrom, const int32_t* row_s, const int32_t* row_e, const int64_t* row_sum,
+                          int64_t n, char* out, int64_t cap, int64_t* len);
+/* One contig end to end, the call `goleft depth` makes per reference sequence in .fai mode (depth.go:129-159 + the
+ * callback 238-364 for each of its chunks, concatenated in order): host segments in -> BED bytes out.  step = the chunk
+ * length (depth.go:132: a multiple of W).  Short-read input is packed to packed8 on `threads` host threads (0 = all)
+ * and streamed up while the first tiles reduce; long segments go up as int32.  Everything is inside the call. */
+int  gl_depth_bed_contig(gl_ctx* ctx, const char* chrom, int64_t contig_len, const int32_t* start, const int32_t* end, int64_t n,
+                         int32_t W, int32_t mincov, int32_t maxmean, int64_t step, int32_t threads,
+                         char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed, int64_t callable_cap,
+                         int64_t* callable_len);
+int  gl_depth_bed_contig_packed8(gl_ctx* ctx, const char* chrom, int64_t contig_len, const int32_t* anchors, const uint8_t* dstart,
+                                 const uint8_t* len, int64_t n_blocks, int32_t W, int32_t mincov, int32_t maxmean, int64_t step,
+                                 char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed, int64_t callable_cap,
+                                 int64_t* callable_len);
 
 /* Host-side text: reproduces the rows the reference callback writes for ONE chunk
  * [rs,re) (depth/depth.go:293-305,326-358 incl. the chunk-edge quirks) from window sums

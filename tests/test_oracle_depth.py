@@ -346,3 +346,31 @@ def test_chunk_rows_match_the_formatted_text():
         rows = [ln.split(b"\t") for ln in hd.splitlines()]
         assert [int(r[1]) for r in rows] == s.tolist() and [int(r[2]) for r in rows] == e.tolist()
         assert hd == orc.walk_chunk("c", rs, re, W, 4, 0, depth)[0]
+
+
+def test_pack_segments8_mt_same_pieces():
+    """the parallel packer yields sorted anchors and the same multiset of pieces as the single-threaded one"""
+    from goleft_b200 import capi, synth
+    for L, cov, idx in ((3_000_000, 30.0, 1), (500_000, 200.0, 2), (2_000_000, 2.0, 3)):
+        s, e = synth.segments(synth.reads(L, coverage=cov, contig_index=idx))
+        a1, d1, l1 = capi.pack_segments8(s, e)
+        u1s, u1e = capi.unpack_segments8(a1, d1, l1)
+        o1 = np.lexsort((u1e, u1s))
+        for T in (0, 2, 3, 8):
+            a2, d2, l2 = capi.pack_segments8(s, e, threads=T)
+            assert (np.diff(a2) >= 0).all()
+            u2s, u2e = capi.unpack_segments8(a2, d2, l2)
+            o2 = np.lexsort((u2e, u2s))
+            assert np.array_equal(u1s[o1], u2s[o2]) and np.array_equal(u1e[o1], u2e[o2])
+            # every block's starts stay within [anchor, next anchor]
+            st = a2.astype(np.int64)[:, None] + np.cumsum(d2.reshape(-1, 64).astype(np.int64), axis=1)
+            assert (st[:-1].max(axis=1) <= a2[1:]).all()
+    # long segments and wild disorder still decode to the same coverage
+    rng = np.random.default_rng(0)
+    s = rng.integers(0, 1_000_000, 50_000).astype(np.int32)
+    e = (s + rng.integers(1, 5000, s.size)).astype(np.int32)
+    a2, d2, l2 = capi.pack_segments8(s, e, threads=4)
+    assert (np.diff(a2) >= 0).all()
+    u2s, u2e = capi.unpack_segments8(a2, d2, l2)
+    assert int((u2e - u2s).sum()) == int((e.astype(np.int64) - s).sum())
+    assert np.array_equal(orc.pileup_diff(u2s.astype(np.int32), u2e.astype(np.int32), 0, 1_010_000), orc.pileup_diff(s, e, 0, 1_010_000))
