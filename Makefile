@@ -22,7 +22,7 @@ HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/host/*.h) include/gole
 NCCL_INC  ?= /usr/include
 NCCL_LIB  ?= /usr/lib/x86_64-linux-gnu
 
-all: lib cli oracle
+all: lib cli oracle synth
 
 lib: $(LIB)
 
@@ -54,7 +54,13 @@ oracle/_build/liboracle.so: $(wildcard oracle/*.c)
 	@mkdir -p oracle/_build
 	$(CC) -O3 -march=x86-64-v2 -fPIC -shared -Wall -ffp-contract=off -o $@ $^ -lm -lpthread
 
-clean:
-	rm -rf $(BUILD) $(LIB) bin oracle/_build
+# bench workload generator (both bench arms load it; not part of the product library)
+synth: tools/synth/libglsynth.so
 
-.PHONY: all lib cli oracle clean
+tools/synth/libglsynth.so: tools/synth/glsynth.c
+	$(CC) -O2 -fPIC -shared -Wall -o $@ $< -lpthread
+
+clean:
+	rm -rf $(BUILD) $(LIB) bin oracle/_build tools/synth/libglsynth.so
+
+.PHONY: all lib cli oracle synth clean

@@ -1,21 +1,22 @@
 #!/usr/bin/env python
 """bench.py — Mbases/s depth-counted on a synthetic 30x WGS-shaped alignment stream (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload wgs|chr20]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" = one pass of the depth hot path over one contig: segments -> per-base depth (on chip only)
--> per-window sums + callable-class runs (gl_depth_begin / add_segments / reduce).
-Workload at N=1 = BASELINE config[1]: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500.
-At N>1 every rank processes its own chr20-sized contig (contigs shard across GPUs with no
-data-path collective) -> weak scaling; value = N * bases / max-over-ranks device time.
+Workload (default, every N): BASELINE configs[2], the 25 primary GRCh38 contigs (3,088,286,401 bp) at 30x / 150 bp
+reads, W=500 — STRONG scaling: the same genome at every N, contigs dealt to the ranks longest-first (gl_lpt_assign, the
+function the CLI's --gpus uses), no data-path collective.  A "step" = one pass of the depth hot path over the rank's
+contigs; time = max over ranks; value = genome bases / that time.
+    --workload chr20 : BASELINE configs[1] (one 64,444,167 bp contig per rank, weak-scaling replicas; round 1's bench).
 
-value  : inputs already resident in HBM in the engine's segment format (packed8) before the timed region;
-         int32_resident: the same from plain int32 (start,end) device arrays.
-e2e    : the one-call C-ABI entry gl_depth_region_packed8 (the feeder's short-read format, 2 B/segment) with
-         PINNED HOST buffers: H2D of the segments, all kernels and D2H of window sums + runs are inside the
-         timed region, every step.  e2e_packed16 / e2e_int32: the same through the 4 B and 8 B/segment entries.
-roofline / cpu_baseline: see DESIGN.md §Measurement.
+value : the rank's contigs already resident in HBM in the engine's segment format (packed8); per step, per contig:
+        gl_depth_begin / add_segments_packed8_device / gl_depth_reduce (window sums + class runs stay on the device).
+e2e   : the drop-in call, per contig: gl_depth_bed_contig — decoder-native int32 (start,end) segments in PINNED HOST
+        memory in, finished .depth.bed + .callable.bed BYTES out in pinned host memory.  H2D of the segments, every
+        kernel, the device %.4g row formatter and the D2H of the text are inside the timed region, every step.  This is
+        the work the reference arm is charged for (per-base counting + window/class walk + BED text).
+roofline / cpu_baseline : DESIGN.md §3.
 """
 import argparse
 import json
@@ -29,12 +30,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools", "synth"))
 
 W = 500
 MINCOV = 4
 MAXMEAN = 0
-STEP = 10_000_000           # depth/depth.go:48 (a multiple of W=500)
+STEP = 10_000_000           # depth/depth.go:48,132 (a multiple of W=500)
 METRIC = "Mbases/s depth-counted (synth 30x WGS)"
+WORKLOADS = {
+    "wgs": "depth: synthetic 30x whole genome (25 GRCh38 contigs, 3,088,286,401 bp, 150 bp reads), W=500, 1 sample, contigs sharded over the GPUs",
+    "chr20": "depth: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500, 1 sample",
+}
 
 
 def log(*a):
@@ -99,12 +105,14 @@ class ClockSampler:
 
 
 def ncu_traffic(kernel):
-    """dram__bytes_read+write per launch of `kernel` from the committed ncu --set full capture (profiles/), or None"""
-    try:
-        j = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))
-        return int(j[kernel]["traffic_bytes"])
-    except Exception:
-        return None
+    """dram__bytes_read+write per launch of `kernel` from the committed ncu --set full captures (profiles/), or None"""
+    for name in ("r02_ncu_full_summary.json", "r01_ncu_full_summary.json"):
+        try:
+            j = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return int(j[kernel]["traffic_bytes"]), name
+        except Exception:
+            continue
+    return None, None
 
 
 def dist_env():
@@ -114,68 +122,97 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_depth_pass(orc, s, e, L, threads, chunks):
-    """The reference's CPU path for one contig, chunk-parallel like `goleft depth -p`:
-    per 10 Mb chunk, per-base counting (the samtools child) + the callback's window/class walk + BED text."""
-    from concurrent.futures import ThreadPoolExecutor
-    order = np.argsort(s, kind="stable") if not (np.diff(s) >= 0).all() else None
-    if order is not None:
-        s, e = s[order], e[order]
-    maxlen = int((e - s).max()) if s.size else 0
+def contig_list(workload, world):
+    import glsynth
+    if workload == "wgs":
+        return [(nm, ln, i) for i, (nm, ln) in enumerate(glsynth.GRCH38)]
+    return [("chr20", glsynth.CHR20_LEN, 19 + r) for r in range(world)]      # one replica per rank (seed differs)
 
-    def one(ch):
-        cs, ce = ch
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_genome_pass(orc, contigs, threads):
+    """The reference's CPU path, chunk-parallel like `goleft depth -p` (depth.go:132,392: one worker per 10 Mb chunk):
+    per chunk, per-base counting (the samtools child) + the callback's window/class walk + BED text.
+    contigs: [(name, length, start, end)] with nearly sorted segments.  Returns (seconds, text bytes, chunks)."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = []
+    for name, L, s, e in contigs:
+        maxlen = 1024                                        # short reads; the searchsorted slack below covers deletions
+        for cs, ce in orc.gen_chunks(L, W):
+            jobs.append((name, s, e, cs, ce, maxlen))
+
+    def one(j):
+        name, s, e, cs, ce, maxlen = j
         lo = np.searchsorted(s, cs - maxlen, "left")
         hi = np.searchsorted(s, ce, "left")
+        lo = max(0, lo - 4096)                               # starts are sorted up to one read's span
         d = orc.pileup_diff(s[lo:hi], e[lo:hi], cs, ce)
-        hd, ca = orc.walk_chunk("chr20", cs, ce, W, MINCOV, MAXMEAN, d)
+        hd, ca = orc.walk_chunk(name, cs, ce, W, MINCOV, MAXMEAN, d)
         return len(hd) + len(ca)
 
+    jobs.sort(key=lambda j: -(j[4] - j[3]))
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
-        nbytes = sum(ex.map(one, chunks))
-    return time.perf_counter() - t0, nbytes
+        nbytes = sum(ex.map(one, jobs))
+    return time.perf_counter() - t0, nbytes, len(jobs)
+
+
+def sorted_copy(s, e):
+    if s.size and not (np.diff(s) >= 0).all():
+        o = np.argsort(s, kind="stable")
+        return s[o], e[o]
+    return s, e
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; neither go nor samtools
-    exists in this image, so oracle/_ref cannot be built), all host threads, bounded sample."""
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: neither go nor samtools exists in
+    this image, so oracle/_ref cannot be built), all host threads, the same workload as the GPU arm."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    from goleft_b200 import synth
+    import glsynth
     from oracle import loader as orc
-    L = synth.CHR20_LEN
-    s, e = synth.chr20_like()
     threads = os.cpu_count() or 1
-    chunks = orc.gen_chunks(L, W)
-    times = []
+    contigs = []
+    t0 = time.time()
+    for nm, ln, idx in contig_list(args.workload, 1):
+        s, e = glsynth.segments(ln, idx, threads=threads)
+        s, e = sorted_copy(s, e)
+        contigs.append((nm, ln, s, e))
+    total = sum(c[1] for c in contigs)
+    nseg = sum(c[2].size for c in contigs)
+    log(f"[reference] synth: {nseg} segments over {total} bp in {time.time() - t0:.1f}s; {threads} threads")
+    times, chunks, budget0 = [], 0, time.time()
     for i in range(args.warmup + args.steps):
-        dt, _ = cpu_depth_pass(orc, s, e, L, threads, chunks)
+        dt, _, chunks = cpu_genome_pass(orc, contigs, threads)
         if i >= args.warmup:
             times.append(dt)
+        if times and time.time() - budget0 > 150:            # bounded: stop after ~2.5 min with at least one timed step
+            break
     t = float(np.mean(times))
-    val = L / t / 1e6
+    val = total / t / 1e6
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mbases/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-           "config": {"workload": "depth: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500, 1 sample",
-                      "window": W, "mincov": MINCOV, "segments": int(s.size)},
-           "cpu_baseline": {"value": val, "unit": "Mbases/s", "cores": min(threads, len(chunks)), "kind": "port",
-                            "sample": "whole chr20 contig, 7 chunks of 10 Mb, one thread per chunk (the reference's own unit of "
-                                      "parallelism, depth.go:132,392); per-base counting + window/class walk + BED text "
-                                      "(samtools text printing/parsing excluded)"},
+           "steps": len(times), "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+           "scaling": "strong" if args.workload == "wgs" else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+           "config": {"workload": WORKLOADS[args.workload], "window": W, "mincov": MINCOV, "segments": int(nseg)},
+           "cpu_baseline": {"value": val, "unit": "Mbases/s", "cores": min(threads, chunks), "cores_available": threads, "kind": "port",
+                            "sample": f"the whole workload per step: {chunks} chunks of 10 Mb, one worker per chunk (the reference's unit of "
+                                      "parallelism, depth.go:132,392) on all host threads; per-base counting + window/class walk + BED text "
+                                      "(BGZF inflate and samtools' text print/parse excluded: it under-estimates the reference)"},
            "e2e": {"value": val, "unit": "Mbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("GL_BENCH_WORKLOAD", "wgs"), choices=["wgs", "chr20"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-path extras (int32 / general path / packed e2e variants)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -185,25 +222,55 @@ def main():
     rank, world, local = dist_env()
     dist = None
     os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
+    from goleft_b200 import capi
+    import glsynth
+    if capi.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; goleft_b200 has no CPU fallback")
+
+    # ---- NUMA placement BEFORE any pinned allocation or pool thread exists: this rank's threads and staging buffers go
+    #      next to its GPU's PCIe root; ranks that share a socket split its cores.
+    nodes = [capi.device_numa_node(d) for d in range(world)] if world <= capi.device_count() else [-1] * world
+    my_node = nodes[local] if local < len(nodes) else -1
+    share = [r for r in range(world) if nodes[r] == my_node] if my_node >= 0 else list(range(world))
+    node, n_cpus = capi.bind_numa_for_device(local, share.index(local) if local in share else 0, len(share))
+    if node < 0:
+        n_cpus = max(1, (os.cpu_count() or 1) // world)
+        os.environ.setdefault("GL_THREADS", str(n_cpus))
+
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from goleft_b200 import capi, synth
-    if capi.device_count() < 1:
-        raise SystemExit("bench.py: no CUDA device; goleft_b200 has no CPU fallback")
-
-    L = synth.CHR20_LEN
-    t0 = time.time()
-    s, e = synth.chr20_like(contig_index=19 + rank)
-    nseg = int(s.size)
-    log(f"[rank {rank}] synth: {nseg} segments over {L} bp in {time.time() - t0:.1f}s")
+    # ---- this rank's share of the workload
+    contigs = contig_list(args.workload, world)
+    lengths = [c[1] for c in contigs]
+    if args.workload == "wgs":
+        bin_of, load = capi.lpt_assign(lengths, world)
+        mine = [i for i in range(len(contigs)) if bin_of[i] == rank]
+    else:
+        load = np.array(lengths, np.int64)
+        mine = [rank]
+    total_bases = int(sum(lengths))
+    my_bases = int(sum(lengths[i] for i in mine))
 
     ctx = capi.Ctx(local)
-    d_s, d_e = ctx.dev_array(s), ctx.dev_array(e)
-    n_win = (L - 1) // W + 1
+    t0 = time.time()
+    work = []               # per contig: dict(name, L, h_s, h_e (pinned int32), d_a, d_d, d_l (device packed8), nb, n_win)
+    for i in mine:
+        nm, L, idx = contigs[i]
+        h_s, h_e = glsynth.segments(L, idx, threads=n_cpus, alloc=ctx.pinned_empty)
+        qa, qd, ql = capi.pack_segments8(h_s, h_e, threads=0)
+        work.append({"name": nm, "L": L, "h_s": h_s, "h_e": h_e, "nseg": int(h_s.size), "nb": int(qa.size),
+                     "d_a": ctx.dev_array(qa), "d_d": ctx.dev_array(qd), "d_l": ctx.dev_array(ql),
+                     "p8_bytes": int(qa.nbytes + qd.nbytes + ql.nbytes), "n_win": (L - 1) // W + 1, "qa": qa, "qd": qd, "ql": ql})
+    nseg = sum(w["nseg"] for w in work)
+    log(f"[rank {rank}] numa node {node}, {n_cpus} cpus; {len(work)} contigs, {my_bases} bp, {nseg} segments in {time.time() - t0:.1f}s")
+    max_win = max(w["n_win"] for w in work)
+    longest_name = max((w["name"] for w in work), key=len)
+    o_hd = ctx.pinned_empty(int(capi.lib.gl_depth_text_bound(longest_name.encode(), max_win)), np.uint8)
+    o_ca = ctx.pinned_empty(max(1 << 20, max(w["L"] for w in work) // 64), np.uint8)
     ctx.flush_l2()
 
     def barrier():
@@ -211,70 +278,67 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    def step_resident_int32():
-        ctx.depth_begin(0, L)
-        ctx.depth_add_segments_device(d_s, d_e, nseg)
-        ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP)
-
-    # the engine's native segment format (packed8: 64-slot blocks, uint8 start delta + uint8 length), resident in HBM
-    qa, qd, ql = capi.pack_segments8(s, e)
-    d_qa, d_qd, d_ql = ctx.dev_array(qa), ctx.dev_array(qd), ctx.dev_array(ql)
-
     def step_resident():
-        ctx.depth_begin(0, L)
-        ctx.depth_add_segments_packed8_device(d_qa, d_qd, d_ql, qa.size)
-        ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP)
+        for w in work:
+            ctx.depth_begin(0, w["L"])
+            ctx.depth_add_segments_packed8_device(w["d_a"], w["d_d"], w["d_l"], w["nb"])
+            ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP)
 
-    # pinned host buffers for the end-to-end arm
-    h_s, h_e = ctx.pinned_empty(nseg, np.int32), ctx.pinned_empty(nseg, np.int32)
-    h_s[:] = s
-    h_e[:] = e
-    run_cap = L // 16 + 4096
-    o_sum, o_rs, o_rc = ctx.pinned_empty(n_win, np.int64), ctx.pinned_empty(run_cap, np.int32), ctx.pinned_empty(run_cap, np.uint8)
-
-    def step_e2e_int32():
-        return ctx.depth_region(0, L, h_s, h_e, W, MINCOV, MAXMEAN, STEP, out=(o_sum, o_rs, o_rc))
-
-    # the feeder's native compact format (packed16: 4 B/segment instead of 8), also in pinned host memory
-    pa, po, pl = capi.pack_segments16(s, e)
-    h_a, h_o, h_l = ctx.pinned_empty(pa.size, np.int32), ctx.pinned_empty(po.size, np.uint16), ctx.pinned_empty(pl.size, np.uint16)
-    h_a[:] = pa
-    h_o[:] = po
-    h_l[:] = pl
-    packed_bytes = int(pa.nbytes + po.nbytes + pl.nbytes)
-
-    def step_e2e_p16():
-        return ctx.depth_region_packed16(0, L, h_a, h_o, h_l, W, MINCOV, MAXMEAN, STEP, out=(o_sum, o_rs, o_rc))
-
-    # the same packed8 words in pinned host memory for the end-to-end arm
-    h8_a, h8_d, h8_l = ctx.pinned_empty(qa.size, np.int32), ctx.pinned_empty(qd.size, np.uint8), ctx.pinned_empty(ql.size, np.uint8)
-    h8_a[:] = qa
-    h8_d[:] = qd
-    h8_l[:] = ql
-    packed8_bytes = int(qa.nbytes + qd.nbytes + ql.nbytes)
+    text_bytes = [0, 0]
 
     def step_e2e():
-        return ctx.depth_region_packed8(0, L, h8_a, h8_d, h8_l, W, MINCOV, MAXMEAN, STEP, out=(o_sum, o_rs, o_rc))
+        hb = cb = 0
+        for w in work:
+            hl, cl = ctx.depth_bed_contig(w["name"], w["L"], w["h_s"], w["h_e"], W, MINCOV, MAXMEAN, STEP, threads=0, out=(o_hd, o_ca), raw=True)
+            hb += hl; cb += cl
+        text_bytes[0], text_bytes[1] = hb, cb
 
     # ---- warm-up (also sizes every grow-only buffer)
     for _ in range(args.warmup):
         step_resident()
-        step_resident_int32()
-    ws, r0, rc = step_e2e()
-    n_runs = int(r0.size)
-    for _ in range(max(0, args.warmup - 1)):
-        step_e2e()
+    n_runs = 0
+    for w in work:
+        ctx.depth_begin(0, w["L"])
+        ctx.depth_add_segments_packed8_device(w["d_a"], w["d_d"], w["d_l"], w["nb"])
+        ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP)
+        w["n_runs"] = ctx.depth_result_sizes()[1]
+        n_runs += w["n_runs"]
     for _ in range(args.warmup):
-        step_e2e_int32()
-        step_e2e_p16()
+        step_e2e()
+
+    # ---- e2e parity check (outside the timed regions): the bytes of the drop-in call against the oracle's walker
+    e2e_check = None
+    if rank == 0:
+        from oracle import loader as orc
+        mid = [w for w in work if 1_000_000 <= w["L"] <= 70_000_000]
+        pick = ([min(mid, key=lambda w: w["L"])] if mid else []) + [w for w in work if w["L"] < 1_000_000]
+        checked = []
+        ok = True
+        for w in pick:
+            got = ctx.depth_bed_contig(w["name"], w["L"], w["h_s"], w["h_e"], W, MINCOV, MAXMEAN, STEP)
+            s_, e_ = sorted_copy(np.array(w["h_s"]), np.array(w["h_e"]))
+            hd, ca = [], []
+            for cs, ce in orc.gen_chunks(w["L"], W):
+                lo = max(0, int(np.searchsorted(s_, cs - 1024, "left")) - 4096)
+                hi = int(np.searchsorted(s_, ce, "left"))
+                d = orc.pileup_diff(s_[lo:hi], e_[lo:hi], cs, ce)
+                h, c = orc.walk_chunk(w["name"], cs, ce, W, MINCOV, MAXMEAN, d)
+                hd.append(h); ca.append(c)
+            ok = ok and got[0] == b"".join(hd) and got[1] == b"".join(ca)
+            checked.append(w["name"])
+        e2e_check = {"contigs": checked, "bytes_equal_oracle_walker": bool(ok),
+                     "inside_timed_region": ["H2D int32 segments (pinned)", "K_index/K_fused/K_gather", "device %.4g row formatter (bed_rows/scan/emit)",
+                                             "D2H .depth.bed + .callable.bed bytes (pinned)"],
+                     "outside": ["BGZF inflate + BAM record parse (the feeder; see cli_wallclock)"]}
+        if not ok:
+            raise SystemExit("bench.py: e2e text differs from the oracle walker")
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
 
-    # ---- timed: device-resident.  The per-step working set (88 MB of segments) fits the 126 MB L2, so L2 is
-    #      flushed (256 MiB memset) before every timed step; each step is timed with CUDA events on the ctx
-    #      stream and the K step times are summed.
+    # ---- timed: device-resident.  L2 is flushed (256 MiB memset) before every timed step; each step is timed with CUDA
+    #      events on the ctx stream (every launch of the step is on that stream) and the K step times are summed.
     barrier()
     l0 = ctx.launch_count()
     ms = 0.0
@@ -285,16 +349,8 @@ def main():
         ms += ctx.timer_stop_ms()
     launches = ctx.launch_count() - l0
     barrier()
-    ms_int32 = 0.0
-    for _ in range(args.steps):
-        ctx.flush_l2()
-        ctx.timer_start()
-        step_resident_int32()
-        ms_int32 += ctx.timer_stop_ms()
-    barrier()
 
-    # ---- timed: end to end through the C ABI with pinned host buffers (H2D + kernels + D2H inside)
-    barrier()
+    # ---- timed: end to end through the C ABI with pinned host buffers (H2D + kernels + formatter + D2H inside)
     ms_e2e = 0.0
     for _ in range(args.steps):
         ctx.flush_l2()
@@ -303,155 +359,187 @@ def main():
         ctx.timer_start()
         step_e2e()
         dev = ctx.timer_stop_ms()
-        ms_e2e += max(dev, (time.perf_counter() - te0) * 1e3)   # synchronous call: host wall time bounds it from above
-    barrier()
-    ms_e2e_int32 = 0.0
-    for _ in range(args.steps):
-        ctx.flush_l2()
-        ctx.sync()
-        te0 = time.perf_counter()
-        ctx.timer_start()
-        step_e2e_int32()
-        dev = ctx.timer_stop_ms()
-        ms_e2e_int32 += max(dev, (time.perf_counter() - te0) * 1e3)
-    barrier()
-    ms_e2e_p16 = 0.0
-    for _ in range(args.steps):
-        ctx.flush_l2()
-        ctx.sync()
-        te0 = time.perf_counter()
-        ctx.timer_start()
-        step_e2e_p16()
-        dev = ctx.timer_stop_ms()
-        ms_e2e_p16 += max(dev, (time.perf_counter() - te0) * 1e3)
+        ms_e2e += max(dev, (time.perf_counter() - te0) * 1e3)   # synchronous calls: host wall time bounds it from above
     barrier()
 
-    # ---- per-kernel live timing for the roofline: CUDA events on the launching stream around every
-    #      kernel of the same step (library-side, gl_profile_*), averaged over the repetitions
-    def kernel_times(reps, step=None):
-        step = step or step_resident
+    # ---- per-kernel live timing for the roofline: CUDA events on the launching stream around every kernel of the same
+    #      step (library-side, gl_profile_*), averaged over the repetitions
+    def kernel_times(reps, step):
         ctx.profile_enable(True)
         ctx.profile_read()
-        acc = {}
+        acc, cnt = {}, {}
         for _ in range(reps):
             ctx.flush_l2()
             step()
             for nm, t in ctx.profile_read():
-                acc.setdefault(nm, []).append(t)
+                acc[nm] = acc.get(nm, 0.0) + t
+                cnt[nm] = cnt.get(nm, 0) + 1
         ctx.profile_enable(False)
-        per_step = {k: float(np.sum(v)) / reps for k, v in acc.items()}
-        return per_step
-    reps = max(5, min(args.steps, 20))
-    k_ms = kernel_times(reps)
+        return {k: v / reps for k, v in acc.items()}, {k: v // reps for k, v in cnt.items()}
+    reps = max(3, min(args.steps, 10))
+    k_ms, k_n = kernel_times(reps, step_resident)
     path = ctx.depth_last_path()
-    k_ms_int32 = kernel_times(reps, step_resident_int32)
-    # the general (scatter) path on the same input, for the record
-    ctx.depth_set_path(2)
-    for _ in range(2):
-        step_resident_int32()
-    ms_general = 0.0
-    for _ in range(reps):
-        ctx.flush_l2()
-        ctx.timer_start()
-        step_resident_int32()
-        ms_general += ctx.timer_stop_ms() / reps
-    k_ms_general = kernel_times(reps, step_resident_int32)
-    ctx.depth_set_path(0)
+    k_ms_e2e, _ = kernel_times(min(reps, 3), step_e2e)
+
+    # ---- extras (rank 0, N=1): the other entries on the largest contig that fits the old chr20-sized buffers
+    extras = {}
+    if world == 1 and not args.no_extras:
+        w = min(work, key=lambda w: abs(w["L"] - glsynth.CHR20_LEN))
+        L, nm = w["L"], w["name"]
+        d_s, d_e = ctx.dev_array(w["h_s"]), ctx.dev_array(w["h_e"])
+        h8 = [ctx.pinned_empty(a.size, a.dtype) for a in (w["qa"], w["qd"], w["ql"])]
+        for dst, src in zip(h8, (w["qa"], w["qd"], w["ql"])):
+            dst[:] = src
+
+        def one_resident():
+            ctx.depth_begin(0, L)
+            ctx.depth_add_segments_packed8_device(w["d_a"], w["d_d"], w["d_l"], w["nb"])
+            ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP)
+
+        def one_int32():
+            ctx.depth_begin(0, L)
+            ctx.depth_add_segments_device(d_s, d_e, w["nseg"])
+            ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP)
+
+        def timed_dev(fn, n):
+            for _ in range(2):
+                fn()
+            t = 0.0
+            for _ in range(n):
+                ctx.flush_l2(); ctx.timer_start(); fn(); t += ctx.timer_stop_ms()
+            return t / n
+
+        def timed_host(fn, n):
+            for _ in range(2):
+                fn()
+            t = 0.0
+            for _ in range(n):
+                ctx.flush_l2(); ctx.sync()
+                t0_ = time.perf_counter(); fn(); t += (time.perf_counter() - t0_) * 1e3
+            return t / n
+        n_x = max(5, min(args.steps, 20))
+        x_res = timed_dev(one_resident, n_x)
+        x_res_k, _ = kernel_times(5, one_resident)
+        x_i32 = timed_dev(one_int32, n_x)
+        x_i32_k, _ = kernel_times(5, one_int32)
+        ctx.depth_set_path(2)
+        x_gen = timed_dev(one_int32, max(3, n_x // 2))
+        x_gen_k, _ = kernel_times(3, one_int32)
+        ctx.depth_set_path(0)
+        x_e2e_text = timed_host(lambda: ctx.depth_bed_contig(nm, L, w["h_s"], w["h_e"], W, MINCOV, MAXMEAN, STEP, out=(o_hd, o_ca), raw=True), n_x)
+        x_e2e_p8 = timed_host(lambda: ctx.depth_bed_contig_packed8(nm, L, h8[0], h8[1], h8[2], W, MINCOV, MAXMEAN, STEP, out=(o_hd, o_ca), raw=True), n_x)
+        run_cap = L // 16 + 4096
+        o_sum, o_rs, o_rc = ctx.pinned_empty(w["n_win"], np.int64), ctx.pinned_empty(run_cap, np.int32), ctx.pinned_empty(run_cap, np.uint8)
+        x_k_only = timed_host(lambda: ctx.depth_region_packed8(0, L, h8[0], h8[1], h8[2], W, MINCOV, MAXMEAN, STEP, out=(o_sum, o_rs, o_rc)), n_x)
+        t_pack = timed_host(lambda: capi.pack_segments8(w["h_s"], w["h_e"], threads=0), 5)
+        extras = {"contig": nm, "bases": L, "segments": w["nseg"],
+                  "resident_packed8": {"ms": x_res, "value": L / x_res / 1e3, "kernel_ms": x_res_k},
+                  "resident_int32": {"ms": x_i32, "value": L / x_i32 / 1e3, "kernel_ms": x_i32_k,
+                                     "note": "plain int32 (start,end) device arrays: K_index + K_fused + K_gather"},
+                  "general_path": {"ms": x_gen, "value": L / x_gen / 1e3, "kernel_ms": x_gen_k,
+                                   "note": "HBM difference array: memset + K_scatter + K_super + K_scan + K_gather"},
+                  "e2e_text_int32": {"ms": x_e2e_text, "value": L / x_e2e_text / 1e3, "h2d_bytes": 8 * w["nseg"],
+                                     "call": "gl_depth_bed_contig (what `e2e` times, on this contig alone)"},
+                  "e2e_text_packed8_words": {"ms": x_e2e_p8, "value": L / x_e2e_p8 / 1e3, "h2d_bytes": w["p8_bytes"],
+                                             "call": "gl_depth_bed_contig_packed8: the feeder's own packed8 words (what the BAM decoder emits) in, BED bytes out"},
+                  "e2e_kernels_only": {"ms": x_k_only, "value": L / x_k_only / 1e3, "h2d_bytes": w["p8_bytes"],
+                                       "call": "gl_depth_region_packed8: packed8 words in, int64 window sums + runs out, no text (round 1's e2e)"},
+                  "host_pack_ms": {"gl_pack_segments8_mt": t_pack, "threads": n_cpus,
+                                   "note": "int32 -> packed8 on the host pool; NOT inside e2e (e2e uploads the int32 arrays as they are)"}}
+        d_s.free(); d_e.free()
     clocks = sampler.stop() if rank == 0 else None
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    per_rank = None
     if dist is not None:
         import torch
-        t = torch.tensor([ms, ms_e2e, ms_e2e_int32, ms_e2e_p16, ms_int32], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        per_rank = [[float(x[0]) / args.steps, float(x[1]) / args.steps] for x in g]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_e2e_int32, ms_e2e_p16, ms_int32 = (float(x) for x in t)
+        ms, ms_e2e = (float(x) for x in t)
+        cnt = torch.tensor([float(launches), float(nseg), float(n_runs), float(text_bytes[0] + text_bytes[1]), float(8 * nseg)],
+                           dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        launches_all, nseg_all, n_runs_all, d2h_all, h2d_all = (int(x) for x in cnt)
+    else:
+        launches_all, nseg_all, n_runs_all, d2h_all, h2d_all = launches, nseg, n_runs, text_bytes[0] + text_bytes[1], 8 * nseg
 
     if rank == 0:
         peak, peak_src = peaks()
         ms_step = ms / args.steps
-        val = world * L / (ms_step * 1e-3) / 1e6
-        e2e_val = world * L / (ms_e2e / args.steps * 1e-3) / 1e6
-        # ALGORITHMIC bytes per launch: what each kernel must move at minimum.
-        # fused path: K_fused reads every (start,end) once (8 B/segment) and writes sums (8 B/window) and
-        # runs (5 B/run); K_index reads the same 8 B/segment and writes the 4 B/cell offset table.
-        # general path: memset 4L, scatter 8 B/segment read + two int32 updates, scan 4L read.
-        ncells = L // 256 + 66
-        p8_bytes = int(qa.nbytes + qd.nbytes + ql.nbytes)
-        alg = {"depth_fused8_kernel": p8_bytes + 8 * n_win + 5 * n_runs,
-               "depth_tileidx8_kernel": int(qa.nbytes) + 8 * ((L - 1) // 4096 + 1),
-               "depth_fused_kernel": 8 * nseg + 8 * n_win + 5 * n_runs,
-               "depth_index_kernel": 8 * nseg + 4 * ncells,
-               "depth_scan_kernel": 4 * L + 8 * n_win + 5 * n_runs,
-               "depth_scatter_kernel": 16 * nseg,
-               "memset_diff": 4 * L}
-        dom = max((k for k in k_ms if k in alg), key=lambda k: k_ms[k])
-        achieved = alg[dom] / (k_ms[dom] * 1e-3) / 1e9
-        step_bytes = sum(alg[k] for k in k_ms if k in alg)
-        survey_bytes = 8 * nseg + 8 * L + 12 * n_win + 9 * n_runs       # SURVEY.md §8(d) formula (HBM difference array)
-        gdom = max((k for k in k_ms_general if k in alg), key=lambda k: k_ms_general[k])
+        ms_e2e_step = ms_e2e / args.steps
+        units = total_bases if args.workload == "wgs" else world * lengths[0]
+        val = units / (ms_step * 1e-3) / 1e6
+        e2e_val = units / (ms_e2e_step * 1e-3) / 1e6
+        # ALGORITHMIC bytes: rank 0's share, per step
+        n_win0 = sum(w["n_win"] for w in work)
+        p8_bytes0 = sum(w["p8_bytes"] for w in work)
+        survey_bytes = 8 * nseg + 8 * my_bases + 12 * n_win0 + 9 * n_runs          # HBM difference-array pipeline
+        own = {"depth_fused8_kernel": p8_bytes0 + 8 * n_win0 + 5 * n_runs,
+               "depth_tileidx8_kernel": sum(4 * w["nb"] + 8 * ((w["L"] - 1) // 4096 + 1) for w in work)}
+        dom = max((k for k in k_ms if k.startswith("depth_")), key=lambda k: k_ms[k])
+        n_launch = max(1, k_n.get(dom, 1))
+        dom_ms_launch = k_ms[dom] / n_launch
+        achieved = survey_bytes / n_launch / (dom_ms_launch * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(dom)
         out = {"metric": METRIC, "value": val, "unit": "Mbases/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+               "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+               "scaling": "strong" if args.workload == "wgs" else "weak",
                "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-               "config": {"workload": "depth: synthetic 30x chr20 (64,444,167 bp, 150 bp reads), W=500, 1 sample per GPU",
-                          "window": W, "mincov": MINCOV, "run_break": STEP, "segments_per_gpu": nseg,
-                          "windows_per_gpu": n_win, "runs_per_gpu": n_runs, "contigs": world,
-                          "resident_format": "packed8 (64-slot blocks: int32 anchor + uint8 start delta + uint8 length per segment), %d bytes" % p8_bytes,
+               "config": {"workload": WORKLOADS[args.workload], "window": W, "mincov": MINCOV, "run_break": STEP,
+                          "segments": nseg_all, "runs": n_runs_all, "contigs": len(contigs), "contigs_rank0": [w["name"] for w in work],
+                          "assignment": "gl_lpt_assign (longest contig first onto the least loaded GPU)" if args.workload == "wgs" else "one replica per rank",
+                          "imbalance": float(load.max() / (load.sum() / world)) if args.workload == "wgs" else 1.0,
+                          "resident_format": "packed8 (64-slot blocks: int32 anchor + uint8 start delta + uint8 length per segment)",
                           "path": {1: "fused (sorted int32 segments -> smem difference tiles)", 2: "general (HBM difference array)",
                                    3: "packed8 (packed words -> smem difference tiles)"}.get(path, str(path)),
-                          "l2": "L2 flushed (256 MiB memset) before every timed step; per-step CUDA-event times summed"},
-               "e2e": {"value": e2e_val, "unit": "Mbases/s", "h2d_bytes_per_step": packed8_bytes,
-                       "d2h_bytes_per_step": 8 * n_win + 5 * n_runs, "ms_per_step": ms_e2e / args.steps,
-                       "call": "gl_depth_region_packed8 (the feeder's short-read segment format: uint8 start delta + uint8 length, pinned host buffers)"},
-               "e2e_packed16": {"value": world * L / (ms_e2e_p16 / args.steps * 1e-3) / 1e6, "unit": "Mbases/s",
-                                "h2d_bytes_per_step": packed_bytes, "d2h_bytes_per_step": 8 * n_win + 5 * n_runs,
-                                "ms_per_step": ms_e2e_p16 / args.steps,
-                                "call": "gl_depth_region_packed16 (uint16 offset + uint16 length per segment, any read length)"},
-               "e2e_int32": {"value": world * L / (ms_e2e_int32 / args.steps * 1e-3) / 1e6, "unit": "Mbases/s",
-                             "h2d_bytes_per_step": 8 * nseg, "d2h_bytes_per_step": 8 * n_win + 5 * n_runs,
-                             "ms_per_step": ms_e2e_int32 / args.steps,
-                             "call": "gl_depth_region (plain int32 start/end arrays, pinned host buffers)"},
-               "gpu_launches": int(launches),
+                          "l2": "L2 flushed (256 MiB memset) before every timed step; per-step CUDA-event times summed; inputs (>= 1.3 GB per step at N=1) exceed L2",
+                          "numa": {"node": node, "cpus": n_cpus}},
+               "e2e": {"value": e2e_val, "unit": "Mbases/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
+                       "ms_per_step": ms_e2e_step, "kernel_ms_rank0": k_ms_e2e,
+                       "call": "gl_depth_bed_contig per contig: int32 (start,end) segments in pinned host memory -> .depth.bed + .callable.bed bytes in pinned host memory"},
+               "e2e_check": e2e_check,
+               "gpu_launches": int(launches_all),
                "roofline": {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src,
-                            # contract definition: SURVEY.md §8(d)'s algorithmic bytes x the units one launch processes.
-                            # The dominant kernel (K_fused) performs that whole per-base pipeline (difference array, scan,
-                            # window reduce, class runs) on chip, so this is its EFFECTIVE bandwidth ...
-                            "achieved": survey_bytes / (k_ms[dom] * 1e-3) / 1e9 if dom in ("depth_fused_kernel", "depth_fused8_kernel") else achieved,
-                            "frac": (survey_bytes / (k_ms[dom] * 1e-3) / 1e9 if dom in ("depth_fused_kernel", "depth_fused8_kernel") else achieved) / peak,
-                            "alg_bytes_per_launch": survey_bytes if dom in ("depth_fused_kernel", "depth_fused8_kernel") else alg[dom],
-                            "basis": "SURVEY.md 8(d): 8*N_seg + 8*L + 12*ceil(L/W) + 9*runs (HBM difference-array pipeline); "
-                                     "effective bandwidth of the kernel that does that pipeline's work",
+                            # contract definition: SURVEY.md §8(d)'s algorithmic bytes x the units one launch processes; the dominant
+                            # kernel performs that whole per-base pipeline on chip, so this is its EFFECTIVE bandwidth ...
+                            "achieved": achieved, "frac": achieved / peak,
+                            "alg_bytes_per_launch": survey_bytes / n_launch, "launches_per_step_rank0": n_launch,
+                            "ms_per_launch": dom_ms_launch,
+                            "basis": "SURVEY.md 8(d): 8*N_seg + 8*L + 12*ceil(L/W) + 9*runs per contig (HBM difference-array pipeline), "
+                                     "averaged over the rank's contig launches; effective bandwidth of the kernel that does that pipeline's work",
                             # ... and these are the bytes the kernel itself has to move, with the ncu DRAM traffic beside them:
-                            "own": {"alg_bytes_per_launch": alg[dom], "achieved": achieved, "frac": achieved / peak,
-                                    "note": "packed segment words in + 8 B/window + 5 B/run out: the 8 B/base difference array never "
-                                            "exists in HBM, so the kernel is latency/issue-bound, not HBM-bound "
-                                            "(ncu: profiles/r01_ncu_full_summary.json)"},
-                            "traffic": ncu_traffic(dom), "kernel_ms": k_ms,
+                            "own": {"alg_bytes_per_launch": own.get(dom, 0) / n_launch,
+                                    "achieved": own.get(dom, 0) / n_launch / (dom_ms_launch * 1e-3) / 1e9,
+                                    "frac": own.get(dom, 0) / n_launch / (dom_ms_launch * 1e-3) / 1e9 / peak,
+                                    "note": "packed words in + 8 B/window + 5 B/run out: the 8 B/base difference array never exists in HBM; "
+                                            "the kernel is issue-bound, not HBM-bound (profiles/)"},
+                            "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": k_ms,
                             "step": {"survey_alg_bytes": survey_bytes, "achieved": survey_bytes / (ms_step * 1e-3) / 1e9,
-                                     "frac": survey_bytes / (ms_step * 1e-3) / 1e9 / peak,
-                                     "own_alg_bytes": step_bytes, "own_achieved": step_bytes / (ms_step * 1e-3) / 1e9}},
-               "int32_resident": {"ms_per_step": ms_int32 / args.steps, "value": world * L / (ms_int32 / args.steps * 1e-3) / 1e6,
-                                  "kernel_ms": k_ms_int32,
-                                  "note": "same region from plain int32 (start,end) device arrays: K_index + K_fused + K_gather"},
-               "general_path": {"ms_per_step": ms_general, "value": world * L / (ms_general * 1e-3) / 1e6,
-                                "kernel_ms": k_ms_general, "dominant": gdom,
-                                "achieved": alg[gdom] / (k_ms_general[gdom] * 1e-3) / 1e9,
-                                "frac": alg[gdom] / (k_ms_general[gdom] * 1e-3) / 1e9 / peak},
+                                     "frac": survey_bytes / (ms_step * 1e-3) / 1e9 / peak}},
                "clocks": clocks}
+        if per_rank is not None:
+            out["per_rank_ms"] = {"resident": [p[0] for p in per_rank], "e2e": [p[1] for p in per_rank]}
+        if extras:
+            out["single_contig"] = extras
         if not args.no_cpu_baseline and world == 1:         # rank 0 at N=1 only (the other ranks' feeders share the host cores at N>1)
             from oracle import loader as orc       # cpu_baseline leg: the oracle port timed on this box's host cores
             threads = os.cpu_count() or 1
-            chunks = orc.gen_chunks(L, W)
-            reps, tot = 0, 0.0
-            while reps < 3 and tot < 20.0:
-                dt, _ = cpu_depth_pass(orc, s, e, L, threads, chunks)
-                tot += dt; reps += 1
-            out["cpu_baseline"] = {"value": L / (tot / reps) / 1e6, "unit": "Mbases/s", "cores": min(threads, len(chunks)), "kind": "port",
-                                   "sample": f"{reps} x whole chr20 contig (7 chunks of 10 Mb, one thread per chunk = the reference's "
-                                             "unit of parallelism): per-base counting + window/class walk + BED text; "
-                                             "samtools text print/parse excluded"}
+            os.sched_setaffinity(0, range(threads))          # the CPU leg may use every core of the box
+            cc = [(w["name"], w["L"]) + sorted_copy(np.array(w["h_s"]), np.array(w["h_e"])) for w in work]
+            reps_c, tot, chunks = 0, 0.0, 0
+            cpu_genome_pass(orc, cc[-1:], threads)
+            while reps_c < 3 and tot < 20.0:
+                dt, _, chunks = cpu_genome_pass(orc, cc, threads)
+                tot += dt; reps_c += 1
+            out["cpu_baseline"] = {"value": units / (tot / reps_c) / 1e6, "unit": "Mbases/s", "cores": min(threads, chunks),
+                                   "cores_available": threads, "kind": "port",
+                                   "sample": f"{reps_c} x the whole workload ({chunks} chunks of 10 Mb, one worker per chunk = the reference's unit of "
+                                             "parallelism, all host threads): per-base counting + window/class walk + BED text; "
+                                             "BGZF inflate and samtools text print/parse excluded"}
         print(json.dumps(out), flush=True)
 
-    d_s.free(); d_e.free(); d_qa.free(); d_qd.free(); d_ql.free()
     ctx.close()
     if dist is not None:
         dist.barrier()

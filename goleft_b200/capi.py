@@ -72,6 +72,9 @@ _proto("gl_flush_l2", C.c_int, _vp)
 _proto("gl_profile_enable", C.c_int, _vp, C.c_int)
 _proto("gl_profile_read", C.c_int, _vp, _vp, C.c_int64, _i64p)
 
+_proto("gl_bind_numa_for_device", C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int))
+_proto("gl_device_numa_node", C.c_int, C.c_int, C.POINTER(C.c_int))
+_proto("gl_lpt_assign", C.c_int, _vp, C.c_int32, C.c_int32, _vp, _vp)
 _proto("gl_depth_begin", C.c_int, _vp, C.c_int64, C.c_int64)
 _proto("gl_depth_add_segments", C.c_int, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_add_segments_device", C.c_int, _vp, _vp, _vp, C.c_int64)
@@ -156,6 +159,29 @@ def device_count() -> int:
     if rc != GL_OK:
         return 0
     return n.value
+
+
+def bind_numa_for_device(device: int, share_index: int = 0, share_count: int = 1) -> Tuple[int, int]:
+    """(numa node or -1, cpus bound) — call before the first pinned allocation / pool use"""
+    node, n = C.c_int(-1), C.c_int(0)
+    lib.gl_bind_numa_for_device(device, share_index, share_count, C.byref(node), C.byref(n))
+    return node.value, n.value
+
+
+def device_numa_node(device: int) -> int:
+    node = C.c_int(-1)
+    lib.gl_device_numa_node(device, C.byref(node))
+    return node.value
+
+
+def lpt_assign(weights, bins: int):
+    """(bin_of int32[n], bin_load int64[bins]) — longest first onto the least loaded bin"""
+    w = np.ascontiguousarray(weights, np.int64)
+    bin_of, load = np.empty(w.size, np.int32), np.empty(bins, np.int64)
+    rc = lib.gl_lpt_assign(w.ctypes.data_as(_vp), w.size, bins, bin_of.ctypes.data_as(_vp), load.ctypes.data_as(_vp))
+    if rc != GL_OK:
+        raise GlError(rc, "gl_lpt_assign: bad arguments")
+    return bin_of, load
 
 
 def _ptr(a: Optional[np.ndarray]):

@@ -1903,16 +1903,18 @@ int gl_depth_bed_contig(gl_ctx* ctx, const char* chrom, int64_t contig_len, cons
     GL_CHECK(gl_use(ctx));
     if (W <= 0 || step <= 0 || step % W != 0) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_contig: step must be a positive multiple of W (depth.go:132)");
     if (n < 0 || (n > 0 && (!start || !end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_contig: bad segments");
-    // short reads (what a 30x WGS BAM holds): pack to 2 B/segment on the host threads, a quarter of the PCIe bytes;
-    // long segments would be cut into many 255-base pieces, so they go up as plain int32.  Judged on a sample.
-    static const int force = [] { const char* e = getenv("GL_BED_PACK"); return e ? atoi(e) : -1; }();   // 0: never pack, 1: always
-    bool pack = n >= 4096;
-    if (pack && force < 0) {
+    // The int32 arrays go up as they are (PCIe-bound: 8 B/segment).  GL_BED_PACK=1 packs short-read input to packed8
+    // (2 B/segment) on the host pool first: a quarter of the PCIe bytes, but on the 2 x 32-core host of the B200 box the
+    // pack costs 2-3 ms per 11 M segments, more than the 1.2 ms of upload it saves (tools/e2e_text_probe.py), so it is
+    // opt-in; a feeder that emits packed8 itself calls gl_depth_bed_contig_packed8.
+    static const int force = [] { const char* e = getenv("GL_BED_PACK"); return e ? atoi(e) : 0; }();
+    bool pack = force == 1 && n >= 4096;
+    if (pack) {                                       // long segments would be cut into many 255-base pieces: judged on a sample
         int64_t tot = 0, cnt = 0;
         for (int part = 0; part < 4; part++)
             for (int64_t i = (n - 1024) * part / 3, j = 0; j < 1024; j++, i++) { tot += std::max<int64_t>(0, (int64_t)end[i] - start[i]); cnt++; }
         pack = tot <= 400 * cnt;
-    } else if (force >= 0) pack = force != 0 && n > 0;
+    }
     if (!pack) {
         GL_CHECK(gl_depth_begin(ctx, 0, contig_len));
         GL_CHECK(gl_depth_add_segments(ctx, start, end, n));

@@ -2,6 +2,8 @@
 #include "gl_common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <ctype.h>
+#include <sched.h>
 
 thread_local std::string g_gl_err;
 
@@ -96,6 +98,71 @@ int gl_ctx_create(int device, gl_ctx** out) {
         return rc;
     }
     *out = ctx;
+    return GL_OK;
+}
+
+// Pin the calling thread (and the threads it creates afterwards: the library's pool, a feeder) to the CPUs of the NUMA
+// node the GPU hangs off, so pinned staging buffers are first-touched next to the GPU's PCIe root and H2D copies do not
+// cross the socket link (round 1: 8 ranks on one box, the ranks on the far socket lost a third of their H2D bandwidth).
+// share_index/share_count split that node's CPUs between the ranks that share it.  Best effort: *node = -1 when the
+// topology cannot be read (then nothing is changed).
+int gl_device_numa_node(int device, int* node) {
+    if (!node) return gl_fail(nullptr, GL_EINVAL, "null out pointer");
+    *node = -1;
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return gl_fail(nullptr, GL_ECUDA, "cudaDeviceGetPCIBusId(%d) failed", device); }
+    for (char* c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+    char path[256];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    int nd = -1;
+    if (f) { if (fscanf(f, "%d", &nd) != 1) nd = -1; fclose(f); }
+    *node = nd;
+    return GL_OK;
+}
+
+int gl_bind_numa_for_device(int device, int share_index, int share_count, int* node, int* n_cpus) {
+    if (node) *node = -1;
+    if (n_cpus) *n_cpus = 0;
+    int nd = -1;
+    GL_CHECK(gl_device_numa_node(device, &nd));
+    if (nd < 0) return GL_OK;
+    char path[256];
+    FILE* f;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", nd);
+    f = fopen(path, "r");
+    if (!f) return GL_OK;
+    char list[4096] = {0};
+    if (!fgets(list, sizeof list, f)) list[0] = 0;
+    fclose(f);
+    std::vector<int> cpus;
+    for (char* p = list; *p;) {
+        char* e = nullptr;
+        long a = strtol(p, &e, 10);
+        if (e == p) break;
+        long b = a;
+        if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) cpus.push_back((int)c);
+        p = (*e == ',') ? e + 1 : e;
+        if (*e != ',') break;
+    }
+    if (cpus.empty()) return GL_OK;
+    // hyper-thread siblings sit in the second half of the list (0-31,64-95): deal whole cores, both siblings together
+    std::vector<int> mine;
+    if (share_count > 1 && share_index >= 0 && share_index < share_count) {
+        const size_t half = cpus.size() / 2;
+        const bool paired = cpus.size() % 2 == 0 && half > 0;
+        const size_t cores = paired ? half : cpus.size();
+        const size_t lo = cores * (size_t)share_index / (size_t)share_count, hi = cores * (size_t)(share_index + 1) / (size_t)share_count;
+        for (size_t k = lo; k < hi; k++) { mine.push_back(cpus[k]); if (paired) mine.push_back(cpus[half + k]); }
+    }
+    if (mine.empty()) mine = cpus;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    for (int c : mine) CPU_SET(c, &set);
+    if (sched_setaffinity(0, sizeof set, &set) != 0) return GL_OK;
+    if (node) *node = nd;
+    if (n_cpus) *n_cpus = (int)mine.size();
     return GL_OK;
 }
 

@@ -1,5 +1,6 @@
 // thread_pool.cpp — see thread_pool.h
 #include "thread_pool.h"
+#include <sched.h>
 #include <stdlib.h>
 #include <chrono>
 #if defined(__x86_64__)
@@ -21,6 +22,8 @@ int ThreadPool::default_threads() {
         const int v = atoi(e);
         if (v > 0) return v > 1024 ? 1024 : v;
     }
+    cpu_set_t set;                                     // the CPUs this process may run on (gl_bind_numa_for_device narrows it)
+    if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) return CPU_COUNT(&set);
     const unsigned hc = std::thread::hardware_concurrency();
     return hc ? (int)hc : 1;
 }

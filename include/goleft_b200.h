@@ -58,6 +58,15 @@ int  gl_launch_count(gl_ctx* ctx, int64_t* n);
 /* raw cudaStream_t of the ctx, as an integer, so a caller can record events on it */
 int  gl_stream_handle(gl_ctx* ctx, uint64_t* stream);
 
+/* Pins the calling thread, and the threads created after it (the library's host pool, feeders), to the CPUs of the NUMA
+ * node of `device`; with share_count > 1 to the share_index-th slice of that node's cores (ranks sharing a socket).
+ * Call it before the first pinned allocation / pool use.  *node = -1 when the topology is unreadable (nothing changed). */
+int  gl_device_numa_node(int device, int* node);     /* -1: unknown */
+int  gl_bind_numa_for_device(int device, int share_index, int share_count, int* node, int* n_cpus);
+/* Longest-processing-time-first placement of n work items (contigs, weight = length) on `bins` GPUs: the unit of
+ * independence of depth/depth.go:129-159.  bin_of[i] = GPU of item i, bin_load[b] = total weight (may be NULL). */
+int  gl_lpt_assign(const int64_t* weight, int32_t n, int32_t bins, int32_t* bin_of, int64_t* bin_load);
+
 /* device memory owned by the ctx's device (plumbing for callers that keep inputs resident) */
 int  gl_dev_alloc(gl_ctx* ctx, int64_t bytes, void** d_ptr);
 int  gl_dev_free(gl_ctx* ctx, void* d_ptr);
