@@ -132,29 +132,12 @@ def contig_list(workload, world):
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_genome_pass(orc, contigs, threads):
     """The reference's CPU path, chunk-parallel like `goleft depth -p` (depth.go:132,392: one worker per 10 Mb chunk):
-    per chunk, per-base counting (the samtools child) + the callback's window/class walk + BED text.
-    contigs: [(name, length, start, end)] with nearly sorted segments.  Returns (seconds, text bytes, chunks)."""
-    from concurrent.futures import ThreadPoolExecutor
-    jobs = []
-    for name, L, s, e in contigs:
-        maxlen = 1024                                        # short reads; the searchsorted slack below covers deletions
-        for cs, ce in orc.gen_chunks(L, W):
-            jobs.append((name, s, e, cs, ce, maxlen))
-
-    def one(j):
-        name, s, e, cs, ce, maxlen = j
-        lo = np.searchsorted(s, cs - maxlen, "left")
-        hi = np.searchsorted(s, ce, "left")
-        lo = max(0, lo - 4096)                               # starts are sorted up to one read's span
-        d = orc.pileup_diff(s[lo:hi], e[lo:hi], cs, ce)
-        hd, ca = orc.walk_chunk(name, cs, ce, W, MINCOV, MAXMEAN, d)
-        return len(hd) + len(ca)
-
-    jobs.sort(key=lambda j: -(j[4] - j[3]))
+    per chunk, per-base counting (the samtools child) + the callback's window/class walk + BED text, on `threads` C
+    workers (oracle/oracle_depth.c::orc_depth_jobs_mt).  contigs: [(name, length, start, end)] sorted by start.
+    Returns (seconds, text bytes, chunks)."""
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        nbytes = sum(ex.map(one, jobs))
-    return time.perf_counter() - t0, nbytes, len(jobs)
+    chunks, nbytes = orc.depth_jobs_mt(contigs, W, MINCOV, MAXMEAN, threads)
+    return time.perf_counter() - t0, nbytes, chunks
 
 
 def sorted_copy(s, e):

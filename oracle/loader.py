@@ -49,6 +49,7 @@ _proto("orc_window_sums", C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, _vp, 
 _proto("orc_class_runs", C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int64)
 _proto("orc_faidx_stats", C.c_int, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp)
 _proto("orc_stats_text", C.c_int, _vp, C.c_char_p, C.c_int64)
+_proto("orc_depth_jobs_mt", C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _i64p)
 
 
 def faidx_stats(fasta: bytes, rec, start: int, end: int):
@@ -135,6 +136,30 @@ def walk_text(txt: bytes, W: int, mincov: int, maxmean: int) -> Tuple[bytes, byt
     if rc != 0:
         raise ValueError("orc_walk_text failed")
     return _take(d, dl), _take(c, cl)
+
+
+class _ChunkJob(C.Structure):
+    _fields_ = [("chrom", C.c_char_p), ("start", _vp), ("end", _vp), ("n", C.c_int64), ("rs", C.c_int64), ("re", C.c_int64)]
+
+
+def depth_jobs_mt(contigs, W: int, mincov: int, maxmean: int, threads: int, slack: int = 20000):
+    """bench CPU arm: contigs = [(name, length, start_sorted int32, end int32)]; every 10 Mb chunk (gen_chunks) of every
+    contig is one job (pileup + callback walk + BED text) on `threads` C workers.  -> (jobs done, text bytes)"""
+    jobs, keep = [], []
+    for name, L, s, e in contigs:
+        s, e = np.ascontiguousarray(s, np.int32), np.ascontiguousarray(e, np.int32)
+        nm = name.encode()
+        keep.append((s, e, nm))
+        for cs, ce in gen_chunks(L, W):
+            jobs.append((ce - cs, nm, s, e, cs, ce))
+    jobs.sort(key=lambda j: -j[0])                        # longest chunks first
+    arr = (_ChunkJob * len(jobs))()
+    for k, (_, nm, s, e, cs, ce) in enumerate(jobs):
+        arr[k].chrom = nm; arr[k].start = s.ctypes.data; arr[k].end = e.ctypes.data; arr[k].n = s.size; arr[k].rs = cs; arr[k].re = ce
+    tb = C.c_int64(0)
+    done = lib.orc_depth_jobs_mt(arr, len(jobs), W, mincov, maxmean, slack, threads, C.byref(tb))
+    assert done == len(jobs)
+    return done, tb.value
 
 
 def window_sums(depth: np.ndarray, rs: int, re: int, W: int):

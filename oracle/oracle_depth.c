@@ -402,3 +402,76 @@ int orc_faidx_stats(const uint8_t* map, int64_t map_len, int64_t rec_start, int6
 int orc_stats_text(const double* st3, char* out, int64_t cap) {
     return snprintf(out, (size_t)cap, "\t%.3g\t%.3g\t%.3g", st3[0], st3[1], st3[2]);
 }
+
+/* ------------------------------------------------------------------ chunk-parallel driver (bench only)
+ * `goleft depth -p N` runs one `samtools depth` child + callback per 10 Mb chunk, N at a time (depth.go:132,150-154,
+ * 392-394).  orc_depth_jobs_mt is that loop for the bench's CPU arm: `threads` workers take chunk jobs from a shared
+ * counter; per job: per-base counting (orc_pileup_diff, the child) + the callback walk + BED text (walk()), all in C with
+ * per-worker buffers, so the Python driver's allocator / GIL do not throttle the baseline.  A job's segments are the
+ * slice of its contig's start-sorted arrays that can reach the chunk (binary search with `slack` bases of look-back).
+ * Returns the number of jobs done; *text_bytes = total bytes of both BED texts.                                        */
+#include <pthread.h>
+typedef struct {
+    const char* chrom; const int32_t* start; const int32_t* end; int64_t n;   /* contig segments, sorted by start */
+    int64_t rs, re;
+} orc_chunk_job;
+
+typedef struct {
+    const orc_chunk_job* jobs; int64_t n_jobs; int64_t W, mincov, maxmean, slack;
+    int64_t next; pthread_mutex_t mu; int64_t text_bytes, done;
+} orc_jobs_ctx;
+
+static int64_t lower_bound_i32(const int32_t* a, int64_t n, int64_t v) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if ((int64_t)a[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+static void* orc_jobs_worker(void* arg) {
+    orc_jobs_ctx* c = (orc_jobs_ctx*)arg;
+    int32_t* depth = NULL;
+    int64_t depth_cap = 0, bytes = 0, done = 0;
+    obuf hd = {0}, ca = {0};
+    for (;;) {
+        pthread_mutex_lock(&c->mu);
+        const int64_t j = c->next++;
+        pthread_mutex_unlock(&c->mu);
+        if (j >= c->n_jobs) break;
+        const orc_chunk_job* jb = &c->jobs[j];
+        const int64_t len = jb->re - jb->rs;
+        if (len > depth_cap) { free(depth); depth = (int32_t*)malloc((size_t)len * 4); depth_cap = len; }
+        const int64_t lo = lower_bound_i32(jb->start, jb->n, jb->rs - c->slack), hi = lower_bound_i32(jb->start, jb->n, jb->re);
+        orc_pileup_diff(jb->start + lo, jb->end + lo, hi - lo, jb->rs, jb->re, depth);
+        hd.len = ca.len = 0;
+        ob_reserve(&hd, 1); ob_reserve(&ca, 1);
+        line_src s; memset(&s, 0, sizeof s);
+        s.next = next_array; s.depth = depth; s.rs = jb->rs; s.re = jb->re; s.x = jb->rs;
+        walk(&s, jb->chrom, jb->rs, jb->re, c->W, c->mincov, c->maxmean, &hd, &ca);
+        bytes += (int64_t)(hd.len + ca.len);
+        done++;
+    }
+    free(depth); free(hd.p); free(ca.p);
+    pthread_mutex_lock(&c->mu);
+    c->text_bytes += bytes; c->done += done;
+    pthread_mutex_unlock(&c->mu);
+    return NULL;
+}
+
+int64_t orc_depth_jobs_mt(const orc_chunk_job* jobs, int64_t n_jobs, int64_t W, int64_t mincov, int64_t maxmean, int64_t slack,
+                          int threads, int64_t* text_bytes) {
+    orc_jobs_ctx c;
+    memset(&c, 0, sizeof c);
+    c.jobs = jobs; c.n_jobs = n_jobs; c.W = W; c.mincov = mincov; c.maxmean = maxmean; c.slack = slack;
+    pthread_mutex_init(&c.mu, NULL);
+    if (threads < 1) threads = 1;
+    if (threads > 1024) threads = 1024;
+    if ((int64_t)threads > n_jobs) threads = (int)(n_jobs > 0 ? n_jobs : 1);
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
+    for (int t = 1; t < threads; t++) pthread_create(&th[t], NULL, orc_jobs_worker, &c);
+    orc_jobs_worker(&c);
+    for (int t = 1; t < threads; t++) pthread_join(th[t], NULL);
+    free(th);
+    pthread_mutex_destroy(&c.mu);
+    if (text_bytes) *text_bytes = c.text_bytes;
+    return c.done;
+}
