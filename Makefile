@@ -57,8 +57,8 @@ oracle/_build/liboracle.so: $(wildcard oracle/*.c)
 # bench workload generator (both bench arms load it; not part of the product library)
 synth: tools/synth/libglsynth.so
 
-tools/synth/libglsynth.so: tools/synth/glsynth.c
-	$(CC) -O2 -fPIC -shared -Wall -o $@ $< -lpthread
+tools/synth/libglsynth.so: tools/synth/glsynth.c tools/synth/bamsynth.c tools/synth/glsynth_core.h
+	$(CC) -O2 -fPIC -shared -Wall -o $@ tools/synth/glsynth.c tools/synth/bamsynth.c -lpthread -lz
 
 clean:
 	rm -rf $(BUILD) $(LIB) bin oracle/_build tools/synth/libglsynth.so

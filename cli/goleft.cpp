@@ -15,7 +15,10 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <regex>
 #include <string>
 #include <thread>
@@ -23,6 +26,7 @@
 #include <zlib.h>
 
 #include "../goleft_b200/csrc/host/hts_io.h"
+#include "../goleft_b200/csrc/host/bam_feed.h"
 #include "goleft_b200.h"
 
 static const char* kVersion = "0.2.6";          // goleft.go:3 (the surface this build mirrors)
@@ -40,6 +44,10 @@ static const char* kVersion = "0.2.6";          // goleft.go:3 (the surface this
 static void glck(gl_ctx* ctx, int rc, const char* what) {
     if (rc != GL_OK) fatal(1, "%s: %s", what, gl_last_error(ctx));
 }
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+extern "C" int glhost_pool_size(void);              // libgoleft_b200.so: size of the host thread pool (creates it)
+static void glhost_pool_warm() { (void)glhost_pool_size(); }
 
 static bool ends_with(const std::string& s, const std::string& suf) {
     return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
@@ -135,33 +143,330 @@ static bool chrom_start_end(const std::string& line, std::string& chrom, long lo
 }
 
 // ------------------------------------------------------------------------------------------------ depth
+// `goleft depth`: depth/depth.go:103-159 builds the work list (10 Mb chunks of every .fai contig, or the BED lines), runs one
+// `samtools depth -r` child per entry and concatenates the per-chunk BED files (-o: in order).  Here the unit of work is a
+// contig (all its chunks in one GPU pass, run_break = step keeps the per-chunk row structure) or, in BED mode, a contig's
+// BED lines; contigs are dealt to the visible GPUs longest first (gl_lpt_assign), one host thread + one gl_ctx + one BAM
+// handle per GPU; the host pool (inflate + parse) is shared.  Output is always in work-list order (a valid -o output).
+namespace {
+
+struct DepthOpts {
+    int W = 250, maxmean = 0, Q = 1, mincov = 4, threads = 0;
+    long long step = 10000000;
+    bool stats = false;
+    std::string reference;
+};
+
+struct DepthRegion { std::string chrom; long long s, e; };
+
+struct DepthJob {                                   // one contig (.fai mode) or the BED lines of one contig (BED mode)
+    std::string chrom;
+    long long len = 0;                              // .fai mode: contig length
+    std::vector<size_t> lines;                      // BED mode: indices into the region list
+    std::string hd, ca;                             // .fai mode output
+    double decode_s = 0, gpu_s = 0;
+    long long records = 0, bytes_in = 0, bytes_out = 0;
+    bool done = false;
+};
+
+struct DepthShared {
+    const DepthOpts* opt;
+    std::string bam_path;
+    const glhts::SegmentSet* preload = nullptr;     // BAM without an index: every contig decoded once up front
+    std::vector<DepthRegion>* regions = nullptr;    // BED mode
+    std::vector<std::string>* out_hd = nullptr;     // BED mode: per line
+    std::vector<std::string>* out_ca = nullptr;
+    std::vector<glhts::RefInfo> fa_index;
+    const uint8_t* fa_map = nullptr; size_t fa_len = 0;
+    std::mutex mu; std::condition_variable cv;
+};
+
+// One GPU's worker: ctx + BAM handle + buffers
+struct DepthEngine {
+    DepthShared& sh;
+    const DepthOpts& o;
+    gl_ctx* ctx = nullptr;
+    glhts::BamFile bam;
+    std::map<std::string, int> tid_of;
+    glhts::ContigSegs segs;
+    std::vector<int64_t> sums; std::vector<int32_t> rstart; std::vector<uint8_t> rclass;
+    std::vector<char> tbuf_hd, tbuf_ca;
+    // --stats state (depth.go:191-200,246-252): chunks of a contig are parked, one gl_fasta_stats launch for all their rows
+    struct Pending { std::string chrom; long long rs, re; std::vector<int64_t> sums; std::vector<int32_t> rs_; std::vector<uint8_t> rc_; std::string *hd, *ca; int64_t row0, nrows; };
+    std::vector<Pending> pending;
+    std::vector<int64_t> row_s, row_e;
+
+    DepthEngine(DepthShared& s, int device) : sh(s), o(*s.opt) {
+        if (gl_ctx_create(device, &ctx) != GL_OK) fatal(1, "goleft depth: %s", gl_last_error(nullptr));
+        if (!sh.preload) {
+            std::string e = bam.open(sh.bam_path);
+            if (!e.empty()) fatal(1, "%s", e.c_str());
+            for (size_t i = 0; i < bam.header.refs.size(); i++) tid_of[bam.header.refs[i].name] = (int)i;
+        } else {
+            for (size_t i = 0; i < sh.preload->header.refs.size(); i++) tid_of[sh.preload->header.refs[i].name] = (int)i;
+        }
+        rstart.resize(1 << 16); rclass.resize(1 << 16);
+    }
+    ~DepthEngine() { gl_ctx_destroy(ctx); }
+
+    // segments of [beg,end) of a contig into `segs` (packed8 or sorted int32); want: 0 auto, 32 int32
+    void fetch(const std::string& c, long long beg, long long end, int want, DepthJob* job) {
+        segs = glhts::ContigSegs();
+        auto it = tid_of.find(c);
+        if (it == tid_of.end()) return;
+        if (sh.preload) {                                              // unindexed BAM: slices of the preloaded arrays (record order)
+            const std::vector<int32_t>& S = sh.preload->start[(size_t)it->second];
+            const std::vector<int32_t>& E = sh.preload->end[(size_t)it->second];
+            segs.format = S.empty() ? 0 : 32;
+            segs.start = S; segs.end = E; segs.n = (int64_t)S.size();
+            return;
+        }
+        glhts::DecodeStats st;
+        std::string e = bam.decode(it->second, beg, end, o.Q, o.threads, want, segs, &st);
+        if (!e.empty()) fatal(1, "%s", e.c_str());
+        if (job) { job->decode_s += st.wall_s; job->records += st.n_records; job->bytes_in += st.bytes_in; job->bytes_out += st.bytes_out; }
+    }
+
+    void add_segments() {
+        if (segs.format == 8 && segs.n_blocks > 0)
+            glck(ctx, gl_depth_add_segments_packed8(ctx, segs.anchors.data(), segs.ds.data(), segs.len.data(), segs.n_blocks), "gl_depth_add_segments_packed8");
+        else if (segs.format == 32 && segs.n > 0)
+            glck(ctx, gl_depth_add_segments(ctx, segs.start.data(), segs.end.data(), segs.n), "gl_depth_add_segments");
+    }
+
+    // window sums + class runs of [rs,re) on the host (the --stats and BED paths)
+    void reduce_to_host(long long rs, long long re, long long run_break, int64_t& nw, int64_t& nr) {
+        glck(ctx, gl_depth_begin(ctx, rs, re), "gl_depth_begin");
+        add_segments();
+        glck(ctx, gl_depth_reduce(ctx, o.W, o.mincov, o.maxmean, run_break), "gl_depth_reduce");
+        int32_t md = 0;
+        glck(ctx, gl_depth_result_sizes(ctx, &nw, &nr, &md), "gl_depth_result_sizes");
+        sums.resize((size_t)nw);
+        if ((int64_t)rstart.size() < nr) { rstart.resize((size_t)nr + 1024); rclass.resize((size_t)nr + 1024); }
+        glck(ctx, gl_depth_get_windows(ctx, sums.data(), nw), "gl_depth_get_windows");
+        glck(ctx, gl_depth_get_runs(ctx, rstart.data(), nullptr, rclass.data(), (int64_t)rstart.size()), "gl_depth_get_runs");
+    }
+
+    void emit(const std::string& c, long long rs, long long re, const int64_t* ws, int64_t nw, const int32_t* rs_, const uint8_t* rc_, int64_t nr,
+              std::string* hd_to, std::string* ca_to) {
+        if (!o.stats) {
+            char *hd = nullptr, *ca = nullptr;
+            int64_t hl = 0, cl = 0;
+            if (gl_depth_format_chunk(c.c_str(), rs, re, o.W, ws, nw, rs_, rc_, nr, &hd, &hl, &ca, &cl) != GL_OK) fatal(1, "gl_depth_format_chunk failed");
+            hd_to->append(hd, (size_t)hl); ca_to->append(ca, (size_t)cl);
+            gl_free_text(hd); gl_free_text(ca);
+            return;
+        }
+        Pending pc{c, rs, re, std::vector<int64_t>(ws, ws + nw), std::vector<int32_t>(rs_, rs_ + nr), std::vector<uint8_t>(rc_, rc_ + nr), hd_to, ca_to,
+                   (int64_t)row_s.size(), 0};
+        int64_t n = 0;
+        gl_depth_chunk_rows(rs, re, o.W, rs_, rc_, nr, nullptr, nullptr, 0, &n);
+        row_s.resize(row_s.size() + (size_t)n); row_e.resize(row_s.size());
+        if (gl_depth_chunk_rows(rs, re, o.W, rs_, rc_, nr, row_s.data() + pc.row0, row_e.data() + pc.row0, n, &n) != GL_OK) fatal(1, "gl_depth_chunk_rows failed");
+        pc.nrows = n;
+        pending.push_back(std::move(pc));
+    }
+
+    void flush_stats() {                                    // all parked chunks belong to one contig
+        if (pending.empty()) return;
+        const std::string& c = pending[0].chrom;
+        std::vector<double> st3(row_s.size() * 3, 0.0);
+        const glhts::RefInfo* ri = nullptr;
+        for (const glhts::RefInfo& r : sh.fa_index) if (r.name == c) { ri = &r; break; }
+        if (!ri) fprintf(stderr, "GC: unknown sequence %s\n", c.c_str());                 // faidx error text; zeros are printed (depth.go:195-199)
+        else if (!row_s.empty()) {
+            const int64_t rec_bytes = std::min<int64_t>((int64_t)sh.fa_len - ri->offset, glhts::fasta_position(*ri, ri->length) + 1);
+            if (ri->offset < 0 || rec_bytes < 0) fatal(1, "bad .fai entry for %s", c.c_str());
+            glck(ctx, gl_fasta_load(ctx, sh.fa_map + ri->offset, rec_bytes), "gl_fasta_load");
+            std::vector<int64_t> ba(row_s.size()), bb(row_s.size());
+            for (size_t i = 0; i < row_s.size(); i++) {
+                // faidx panics on coordinates past the contig; rows are clipped to it here instead
+                const int64_t s = std::min<int64_t>(std::max<int64_t>(row_s[i], 0), ri->length), e = std::min<int64_t>(std::max<int64_t>(row_e[i], s), ri->length);
+                const int64_t ps = glhts::fasta_position(*ri, s), pe = glhts::fasta_position(*ri, e);
+                ba[i] = std::min(ps, rec_bytes);
+                bb[i] = std::max(ba[i], std::min<int64_t>(pe + ((ri->offset + pe < (int64_t)sh.fa_len) ? 1 : 0), rec_bytes));
+            }
+            glck(ctx, gl_fasta_stats(ctx, ba.data(), bb.data(), (int64_t)ba.size(), nullptr, st3.data()), "gl_fasta_stats");
+        }
+        for (const Pending& pc : pending) {
+            char *hd = nullptr, *ca = nullptr;
+            int64_t hl = 0, cl = 0;
+            if (gl_depth_format_chunk_stats(pc.chrom.c_str(), pc.rs, pc.re, o.W, pc.sums.data(), (int64_t)pc.sums.size(), pc.rs_.data(), pc.rc_.data(),
+                                            (int64_t)pc.rs_.size(), st3.data() + pc.row0 * 3, pc.nrows, &hd, &hl, &ca, &cl) != GL_OK)
+                fatal(1, "gl_depth_format_chunk_stats failed");
+            pc.hd->append(hd, (size_t)hl); pc.ca->append(ca, (size_t)cl);
+            gl_free_text(hd); gl_free_text(ca);
+        }
+        pending.clear(); row_s.clear(); row_e.clear();
+    }
+
+    // ---- .fai mode: one contig.  The GPU pass covers at most 2^30-1 bases; longer contigs go in whole-chunk pieces
+    //      whose texts concatenate (chunk edges are run breaks anyway).
+    void run_contig(DepthJob& job) {
+        const long long kMaxPass = ((1LL << 30) - 1) / o.step * o.step;
+        const double t_all = now_s();
+        for (long long ps = 0; ps < job.len; ps += kMaxPass) {
+            const long long pe = std::min(job.len, ps + kMaxPass);
+            fetch(job.chrom, ps, pe, 0, &job);
+            const double tg = now_s();
+            const bool device_text = !o.stats && job.chrom.size() <= 64;
+            if (device_text) {
+                const int64_t nwin = (pe - 1) / o.W - ps / o.W + 1;
+                const size_t need_hd = (size_t)gl_depth_text_bound(job.chrom.c_str(), nwin);
+                if (tbuf_hd.size() < need_hd) tbuf_hd.resize(need_hd);
+                if (tbuf_ca.size() < (size_t)(1 << 20)) tbuf_ca.resize(1 << 20);
+                int64_t hl = 0, cl = 0;
+                for (int attempt = 0; attempt < 2; attempt++) {
+                    int rc;
+                    if (segs.format == 8)
+                        rc = gl_depth_bed_region_packed8(ctx, job.chrom.c_str(), ps, pe, segs.anchors.data(), segs.ds.data(), segs.len.data(), segs.n_blocks, o.W,
+                                                         o.mincov, o.maxmean, o.step, tbuf_hd.data(), (int64_t)tbuf_hd.size(), &hl, tbuf_ca.data(), (int64_t)tbuf_ca.size(), &cl);
+                    else
+                        rc = gl_depth_bed_region(ctx, job.chrom.c_str(), ps, pe, segs.start.data(), segs.end.data(), segs.n, o.W, o.mincov, o.maxmean, o.step,
+                                                 o.threads, tbuf_hd.data(), (int64_t)tbuf_hd.size(), &hl, tbuf_ca.data(), (int64_t)tbuf_ca.size(), &cl);
+                    if (rc == GL_ERANGE && attempt == 0) { tbuf_hd.resize((size_t)hl + 16); tbuf_ca.resize((size_t)cl + 16); continue; }
+                    glck(ctx, rc, "gl_depth_bed_region");
+                    break;
+                }
+                job.hd.append(tbuf_hd.data(), (size_t)hl);
+                job.ca.append(tbuf_ca.data(), (size_t)cl);
+            } else {
+                int64_t nw = 0, nr = 0;
+                reduce_to_host(ps, pe, o.step, nw, nr);
+                for (long long cs = ps; cs < pe; cs += o.step) {
+                    const long long ce = std::min(cs + o.step, pe);
+                    const int32_t* lo = std::lower_bound(rstart.data(), rstart.data() + nr, (int32_t)cs);
+                    const int32_t* hi = std::lower_bound(rstart.data(), rstart.data() + nr, (int32_t)ce);
+                    emit(job.chrom, cs, ce, sums.data() + (cs / o.W - ps / o.W), (ce - 1) / o.W - cs / o.W + 1, lo, rclass.data() + (lo - rstart.data()), hi - lo,
+                         &job.hd, &job.ca);
+                }
+                flush_stats();
+            }
+            job.gpu_s += now_s() - tg;
+        }
+        (void)t_all;
+    }
+
+    // ---- BED mode: the lines of one contig.  One pass over the span they cover (window sums + class runs, run_break 0),
+    //      the clipped first/last window of every line from gl_depth_interval_sums, then the reference's rows line by line
+    //      (depth.go:293-358 sees each line as its own chunk).
+    void run_bed_chrom(DepthJob& job) {
+        std::vector<DepthRegion>& regions = *sh.regions;
+        const std::vector<size_t>& ks = job.lines;
+        const int W = o.W;
+        long long lo = regions[ks[0]].s, hi = regions[ks[0]].e;
+        for (size_t k : ks) { lo = std::min(lo, regions[k].s); hi = std::max(hi, regions[k].e); }
+        const long long span_s = lo / W * W;
+        fetch(job.chrom, span_s, hi, 32, &job);                               // sorted int32: the interval sums and the per-line slices want arrays
+        const double tg = now_s();
+        int64_t nw = 0, nr = 0;
+        auto format_one = [&](size_t k, const int64_t* ws, int64_t nw_, const int32_t* rs_, const uint8_t* rc_, int64_t nr_) {
+            emit(regions[k].chrom, regions[k].s, regions[k].e, ws, nw_, rs_, rc_, nr_, &(*sh.out_hd)[k], &(*sh.out_ca)[k]);
+        };
+        bool batched = ks.size() > 1 && hi - span_s < (1LL << 30) - 2 * (long long)W;
+        if (batched) {
+            reduce_to_host(span_s, hi, 0, nw, nr);
+            int32_t path = 0;
+            batched = gl_depth_last_path(ctx, &path) == GL_OK && (path == 1 || segs.n == 0);   // the interval sums want the fused path's cell index
+        }
+        if (!batched) {
+            // per-line passes over the slice of segments that can reach the line (the arrays are sorted by start)
+            glhts::ContigSegs all;
+            all.start.swap(segs.start); all.end.swap(segs.end); all.n = segs.n; all.format = segs.format; all.max_len = segs.max_len;
+            const int32_t maxlen = std::max<int32_t>(all.max_len, 1);
+            const bool sorted = !sh.preload;                                   // the index-guided decoder sorts; preloaded arrays are in record order
+            for (size_t k : ks) {
+                if (regions[k].e - regions[k].s >= (1LL << 30)) fatal(1, "BED region longer than 2^30-1 bases: %s", regions[k].chrom.c_str());
+                size_t a = 0, b = (size_t)all.n;
+                if (sorted && all.n > 0) {
+                    a = (size_t)(std::lower_bound(all.start.begin(), all.start.end(), (int32_t)std::max<long long>(regions[k].s - maxlen, INT32_MIN)) - all.start.begin());
+                    b = (size_t)(std::lower_bound(all.start.begin(), all.start.end(), (int32_t)std::min<long long>(regions[k].e, INT32_MAX)) - all.start.begin());
+                }
+                segs.format = b > a ? 32 : 0;
+                segs.start.assign(all.start.begin() + (long)a, all.start.begin() + (long)b);
+                segs.end.assign(all.end.begin() + (long)a, all.end.begin() + (long)b);
+                segs.n = (int64_t)(b - a);
+                reduce_to_host(regions[k].s, regions[k].e, 0, nw, nr);
+                format_one(k, sums.data(), nw, rstart.data(), rclass.data(), nr);
+            }
+            flush_stats();
+            job.gpu_s += now_s() - tg;
+            return;
+        }
+        std::vector<int64_t> rsum, edge;
+        std::vector<int32_t> ia, ib, rrs;
+        std::vector<uint8_t> rrc;
+        for (size_t k : ks) {                                            // clipped edge windows
+            const long long s = regions[k].s, e = regions[k].e, w0 = s / W, w1 = (e - 1) / W;
+            if (s % W != 0 || (w0 == w1 && e != (w0 + 1) * W)) { ia.push_back((int32_t)s); ib.push_back((int32_t)std::min(e, (w0 + 1) * W)); }
+            if (w1 > w0 && e != (w1 + 1) * W) { ia.push_back((int32_t)(w1 * W)); ib.push_back((int32_t)e); }
+        }
+        edge.resize(ia.size());
+        if (!ia.empty()) glck(ctx, gl_depth_interval_sums(ctx, ia.data(), ib.data(), (int64_t)ia.size(), edge.data()), "gl_depth_interval_sums");
+        size_t ei = 0;
+        const long long sw0 = span_s / W;
+        for (size_t k : ks) {
+            const long long s = regions[k].s, e = regions[k].e, w0 = s / W, w1 = (e - 1) / W;
+            rsum.assign(sums.begin() + (w0 - sw0), sums.begin() + (w1 - sw0) + 1);
+            if (s % W != 0 || (w0 == w1 && e != (w0 + 1) * W)) rsum[0] = edge[ei++];
+            if (w1 > w0 && e != (w1 + 1) * W) rsum.back() = edge[ei++];
+            const int32_t* rb = rstart.data();
+            const int32_t* first = std::upper_bound(rb, rb + nr, (int32_t)s);          // first run starting after s
+            const int32_t* last = std::lower_bound(rb, rb + nr, (int32_t)e);
+            rrs.assign(1, (int32_t)s);
+            rrc.assign(1, rclass[(size_t)(first - rb) - 1]);                           // run_start[0] == span_s <= s
+            rrs.insert(rrs.end(), first, last);
+            rrc.insert(rrc.end(), rclass.data() + (first - rb), rclass.data() + (last - rb));
+            format_one(k, rsum.data(), (int64_t)rsum.size(), rrs.data(), rrc.data(), (int64_t)rrs.size());
+        }
+        flush_stats();
+        job.gpu_s += now_s() - tg;
+    }
+};
+
+}  // namespace
+
 static int cmd_depth(int argc, char** argv) {
-    std::string w = "250", m = "0", q = "1", chrom, mincov = "4", reference, procs = "0", bed, prefix;
-    bool ordered = false, stats = false;
+    std::string w = "250", m = "0", q = "1", chrom, mincov = "4", reference, procs = "0", bed, prefix, gpus = "0";
+    bool ordered = false, stats = false, timing = false;
     ArgParser ap;
     ap.prog = "goleft depth";
     ap.add("windowsize", 'w', &w); ap.add("maxmeandepth", 'm', &m); ap.addb("ordered", 'o', &ordered);
     ap.add("q", 'Q', &q); ap.add("chrom", 'c', &chrom); ap.add("mincov", 0, &mincov); ap.addb("stats", 's', &stats);
     ap.add("reference", 'r', &reference); ap.add("processes", 'p', &procs); ap.add("bed", 'b', &bed);
     ap.add("prefix", 0, &prefix, true);
+    ap.add("gpus", 0, &gpus);                       // extension: GPUs to use (0 = every visible one)
+    ap.addb("timing", 0, &timing);                  // extension: per-phase wall clock on stderr
     ap.parse(argc, argv);
     if (ap.positional.empty()) ap.fail("bam is required");
     const std::string bam = ap.positional[0];
-    const int W = atoi(w.c_str()), maxmean = atoi(m.c_str()), Q = atoi(q.c_str()), mcov = atoi(mincov.c_str());
-    if (W <= 0) ap.fail("windowsize must be > 0");
-    int threads = atoi(procs.c_str());
-    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    DepthOpts o;
+    o.W = atoi(w.c_str()); o.maxmean = atoi(m.c_str()); o.Q = atoi(q.c_str()); o.mincov = atoi(mincov.c_str());
+    o.stats = stats; o.reference = reference;
+    if (o.W <= 0) ap.fail("windowsize must be > 0");
+    o.threads = atoi(procs.c_str());
+    if (o.threads < 0) o.threads = 0;               // 0 = every thread of the host pool
+    o.step = std::max(1LL, 10000000LL / o.W) * o.W;                          // depth.go:132
+    const double t_start = now_s();
 
     // work list (depth.go:103-159)
-    struct Region { std::string chrom; long long s, e; };
-    std::vector<Region> regions;
-    long long step = std::max(1LL, 10000000LL / W) * W;                    // depth.go:132
+    std::vector<DepthRegion> regions;
+    std::vector<DepthJob> jobs;
     if (!bed.empty()) {
         for (const std::string& ln : read_lines(bed, true)) {
             if (ln.empty()) continue;
-            Region r;
+            DepthRegion r;
             if (!chrom_start_end(ln, r.chrom, r.s, r.e)) fatal(1, "couldn't get region from line%s", ln.c_str());
             regions.push_back(r);
+        }
+        std::map<std::string, size_t> job_of;
+        for (size_t k = 0; k < regions.size(); k++) {
+            if (regions[k].e <= regions[k].s) continue;
+            auto ins = job_of.emplace(regions[k].chrom, jobs.size());
+            if (ins.second) { jobs.emplace_back(); jobs.back().chrom = regions[k].chrom; }
+            DepthJob& j = jobs[ins.first->second];
+            j.lines.push_back(k);
+            j.len = std::max(j.len, regions[k].e);
         }
     } else {
         for (const std::string& ln : read_lines(reference + ".fai", true)) {
@@ -169,220 +474,114 @@ static int cmd_depth(int argc, char** argv) {
             if (t1 == std::string::npos) continue;
             std::string c = ln.substr(0, t1);
             if (!chrom.empty() && c != chrom) continue;
-            long long len = atoll(ln.c_str() + t1 + 1);
-            for (long long i = 0; i < len; i += step) regions.push_back({c, i, std::min(i + step, len)});
+            const long long len = atoll(ln.c_str() + t1 + 1);
+            if (len <= 0) continue;
+            jobs.emplace_back();
+            jobs.back().chrom = c; jobs.back().len = len;
         }
     }
 
-    glhts::SegmentSet segs;
-    std::string err = glhts::bam_decode_segments(bam, Q, threads, -1, segs);
-    if (!err.empty()) fatal(1, "%s", err.c_str());
-    std::map<std::string, int> tid_of;
-    for (size_t i = 0; i < segs.header.refs.size(); i++) tid_of[segs.header.refs[i].name] = (int)i;
+    DepthShared sh;
+    sh.opt = &o;
+    sh.bam_path = bam;
+    std::vector<std::string> out_hd(regions.size()), out_ca(regions.size());
+    sh.regions = &regions; sh.out_hd = &out_hd; sh.out_ca = &out_ca;
+    // an unindexed BAM cannot be seeked: decode it once, whole (the reference's `samtools depth -r` would refuse it)
+    glhts::SegmentSet preload;
+    {
+        glhts::BamFile probe;
+        std::string e = probe.open(bam);
+        if (!e.empty()) fatal(1, "%s", e.c_str());
+        bool usable = probe.has_index;
+        // a stub index (stats bin but an empty / all-zero linear index for a reference that has reads) cannot be seeked with
+        for (size_t r = 0; usable && r < probe.bai.ioffsets.size(); r++) {
+            if (!probe.bai.has_stats[r] || probe.bai.mapped[r] + probe.bai.unmapped[r] == 0) continue;
+            bool any = false;
+            for (uint64_t v : probe.bai.ioffsets[r]) if (v) { any = true; break; }
+            usable = any;
+        }
+        if (!usable) {
+            fprintf(stderr, "goleft depth: no usable .bai next to %s: decoding the whole file (index it for -c / --bed to read only what they need)\n", bam.c_str());
+            int thr = o.threads > 0 ? o.threads : (int)std::max(1u, std::thread::hardware_concurrency());
+            int only = -1;
+            if (!chrom.empty()) for (size_t i = 0; i < probe.header.refs.size(); i++) if (probe.header.refs[i].name == chrom) only = (int)i;
+            e = glhts::bam_decode_segments(bam, o.Q, thr, only, preload);
+            if (!e.empty()) fatal(1, "%s", e.c_str());
+            sh.preload = &preload;
+        }
+    }
+    if (stats) {
+        if (reference.empty()) fatal(1, "goleft depth: --stats needs --reference");
+        std::string e2 = glhts::fai_read(reference + ".fai", sh.fa_index);
+        if (!e2.empty()) fatal(1, "%s", e2.c_str());
+        int fd = open(reference.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd < 0 || fstat(fd, &st) != 0) fatal(1, "cannot open %s", reference.c_str());
+        sh.fa_len = (size_t)st.st_size;
+        if (sh.fa_len) {
+            void* mm = mmap(nullptr, sh.fa_len, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (mm == MAP_FAILED) fatal(1, "cannot mmap %s", reference.c_str());
+            sh.fa_map = static_cast<const uint8_t*>(mm);
+        }
+        close(fd);
+    }
 
-    gl_ctx* ctx = nullptr;
-    if (gl_ctx_create(0, &ctx) != GL_OK) fatal(1, "goleft depth: %s", gl_last_error(nullptr));
     const std::string sfx = chrom.empty() ? "" : "." + chrom;               // depth.go:378-389
     FILE* fca = fopen((prefix + sfx + ".callable.bed").c_str(), "w");
     FILE* fhd = fopen((prefix + sfx + ".depth.bed").c_str(), "w");
     if (!fca || !fhd) fatal(1, "cannot create output files with prefix %s", prefix.c_str());
 
-    std::vector<int64_t> sums;
-    std::vector<int32_t> rstart;
-    std::vector<uint8_t> rclass;
-    auto run_region = [&](const std::string& c, long long rs, long long re, long long run_break, int64_t& nw, int64_t& nr) {
-        static const int32_t none = 0;
-        const int32_t *ps = &none, *pe = &none;
-        int64_t n = 0;
-        auto it = tid_of.find(c);
-        if (it != tid_of.end()) { ps = segs.start[it->second].data(); pe = segs.end[it->second].data(); n = (int64_t)segs.start[it->second].size(); }
-        sums.resize((size_t)((re - 1) / W - rs / W + 1));
-        for (;;) {
-            int rc = gl_depth_region(ctx, rs, re, n ? ps : nullptr, n ? pe : nullptr, n, W, mcov, maxmean, run_break, sums.data(),
-                                     (int64_t)sums.size(), &nw, rstart.data(), rclass.data(), (int64_t)rstart.size(), &nr);
-            if (rc == GL_ERANGE && nr > (int64_t)rstart.size()) { rstart.resize((size_t)nr + 1024); rclass.resize((size_t)nr + 1024); continue; }
-            glck(ctx, rc, "gl_depth_region");
-            break;
-        }
-    };
-    rstart.resize(1 << 16); rclass.resize(1 << 16);
-
-    // ---- row text.  Without --stats a chunk is formatted at once; with it (depth.go:191-200,246-252) the chunks of a
-    // contig are parked, their window rows listed, one gl_fasta_stats launch counts GC/CpG/masked for all of them from
-    // the contig's raw FASTA bytes, and only then is the text made.
-    std::vector<glhts::RefInfo> fa_index;
-    const uint8_t* fa_map = nullptr;
-    size_t fa_len = 0;
-    if (stats) {
-        if (reference.empty()) fatal(1, "goleft depth: --stats needs --reference");
-        std::string e2 = glhts::fai_read(reference + ".fai", fa_index);
-        if (!e2.empty()) fatal(1, "%s", e2.c_str());
-        int fd = open(reference.c_str(), O_RDONLY);
-        struct stat st;
-        if (fd < 0 || fstat(fd, &st) != 0) fatal(1, "cannot open %s", reference.c_str());
-        fa_len = (size_t)st.st_size;
-        if (fa_len) {
-            void* m = mmap(nullptr, fa_len, PROT_READ, MAP_PRIVATE, fd, 0);
-            if (m == MAP_FAILED) fatal(1, "cannot mmap %s", reference.c_str());
-            fa_map = static_cast<const uint8_t*>(m);
-        }
-        close(fd);
+    // ---- GPUs and placement
+    int n_dev = 0;
+    if (gl_device_count(&n_dev) != GL_OK || n_dev < 1) fatal(1, "goleft depth: %s", gl_last_error(nullptr));
+    int G = atoi(gpus.c_str());
+    if (G <= 0 || G > n_dev) G = n_dev;
+    G = (int)std::min<size_t>((size_t)G, std::max<size_t>(jobs.size(), 1));
+    std::vector<int32_t> gpu_of(jobs.size(), 0);
+    {
+        std::vector<int64_t> wts(jobs.size());
+        for (size_t i = 0; i < jobs.size(); i++) wts[i] = jobs[i].len;
+        if (!jobs.empty() && gl_lpt_assign(wts.data(), (int32_t)jobs.size(), G, gpu_of.data(), nullptr) != GL_OK) fatal(1, "gl_lpt_assign failed");
     }
-    struct Pending {
-        std::string chrom; long long rs, re;
-        std::vector<int64_t> sums; std::vector<int32_t> rs_; std::vector<uint8_t> rc_;
-        std::string *hd, *ca;                               // null: straight to the output files
-        int64_t row0, nrows;
-    };
-    std::vector<Pending> pending;
-    std::vector<int64_t> row_s, row_e;
-    auto put_text = [&](std::string* hd_to, std::string* ca_to, char* hd, int64_t hl, char* ca, int64_t cl) {
-        if (hd_to) { hd_to->assign(hd, (size_t)hl); ca_to->assign(ca, (size_t)cl); }
-        else { fwrite(hd, 1, (size_t)hl, fhd); fwrite(ca, 1, (size_t)cl, fca); }
-        gl_free_text(hd); gl_free_text(ca);
-    };
-    auto emit = [&](const std::string& c, long long rs, long long re, const int64_t* ws, int64_t nw, const int32_t* rs_, const uint8_t* rc_,
-                    int64_t nr, std::string* hd_to, std::string* ca_to) {
-        if (!stats) {
-            char *hd = nullptr, *ca = nullptr;
-            int64_t hl = 0, cl = 0;
-            if (gl_depth_format_chunk(c.c_str(), rs, re, W, ws, nw, rs_, rc_, nr, &hd, &hl, &ca, &cl) != GL_OK) fatal(1, "gl_depth_format_chunk failed");
-            put_text(hd_to, ca_to, hd, hl, ca, cl);
-            return;
+    auto worker = [&](int g) {
+        int node = -1, ncpu = 0;
+        if (G > 1) gl_bind_numa_for_device(g, 0, 1, &node, &ncpu);            // this feeder thread next to its GPU (the pool keeps all cores)
+        DepthEngine eng(sh, g);
+        for (size_t i = 0; i < jobs.size(); i++) {
+            if (gpu_of[i] != g) continue;
+            if (bed.empty()) eng.run_contig(jobs[i]); else eng.run_bed_chrom(jobs[i]);
+            { std::lock_guard<std::mutex> lk(sh.mu); jobs[i].done = true; }
+            sh.cv.notify_all();
         }
-        Pending pc{c, rs, re, std::vector<int64_t>(ws, ws + nw), std::vector<int32_t>(rs_, rs_ + nr), std::vector<uint8_t>(rc_, rc_ + nr), hd_to, ca_to,
-                   (int64_t)row_s.size(), 0};
-        int64_t n = 0;
-        gl_depth_chunk_rows(rs, re, W, rs_, rc_, nr, nullptr, nullptr, 0, &n);
-        row_s.resize(row_s.size() + (size_t)n); row_e.resize(row_s.size());
-        if (gl_depth_chunk_rows(rs, re, W, rs_, rc_, nr, row_s.data() + pc.row0, row_e.data() + pc.row0, n, &n) != GL_OK) fatal(1, "gl_depth_chunk_rows failed");
-        pc.nrows = n;
-        pending.push_back(std::move(pc));
     };
-    auto flush_stats = [&]() {                              // all parked chunks belong to one contig
-        if (pending.empty()) return;
-        const std::string& c = pending[0].chrom;
-        std::vector<double> st3(row_s.size() * 3, 0.0);
-        const glhts::RefInfo* ri = nullptr;
-        for (const glhts::RefInfo& r : fa_index) if (r.name == c) { ri = &r; break; }
-        if (!ri) fprintf(stderr, "GC: unknown sequence %s\n", c.c_str());                 // faidx error text; zeros are printed (depth.go:195-199)
-        else if (!row_s.empty()) {
-            const int64_t rec_bytes = std::min<int64_t>((int64_t)fa_len - ri->offset, glhts::fasta_position(*ri, ri->length) + 1);
-            if (ri->offset < 0 || rec_bytes < 0) fatal(1, "bad .fai entry for %s", c.c_str());
-            glck(ctx, gl_fasta_load(ctx, fa_map + ri->offset, rec_bytes), "gl_fasta_load");
-            std::vector<int64_t> ba(row_s.size()), bb(row_s.size());
-            for (size_t i = 0; i < row_s.size(); i++) {
-                // faidx panics on coordinates past the contig; rows are clipped to it here instead
-                const int64_t s = std::min<int64_t>(std::max<int64_t>(row_s[i], 0), ri->length), e = std::min<int64_t>(std::max<int64_t>(row_e[i], s), ri->length);
-                const int64_t ps = glhts::fasta_position(*ri, s), pe = glhts::fasta_position(*ri, e);
-                ba[i] = std::min(ps, rec_bytes);
-                bb[i] = std::max(ba[i], std::min<int64_t>(pe + ((ri->offset + pe < (int64_t)fa_len) ? 1 : 0), rec_bytes));
-            }
-            glck(ctx, gl_fasta_stats(ctx, ba.data(), bb.data(), (int64_t)ba.size(), nullptr, st3.data()), "gl_fasta_stats");
+    glhost_pool_warm();                                                       // create the host pool before the feeder threads narrow their affinity
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++) th.emplace_back(worker, g);
+    // ---- ordered output as the jobs finish
+    if (bed.empty()) {
+        for (size_t i = 0; i < jobs.size(); i++) {
+            { std::unique_lock<std::mutex> lk(sh.mu); sh.cv.wait(lk, [&] { return jobs[i].done; }); }
+            fwrite(jobs[i].hd.data(), 1, jobs[i].hd.size(), fhd);
+            fwrite(jobs[i].ca.data(), 1, jobs[i].ca.size(), fca);
+            std::string().swap(jobs[i].hd); std::string().swap(jobs[i].ca);
         }
-        for (const Pending& pc : pending) {
-            char *hd = nullptr, *ca = nullptr;
-            int64_t hl = 0, cl = 0;
-            if (gl_depth_format_chunk_stats(pc.chrom.c_str(), pc.rs, pc.re, W, pc.sums.data(), (int64_t)pc.sums.size(), pc.rs_.data(), pc.rc_.data(),
-                                            (int64_t)pc.rs_.size(), st3.data() + pc.row0 * 3, pc.nrows, &hd, &hl, &ca, &cl) != GL_OK)
-                fatal(1, "gl_depth_format_chunk_stats failed");
-            put_text(pc.hd, pc.ca, hd, hl, ca, cl);
-        }
-        pending.clear(); row_s.clear(); row_e.clear();
-    };
-
+    }
+    for (auto& t : th) t.join();
     if (!bed.empty()) {
-        // One pass per contig instead of one per BED line: window sums + class runs of the span the contig's regions
-        // cover (run_break 0), the clipped first/last window of every region from gl_depth_interval_sums, then the
-        // reference's rows region by region in BED order (depth.go:293-358 sees each line as its own chunk).
-        std::vector<std::string> out_hd(regions.size()), out_ca(regions.size());
-        auto format_one = [&](size_t k, const int64_t* ws, int64_t nw, const int32_t* rs_, const uint8_t* rc_, int64_t nr) {
-            emit(regions[k].chrom, regions[k].s, regions[k].e, ws, nw, rs_, rc_, nr, &out_hd[k], &out_ca[k]);
-        };
-        std::map<std::string, std::vector<size_t>> by_chrom;
-        std::vector<std::string> chrom_order;
-        for (size_t k = 0; k < regions.size(); k++) {
-            if (regions[k].e <= regions[k].s) continue;
-            auto ins = by_chrom.emplace(regions[k].chrom, std::vector<size_t>());
-            if (ins.second) chrom_order.push_back(regions[k].chrom);
-            ins.first->second.push_back(k);
-        }
-        std::vector<int64_t> rsum, edge;
-        std::vector<int32_t> ia, ib, rrs;
-        std::vector<uint8_t> rrc;
-        for (const std::string& c : chrom_order) {
-            const std::vector<size_t>& ks = by_chrom[c];
-            long long lo = regions[ks[0]].s, hi = regions[ks[0]].e;
-            for (size_t k : ks) { lo = std::min(lo, regions[k].s); hi = std::max(hi, regions[k].e); }
-            const long long span_s = lo / W * W;
-            int64_t nw = 0, nr = 0;
-            bool batched = tid_of.count(c) != 0 && ks.size() > 1 && hi - span_s < (1LL << 31) - 2 * (long long)W;
-            if (batched) {
-                run_region(c, span_s, hi, 0, nw, nr);
-                int32_t path = 0;
-                batched = gl_depth_last_path(ctx, &path) == GL_OK && path == 1;                     // the interval sums want the fused path's cell index
-            }
-            if (!batched) {
-                for (size_t k : ks) {
-                    run_region(c, regions[k].s, regions[k].e, 0, nw, nr);
-                    format_one(k, sums.data(), nw, rstart.data(), rclass.data(), nr);
-                }
-                flush_stats();
-                continue;
-            }
-            ia.clear(); ib.clear();
-            for (size_t k : ks) {                                            // clipped edge windows
-                const long long s = regions[k].s, e = regions[k].e, w0 = s / W, w1 = (e - 1) / W;
-                if (s % W != 0 || (w0 == w1 && e != (w0 + 1) * W)) { ia.push_back((int32_t)s); ib.push_back((int32_t)std::min(e, (w0 + 1) * W)); }
-                if (w1 > w0 && e != (w1 + 1) * W) { ia.push_back((int32_t)(w1 * W)); ib.push_back((int32_t)e); }
-            }
-            edge.resize(ia.size());
-            if (!ia.empty()) glck(ctx, gl_depth_interval_sums(ctx, ia.data(), ib.data(), (int64_t)ia.size(), edge.data()), "gl_depth_interval_sums");
-            size_t ei = 0;
-            const long long sw0 = span_s / W;
-            for (size_t k : ks) {
-                const long long s = regions[k].s, e = regions[k].e, w0 = s / W, w1 = (e - 1) / W;
-                rsum.assign(sums.begin() + (w0 - sw0), sums.begin() + (w1 - sw0) + 1);
-                if (s % W != 0 || (w0 == w1 && e != (w0 + 1) * W)) rsum[0] = edge[ei++];
-                if (w1 > w0 && e != (w1 + 1) * W) rsum.back() = edge[ei++];
-                const int32_t* rb = rstart.data();
-                const int32_t* first = std::upper_bound(rb, rb + nr, (int32_t)s);          // first run starting after s
-                const int32_t* last = std::lower_bound(rb, rb + nr, (int32_t)e);
-                rrs.assign(1, (int32_t)s);
-                rrc.assign(1, rclass[(size_t)(first - rb) - 1]);                           // run_start[0] == span_s <= s
-                rrs.insert(rrs.end(), first, last);
-                rrc.insert(rrc.end(), rclass.data() + (first - rb), rclass.data() + (last - rb));
-                format_one(k, rsum.data(), (int64_t)rsum.size(), rrs.data(), rrc.data(), (int64_t)rrs.size());
-            }
-            flush_stats();
-        }
         for (size_t k = 0; k < regions.size(); k++) {
             fwrite(out_hd[k].data(), 1, out_hd[k].size(), fhd);
             fwrite(out_ca[k].data(), 1, out_ca[k].size(), fca);
         }
-    } else {
-        // whole contig in one pass (run_break = step reproduces the reference's per-chunk run boundaries),
-        // then the reference's rows chunk by chunk, always in order (a valid -o/--ordered output)
-        size_t i = 0;
-        while (i < regions.size()) {
-            size_t j = i;
-            while (j < regions.size() && regions[j].chrom == regions[i].chrom) j++;
-            const long long len = regions[j - 1].e;
-            int64_t nw = 0, nr = 0;
-            run_region(regions[i].chrom, 0, len, step, nw, nr);
-            for (size_t k = i; k < j; k++) {
-                const long long cs = regions[k].s, ce = regions[k].e;
-                const int32_t* lo = std::lower_bound(rstart.data(), rstart.data() + nr, (int32_t)cs);
-                const int32_t* hi = std::lower_bound(rstart.data(), rstart.data() + nr, (int32_t)ce);
-                emit(regions[k].chrom, cs, ce, sums.data() + cs / W, (ce - 1) / W - cs / W + 1, lo, rclass.data() + (lo - rstart.data()), hi - lo, nullptr, nullptr);
-            }
-            flush_stats();
-            i = j;
-        }
     }
     fclose(fca); fclose(fhd);
-    if (fa_map) munmap(const_cast<uint8_t*>(fa_map), fa_len);
-    gl_ctx_destroy(ctx);
+    if (sh.fa_map) munmap(const_cast<uint8_t*>(sh.fa_map), sh.fa_len);
+    if (timing) {
+        double dec = 0, gpu = 0; long long rec = 0, bin = 0, bout = 0;
+        for (const DepthJob& j : jobs) { dec += j.decode_s; gpu += j.gpu_s; rec += j.records; bin += j.bytes_in; bout += j.bytes_out; }
+        fprintf(stderr, "{\"goleft_depth_timing\": {\"wall_s\": %.4f, \"gpus\": %d, \"jobs\": %zu, \"decode_wall_s_sum\": %.4f, \"gpu_call_s_sum\": %.4f, "
+                        "\"records\": %lld, \"bgzf_bytes_in\": %lld, \"bgzf_bytes_out\": %lld, \"host_threads\": %d}}\n",
+                now_s() - t_start, G, jobs.size(), dec, gpu, rec, bin, bout, glhost_pool_size());
+    }
     return 0;
 }
 

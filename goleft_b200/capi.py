@@ -117,6 +117,11 @@ _proto("gl_bam_decode_segments", C.c_int, C.c_char_p, C.c_int32, C.c_int32, C.c_
 _proto("gl_segset_n_refs", C.c_int, _vp, _i32p, _i64p, _i64p)
 _proto("gl_segset_ref", C.c_int, _vp, C.c_int32, C.POINTER(C.c_char_p), _i64p, C.POINTER(_vp), C.POINTER(_vp), _i64p)
 _proto("gl_segset_free", None, _vp)
+_proto("gl_bam_open", C.c_int, C.c_char_p, C.POINTER(_vp), _vp, C.c_int64)
+_proto("gl_bam_close", None, _vp)
+_proto("gl_bam_info", C.c_int, _vp, _i32p, _i32p)
+_proto("gl_bam_ref", C.c_int, _vp, C.c_int32, C.POINTER(C.c_char_p), _i64p, _i64p)
+_proto("gl_bam_decode", C.c_int, _vp, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int64)
 _proto("gl_bai_read", C.c_int, C.c_char_p, C.POINTER(_vp), _vp, C.c_int64)
 _proto("gl_bai_n_refs", C.c_int, _vp, _i32p, _u64p)
 _proto("gl_bai_ref", C.c_int, _vp, C.c_int32, C.POINTER(_vp), _i64p, _u64p, _u64p, _i32p)
@@ -333,6 +338,55 @@ def bam_segments(path: str, min_mapq: int = 1, threads: int = 4, only_tid: int =
         return {"refs": refs, "segments": segs, "n_records": nrec.value, "n_pass": npass.value}
     finally:
         lib.gl_segset_free(h)
+
+
+class _BamSegments(C.Structure):
+    _fields_ = [("format", C.c_int32), ("units", C.c_int32), ("max_len", C.c_int32), ("_pad", C.c_int32), ("n", C.c_int64),
+                ("a0", _vp), ("a1", _vp), ("a2", _vp), ("n_records", C.c_int64), ("n_pass", C.c_int64), ("bytes_in", C.c_int64),
+                ("bytes_out", C.c_int64), ("inflate_s", C.c_double), ("parse_s", C.c_double), ("wall_s", C.c_double)]
+
+
+class Bam:
+    """Index-guided parallel feeder (gl_bam_*): host-only."""
+
+    def __init__(self, path: str):
+        h = _vp()
+        err = C.create_string_buffer(512)
+        rc = lib.gl_bam_open(path.encode(), C.byref(h), C.cast(err, _vp), 512)
+        if rc != GL_OK:
+            raise GlError(rc, err.value.decode())
+        self.h = h
+        n, hi = C.c_int32(0), C.c_int32(0)
+        lib.gl_bam_info(h, C.byref(n), C.byref(hi))
+        self.has_index = bool(hi.value)
+        self.refs = []
+        for tid in range(n.value):
+            name, ln, nm = C.c_char_p(), C.c_int64(0), C.c_int64(0)
+            lib.gl_bam_ref(h, tid, C.byref(name), C.byref(ln), C.byref(nm))
+            self.refs.append((name.value.decode(), ln.value, nm.value))
+
+    def close(self):
+        if self.h:
+            lib.gl_bam_close(self.h)
+            self.h = None
+
+    def decode(self, tid: int, beg: int = 0, end: int = 1 << 40, min_mapq: int = 1, threads: int = 0, want: int = 0):
+        """-> dict(format, arrays (copies), stats)"""
+        o = _BamSegments()
+        err = C.create_string_buffer(512)
+        rc = lib.gl_bam_decode(self.h, tid, beg, end, min_mapq, threads, want, C.byref(o), C.cast(err, _vp), 512)
+        if rc != GL_OK:
+            raise GlError(rc, err.value.decode())
+        out = {"format": o.format, "n": o.n, "units": o.units, "max_len": o.max_len, "n_records": o.n_records, "n_pass": o.n_pass,
+               "bytes_in": o.bytes_in, "bytes_out": o.bytes_out, "inflate_s": o.inflate_s, "parse_s": o.parse_s, "wall_s": o.wall_s}
+        if o.format == 8 and o.n:
+            out["anchors"] = np.ctypeslib.as_array(C.cast(o.a0, _i32p), (o.n,)).copy()
+            out["dstart"] = np.ctypeslib.as_array(C.cast(o.a1, _u8p), (o.n * 64,)).copy()
+            out["len"] = np.ctypeslib.as_array(C.cast(o.a2, _u8p), (o.n * 64,)).copy()
+        elif o.format == 32 and o.n:
+            out["start"] = np.ctypeslib.as_array(C.cast(o.a0, _i32p), (o.n,)).copy()
+            out["end"] = np.ctypeslib.as_array(C.cast(o.a1, _i32p), (o.n,)).copy()
+        return out
 
 
 def crai_make_sizes(start, span, nbytes) -> np.ndarray:

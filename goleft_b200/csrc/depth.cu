@@ -1884,29 +1884,36 @@ int gl_depth_region(gl_ctx* ctx, int64_t region_start, int64_t region_end, const
     return region_fetch(ctx, sum_out, win_cap, n_windows, run_start, run_class, run_cap, n_runs);
 }
 
-// ---- one contig, segments in, BED text out (depth/depth.go:238-364 for every 10 Mb chunk of the contig, in order)
-int gl_depth_bed_contig_packed8(gl_ctx* ctx, const char* chrom, int64_t contig_len, const int32_t* anchors, const uint8_t* dstart,
+// ---- one region of a contig (whole chunks), segments in, BED text out: depth/depth.go:238-364 for every chunk, in order
+static int bed_args_ok(gl_ctx* ctx, int64_t rs, int64_t re, int32_t W, int64_t step) {
+    if (W <= 0 || step <= 0 || step % W != 0) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_region: step must be a positive multiple of W (depth.go:132)");
+    if (rs < 0 || re <= rs || rs % step != 0) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_region: the region must start on a chunk boundary (a multiple of step)");
+    return GL_OK;
+}
+
+int gl_depth_bed_region_packed8(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, const int32_t* anchors, const uint8_t* dstart,
                                 const uint8_t* len, int64_t n_blocks, int32_t W, int32_t mincov, int32_t maxmean, int64_t step,
                                 char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed, int64_t callable_cap,
                                 int64_t* callable_len) {
-    if (W <= 0 || step <= 0 || step % W != 0) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_contig: step must be a positive multiple of W (depth.go:132)");
-    GL_CHECK(gl_depth_begin(ctx, 0, contig_len));
+    GL_CHECK(gl_use(ctx));
+    GL_CHECK(bed_args_ok(ctx, rs, re, W, step));
+    GL_CHECK(gl_depth_begin(ctx, rs, re));
     GL_CHECK(add_packed8_host(ctx, anchors, dstart, len, n_blocks, true));
     GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, step));
     return gl_depth_text(ctx, chrom, depth_bed, depth_cap, depth_len, callable_bed, callable_cap, callable_len);
 }
 
-int gl_depth_bed_contig(gl_ctx* ctx, const char* chrom, int64_t contig_len, const int32_t* start, const int32_t* end, int64_t n,
+int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, const int32_t* start, const int32_t* end, int64_t n,
                         int32_t W, int32_t mincov, int32_t maxmean, int64_t step, int32_t threads,
                         char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed, int64_t callable_cap,
                         int64_t* callable_len) {
     GL_CHECK(gl_use(ctx));
-    if (W <= 0 || step <= 0 || step % W != 0) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_contig: step must be a positive multiple of W (depth.go:132)");
-    if (n < 0 || (n > 0 && (!start || !end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_contig: bad segments");
+    GL_CHECK(bed_args_ok(ctx, rs, re, W, step));
+    if (n < 0 || (n > 0 && (!start || !end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_region: bad segments");
     // The int32 arrays go up as they are (PCIe-bound: 8 B/segment).  GL_BED_PACK=1 packs short-read input to packed8
     // (2 B/segment) on the host pool first: a quarter of the PCIe bytes, but on the 2 x 32-core host of the B200 box the
     // pack costs 2-3 ms per 11 M segments, more than the 1.2 ms of upload it saves (tools/e2e_text_probe.py), so it is
-    // opt-in; a feeder that emits packed8 itself calls gl_depth_bed_contig_packed8.
+    // opt-in; a feeder that emits packed8 itself (gl_bam_decode) calls gl_depth_bed_region_packed8.
     static const int force = [] { const char* e = getenv("GL_BED_PACK"); return e ? atoi(e) : 0; }();
     bool pack = force == 1 && n >= 4096;
     if (pack) {                                       // long segments would be cut into many 255-base pieces: judged on a sample
@@ -1916,7 +1923,7 @@ int gl_depth_bed_contig(gl_ctx* ctx, const char* chrom, int64_t contig_len, cons
         pack = tot <= 400 * cnt;
     }
     if (!pack) {
-        GL_CHECK(gl_depth_begin(ctx, 0, contig_len));
+        GL_CHECK(gl_depth_begin(ctx, rs, re));
         GL_CHECK(gl_depth_add_segments(ctx, start, end, n));
         GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, step));
         return gl_depth_text(ctx, chrom, depth_bed, depth_cap, depth_len, callable_bed, callable_cap, callable_len);
@@ -1940,10 +1947,26 @@ int gl_depth_bed_contig(gl_ctx* ctx, const char* chrom, int64_t contig_len, cons
         const int rc = gl_pack_segments8_mt(start, end, n, threads, a, d, l, cap_now, &nb);
         if (rc == GL_ERANGE) { cap = nb + 16; continue; }
         if (rc != GL_OK) return gl_fail(ctx, rc, "gl_pack_segments8_mt failed");
-        return gl_depth_bed_contig_packed8(ctx, chrom, contig_len, a, d, l, nb, W, mincov, maxmean, step, depth_bed, depth_cap, depth_len,
+        return gl_depth_bed_region_packed8(ctx, chrom, rs, re, a, d, l, nb, W, mincov, maxmean, step, depth_bed, depth_cap, depth_len,
                                            callable_bed, callable_cap, callable_len);
     }
-    return gl_fail(ctx, GL_ERANGE, "gl_depth_bed_contig: packing did not converge");
+    return gl_fail(ctx, GL_ERANGE, "gl_depth_bed_region: packing did not converge");
+}
+
+int gl_depth_bed_contig_packed8(gl_ctx* ctx, const char* chrom, int64_t contig_len, const int32_t* anchors, const uint8_t* dstart,
+                                const uint8_t* len, int64_t n_blocks, int32_t W, int32_t mincov, int32_t maxmean, int64_t step,
+                                char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed, int64_t callable_cap,
+                                int64_t* callable_len) {
+    return gl_depth_bed_region_packed8(ctx, chrom, 0, contig_len, anchors, dstart, len, n_blocks, W, mincov, maxmean, step, depth_bed, depth_cap,
+                                       depth_len, callable_bed, callable_cap, callable_len);
+}
+
+int gl_depth_bed_contig(gl_ctx* ctx, const char* chrom, int64_t contig_len, const int32_t* start, const int32_t* end, int64_t n,
+                        int32_t W, int32_t mincov, int32_t maxmean, int64_t step, int32_t threads,
+                        char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed, int64_t callable_cap,
+                        int64_t* callable_len) {
+    return gl_depth_bed_region(ctx, chrom, 0, contig_len, start, end, n, W, mincov, maxmean, step, threads, depth_bed, depth_cap, depth_len,
+                               callable_bed, callable_cap, callable_len);
 }
 
 static int region_fetch(gl_ctx* ctx, int64_t* sum_out, int64_t win_cap, int64_t* n_windows, int32_t* run_start, uint8_t* run_class,

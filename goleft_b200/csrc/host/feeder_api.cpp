@@ -5,9 +5,11 @@
 #include <vector>
 #include "../../../include/goleft_b200.h"
 #include "hts_io.h"
+#include "bam_feed.h"
 
 struct gl_segset { glhts::SegmentSet s; };
 struct gl_bai { glhts::BaiIndex b; };
+struct gl_bam { glhts::BamFile f; glhts::ContigSegs segs; };
 
 static void put_err(char* err, int64_t cap, const std::string& m) {
     if (!err || cap <= 0) return;
@@ -77,6 +79,52 @@ int gl_bai_ref(const gl_bai* b, int32_t tid, const uint64_t** ioffsets, int64_t*
 }
 
 void gl_bai_free(gl_bai* b) { delete b; }
+
+// ---- index-guided parallel feeder (bam_feed.h)
+int gl_bam_open(const char* path, gl_bam** out, char* err, int64_t err_cap) {
+    if (!path || !out) return GL_EINVAL;
+    gl_bam* b = new gl_bam();
+    const std::string e = b->f.open(path);
+    if (!e.empty()) { put_err(err, err_cap, e); delete b; *out = nullptr; return GL_EINVAL; }
+    *out = b;
+    return GL_OK;
+}
+
+void gl_bam_close(gl_bam* b) { delete b; }
+
+int gl_bam_info(const gl_bam* b, int32_t* n_refs, int32_t* has_index) {
+    if (!b) return GL_EINVAL;
+    if (n_refs) *n_refs = (int32_t)b->f.header.refs.size();
+    if (has_index) *has_index = b->f.has_index ? 1 : 0;
+    return GL_OK;
+}
+
+int gl_bam_ref(const gl_bam* b, int32_t tid, const char** name, int64_t* length, int64_t* n_mapped) {
+    if (!b || tid < 0 || tid >= (int32_t)b->f.header.refs.size()) return GL_EINVAL;
+    if (name) *name = b->f.header.refs[tid].name.c_str();
+    if (length) *length = b->f.header.refs[tid].length;
+    if (n_mapped) *n_mapped = (b->f.has_index && tid < (int32_t)b->f.bai.mapped.size() && b->f.bai.has_stats[tid]) ? (int64_t)b->f.bai.mapped[tid] : -1;
+    return GL_OK;
+}
+
+int gl_bam_decode(gl_bam* b, int32_t tid, int64_t beg, int64_t end, int32_t min_mapq, int32_t threads, int32_t want_format,
+                  gl_bam_segments* out, char* err, int64_t err_cap) {
+    if (!b || !out) return GL_EINVAL;
+    memset(out, 0, sizeof *out);
+    glhts::DecodeStats st;
+    const std::string e = b->f.decode(tid, beg, end, min_mapq, threads, want_format, b->segs, &st);
+    if (!e.empty()) { put_err(err, err_cap, e); return GL_EINVAL; }
+    out->format = b->segs.format;
+    if (b->segs.format == 8) {
+        out->n = b->segs.n_blocks; out->a0 = b->segs.anchors.data(); out->a1 = b->segs.ds.data(); out->a2 = b->segs.len.data();
+    } else if (b->segs.format == 32) {
+        out->n = b->segs.n; out->a0 = b->segs.start.data(); out->a1 = b->segs.end.data(); out->a2 = nullptr;
+    }
+    out->n_records = st.n_records; out->n_pass = st.n_pass; out->bytes_in = st.bytes_in; out->bytes_out = st.bytes_out;
+    out->inflate_s = st.inflate_s; out->parse_s = st.parse_s; out->wall_s = st.wall_s; out->units = st.units;
+    out->max_len = b->segs.max_len;
+    return GL_OK;
+}
 
 int gl_crai_make_sizes(const int64_t* aln_start, const int64_t* aln_span, const int32_t* slice_len, int64_t n, int64_t* sizes,
                        int64_t cap, int64_t* n_sizes) {

@@ -427,6 +427,8 @@ std::string bai_read(const std::string& path, BaiIndex& out) {
     out.mapped.assign((size_t)n_ref, 0);
     out.unmapped.assign((size_t)n_ref, 0);
     out.has_stats.assign((size_t)n_ref, 0);
+    out.ref_beg.assign((size_t)n_ref, 0);
+    out.ref_end.assign((size_t)n_ref, 0);
     for (int32_t r = 0; r < n_ref; r++) {
         if (off + 4 > b.size()) return "truncated BAI: " + path;
         const int32_t n_bin = rdi32(b.data() + off); off += 4;
@@ -440,6 +442,12 @@ std::string bai_read(const std::string& path, BaiIndex& out) {
                 out.mapped[r] = rd64(b.data() + off + 16);
                 out.unmapped[r] = rd64(b.data() + off + 24);
                 out.has_stats[r] = 1;
+            } else {
+                for (int32_t c = 0; c < n_chunk; c++) {
+                    const uint64_t cb = rd64(b.data() + off + 16 * (size_t)c), ce = rd64(b.data() + off + 16 * (size_t)c + 8);
+                    if (out.ref_beg[r] == 0 || cb < out.ref_beg[r]) out.ref_beg[r] = cb;
+                    if (ce > out.ref_end[r]) out.ref_end[r] = ce;
+                }
             }
             off += 16 * (size_t)n_chunk;
         }

@@ -68,6 +68,8 @@ struct BaiIndex {
     std::vector<uint64_t> mapped, unmapped;              // stats pseudo-bin 0x924a (indexcov/types.go:19,33-43)
     std::vector<uint8_t> has_stats;
     uint64_t n_no_coor = 0;
+    std::vector<uint64_t> ref_beg, ref_end;              // virtual-offset range of the reference's records (min chunk begin /
+                                                         // max chunk end over its bins; 0 = no records)
 };
 std::string bai_read(const std::string& path, BaiIndex& out);
 

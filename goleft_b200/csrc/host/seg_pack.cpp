@@ -164,23 +164,19 @@ int gl_pack_segments8(const int32_t* start, const int32_t* end, int64_t n, int32
 
 // ------------------------------------------------------------------------------------------------ parallel packed8
 // gl_pack_segments8_mt: the same format from `threads` workers.  The input (BAM order: starts sorted up to one read's
-// span) is cut into P index chunks; x_k = the smallest start in chunks >= k, so the position ranges [x_k, x_{k+1}) are
-// disjoint, increasing, and every piece of chunk k starts at or after x_k.  Worker k keeps the pieces of its chunk that
-// start below x_{k+1} ("own", nearly sorted: bounded insertion sort) and sets aside the few that start later (second
-// blocks of deletion / spliced reads at a chunk edge, tails of long segments); after every earlier chunk has published
-// its set-aside list, worker k merges the ones that fall in its range, encodes its blocks privately, and copies them
-// behind the blocks of worker k-1.  Anchors come out globally sorted, which is what K_tileidx8 needs.
+// span) is cut into P index chunks; each worker turns its chunk into a start-sorted piece list (bounded insertion sort);
+// assemble_p8 (seg_pack.h) then gives every worker a position range [x_k, x_{k+1}), x_k = the smallest start in chunks
+// >= k: it takes its own pieces below x_{k+1} plus the few pieces earlier chunks hold beyond their range (second blocks
+// of deletion / spliced reads at a chunk edge, tails of long segments), encodes its blocks privately, and the parts are
+// concatenated.  Anchors come out globally sorted, which is what K_tileidx8 needs.
 #include <atomic>
 #include <limits.h>
 #include <memory>
 #include <mutex>
+#include "seg_pack.h"
 #include "thread_pool.h"
 
-namespace {
-
-typedef std::pair<int32_t, int32_t> Piece;          // (start, length 1..255)
-
-struct P8Out { std::vector<int32_t> anchors; std::vector<uint8_t> ds, len; int64_t nb = 0; };
+namespace glhost {
 
 void sort_nearly_sorted(Piece* seg, size_t m) {
     size_t budget = 64 * m + 1024;
@@ -200,19 +196,33 @@ void sort_nearly_sorted(Piece* seg, size_t m) {
         }
     }
 }
-void sort_nearly_sorted(std::vector<Piece>& seg) { sort_nearly_sorted(seg.data(), seg.size()); }
+
+void split_long_pieces(std::vector<Piece>& list) {
+    bool any = false;
+    for (const Piece& p : list) if (p.second > 255) { any = true; break; }
+    if (!any) return;
+    std::vector<Piece> out;
+    out.reserve(list.size() + list.size() / 4 + 16);
+    for (const Piece& p : list) {
+        int64_t s = p.first, left = p.second;
+        while (left > 0) { const int64_t k = left > 255 ? 255 : left; out.emplace_back((int32_t)s, (int32_t)k); s += k; left -= k; }
+    }
+    sort_nearly_sorted(out.data(), out.size());
+    list.swap(out);
+}
 
 // blocks of 64 slots from pieces in start order (same rules as gl_pack_segments8)
 void encode_pieces(const Piece* seg, size_t m, P8Out& o) {
-    o.anchors.clear(); o.ds.clear(); o.len.clear();
+    o.anchors.clear();
     o.anchors.reserve(m / 48 + 16);
-    o.ds.resize((m / 48 + 16) * kP8); o.len.resize((m / 48 + 16) * kP8);
+    size_t cap = m / 48 + 16;
+    if (o.ds.size() < cap * kP8) { o.ds.resize(cap * kP8); o.len.resize(cap * kP8); }
+    cap = o.ds.size() / kP8;
     int64_t nb = 0;
     int cnt = kP8;
     int64_t last = 0;
     uint8_t* ds = o.ds.data();
     uint8_t* ln = o.len.data();
-    size_t cap = o.ds.size() / kP8;
     auto grow = [&]() {
         cap = cap * 2 + 16;
         o.ds.resize(cap * kP8); o.len.resize(cap * kP8);
@@ -258,108 +268,148 @@ void encode_pieces(const Piece* seg, size_t m, P8Out& o) {
     o.nb = nb;
 }
 
-struct MtScratch { std::vector<Piece> own, over, merged; P8Out out; };
+namespace {
+
+// x[k] = min start over lists >= k (x[0] = -inf, x[P] = +inf)
+std::vector<int64_t> range_bounds(const std::vector<const std::vector<Piece>*>& lists) {
+    const size_t P = lists.size();
+    std::vector<int64_t> x(P + 1, INT64_MAX);
+    for (size_t k = P; k-- > 0;) {
+        x[k] = x[k + 1];
+        if (!lists[k]->empty()) x[k] = std::min<int64_t>(x[k], lists[k]->front().first);
+    }
+    if (P) x[0] = INT64_MIN;
+    return x;
+}
+
+// the pieces task k owns: list k below x[k+1] (a prefix) + what earlier lists hold in [x[k], x[k+1]).  Returns a pointer
+// into list k when nothing has to be merged in, else fills `scratch`.
+const Piece* gather_range(const std::vector<const std::vector<Piece>*>& lists, const std::vector<int64_t>& x, size_t k,
+                          std::vector<Piece>& scratch, size_t* m) {
+    auto cmp = [](const Piece& p, int64_t v) { return (int64_t)p.first < v; };
+    const std::vector<Piece>& mine = *lists[k];
+    const size_t own = (size_t)(std::lower_bound(mine.begin(), mine.end(), x[k + 1], cmp) - mine.begin());
+    scratch.clear();
+    for (size_t j = 0; j < k; j++) {
+        const std::vector<Piece>& ov = *lists[j];
+        if (ov.empty() || (int64_t)ov.back().first < x[k]) continue;
+        auto lo = std::lower_bound(ov.begin(), ov.end(), x[k], cmp);
+        auto up = std::lower_bound(lo, ov.end(), x[k + 1], cmp);
+        scratch.insert(scratch.end(), lo, up);
+    }
+    if (scratch.empty()) { *m = own; return mine.data(); }
+    auto less = [](const Piece& p, const Piece& q) { return p.first < q.first; };
+    std::stable_sort(scratch.begin(), scratch.end(), less);
+    const size_t mid = scratch.size();
+    scratch.insert(scratch.end(), mine.begin(), mine.begin() + (long)own);
+    std::inplace_merge(scratch.begin(), scratch.begin() + (long)mid, scratch.end(), less);
+    *m = scratch.size();
+    return scratch.data();
+}
 
 }  // namespace
 
+void assemble_p8(const std::vector<const std::vector<Piece>*>& lists, int threads, Assembled& a) {
+    const size_t P = lists.size();
+    const std::vector<int64_t> x = range_bounds(lists);
+    if (a.parts.size() < P) a.parts.resize(P);
+    if (a.merged.size() < P) a.merged.resize(P);
+    a.off.assign(P + 1, 0);
+    ThreadPool::global().run((int64_t)P, [&](int64_t k, int) {
+        size_t m = 0;
+        const Piece* src = gather_range(lists, x, (size_t)k, a.merged[(size_t)k], &m);
+        encode_pieces(src, m, a.parts[(size_t)k]);
+    }, threads);
+    for (size_t k = 0; k < P; k++) a.off[k + 1] = a.off[k] + a.parts[k].nb;
+    a.total = a.off[P];
+}
+
+void assemble_i32(const std::vector<const std::vector<Piece>*>& lists, int threads, Assembled& a) {
+    const size_t P = lists.size();
+    const std::vector<int64_t> x = range_bounds(lists);
+    if (a.merged.size() < P) a.merged.resize(P);
+    a.off.assign(P + 1, 0);
+    ThreadPool::global().run((int64_t)P, [&](int64_t k, int) {
+        size_t m = 0;
+        std::vector<Piece>& sc = a.merged[(size_t)k];
+        const Piece* src = gather_range(lists, x, (size_t)k, sc, &m);
+        if (src != sc.data()) sc.assign(src, src + m);           // keep a private copy: concat_i32 reads a.merged
+    }, threads);
+    for (size_t k = 0; k < P; k++) a.off[k + 1] = a.off[k] + (int64_t)a.merged[k].size();
+    a.total = a.off[P];
+}
+
+void concat_p8(const Assembled& a, int threads, int32_t* anchors, uint8_t* dstart, uint8_t* len) {
+    const size_t P = a.off.size() - 1;
+    ThreadPool::global().run((int64_t)P, [&](int64_t k, int) {
+        const P8Out& o = a.parts[(size_t)k];
+        const int64_t at = a.off[(size_t)k];
+        if (o.nb == 0) return;
+        memcpy(anchors + at, o.anchors.data(), (size_t)o.nb * 4);
+        memcpy(dstart + at * kP8, o.ds.data(), (size_t)o.nb * kP8);
+        memcpy(len + at * kP8, o.len.data(), (size_t)o.nb * kP8);
+    }, threads);
+}
+
+void concat_i32(const Assembled& a, int threads, int32_t* start, int32_t* end) {
+    const size_t P = a.off.size() - 1;
+    ThreadPool::global().run((int64_t)P, [&](int64_t k, int) {
+        const std::vector<Piece>& v = a.merged[(size_t)k];
+        int32_t* s = start + a.off[(size_t)k];
+        int32_t* e = end + a.off[(size_t)k];
+        for (size_t i = 0; i < v.size(); i++) { s[i] = v[i].first; e[i] = v[i].first + v[i].second; }
+    }, threads);
+}
+
+}  // namespace glhost
+
 extern "C" int gl_pack_segments8_mt(const int32_t* start, const int32_t* end, int64_t n, int32_t threads, int32_t* anchors, uint8_t* dstart,
                                     uint8_t* len, int64_t cap_blocks, int64_t* n_blocks) {
+    using namespace glhost;
     if (n < 0 || !n_blocks || (n > 0 && (!start || !end))) return GL_EINVAL;
-    glhost::ThreadPool& pool = glhost::ThreadPool::global();
-    int T = threads > 0 ? std::min<int>(threads, pool.size()) : pool.size();
-    int64_t P = std::min<int64_t>((int64_t)T, n / 8192 + 1);
+    ThreadPool& pool = ThreadPool::global();
+    const int T = threads > 0 ? std::min<int>(threads, pool.size()) : pool.size();
+    const int64_t P = std::min<int64_t>((int64_t)T, n / 8192 + 1);
     if (P <= 1) return gl_pack_segments8(start, end, n, anchors, dstart, len, cap_blocks, n_blocks);
-    std::vector<int64_t> cmin((size_t)P, INT64_MAX), x((size_t)P + 1);
+    // scratch kept between calls so the big lists are allocated and page-faulted once; concurrent callers take turns
+    // (each call uses every pool thread anyway)
+    struct Scratch { std::vector<std::vector<Piece>> lists; Assembled a; };
+    static std::mutex scratch_mu;
+    static Scratch S;
+    std::lock_guard<std::mutex> scratch_lk(scratch_mu);
+    if ((int64_t)S.lists.size() < P) S.lists.resize((size_t)P);
     auto lo_of = [&](int64_t k) { return (int64_t)((__int128)n * k / P); };
     pool.run(P, [&](int64_t k, int) {
-        int64_t m = INT64_MAX;
+        std::vector<Piece>& L = S.lists[(size_t)k];
         const int64_t a = lo_of(k), b = lo_of(k + 1);
-        for (int64_t i = a; i < b; i++) if (end[i] > start[i] && start[i] < m) m = start[i];
-        cmin[(size_t)k] = m;
-    }, T);
-    x[(size_t)P] = INT64_MAX;
-    for (int64_t k = P - 1; k >= 0; k--) x[(size_t)k] = std::min(cmin[(size_t)k], x[(size_t)k + 1]);
-    x[0] = INT64_MIN;
-
-    // scratch per task (a fast worker may run two tasks), kept between calls so the big lists are allocated and
-    // page-faulted once; concurrent callers take turns (each call uses every pool thread anyway)
-    static std::mutex scratch_mu;
-    static std::vector<std::unique_ptr<MtScratch>> scratch;
-    std::lock_guard<std::mutex> scratch_lk(scratch_mu);
-    while ((int64_t)scratch.size() < P) scratch.emplace_back(new MtScratch());
-    std::vector<MtScratch*> scr((size_t)P, nullptr);
-    for (int64_t k = 0; k < P; k++) scr[(size_t)k] = scratch[(size_t)k].get();
-    std::vector<std::atomic<int>> phase((size_t)P);          // 1: set-aside list published, 2: block count published
-    std::vector<int64_t> off((size_t)P + 1, 0);
-    for (auto& f : phase) f.store(0, std::memory_order_relaxed);
-    const bool have_out = anchors && dstart && len;
-    std::atomic<bool> fits(true);
-    pool.run(P, [&](int64_t k, int) {
-        MtScratch& S = *scr[(size_t)k];
-        S.over.clear();
-        const int64_t a = lo_of(k), b = lo_of(k + 1), hi = x[(size_t)k + 1];
-        // one pass: split into pieces of <= 255, keep or set aside, and notice whether the kept ones are already sorted
-        size_t own_cap = (size_t)(b - a) + 64, m_own = 0;
-        if (S.own.size() < own_cap) S.own.resize(own_cap);
-        Piece* own = S.own.data();
-        bool own_sorted = true;
+        size_t cap = (size_t)(b - a) + 64, m = 0;
+        if (L.size() < cap) L.resize(cap);
+        Piece* out = L.data();
+        bool sorted = true;
         int32_t prev = INT32_MIN;
         for (int64_t i = a; i < b; i++) {
             const int32_t s0 = start[i], e0 = end[i];
             const int64_t l0 = (int64_t)e0 - s0;
             if (l0 <= 0) continue;
-            if (l0 <= 255 && s0 < hi) {                                  // the common case: one piece, kept
-                if (m_own == own_cap) { S.own.resize(own_cap *= 2); own = S.own.data(); }
-                own_sorted &= s0 >= prev;
-                prev = s0;
-                own[m_own++] = Piece(s0, (int32_t)l0);
-                continue;
-            }
             int64_t sx = s0;
-            while (sx < e0) {
+            do {                                                       // pieces of <= 255 (one for a short read's block)
                 const int64_t piece = e0 - sx > 255 ? 255 : e0 - sx;
-                if (sx < hi) {
-                    if (m_own == own_cap) { S.own.resize(own_cap *= 2); own = S.own.data(); }
-                    own_sorted &= sx >= prev;
-                    prev = (int32_t)sx;
-                    own[m_own++] = Piece((int32_t)sx, (int32_t)piece);
-                } else S.over.emplace_back((int32_t)sx, (int32_t)piece);
+                if (m == cap) { L.resize(cap *= 2); out = L.data(); }
+                sorted &= sx >= prev;
+                prev = (int32_t)sx;
+                out[m++] = Piece((int32_t)sx, (int32_t)piece);
                 sx += piece;
-            }
+            } while (sx < e0);
         }
-        sort_nearly_sorted(S.over);
-        phase[(size_t)k].store(1, std::memory_order_release);
-        if (!own_sorted) sort_nearly_sorted(own, m_own);
-        // pieces the earlier chunks set aside that start in [x_k, x_{k+1})
-        S.merged.clear();
-        for (int64_t j = 0; j < k; j++) {
-            while (phase[(size_t)j].load(std::memory_order_acquire) < 1) std::this_thread::yield();
-            const std::vector<Piece>& ov = scr[(size_t)j]->over;
-            auto lo = std::lower_bound(ov.begin(), ov.end(), x[(size_t)k], [](const Piece& p, int64_t v) { return (int64_t)p.first < v; });
-            auto up = std::lower_bound(ov.begin(), ov.end(), hi, [](const Piece& p, int64_t v) { return (int64_t)p.first < v; });
-            S.merged.insert(S.merged.end(), lo, up);
-        }
-        const Piece* src = own;
-        size_t m = m_own;
-        if (!S.merged.empty()) {
-            std::stable_sort(S.merged.begin(), S.merged.end(), [](const Piece& p, const Piece& q) { return p.first < q.first; });
-            const size_t mid = S.merged.size();
-            S.merged.insert(S.merged.end(), own, own + m_own);
-            std::inplace_merge(S.merged.begin(), S.merged.begin() + (long)mid, S.merged.end(), [](const Piece& p, const Piece& q) { return p.first < q.first; });
-            src = S.merged.data();
-            m = S.merged.size();
-        }
-        encode_pieces(src, m, S.out);
-        if (k > 0) while (phase[(size_t)k - 1].load(std::memory_order_acquire) < 2) std::this_thread::yield();
-        const int64_t o = off[(size_t)k];
-        off[(size_t)k + 1] = o + S.out.nb;
-        phase[(size_t)k].store(2, std::memory_order_release);
-        if (have_out && o + S.out.nb <= cap_blocks) {
-            memcpy(anchors + o, S.out.anchors.data(), (size_t)S.out.nb * 4);
-            memcpy(dstart + o * kP8, S.out.ds.data(), (size_t)S.out.nb * kP8);
-            memcpy(len + o * kP8, S.out.len.data(), (size_t)S.out.nb * kP8);
-        } else if (S.out.nb > 0) fits.store(false);
+        L.resize(m);
+        if (!sorted) sort_nearly_sorted(L.data(), m);
     }, T);
-    *n_blocks = off[(size_t)P];
-    return (fits.load() && have_out) || off[(size_t)P] == 0 ? GL_OK : GL_ERANGE;
+    std::vector<const std::vector<Piece>*> lists((size_t)P);
+    for (int64_t k = 0; k < P; k++) lists[(size_t)k] = &S.lists[(size_t)k];
+    assemble_p8(lists, T, S.a);
+    *n_blocks = S.a.total;
+    if (S.a.total == 0) return GL_OK;
+    if (!(anchors && dstart && len) || S.a.total > cap_blocks) return GL_ERANGE;
+    concat_p8(S.a, T, anchors, dstart, len);
+    return GL_OK;
 }

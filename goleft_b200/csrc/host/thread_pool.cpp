@@ -110,3 +110,6 @@ void ThreadPool::run(int64_t n_tasks, const std::function<void(int64_t, int)>& f
 }
 
 }  // namespace glhost
+
+// size of the library's host pool (creates it on first use: call before narrowing a thread's CPU affinity)
+extern "C" int glhost_pool_size(void) { return glhost::ThreadPool::global().size(); }

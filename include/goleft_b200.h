@@ -210,6 +210,16 @@ int  gl_depth_format_rows(gl_ctx* ctx, const char* chrom, const int32_t* row_s, 
  * callback 238-364 for each of its chunks, concatenated in order): host segments in -> BED bytes out.  step = the chunk
  * length (depth.go:132: a multiple of W).  Short-read input is packed to packed8 on `threads` host threads (0 = all)
  * and streamed up while the first tiles reduce; long segments go up as int32.  Everything is inside the call. */
+/* The same for [region_start, region_end) of a contig: region_start must be a multiple of step (whole chunks), so that
+ * contigs longer than 2^30-1 bases, or one GPU's share of a contig, can be done in pieces whose texts concatenate. */
+int  gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t region_start, int64_t region_end, const int32_t* start, const int32_t* end,
+                         int64_t n, int32_t W, int32_t mincov, int32_t maxmean, int64_t step, int32_t threads,
+                         char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed, int64_t callable_cap,
+                         int64_t* callable_len);
+int  gl_depth_bed_region_packed8(gl_ctx* ctx, const char* chrom, int64_t region_start, int64_t region_end, const int32_t* anchors,
+                                 const uint8_t* dstart, const uint8_t* len, int64_t n_blocks, int32_t W, int32_t mincov, int32_t maxmean,
+                                 int64_t step, char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed,
+                                 int64_t callable_cap, int64_t* callable_len);
 int  gl_depth_bed_contig(gl_ctx* ctx, const char* chrom, int64_t contig_len, const int32_t* start, const int32_t* end, int64_t n,
                          int32_t W, int32_t mincov, int32_t maxmean, int64_t step, int32_t threads,
                          char* depth_bed, int64_t depth_cap, int64_t* depth_len, char* callable_bed, int64_t callable_cap,
@@ -260,6 +270,29 @@ int  gl_segset_n_refs(const gl_segset* s, int32_t* n_refs, int64_t* n_records, i
 int  gl_segset_ref(const gl_segset* s, int32_t tid, const char** name, int64_t* length, const int32_t** start,
                    const int32_t** end, int64_t* n);
 void gl_segset_free(gl_segset* s);
+/* Index-guided parallel feeder: what `samtools depth -r chr:b-e` gives the reference (depth/depth.go:116,152) — only
+ * the BGZF blocks of the requested reference range are read (BAI linear index -> record-aligned virtual offsets); the
+ * range is cut into units at those offsets and every host-pool thread inflates and parses its own units.
+ * gl_bam_open also loads path + ".bai" (or .bam -> .bai); decoding needs that index.
+ * gl_bam_decode: the M/=/X blocks of the records of `tid` that pass the filter and can overlap [beg,end), as
+ *   format 8  : packed8 words  (a0 = int32 anchors[n], a1 = uint8 dstart[64 n], a2 = uint8 len[64 n]; n blocks), or
+ *   format 32 : (a0 = int32 start[n], a1 = int32 end[n]) sorted by start,
+ * want_format 0 chooses (packed8 unless the blocks average more than 400 bases: long reads).  The arrays belong to the
+ * handle and stay valid until its next gl_bam_decode / gl_bam_close; one handle per decoding thread. */
+typedef struct gl_bam gl_bam;
+typedef struct {
+    int32_t format, units, max_len, _pad;
+    int64_t n;
+    const int32_t* a0; const void* a1; const void* a2;
+    int64_t n_records, n_pass, bytes_in, bytes_out;      /* records seen / passing; compressed bytes read / bytes inflated */
+    double inflate_s, parse_s, wall_s;                   /* summed over the workers; wall clock of the call */
+} gl_bam_segments;
+int  gl_bam_open(const char* path, gl_bam** out, char* err, int64_t err_cap);
+void gl_bam_close(gl_bam* b);
+int  gl_bam_info(const gl_bam* b, int32_t* n_refs, int32_t* has_index);
+int  gl_bam_ref(const gl_bam* b, int32_t tid, const char** name, int64_t* length, int64_t* n_mapped /* -1: no stats bin */);
+int  gl_bam_decode(gl_bam* b, int32_t tid, int64_t beg, int64_t end, int32_t min_mapq, int32_t threads, int32_t want_format,
+                   gl_bam_segments* out, char* err, int64_t err_cap);
 /* BAI: per-reference linear index (16 KB tiles) + the 0x924a stats bin (indexcov/types.go:19,45-58),
  * what indexcov takes from biogo's bam.ReadIndex (indexcov/indexcov.go:514). */
 typedef struct gl_bai gl_bai;

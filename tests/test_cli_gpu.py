@@ -11,7 +11,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from bamutil import make_bai, make_bam  # noqa: E402
+from bamutil import make_bai, make_bam, make_bam_indexed  # noqa: E402
 from goleft_b200 import capi  # noqa: E402
 from oracle import loader as orc  # noqa: E402
 
@@ -40,7 +40,7 @@ def test_dispatcher_and_arg_errors():
     assert p.returncode == 255 and "size is required" in p.stderr
 
 
-def _make_bam(tmp_path, seed=0, n=40000):
+def _make_bam(tmp_path, seed=0, n=40000, indexed=True):
     rng = np.random.default_rng(seed)
     refs = [("chrM", 16571), ("chr22", 20001), ("HLA-A*01:01:01:01", 3000)]
     recs, mates = [], []
@@ -58,11 +58,16 @@ def _make_bam(tmp_path, seed=0, n=40000):
     for _ in range(50):
         recs.append((-1, -1, 0, 4, [(100, "M")])); mates.append((-1, 0))
     bam = tmp_path / "s.bam"
-    bam.write_bytes(make_bam(refs, recs, sample="S1", mates=mates))
     fai = tmp_path / "ref.fa.fai"
     fai.write_text("".join("%s\t%d\t6\t60\t61\n" % r for r in refs))
-    n_mapped = [sum(1 for r in recs if r[0] == t) for t in range(len(refs))]
-    (tmp_path / "s.bam.bai").write_bytes(make_bai([[0] for _ in refs], [(n_mapped[t], 0) for t in range(len(refs))]))
+    if indexed:                                       # a real .bai: the CLI seeks with it (samtools depth -r needs one too)
+        bam_b, bai_b = make_bam_indexed(refs, recs, sample="S1", mates=mates)
+        bam.write_bytes(bam_b)
+        (tmp_path / "s.bam.bai").write_bytes(bai_b)
+    else:                                             # linear index absent: stats bin only -> the CLI decodes the whole file
+        bam.write_bytes(make_bam(refs, recs, sample="S1", mates=mates))
+        n_mapped = [sum(1 for r in recs if r[0] == t) for t in range(len(refs))]
+        (tmp_path / "s.bam.bai").write_bytes(make_bai([[0] for _ in refs], [(n_mapped[t], 0) for t in range(len(refs))]))
     return str(bam), str(tmp_path / "ref.fa"), refs, recs, mates
 
 
@@ -82,6 +87,79 @@ def test_depth_fai_mode(tmp_path, W):
             exp_hd += h; exp_ca += c
     assert open(prefix + ".depth.bed", "rb").read() == exp_hd
     assert open(prefix + ".callable.bed", "rb").read() == exp_ca
+
+
+@pytest.mark.gpu
+def test_depth_unindexed_bam_falls_back_to_whole_file_decode(tmp_path):
+    bam, ref, refs, _, _ = _make_bam(tmp_path, seed=4, indexed=False)
+    prefix = str(tmp_path / "u")
+    p = run("depth", "-Q", "1", "-w", "100", "--prefix", prefix, "--reference", ref, bam)
+    assert "decoding the whole file" in p.stderr
+    seg = capi.bam_segments(bam, 1, 2)
+    exp_hd, exp_ca = b"", b""
+    for tid, (name, L) in enumerate(refs):
+        s, e = seg["segments"][tid]
+        h, c = orc.walk_chunk(name, 0, L, 100, 4, 0, orc.pileup_brute(s, e, 0, L))
+        exp_hd += h; exp_ca += c
+    assert open(prefix + ".depth.bed", "rb").read() == exp_hd
+    assert open(prefix + ".callable.bed", "rb").read() == exp_ca
+
+
+@pytest.mark.gpu
+def test_depth_synthetic_bam_index_seek_and_gpus(tmp_path):
+    """a BGZF-realistic BAM (records straddle blocks, every flag/MAPQ class, deletions) + its BAI from the workload generator:
+    the index-guided parallel feeder -> packed8 -> device BED text; -c reads only that contig's blocks; --gpus N output is
+    byte-identical to --gpus 1"""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tools", "synth"))
+    import glsynth
+    contigs = [("chr1", 23_000_000, 1), ("chr2", 4_100_000, 2), ("chrM", 16_569, 24)]
+    bam = str(tmp_path / "synth.bam")
+    glsynth.write_bam(bam, contigs, coverage=6.0)
+    (tmp_path / "g.fa.fai").write_text("".join("%s\t%d\t6\t60\t61\n" % (c[0], c[1]) for c in contigs))
+    ref = str(tmp_path / "g.fa")
+    prefix = str(tmp_path / "s1")
+    p = run("depth", "--gpus", "1", "--timing", "-w", "500", "--prefix", prefix, "-r", ref, bam)
+    t_all = json.loads(p.stderr.strip().splitlines()[-1])["goleft_depth_timing"]
+    exp_hd, exp_ca = b"", b""
+    for name, L, idx in contigs:
+        s, e = glsynth.segments(L, idx, coverage=6.0)
+        o = np.argsort(s, kind="stable")
+        s, e = s[o], e[o]
+        for cs, ce in orc.gen_chunks(L, 500):
+            lo = max(0, int(np.searchsorted(s, cs - 1000)) - 64)
+            hi = int(np.searchsorted(s, ce))
+            h, c = orc.walk_chunk(name, cs, ce, 500, 4, 0, orc.pileup_diff(s[lo:hi], e[lo:hi], cs, ce))
+            exp_hd += h; exp_ca += c
+    assert open(prefix + ".depth.bed", "rb").read() == exp_hd
+    assert open(prefix + ".callable.bed", "rb").read() == exp_ca
+    # -c chrM: only chrM's BGZF blocks are read (samtools depth -r gives the reference that, depth.go:116,152)
+    prefix2 = str(tmp_path / "s2")
+    p = run("depth", "-c", "chrM", "--timing", "-w", "500", "--prefix", prefix2, "-r", ref, bam)
+    t_m = json.loads(p.stderr.strip().splitlines()[-1])["goleft_depth_timing"]
+    assert t_m["bgzf_bytes_in"] < t_all["bgzf_bytes_in"] / 50 and t_m["records"] < 5000
+    sM, eM = glsynth.segments(16_569, 24, coverage=6.0)
+    assert open(prefix2 + ".chrM.depth.bed", "rb").read() == orc.walk_chunk("chrM", 0, 16_569, 500, 4, 0, orc.pileup_diff(sM, eM, 0, 16_569))[0]
+    # every visible GPU: same bytes
+    if capi.device_count() > 1:
+        prefix3 = str(tmp_path / "s3")
+        run("depth", "-w", "500", "--prefix", prefix3, "-r", ref, bam)
+        assert open(prefix3 + ".depth.bed", "rb").read() == exp_hd
+        assert open(prefix3 + ".callable.bed", "rb").read() == exp_ca
+    # BED mode on the indexed BAM: region queries through the linear index
+    bed = tmp_path / "r.bed"
+    regions = [("chr1", 10_000_123, 10_050_456), ("chr2", 5, 900), ("chr1", 22_990_000, 23_000_000), ("chr1", 9_999_000, 10_001_000)]
+    bed.write_text("".join("%s\t%d\t%d\n" % r for r in regions))
+    prefix4 = str(tmp_path / "s4")
+    run("depth", "--bed", str(bed), "-w", "250", "--prefix", prefix4, "-r", ref, bam)
+    segs = {c[0]: glsynth.segments(c[1], c[2], coverage=6.0) for c in contigs}
+    exp_hd, exp_ca = b"", b""
+    for name, rs, re in regions:
+        s, e = segs[name]
+        h, c = orc.walk_chunk(name, rs, re, 250, 4, 0, orc.pileup_diff(s, e, rs, re))
+        exp_hd += h; exp_ca += c
+    assert open(prefix4 + ".depth.bed", "rb").read() == exp_hd
+    assert open(prefix4 + ".callable.bed", "rb").read() == exp_ca
 
 
 @pytest.mark.gpu

@@ -149,3 +149,42 @@ def test_gpu_bed_mode_text(ctx, W):
         exp = orc.walk_chunk(name, rs, re, W, 4, 0, depth)
         ws, r0, rc = ctx.depth_region(rs, re, s, e, W, 4, 0)
         assert capi.format_chunk(name, rs, re, W, ws, r0, rc) == exp
+
+
+def test_indexed_feeder_equals_stream_decoder(tmp_path):
+    """bam_feed (index-guided, parallel units, sorted emission) yields the same M/=/X blocks as the streaming decoder, as
+    packed8 and as sorted int32, on a BGZF-realistic synthetic BAM; region queries return every block that can overlap"""
+    import os, sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(ROOT, "tools", "synth"))
+    import glsynth
+    from goleft_b200 import capi
+    from oracle import loader as orc
+    contigs = [("chrA", 3_000_000, 1), ("chrB", 700_000, 2), ("chrM", 16_569, 24)]
+    bam = str(tmp_path / "t.bam")
+    glsynth.write_bam(bam, contigs, coverage=20.0)
+    old = capi.bam_segments(bam, 1, 4)
+    b = capi.Bam(bam)
+    assert b.has_index and [r[0] for r in b.refs] == [c[0] for c in contigs]
+    for tid, (nm, L, idx) in enumerate(contigs):
+        s, e = glsynth.segments(L, idx, coverage=20.0)
+        gs, ge = old["segments"][tid]
+        assert np.array_equal(gs, s) and np.array_equal(ge, e)                  # the stream decoder's filter == the generator's
+        o = np.lexsort((e, s))
+        for threads in (1, 3, 0):
+            d = b.decode(tid, threads=threads)
+            assert d["format"] == 8 and (np.diff(d["anchors"]) >= 0).all()
+            us, ue = capi.unpack_segments8(d["anchors"], d["dstart"], d["len"])
+            o2 = np.lexsort((ue, us))
+            assert np.array_equal(us[o2], s[o]) and np.array_equal(ue[o2], e[o])
+            d = b.decode(tid, threads=threads, want=32)
+            assert (np.diff(d["start"]) >= 0).all()
+            o3 = np.lexsort((d["end"], d["start"]))
+            assert np.array_equal(d["start"][o3], s[o]) and np.array_equal(d["end"][o3], e[o])
+    s, e = glsynth.segments(3_000_000, 1, coverage=20.0)
+    for rs, re in ((0, 1), (1_000_000, 1_000_001), (1_234_567, 1_300_000), (2_990_000, 3_000_000), (16_383, 16_385)):
+        d = b.decode(0, rs, re, want=32)
+        got = orc.pileup_diff(d["start"], d["end"], rs, re) if d["n"] else np.zeros(re - rs, np.int32)
+        assert np.array_equal(got, orc.pileup_diff(s, e, rs, re))
+        assert d["n_records"] < 400_000 * (re - rs + 40_000) / 3_000_000 + 20_000     # only the region's blocks were parsed
+    b.close()

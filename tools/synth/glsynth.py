@@ -22,12 +22,29 @@ SEED0 = 0x601EF7
 
 def _lib():
     if not os.path.exists(_SO):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", _SO, os.path.join(_HERE, "glsynth.c"), "-lpthread"])
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", _SO, os.path.join(_HERE, "glsynth.c"),
+                               os.path.join(_HERE, "bamsynth.c"), "-lpthread", "-lz"])
     lib = C.CDLL(_SO)
     lib.gls_segments.restype = C.c_int
     lib.gls_segments.argtypes = [C.c_int64, C.c_double, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.gls_write_bam.restype = C.c_int
+    lib.gls_write_bam.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.c_double,
+                                  C.c_int, C.c_int]
     return lib
+
+
+def write_bam(path, contigs, coverage=30.0, read_len=150, threads=0):
+    """contigs = [(name, length, contig_index)] -> path + path.bai holding EVERY read of the recipe (the filter is the
+    decoder's job); segments(length, contig_index) are exactly what `samtools depth -Q 1` would count from it."""
+    lib = _lib()
+    n = len(contigs)
+    names = (C.c_char_p * n)(*[c[0].encode() for c in contigs])
+    lens = (C.c_int64 * n)(*[c[1] for c in contigs])
+    seeds = (C.c_int * n)(*[c[2] for c in contigs])
+    rc = lib.gls_write_bam(path.encode(), n, names, lens, seeds, coverage, read_len, threads or (os.cpu_count() or 1))
+    if rc != 0:
+        raise RuntimeError("gls_write_bam failed")
 
 
 def segments(length, contig_index=0, coverage=30.0, read_len=150, min_mapq=1, gap=True, pileup=True, threads=0, alloc=None):
