@@ -164,7 +164,7 @@ struct DepthJob {                                   // one contig (.fai mode) or
     long long len = 0;                              // .fai mode: contig length
     std::vector<size_t> lines;                      // BED mode: indices into the region list
     std::string hd, ca;                             // .fai mode output
-    double decode_s = 0, gpu_s = 0;
+    double decode_s = 0, gpu_s = 0, inflate_s = 0, parse_s = 0;
     long long records = 0, bytes_in = 0, bytes_out = 0;
     bool done = false;
 };
@@ -224,7 +224,7 @@ struct DepthEngine {
         glhts::DecodeStats st;
         std::string e = bam.decode(it->second, beg, end, o.Q, o.threads, want, segs, &st);
         if (!e.empty()) fatal(1, "%s", e.c_str());
-        if (job) { job->decode_s += st.wall_s; job->records += st.n_records; job->bytes_in += st.bytes_in; job->bytes_out += st.bytes_out; }
+        if (job) { job->decode_s += st.wall_s; job->inflate_s += st.inflate_s; job->parse_s += st.parse_s; job->records += st.n_records; job->bytes_in += st.bytes_in; job->bytes_out += st.bytes_out; }
     }
 
     void add_segments() {
@@ -576,11 +576,12 @@ static int cmd_depth(int argc, char** argv) {
     fclose(fca); fclose(fhd);
     if (sh.fa_map) munmap(const_cast<uint8_t*>(sh.fa_map), sh.fa_len);
     if (timing) {
-        double dec = 0, gpu = 0; long long rec = 0, bin = 0, bout = 0;
-        for (const DepthJob& j : jobs) { dec += j.decode_s; gpu += j.gpu_s; rec += j.records; bin += j.bytes_in; bout += j.bytes_out; }
+        double dec = 0, gpu = 0, inf = 0, par = 0; long long rec = 0, bin = 0, bout = 0;
+        for (const DepthJob& j : jobs) { dec += j.decode_s; gpu += j.gpu_s; inf += j.inflate_s; par += j.parse_s; rec += j.records; bin += j.bytes_in; bout += j.bytes_out; }
         fprintf(stderr, "{\"goleft_depth_timing\": {\"wall_s\": %.4f, \"gpus\": %d, \"jobs\": %zu, \"decode_wall_s_sum\": %.4f, \"gpu_call_s_sum\": %.4f, "
+                        "\"inflate_thread_s_sum\": %.4f, \"parse_thread_s_sum\": %.4f, "
                         "\"records\": %lld, \"bgzf_bytes_in\": %lld, \"bgzf_bytes_out\": %lld, \"host_threads\": %d}}\n",
-                now_s() - t_start, G, jobs.size(), dec, gpu, rec, bin, bout, glhost_pool_size());
+                now_s() - t_start, G, jobs.size(), dec, gpu, inf, par, rec, bin, bout, glhost_pool_size());
     }
     return 0;
 }
