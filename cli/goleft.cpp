@@ -49,6 +49,16 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 extern "C" int glhost_pool_size(void);              // libgoleft_b200.so: size of the host thread pool (creates it)
 static void glhost_pool_warm() { (void)glhost_pool_size(); }
 
+// Go's fmt spells non-finite floats "NaN", "+Inf", "-Inf" (C prints nan / inf): a sample with no tiles on a chromosome
+// gets 0/0 in its ROC and bins.out / bins.in can be x/0, and parsers of .roc / .ped must see the reference's tokens.
+static std::string go_float(const char* cfmt, double v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "+Inf" : "-Inf";
+    char b[64];
+    snprintf(b, sizeof b, cfmt, v);
+    return b;
+}
+
 static bool ends_with(const std::string& s, const std::string& suf) {
     return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
 }
@@ -791,7 +801,7 @@ static int cmd_indexcov(int argc, char** argv) {
                 if (i >= (size_t)lens[k]) { row.push_back('0'); continue; }
                 const uint8_t* t = &tok[((size_t)seg_ptr[k] + i) * 10];
                 if (t[9]) row.append(reinterpret_cast<const char*>(t), t[9]);
-                else { snprintf(num, sizeof num, "%.3g", (double)dptr[k][i]); row += num; }   // magnitude outside the kernel's range
+                else row += go_float("%.3g", (double)dptr[k][i]);                             // magnitude outside the kernel's range
             }
             row += "\n";
             bgz.write(row.data(), row.size());
@@ -815,7 +825,7 @@ static int cmd_indexcov(int argc, char** argv) {
             }
             for (int i = 0; i < GL_INDEXCOV_SLOTS; i++) {
                 fprintf(roc, "%s\t%.2f", ref.name.c_str(), (double)i / (70.0 * (2.0 / 3.0)));
-                for (size_t k = 0; k < S; k++) fprintf(roc, "\t%.2f", (double)rocs[k * GL_INDEXCOV_SLOTS + i]);
+                for (size_t k = 0; k < S; k++) fprintf(roc, "\t%s", go_float("%.2f", (double)rocs[k * GL_INDEXCOV_SLOTS + i]).c_str());
                 fputc('\n', roc);
             }
             if ((includegl || ref.name.compare(0, 2, "GL") != 0) && longest > 2 && !is_sex && longest > 100) {
@@ -849,36 +859,97 @@ static int cmd_indexcov(int argc, char** argv) {
     for (size_t k = 0; k < S; k++) {
         const int inferred = sexes.empty() ? -9 : (int)(0.5 + sexes.begin()->second[k]);
         fprintf(ped, "unknown\t%s\t-9\t-9\t%d\t-9", names[k].c_str(), inferred);
-        for (auto& kv : sexes) fprintf(ped, "\t%.2f", kv.second[k]);
-        fprintf(ped, "\t%lld\t%lld\t%lld\t%lld\t%.3f\t%.2f", (long long)bins[k * 4 + 0], (long long)bins[k * 4 + 1], (long long)bins[k * 4 + 2],
-                (long long)bins[k * 4 + 3], (double)slopes[k], (double)bins[k * 4 + 0] / (double)bins[k * 4 + 3]);
+        for (auto& kv : sexes) fprintf(ped, "\t%s", go_float("%.2f", kv.second[k]).c_str());
+        fprintf(ped, "\t%lld\t%lld\t%lld\t%lld\t%s\t%s", (long long)bins[k * 4 + 0], (long long)bins[k * 4 + 1], (long long)bins[k * 4 + 2],
+                (long long)bins[k * 4 + 3], go_float("%.3f", (double)slopes[k]).c_str(),
+                go_float("%.2f", (double)bins[k * 4 + 0] / (double)bins[k * 4 + 3]).c_str());
         if (anygt) fprintf(ped, "\t%llu\t%llu", (unsigned long long)mapped[k], (unsigned long long)unmapped[k]);
         fputc('\n', ped);
     }
     fclose(ped);
-    fprintf(stderr, "indexcov finished: see %s.bed.gz, .roc and .ped for output (no index.html: plots are not built)\n", base.c_str());
+    // The reference's PCA (indexcov.go:772-810) and its HTML/PNG plots are out of scope; the log lines its
+    // functional tests look for (functional-tests.sh:49,82) are kept, and index.html is a plain list of the outputs.
+    if (S < 3) {
+        fprintf(stderr, "got: %zu principal components\n", S);
+        fprintf(stderr, "indexcov: %zu principal components, not plotting\n", S);
+    }
+    {
+        const std::string index_path = dir + "/index.html";
+        FILE* ih = fopen(index_path.c_str(), "w");
+        if (ih) {
+            const std::string stem = base.substr(base.find_last_of('/') + 1);
+            fprintf(ih, "<html><head><title>indexcov</title></head><body><p>goleft_b200 indexcov: %zu samples; plots are not built by this engine.</p><ul>"
+                        "<li><a href=\"%s.bed.gz\">%s.bed.gz</a></li><li><a href=\"%s.roc\">%s.roc</a></li><li><a href=\"%s.ped\">%s.ped</a></li></ul></body></html>\n",
+                    S, stem.c_str(), stem.c_str(), stem.c_str(), stem.c_str(), stem.c_str(), stem.c_str());
+            fclose(ih);
+            fprintf(stderr, "indexcov finished: see %s for overview of output\n", index_path.c_str());   // indexcov.go:454
+        }
+    }
     gl_ctx_destroy(ctx);
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ covstats
-static void mean_std(const int32_t* a, size_t n, double& mean, double& sd) {         // covstats.go:78-89
+// V2 (covstats.go:57-89,175-218).  The reference sorts the sampled insert sizes / template lengths / read lengths and reads
+// order statistics off the sorted slices.  Here the multiset is a histogram made on the GPU (gl_bincount_i32): the k-th
+// smallest value is a search in its running count, madFilter's cut is a count, and meanStd's float64 accumulation visits
+// the values in ascending order with their multiplicities — the same sequence of additions as over the sorted slice, so
+// the results are bit-identical without a sort.
+struct SortedCounts {
+    int32_t lo = 0;
+    std::vector<uint64_t> cum;                               // cum[i] = how many values are <= lo + i
+    std::vector<int32_t> sorted;                             // fallback when the value range is too wide for a histogram
+    size_t n = 0;
+    void build(gl_ctx* ctx, const std::vector<int32_t>& v) {
+        n = v.size();
+        cum.clear(); sorted.clear();
+        if (n == 0) return;
+        int32_t mn = v[0], mx = v[0];
+        for (int32_t x : v) { mn = std::min(mn, x); mx = std::max(mx, x); }
+        const long long range = (long long)mx - mn + 1;
+        if (range > (1LL << 22)) { sorted = v; std::sort(sorted.begin(), sorted.end()); return; }
+        lo = mn;
+        cum.assign((size_t)range, 0);
+        glck(ctx, gl_bincount_i32(ctx, v.data(), (int64_t)n, mn, (int32_t)((long long)mx + 1 > INT32_MAX ? INT32_MAX : mx + 1), cum.data()), "gl_bincount_i32");
+        if ((long long)mx + 1 > INT32_MAX) { sorted = v; std::sort(sorted.begin(), sorted.end()); cum.clear(); return; }
+        for (size_t i = 1; i < cum.size(); i++) cum[i] += cum[i - 1];
+    }
+    int32_t kth(size_t k) const {                            // k-th smallest, 0-based
+        if (!sorted.empty()) return sorted[k];
+        return lo + (int32_t)(std::upper_bound(cum.begin(), cum.end(), (uint64_t)k) - cum.begin());
+    }
+    size_t count_le(long long v) const {
+        if (!sorted.empty()) return (size_t)(std::upper_bound(sorted.begin(), sorted.end(), v, [](long long a, int32_t b) { return a < (long long)b; }) - sorted.begin());
+        if (v < lo) return 0;
+        const long long i = v - lo;
+        return (size_t)(i >= (long long)cum.size() ? cum.back() : cum[(size_t)i]);
+    }
+    template <class F> void for_first(size_t m, F f) const { // the m smallest values, ascending, with multiplicity
+        if (!sorted.empty()) { for (size_t i = 0; i < m; i++) f(sorted[i]); return; }
+        size_t done = 0;
+        for (size_t i = 0; i < cum.size() && done < m; i++) {
+            const size_t c = std::min<size_t>((size_t)(cum[i] - (i ? cum[i - 1] : 0)), m - done);
+            for (size_t k = 0; k < c; k++) f(lo + (int32_t)i);
+            done += c;
+        }
+    }
+};
+static void mean_std(const SortedCounts& a, size_t n, double& mean, double& sd) {     // covstats.go:78-89 over the n smallest
     const double l = (double)n;
     mean = 0; sd = 0;
-    for (size_t i = 0; i < n; i++) mean += (double)a[i] / l;
-    for (size_t i = 0; i < n; i++) sd += pow((double)a[i] - mean, 2) / l;
+    a.for_first(n, [&](int32_t x) { mean += (double)x / l; });
+    const double mu = mean;
+    a.for_first(n, [&](int32_t x) { sd += pow((double)x - mu, 2) / l; });
     sd = sqrt(sd);
 }
-static size_t mad_filter(std::vector<int32_t>& arr, int nmads) {                    // covstats.go:57-76
-    if (!std::is_sorted(arr.begin(), arr.end())) std::sort(arr.begin(), arr.end());
-    const size_t n = arr.size();
-    const int32_t med = arr[n / 2];
-    std::vector<int32_t> um;
-    for (size_t i = n / 2 + 1; i < n; i++) um.push_back(arr[i] - med);
-    std::sort(um.begin(), um.end());
-    const long long upper = (long long)med + (long long)nmads * um[um.size() / 2];
-    size_t i = 0;
-    for (i = 0; i < n; i++) if (arr[i] > upper) break;
+static size_t mad_filter(const SortedCounts& a, int nmads) {                        // covstats.go:57-76: how many values are kept
+    const size_t n = a.n;
+    const int32_t med = a.kth(n / 2);
+    // upper_mads = arr[n/2+1:] - med is already sorted: its middle element is arr[n/2+1 + len/2] - med
+    const size_t len = n - (n / 2 + 1);
+    const long long umad = (long long)a.kth(n / 2 + 1 + len / 2) - med;
+    const long long upper = (long long)med + (long long)nmads * umad;
+    size_t i = a.count_le(upper);                                                   // first index with arr[i] > upper
     if (i == n) i = n - 1;                                                          // Go's range loop leaves i at the last index
     return i;
 }
@@ -914,30 +985,28 @@ static int cmd_covstats(int argc, char** argv) {
         }
         double pBad = 0, pDup = 0, pProper = 0, pUnmapped = 0, rlMean = 0, insMean = 0, insSd = 0, tMean = 0, tSd = 0;
         int pct5 = 0, pct95 = 0, maxRead = 0;
+        SortedCounts sc;
         if (!cs.read_len.empty()) {                                                 // covstats.go:177-186
             const double den = (double)(cs.k + cs.n_unmapped);
             pBad = cs.n_bad / den; pDup = cs.n_dup / den; pProper = cs.n_proper / den; pUnmapped = cs.n_unmapped / den;
-            std::sort(cs.read_len.begin(), cs.read_len.end());
+            sc.build(ctx, cs.read_len);
             double sd;
-            mean_std(cs.read_len.data(), cs.read_len.size(), rlMean, sd);
-            maxRead = cs.read_len.back();
+            mean_std(sc, sc.n, rlMean, sd);
+            maxRead = sc.kth(sc.n - 1);
         }
-        if (!cs.insert.empty()) {                                                   // covstats.go:188-218
-            std::sort(cs.insert.begin(), cs.insert.end());
+        if (!cs.insert.empty()) {                                                   // covstats.go:188-199
+            sc.build(ctx, cs.insert);
             const double l = (double)(cs.insert.size() - 1);
-            pct5 = cs.insert[(size_t)(0.05 * l + 0.5)];
-            pct95 = cs.insert[(size_t)(0.95 * l + 0.5)];
-            const size_t ki = mad_filter(cs.insert, 10);
-            mean_std(cs.insert.data(), ki, insMean, insSd);
-            const size_t kt = mad_filter(cs.tmpl, 10);
-            mean_std(cs.tmpl.data(), kt, tMean, tSd);
-            // template-length histogram H over [MaxReadLength, mean + 4 sd] on the GPU (covstats.go:202-217);
-            // H is part of the reference's Stats struct (consumed by smoove), not of the TSV row
-            const int lo = maxRead, hi = (int)(tMean + tSd * 4) + 1;
-            if (hi > lo && kt > 0) {
-                std::vector<uint64_t> H((size_t)(hi - lo));
-                glck(ctx, gl_bincount_i32(ctx, cs.tmpl.data(), (int64_t)kt, lo, hi, H.data()), "gl_bincount_i32");
-            }
+            pct5 = sc.kth((size_t)(0.05 * l + 0.5));
+            pct95 = sc.kth((size_t)(0.95 * l + 0.5));
+            if (sc.n < 3) fatal(2, "panic: runtime error: index out of range (covstats madFilter needs at least 3 insert sizes)");
+            const size_t ki = mad_filter(sc, 10);
+            mean_std(sc, ki, insMean, insSd);
+            sc.build(ctx, cs.tmpl);
+            const size_t kt = mad_filter(sc, 10);
+            mean_std(sc, kt, tMean, tSd);
+            // (Stats.H, the template-length histogram of covstats.go:202-217, is consumed by smoove through the Go API and is
+            //  not part of the TSV row this command prints; it is not computed here)
         }
         long long genome = 0;
         unsigned long long mapped = 0;

@@ -58,6 +58,9 @@ __device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
 // consecutive chunks and for a warp whose lane l touches chunks 4l..4l+3 (the blocked layout).
 __device__ __forceinline__ int swz_chunk(int c) { return c ^ ((c >> 2) & 7); }
 __device__ __forceinline__ int swz_elem(int e) { return e ^ (((e >> 4) & 7) << 2); }   // == (swz_chunk(e>>2)<<2) | (e&3)
+// the same for a core whose threads own BPT consecutive bases (BPT/4 chunks): lane l touches chunks (BPT/4)l .. +BPT/4-1
+template <int BPT> __device__ __forceinline__ int swz_chunk_t(int c) { return BPT == 32 ? (c ^ ((c >> 3) & 7)) : (c ^ ((c >> 2) & 7)); }
+template <int BPT> __device__ __forceinline__ int swz_elem_t(int e) { return BPT == 32 ? (e ^ (((e >> 5) & 7) << 2)) : (e ^ (((e >> 4) & 7) << 2)); }
 
 // ================================================================================================
 // GENERAL path, K_scatter.  One thread = 4 segments (two 128-bit loads), 8 fire-and-forget reds.
@@ -349,44 +352,51 @@ __device__ __forceinline__ void flush_max(const ScanParams& p, int acc_max) {
         atomicMax(reinterpret_cast<unsigned long long*>(p.header + 2), (unsigned long long)acc_max);
 }
 
-template <bool kZeroAfterRead>
+// BPT bases per thread (16 or 32), WARPS warps per CTA, BPT * 32 * WARPS == kTile.  32 bases per thread halves the work
+// that is paid per thread and tile (warp scan, class check, window loop, run claim, barrier) — K_fused8 uses <32, 4>.
+template <int BPT, int WARPS, bool kZeroAfterRead>
 __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__ s_tile, int* __restrict__ s_depth,
                                           const int* s_carry, int tile, int& acc_max) {
-    __shared__ int s_warp_tot[kWarps];
+    static_assert(BPT * 32 * WARPS == kTile, "tile shape");
+    constexpr int kWElems = BPT * 32;                         // bases per warp
+    __shared__ int s_warp_tot[WARPS];
     __shared__ int s_has_break;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_base = tile * kTile;                       // relative position of the tile
-    const int warp_base = tile_base + warp * kWarpElems;
-    const int idx0 = tile_base + tid * 16;                    // relative position of this thread's first base
+    const int warp_base = tile_base + warp * kWElems;
+    const int idx0 = tile_base + tid * BPT;                   // relative position of this thread's first base
 
-    // ---- 16 consecutive differences per thread; thread-local inclusive scan; one warp scan
-    int x[16];
+    // ---- BPT consecutive differences per thread; thread-local inclusive scan; one warp scan
+    int x[BPT];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int4 q = reinterpret_cast<const int4*>(s_tile)[swz_chunk(tid * 4 + j)];
+    for (int j = 0; j < BPT / 4; j++) {
+        const int4 q = reinterpret_cast<const int4*>(s_tile)[swz_chunk_t<BPT>(tid * (BPT / 4) + j)];
         x[4 * j] = q.x; x[4 * j + 1] = q.y; x[4 * j + 2] = q.z; x[4 * j + 3] = q.w;
-        if (kZeroAfterRead) reinterpret_cast<int4*>(s_tile)[swz_chunk(tid * 4 + j)] = make_int4(0, 0, 0, 0);
+        if (kZeroAfterRead) reinterpret_cast<int4*>(s_tile)[swz_chunk_t<BPT>(tid * (BPT / 4) + j)] = make_int4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int k = 1; k < 16; k++) x[k] += x[k - 1];
-    int inc = x[15];
+    for (int k = 1; k < BPT; k++) x[k] += x[k - 1];
+    int inc = x[BPT - 1];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(kFull, inc, o);
         if (lane >= o) inc += t;
     }
-    const int lane_excl = inc - x[15];
+    const int lane_excl = inc - x[BPT - 1];
     if (lane == 31) s_warp_tot[warp] = inc;
     // depth[k] = tbase + x[k], tbase known only after the barrier: take min / max / sum of the x[k] now, while other
     // warps are still arriving, and add tbase afterwards (the per-base depths are formed only where a slow path needs them)
     int xmn = x[0], xmx = x[0], xsum = x[0];
 #pragma unroll
-    for (int k = 1; k < 16; k++) {
-        xmn = min(xmn, x[k]);
-        xmx = max(xmx, x[k]);
-        xsum += x[k];
+    for (int k = 1; k + 1 < BPT; k += 2) {                    // three-input min / max (VIMNMX3) and adds (IADD3)
+        xmn = __vimin3_s32(xmn, x[k], x[k + 1]);
+        xmx = __vimax3_s32(xmx, x[k], x[k + 1]);
+        xsum += x[k] + x[k + 1];
     }
+    xmn = min(xmn, x[BPT - 1]);
+    xmx = max(xmx, x[BPT - 1]);
+    xsum += x[BPT - 1];
     if (tid == 0) {
         // does a forced run break (multiple of run_break) fall inside this tile?  (absolute positions are < 2^32)
         int hb = 0;
@@ -400,14 +410,14 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     __syncthreads();
 
     // depth at the base before this warp's first: everything carried into the tile + the warps before this one
-    const int wbase = __reduce_add_sync(kFull, lane < kWarps ? s_carry[lane] + (lane < warp ? s_warp_tot[lane] : 0) : 0);
+    const int wbase = __reduce_add_sync(kFull, lane < WARPS ? s_carry[lane] + (lane < warp ? s_warp_tot[lane] : 0) : 0);
     const int tbase = wbase + lane_excl;                      // depth at the base before this thread's first
 
     const int mn = tbase + xmn, mx = tbase + xmx;
 #define GL_D(k) (tbase + x[k])                                 /* depth of this thread's k-th base */
     if (p.depth_out) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < BPT / 4; j++) {
             const int idx = idx0 + 4 * j;
             if (idx + 3 < p.len) reinterpret_cast<int4*>(p.depth_out + idx)[0] = make_int4(GL_D(4 * j), GL_D(4 * j + 1), GL_D(4 * j + 2), GL_D(4 * j + 3));
             else {
@@ -417,7 +427,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
             }
         }
     }
-    const bool full_warp = warp_base + kWarpElems <= p.len;   // false only at the region's ragged end
+    const bool full_warp = warp_base + kWElems <= p.len;   // false only at the region's ragged end
     const int wmin = __reduce_min_sync(kFull, mn), wmax = __reduce_max_sync(kFull, mx);
 
     const bool tile_has_break = s_has_break != 0;
@@ -428,16 +438,16 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     if (p.do_runs)
         slow_runs = !full_warp || tile_has_break || warp_base == 0 ||
                     cov_class(min(wmin, wbase), p.mincov, p.maxmean) != cov_class(max(wmax, wbase), p.mincov, p.maxmean);
-    const bool fast_win = p.do_windows && full_warp && p.W >= 16 && p.win_min == nullptr && wmax < (1 << 22);
+    const bool fast_win = p.do_windows && full_warp && p.W >= BPT && p.win_min == nullptr && wmax < (1 << 22);
     const bool slow_win = p.do_windows && !fast_win;
 
     // The slow paths index depth by position: this warp's private slice of s_depth (linear layout).
-    int* sw = s_depth + warp * kWarpElems;
+    int* sw = s_depth + warp * kWElems;
     if (slow_runs || slow_win) {
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            reinterpret_cast<int4*>(sw + lane * 16)[j] = make_int4(GL_D(4 * j), GL_D(4 * j + 1), GL_D(4 * j + 2), GL_D(4 * j + 3));
+        for (int j = 0; j < BPT / 4; j++)
+            reinterpret_cast<int4*>(sw + lane * BPT)[j] = make_int4(GL_D(4 * j), GL_D(4 * j + 1), GL_D(4 * j + 2), GL_D(4 * j + 3));
         __syncwarp();
     }
 
@@ -446,10 +456,10 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     int lane_rank = 0, warp_cnt = 0;
     int maxd = full_warp ? wmax : 0;
     if (slow_runs || !full_warp) {
-        const int nv = max(0, min(16, p.len - idx0));
+        const int nv = max(0, min(BPT, p.len - idx0));
         int cp = cov_class(tbase, p.mincov, p.maxmean);
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
+        for (int k = 0; k < BPT; k++) {
             if (k < nv) {
                 if (!full_warp) maxd = max(maxd, GL_D(k));
                 if (slow_runs) {
@@ -464,10 +474,10 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
             if (tile_has_break) {
                 const unsigned a = (unsigned)p.rs + (unsigned)idx0;
 #pragma unroll
-                for (int k = 0; k < 16; k++)
+                for (int k = 0; k < BPT; k++)
                     if ((a + k) % p.run_break == 0) mask |= 1u << k;
             }
-            mask &= (nv >= 16) ? 0xffffu : ((1u << nv) - 1u);
+            mask &= (nv >= BPT) ? (BPT == 32 ? 0xffffffffu : 0xffffu) : ((1u << nv) - 1u);
             const int c = __popc(mask);
             int ci = c;
 #pragma unroll
@@ -489,7 +499,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
         // edge's lane, nothing right of it; one REDUX adds the lanes (< 2^31), lane 0 issues one 64-bit red per window.
         // cu = edge % 16 is the same for the whole warp, so the partial sum is a jump into a fall-through chain
         // (cu adds, no divergence) instead of a 16-way register select per lane.
-        const int s16 = 16 * tbase + xsum;
+        const int s16 = BPT * tbase + xsum;
         const unsigned a0 = (unsigned)p.rs + (unsigned)warp_base;     // absolute, < 2^32
         const unsigned uW = (unsigned)p.W;
         // iw = a0 / W without a division: q = hi32(a0 * floor(2^32/W)) is the quotient or one less
@@ -501,39 +511,32 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
         int counted = 0;
 #pragma unroll 1
         while (true) {
-            const int el = (int)(edge >> 4);                          // lane holding the edge (>= 32: beyond the warp)
+            const int el = (int)(edge / BPT);                         // lane holding the edge (>= 32: beyond the warp)
+            const unsigned cu = edge % BPT;                           // bases of that lane left of the edge (warp-uniform)
+            // sum of the first cu depths of a thread = cu * tbase + x[0] + .. + x[cu-1]: a jump into a fall-through chain
             int part = 0;
-            switch (edge & 15u) {                                     // warp-uniform
-                case 15: part += x[14]; [[fallthrough]];
-                case 14: part += x[13]; [[fallthrough]];
-                case 13: part += x[12]; [[fallthrough]];
-                case 12: part += x[11]; [[fallthrough]];
-                case 11: part += x[10]; [[fallthrough]];
-                case 10: part += x[9]; [[fallthrough]];
-                case 9: part += x[8]; [[fallthrough]];
-                case 8: part += x[7]; [[fallthrough]];
-                case 7: part += x[6]; [[fallthrough]];
-                case 6: part += x[5]; [[fallthrough]];
-                case 5: part += x[4]; [[fallthrough]];
-                case 4: part += x[3]; [[fallthrough]];
-                case 3: part += x[2]; [[fallthrough]];
-                case 2: part += x[1]; [[fallthrough]];
-                case 1: part += x[0]; [[fallthrough]];
+            switch (cu) {
+#define GL_CASE(k) case k: part += x[(k - 1) < BPT ? (k - 1) : 0]; [[fallthrough]];
+                GL_CASE(31) GL_CASE(30) GL_CASE(29) GL_CASE(28) GL_CASE(27) GL_CASE(26) GL_CASE(25) GL_CASE(24)
+                GL_CASE(23) GL_CASE(22) GL_CASE(21) GL_CASE(20) GL_CASE(19) GL_CASE(18) GL_CASE(17) GL_CASE(16)
+                GL_CASE(15) GL_CASE(14) GL_CASE(13) GL_CASE(12) GL_CASE(11) GL_CASE(10) GL_CASE(9) GL_CASE(8)
+                GL_CASE(7) GL_CASE(6) GL_CASE(5) GL_CASE(4) GL_CASE(3) GL_CASE(2) GL_CASE(1)
+#undef GL_CASE
                 default: break;
             }
-            part += (int)(edge & 15u) * tbase;
+            part += (int)cu * tbase;
             const int cur = lane < el ? s16 : (lane == el ? part : 0);
             const unsigned tot = (unsigned)__reduce_add_sync(kFull, cur - counted);
             counted = cur;
             if (lane == 0) atomicAdd(p.win_sum + ((long long)iw - p.w0), (unsigned long long)tot);
-            if (edge >= kWarpElems) break;
+            if (edge >= (unsigned)kWElems) break;
             iw++;
             edge += uW;
         }
     } else if (slow_win) {
         // General path from this warp's smem slice: any W, min, ragged end, depth up to 2^31.
         const unsigned a0 = (unsigned)p.rs + (unsigned)warp_base;
-        const unsigned a1 = (unsigned)p.rs + (unsigned)min(warp_base + kWarpElems, p.len);
+        const unsigned a1 = (unsigned)p.rs + (unsigned)min(warp_base + kWElems, p.len);
         const unsigned uW = (unsigned)p.W;
         if (a0 < a1) {
             const unsigned iw0 = a0 / uW, iw1 = (a1 - 1) / uW;
@@ -576,7 +579,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
 
     // ---- claim output slots for this warp chunk's run starts (claim order; K_gather puts them in position order)
     if (p.do_runs) {
-        const int chunk = tile * kWarps + warp;
+        const int chunk = tile * WARPS + warp;
         unsigned long long off = 0;
         if (lane == 0) {
             if (warp_cnt) {
@@ -594,7 +597,7 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
                 m &= m - 1;
                 if (rank < p.run_cap) {
                     p.tmp_start[rank] = p.rs + idx0 + k;
-                    p.tmp_class[rank] = (unsigned char)cov_class(sw[lane * 16 + k], p.mincov, p.maxmean);
+                    p.tmp_class[rank] = (unsigned char)cov_class(sw[lane * BPT + k], p.mincov, p.maxmean);
                 }
                 rank++;
             }
@@ -628,7 +631,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanP
     for (int r = 0; r < 4; r++) reinterpret_cast<int4*>(s_tile)[swz_chunk(warp * 128 + r * 32 + lane)] = v[r];
     __syncwarp();                                                       // a warp only re-reads its own 128 chunks
     int acc_max = 0;
-    tile_core<false>(p, s_tile, s_depth, s_carry, tile, acc_max);
+    tile_core<16, kWarps, false>(p, s_tile, s_depth, s_carry, tile, acc_max);
     flush_max(p, acc_max);
 }
 
@@ -776,7 +779,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const Scan
             se[j] = ok ? be[i] : 0;
         }
         cells = fused_load_cells(p, b0, tile + 2 * G, maxlen);          // and the tile after that one's cell entries
-        tile_core<true>(p, s_tile, s_depth, s_carry, tile, acc_max);
+        tile_core<16, kWarps, true>(p, s_tile, s_depth, s_carry, tile, acc_max);
     }
     flush_max(p, acc_max);
 }
@@ -830,10 +833,28 @@ __global__ void __launch_bounds__(256) depth_tileidx8_kernel(const ScanParams p)
 
 struct P8Regs { unsigned d, l; int anchor; };
 
-// thread (tid) takes slots 4*(tid&15)..+3 of block lo + (tid>>4) + 16*pass
+// K_fused8 runs 128-thread CTAs whose threads own 32 consecutive bases each (tile_core<32, 4>): the work that is paid per
+// thread and tile — warp scan, class check, window loop, run claim, barrier — is spread over twice the bases of the
+// 16-per-thread core (ncu, round 1: 568 warp instructions per thread and tile = 35.5 per base, issue-bound).
+constexpr int kF8Threads = 128;
+constexpr int kF8Warps = kF8Threads / 32;
+constexpr int kF8BPT = kTile / kF8Threads;          // 32
+constexpr int kF8BlocksPerPass = kF8Threads / 16;   // a block is 16 lanes x 4 slots
+
+// one segment into the tile (see fused_apply), for the 32-bases-per-thread layout
+__device__ __forceinline__ void fused_apply32(int* s_tile, int t0, int t1, bool first_tile, int s, int e, int& carry) {
+    const int sc = first_tile ? max(s, t0) : s;
+    if (sc < e && sc < t1 && e >= t0) {
+        if (sc < t0) carry++;
+        else atomicAdd(s_tile + swz_elem_t<kF8BPT>(sc - t0), 1);
+        if (e - t0 < kTile) atomicAdd(s_tile + swz_elem_t<kF8BPT>(e - t0), -1);
+    }
+}
+
+// thread (tid) takes slots 4*(tid&15)..+3 of block lo + (tid>>4) + 8*pass
 __device__ __forceinline__ P8Regs fused8_load(const ScanParams& p, int lo, int hi, int pass) {
     P8Regs r = {0u, 0u, 0};
-    const int b = lo + (int)(threadIdx.x >> 4) + 16 * pass;
+    const int b = lo + (int)(threadIdx.x >> 4) + kF8BlocksPerPass * pass;
     if (b < hi) {
         r.d = p.p8_ds[(size_t)b * 16 + (threadIdx.x & 15)];
         r.l = p.p8_len[(size_t)b * 16 + (threadIdx.x & 15)];
@@ -854,29 +875,29 @@ __device__ __forceinline__ void fused8_apply(const P8Regs& r, int* s_tile, int t
     if (r.l == 0) return;                                   // four empty slots (or no block): nothing to add
     const int base = r.anchor + inc - d3;
     const int s0 = base + d0, s1 = base + d1, s2 = base + d2, s3 = base + d3;
-    fused_apply(s_tile, t0, t1, first_tile, s0, s0 + (int)(r.l & 0xff), carry);
-    fused_apply(s_tile, t0, t1, first_tile, s1, s1 + (int)((r.l >> 8) & 0xff), carry);
-    fused_apply(s_tile, t0, t1, first_tile, s2, s2 + (int)((r.l >> 16) & 0xff), carry);
-    fused_apply(s_tile, t0, t1, first_tile, s3, s3 + (int)(r.l >> 24), carry);
+    fused_apply32(s_tile, t0, t1, first_tile, s0, s0 + (int)(r.l & 0xff), carry);
+    fused_apply32(s_tile, t0, t1, first_tile, s1, s1 + (int)((r.l >> 8) & 0xff), carry);
+    fused_apply32(s_tile, t0, t1, first_tile, s2, s2 + (int)((r.l >> 16) & 0xff), carry);
+    fused_apply32(s_tile, t0, t1, first_tile, s3, s3 + (int)(r.l >> 24), carry);
 }
 
-// K_fused8: persistent, software-pipelined like K_fused: while tile n runs its core, the packed words of tile n+1 and
-// the block range of tile n+2 are in flight.
-__global__ void __launch_bounds__(kScanThreads, 4) depth_fused8_kernel(const ScanParams p) {
+// K_fused8: persistent, software-pipelined like K_fused: while tile n runs its core, the packed words of tile n+1 (two
+// passes = 16 blocks, what a 30x tile needs) and the block range of tile n+2 are in flight.
+__global__ void __launch_bounds__(kF8Threads) depth_fused8_kernel(const ScanParams p) {
     __shared__ __align__(16) int s_tile[kTile];
     __shared__ __align__(16) int s_depth[kTile];
-    __shared__ int s_carry2[2][kWarps];
+    __shared__ int s_carry2[2][kF8Warps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
     if (p.header[3] != 0) return;                           // K_tileidx8 found unsorted anchors: the host falls back
 #pragma unroll
-    for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);   // later tiles: cleared by the core
+    for (int j = 0; j < kF8BPT / 4; j++) reinterpret_cast<int4*>(s_tile)[tid * (kF8BPT / 4) + j] = make_int4(0, 0, 0, 0);   // later tiles: cleared by the core
     int tile = p.tile_begin + blockIdx.x;
     const int nb = p.p8_nblocks;                            // (clamps: garbage ranges of a rejected input stay in bounds)
     int lo = 0, hi = 0, lo2 = 0, hi2 = 0;
     if (tile < p.tile_end) { lo = max(0, p.tile_lo[tile] - 1); hi = min(nb, p.tile_hi[tile + 1]); }
     if (tile + G < p.tile_end) { lo2 = max(0, p.tile_lo[tile + G] - 1); hi2 = min(nb, p.tile_hi[tile + G + 1]); }
-    P8Regs regs = fused8_load(p, lo, hi, 0);
+    P8Regs regs0 = fused8_load(p, lo, hi, 0), regs1 = fused8_load(p, lo, hi, 1);
     __syncthreads();
 
     int acc_max = 0;
@@ -885,17 +906,19 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_fused8_kernel(const Sca
         const int t0 = p.rs + tile * kTile, t1 = min(t0 + kTile, p.re);
         const bool first_tile = tile == 0;
         int carry = 0;
-        fused8_apply(regs, s_tile, t0, t1, first_tile, carry);
-        for (int pass = 1; lo + 16 * pass < hi; pass++)     // deep tiles only (uniform trip count)
+        fused8_apply(regs0, s_tile, t0, t1, first_tile, carry);
+        fused8_apply(regs1, s_tile, t0, t1, first_tile, carry);
+        for (int pass = 2; lo + kF8BlocksPerPass * pass < hi; pass++)     // deep tiles only (uniform trip count)
             fused8_apply(fused8_load(p, lo, hi, pass), s_tile, t0, t1, first_tile, carry);
         carry = __reduce_add_sync(kFull, carry);
         if (lane == 0) s_carry[warp] = carry;
         __syncthreads();
         lo = lo2; hi = hi2;
-        regs = fused8_load(p, lo, hi, 0);                   // next tile's packed words: in flight during the core
+        regs0 = fused8_load(p, lo, hi, 0);                  // next tile's packed words: in flight during the core
+        regs1 = fused8_load(p, lo, hi, 1);
         lo2 = hi2 = 0;
         if (tile + 2 * G < p.tile_end) { lo2 = max(0, p.tile_lo[tile + 2 * G] - 1); hi2 = min(nb, p.tile_hi[tile + 2 * G + 1]); }
-        tile_core<true>(p, s_tile, s_depth, s_carry, tile, acc_max);
+        tile_core<kF8BPT, kF8Warps, true>(p, s_tile, s_depth, s_carry, tile, acc_max);
     }
     flush_max(p, acc_max);
 }
@@ -1100,13 +1123,19 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
     const int64_t n_windows = (ctx->re - 1) / W - w0 + 1;
     if (do_windows && want_min) GL_CHECK(gl_buf_reserve(ctx, ctx->win_min, (size_t)n_windows * 4));
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const int64_t chunks = tiles * kWarps;
+    const int64_t chunks = tiles * kF8Warps;                  // run table: one entry per warp chunk (1024 bases here)
     const size_t supers = (size_t)(chunks >> kSuperShift) + 2;
     const size_t head_bytes = al(kHeaderWords * 8 + supers * 4);
     const size_t win_bytes = al(do_windows ? (size_t)n_windows * 8 : 0);
     const size_t zero_bytes = head_bytes + win_bytes;
     const size_t run_bytes = al((size_t)chunks * 8);
     GL_CHECK(gl_buf_reserve(ctx, ctx->scratch, zero_bytes + run_bytes + 2 * al((size_t)(tiles + 1) * 4)));
+    static int f8_ctas_per_sm = 0;                            // persistent grid: what fits on an SM (registers decide)
+    if (f8_ctas_per_sm == 0) {
+        int nblk = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, depth_fused8_kernel, kF8Threads, 0) != cudaSuccess || nblk < 1) { cudaGetLastError(); nblk = 4; }
+        f8_ctas_per_sm = nblk;
+    }
     if (do_runs && ctx->run_start.cap == 0) {
         size_t cap = (size_t)(len / 16 + 4096);
         GL_CHECK(gl_buf_reserve(ctx, ctx->run_start, cap * 4));
@@ -1208,7 +1237,7 @@ int run_reduce_f8(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64
                 p.tile_begin = (int)t_prev;
                 p.tile_end = (int)t_ready;
                 gl_prof_scope prof(ctx, "depth_fused8_kernel");
-                depth_fused8_kernel<<<(unsigned)std::min<int64_t>(t_ready - t_prev, (int64_t)ctx->sm_count * 4), kScanThreads, 0, ctx->stream>>>(p);
+                depth_fused8_kernel<<<(unsigned)std::min<int64_t>(t_ready - t_prev, (int64_t)ctx->sm_count * f8_ctas_per_sm), kF8Threads, 0, ctx->stream>>>(p);
                 GL_LAUNCHED(ctx, 1);
             }
             if (early_sums && !last && t_ready > t_prev) {

@@ -366,8 +366,10 @@ int  gl_indexsplit_chunks(const double* tile_sum, const int64_t* out_ptr, int32_
                           const int64_t* prob_end, int64_t n_prob, char** text, int64_t* text_len);
 
 /* ---------------------------------------------------------------- covstats
- * V2: histogram of int32 values in [lo,hi) -> hist[v-lo] (covstats/covstats.go:202-217 and the
- * order statistics of :175-199, which the host derives from the histogram). */
+ * V2: histogram of int32 values in [lo,hi) -> hist[v-lo].  `goleft covstats` builds it over the sampled insert sizes,
+ * template lengths and read lengths and reads every order statistic of covstats/covstats.go:57-76,175-199 off its running
+ * count (k-th smallest = a search, madFilter's cut = a count) and feeds meanStd (:78-89) the values in ascending order
+ * with multiplicity — no host sort (cli/goleft.cpp SortedCounts). */
 int  gl_bincount_i32(gl_ctx* ctx, const int32_t* v, int64_t n, int32_t lo, int32_t hi, uint64_t* hist);
 
 /* ---------------------------------------------------------------- depthwed
