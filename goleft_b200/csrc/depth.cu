@@ -387,16 +387,21 @@ __device__ __forceinline__ void tile_core(const ScanParams& p, int* __restrict__
     if (lane == 31) s_warp_tot[warp] = inc;
     // depth[k] = tbase + x[k], tbase known only after the barrier: take min / max / sum of the x[k] now, while other
     // warps are still arriving, and add tbase afterwards (the per-base depths are formed only where a slow path needs them)
-    int xmn = x[0], xmx = x[0], xsum = x[0];
+    int xmn = x[0], xmx = x[0];
 #pragma unroll
-    for (int k = 1; k + 1 < BPT; k += 2) {                    // three-input min / max (VIMNMX3) and adds (IADD3)
+    for (int k = 1; k + 1 < BPT; k += 2) {                    // three-input min / max (VIMNMX3)
         xmn = __vimin3_s32(xmn, x[k], x[k + 1]);
         xmx = __vimax3_s32(xmx, x[k], x[k + 1]);
-        xsum += x[k] + x[k + 1];
     }
     xmn = min(xmn, x[BPT - 1]);
     xmx = max(xmx, x[BPT - 1]);
-    xsum += x[BPT - 1];
+    int g8[BPT / 8];                                          // sums of groups of 8 (the window path reuses them)
+#pragma unroll
+    for (int g = 0; g < BPT / 8; g++)
+        g8[g] = (x[8 * g] + x[8 * g + 1] + x[8 * g + 2]) + (x[8 * g + 3] + x[8 * g + 4] + x[8 * g + 5]) + (x[8 * g + 6] + x[8 * g + 7]);
+    int xsum = g8[0];
+#pragma unroll
+    for (int g = 1; g < BPT / 8; g++) xsum += g8[g];
     if (tid == 0) {
         // does a forced run break (multiple of run_break) fall inside this tile?  (absolute positions are < 2^32)
         int hb = 0;
@@ -841,14 +846,17 @@ constexpr int kF8Warps = kF8Threads / 32;
 constexpr int kF8BPT = kTile / kF8Threads;          // 32
 constexpr int kF8BlocksPerPass = kF8Threads / 16;   // a block is 16 lanes x 4 slots
 
-// one segment into the tile (see fused_apply), for the 32-bases-per-thread layout
-__device__ __forceinline__ void fused_apply32(int* s_tile, int t0, int t1, bool first_tile, int s, int e, int& carry) {
-    const int sc = first_tile ? max(s, t0) : s;
-    if (sc < e && sc < t1 && e >= t0) {
-        if (sc < t0) carry++;
-        else atomicAdd(s_tile + swz_elem_t<kF8BPT>(sc - t0), 1);
-        if (e - t0 < kTile) atomicAdd(s_tile + swz_elem_t<kF8BPT>(e - t0), -1);
-    }
+// one segment [s, s+len) into the tile that starts at t0, in tile-relative coordinates a = s - t0, b = a + len:
+//   +1 at a when a is inside the tile, carried in when the segment starts before the tile and reaches it (a < 0 <= b:
+//   it covers base t0-1 or ends exactly at t0 — then its -1 lands on base 0 and cancels the carry);  -1 at b when inside.
+// A start before the region (first tile) is a carry like any other: the region's first base starts a run regardless, so
+// the depth "before" it is never looked at.  Starts / ends beyond the region end fall in the masked tail of the last tile.
+__device__ __forceinline__ void fused_apply32(int* s_tile, int a, int len, int& carry) {
+    if (len == 0) return;                                   // filler / empty slot
+    const int b = a + len;
+    if ((unsigned)a < (unsigned)kTile) atomicAdd(s_tile + swz_elem_t<kF8BPT>(a), 1);
+    else if (a < 0 && b >= 0) carry++;
+    if ((unsigned)b < (unsigned)kTile) atomicAdd(s_tile + swz_elem_t<kF8BPT>(b), -1);
 }
 
 // thread (tid) takes slots 4*(tid&15)..+3 of block lo + (tid>>4) + 8*pass
@@ -863,7 +871,7 @@ __device__ __forceinline__ P8Regs fused8_load(const ScanParams& p, int lo, int h
     return r;
 }
 
-__device__ __forceinline__ void fused8_apply(const P8Regs& r, int* s_tile, int t0, int t1, bool first_tile, int& carry) {
+__device__ __forceinline__ void fused8_apply(const P8Regs& r, int* s_tile, int t0, int& carry) {
     const int sub = threadIdx.x & 15;
     const int d0 = r.d & 0xff, d1 = d0 + ((r.d >> 8) & 0xff), d2 = d1 + ((r.d >> 16) & 0xff), d3 = d2 + (r.d >> 24);
     int inc = d3;
@@ -873,12 +881,11 @@ __device__ __forceinline__ void fused8_apply(const P8Regs& r, int* s_tile, int t
         if (sub >= o) inc += v;
     }
     if (r.l == 0) return;                                   // four empty slots (or no block): nothing to add
-    const int base = r.anchor + inc - d3;
-    const int s0 = base + d0, s1 = base + d1, s2 = base + d2, s3 = base + d3;
-    fused_apply32(s_tile, t0, t1, first_tile, s0, s0 + (int)(r.l & 0xff), carry);
-    fused_apply32(s_tile, t0, t1, first_tile, s1, s1 + (int)((r.l >> 8) & 0xff), carry);
-    fused_apply32(s_tile, t0, t1, first_tile, s2, s2 + (int)((r.l >> 16) & 0xff), carry);
-    fused_apply32(s_tile, t0, t1, first_tile, s3, s3 + (int)(r.l >> 24), carry);
+    const int base = r.anchor + inc - d3 - t0;              // tile-relative start of the slot before this thread's first
+    fused_apply32(s_tile, base + d0, (int)(r.l & 0xff), carry);
+    fused_apply32(s_tile, base + d1, (int)((r.l >> 8) & 0xff), carry);
+    fused_apply32(s_tile, base + d2, (int)((r.l >> 16) & 0xff), carry);
+    fused_apply32(s_tile, base + d3, (int)(r.l >> 24), carry);
 }
 
 // K_fused8: persistent, software-pipelined like K_fused: while tile n runs its core, the packed words of tile n+1 (two
@@ -903,13 +910,12 @@ __global__ void __launch_bounds__(kF8Threads) depth_fused8_kernel(const ScanPara
     int acc_max = 0;
     for (int it = 0; tile < p.tile_end; tile += G, it ^= 1) {
         int* s_carry = s_carry2[it];
-        const int t0 = p.rs + tile * kTile, t1 = min(t0 + kTile, p.re);
-        const bool first_tile = tile == 0;
+        const int t0 = p.rs + tile * kTile;
         int carry = 0;
-        fused8_apply(regs0, s_tile, t0, t1, first_tile, carry);
-        fused8_apply(regs1, s_tile, t0, t1, first_tile, carry);
+        fused8_apply(regs0, s_tile, t0, carry);
+        fused8_apply(regs1, s_tile, t0, carry);
         for (int pass = 2; lo + kF8BlocksPerPass * pass < hi; pass++)     // deep tiles only (uniform trip count)
-            fused8_apply(fused8_load(p, lo, hi, pass), s_tile, t0, t1, first_tile, carry);
+            fused8_apply(fused8_load(p, lo, hi, pass), s_tile, t0, carry);
         carry = __reduce_add_sync(kFull, carry);
         if (lane == 0) s_carry[warp] = carry;
         __syncthreads();
