@@ -27,6 +27,7 @@
 
 #include "../goleft_b200/csrc/host/hts_io.h"
 #include "../goleft_b200/csrc/host/bam_feed.h"
+#include "../goleft_b200/csrc/host/thread_pool.h"
 #include "goleft_b200.h"
 
 static const char* kVersion = "0.2.6";          // goleft.go:3 (the surface this build mirrors)
@@ -709,40 +710,75 @@ static int cmd_indexcov(int argc, char** argv) {
     if (gl_ctx_create(0, &ctx) != GL_OK) fatal(1, "goleft indexcov: %s", gl_last_error(nullptr));
     fprintf(stderr, "indexcov: running on %zu indexes\n", S);
 
-    // tile sizes per sample (I1), then medians + normalised depths for the cohort in one kernel (I2+I3)
-    std::vector<int64_t> all_sizes, sample_ptr(1, 0);
+    // ---- I1 for the whole cohort in ONE launch (indexcov/types.go:45-82): every sample's linear-index offsets go up once,
+    //      one descriptor per (sample, reference with >= 2 entries); CRAM samples bring host-made pseudo-tile sizes
+    std::vector<int64_t> sample_ptr(1, 0);
     std::vector<std::vector<int64_t>> size_ptr(S);                          // per sample: CSR over its refs
     std::vector<uint64_t> mapped(S, 0), unmapped(S, 0);
+    std::vector<uint64_t> voff_all;
+    std::vector<int64_t> desc_voff, desc_size;
+    std::vector<int32_t> desc_n;
+    std::vector<std::pair<int64_t, std::vector<int64_t>>> crai_sizes;       // (offset into the cohort's sizes, values)
     for (size_t i = 0; i < S; i++) {
+        const int64_t base = sample_ptr.back();
         if (ends_with(bams[i], ".crai")) {                                  // CRAM: interpolated pseudo-tiles (crai.go:56-127)
             const size_t nr = crai[i].size();
-            std::vector<int64_t> sp(nr + 1, 0), sz;
+            std::vector<int64_t> sp(nr + 1, 0), all;
             for (size_t r = 0; r < nr; r++) {
                 std::vector<int64_t> one;
                 if (!glhts::crai_make_sizes(crai[i][r].start.data(), crai[i][r].span.data(), crai[i][r].bytes.data(),
                                             (int64_t)crai[i][r].start.size(), one)) fatal(2, "panic: tilewidth logic error");
-                all_sizes.insert(all_sizes.end(), one.begin(), one.end());
+                all.insert(all.end(), one.begin(), one.end());
                 sp[r + 1] = sp[r] + (int64_t)one.size();
             }
             if (sp[nr] < 1) fatal(1, "indexcov: no usable chromsomes in bam: %s", bams[i].c_str());
-            sample_ptr.push_back((int64_t)all_sizes.size());
+            sample_ptr.push_back(base + sp[nr]);
+            crai_sizes.emplace_back(base, std::move(all));
             size_ptr[i] = sp;
             continue;
         }
         const size_t nr = idx[i].ioffsets.size();
-        std::vector<uint64_t> voff;
-        std::vector<int64_t> rp(nr + 1, 0);
-        for (size_t r = 0; r < nr; r++) { voff.insert(voff.end(), idx[i].ioffsets[r].begin(), idx[i].ioffsets[r].end()); rp[r + 1] = (int64_t)voff.size(); mapped[i] += idx[i].mapped[r]; unmapped[i] += idx[i].unmapped[r]; }
-        std::vector<int64_t> sz(voff.size() + 1), sp(nr + 1, 0);
-        glck(ctx, gl_indexcov_sizes(ctx, voff.data(), rp.data(), (int32_t)nr, sz.data(), sp.data()), "gl_indexcov_sizes");
+        std::vector<int64_t> sp(nr + 1, 0);
+        for (size_t r = 0; r < nr; r++) {
+            const std::vector<uint64_t>& io = idx[i].ioffsets[r];
+            mapped[i] += idx[i].mapped[r]; unmapped[i] += idx[i].unmapped[r];
+            sp[r + 1] = sp[r] + (io.size() >= 2 ? (int64_t)io.size() - 1 : 0);          // types.go:68-72
+            if (io.size() >= 2) {
+                desc_voff.push_back((int64_t)voff_all.size()); desc_n.push_back((int32_t)io.size()); desc_size.push_back(base + sp[r]);
+                voff_all.insert(voff_all.end(), io.begin(), io.end());
+            }
+        }
         if (sp[nr] < 1) fatal(1, "indexcov: no usable chromsomes in bam: %s", bams[i].c_str());   // indexcov.go:100-102
-        all_sizes.insert(all_sizes.end(), sz.begin(), sz.begin() + sp[nr]);
-        sample_ptr.push_back((int64_t)all_sizes.size());
+        sample_ptr.push_back(base + sp[nr]);
         size_ptr[i] = sp;
     }
+    const int64_t total = sample_ptr.back();
+    auto dalloc = [&](size_t bytes) { void* p = nullptr; glck(ctx, gl_dev_alloc(ctx, (int64_t)std::max<size_t>(bytes, 16), &p), "gl_dev_alloc"); return p; };
+    auto up = [&](const void* h, size_t bytes) { void* p = dalloc(bytes); if (bytes) glck(ctx, gl_memcpy_h2d(ctx, p, h, (int64_t)bytes), "gl_memcpy_h2d"); return p; };
+    int64_t* d_sizes = static_cast<int64_t*>(dalloc((size_t)total * 8));
+    if (!desc_n.empty()) {
+        void* d_voff = up(voff_all.data(), voff_all.size() * 8);
+        void* d_dv = up(desc_voff.data(), desc_voff.size() * 8);
+        void* d_dn = up(desc_n.data(), desc_n.size() * 4);
+        void* d_ds = up(desc_size.data(), desc_size.size() * 8);
+        const int rc = gl_indexcov_sizes_batch_device(ctx, static_cast<const uint64_t*>(d_voff), static_cast<const int64_t*>(d_dv),
+                                                      static_cast<const int32_t*>(d_dn), static_cast<const int64_t*>(d_ds), (int64_t)desc_n.size(), d_sizes);
+        if (rc == GL_ERANGE) fatal(2, "panic: expected positive change in vOffset");                 // types.go:75-77
+        glck(ctx, rc, "gl_indexcov_sizes_batch_device");
+        gl_dev_free(ctx, d_voff); gl_dev_free(ctx, d_dv); gl_dev_free(ctx, d_dn); gl_dev_free(ctx, d_ds);
+        std::vector<uint64_t>().swap(voff_all);
+    }
+    for (auto& cs : crai_sizes) glck(ctx, gl_memcpy_h2d(ctx, d_sizes + cs.first, cs.second.data(), (int64_t)cs.second.size() * 8), "gl_memcpy_h2d");
+    // ---- I2+I3 for the cohort in one kernel, on the resident sizes (indexcov.go:83-151)
     std::vector<double> med(S);
-    std::vector<float> dep(all_sizes.size());
-    glck(ctx, gl_indexcov_cohort(ctx, all_sizes.data(), sample_ptr.data(), (int32_t)S, med.data(), dep.data()), "gl_indexcov_cohort");
+    std::vector<float> dep((size_t)total);
+    void* d_sp = up(sample_ptr.data(), sample_ptr.size() * 8);
+    double* d_med = static_cast<double*>(dalloc(S * 8));
+    float* d_dep = static_cast<float*>(dalloc((size_t)total * 4));
+    glck(ctx, gl_indexcov_cohort_device(ctx, d_sizes, static_cast<const int64_t*>(d_sp), (int32_t)S, d_med, d_dep), "gl_indexcov_cohort_device");
+    glck(ctx, gl_memcpy_d2h(ctx, med.data(), d_med, (int64_t)S * 8), "gl_memcpy_d2h");
+    glck(ctx, gl_memcpy_d2h(ctx, dep.data(), d_dep, total * 4), "gl_memcpy_d2h");
+    gl_dev_free(ctx, d_sizes); gl_dev_free(ctx, d_sp); gl_dev_free(ctx, d_med);
 
     const std::string base = dir + "/" + dir.substr(dir.find_last_of('/') == std::string::npos ? 0 : dir.find_last_of('/') + 1) + "-indexcov";
     glhts::BgzfWriter bgz(base + ".bed.gz");
@@ -750,61 +786,131 @@ static int cmd_indexcov(int argc, char** argv) {
     if (!bgz.ok() || !roc) fatal(1, "cannot create outputs in %s", dir.c_str());
     { std::string h = "#chrom\tstart\tend"; for (auto& n : names) h += "\t" + n; h += "\n"; bgz.write(h.data(), h.size()); }
 
+    // the references that are reported (exclude pattern, indexcov.go:637-646)
+    std::vector<const IcRef*> kept;
+    {
+        int n_reported = 0;
+        for (const IcRef& ref : refs) {
+            if (!exclude.empty() && std::regex_search(ref.name, excl)) {
+                if (n_reported < 10) { fprintf(stderr, "indexcv: excluding chromosome: %s because of exclude-pattern: %s\n", ref.name.c_str(), exclude.c_str()); if (++n_reported == 10) fprintf(stderr, "not reporting further skipped chromosomes\n"); }
+                continue;
+            }
+            kept.push_back(&ref);
+        }
+    }
+    // ---- without -n the values never change after I3: the "%.3g" token of EVERY value (I6) and the slot histograms +
+    //      counters of EVERY (reference, sample) pair (I4+I5) come from two launches over the resident depths
+    std::vector<uint8_t> tok_all;
+    std::vector<int32_t> counts_all;
+    std::vector<int64_t> b4_all;
+    if (!extranorm) {
+        tok_all.resize((size_t)total * 10 + 16);
+        uint8_t* d_tok = static_cast<uint8_t*>(dalloc((size_t)total * 10));
+        if (total) glck(ctx, gl_format_g3_device(ctx, d_dep, total, d_tok), "gl_format_g3_device");
+        if (total) glck(ctx, gl_memcpy_d2h(ctx, tok_all.data(), d_tok, total * 10), "gl_memcpy_d2h");
+        gl_dev_free(ctx, d_tok);
+        const size_t nseg = kept.size() * S;
+        std::vector<int64_t> seg_start(nseg, 0), seg_len(nseg, 0), seg_longest(nseg, 0);
+        for (size_t q = 0; q < kept.size(); q++) {
+            int64_t longest = 0;
+            for (size_t k = 0; k < S; k++) {
+                if (kept[q]->id + 1 < (int)size_ptr[k].size() && med[k] != 0) {
+                    seg_start[q * S + k] = sample_ptr[k] + size_ptr[k][kept[q]->id];
+                    seg_len[q * S + k] = size_ptr[k][kept[q]->id + 1] - size_ptr[k][kept[q]->id];
+                }
+                longest = std::max(longest, seg_len[q * S + k]);
+            }
+            for (size_t k = 0; k < S; k++) seg_longest[q * S + k] = longest;
+        }
+        counts_all.resize(nseg * GL_INDEXCOV_SLOTS);
+        b4_all.resize(nseg * 4);
+        if (nseg) {
+            void* d_ss = up(seg_start.data(), nseg * 8);
+            void* d_sl = up(seg_len.data(), nseg * 8);
+            void* d_lg = up(seg_longest.data(), nseg * 8);
+            int32_t* d_c = static_cast<int32_t*>(dalloc(nseg * GL_INDEXCOV_SLOTS * 4));
+            int64_t* d_b = static_cast<int64_t*>(dalloc(nseg * 32));
+            glck(ctx, gl_indexcov_counts_segs_device(ctx, d_dep, static_cast<const int64_t*>(d_ss), static_cast<const int64_t*>(d_sl),
+                                                     static_cast<const int64_t*>(d_lg), (int32_t)nseg, d_c, d_b), "gl_indexcov_counts_segs_device");
+            glck(ctx, gl_memcpy_d2h(ctx, counts_all.data(), d_c, (int64_t)nseg * GL_INDEXCOV_SLOTS * 4), "gl_memcpy_d2h");
+            glck(ctx, gl_memcpy_d2h(ctx, b4_all.data(), d_b, (int64_t)nseg * 32), "gl_memcpy_d2h");
+            gl_dev_free(ctx, d_ss); gl_dev_free(ctx, d_sl); gl_dev_free(ctx, d_lg); gl_dev_free(ctx, d_c); gl_dev_free(ctx, d_b);
+        }
+    }
+    gl_dev_free(ctx, d_dep);
+
     std::map<std::string, std::vector<double>> sexes;
     std::vector<int64_t> bins(S * 4, 0);
     std::vector<float> slopes(S, 0);
-    int n_slopes = 0, n_reported = 0;
-    for (const IcRef& ref : refs) {
-        if (!exclude.empty() && std::regex_search(ref.name, excl)) {
-            if (n_reported < 10) { fprintf(stderr, "indexcv: excluding chromosome: %s because of exclude-pattern: %s\n", ref.name.c_str(), exclude.c_str()); if (++n_reported == 10) fprintf(stderr, "not reporting further skipped chromosomes\n"); }
-            continue;
-        }
+    int n_slopes = 0;
+    for (size_t q = 0; q < kept.size(); q++) {
+        const IcRef& ref = *kept[q];
         // per-sample slices of this reference (ref.ID() indexes the index's reference array, indexcov.go:656)
         std::vector<const float*> dptr(S, nullptr);
+        std::vector<int64_t> doff(S, 0);
         std::vector<int32_t> lens(S, 0);
         size_t longest = 0;
         for (size_t k = 0; k < S; k++) {
             if (ref.id + 1 < (int)size_ptr[k].size() && med[k] != 0) {
                 const int64_t a = size_ptr[k][ref.id], b = size_ptr[k][ref.id + 1];
-                dptr[k] = dep.data() + sample_ptr[k] + a;
+                doff[k] = sample_ptr[k] + a;
+                dptr[k] = dep.data() + doff[k];
                 lens[k] = (int32_t)(b - a);
             }
             longest = std::max(longest, (size_t)lens[k]);
         }
         const bool is_sex = same_chrom(sexes_wanted, ref.name);
         std::vector<float> mat;                                             // S x longest, used when values are rewritten
-        if (extranorm && !is_sex && longest > 0) {
-            mat.assign(S * longest, 0.f);
-            for (size_t k = 0; k < S; k++) if (lens[k]) memcpy(&mat[k * longest], dptr[k], (size_t)lens[k] * 4);
-            glck(ctx, gl_indexcov_xnorm(ctx, mat.data(), lens.data(), (int32_t)S, (int32_t)longest), "gl_indexcov_xnorm");
-            for (size_t k = 0; k < S; k++) dptr[k] = &mat[k * longest];
-        }
-        // slot histograms + in/out counters for every sample on this reference (I4+I5)
-        std::vector<float> flat;
-        std::vector<int64_t> seg_ptr(1, 0), lg(S, (int64_t)longest);
-        for (size_t k = 0; k < S; k++) { flat.insert(flat.end(), dptr[k], dptr[k] + lens[k]); seg_ptr.push_back((int64_t)flat.size()); }
-        std::vector<int32_t> counts(S * GL_INDEXCOV_SLOTS);
-        std::vector<int64_t> b4(S * 4);
-        glck(ctx, gl_indexcov_counts_batch(ctx, flat.data(), seg_ptr.data(), lg.data(), (int32_t)S, counts.data(), b4.data()), "gl_indexcov_counts_batch");
-
-        // bed.gz rows (indexcov.go:678-680,1038-1048): every "%.3g" comes from the GPU formatter as a 10-byte token
-        std::vector<uint8_t> tok(flat.size() * 10 + 10);
-        glck(ctx, gl_format_g3(ctx, flat.data(), (int64_t)flat.size(), tok.data()), "gl_format_g3");
-        std::string row;
-        char num[48];
-        for (size_t i = 0; i < longest; i++) {
-            row = ref.name;
-            snprintf(num, sizeof num, "\t%zu\t%zu", i * 16384, (i + 1) * 16384);
-            row += num;
-            for (size_t k = 0; k < S; k++) {
-                row.push_back('\t');
-                if (i >= (size_t)lens[k]) { row.push_back('0'); continue; }
-                const uint8_t* t = &tok[((size_t)seg_ptr[k] + i) * 10];
-                if (t[9]) row.append(reinterpret_cast<const char*>(t), t[9]);
-                else row += go_float("%.3g", (double)dptr[k][i]);                             // magnitude outside the kernel's range
+        std::vector<int32_t> counts_ref;
+        std::vector<int64_t> b4_ref;
+        std::vector<uint8_t> tok_ref;
+        std::vector<int64_t> seg_ptr(1, 0);
+        const int32_t* counts = nullptr;
+        const int64_t* b4 = nullptr;
+        if (extranorm) {
+            if (!is_sex && longest > 0) {
+                mat.assign(S * longest, 0.f);
+                for (size_t k = 0; k < S; k++) if (lens[k]) memcpy(&mat[k * longest], dptr[k], (size_t)lens[k] * 4);
+                glck(ctx, gl_indexcov_xnorm(ctx, mat.data(), lens.data(), (int32_t)S, (int32_t)longest), "gl_indexcov_xnorm");
+                for (size_t k = 0; k < S; k++) dptr[k] = &mat[k * longest];
             }
-            row += "\n";
-            bgz.write(row.data(), row.size());
+            // -n rewrites the values per reference: slot histograms, counters and tokens from this reference's values
+            std::vector<float> flat;
+            std::vector<int64_t> lg(S, (int64_t)longest);
+            for (size_t k = 0; k < S; k++) { flat.insert(flat.end(), dptr[k], dptr[k] + lens[k]); seg_ptr.push_back((int64_t)flat.size()); }
+            counts_ref.resize(S * GL_INDEXCOV_SLOTS); b4_ref.resize(S * 4);
+            glck(ctx, gl_indexcov_counts_batch(ctx, flat.data(), seg_ptr.data(), lg.data(), (int32_t)S, counts_ref.data(), b4_ref.data()), "gl_indexcov_counts_batch");
+            tok_ref.resize(flat.size() * 10 + 10);
+            glck(ctx, gl_format_g3(ctx, flat.data(), (int64_t)flat.size(), tok_ref.data()), "gl_format_g3");
+            counts = counts_ref.data(); b4 = b4_ref.data();
+        } else {
+            counts = &counts_all[q * S * GL_INDEXCOV_SLOTS];
+            b4 = &b4_all[q * S * 4];
+        }
+        // bed.gz rows (indexcov.go:678-680,1038-1048): every "%.3g" comes from the GPU formatter as a 10-byte token; the rows
+        // are put together by all host threads, 256 rows per task, and handed to the BGZF writer in order
+        {
+            const size_t kRows = 256, n_tasks = (longest + kRows - 1) / kRows;
+            std::vector<std::string> parts(n_tasks);
+            glhost::ThreadPool::global().run((int64_t)n_tasks, [&](int64_t t, int) {
+                std::string& out = parts[(size_t)t];
+                out.reserve(kRows * (ref.name.size() + 24 + S * 7));
+                char num[48];
+                const size_t i0 = (size_t)t * kRows, i1 = std::min(longest, i0 + kRows);
+                for (size_t i = i0; i < i1; i++) {
+                    out += ref.name;
+                    out.append(num, (size_t)snprintf(num, sizeof num, "\t%zu\t%zu", i * 16384, (i + 1) * 16384));
+                    for (size_t k = 0; k < S; k++) {
+                        out.push_back('\t');
+                        if (i >= (size_t)lens[k]) { out.push_back('0'); continue; }
+                        const uint8_t* tk = extranorm ? &tok_ref[((size_t)seg_ptr[k] + i) * 10] : &tok_all[((size_t)doff[k] + i) * 10];
+                        if (tk[9]) out.append(reinterpret_cast<const char*>(tk), tk[9]);
+                        else out += go_float("%.3g", (double)dptr[k][i]);                           // magnitude outside the kernel's range
+                    }
+                    out.push_back('\n');
+                }
+            });
+            for (const std::string& part : parts) bgz.write(part.data(), part.size());
         }
         if (is_sex) {
             if (longest > 0) { std::vector<double> cn(S); for (size_t k = 0; k < S; k++) cn[k] = get_cn(dptr[k], (size_t)lens[k]); sexes[ref.name] = cn; }

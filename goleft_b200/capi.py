@@ -98,6 +98,8 @@ _proto("gl_indexcov_scale", C.c_int, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_indexcov_normalize", C.c_int, _vp, _vp, C.c_int64, C.c_double, _vp)
 _proto("gl_indexcov_cohort", C.c_int, _vp, _vp, _vp, C.c_int32, _vp, _vp)
 _proto("gl_indexcov_cohort_device", C.c_int, _vp, _vp, _vp, C.c_int32, _vp, _vp)
+_proto("gl_indexcov_cohort_fallbacks", C.c_int, _vp, _i32p)
+_proto("gl_indexcov_sizes_batch_device", C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int64, _vp)
 _proto("gl_indexcov_counts", C.c_int, _vp, _vp, C.c_int64, _vp)
 _proto("gl_indexcov_bins", C.c_int, _vp, _vp, C.c_int64, C.c_int64, _vp)
 _proto("gl_indexcov_counts_batch", C.c_int, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp)
@@ -750,6 +752,23 @@ class Ctx:
         dep = np.empty(sizes.size, np.float32) if want_depth else None
         self._ck(lib.gl_indexcov_cohort(self.h, _ptr(sizes), _ptr(sample_ptr), S, _ptr(med), _ptr(dep)))
         return med, dep
+
+    def indexcov_cohort_fallbacks(self) -> int:
+        n = C.c_int32(0)
+        self._ck(lib.gl_indexcov_cohort_fallbacks(self.h, C.byref(n)))
+        return n.value
+
+    def indexcov_sizes_batch(self, voff: np.ndarray, voff_off, n_intv, size_off, total_sizes: int) -> np.ndarray:
+        """I1 for many (sample, reference) descriptors in one launch (arrays uploaded here; the device form keeps them resident)"""
+        d_v, d_o = self.dev_array(_as(voff, np.uint64)), self.dev_array(_as(voff_off, np.int64))
+        d_n, d_s = self.dev_array(_as(n_intv, np.int32)), self.dev_array(_as(size_off, np.int64))
+        d_out = self.dev_empty(max(total_sizes, 1) * 8)
+        try:
+            self._ck(lib.gl_indexcov_sizes_batch_device(self.h, d_v.ptr, d_o.ptr, d_n.ptr, d_s.ptr, len(n_intv), d_out.ptr))
+            return d_out.download(np.int64, total_sizes)
+        finally:
+            for b in (d_v, d_o, d_n, d_s, d_out):
+                b.free()
 
     def indexcov_counts(self, depth: np.ndarray, counts: Optional[np.ndarray] = None) -> np.ndarray:
         depth = _as(depth, np.float32)

@@ -51,7 +51,7 @@ constexpr int kSelBins = 1024;
 
 struct SelSmem {
     unsigned long long w[kSelBins];
-    long long red_lo[kCohortThreads / 32], red_hi[kCohortThreads / 32];
+    long long red_lo[32], red_hi[32];
     long long bcast[3];
 };
 
@@ -73,7 +73,7 @@ __device__ void block_minmax(const long long* __restrict__ v, long long n, long 
     if ((threadIdx.x & 31) == 0) { sm.red_lo[threadIdx.x >> 5] = mn; sm.red_hi[threadIdx.x >> 5] = mx; }
     __syncthreads();
     mn = 0x7fffffffffffffffll; mx = -0x7fffffffffffffffll - 1;
-    for (int w = 0; w < kCohortThreads / 32; w++) { mn = min(mn, sm.red_lo[w]); mx = max(mx, sm.red_hi[w]); }
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { mn = min(mn, sm.red_lo[w]); mx = max(mx, sm.red_hi[w]); }
     __syncthreads();
     out_lo = mn; out_hi = mx;
 }
@@ -166,6 +166,272 @@ __global__ void __launch_bounds__(kCohortThreads) ic_cohort_kernel(const long lo
     }
 }
 
+// ------------------------------------------------------------------------------------------------ I2 + I3, version 2
+// ic_cohort2_kernel: the same two order statistics, but the sample's tiles are streamed TWICE instead of ~17 times and no
+// shared-memory histogram (64-bit shared atomics are a CAS loop on sm_100) is involved:
+//   small samples (n <= 8192): all tiles sorted in shared memory (bitonic), Index.init done literally.
+//   large samples: a strided sample of 8192 tiles is sorted in shared memory; it brackets the 98th-percentile element
+//     (n98) and the capped weighted median (med) by VALUE:  [lo98, hi98] around sample rank 0.98 K (+-64 ranks, > 5 sigma)
+//     and [loM, hiM] around the sample's own capped weighted median (+-136 ranks, 3 sigma).  One pass over the tiles then
+//     sums what lies below / between the brackets, counts what lies above, and collects the tiles INSIDE the brackets into
+//     two small shared-memory lists (warp-aggregated appends); the lists are sorted and the exact answers read off them:
+//       n98   = cand98[k98 - #{s < lo98}],
+//       total = sum(s < loM) + sum(candM) + sum(hiM < s < lo98) + sum(min(cand98, n98)) + n98 * #{s > hi98},
+//       med   = first candM value whose running sum (from sum(s < loM)) exceeds total/2.
+//     Every step is verified (rank inside the list, brackets disjoint, lists not overflowing); on any failure — heavy ties,
+//     a pathological order — the sample falls back to the range-adaptive select above, so the result is always exact.
+//   A last pass writes float32(float64(size)/med).  Traffic: 2 reads of 8 B + 1 write of 4 B per tile.
+constexpr int kC2Threads = 1024;
+constexpr int kC2Sample = 8192;
+constexpr int kC2CandM = 8192;
+constexpr int kC2Cand98 = 4096;
+constexpr long long kI64Max = 0x7fffffffffffffffll;
+
+struct C2Smem {
+    long long samp[kC2Sample];
+    long long candM[kC2CandM];
+    long long cand98[kC2Cand98];
+};
+
+// ascending bitonic sort of a[0..n2), n2 a power of two, by the whole block
+__device__ void block_bitonic(long long* a, int n2) {
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & k) == 0;
+                    const long long x = a[i], y = a[ixj];
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+// block-wide sum of one long long per thread (result to every thread); red has blockDim/32 slots
+__device__ long long block_sum(long long v, long long* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+    __syncthreads();
+    return t;
+}
+
+// in-place inclusive prefix sum of a[0..m), m <= 8 * blockDim.x
+__device__ void block_prefix(long long* a, int m, long long* red) {
+    const int per = (m + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int b = threadIdx.x * per, e = min(m, b + per);
+    long long loc = 0;
+    for (int i = b; i < e; i++) loc += a[i];
+    long long inc = loc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) red[warp] = inc;
+    __syncthreads();
+    long long base = inc - loc;
+    for (int w = 0; w < warp; w++) base += red[w];
+    __syncthreads();
+    for (int i = b; i < e; i++) { base += a[i]; a[i] = base; }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void warp_append(long long* list, int cap, int* counter, int* overflow, bool take, long long x) {
+    const unsigned m = __ballot_sync(kFull, take);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(kFull, base, __ffs(m) - 1);
+    if (take) {
+        const int at = base + __popc(m & ((1u << lane) - 1u));
+        if (at < cap) list[at] = x; else *overflow = 1;
+    }
+}
+
+__global__ void __launch_bounds__(kC2Threads, 1) ic_cohort2_kernel(const long long* __restrict__ sizes, const long long* __restrict__ sample_ptr,
+                                                                     int S, double* __restrict__ medians, float* __restrict__ depth_out,
+                                                                     unsigned* __restrict__ fallback_count) {
+    extern __shared__ __align__(16) unsigned char c2_raw[];
+    C2Smem& sm = *reinterpret_cast<C2Smem*>(c2_raw);
+    __shared__ long long s_red[kC2Threads / 32];
+    __shared__ long long s_b[8];
+    __shared__ int s_cnt[4];
+    const int tid = threadIdx.x;
+    for (int smp = blockIdx.x; smp < S; smp += gridDim.x) {
+        const long long a = sample_ptr[smp], n = sample_ptr[smp + 1] - a;
+        const long long* v = sizes + a;
+        if (n <= 0) { if (tid == 0) medians[smp] = 0.0; continue; }
+        const long long k98 = (long long)(0.98 * (double)n);                     // indexcov.go:111
+        long long med = 0;
+        bool ok = true;
+        if (n <= kC2Sample) {
+            // ---- everything fits: sort and follow Index.init literally
+            const int n2 = next_pow2((int)n);
+            for (int i = tid; i < n2; i += kC2Threads) sm.samp[i] = i < n ? v[i] : kI64Max;
+            __syncthreads();
+            block_bitonic(sm.samp, n2);
+            const long long n98 = sm.samp[k98];
+            for (int i = tid; i < (int)n; i += kC2Threads) sm.candM[i] = min(sm.samp[i], n98);
+            __syncthreads();
+            block_prefix(sm.candM, (int)n, s_red);
+            const long long total = sm.candM[n - 1];
+            // first i with cumsum[i] > total/2 (sort.Search); when none (total == 0) the clamp picks the last element
+            int lo = 0, hi = (int)n;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.candM[mid] > total / 2) hi = mid; else lo = mid + 1; }
+            med = sm.samp[min(lo, (int)n - 1)];
+            __syncthreads();
+        } else {
+            // ---- sorted sample -> brackets
+            for (int i = tid; i < kC2Sample; i += kC2Threads) sm.samp[i] = v[(long long)(((__int128)i * n) / kC2Sample)];
+            __syncthreads();
+            block_bitonic(sm.samp, kC2Sample);
+            const int p98 = (int)(((__int128)k98 * kC2Sample) / n);
+            const long long cap_est = sm.samp[p98];
+            for (int i = tid; i < kC2Sample; i += kC2Threads) sm.candM[i] = min(sm.samp[i], cap_est);
+            __syncthreads();
+            block_prefix(sm.candM, kC2Sample, s_red);
+            if (tid == 0) {
+                const long long tot = sm.candM[kC2Sample - 1];
+                int lo = 0, hi = kC2Sample;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.candM[mid] > tot / 2) hi = mid; else lo = mid + 1; }
+                const int pM = min(lo, kC2Sample - 1);
+                s_b[0] = sm.samp[max(0, pM - 136)];                                            // loM
+                s_b[1] = sm.samp[min(kC2Sample - 1, pM + 136)];                                // hiM
+                s_b[2] = sm.samp[max(0, p98 - 64)];                                            // lo98
+                s_b[3] = p98 + 64 < kC2Sample ? sm.samp[p98 + 64] : kI64Max;                   // hi98
+                s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+            }
+            __syncthreads();
+            const long long loM = s_b[0], hiM = s_b[1], lo98 = s_b[2], hi98 = s_b[3];
+            ok = hiM < lo98;                                                       // brackets must not touch
+            long long sum_lo = 0, sum_mid = 0, cnt_above = 0, vmax = 0;
+            if (ok) {
+                const long long n_round = (n + kC2Threads - 1) / kC2Threads * kC2Threads;
+                for (long long i = tid; i < n_round; i += kC2Threads) {
+                    const bool live = i < n;
+                    const long long x = live ? v[i] : 0;
+                    const bool inM = live && x >= loM && x <= hiM, in98 = live && x >= lo98 && x <= hi98;
+                    if (live) {
+                        vmax = max(vmax, x);
+                        if (x < loM) sum_lo += x;
+                        else if (x > hiM && x < lo98) sum_mid += x;
+                        else if (x > hi98) cnt_above++;
+                    }
+                    warp_append(sm.candM, kC2CandM, &s_cnt[0], &s_cnt[2], inM, x);
+                    warp_append(sm.cand98, kC2Cand98, &s_cnt[1], &s_cnt[2], in98, x);
+                }
+                sum_lo = block_sum(sum_lo, s_red);
+                sum_mid = block_sum(sum_mid, s_red);
+                cnt_above = block_sum(cnt_above, s_red);
+                {                                                                   // block max
+                    long long m = vmax;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(kFull, m, o));
+                    if ((tid & 31) == 0) s_red[tid >> 5] = m;
+                    __syncthreads();
+                    m = 0;
+                    for (int w = 0; w < kC2Threads / 32; w++) m = max(m, s_red[w]);
+                    __syncthreads();
+                    vmax = m;
+                }
+                ok = s_cnt[2] == 0;
+            }
+            long long n98 = 0, total = 0;
+            if (ok) {
+                const int nM = s_cnt[0], n9 = s_cnt[1];
+                const long long below98 = n - n9 - cnt_above;                       // #{s < lo98}
+                const long long idx = k98 - below98;
+                ok = idx >= 0 && idx < n9;
+                if (ok) {
+                    const int n92 = next_pow2(max(n9, 1));
+                    for (int i = n9 + tid; i < n92; i += kC2Threads) sm.cand98[i] = kI64Max;
+                    const int nM2 = next_pow2(max(nM, 1));
+                    for (int i = nM + tid; i < nM2; i += kC2Threads) sm.candM[i] = kI64Max;
+                    __syncthreads();
+                    block_bitonic(sm.cand98, n92);
+                    block_bitonic(sm.candM, nM2);
+                    n98 = sm.cand98[idx];
+                    long long part = 0;
+                    for (int i = tid; i < n9; i += kC2Threads) part += min(sm.cand98[i], n98);
+                    long long partM = 0;
+                    for (int i = tid; i < nM; i += kC2Threads) partM += sm.candM[i];
+                    part = block_sum(part, s_red);
+                    partM = block_sum(partM, s_red);
+                    total = sum_lo + partM + sum_mid + part + n98 * cnt_above;
+                    if (total == 0) med = vmax;                                     // cumsum never exceeds 0: the clamp picks the largest
+                    else {
+                        const long long target = total / 2;
+                        // running sums of candM on top of sum_lo, in samp[] (the sample is no longer needed)
+                        for (int i = tid; i < nM; i += kC2Threads) sm.samp[i] = sm.candM[i];
+                        __syncthreads();
+                        block_prefix(sm.samp, nM, s_red);
+                        if (tid == 0) {
+                            int lo = 0, hi = nM;
+                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sum_lo + sm.samp[mid] > target) hi = mid; else lo = mid + 1; }
+                            // the answer must be INSIDE the list: below it the running sum is still <= target, and it is reached
+                            s_cnt[3] = (sum_lo <= target && lo < nM) ? lo : -1;
+                        }
+                        __syncthreads();
+                        ok = s_cnt[3] >= 0;
+                        if (ok) med = sm.candM[s_cnt[3]];
+                    }
+                }
+            }
+            __syncthreads();
+            if (!ok) {
+                // ---- exact fallback: the range-adaptive select (uses the same shared memory)
+                SelSmem& sel = *reinterpret_cast<SelSmem*>(c2_raw);
+                if (tid == 0 && fallback_count) atomicAdd(fallback_count, 1u);
+                long long vmin, vmx;
+                block_minmax(v, n, -kI64Max - 1, kI64Max, 0, 0.0, -1, sel, vmin, vmx);
+                const long long f98 = block_select<false>(v, n, 0, k98, vmin, vmx, sel);
+                long long part = 0;
+                for (long long i = tid; i < n; i += kC2Threads) part += min(v[i], f98);
+                const long long tot = block_sum(part, s_red);
+                med = (tot == 0) ? vmx : block_select<true>(v, n, f98, tot / 2, vmin, vmx, sel);
+                __syncthreads();
+            }
+        }
+        const double dm = (double)med;
+        if (tid == 0) medians[smp] = dm;
+        // depth = float32(float64(o)/median), capped at 50000                    (indexcov.go:129-151)
+        if (depth_out) {
+            float* out = depth_out + a;
+            for (long long i = tid; i < n; i += kC2Threads) {
+                float d = (med == 0) ? 0.0f : __double2float_rn(__ddiv_rn((double)v[i], dm));
+                if (d > 50000.0f) d = 50000.0f;
+                out[i] = d;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// I1 for a whole cohort in one launch: one warp per (sample, reference) descriptor, sizes = consecutive differences of the
+// reference's linear-index virtual offsets (indexcov/types.go:60-78)
+__global__ void __launch_bounds__(256) ic_sizes_batch_kernel(const unsigned long long* __restrict__ voff, const long long* __restrict__ d_voff_off,
+                                                            const int* __restrict__ d_n_intv, const long long* __restrict__ d_size_off,
+                                                            long long n_desc, long long* __restrict__ sizes, int* __restrict__ neg_flag) {
+    const long long w = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_desc) return;
+    const long long a = d_voff_off[w], o = d_size_off[w];
+    const int n = d_n_intv[w];
+    for (int k = lane; k + 1 < n; k += 32) {
+        const long long d = (long long)voff[a + k + 1] - (long long)voff[a + k];
+        if (d < 0) *neg_flag = 1;
+        sizes[o + k] = d;
+    }
+}
+
 __global__ void __launch_bounds__(256) ic_normalize_kernel(const long long* __restrict__ sizes, long long n, double median,
                                                           float* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,7 +443,10 @@ __global__ void __launch_bounds__(256) ic_normalize_kernel(const long long* __re
 
 // ------------------------------------------------------------------------------------------------ I4 + I5
 // one CTA per segment (a sample's tiles on one chromosome)
+// seg_len == null: segment seg = [seg_ptr[seg], seg_ptr[seg+1]) (CSR); else [seg_ptr[seg], seg_ptr[seg] + seg_len[seg]) —
+// the (sample, chromosome) slices of a cohort's depth array are not contiguous per chromosome
 __global__ void __launch_bounds__(256) ic_counts_kernel(const float* __restrict__ depth, const long long* __restrict__ seg_ptr,
+                                                       const long long* __restrict__ seg_len,
                                                        const long long* __restrict__ longest, int n_seg,
                                                        int* __restrict__ counts70, long long* __restrict__ bins4) {
     __shared__ int s_cnt[GL_INDEXCOV_SLOTS];
@@ -187,7 +456,7 @@ __global__ void __launch_bounds__(256) ic_counts_kernel(const float* __restrict_
     for (int i = threadIdx.x; i < GL_INDEXCOV_SLOTS; i += blockDim.x) s_cnt[i] = 0;
     if (threadIdx.x < 4) s_bin[threadIdx.x] = 0;
     __syncthreads();
-    const long long a = seg_ptr[seg], n = seg_ptr[seg + 1] - a;
+    const long long a = seg_ptr[seg], n = seg_len ? seg_len[seg] : seg_ptr[seg + 1] - a;
     const float K = 46.66666793823242f;                      // float32(70 * float32(2/3)), indexcov.go:153-157,175
     int b_out = 0, b_low = 0, b_hi = 0, b_in = 0;
     for (long long i = threadIdx.x; i < n; i += blockDim.x) {
@@ -518,14 +787,59 @@ int gl_indexcov_cohort_device(gl_ctx* ctx, const int64_t* d_sizes, const int64_t
     GL_CHECK(gl_use(ctx));
     if (S < 0 || !d_sizes || !d_sample_ptr || !d_medians) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_cohort_device: bad argument");
     if (S == 0) return GL_OK;
-    {
+    static const bool use_v1 = [] { const char* e = getenv("GL_COHORT_V1"); return e && atoi(e) != 0; }();
+    if (use_v1) {
         gl_prof_scope prof(ctx, "ic_cohort_kernel");
         ic_cohort_kernel<<<(unsigned)S, kCohortThreads, 0, ctx->stream>>>(reinterpret_cast<const long long*>(d_sizes),
                                                                           reinterpret_cast<const long long*>(d_sample_ptr), S,
                                                                           d_medians, d_depth_out);
+    } else {
+        static bool attr_set = false;
+        if (!attr_set) {
+            GL_CUDA(ctx, cudaFuncSetAttribute(ic_cohort2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C2Smem)));
+            attr_set = true;
+        }
+        GL_CHECK(gl_buf_reserve(ctx, ctx->misc, 64));
+        GL_CUDA(ctx, cudaMemsetAsync(ctx->misc.p, 0, 4, ctx->stream));
+        gl_prof_scope prof(ctx, "ic_cohort2_kernel");
+        const unsigned grid = (unsigned)std::min<int64_t>((int64_t)S, (int64_t)ctx->sm_count);
+        ic_cohort2_kernel<<<grid, kC2Threads, sizeof(C2Smem), ctx->stream>>>(reinterpret_cast<const long long*>(d_sizes),
+                                                                              reinterpret_cast<const long long*>(d_sample_ptr), S, d_medians,
+                                                                              d_depth_out, static_cast<unsigned*>(ctx->misc.p));
     }
     GL_LAUNCHED(ctx, 1);
+    if (!use_v1) GL_CUDA(ctx, cudaMemcpyAsync(&ctx->cohort_fallbacks, ctx->misc.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+// how many samples of the last gl_indexcov_cohort* call took the exact fallback select instead of the bracketed path
+int gl_indexcov_cohort_fallbacks(gl_ctx* ctx, int32_t* n) {
+    if (!ctx || !n) return gl_fail(ctx, GL_EINVAL, "null argument");
+    *n = (int32_t)ctx->cohort_fallbacks;
+    return GL_OK;
+}
+
+// I1 for every sample at once (one launch): voff = all samples' linear-index virtual offsets concatenated; descriptor d
+// says reference d's n_intv[d] entries start at voff_off[d] and its n_intv[d]-1 sizes go to size_off[d] (device pointers).
+int gl_indexcov_sizes_batch_device(gl_ctx* ctx, const uint64_t* d_voff, const int64_t* d_voff_off, const int32_t* d_n_intv,
+                                   const int64_t* d_size_off, int64_t n_desc, int64_t* d_sizes) {
+    GL_CHECK(gl_use(ctx));
+    if (n_desc < 0 || (n_desc > 0 && (!d_voff || !d_voff_off || !d_n_intv || !d_size_off || !d_sizes))) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_sizes_batch_device: bad argument");
+    if (n_desc == 0) return GL_OK;
+    GL_CHECK(gl_buf_reserve(ctx, ctx->misc, 64));
+    GL_CUDA(ctx, cudaMemsetAsync(static_cast<char*>(ctx->misc.p) + 16, 0, 4, ctx->stream));
+    {
+        gl_prof_scope prof(ctx, "ic_sizes_batch_kernel");
+        ic_sizes_batch_kernel<<<(unsigned)((n_desc * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const unsigned long long*>(d_voff), reinterpret_cast<const long long*>(d_voff_off), d_n_intv,
+            reinterpret_cast<const long long*>(d_size_off), n_desc, reinterpret_cast<long long*>(d_sizes), reinterpret_cast<int*>(static_cast<char*>(ctx->misc.p) + 16));
+    }
+    GL_LAUNCHED(ctx, 1);
+    int neg = 0;
+    GL_CUDA(ctx, cudaMemcpyAsync(&neg, static_cast<char*>(ctx->misc.p) + 16, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (neg) return gl_fail(ctx, GL_ERANGE, "gl_indexcov_sizes_batch: expected positive change in vOffset");   // types.go:75-77
     return GL_OK;
 }
 
@@ -592,7 +906,25 @@ int gl_indexcov_counts_batch_device(gl_ctx* ctx, const float* d_depth, const int
     if (n_seg == 0) return GL_OK;
     {
         gl_prof_scope prof(ctx, "ic_counts_kernel");
-        ic_counts_kernel<<<(unsigned)n_seg, 256, 0, ctx->stream>>>(d_depth, reinterpret_cast<const long long*>(d_seg_ptr),
+        ic_counts_kernel<<<(unsigned)n_seg, 256, 0, ctx->stream>>>(d_depth, reinterpret_cast<const long long*>(d_seg_ptr), nullptr,
+                                                                   reinterpret_cast<const long long*>(d_longest), n_seg, d_counts70,
+                                                                   reinterpret_cast<long long*>(d_bins4));
+    }
+    GL_LAUNCHED(ctx, 1);
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+// I4+I5 for arbitrary slices of a device-resident depth array: every (chromosome, sample) pair of a cohort in one launch
+int gl_indexcov_counts_segs_device(gl_ctx* ctx, const float* d_depth, const int64_t* d_seg_start, const int64_t* d_seg_len,
+                                   const int64_t* d_longest, int32_t n_seg, int32_t* d_counts70, int64_t* d_bins4) {
+    GL_CHECK(gl_use(ctx));
+    if (n_seg < 0 || !d_seg_start || !d_seg_len || !d_counts70 || !d_bins4) return gl_fail(ctx, GL_EINVAL, "gl_indexcov_counts_segs_device: bad argument");
+    if (n_seg == 0) return GL_OK;
+    {
+        gl_prof_scope prof(ctx, "ic_counts_kernel");
+        ic_counts_kernel<<<(unsigned)n_seg, 256, 0, ctx->stream>>>(d_depth, reinterpret_cast<const long long*>(d_seg_start),
+                                                                   reinterpret_cast<const long long*>(d_seg_len),
                                                                    reinterpret_cast<const long long*>(d_longest), n_seg, d_counts70,
                                                                    reinterpret_cast<long long*>(d_bins4));
     }

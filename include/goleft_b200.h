@@ -331,6 +331,14 @@ int  gl_indexcov_cohort(gl_ctx* ctx, const int64_t* sizes, const int64_t* sample
                         double* medians, float* depth_out);
 int  gl_indexcov_cohort_device(gl_ctx* ctx, const int64_t* d_sizes, const int64_t* d_sample_ptr, int32_t S,
                                double* d_medians, float* d_depth_out);
+/* how many samples of the last gl_indexcov_cohort* call needed the exact fallback select (heavy ties / overlapping
+ * brackets) instead of the two-pass bracketed path; the results are identical either way */
+int  gl_indexcov_cohort_fallbacks(gl_ctx* ctx, int32_t* n);
+/* I1 for a whole cohort in ONE launch, on device-resident data: d_voff = every sample's linear-index virtual offsets
+ * concatenated; descriptor d (one per sample x reference with >= 2 entries) = its n_intv[d] entries start at voff_off[d] and
+ * its n_intv[d]-1 sizes go to size_off[d].  GL_ERANGE on a negative delta (types.go:75-77). */
+int  gl_indexcov_sizes_batch_device(gl_ctx* ctx, const uint64_t* d_voff, const int64_t* d_voff_off, const int32_t* d_n_intv,
+                                    const int64_t* d_size_off, int64_t n_desc, int64_t* d_sizes);
 /* I4: 70-slot histogram of one depth array (counts += ..., like the reference's counts[...]++). */
 int  gl_indexcov_counts(gl_ctx* ctx, const float* depth, int64_t n, int32_t counts[GL_INDEXCOV_SLOTS]);
 /* I5: counter.count over depth[0..n) with `longest` tiles expected; out4 += {out, low, hi, in}. */
@@ -341,6 +349,10 @@ int  gl_indexcov_counts_batch(gl_ctx* ctx, const float* depth, const int64_t* se
                               int32_t n_seg, int32_t* counts70, int64_t* bins4);
 int  gl_indexcov_counts_batch_device(gl_ctx* ctx, const float* d_depth, const int64_t* d_seg_ptr,
                                      const int64_t* d_longest, int32_t n_seg, int32_t* d_counts70, int64_t* d_bins4);
+/* the same for arbitrary slices [seg_start[k], seg_start[k] + seg_len[k]) of a device-resident depth array: every
+ * (chromosome, sample) pair of a cohort in one launch, straight from gl_indexcov_cohort_device's output */
+int  gl_indexcov_counts_segs_device(gl_ctx* ctx, const float* d_depth, const int64_t* d_seg_start, const int64_t* d_seg_len,
+                                    const int64_t* d_longest, int32_t n_seg, int32_t* d_counts70, int64_t* d_bins4);
 /* I6: the "%.3g" of every value (the bed.gz row writer, indexcov.go:678-680,1038-1048): 10-byte tokens,
  * bytes [0..len) = text, byte 9 = len; len 0 means the magnitude is outside [1e-15,1e15) and the host formats it. */
 int  gl_format_g3(gl_ctx* ctx, const float* vals, int64_t n, uint8_t* tokens);

@@ -73,6 +73,59 @@ def test_cohort_medians_and_depths(ctx):
             assert (dep[ptr[i]:ptr[i + 1]] == 0).all()
 
 
+def test_cohort_large_samples_bracketed_path_and_fallbacks(ctx):
+    """n > 8192 takes the sorted-sample bracketing (two passes); heavy ties / odd shapes must fall back and still be exact"""
+    rng = np.random.default_rng(14)
+    rows = [synth_cohort(rng, 1, n)[0] for n in (8193, 20_000, 191_000, 191_000, 250_000)]
+    rows.append(np.sort(synth_cohort(rng, 1, 60_000)[0]))                       # ascending input (strided sample = quantiles)
+    rows.append(np.sort(synth_cohort(rng, 1, 60_000)[0])[::-1].copy())          # descending
+    rows.append(rng.choice(np.array([0, 5, 7, 1_000_000_007], np.int64), 100_000))    # four distinct values: ties everywhere
+    rows.append(np.full(30_000, 123_456_789, np.int64))                         # all ties
+    rows.append(np.zeros(50_000, np.int64))                                     # all zero: median 0
+    heavy = synth_cohort(rng, 1, 120_000)[0]
+    heavy[::3] *= 40                                                            # a third of the tiles 40x larger: the weighted median sits near the cap
+    rows.append(heavy)
+    cram = np.repeat(rng.integers(10_000, 90_000, 400), 300).astype(np.int64)   # CRAM pseudo-tiles: long constant runs (crai.go:56-127)
+    rows.append(cram)
+    lens = [r.size for r in rows]
+    sizes = np.concatenate(rows)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    med, dep = ctx.indexcov_cohort(sizes, ptr)
+    for i, r in enumerate(rows):
+        m = orc.ic_median(r)
+        assert med[i] == float(m), (i, med[i], m)
+        if m != 0:
+            assert np.array_equal(dep[ptr[i]:ptr[i + 1]].view(np.uint32), orc.ic_normalize(r, float(m)).view(np.uint32)), i
+        else:
+            assert (dep[ptr[i]:ptr[i + 1]] == 0).all()
+    fb = ctx.indexcov_cohort_fallbacks()
+    assert 1 <= fb <= 6, fb                                                     # the tie-heavy samples fall back, the realistic ones do not
+    # realistic samples only: the bracketed path must carry all of them
+    real = [synth_cohort(rng, 1, 189_000)[0] for _ in range(24)]
+    ptr2 = np.concatenate([[0], np.cumsum([r.size for r in real])]).astype(np.int64)
+    med2, _ = ctx.indexcov_cohort(np.concatenate(real), ptr2, want_depth=False)
+    assert [float(orc.ic_median(r)) for r in real] == med2.tolist()
+    assert ctx.indexcov_cohort_fallbacks() == 0
+
+
+def test_sizes_batch_equals_per_sample(ctx):
+    rng = np.random.default_rng(15)
+    voffs, voff_off, n_intv, size_off, exp = [], [], [], [], []
+    at = so = 0
+    for s in range(7):
+        for r in range(int(rng.integers(1, 30))):
+            k = int(rng.choice([0, 1, 2, 3, 50, 4000]))
+            v = np.cumsum(rng.integers(0, 1 << 30, k)).astype(np.uint64)
+            voffs.append(v)
+            if k >= 2:
+                voff_off.append(at); n_intv.append(k); size_off.append(so)
+                exp.append(np.diff(v.astype(np.int64)))
+                so += k - 1
+            at += k
+    got = ctx.indexcov_sizes_batch(np.concatenate(voffs), voff_off, n_intv, size_off, so)
+    assert np.array_equal(got, np.concatenate(exp))
+
+
 def test_counts_batch(ctx):
     rng = np.random.default_rng(5)
     n_seg = 40
