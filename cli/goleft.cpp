@@ -1158,7 +1158,9 @@ static int cmd_depthwed(int argc, char** argv) {
     std::vector<std::string> chroms;
     std::map<std::string, int> chrom_id;
     std::vector<int32_t> starts, ends, cid;
-    std::vector<double> means;
+    std::vector<double> means;                       // kept only for the rare case a depth does not fit int32
+    std::vector<int32_t> depth32;                    // int(0.5 + mean), rounded where the reference rounds: at parse time (depthwed.go:103)
+    bool fits32 = true;
     size_t R = 0;
     std::string header = "#chrom\tstart\tend";
     for (size_t f = 0; f < S; f++) {
@@ -1167,13 +1169,17 @@ static int cmd_depthwed(int argc, char** argv) {
         for (const char* suf : {".gz", ".bed", ".depth"}) if (ends_with(nm, suf)) nm = nm.substr(0, nm.size() - strlen(suf));
         header += "\t" + nm;
         std::vector<std::string> lines = read_lines(ap.positional[f], true);
-        if (f == 0) { R = lines.size(); means.resize(S * R); }
+        if (f == 0) { R = lines.size(); means.resize(S * R); depth32.resize(S * R); }
         else if (lines.size() != R) fatal(2, "panic: not all files have same number of records");
         for (size_t r = 0; r < R; r++) {
             const std::string& ln = lines[r];
             size_t t1 = ln.find('\t'), t2 = ln.find('\t', t1 + 1), t3 = ln.find('\t', t2 + 1);
             if (t1 == std::string::npos || t2 == std::string::npos || t3 == std::string::npos) fatal(1, "bad line in %s: %s", ap.positional[f].c_str(), ln.c_str());
-            means[f * R + r] = strtod(ln.c_str() + t3 + 1, nullptr);
+            const double dep = strtod(ln.c_str() + t3 + 1, nullptr);
+            means[f * R + r] = dep;
+            const double rd = 0.5 + dep;                                            // Go: int(0.5 + dep) truncates toward zero
+            if (!(rd > -2147483648.0 && rd < 2147483648.0)) fits32 = false;
+            else depth32[f * R + r] = (int32_t)rd;
             if (f == 0) {
                 std::string c = ln.substr(0, t1);
                 auto it = chrom_id.find(c);
@@ -1189,16 +1195,28 @@ static int cmd_depthwed(int argc, char** argv) {
     gl_ctx* ctx = nullptr;
     if (gl_ctx_create(0, &ctx) != GL_OK) fatal(1, "goleft depthwed: %s", gl_last_error(nullptr));
     std::vector<int32_t> os(R), oe(R), oc(R);
-    std::vector<int64_t> out(R * S);
+    std::vector<int64_t> out;
+    std::vector<int32_t> out32;
     int64_t n_out = 0;
-    glck(ctx, gl_depthwed_aggregate(ctx, means.data(), (int32_t)S, (int64_t)R, starts.data(), ends.data(), cid.data(), sz, os.data(), oe.data(),
-                                    oc.data(), out.data(), (int64_t)R, &n_out), "gl_depthwed_aggregate");
+    bool have32 = false;
+    if (fits32) {                                    // 4 B in + 4 B out per cell; a group sum beyond int32 falls through to the 64-bit path
+        out32.resize(R * S);
+        const int rc = gl_depthwed_aggregate_i32(ctx, depth32.data(), (int32_t)S, (int64_t)R, starts.data(), ends.data(), cid.data(), sz, os.data(),
+                                                 oe.data(), oc.data(), out32.data(), (int64_t)R, &n_out);
+        if (rc == GL_OK) have32 = true;
+        else if (!(rc == GL_ERANGE && n_out == -1)) glck(ctx, rc, "gl_depthwed_aggregate_i32");
+    }
+    if (!have32) {
+        out.resize(R * S);
+        glck(ctx, gl_depthwed_aggregate(ctx, means.data(), (int32_t)S, (int64_t)R, starts.data(), ends.data(), cid.data(), sz, os.data(), oe.data(),
+                                        oc.data(), out.data(), (int64_t)R, &n_out), "gl_depthwed_aggregate");
+    }
     std::string row;
     char num[32];
     for (int64_t g = 0; g < n_out; g++) {
         row = chroms[oc[g]];
         snprintf(num, sizeof num, "\t%d\t%d", os[g], oe[g]); row += num;
-        for (size_t s = 0; s < S; s++) { snprintf(num, sizeof num, "\t%lld", (long long)out[(size_t)g * S + s]); row += num; }
+        for (size_t s = 0; s < S; s++) { snprintf(num, sizeof num, "\t%lld", have32 ? (long long)out32[(size_t)g * S + s] : (long long)out[(size_t)g * S + s]); row += num; }
         row += "\n";
         fwrite(row.data(), 1, row.size(), stdout);
     }

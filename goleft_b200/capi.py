@@ -111,6 +111,10 @@ _proto("gl_bincount_i32", C.c_int, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, _v
 _proto("gl_depthwed_aggregate", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp,
        C.c_int64, _i64p)
 _proto("gl_depthwed_aggregate_device", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp)
+_proto("gl_depthwed_aggregate_i32", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_depthwed_aggregate_i32_device", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, _vp)
+_proto("gl_allgather_device_async", C.c_int, _vp, _vp, _vp, C.c_int64)
+_proto("gl_comm_wait", C.c_int, _vp)
 _proto("gl_comm_unique_id", C.c_int, _vp)
 _proto("gl_comm_init", C.c_int, _vp, _vp, C.c_int, C.c_int)
 _proto("gl_comm_destroy", C.c_int, _vp)
@@ -834,6 +838,31 @@ class Ctx:
                                            _ptr(o_s), _ptr(o_e), _ptr(o_c), _ptr(out), cap, C.byref(n)))
         k = n.value
         return o_s[:k], o_e[:k], o_c[:k], out[:k]
+
+    def depthwed_aggregate_i32(self, depth: np.ndarray, starts, ends, chrom_id, size: int):
+        """int32 form: depth = int(0.5 + mean) per (sample, row), as the reference rounds at parse time (depthwed.go:103)"""
+        depth = np.ascontiguousarray(depth, np.int32)
+        S, R = depth.shape
+        starts, ends, chrom_id = _as(starts, np.int32), _as(ends, np.int32), _as(chrom_id, np.int32)
+        cap = max(R, 1)
+        o_s, o_e, o_c = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32)
+        out = np.empty((cap, S), np.int32)
+        n = C.c_int64(0)
+        self._ck(lib.gl_depthwed_aggregate_i32(self.h, _ptr(depth), S, R, _ptr(starts), _ptr(ends), _ptr(chrom_id), size,
+                                               _ptr(o_s), _ptr(o_e), _ptr(o_c), _ptr(out), cap, C.byref(n)))
+        k = n.value
+        return o_s[:k], o_e[:k], o_c[:k], out[:k]
+
+    def depthwed_aggregate_i32_device(self, d_depth: DevBuf, S: int, R: int, d_grp: Optional[DevBuf], g_begin: int, g_end: int,
+                                      d_out_ptr: int, d_overflow: DevBuf):
+        self._ck(lib.gl_depthwed_aggregate_i32_device(self.h, d_depth.ptr, S, R, d_grp.ptr if d_grp is not None else None, g_begin, g_end,
+                                                      d_out_ptr, d_overflow.ptr))
+
+    def allgather_device_async(self, send_ptr: int, recv_ptr: int, nbytes: int):
+        self._ck(lib.gl_allgather_device_async(self.h, send_ptr, recv_ptr, nbytes))
+
+    def comm_wait(self):
+        self._ck(lib.gl_comm_wait(self.h))
 
     # ---- multi-GPU
     def comm_init(self, id128: bytes, rank: int, world: int):

@@ -101,4 +101,28 @@ int gl_allgather_device(gl_ctx* ctx, const void* d_send, void* d_recv, int64_t b
     return GL_OK;
 }
 
+// The same, ASYNCHRONOUS on the ctx's communication stream: the gather starts when everything queued on the compute stream
+// so far has finished (so the block an earlier kernel wrote is complete) and runs beside later kernels — the depthwed
+// matrix is gathered chunk by chunk while the next chunk is still being aggregated.  gl_comm_wait() joins.
+int gl_allgather_device_async(gl_ctx* ctx, const void* d_send, void* d_recv, int64_t bytes) {
+    GL_CHECK(gl_use(ctx));
+    if (!ctx->nccl) return gl_fail(ctx, GL_ESTATE, "gl_allgather_device_async: call gl_comm_init first");
+    if (bytes < 0 || !d_send || !d_recv) return gl_fail(ctx, GL_EINVAL, "gl_allgather_device_async: bad argument");
+    if (!ctx->comm_stream) {
+        GL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+        GL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+    }
+    GL_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->stream));
+    GL_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_comm, 0));
+    GL_NCCL(ctx, g_nccl.AllGather(d_send, d_recv, (size_t)bytes, kNcclInt8, static_cast<ncclComm_t>(ctx->nccl), ctx->comm_stream));
+    return GL_OK;
+}
+
+int gl_comm_wait(gl_ctx* ctx) {
+    GL_CHECK(gl_use(ctx));
+    if (ctx->comm_stream) GL_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
 }  // extern "C"

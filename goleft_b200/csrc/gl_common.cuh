@@ -84,6 +84,7 @@ struct gl_ctx {
     std::vector<cudaEvent_t> prof_pool;
 
     unsigned cohort_fallbacks = 0;   // ic_cohort2_kernel: samples that took the exact fallback select in the last call
+    cudaStream_t comm_stream = nullptr; cudaEvent_t ev_comm = nullptr;   // gl_allgather_device_async
     void* nccl = nullptr; // ncclComm_t when gl_comm_init was called
     int rank = 0, world = 1;
 };

@@ -193,6 +193,8 @@ int gl_ctx_destroy(gl_ctx* ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     delete ctx;
     return GL_OK;
 }

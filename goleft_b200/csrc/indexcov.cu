@@ -634,6 +634,36 @@ __global__ void __launch_bounds__(256) depthwed_kernel(const double* __restrict_
     }
 }
 
+// The same at the width BASELINE budgets (4 B in + 4 B out per cell): the reference rounds when it PARSES a line
+// (depthwed.go:103 d.depth = int(0.5 + dep)), so the matrix that travels is int32.  Group sums are taken in 64 bits; a sum
+// that does not fit int32 raises *overflow and the caller reruns on the int64 path.  Groups [g_begin, g_end) only: the
+// caller walks the rows in chunks so that the all-gather of one chunk overlaps the aggregation of the next.
+__global__ void __launch_bounds__(256) depthwed_i32_kernel(const int* __restrict__ depth, int S, long long R, const long long* __restrict__ grp,
+                                                          long long g_begin, long long g_end, int simple, int* __restrict__ out,
+                                                          int* __restrict__ overflow) {
+    __shared__ int s_t[32][33];
+    const long long g0 = g_begin + (long long)blockIdx.x * 32;
+    const int s0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    for (int k = ty; k < 32; k += 8) {                             // k: sample inside the tile, tx: group
+        const int s = s0 + k;
+        const long long g = g0 + tx;
+        long long acc = 0;
+        if (s < S && g < g_end) {
+            const long long a = simple ? g : grp[g], b = simple ? g + 1 : grp[g + 1];
+            for (long long r = a; r < b; r++) acc += depth[(size_t)s * R + r];
+            if (acc > 2147483647ll || acc < -2147483648ll) *overflow = 1;
+        }
+        s_t[k][tx] = (int)acc;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {                             // k: group inside the tile, tx: sample
+        const long long g = g0 + k;
+        const int s = s0 + tx;
+        if (s < S && g < g_end) out[(size_t)(g - g_begin) * S + s] = s_t[tx][k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ I6
 // float32 -> the bytes of Go's fmt "%.3g" (== C printf "%.3g" of the same value), exactly: the three significant
 // digits come from integer arithmetic on mantissa * 10^k (128-bit), rounded half-to-even on the exact binary
@@ -1133,6 +1163,65 @@ int gl_depthwed_aggregate_device(gl_ctx* ctx, const double* d_means, int32_t S, 
     GL_LAUNCHED(ctx, 1);
     GL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GL_OK;
+}
+
+// int32 form (depthwed.go:103 rounds at parse time): d_depth S x R sample-major; the groups [g_begin, g_end) of d_grp (NULL:
+// one row per output line) go to d_out[(g - g_begin) * S + s].  ASYNCHRONOUS on the ctx stream (gl_sync / a later
+// synchronous call waits); *d_overflow (device int, zeroed by the caller) is set when a group sum does not fit int32.
+int gl_depthwed_aggregate_i32_device(gl_ctx* ctx, const int32_t* d_depth, int32_t S, int64_t R, const int64_t* d_grp, int64_t g_begin,
+                                     int64_t g_end, int32_t* d_out, int32_t* d_overflow) {
+    GL_CHECK(gl_use(ctx));
+    if (S <= 0 || R < 0 || g_begin < 0 || g_end < g_begin || !d_depth || !d_out || !d_overflow)
+        return gl_fail(ctx, GL_EINVAL, "gl_depthwed_aggregate_i32_device: bad argument");
+    if (g_end == g_begin) return GL_OK;
+    dim3 grid((unsigned)((g_end - g_begin + 31) / 32), (unsigned)((S + 31) / 32));
+    {
+        gl_prof_scope prof(ctx, "depthwed_i32_kernel");
+        depthwed_i32_kernel<<<grid, 256, 0, ctx->stream>>>(d_depth, S, R, reinterpret_cast<const long long*>(d_grp), g_begin, g_end, d_grp ? 0 : 1,
+                                                           d_out, d_overflow);
+    }
+    GL_LAUNCHED(ctx, 1);
+    return GL_OK;
+}
+
+// host form: depth S x R int32 (already int(0.5 + mean)); GL_ERANGE with *n_out set when out_cap is too small, and
+// GL_ERANGE with *n_out = -1 when a group sum overflows int32 (use gl_depthwed_aggregate)
+int gl_depthwed_aggregate_i32(gl_ctx* ctx, const int32_t* depth, int32_t S, int64_t R, const int32_t* starts, const int32_t* ends,
+                              const int32_t* chrom_id, int64_t size, int32_t* out_start, int32_t* out_end, int32_t* out_chrom,
+                              int32_t* out, int64_t out_cap, int64_t* n_out) {
+    GL_CHECK(gl_use(ctx));
+    if (S <= 0 || R < 0 || !depth || !starts || !ends || !chrom_id || !n_out || size <= 0)
+        return gl_fail(ctx, GL_EINVAL, "gl_depthwed_aggregate_i32: bad argument");
+    std::vector<int64_t> grp;
+    const int64_t ng = depthwed_groups(R, starts, ends, chrom_id, size, grp);
+    *n_out = ng;
+    if (ng > out_cap) return gl_fail(ctx, GL_ERANGE, "gl_depthwed_aggregate_i32: %lld rows > cap %lld", (long long)ng, (long long)out_cap);
+    if (ng == 0) return GL_OK;
+    for (int64_t g = 0; g < ng; g++) {
+        out_start[g] = starts[grp[g]];
+        out_end[g] = ends[grp[g + 1] - 1];
+        out_chrom[g] = chrom_id[grp[g]];
+    }
+    gl_buf bm, bg, bo, bf;
+    GL_CHECK(dev_tmp(ctx, bm, (size_t)S * R * 4));
+    GL_CHECK(dev_tmp(ctx, bg, (size_t)(ng + 1) * 8));
+    GL_CHECK(dev_tmp(ctx, bo, (size_t)ng * S * 4));
+    GL_CHECK(dev_tmp(ctx, bf, 16));
+    int rc = GL_OK, ovf = 0;
+    do {
+        if (cudaMemcpyAsync(bm.p, depth, (size_t)S * R * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(bg.p, grp.data(), (size_t)(ng + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemsetAsync(bf.p, 0, 4, ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_depthwed_aggregate_i32: H2D failed"); break; }
+        rc = gl_depthwed_aggregate_i32_device(ctx, static_cast<const int32_t*>(bm.p), S, R, static_cast<const int64_t*>(bg.p), 0, ng,
+                                              static_cast<int32_t*>(bo.p), static_cast<int32_t*>(bf.p));
+        if (rc != GL_OK) break;
+        if (cudaMemcpyAsync(out, bo.p, (size_t)ng * S * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(&ovf, bf.p, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = gl_fail(ctx, GL_ECUDA, "gl_depthwed_aggregate_i32: D2H failed"); break; }
+    } while (0);
+    cudaFree(bm.p); cudaFree(bg.p); cudaFree(bo.p); cudaFree(bf.p);
+    if (rc == GL_OK && ovf) { *n_out = -1; return gl_fail(ctx, GL_ERANGE, "gl_depthwed_aggregate_i32: a group sum does not fit int32"); }
+    return rc;
 }
 
 int gl_depthwed_aggregate(gl_ctx* ctx, const double* means, int32_t S, int64_t R, const int32_t* starts, const int32_t* ends,

@@ -63,3 +63,31 @@ def depthwed_sharded(aggregate_local: Callable[[np.ndarray], np.ndarray], means:
     local = aggregate_local(means[lo:hi])
     blk = depthwed_pad_block(local, padded_width(S, world))
     return depthwed_assemble(allgather(blk), S, world)
+
+
+# ---- int32 matrix, row-chunked, gather overlapped with aggregation (BASELINE config 4: 500 samples x 6.18 M windows)
+def chunk_bounds(n_rows: int, n_chunks: int) -> List[Tuple[int, int]]:
+    n_chunks = max(1, min(n_chunks, n_rows)) if n_rows else 1
+    return [(n_rows * c // n_chunks, n_rows * (c + 1) // n_chunks) for c in range(n_chunks)]
+
+
+def depthwed_gather_overlapped(ctx, d_depth, width: int, R: int, world: int, d_local, d_all, d_overflow, n_chunks: int = 8):
+    """Every rank: aggregate its `width` sample columns chunk by chunk (depthwed_i32_kernel on the compute stream) and
+    all-gather each finished chunk on the communication stream while the next one is being aggregated.
+    d_all layout: [chunk][rank][rows of the chunk][width] int32.  Returns after both streams have drained."""
+    for g0, g1 in chunk_bounds(R, n_chunks):
+        ctx.depthwed_aggregate_i32_device(d_depth, width, R, None, g0, g1, d_local.ptr + g0 * width * 4, d_overflow)
+        ctx.allgather_device_async(d_local.ptr + g0 * width * 4, d_all.ptr + g0 * width * 4 * world, (g1 - g0) * width * 4)
+    ctx.comm_wait()
+
+
+def depthwed_assemble_chunked(flat: np.ndarray, R: int, width: int, world: int, S: int, n_chunks: int) -> np.ndarray:
+    """flat: the int32 contents of d_all -> R x S with the samples in their original order"""
+    out = np.empty((R, S), np.int32)
+    for g0, g1 in chunk_bounds(R, n_chunks):
+        base = g0 * width * world
+        for r in range(world):
+            lo, hi = shard_range(S, r, world)
+            blk = flat[base + r * (g1 - g0) * width: base + (r + 1) * (g1 - g0) * width].reshape(g1 - g0, width)
+            out[g0:g1, lo:hi] = blk[:, : hi - lo]
+    return out

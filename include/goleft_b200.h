@@ -397,6 +397,18 @@ int  gl_depthwed_aggregate(gl_ctx* ctx, const double* means, int32_t S, int64_t 
 int  gl_depthwed_aggregate_device(gl_ctx* ctx, const double* d_means, int32_t S, int64_t R, const int64_t* d_grp,
                                   int64_t n_out, int64_t* d_out);
 
+/* int32 forms — what BASELINE budgets (4 B in + 4 B out per cell): the reference rounds when it parses a line
+ * (depthwed.go:103 d.depth = int(0.5 + dep)), so the caller hands over int32 depths and the matrix that travels over NVLink is
+ * int32.  Group sums are taken in 64 bits; one that does not fit int32 makes the host form return GL_ERANGE with *n_out = -1
+ * (rerun with gl_depthwed_aggregate).  The device form does the groups [g_begin, g_end) only (so the all-gather of one row
+ * chunk can overlap the aggregation of the next), is ASYNCHRONOUS on the ctx stream, and sets *d_overflow (a device int the
+ * caller zeroed) instead. */
+int  gl_depthwed_aggregate_i32(gl_ctx* ctx, const int32_t* depth, int32_t S, int64_t R, const int32_t* starts, const int32_t* ends,
+                               const int32_t* chrom_id, int64_t size, int32_t* out_start, int32_t* out_end, int32_t* out_chrom,
+                               int32_t* out, int64_t out_cap, int64_t* n_out);
+int  gl_depthwed_aggregate_i32_device(gl_ctx* ctx, const int32_t* d_depth, int32_t S, int64_t R, const int64_t* d_grp, int64_t g_begin,
+                                      int64_t g_end, int32_t* d_out, int32_t* d_overflow);
+
 /* ------------------------------------------------------------- multi-GPU
  * One process per GPU.  The caller distributes a 128-byte NCCL unique id (rank 0 creates it).
  * The one collective on this path: an all-gather over NVLink that assembles the depthwed
@@ -406,6 +418,10 @@ int  gl_comm_init(gl_ctx* ctx, const uint8_t id128[128], int rank, int world);
 int  gl_comm_destroy(gl_ctx* ctx);
 /* all-gather equal-sized blocks that live on the device: d_recv holds world*bytes */
 int  gl_allgather_device(gl_ctx* ctx, const void* d_send, void* d_recv, int64_t bytes);
+/* asynchronous on the ctx's communication stream: starts when the work queued on the compute stream so far is done, runs
+ * beside later kernels; gl_comm_wait() joins both streams */
+int  gl_allgather_device_async(gl_ctx* ctx, const void* d_send, void* d_recv, int64_t bytes);
+int  gl_comm_wait(gl_ctx* ctx);
 
 #ifdef __cplusplus
 }

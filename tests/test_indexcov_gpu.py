@@ -188,6 +188,30 @@ def test_depthwed(ctx):
             assert np.array_equal(a, b), size
 
 
+def test_depthwed_i32(ctx):
+    """int32 form: the reference rounds at parse time (depthwed.go:103); same groups, int32 sums, overflow detected"""
+    from goleft_b200 import capi
+    rng = np.random.default_rng(8)
+    for S, R, size in [(3, 40, 1000), (17, 1000, 750), (64, 5000, 250), (5, 333, 10_000)]:
+        starts = (np.arange(R) * 250).astype(np.int32)
+        chrom = np.sort(rng.integers(0, 3, R)).astype(np.int32)
+        for c in range(3):
+            m = chrom == c
+            starts[m] -= starts[m][0] if m.any() else 0
+        ends = starts + 250
+        means = np.array([[float("%.4g" % x) for x in rng.gamma(9, 3.3, R)] for _ in range(S)])
+        depth = (0.5 + means).astype(np.int64).astype(np.int32)              # int(0.5 + dep)
+        es, ee, ec, eo = orc.depthwed(means, starts, ends, chrom, size)
+        gs, ge, gc, go = ctx.depthwed_aggregate_i32(depth, starts, ends, chrom, size)
+        assert np.array_equal(gs, es) and np.array_equal(ge, ee) and np.array_equal(gc, ec)
+        assert np.array_equal(go.astype(np.int64), eo)
+    big = np.full((2, 8), 2_000_000_000, np.int32)
+    st = (np.arange(8) * 250).astype(np.int32)
+    with pytest.raises(capi.GlError) as ei:
+        ctx.depthwed_aggregate_i32(big, st, st + 250, np.zeros(8, np.int32), 1000)
+    assert ei.value.code == capi.GL_ERANGE
+
+
 def test_format_g3_exact(ctx):
     """I6: the GPU "%.3g" tokens equal printf's for every value tried: random magnitudes, the half-way cases of
     3-digit rounding, powers of ten, denormals/huge values (host fallback), zero, inf, nan"""

@@ -116,7 +116,19 @@ def _nccl_worker(rank, world, uid, q):
         return [flat[r * blk.size:(r + 1) * blk.size].reshape(blk.shape) for r in range(world)]
 
     full = multigpu.depthwed_sharded(agg, means, rank, world, allgather)
-    q.put((rank, full))
+    # the int32, row-chunked, overlapped form (what bench.py runs at 500 x 6.18 M): one row per output line
+    S2, R2, n_chunks = 11, 5000, 4
+    lo, hi = multigpu.shard_range(S2, rank, world)
+    width = multigpu.padded_width(S2, world)
+    depth = ((np.arange(R2, dtype=np.int64)[None, :] * 7919 + np.arange(S2)[:, None] * 104729) % 1000).astype(np.int32)
+    loc = np.zeros((width, R2), np.int32)
+    loc[: hi - lo] = depth[lo:hi]
+    d_depth = c.dev_array(loc)
+    d_local, d_all, d_ovf = c.dev_empty(R2 * width * 4), c.dev_empty(R2 * width * 4 * world), c.dev_array(np.zeros(4, np.int32))
+    multigpu.depthwed_gather_overlapped(c, d_depth, width, R2, world, d_local, d_all, d_ovf, n_chunks)
+    got = multigpu.depthwed_assemble_chunked(d_all.download(np.int32, R2 * width * world), R2, width, world, S2, n_chunks)
+    ok32 = bool(np.array_equal(got, depth.T)) and int(d_ovf.download(np.int32, 1)[0]) == 0
+    q.put((rank, full, ok32))
     c.close()
 
 
@@ -133,10 +145,28 @@ def test_nccl_world2_depthwed_allgather():
     procs = [ctx.Process(target=_nccl_worker, args=(r, 2, uid, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=240) for _ in range(2))
+    got = [q.get(timeout=240) for _ in range(2)]
+    res = {g[0]: g[1] for g in got}
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
     means, starts, ends, chrom = _problem(seed=3, S=9)
     exp = orc.depthwed(means, starts, ends, chrom, 1000)[3]
     assert np.array_equal(res[0], exp) and np.array_equal(res[1], exp)
+    assert all(g[2] for g in got)                               # int32 chunked + overlapped gather, verified on every rank
+
+
+def test_chunked_assembly_layout():
+    """CPU: the [chunk][rank][rows][width] layout of the overlapped gather reassembles to R x S"""
+    S, R, world, n_chunks = 11, 103, 4, 5
+    width = multigpu.padded_width(S, world)
+    depth = (np.arange(S)[:, None] * 1000 + np.arange(R)[None, :]).astype(np.int32)
+    flat = np.zeros(R * width * world, np.int32)
+    for g0, g1 in multigpu.chunk_bounds(R, n_chunks):
+        for r in range(world):
+            lo, hi = multigpu.shard_range(S, r, world)
+            blk = np.zeros((g1 - g0, width), np.int32)
+            blk[:, : hi - lo] = depth[lo:hi, g0:g1].T
+            o = g0 * width * world + r * (g1 - g0) * width
+            flat[o:o + blk.size] = blk.ravel()
+    assert np.array_equal(multigpu.depthwed_assemble_chunked(flat, R, width, world, S, n_chunks), depth.T)
