@@ -44,6 +44,7 @@ def main():
         ctx.flush_l2(); ctx.timer_start()
         ctx.indexcov_cohort_device(d_sizes, d_ptr, S, d_med, d_dep)
         ms.append(ctx.timer_stop_ms())
+    fallbacks = ctx.indexcov_cohort_fallbacks()
     med = d_med.download(np.float64, S)
     from oracle import loader as orc                               # spot check against the oracle (the checker only)
     for k in (0, S // 2, S - 1):
@@ -56,7 +57,9 @@ def main():
     out["indexcov_cohort"] = {"samples": S, "tiles": T, "ms": float(np.mean(ms)), "tile_samples_per_s": S * T / (np.mean(ms) * 1e-3),
                               "alg_bytes": alg, "achieved_gbs": alg / (np.mean(ms) * 1e-3) / 1e9,
                               "frac_of_measured_peak": alg / (np.mean(ms) * 1e-3) / 1e9 / peak,
-                              "note": "min/max pass + two range-adaptive histogram selects (~3 levels x 2 passes each) + total + normalise, all but the first pass from L2",
+                              "kernel": "ic_cohort_kernel (v1: range-adaptive histogram selects, ~17 passes)" if os.environ.get("GL_COHORT_V1") else
+                                        "ic_cohort2_kernel (sorted-sample brackets: one counting/collecting pass + one normalise pass)",
+                              "fallback_samples": fallbacks,
                               "cpu_port_ms_per_sample_1thread": cpu_per_sample * 1e3}
     for b in (d_sizes, d_ptr, d_med, d_dep):
         b.free()
@@ -80,6 +83,24 @@ def main():
     out["depthwed"] = {"samples": S2, "rows": R, "ms": float(np.mean(ms)), "cells_per_s": S2 * R / (np.mean(ms) * 1e-3),
                        "alg_bytes": alg, "achieved_gbs": alg / (np.mean(ms) * 1e-3) / 1e9,
                        "frac_of_measured_peak": alg / (np.mean(ms) * 1e-3) / 1e9 / peak}
+    # ---- depthwed, int32 in / int32 out (the form that travels over NVLink)
+    d_i32 = ctx.dev_empty(S2 * R * 4)
+    dep32 = (0.5 + means).astype(np.int32)
+    for k in range(S2):
+        capi.lib.gl_memcpy_h2d(ctx.h, d_i32.ptr + k * R * 4, dep32.ctypes.data, R * 4)
+    d_o32, d_ovf = ctx.dev_empty(S2 * R * 4), ctx.dev_array(np.zeros(4, np.int32))
+    ctx.depthwed_aggregate_i32_device(d_i32, S2, R, None, 0, R, d_o32.ptr, d_ovf); ctx.sync()
+    ms = []
+    for _ in range(args.reps):
+        ctx.flush_l2(); ctx.timer_start()
+        ctx.depthwed_aggregate_i32_device(d_i32, S2, R, None, 0, R, d_o32.ptr, d_ovf)
+        ms.append(ctx.timer_stop_ms())
+    got = d_o32.download(np.int32, S2 * 1000).reshape(1000, S2)
+    assert np.array_equal(got[:, 0], dep32[:1000]) and int(d_ovf.download(np.int32, 1)[0]) == 0
+    alg = S2 * R * 8
+    out["depthwed_i32"] = {"samples": S2, "rows": R, "ms": float(np.mean(ms)), "cells_per_s": S2 * R / (np.mean(ms) * 1e-3),
+                           "alg_bytes": alg, "achieved_gbs": alg / (np.mean(ms) * 1e-3) / 1e9,
+                           "frac_of_measured_peak": alg / (np.mean(ms) * 1e-3) / 1e9 / peak}
     print(json.dumps(out))
     ctx.close()
 
