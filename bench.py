@@ -512,9 +512,12 @@ def main():
         x_res_k, _ = kernel_times(5, one_resident)
         x_i32 = timed_dev(one_int32, n_x)
         x_i32_k, _ = kernel_times(5, one_int32)
-        ctx.depth_set_path(2)
+        ctx.depth_set_path(4)
         x_gen = timed_dev(one_int32, max(3, n_x // 2))
         x_gen_k, _ = kernel_times(3, one_int32)
+        ctx.depth_set_path(2)
+        x_hbm = timed_dev(one_int32, max(3, n_x // 2))
+        x_hbm_k, _ = kernel_times(3, one_int32)
         ctx.depth_set_path(0)
         x_e2e_text = timed_host(lambda: ctx.depth_bed_contig(nm, L, w["h_s"], w["h_e"], W, MINCOV, MAXMEAN, STEP, out=(o_hd, o_ca), raw=True), n_x)
         x_e2e_p8 = timed_host(lambda: ctx.depth_bed_contig_packed8(nm, L, h8[0], h8[1], h8[2], W, MINCOV, MAXMEAN, STEP, out=(o_hd, o_ca), raw=True), n_x)
@@ -527,7 +530,10 @@ def main():
                   "resident_int32": {"ms": x_i32, "value": L / x_i32 / 1e3, "kernel_ms": x_i32_k,
                                      "note": "plain int32 (start,end) device arrays: K_index + K_fused + K_gather"},
                   "general_path": {"ms": x_gen, "value": L / x_gen / 1e3, "kernel_ms": x_gen_k,
-                                   "note": "HBM difference array: memset + K_scatter + K_super + K_scan + K_gather"},
+                                   "note": "bucketed events (any order, any segment length): K_evcount + K_evscan + K_evscatter + K_evtile + K_gather"},
+                  "hbm_difference_array_path": {"ms": x_hbm, "value": L / x_hbm / 1e3, "kernel_ms": x_hbm_k,
+                                                "note": "the pipeline north_star sketches, on request (gl_depth_set_path(2)): memset + K_scatter "
+                                                        "(red.global) + K_super + K_scan + K_gather"},
                   "e2e_text_int32": {"ms": x_e2e_text, "value": L / x_e2e_text / 1e3, "h2d_bytes": 8 * w["nseg"],
                                      "call": "gl_depth_bed_contig (what `e2e` times, on this contig alone)"},
                   "e2e_text_packed8_words": {"ms": x_e2e_p8, "value": L / x_e2e_p8 / 1e3, "h2d_bytes": w["p8_bytes"],

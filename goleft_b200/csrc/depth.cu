@@ -640,6 +640,148 @@ __global__ void __launch_bounds__(kScanThreads, 4) depth_scan_kernel(const ScanP
     flush_max(p, acc_max);
 }
 
+// ================================================================================================
+// GENERAL path, version 2 ("bucketed events"): any order, any segment length, no difference array in HBM.
+// A segment is two events, +1 at its (clipped) start and -1 at its (clipped) end; an event belongs to the 4096-base
+// tile it falls in.  K_evcount counts starts and ends per tile (warp-aggregated reds), K_evscan turns the counts into
+// bucket offsets and into the depth carried into every tile (running starts - ends), K_evscatter writes each event as
+// 16 bits (position in the tile | sign) into its tile's bucket, K_evtile builds the tile's difference array in shared
+// memory from its bucket (coalesced 2-byte reads, shared-memory atomics) and runs the tile core.
+// Bytes: 8 B/segment read twice, 4 B/segment written and read once — against 8 B/base for the HBM difference array.
+// ================================================================================================
+__device__ __forceinline__ void ev_clip(int s, int e, int rs, int re, int& a, int& b, bool& live) {
+    a = max(s, rs) - rs;
+    b = min(e, re) - rs;
+    live = a < b;
+}
+
+template <bool kScatter>
+__global__ void __launch_bounds__(256) depth_events_kernel(const int* __restrict__ start, const int* __restrict__ end, long long n, int rs, int re,
+                                                          int num_tiles, int* __restrict__ tile_starts, int* __restrict__ tile_ends,
+                                                          const unsigned* __restrict__ bucket_off, unsigned* __restrict__ cursor,
+                                                          unsigned short* __restrict__ events) {
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int lane = threadIdx.x & 31;
+    int s[4], e[4];
+    int cnt = 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(start) | reinterpret_cast<uintptr_t>(end)) & 15) == 0;
+    if (i0 + 3 < n && vec) {
+        const int4 a4 = ld_stream_int4(reinterpret_cast<const int4*>(start + i0));
+        const int4 b4 = ld_stream_int4(reinterpret_cast<const int4*>(end + i0));
+        s[0] = a4.x; s[1] = a4.y; s[2] = a4.z; s[3] = a4.w;
+        e[0] = b4.x; e[1] = b4.y; e[2] = b4.z; e[3] = b4.w;
+        cnt = 4;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (i0 + j < n) { s[j] = start[i0 + j]; e[j] = end[i0 + j]; cnt = j + 1; }
+    }
+    if (!kScatter) {
+        // per-tile start / end counts; sorted input puts a thread's (and most of a warp's) events in one or two tiles
+        int tS = 0, cS = 0, tE = 0, cE = 0;
+        bool uni = true;
+        int ta_[4], tb_[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            ta_[j] = tb_[j] = -1;
+            if (j < cnt) {
+                int a, b; bool live;
+                ev_clip(s[j], e[j], rs, re, a, b, live);
+                if (live) {
+                    const int ta = a >> kTileShift, tb = b >> kTileShift;          // tb == num_tiles: an end on the region end, no event
+                    ta_[j] = ta; tb_[j] = tb < num_tiles ? tb : -1;
+                    if (cS == 0) { tS = ta; cS = 1; } else if (ta == tS) cS++; else uni = false;
+                    if (tb_[j] >= 0) { if (cE == 0) { tE = tb; cE = 1; } else if (tb == tE) cE++; else uni = false; }
+                }
+            }
+        }
+        if (!uni) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { if (ta_[j] >= 0) atomicAdd(tile_starts + ta_[j], 1); if (tb_[j] >= 0) atomicAdd(tile_ends + tb_[j], 1); }
+            cS = 0; cE = 0;
+        }
+        warp_tile_add(tile_starts, tS, cS, 1, lane);
+        warp_tile_add(tile_ends, tE, cE, 1, lane);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int a = 0, b = 0; bool live = false;
+            if (j < cnt) ev_clip(s[j], e[j], rs, re, a, b, live);
+            // two events per live segment; lanes whose event falls in the same tile share one cursor atomic
+#pragma unroll
+            for (int which = 0; which < 2; which++) {
+                const int pos = which ? b : a;
+                const int t = pos >> kTileShift;
+                const bool on = live && t < num_tiles;
+                const unsigned grp = __match_any_sync(kFull, on ? t : -1 - lane);   // lanes without an event are alone in their group
+                if (on) {
+                    const int leader = __ffs(grp) - 1;
+                    unsigned base = 0;
+                    if (lane == leader) base = atomicAdd(cursor + t, (unsigned)__popc(grp));
+                    base = __shfl_sync(grp, base, leader);
+                    const unsigned slot = bucket_off[t] + base + (unsigned)__popc(grp & ((1u << lane) - 1u));
+                    events[slot] = (unsigned short)((pos & (kTile - 1)) | (which << 15));
+                }
+            }
+        }
+    }
+}
+
+// bucket_off[t] = events in tiles < t; carry[t] = (starts - ends) in tiles < t = the depth carried into tile t.  One CTA.
+__global__ void __launch_bounds__(1024) depth_evscan_kernel(const int* __restrict__ tile_starts, const int* __restrict__ tile_ends, int num_tiles,
+                                                           unsigned* __restrict__ bucket_off, int* __restrict__ carry) {
+    __shared__ long long s_w[32];
+    __shared__ long long s_c[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_c[0] = 0; s_c[1] = 0; }
+    __syncthreads();
+    for (int base = 0; base <= num_tiles; base += 1024) {
+        const int i = base + tid;
+        const int st = i < num_tiles ? tile_starts[i] : 0, en = i < num_tiles ? tile_ends[i] : 0;
+        // pack both scans in one 64-bit lane: events in the high word, net depth (can be negative inside) in the low word
+        long long v = ((long long)(st + en) << 32) + (long long)(st - en);
+        long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += y; }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        long long wb = 0;
+        for (int k = 0; k < warp; k++) wb += s_w[k];
+        const long long tot = s_c[0] + wb + inc - v;                 // exclusive
+        if (i <= num_tiles) {
+            const long long lo = (long long)(int)(tot & 0xffffffffll);   // low word, sign-extended
+            const long long hi = (tot - lo) >> 32;
+            bucket_off[i] = (unsigned)hi;
+            carry[i] = (int)lo;
+        }
+        __syncthreads();
+        if (tid == 1023) s_c[0] = s_c[0] + wb + inc;
+        __syncthreads();
+    }
+}
+
+// K_evtile: one CTA per tile: zero 16 KB, the tile's events into shared memory, tile core
+__global__ void __launch_bounds__(kScanThreads, 4) depth_evtile_kernel(const ScanParams p, const unsigned short* __restrict__ events,
+                                                                       const unsigned* __restrict__ bucket_off, const int* __restrict__ carry) {
+    __shared__ __align__(16) int s_tile[kTile];
+    __shared__ __align__(16) int s_depth[kTile];
+    __shared__ int s_carry[kWarps];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);
+    if (tid < kWarps) s_carry[tid] = tid == 0 ? carry[tile] : 0;
+    const unsigned lo = bucket_off[tile], hi = bucket_off[tile + 1];
+    __syncthreads();
+    for (unsigned i = lo + tid; i < hi; i += kScanThreads) {
+        const unsigned ev = events[i];
+        atomicAdd(s_tile + swz_elem((int)(ev & (kTile - 1))), (ev >> 15) ? -1 : 1);
+    }
+    __syncthreads();
+    int acc_max = 0;
+    tile_core<16, kWarps, false>(p, s_tile, s_depth, s_carry, tile, acc_max);
+    flush_max(p, acc_max);
+}
+
 // FUSED path, K_fused: build each tile's difference array in shared memory straight from the segments.
 // Persistent CTAs (tile += gridDim.x), software-pipelined two tiles deep so that no CTA ever waits on
 // a dependent global load chain: while tile n runs its core, the segments of tile n+1 are already in
@@ -1048,6 +1190,7 @@ int launch_scatter(gl_ctx* ctx, const int32_t* d_start, const int32_t* d_end, in
 // general path: (re)build the HBM difference array from every batch
 int accumulate_general(gl_ctx* ctx) {
     if (ctx->g_valid) return GL_OK;
+    ctx->ev_valid = false;                     // the two general paths share ctx->diff
     const int64_t len = ctx->re - ctx->rs;
     const size_t entries = diff_entries_for(len) + tile_entries_for(len) + super_entries_for(len);
     GL_CHECK(gl_buf_reserve(ctx, ctx->diff, entries * 4));
@@ -1064,6 +1207,58 @@ int accumulate_general(gl_ctx* ctx) {
     }
     GL_LAUNCHED(ctx, 1);
     ctx->g_valid = true;
+    return GL_OK;
+}
+
+// bucketed-events general path: (re)build the per-tile event buckets from every batch
+//   ctx->diff layout: tile_starts[T+1] | tile_ends[T+1] | cursor[T+1] | bucket_off[T+2] | carry[T+2] | events u16[2 * n_total]
+struct EvLayout { int* tile_starts; int* tile_ends; unsigned* cursor; unsigned* bucket_off; int* carry; unsigned short* events; size_t zero_bytes; };
+EvLayout ev_layout(gl_ctx* ctx, int64_t tiles) {
+    const size_t T = ((size_t)tiles + 2 + 3) & ~size_t(3);
+    char* b = static_cast<char*>(ctx->diff.p);
+    EvLayout L;
+    L.tile_starts = reinterpret_cast<int*>(b);
+    L.tile_ends = L.tile_starts + T;
+    L.cursor = reinterpret_cast<unsigned*>(L.tile_ends + T);
+    L.bucket_off = L.cursor + T;
+    L.carry = reinterpret_cast<int*>(L.bucket_off + T);
+    L.events = reinterpret_cast<unsigned short*>(L.carry + T);
+    L.zero_bytes = 3 * T * 4;
+    return L;
+}
+
+int accumulate_events(gl_ctx* ctx) {
+    if (ctx->ev_valid) return GL_OK;
+    ctx->g_valid = false;                      // the two general paths share ctx->diff
+    const int64_t len = ctx->re - ctx->rs;
+    const int64_t tiles = num_tiles_for(len);
+    int64_t n_total = 0;
+    for (const gl_seg_batch& b : ctx->batches) n_total += b.n;
+    if (2 * n_total >= (int64_t(1) << 32)) return gl_fail(ctx, GL_ERANGE, "more than 2^31 segments in one region");
+    const size_t T = ((size_t)tiles + 2 + 3) & ~size_t(3);
+    GL_CHECK(gl_buf_reserve(ctx, ctx->diff, 5 * T * 4 + (size_t)n_total * 4 + 64));
+    const EvLayout L = ev_layout(ctx, tiles);
+    GL_CUDA(ctx, cudaMemsetAsync(ctx->diff.p, 0, L.zero_bytes, ctx->stream));
+    for (int pass = 0; pass < 2; pass++) {
+        for (const gl_seg_batch& b : ctx->batches) {
+            if (b.n <= 0) continue;
+            const unsigned grid = (unsigned)(((b.n + 3) / 4 + 255) / 256);
+            gl_prof_scope prof(ctx, pass == 0 ? "depth_evcount_kernel" : "depth_evscatter_kernel");
+            if (pass == 0)
+                depth_events_kernel<false><<<grid, 256, 0, ctx->stream>>>(batch_start(ctx, b), batch_end(ctx, b), b.n, (int)ctx->rs, (int)ctx->re, (int)tiles,
+                                                                        L.tile_starts, L.tile_ends, nullptr, nullptr, nullptr);
+            else
+                depth_events_kernel<true><<<grid, 256, 0, ctx->stream>>>(batch_start(ctx, b), batch_end(ctx, b), b.n, (int)ctx->rs, (int)ctx->re, (int)tiles,
+                                                                       nullptr, nullptr, L.bucket_off, L.cursor, L.events);
+            GL_LAUNCHED(ctx, 1);
+        }
+        if (pass == 0) {
+            gl_prof_scope prof(ctx, "depth_evscan_kernel");
+            depth_evscan_kernel<<<1, 1024, 0, ctx->stream>>>(L.tile_starts, L.tile_ends, (int)tiles, L.bucket_off, L.carry);
+            GL_LAUNCHED(ctx, 1);
+        }
+    }
+    ctx->ev_valid = true;
     return GL_OK;
 }
 
@@ -1337,7 +1532,7 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
     if (do_windows && want_min) GL_CHECK(gl_buf_reserve(ctx, ctx->win_min, (size_t)n_windows * 4));
     // One scratch buffer; everything that must start at zero is contiguous so a single memset clears it:
     //   [header u64[8] | super_cnt u32[supers]] [win_sum u64[n_windows]] [flags] [cell_hi|cell_cnt|cell_lo per batch]  | chunk_runs
-    bool try_fused = ctx->force_path != 2 && !ctx->batches.empty() && (int)ctx->batches.size() <= kMaxBatches;
+    bool try_fused = ctx->force_path != 2 && ctx->force_path != 4 && !ctx->batches.empty() && (int)ctx->batches.size() <= kMaxBatches;
     for (const gl_seg_batch& b : ctx->batches) if (b.n >= INT32_MAX) try_fused = false;
     const int origin = (int)(std::max<int64_t>(0, ctx->rs - kMaxLookback) & ~int64_t((1 << kCellShift) - 1));
     const int ncells = (int)(((ctx->re - 1 - origin) >> kCellShift) + 1);
@@ -1413,11 +1608,16 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
 
     for (int attempt = 0; attempt < 3; attempt++) {
         const bool fused = try_fused;
-        if (!fused) {
+        const bool hbm_diff = !fused && ctx->force_path == 2;      // the north-star pipeline (HBM difference array), on request only
+        EvLayout evl = {};
+        if (hbm_diff) {
             GL_CHECK(accumulate_general(ctx));
             p.diff = static_cast<const int*>(ctx->diff.p);
             p.tile_sum = tile_sum_ptr(ctx);
             p.super_sum = super_sum_ptr(ctx);
+        } else if (!fused) {
+            GL_CHECK(accumulate_events(ctx));
+            evl = ev_layout(ctx, tiles);
         }
         p.win_sum = static_cast<unsigned long long*>(ctx->win_sum_p);
         p.win_min = (do_windows && want_min) ? static_cast<int*>(ctx->win_min.p) : nullptr;
@@ -1435,10 +1635,11 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
         if (attempt > 0) GL_CUDA(ctx, cudaMemsetAsync(sbase, 0, head_bytes + win_bytes, ctx->stream));   // header + window sums again
         if (do_windows && want_min) GL_CUDA(ctx, cudaMemsetAsync(ctx->win_min.p, 0x7f, (size_t)n_windows * 4, ctx->stream));
         {
-            gl_prof_scope prof(ctx, fused ? "depth_fused_kernel" : "depth_scan_kernel");
+            gl_prof_scope prof(ctx, fused ? "depth_fused_kernel" : (hbm_diff ? "depth_scan_kernel" : "depth_evtile_kernel"));
             const unsigned fused_grid = (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 4);
             if (fused) depth_fused_kernel<<<fused_grid, kScanThreads, 0, ctx->stream>>>(p);
-            else depth_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p);
+            else if (hbm_diff) depth_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p);
+            else depth_evtile_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p, evl.events, evl.bucket_off, evl.carry);
         }
         GL_LAUNCHED(ctx, 1);
         if (do_runs) {
@@ -1466,7 +1667,7 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
         uint64_t hdr[4];
         GL_CHECK(read_header(ctx, hdr));
         if (fused && hdr[3] != 0) { try_fused = false; ctx->prefetched = false; ctx->prefetched_runs = 0; continue; }        // not in BAM order / segments too long
-        ctx->last_path = fused ? 1 : 2;
+        ctx->last_path = fused ? 1 : (hbm_diff ? 2 : 4);
         ctx->idx_flags = fused ? flags : nullptr;
         ctx->idx_cells = fused ? cells : nullptr;
         ctx->idx_origin = origin;
@@ -1536,6 +1737,7 @@ int gl_depth_begin(gl_ctx* ctx, int64_t region_start, int64_t region_end) {
     ctx->p8.pending = false;
     ctx->p8.upload_pending = false;
     ctx->g_valid = false;
+    ctx->ev_valid = false;
     ctx->depth_active = true;
     ctx->depth_reduced = false;
     ctx->n_windows = 0;
@@ -1554,6 +1756,7 @@ int gl_depth_add_segments_device(gl_ctx* ctx, const int32_t* d_start, const int3
     b.s = d_start; b.e = d_end; b.n = n;
     ctx->batches.push_back(b);
     ctx->g_valid = false;
+    ctx->ev_valid = false;
     ctx->depth_reduced = false;
     return GL_OK;
 }
@@ -1607,6 +1810,7 @@ int gl_depth_add_segments(gl_ctx* ctx, const int32_t* start, const int32_t* end,
     }
     ctx->store_n += n;
     ctx->g_valid = false;
+    ctx->ev_valid = false;
     ctx->depth_reduced = false;
     return GL_OK;
 }
@@ -1656,6 +1860,7 @@ int gl_depth_add_segments_packed16(gl_ctx* ctx, const int32_t* anchors, const ui
     }
     ctx->store_n += n;
     ctx->g_valid = false;
+    ctx->ev_valid = false;
     ctx->depth_reduced = false;
     return GL_OK;
 }
@@ -1673,6 +1878,7 @@ static int p8_register(gl_ctx* ctx, const int* d_anchor, const void* d_ds, const
     ctx->p8.pending = true;
     if (ctx->batches.size() > 1) GL_CHECK(p8_materialize(ctx));   // not the only batch: the int32 paths take it
     ctx->g_valid = false;
+    ctx->ev_valid = false;
     ctx->depth_reduced = false;
     return GL_OK;
 }
@@ -1747,7 +1953,7 @@ int gl_depth_last_path(gl_ctx* ctx, int32_t* path) {
 }
 
 int gl_depth_set_path(gl_ctx* ctx, int32_t path) {
-    if (!ctx || path < 0 || path > 2) return gl_fail(ctx, GL_EINVAL, "gl_depth_set_path: path must be 0 (auto), 1 (no packed8 kernel) or 2 (general only)");
+    if (!ctx || path < 0 || path > 4 || path == 3) return gl_fail(ctx, GL_EINVAL, "gl_depth_set_path: path must be 0 (auto), 1 (no packed8 kernel), 2 (HBM difference array only) or 4 (bucketed events only)");
     ctx->force_path = path;
     return GL_OK;
 }

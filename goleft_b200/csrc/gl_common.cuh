@@ -46,6 +46,7 @@ struct gl_ctx {
     int64_t store_n = 0;
     bool copies_pending = false;            // H2D into the store still in flight on copy_stream
     bool g_valid = false;                   // the HBM difference array holds every batch (general path)
+    bool ev_valid = false;                  // the per-tile event buckets hold every batch (general path, version 2)
     int last_path = 0;                      // 1 = fused sorted path, 2 = general scatter path
     // index tables of the last fused reduce (valid until the next reduce): used by gl_depth_interval_sums
     const int* idx_flags = nullptr; const unsigned* idx_cells = nullptr; int idx_origin = 0, idx_ncells = 0, idx_maxlen = -1;

@@ -106,8 +106,8 @@ int  gl_depth_begin(gl_ctx* ctx, int64_t region_start, int64_t region_end);
  * stay valid until the results have been fetched.
  * Any order is accepted.  Coordinate-sorted segments (non-decreasing start, what a BAM yields) of at
  * most 16384 bases take the fused path: each 4096-base tile's difference array is built in shared
- * memory straight from the segments.  Anything else takes the general path: int32 reds onto a
- * difference array in HBM.  The device checks eligibility itself; results are identical. */
+ * memory straight from the segments.  Anything else takes the general path (bucketed events, see
+ * gl_depth_last_path).  The device checks eligibility itself; results are identical. */
 int  gl_depth_add_segments(gl_ctx* ctx, const int32_t* start, const int32_t* end, int64_t n);
 int  gl_depth_add_segments_device(gl_ctx* ctx, const int32_t* d_start, const int32_t* d_end, int64_t n);
 
@@ -151,10 +151,13 @@ int  gl_depth_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, in
 
 /* Sizes of the results of the last gl_depth_reduce. */
 int  gl_depth_result_sizes(gl_ctx* ctx, int64_t* n_windows, int64_t* n_runs, int32_t* max_depth);
-/* Which path the last reduce took: 1 = fused (nearly sorted int32 segments), 2 = general (scatter into an HBM difference
- * array), 3 = packed8 (the region's only batch is packed8: read as it is, no int32 copy, no per-segment index). */
+/* Which path the last reduce took: 1 = fused (nearly sorted int32 segments), 2 = HBM difference array (the north-star
+ * pipeline: red.global scatter + scan; on request only), 3 = packed8 (the region's only batch is packed8: read as it is, no
+ * int32 copy, no per-segment index), 4 = bucketed events (the general path: any order, any length; two 16-bit events per
+ * segment bucketed by 4096-base tile, difference arrays built in shared memory). */
 int  gl_depth_last_path(gl_ctx* ctx, int32_t* path);
-/* 0 = choose automatically (default), 1 = never the packed8 kernel, 2 = always the general path (tests, comparison runs). */
+/* 0 = choose automatically (default: packed8 -> fused -> bucketed events), 1 = never the packed8 kernel, 2 = always the HBM
+ * difference array, 4 = always bucketed events (tests, comparison runs). */
 int  gl_depth_set_path(gl_ctx* ctx, int32_t path);
 
 /* Fetch results (host buffers).  run_end may be NULL (run i ends where run i+1 starts; the last

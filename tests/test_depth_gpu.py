@@ -70,14 +70,15 @@ def check_region(ctx, s, e, rs, re, W, mincov=4, maxmean=0, run_break=0, device=
     short = bool(((e - s) <= 16384).all()) if s.size else True
     # unsorted input is correct on either path (the fused kernel only bails out when its index span explodes)
     out = _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device,
-                    (1 if short else 2) if is_sorted else (None if short else 2), exp)
+                    (1 if short else 4) if is_sorted else (None if short else 4), exp)
     if not is_sorted:
         o = np.argsort(s, kind="stable")
-        _run_once(ctx, s[o], e[o], rs, re, W, mincov, maxmean, run_break, device, 1 if short else 2, exp)
-    else:
-        ctx.depth_set_path(2)
+        _run_once(ctx, s[o], e[o], rs, re, W, mincov, maxmean, run_break, device, 1 if short else 4, exp)
+    # both general paths, forced: 4 = bucketed events (the default fallback), 2 = the HBM difference array
+    for forced in (4, 2):
+        ctx.depth_set_path(forced)
         try:
-            _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device, 2, exp)
+            _run_once(ctx, s, e, rs, re, W, mincov, maxmean, run_break, device, forced, exp)
         finally:
             ctx.depth_set_path(0)
     # the packed8 kernel (any input packs: long segments are cut, order does not matter), then the same packed batch
@@ -155,7 +156,7 @@ def test_bam_order_segments_take_fused_path(ctx):
     ctx.depth_begin(0, L)
     ctx.depth_add_segments(s[p], e[p])
     ctx.depth_reduce(500, 4, 0, 0)
-    assert ctx.depth_last_path() == 2
+    assert ctx.depth_last_path() == 4
     assert np.array_equal(ctx.depth_get_windows(), es)
     r0, rc = ctx.depth_get_runs()
     assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
@@ -277,17 +278,18 @@ def test_full_size_chr20(ctx):
     ea, ec = orc.class_runs(exp, 0, L, 4, 0, 10_000_000)
     assert np.array_equal(ws, es)
     assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
-    # the general (scatter) path at full size gives the same integers
-    ctx.depth_set_path(2)
-    ctx.depth_begin(0, L)
-    ctx.depth_add_segments_device(ds, de, s.size)
-    ctx.depth_reduce(W, 4, 0, 10_000_000)
-    assert ctx.depth_last_path() == 2
-    assert np.array_equal(ctx.depth_get_windows(), es)
-    r0, rc = ctx.depth_get_runs()
-    assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
-    ws2, wm2 = ctx.depth_windows(W, es.size)
-    assert np.array_equal(ws2, es) and np.array_equal(wm2, em)
+    # both general paths at full size give the same integers (4: bucketed events, 2: HBM difference array)
+    for forced in (4, 2):
+        ctx.depth_set_path(forced)
+        ctx.depth_begin(0, L)
+        ctx.depth_add_segments_device(ds, de, s.size)
+        ctx.depth_reduce(W, 4, 0, 10_000_000)
+        assert ctx.depth_last_path() == forced
+        assert np.array_equal(ctx.depth_get_windows(), es)
+        r0, rc = ctx.depth_get_runs()
+        assert np.array_equal(r0, ea) and np.array_equal(rc, ec)
+        ws2, wm2 = ctx.depth_windows(W, es.size)
+        assert np.array_equal(ws2, es) and np.array_equal(wm2, em)
     ctx.depth_set_path(0)
     ds.free(); de.free()
     # the packed8 kernel at full size, packed words resident on the device
@@ -474,7 +476,7 @@ def test_interval_sums(ctx):
     ac, bc = np.clip(a, rs, re), np.clip(b, rs, re)
     exp = np.where(bc > ac, cs[np.maximum(bc, ac) - rs] - cs[ac - rs], 0)
     half = s.size // 2
-    for path in (0, 2):
+    for path in (0, 2, 4):
         ctx.depth_set_path(path)
         ctx.depth_begin(rs, re)
         ctx.depth_add_segments(s[:half], e[:half])
@@ -482,7 +484,7 @@ def test_interval_sums(ctx):
         if path == 2:
             assert np.array_equal(ctx.depth_interval_sums(a[:200], b[:200]), exp[:200])      # before any reduce
         ctx.depth_reduce(500, 4, 0, 0)
-        assert ctx.depth_last_path() == (1 if path == 0 else 2)
+        assert ctx.depth_last_path() == (1 if path == 0 else path)
         n = a.size if path == 0 else 300                     # no index -> brute force over all segments: keep it small
         assert np.array_equal(ctx.depth_interval_sums(a[:n], b[:n]), exp[:n])
         assert ctx.depth_interval_sums(a[:0], b[:0]).size == 0

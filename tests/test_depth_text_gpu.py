@@ -68,6 +68,7 @@ def test_long_chrom_name_and_long_reads(ctx):
     name = "HLA-DRB1*15:03:01:02_some_very_long_decoy_contig_name_0123456789"[:64]
     exp = oracle_contig_text(name, L, s, e, 250, 4, 0)
     assert ctx.depth_bed_contig(name, L, s, e, 250, 4, 0, 10_000_000) == exp
+    assert ctx.depth_last_path() == 4                                    # segments beyond the fused path's 16384-base look-back: bucketed events
     with pytest.raises(capi.GlError):
         ctx.depth_bed_contig(name + "x", L, s, e, 250, 4, 0, 10_000_000)
 

@@ -22,6 +22,8 @@ for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 4):
     else:
         ctx.depth_add_segments_device(d_s, d_e, s.size)
     if which == "general":
+        ctx.depth_set_path(4)
+    if which == "hbm":
         ctx.depth_set_path(2)
     ctx.depth_reduce(500, 4, 0, 10_000_000)
 print("path", ctx.depth_last_path(), ctx.depth_result_sizes())
