@@ -232,9 +232,47 @@ def depthwed_leg(ctx, dist, rank, world, local, S=500, R=6_176_584, n_chunks=8, 
             blk = buf.reshape(rows, width)
             for k in (0, rhi - rlo - 1):
                 ok = ok and bool(np.array_equal(blk[:, k], base[g0:g0 + rows] + np.int32(rlo + k)))
-    tt = torch.tensor([np.mean(t_over), np.mean(t_agg), np.mean(t_gather), 0.0 if ok else 1.0], dtype=torch.float64, device="cuda")
+    d_local.free(); d_all.free()
+    # ---- the fused form: the aggregation kernel stores each row into the row-major R x (width*world) matrix of EVERY rank
+    #      through NVLink peer mappings (gl_ipc_*): no all-gather pass, no block re-assembly
+    t_p2p, ok_p2p = [], True
+    try:
+        row_stride = width * world
+        d_full = ctx.dev_empty(R * row_stride * 4)
+        mine = torch.tensor(list(ctx.ipc_export(d_full)), dtype=torch.uint8, device="cuda")
+        hs = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(hs, mine)
+        ptrs = [d_full.ptr if r == rank else ctx.ipc_open(bytes(hs[r].cpu().tolist())) for r in range(world)]
+        for it in range(reps + 1):
+            ctx.sync(); dist.barrier()
+            ctx.timer_start()
+            ctx.depthwed_aggregate_i32_p2p(d_depth, width, R, None, 0, R, ptrs, row_stride, rank * width, d_ovf)
+            ms_k = ctx.timer_stop_ms()
+            dist.barrier()
+            if it:
+                t_p2p.append(ms_k)
+        ok_p2p = int(d_ovf.download(np.int32, 1)[0]) == 0
+        for g0 in (0, R // 2, R - 2000):                              # rows of the finished matrix on THIS rank: every rank's columns
+            buf = np.empty(2000 * row_stride, np.int32)
+            capi.lib.gl_memcpy_d2h(ctx.h, buf.ctypes.data, d_full.ptr + g0 * row_stride * 4, buf.nbytes)
+            m = buf.reshape(2000, row_stride)
+            for r in range(world):
+                rlo, rhi = multigpu.shard_range(S, r, world)
+                for k in (0, rhi - rlo - 1):
+                    ok_p2p = ok_p2p and bool(np.array_equal(m[:, r * width + k], base[g0:g0 + 2000] + np.int32(rlo + k)))
+        dist.barrier()
+        for r in range(world):
+            if r != rank:
+                ctx.ipc_close(ptrs[r])
+        dist.barrier()
+        d_full.free()
+    except Exception as ex:
+        t_p2p, ok_p2p = [float("nan")], False
+        log(f"[rank {rank}] fused p2p depthwed leg failed: {ex}")
+    tt = torch.tensor([np.mean(t_over), np.mean(t_agg), np.mean(t_gather), 0.0 if ok else 1.0, float(np.mean(t_p2p)), 0.0 if ok_p2p else 1.0],
+                      dtype=torch.float64, device="cuda")
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    for b in (d_depth, d_local, d_all, d_ovf):
+    for b in (d_depth, d_ovf):
         b.free()
     total = R * width * 4 * world
     return {"samples": S, "rows": R, "dtype": "int32", "matrix_bytes": total, "chunks": n_chunks,
@@ -244,6 +282,10 @@ def depthwed_leg(ctx, dist, rank, world, local, S=500, R=6_176_584, n_chunks=8, 
             "overlapped_ms": float(tt[0]), "sequential_ms": float(tt[1]) + float(tt[2]),
             "overlapped_busbw_gbs": total * (world - 1) / world / (float(tt[0]) * 1e-3) / 1e9,
             "verified_on_every_rank": float(tt[3]) == 0.0,
+            "fused_p2p": {"ms": float(tt[4]), "busbw_gbs": total * (world - 1) / world / (float(tt[4]) * 1e-3) / 1e9,
+                          "verified_on_every_rank": float(tt[5]) == 0.0,
+                          "note": "depthwed_i32_p2p_kernel: aggregate + store every row into all ranks' row-major matrices over NVLink peer memory "
+                                  "(one kernel per rank, CUDA-event time, max over ranks); busbw by the all-gather formula for comparison"},
             "note": "sample-sharded; per rank: depthwed_i32_kernel over 8 row chunks on the compute stream, ncclAllGather of each finished chunk "
                     "on the communication stream (gl_allgather_device_async); times are max over ranks"}
 

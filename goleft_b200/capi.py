@@ -113,6 +113,10 @@ _proto("gl_depthwed_aggregate", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, _v
 _proto("gl_depthwed_aggregate_device", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp)
 _proto("gl_depthwed_aggregate_i32", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_depthwed_aggregate_i32_device", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, _vp)
+_proto("gl_depthwed_aggregate_i32_p2p", C.c_int, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, C.c_int32, C.c_int64, C.c_int32, _vp)
+_proto("gl_ipc_export", C.c_int, _vp, _vp, _vp)
+_proto("gl_ipc_open", C.c_int, _vp, _vp, C.POINTER(_vp))
+_proto("gl_ipc_close", C.c_int, _vp, _vp)
 _proto("gl_allgather_device_async", C.c_int, _vp, _vp, _vp, C.c_int64)
 _proto("gl_comm_wait", C.c_int, _vp)
 _proto("gl_comm_unique_id", C.c_int, _vp)
@@ -857,6 +861,26 @@ class Ctx:
                                       d_out_ptr: int, d_overflow: DevBuf):
         self._ck(lib.gl_depthwed_aggregate_i32_device(self.h, d_depth.ptr, S, R, d_grp.ptr if d_grp is not None else None, g_begin, g_end,
                                                       d_out_ptr, d_overflow.ptr))
+
+    def ipc_export(self, buf: DevBuf) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self._ck(lib.gl_ipc_export(self.h, buf.ptr, C.cast(h, _vp)))
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = _vp()
+        self._ck(lib.gl_ipc_open(self.h, C.cast(h, _vp), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr: int):
+        self._ck(lib.gl_ipc_close(self.h, ptr))
+
+    def depthwed_aggregate_i32_p2p(self, d_depth: DevBuf, S: int, R: int, d_grp: Optional[DevBuf], g_begin: int, g_end: int, dst_ptrs,
+                                   row_stride: int, col_off: int, d_overflow: DevBuf):
+        arr = (_vp * len(dst_ptrs))(*dst_ptrs)
+        self._ck(lib.gl_depthwed_aggregate_i32_p2p(self.h, d_depth.ptr, S, R, d_grp.ptr if d_grp is not None else None, g_begin, g_end,
+                                                   C.cast(arr, _vp), len(dst_ptrs), row_stride, col_off, d_overflow.ptr))
 
     def allgather_device_async(self, send_ptr: int, recv_ptr: int, nbytes: int):
         self._ck(lib.gl_allgather_device_async(self.h, send_ptr, recv_ptr, nbytes))

@@ -118,6 +118,34 @@ int gl_allgather_device_async(gl_ctx* ctx, const void* d_send, void* d_recv, int
     return GL_OK;
 }
 
+// ---- peer memory between the per-GPU processes of one box (NVLink / NVSwitch): a device allocation of one rank mapped
+// into another rank's address space, so that a kernel there can store into it directly (gl_depthwed_aggregate_i32_p2p).
+int gl_ipc_export(gl_ctx* ctx, void* d_ptr, uint8_t handle64[64]) {
+    GL_CHECK(gl_use(ctx));
+    if (!d_ptr || !handle64) return gl_fail(ctx, GL_EINVAL, "gl_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    GL_CUDA(ctx, cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle64, &h, 64);
+    return GL_OK;
+}
+
+int gl_ipc_open(gl_ctx* ctx, const uint8_t handle64[64], void** d_peer_ptr) {
+    GL_CHECK(gl_use(ctx));
+    if (!handle64 || !d_peer_ptr) return gl_fail(ctx, GL_EINVAL, "gl_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    *d_peer_ptr = nullptr;
+    GL_CUDA(ctx, cudaIpcOpenMemHandle(d_peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GL_OK;
+}
+
+int gl_ipc_close(gl_ctx* ctx, void* d_peer_ptr) {
+    GL_CHECK(gl_use(ctx));
+    if (d_peer_ptr) GL_CUDA(ctx, cudaIpcCloseMemHandle(d_peer_ptr));
+    return GL_OK;
+}
+
 int gl_comm_wait(gl_ctx* ctx) {
     GL_CHECK(gl_use(ctx));
     if (ctx->comm_stream) GL_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));

@@ -664,6 +664,48 @@ __global__ void __launch_bounds__(256) depthwed_i32_kernel(const int* __restrict
     }
 }
 
+// W1 fused with its collective: the aggregation kernel stores every output row straight into the row-major n-sites x
+// n-samples matrix of EVERY GPU — its own and, through NVLink peer mappings, the other ranks' — so the matrix is assembled
+// while it is computed and no separate all-gather pass (and no block re-assembly on the receiving side) exists.
+// dst[d] = base of rank d's matrix (row stride `row_stride` ints); this rank owns columns [col_off, col_off + S).
+// A warp stores 32 consecutive samples of one row (128 B), one store per destination; the destinations are visited in a
+// per-block rotated order so that all NVLink links carry traffic all the time.  Stores to a peer are complete when the
+// kernel is; the ranks then meet at a host barrier.
+struct WedPeers { int* dst[16]; };
+__global__ void __launch_bounds__(256) depthwed_i32_p2p_kernel(const int* __restrict__ depth, int S, long long R, const long long* __restrict__ grp,
+                                                              long long g_begin, long long g_end, int simple, WedPeers peers, int world,
+                                                              long long row_stride, int col_off, int* __restrict__ overflow) {
+    __shared__ int s_t[32][33];
+    const long long g0 = g_begin + (long long)blockIdx.x * 32;
+    const int s0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    for (int k = ty; k < 32; k += 8) {                             // k: sample inside the tile, tx: group
+        const int s = s0 + k;
+        const long long g = g0 + tx;
+        long long acc = 0;
+        if (s < S && g < g_end) {
+            const long long a = simple ? g : grp[g], b = simple ? g + 1 : grp[g + 1];
+            for (long long r = a; r < b; r++) acc += depth[(size_t)s * R + r];
+            if (acc > 2147483647ll || acc < -2147483648ll) *overflow = 1;
+        }
+        s_t[k][tx] = (int)acc;
+    }
+    __syncthreads();
+    const int rot = (int)((blockIdx.x + blockIdx.y) % (unsigned)world);
+    for (int k = ty; k < 32; k += 8) {                             // k: group inside the tile, tx: sample
+        const long long g = g0 + k;
+        const int s = s0 + tx;
+        if (s < S && g < g_end) {
+            const int v = s_t[tx][k];
+            const size_t at = (size_t)g * (size_t)row_stride + (size_t)(col_off + s);
+            for (int d = 0; d < world; d++) {
+                int dd = d + rot; if (dd >= world) dd -= world;
+                peers.dst[dd][at] = v;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ I6
 // float32 -> the bytes of Go's fmt "%.3g" (== C printf "%.3g" of the same value), exactly: the three significant
 // digits come from integer arithmetic on mantissa * 10^k (128-bit), rounded half-to-even on the exact binary
@@ -1179,6 +1221,27 @@ int gl_depthwed_aggregate_i32_device(gl_ctx* ctx, const int32_t* d_depth, int32_
         gl_prof_scope prof(ctx, "depthwed_i32_kernel");
         depthwed_i32_kernel<<<grid, 256, 0, ctx->stream>>>(d_depth, S, R, reinterpret_cast<const long long*>(d_grp), g_begin, g_end, d_grp ? 0 : 1,
                                                            d_out, d_overflow);
+    }
+    GL_LAUNCHED(ctx, 1);
+    return GL_OK;
+}
+
+// fused aggregate + all-gather over peer memory: d_dst[d] = rank d's full matrix (device pointers valid on this device:
+// its own allocation and gl_ipc_open / peer-enabled pointers of the others).  ASYNCHRONOUS on the ctx stream.
+int gl_depthwed_aggregate_i32_p2p(gl_ctx* ctx, const int32_t* d_depth, int32_t S, int64_t R, const int64_t* d_grp, int64_t g_begin, int64_t g_end,
+                                  int32_t* const* d_dst, int32_t world, int64_t row_stride, int32_t col_off, int32_t* d_overflow) {
+    GL_CHECK(gl_use(ctx));
+    if (S <= 0 || R < 0 || g_begin < 0 || g_end < g_begin || !d_depth || !d_dst || world < 1 || world > 16 || row_stride < col_off + S || col_off < 0 || !d_overflow)
+        return gl_fail(ctx, GL_EINVAL, "gl_depthwed_aggregate_i32_p2p: bad argument");
+    if (g_end == g_begin) return GL_OK;
+    WedPeers peers;
+    for (int d = 0; d < 16; d++) peers.dst[d] = d < world ? d_dst[d] : nullptr;
+    for (int d = 0; d < world; d++) if (!peers.dst[d]) return gl_fail(ctx, GL_EINVAL, "gl_depthwed_aggregate_i32_p2p: null destination %d", d);
+    dim3 grid((unsigned)((g_end - g_begin + 31) / 32), (unsigned)((S + 31) / 32));
+    {
+        gl_prof_scope prof(ctx, "depthwed_i32_p2p_kernel");
+        depthwed_i32_p2p_kernel<<<grid, 256, 0, ctx->stream>>>(d_depth, S, R, reinterpret_cast<const long long*>(d_grp), g_begin, g_end, d_grp ? 0 : 1,
+                                                               peers, world, row_stride, col_off, d_overflow);
     }
     GL_LAUNCHED(ctx, 1);
     return GL_OK;

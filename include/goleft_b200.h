@@ -412,6 +412,20 @@ int  gl_depthwed_aggregate_i32(gl_ctx* ctx, const int32_t* depth, int32_t S, int
 int  gl_depthwed_aggregate_i32_device(gl_ctx* ctx, const int32_t* d_depth, int32_t S, int64_t R, const int64_t* d_grp, int64_t g_begin,
                                       int64_t g_end, int32_t* d_out, int32_t* d_overflow);
 
+/* W1 fused with its collective: the aggregation kernel stores every output row straight into the row-major n-sites x
+ * n-samples matrix of EVERY GPU of the box (its own + NVLink peer mappings of the others): d_dst[d] = base of rank d's matrix
+ * as a pointer valid on this ctx's device (gl_ipc_open between processes; plain peer pointers inside one process), row stride
+ * `row_stride` ints, this rank's samples at columns [col_off, col_off + S).  No separate all-gather, no re-assembly.
+ * ASYNCHRONOUS on the ctx stream; after gl_sync on every rank and a host barrier the matrix is complete everywhere. */
+int  gl_depthwed_aggregate_i32_p2p(gl_ctx* ctx, const int32_t* d_depth, int32_t S, int64_t R, const int64_t* d_grp, int64_t g_begin,
+                                   int64_t g_end, int32_t* const* d_dst, int32_t world, int64_t row_stride, int32_t col_off,
+                                   int32_t* d_overflow);
+/* peer memory between the per-GPU processes of one box: export a gl_dev_alloc allocation as a 64-byte handle, open another
+ * rank's handle as a device pointer usable by kernels of this ctx (cudaIpc*; the link is NVLink / NVSwitch) */
+int  gl_ipc_export(gl_ctx* ctx, void* d_ptr, uint8_t handle64[64]);
+int  gl_ipc_open(gl_ctx* ctx, const uint8_t handle64[64], void** d_peer_ptr);
+int  gl_ipc_close(gl_ctx* ctx, void* d_peer_ptr);
+
 /* ------------------------------------------------------------- multi-GPU
  * One process per GPU.  The caller distributes a 128-byte NCCL unique id (rank 0 creates it).
  * The one collective on this path: an all-gather over NVLink that assembles the depthwed

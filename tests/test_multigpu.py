@@ -97,7 +97,7 @@ def test_gloo_world2_depthwed_and_contig_sharding():
         assert tot == 3000 * 150 - 0 or tot <= 3000 * 150        # clipped at the contig end
 
 
-def _nccl_worker(rank, world, uid, q):
+def _nccl_worker(rank, world, uid, q, shared=None, bar=None):
     from goleft_b200 import capi
     from oracle import loader as orc  # noqa: F401
     c = capi.Ctx(rank)
@@ -128,6 +128,24 @@ def _nccl_worker(rank, world, uid, q):
     multigpu.depthwed_gather_overlapped(c, d_depth, width, R2, world, d_local, d_all, d_ovf, n_chunks)
     got = multigpu.depthwed_assemble_chunked(d_all.download(np.int32, R2 * width * world), R2, width, world, S2, n_chunks)
     ok32 = bool(np.array_equal(got, depth.T)) and int(d_ovf.download(np.int32, 1)[0]) == 0
+    # the fused form: every rank's kernel stores its columns into both ranks' row-major matrices over peer memory
+    if shared is not None:
+        row_stride = width * world
+        d_full = c.dev_array(np.full(R2 * row_stride, -1, np.int32))
+        shared[rank * 64:(rank + 1) * 64] = list(c.ipc_export(d_full))
+        bar.wait()
+        ptrs = [d_full.ptr if r == rank else c.ipc_open(bytes(shared[r * 64:(r + 1) * 64])) for r in range(world)]
+        c.depthwed_aggregate_i32_p2p(d_depth, width, R2, None, 0, R2, ptrs, row_stride, rank * width, d_ovf)
+        c.sync()
+        bar.wait()
+        m = d_full.download(np.int32, R2 * row_stride).reshape(R2, row_stride)
+        for r in range(world):
+            rlo, rhi = multigpu.shard_range(S2, r, world)
+            ok32 = ok32 and bool(np.array_equal(m[:, r * width:r * width + (rhi - rlo)], depth[rlo:rhi].T))
+        bar.wait()
+        for r in range(world):
+            if r != rank:
+                c.ipc_close(ptrs[r])
     q.put((rank, full, ok32))
     c.close()
 
@@ -142,7 +160,8 @@ def test_nccl_world2_depthwed_allgather():
     ctx = mp.get_context("spawn")
     uid = capi.comm_unique_id()
     q = ctx.Queue()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, uid, q)) for r in range(2)]
+    shared, bar = ctx.Array("B", 128), ctx.Barrier(2)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, uid, q, shared, bar)) for r in range(2)]
     for p in procs:
         p.start()
     got = [q.get(timeout=240) for _ in range(2)]
