@@ -138,6 +138,7 @@ _proto("gl_bai_ref", C.c_int, _vp, C.c_int32, C.POINTER(_vp), _i64p, _u64p, _u64
 _proto("gl_bai_free", None, _vp)
 _proto("gl_pack_segments16_bound", C.c_int64, C.c_int64)
 _proto("gl_pack_segments16", C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_pack_segments16_mt", C.c_int, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_depth_add_segments_packed16", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_region_packed16", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
@@ -239,8 +240,9 @@ def chunk_rows(rs: int, re: int, W: int, run_start: np.ndarray, run_class: np.nd
     return s, e
 
 
-def pack_segments16(start: np.ndarray, end: np.ndarray):
-    """Host-only: (anchors int32[nb], off uint16[nb*256], len uint16[nb*256]) — the feeder's compact format."""
+def pack_segments16(start: np.ndarray, end: np.ndarray, threads: Optional[int] = None):
+    """Host-only: (anchors int32[nb], off uint16[nb*256], len uint16[nb*256]) — the feeder's compact format.
+    threads=None: single-threaded; an int: gl_pack_segments16_mt (0 = the whole pool)."""
     start, end = _as(start, np.int32), _as(end, np.int32)
     nb = C.c_int64(0)
     cap = max(1, int(lib.gl_pack_segments16_bound(start.size)) // 8 + start.size // 256 + 2)
@@ -248,7 +250,10 @@ def pack_segments16(start: np.ndarray, end: np.ndarray):
         a = np.empty(cap, np.int32)
         o = np.empty(cap * 256, np.uint16)
         ln = np.empty(cap * 256, np.uint16)
-        rc = lib.gl_pack_segments16(_ptr(start), _ptr(end), start.size, _ptr(a), _ptr(o), _ptr(ln), cap, C.byref(nb))
+        if threads is None:
+            rc = lib.gl_pack_segments16(_ptr(start), _ptr(end), start.size, _ptr(a), _ptr(o), _ptr(ln), cap, C.byref(nb))
+        else:
+            rc = lib.gl_pack_segments16_mt(_ptr(start), _ptr(end), start.size, threads, _ptr(a), _ptr(o), _ptr(ln), cap, C.byref(nb))
         if rc == GL_OK:
             k = nb.value
             return a[:k], o[: k * 256], ln[: k * 256]

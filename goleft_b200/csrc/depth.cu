@@ -2151,11 +2151,51 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
     GL_CHECK(gl_use(ctx));
     GL_CHECK(bed_args_ok(ctx, rs, re, W, step));
     if (n < 0 || (n > 0 && (!start || !end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_region: bad segments");
-    // The int32 arrays go up as they are (PCIe-bound: 8 B/segment).  GL_BED_PACK=1 packs short-read input to packed8
-    // (2 B/segment) on the host pool first: a quarter of the PCIe bytes, but on the 2 x 32-core host of the B200 box the
-    // pack costs 2-3 ms per 11 M segments, more than the 1.2 ms of upload it saves (tools/e2e_text_probe.py), so it is
-    // opt-in; a feeder that emits packed8 itself (gl_bam_decode) calls gl_depth_bed_region_packed8.
-    static const int force = [] { const char* e = getenv("GL_BED_PACK"); return e ? atoi(e) : 0; }();
+    // How the int32 arrays travel (GL_BED_PACK): the call is PCIe-bound at 8 B/segment, so by default (16) the host pool
+    // repacks them, order-preserving and without a sort, to packed16 (4 B/segment: int32 anchor per 256 slots + uint16
+    // offset / length) in 8 index chunks — chunk k+1 is packed while chunk k is on the wire and chunk k-1 is unpacked on the
+    // device.  0: upload as they are.  1: packed8 (2 B/segment, needs a sort: 2-3 ms per 11 M segments on the 2 x 32-core
+    // host, more than it saves; a feeder that emits packed8 itself calls gl_depth_bed_region_packed8).
+    static const int force = [] { const char* e = getenv("GL_BED_PACK"); return e ? atoi(e) : 16; }();
+    if (force == 16 && n >= (int64_t(1) << 18)) {
+        const int K = 8;
+        int64_t cap = n / 256 + n / 1024 + 64 * K;                     // blocks: full ones + slack for sparse stretches
+        const size_t bytes = (size_t)cap * (4 + 512 + 512) + 256;
+        if (ctx->pack_pinned_bytes < bytes) {
+            GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            if (ctx->pack_pinned) cudaFreeHost(ctx->pack_pinned);
+            ctx->pack_pinned = nullptr; ctx->pack_pinned_bytes = 0;
+            cudaError_t e = cudaHostAlloc(&ctx->pack_pinned, bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) { ctx->pack_pinned = nullptr; cudaGetLastError(); return gl_fail(ctx, GL_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+            ctx->pack_pinned_bytes = bytes;
+        }
+        cap = (int64_t)((ctx->pack_pinned_bytes - 256) / 1028);
+        int32_t* A = static_cast<int32_t*>(ctx->pack_pinned);
+        uint16_t* O = reinterpret_cast<uint16_t*>(A + ((cap + 3) & ~int64_t(3)));
+        uint16_t* Ln = O + (size_t)cap * 256;
+        GL_CHECK(gl_depth_begin(ctx, rs, re));
+        GL_CHECK(store_reserve(ctx, (n + n / 4 + 256 * 64 * K)));       // the unpacked slots land here: no regrowth between chunks
+        // ... and the device staging of the packed words is sized once for the largest chunk there can be (a regrowth
+        // between chunks would free a buffer the copy stream is still writing)
+        GL_CHECK(gl_buf_reserve(ctx, ctx->packed, (((size_t)cap * 4 + 255) & ~size_t(255)) + 2 * (((size_t)cap * 512 + 255) & ~size_t(255))));
+        int64_t b_off = 0;
+        for (int c = 0; c < K; c++) {
+            const int64_t i0 = n * c / K, i1 = n * (c + 1) / K;
+            if (i1 <= i0) continue;
+            int64_t nb = 0;
+            // (an earlier call's uploads out of this buffer have finished: every entry point synchronises before it returns)
+            const int rc = gl_pack_segments16_mt(start + i0, end + i0, i1 - i0, threads, A + b_off, O + b_off * 256, Ln + b_off * 256, cap - b_off, &nb);
+            if (rc == GL_ERANGE) {                                       // very sparse input: the rest goes up as plain int32
+                GL_CHECK(gl_depth_add_segments(ctx, start + i0, end + i0, n - i0));
+                break;
+            }
+            if (rc != GL_OK) return gl_fail(ctx, rc, "gl_pack_segments16_mt failed");
+            GL_CHECK(gl_depth_add_segments_packed16(ctx, A + b_off, O + b_off * 256, Ln + b_off * 256, nb));
+            b_off += nb;
+        }
+        GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, step));
+        return gl_depth_text(ctx, chrom, depth_bed, depth_cap, depth_len, callable_bed, callable_cap, callable_len);
+    }
     bool pack = force == 1 && n >= 4096;
     if (pack) {                                       // long segments would be cut into many 255-base pieces: judged on a sample
         int64_t tot = 0, cnt = 0;

@@ -413,3 +413,66 @@ extern "C" int gl_pack_segments8_mt(const int32_t* start, const int32_t* end, in
     concat_p8(S.a, T, anchors, dstart, len);
     return GL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ parallel packed16
+// gl_pack_segments16_mt: packed16 keeps the caller's order and needs no sort, so the input is simply cut into index
+// chunks; every worker first counts the blocks its chunk needs (a dry run of the same loop), the counts are prefix-summed,
+// and a second pass writes the blocks in place.  Each chunk opens its own first block, so the result can differ from the
+// single-threaded packer's by a few partly filled blocks; it decodes to the same segments in the same order.
+namespace {
+// one chunk: returns the number of blocks; writes when anchors != null (to block index b0 ...)
+int64_t pack16_chunk(const int32_t* start, const int32_t* end, int64_t a, int64_t b, int32_t* anchors, uint16_t* off, uint16_t* len, int64_t b0) {
+    int64_t nb = 0;
+    int cnt = 256;
+    int32_t anchor = 0;
+    const bool wr = anchors != nullptr;
+    for (int64_t i = a; i < b; i++) {
+        int64_t s = start[i];
+        const int64_t e = end[i];
+        if (e <= s) continue;
+        while (s < e) {
+            const int64_t piece = (e - s > 65535) ? 65535 : e - s;
+            const int64_t o = s - anchor;
+            if (cnt == 256 || o < 0 || o > 65535) {
+                if (wr && nb > 0 && cnt < 256) {
+                    memset(off + (b0 + nb - 1) * 256 + cnt, 0, (size_t)(256 - cnt) * 2);
+                    memset(len + (b0 + nb - 1) * 256 + cnt, 0, (size_t)(256 - cnt) * 2);
+                }
+                anchor = s > INT32_MIN + 16384 ? (int32_t)(s - 16384) : (int32_t)s;
+                if (wr) anchors[b0 + nb] = anchor;
+                nb++;
+                cnt = 0;
+            }
+            if (wr) {
+                off[(b0 + nb - 1) * 256 + cnt] = (uint16_t)(s - anchor);
+                len[(b0 + nb - 1) * 256 + cnt] = (uint16_t)piece;
+            }
+            cnt++;
+            s += piece;
+        }
+    }
+    if (wr && nb > 0 && cnt < 256) {
+        memset(off + (b0 + nb - 1) * 256 + cnt, 0, (size_t)(256 - cnt) * 2);
+        memset(len + (b0 + nb - 1) * 256 + cnt, 0, (size_t)(256 - cnt) * 2);
+    }
+    return nb;
+}
+}  // namespace
+
+extern "C" int gl_pack_segments16_mt(const int32_t* start, const int32_t* end, int64_t n, int32_t threads, int32_t* anchors, uint16_t* off,
+                                     uint16_t* len, int64_t cap_blocks, int64_t* n_blocks) {
+    using namespace glhost;
+    if (n < 0 || !n_blocks || (n > 0 && (!start || !end))) return GL_EINVAL;
+    ThreadPool& pool = ThreadPool::global();
+    const int T = threads > 0 ? std::min<int>(threads, pool.size()) : pool.size();
+    const int64_t P = std::min<int64_t>((int64_t)T, n / 16384 + 1);
+    std::vector<int64_t> cnt((size_t)P + 1, 0);
+    auto lo_of = [&](int64_t k) { return (int64_t)((__int128)n * k / P); };
+    pool.run(P, [&](int64_t k, int) { cnt[(size_t)k + 1] = pack16_chunk(start, end, lo_of(k), lo_of(k + 1), nullptr, nullptr, nullptr, 0); }, T);
+    for (int64_t k = 0; k < P; k++) cnt[(size_t)k + 1] += cnt[(size_t)k];
+    *n_blocks = cnt[(size_t)P];
+    if (cnt[(size_t)P] == 0) return GL_OK;
+    if (!(anchors && off && len) || cnt[(size_t)P] > cap_blocks) return GL_ERANGE;
+    pool.run(P, [&](int64_t k, int) { pack16_chunk(start, end, lo_of(k), lo_of(k + 1), anchors, off, len, cnt[(size_t)k]); }, T);
+    return GL_OK;
+}

@@ -119,6 +119,9 @@ int  gl_depth_add_segments_device(gl_ctx* ctx, const int32_t* d_start, const int
 int64_t gl_pack_segments16_bound(int64_t n);
 int  gl_pack_segments16(const int32_t* start, const int32_t* end, int64_t n, int32_t* anchors, uint16_t* off,
                         uint16_t* len, int64_t cap_blocks, int64_t* n_blocks);
+/* the same from `threads` host threads (0 = the whole pool): order-preserving, no sort; index chunks are packed independently */
+int  gl_pack_segments16_mt(const int32_t* start, const int32_t* end, int64_t n, int32_t threads, int32_t* anchors, uint16_t* off,
+                           uint16_t* len, int64_t cap_blocks, int64_t* n_blocks);
 int  gl_depth_add_segments_packed16(gl_ctx* ctx, const int32_t* anchors, const uint16_t* off, const uint16_t* len,
                                     int64_t n_blocks);
 /* "packed8": a quarter of the bytes, for short-read data.  Blocks of 64 slots: int32 anchor (start of slot 0) +
