@@ -237,7 +237,8 @@ def depthwed_leg(ctx, dist, rank, world, local, S=500, R=6_176_584, n_chunks=8, 
     #      through NVLink peer mappings (gl_ipc_*): no all-gather pass, no block re-assembly
     t_p2p, ok_p2p = [], True
     try:
-        row_stride = width * world
+        wpad = (width + 3) // 4 * 4                                   # 16-byte stores: every rank's column block starts on a multiple of 4
+        row_stride = wpad * world
         d_full = ctx.dev_empty(R * row_stride * 4)
         mine = torch.tensor(list(ctx.ipc_export(d_full)), dtype=torch.uint8, device="cuda")
         hs = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
@@ -246,7 +247,7 @@ def depthwed_leg(ctx, dist, rank, world, local, S=500, R=6_176_584, n_chunks=8, 
         for it in range(reps + 1):
             ctx.sync(); dist.barrier()
             ctx.timer_start()
-            ctx.depthwed_aggregate_i32_p2p(d_depth, width, R, None, 0, R, ptrs, row_stride, rank * width, d_ovf)
+            ctx.depthwed_aggregate_i32_p2p(d_depth, width, R, None, 0, R, ptrs, row_stride, rank * wpad, d_ovf)
             ms_k = ctx.timer_stop_ms()
             dist.barrier()
             if it:
@@ -259,7 +260,7 @@ def depthwed_leg(ctx, dist, rank, world, local, S=500, R=6_176_584, n_chunks=8, 
             for r in range(world):
                 rlo, rhi = multigpu.shard_range(S, r, world)
                 for k in (0, rhi - rlo - 1):
-                    ok_p2p = ok_p2p and bool(np.array_equal(m[:, r * width + k], base[g0:g0 + 2000] + np.int32(rlo + k)))
+                    ok_p2p = ok_p2p and bool(np.array_equal(m[:, r * wpad + k], base[g0:g0 + 2000] + np.int32(rlo + k)))
         dist.barrier()
         for r in range(world):
             if r != rank:
@@ -283,6 +284,7 @@ def depthwed_leg(ctx, dist, rank, world, local, S=500, R=6_176_584, n_chunks=8, 
             "overlapped_busbw_gbs": total * (world - 1) / world / (float(tt[0]) * 1e-3) / 1e9,
             "verified_on_every_rank": float(tt[3]) == 0.0,
             "fused_p2p": {"ms": float(tt[4]), "busbw_gbs": total * (world - 1) / world / (float(tt[4]) * 1e-3) / 1e9,
+                          "matrix_layout": "row-major n-sites x (ceil4(samples per rank) * ranks) int32 on every rank",
                           "verified_on_every_rank": float(tt[5]) == 0.0,
                           "note": "depthwed_i32_p2p_kernel: aggregate + store every row into all ranks' row-major matrices over NVLink peer memory "
                                   "(one kernel per rank, CUDA-event time, max over ranks); busbw by the all-gather formula for comparison"},

@@ -726,59 +726,60 @@ __global__ void __launch_bounds__(256) depth_events_kernel(const int* __restrict
     }
 }
 
-// bucket_off[t] = events in tiles < t; carry[t] = (starts - ends) in tiles < t = the depth carried into tile t.  One CTA.
+// bucket_off[t] = events in tiles < t; carry[t] = (starts - ends) in tiles < t = the depth carried into tile t.  One CTA:
+// every thread owns a run of consecutive tiles (local sums), one block scan of the 1024 run totals, then the run is
+// written out.  Both scans ride in one 64-bit word: events in the high half, net depth (signed) in the low half.
 __global__ void __launch_bounds__(1024) depth_evscan_kernel(const int* __restrict__ tile_starts, const int* __restrict__ tile_ends, int num_tiles,
                                                            unsigned* __restrict__ bucket_off, int* __restrict__ carry) {
     __shared__ long long s_w[32];
-    __shared__ long long s_c[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_c[0] = 0; s_c[1] = 0; }
-    __syncthreads();
-    for (int base = 0; base <= num_tiles; base += 1024) {
-        const int i = base + tid;
+    const int per = (num_tiles + 1 + 1023) / 1024;                   // entries 0 .. num_tiles (the last one closes the last bucket)
+    const int b = tid * per, e = min(num_tiles + 1, b + per);
+    long long loc = 0;
+    for (int i = b; i < e; i++) {
         const int st = i < num_tiles ? tile_starts[i] : 0, en = i < num_tiles ? tile_ends[i] : 0;
-        // pack both scans in one 64-bit lane: events in the high word, net depth (can be negative inside) in the low word
-        long long v = ((long long)(st + en) << 32) + (long long)(st - en);
-        long long inc = v;
+        loc += ((long long)(st + en) << 32) + (long long)(st - en);
+    }
+    long long inc = loc;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += y; }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        long long wb = 0;
-        for (int k = 0; k < warp; k++) wb += s_w[k];
-        const long long tot = s_c[0] + wb + inc - v;                 // exclusive
-        if (i <= num_tiles) {
-            const long long lo = (long long)(int)(tot & 0xffffffffll);   // low word, sign-extended
-            const long long hi = (tot - lo) >> 32;
-            bucket_off[i] = (unsigned)hi;
-            carry[i] = (int)lo;
-        }
-        __syncthreads();
-        if (tid == 1023) s_c[0] = s_c[0] + wb + inc;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    long long run = inc - loc;                                       // exclusive prefix of this thread's run
+    for (int k = 0; k < warp; k++) run += s_w[k];
+    for (int i = b; i < e; i++) {
+        const long long lo = (long long)(int)(run & 0xffffffffll);   // low word, sign-extended
+        bucket_off[i] = (unsigned)((run - lo) >> 32);
+        carry[i] = (int)lo;
+        const int st = i < num_tiles ? tile_starts[i] : 0, en = i < num_tiles ? tile_ends[i] : 0;
+        run += ((long long)(st + en) << 32) + (long long)(st - en);
     }
 }
 
-// K_evtile: one CTA per tile: zero 16 KB, the tile's events into shared memory, tile core
-__global__ void __launch_bounds__(kScanThreads, 4) depth_evtile_kernel(const ScanParams p, const unsigned short* __restrict__ events,
-                                                                       const unsigned* __restrict__ bucket_off, const int* __restrict__ carry) {
+// K_evtile: one 128-thread CTA per tile (32 bases per thread, the core K_fused8 uses): zero 16 KB, the tile's events
+// into shared memory, tile core
+constexpr int kEvThreads = 128;
+constexpr int kEvWarps = kEvThreads / 32;
+constexpr int kEvBPT = kTile / kEvThreads;
+__global__ void __launch_bounds__(kEvThreads) depth_evtile_kernel(const ScanParams p, const unsigned short* __restrict__ events,
+                                                                  const unsigned* __restrict__ bucket_off, const int* __restrict__ carry) {
     __shared__ __align__(16) int s_tile[kTile];
     __shared__ __align__(16) int s_depth[kTile];
-    __shared__ int s_carry[kWarps];
+    __shared__ int s_carry[kEvWarps];
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
 #pragma unroll
-    for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);
-    if (tid < kWarps) s_carry[tid] = tid == 0 ? carry[tile] : 0;
+    for (int j = 0; j < kEvBPT / 4; j++) reinterpret_cast<int4*>(s_tile)[tid * (kEvBPT / 4) + j] = make_int4(0, 0, 0, 0);
+    if (tid < kEvWarps) s_carry[tid] = tid == 0 ? carry[tile] : 0;
     const unsigned lo = bucket_off[tile], hi = bucket_off[tile + 1];
     __syncthreads();
-    for (unsigned i = lo + tid; i < hi; i += kScanThreads) {
+    for (unsigned i = lo + tid; i < hi; i += kEvThreads) {
         const unsigned ev = events[i];
-        atomicAdd(s_tile + swz_elem((int)(ev & (kTile - 1))), (ev >> 15) ? -1 : 1);
+        atomicAdd(s_tile + swz_elem_t<kEvBPT>((int)(ev & (kTile - 1))), (ev >> 15) ? -1 : 1);
     }
     __syncthreads();
     int acc_max = 0;
-    tile_core<16, kWarps, false>(p, s_tile, s_depth, s_carry, tile, acc_max);
+    tile_core<kEvBPT, kEvWarps, false>(p, s_tile, s_depth, s_carry, tile, acc_max);
     flush_max(p, acc_max);
 }
 
@@ -1639,13 +1640,15 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
             const unsigned fused_grid = (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 4);
             if (fused) depth_fused_kernel<<<fused_grid, kScanThreads, 0, ctx->stream>>>(p);
             else if (hbm_diff) depth_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p);
-            else depth_evtile_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p, evl.events, evl.bucket_off, evl.carry);
+            else depth_evtile_kernel<<<(unsigned)tiles, kEvThreads, 0, ctx->stream>>>(p, evl.events, evl.bucket_off, evl.carry);
         }
         GL_LAUNCHED(ctx, 1);
         if (do_runs) {
+            // the run table has one entry per warp chunk of the kernel that ran (8 per tile, 4 for the 32-bases-per-thread K_evtile)
+            const int64_t chunks_now = tiles * ((fused || hbm_diff) ? kWarps : kEvWarps);
             gl_prof_scope prof(ctx, "depth_gather_runs_kernel");
-            depth_gather_runs_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, ctx->stream>>>(
-                header, chunk_runs, super_cnt, (int)chunks, p.tmp_start, p.tmp_class, static_cast<int*>(ctx->run_start.p),
+            depth_gather_runs_kernel<<<(unsigned)((chunks_now + 255) / 256), 256, 0, ctx->stream>>>(
+                header, chunk_runs, super_cnt, (int)chunks_now, p.tmp_start, p.tmp_class, static_cast<int*>(ctx->run_start.p),
                 static_cast<unsigned char*>(ctx->run_class.p), cap);
             GL_LAUNCHED(ctx, 1);
         }

@@ -672,14 +672,19 @@ __global__ void __launch_bounds__(256) depthwed_i32_kernel(const int* __restrict
 // per-block rotated order so that all NVLink links carry traffic all the time.  Stores to a peer are complete when the
 // kernel is; the ranks then meet at a host barrier.
 struct WedPeers { int* dst[16]; };
+// A CTA takes 32 rows (groups) x 128 samples.  Phase 1 reads the sample-major input coalesced along the rows (one warp
+// instruction = 32 consecutive rows of one sample) and parks the group sums in shared memory; phase 2 stores them
+// row-major with 16-BYTE stores: a lane owns 4 consecutive samples of one row, a warp instruction covers 512 B of it —
+// NVLink likes wide stores (4-byte stores reached a quarter of the link rate).  Needs row_stride and col_off to be
+// multiples of 4 (callers pad the per-rank width to a multiple of 4); otherwise scalar stores.
 __global__ void __launch_bounds__(256) depthwed_i32_p2p_kernel(const int* __restrict__ depth, int S, long long R, const long long* __restrict__ grp,
                                                               long long g_begin, long long g_end, int simple, WedPeers peers, int world,
                                                               long long row_stride, int col_off, int* __restrict__ overflow) {
-    __shared__ int s_t[32][33];
+    __shared__ __align__(16) int s_t[32][132];                     // [row][sample], padded: 132 keeps int4 alignment and spreads banks
     const long long g0 = g_begin + (long long)blockIdx.x * 32;
-    const int s0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
-    for (int k = ty; k < 32; k += 8) {                             // k: sample inside the tile, tx: group
+    const int s0 = blockIdx.y * 128;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 lanes x 8 warps
+    for (int k = ty; k < 128; k += 8) {                            // k: sample inside the tile, tx: row
         const int s = s0 + k;
         const long long g = g0 + tx;
         long long acc = 0;
@@ -688,19 +693,26 @@ __global__ void __launch_bounds__(256) depthwed_i32_p2p_kernel(const int* __rest
             for (long long r = a; r < b; r++) acc += depth[(size_t)s * R + r];
             if (acc > 2147483647ll || acc < -2147483648ll) *overflow = 1;
         }
-        s_t[k][tx] = (int)acc;
+        s_t[tx][k] = (int)acc;
     }
     __syncthreads();
+    const bool vec = ((row_stride | (long long)col_off) & 3) == 0;
     const int rot = (int)((blockIdx.x + blockIdx.y) % (unsigned)world);
-    for (int k = ty; k < 32; k += 8) {                             // k: group inside the tile, tx: sample
+    for (int k = ty; k < 32; k += 8) {                             // k: row inside the tile, tx: 4 consecutive samples
         const long long g = g0 + k;
-        const int s = s0 + tx;
-        if (s < S && g < g_end) {
-            const int v = s_t[tx][k];
-            const size_t at = (size_t)g * (size_t)row_stride + (size_t)(col_off + s);
-            for (int d = 0; d < world; d++) {
-                int dd = d + rot; if (dd >= world) dd -= world;
-                peers.dst[dd][at] = v;
+        const int s = s0 + 4 * tx;
+        if (g >= g_end || s >= S) continue;
+        const size_t at = (size_t)g * (size_t)row_stride + (size_t)(col_off + s);
+        const int4 v = *reinterpret_cast<const int4*>(&s_t[k][4 * tx]);
+        for (int d = 0; d < world; d++) {
+            int dd = d + rot; if (dd >= world) dd -= world;
+            int* dst = peers.dst[dd] + at;
+            if (vec && s + 3 < S) *reinterpret_cast<int4*>(dst) = v;
+            else {
+                dst[0] = v.x;
+                if (s + 1 < S) dst[1] = v.y;
+                if (s + 2 < S) dst[2] = v.z;
+                if (s + 3 < S) dst[3] = v.w;
             }
         }
     }
@@ -1237,7 +1249,7 @@ int gl_depthwed_aggregate_i32_p2p(gl_ctx* ctx, const int32_t* d_depth, int32_t S
     WedPeers peers;
     for (int d = 0; d < 16; d++) peers.dst[d] = d < world ? d_dst[d] : nullptr;
     for (int d = 0; d < world; d++) if (!peers.dst[d]) return gl_fail(ctx, GL_EINVAL, "gl_depthwed_aggregate_i32_p2p: null destination %d", d);
-    dim3 grid((unsigned)((g_end - g_begin + 31) / 32), (unsigned)((S + 31) / 32));
+    dim3 grid((unsigned)((g_end - g_begin + 31) / 32), (unsigned)((S + 127) / 128));
     {
         gl_prof_scope prof(ctx, "depthwed_i32_p2p_kernel");
         depthwed_i32_p2p_kernel<<<grid, 256, 0, ctx->stream>>>(d_depth, S, R, reinterpret_cast<const long long*>(d_grp), g_begin, g_end, d_grp ? 0 : 1,

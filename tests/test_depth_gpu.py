@@ -414,7 +414,7 @@ def test_packed8_streamed_upload(ctx):
                  np.ascontiguousarray(ln.reshape(nb, 64)[perm]).reshape(-1))
     exp = orc.pileup_diff(s, e, 0, L)
     ws, r0, rc = ctx.depth_region_packed8(0, L, hs[0], hs[1], hs[2], 500, 4, 0)
-    assert ctx.depth_last_path() in (1, 2)
+    assert ctx.depth_last_path() in (1, 4)                     # unsorted anchors are rejected: the batch is unpacked, the general path takes it
     ea, ec = orc.class_runs(exp, 0, L, 4, 0, 0)
     assert np.array_equal(ws, orc.window_sums(exp, 0, L, 500)[0]) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
 
@@ -432,7 +432,7 @@ def test_packed8_unsorted_anchors_fall_back(ctx):
     l2 = np.ascontiguousarray(ln.reshape(nb, 64)[perm]).reshape(-1)
     exp = orc.pileup_diff(s, e, 0, L)
     ws, r0, rc = ctx.depth_region_packed8(0, L, a2, d2, l2, 500, 4, 0)
-    assert ctx.depth_last_path() in (1, 2)
+    assert ctx.depth_last_path() in (1, 4)                     # unsorted anchors are rejected: the batch is unpacked, the general path takes it
     ea, ec = orc.class_runs(exp, 0, L, 4, 0, 0)
     assert np.array_equal(ws, orc.window_sums(exp, 0, L, 500)[0]) and np.array_equal(r0, ea) and np.array_equal(rc, ec)
 

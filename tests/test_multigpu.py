@@ -130,18 +130,19 @@ def _nccl_worker(rank, world, uid, q, shared=None, bar=None):
     ok32 = bool(np.array_equal(got, depth.T)) and int(d_ovf.download(np.int32, 1)[0]) == 0
     # the fused form: every rank's kernel stores its columns into both ranks' row-major matrices over peer memory
     if shared is not None:
-        row_stride = width * world
+        wpad = (width + 3) // 4 * 4
+        row_stride = wpad * world
         d_full = c.dev_array(np.full(R2 * row_stride, -1, np.int32))
         shared[rank * 64:(rank + 1) * 64] = list(c.ipc_export(d_full))
         bar.wait()
         ptrs = [d_full.ptr if r == rank else c.ipc_open(bytes(shared[r * 64:(r + 1) * 64])) for r in range(world)]
-        c.depthwed_aggregate_i32_p2p(d_depth, width, R2, None, 0, R2, ptrs, row_stride, rank * width, d_ovf)
+        c.depthwed_aggregate_i32_p2p(d_depth, width, R2, None, 0, R2, ptrs, row_stride, rank * wpad, d_ovf)
         c.sync()
         bar.wait()
         m = d_full.download(np.int32, R2 * row_stride).reshape(R2, row_stride)
         for r in range(world):
             rlo, rhi = multigpu.shard_range(S2, r, world)
-            ok32 = ok32 and bool(np.array_equal(m[:, r * width:r * width + (rhi - rlo)], depth[rlo:rhi].T))
+            ok32 = ok32 and bool(np.array_equal(m[:, r * wpad:r * wpad + (rhi - rlo)], depth[rlo:rhi].T))
         bar.wait()
         for r in range(world):
             if r != rank:
