@@ -686,6 +686,9 @@ static int cmd_indexcov(int argc, char** argv) {
     }
 
     // indexes (indexcov.go:471-525)
+    const bool ic_timing = getenv("GL_TIMING") != nullptr;               // phase wall clocks on stderr
+    double ic_t0 = now_s(), ic_tp = ic_t0;
+    auto ic_mark = [&](const char* what) { if (ic_timing) { const double t = now_s(); fprintf(stderr, "[indexcov timing] %-28s %.3f s\n", what, t - ic_tp); ic_tp = t; } };
     const size_t S = bams.size();
     std::vector<std::string> names(S);
     std::vector<glhts::BaiIndex> idx(S);
@@ -706,8 +709,10 @@ static int cmd_indexcov(int argc, char** argv) {
         else { glhts::BamHeader h; std::string he = glhts::bam_read_header(b, h); if (!he.empty()) fatal(1, "%s", he.c_str()); names[i] = short_name(b, false, &h); }
     }
 
+    ic_mark("read indexes");
     gl_ctx* ctx = nullptr;
     if (gl_ctx_create(0, &ctx) != GL_OK) fatal(1, "goleft indexcov: %s", gl_last_error(nullptr));
+    ic_mark("gl_ctx_create");
     fprintf(stderr, "indexcov: running on %zu indexes\n", S);
 
     // ---- I1 for the whole cohort in ONE launch (indexcov/types.go:45-82): every sample's linear-index offsets go up once,
@@ -779,6 +784,7 @@ static int cmd_indexcov(int argc, char** argv) {
     glck(ctx, gl_memcpy_d2h(ctx, med.data(), d_med, (int64_t)S * 8), "gl_memcpy_d2h");
     glck(ctx, gl_memcpy_d2h(ctx, dep.data(), d_dep, total * 4), "gl_memcpy_d2h");
     gl_dev_free(ctx, d_sizes); gl_dev_free(ctx, d_sp); gl_dev_free(ctx, d_med);
+    ic_mark("I1 + I2 + I3 (GPU, + D2H)");
 
     const std::string base = dir + "/" + dir.substr(dir.find_last_of('/') == std::string::npos ? 0 : dir.find_last_of('/') + 1) + "-indexcov";
     glhts::BgzfWriter bgz(base + ".bed.gz");
@@ -838,6 +844,7 @@ static int cmd_indexcov(int argc, char** argv) {
         }
     }
     gl_dev_free(ctx, d_dep);
+    ic_mark("tokens + counts (GPU, + D2H)");
 
     std::map<std::string, std::vector<double>> sexes;
     std::vector<int64_t> bins(S * 4, 0);
@@ -943,8 +950,10 @@ static int cmd_indexcov(int argc, char** argv) {
             }
         }
     }
+    ic_mark("rows + roc per reference");
     bgz.close();
     fclose(roc);
+    ic_mark("bgzf close");
     for (size_t k = 0; k < S; k++) slopes[k] = slopes[k] / (float)n_slopes;
     if (sexes.size() != sexes_wanted.size()) {                              // checkSexes (indexcov.go:760-770)
         std::string keys; for (auto& kv : sexes) keys += (keys.empty() ? "" : ",") + kv.first;
@@ -992,6 +1001,7 @@ static int cmd_indexcov(int argc, char** argv) {
         }
     }
     gl_ctx_destroy(ctx);
+    if (ic_timing) fprintf(stderr, "[indexcov timing] %-28s %.3f s\n", "total", now_s() - ic_t0);
     return 0;
 }
 

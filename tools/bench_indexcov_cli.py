@@ -58,6 +58,7 @@ def main():
                                                               for i, L in enumerate(HS37D5)))
         out = os.path.join(tmp, "out")
         t0 = time.perf_counter()
+        os.environ["GL_TIMING"] = "1"
         p = subprocess.run([exe, "indexcov", "-d", out, "--fai", os.path.join(tmp, "ref.fai"), "--includegl", "--excludepatt", "^$"] + paths, capture_output=True, text=True)
         wall = time.perf_counter() - t0
         if p.returncode != 0:
@@ -66,7 +67,9 @@ def main():
         bed = os.path.join(out, "out-indexcov.bed.gz")
         res = {"samples": args.samples, "tiles_per_sample": tiles, "tile_samples": args.samples * tiles, "index_bytes": sum(os.path.getsize(x) for x in paths),
                "write_indexes_s": t_write, "cli_wall_s": wall, "tile_samples_per_s": args.samples * tiles / wall,
-               "bed_gz_bytes": os.path.getsize(bed), "host_threads": os.cpu_count(), "stderr_tail": p.stderr.strip().splitlines()[-2:]}
+               "bed_gz_bytes": os.path.getsize(bed), "host_threads": os.cpu_count(),
+               "phases": [ln.replace("[indexcov timing]", "").strip() for ln in p.stderr.splitlines() if ln.startswith("[indexcov timing]")],
+               "stderr_tail": p.stderr.strip().splitlines()[-2:]}
         print(json.dumps(res))
     finally:
         if not args.keep:
