@@ -2154,12 +2154,13 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
     GL_CHECK(gl_use(ctx));
     GL_CHECK(bed_args_ok(ctx, rs, re, W, step));
     if (n < 0 || (n > 0 && (!start || !end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_region: bad segments");
-    // How the int32 arrays travel (GL_BED_PACK): the call is PCIe-bound at 8 B/segment, so by default (16) the host pool
-    // repacks them, order-preserving and without a sort, to packed16 (4 B/segment: int32 anchor per 256 slots + uint16
-    // offset / length) in 8 index chunks — chunk k+1 is packed while chunk k is on the wire and chunk k-1 is unpacked on the
-    // device.  0: upload as they are.  1: packed8 (2 B/segment, needs a sort: 2-3 ms per 11 M segments on the 2 x 32-core
-    // host, more than it saves; a feeder that emits packed8 itself calls gl_depth_bed_region_packed8).
-    static const int force = [] { const char* e = getenv("GL_BED_PACK"); return e ? atoi(e) : 16; }();
+    // How the int32 arrays travel (GL_BED_PACK).  0 (default): as they are — the call is PCIe-bound at 8 B/segment (chr20:
+    // 88 MB, 1.9 ms) and that is still the fastest on the B200 box's host.  16: the host pool repacks them, order-preserving
+    // and without a sort, to packed16 (4 B/segment) in 8 index chunks pipelined with the upload — measured: the repack
+    // costs 1.3 ms on 128 threads (3.4 ms on 32) plus 16 pool dispatches, 2.5-3.3 ms per call at best with a long tail, so
+    // it does not pay.  1: packed8 (2 B/segment, needs a sort: 2-3 ms).  A feeder that emits packed8 itself (gl_bam_decode)
+    // calls gl_depth_bed_region_packed8: 0.65 ms.  tools/e2e_text_probe.py measures all three.
+    static const int force = [] { const char* e = getenv("GL_BED_PACK"); return e ? atoi(e) : 0; }();
     if (force == 16 && n >= (int64_t(1) << 18)) {
         const int K = 8;
         int64_t cap = n / 256 + n / 1024 + 64 * K;                     // blocks: full ones + slack for sparse stretches
