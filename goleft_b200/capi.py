@@ -132,6 +132,7 @@ _proto("gl_bam_close", None, _vp)
 _proto("gl_bam_info", C.c_int, _vp, _i32p, _i32p)
 _proto("gl_bam_ref", C.c_int, _vp, C.c_int32, C.POINTER(C.c_char_p), _i64p, _i64p)
 _proto("gl_bam_decode", C.c_int, _vp, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int64)
+_proto("gl_bgzf_inflate_device", C.c_int, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp)
 _proto("gl_bai_read", C.c_int, C.c_char_p, C.POINTER(_vp), _vp, C.c_int64)
 _proto("gl_bai_n_refs", C.c_int, _vp, _i32p, _u64p)
 _proto("gl_bai_ref", C.c_int, _vp, C.c_int32, C.POINTER(_vp), _i64p, _u64p, _u64p, _i32p)
@@ -736,6 +737,28 @@ class Ctx:
         if raw:
             return hl.value, cl.value
         return hd[: hl.value].tobytes(), ca[: cl.value].tobytes()
+
+    def bgzf_inflate(self, data: bytes):
+        """GPU inflate of a whole BGZF byte string -> (inflated bytes, per-block status int32[]); test / tool helper"""
+        b = np.frombuffer(data, np.uint8)
+        offs, outs, p = [0], [0], 0
+        while p + 18 <= b.size:
+            bs = int(b[p + 16]) + (int(b[p + 17]) << 8) + 1
+            if p + bs > b.size:
+                break
+            isize = int.from_bytes(bytes(b[p + bs - 4:p + bs]), "little")
+            p += bs
+            offs.append(p); outs.append(outs[-1] + isize)
+        nb = len(offs) - 1
+        d_c, d_co, d_oo = self.dev_array(b), self.dev_array(np.array(offs, np.int64)), self.dev_array(np.array(outs, np.int64))
+        d_out, d_st = self.dev_empty(max(outs[-1], 16)), self.dev_array(np.full(max(nb, 1), -1, np.int32))
+        try:
+            self._ck(lib.gl_bgzf_inflate_device(self.h, d_c.ptr, d_co.ptr, d_oo.ptr, nb, d_out.ptr, d_st.ptr))
+            self.sync()
+            return d_out.download(np.uint8, outs[-1]).tobytes(), d_st.download(np.int32, nb)
+        finally:
+            for x in (d_c, d_co, d_oo, d_out, d_st):
+                x.free()
 
     # ---- indexcov
     def indexcov_sizes(self, voff: np.ndarray, ref_ptr: np.ndarray):

@@ -299,6 +299,12 @@ int  gl_bam_info(const gl_bam* b, int32_t* n_refs, int32_t* has_index);
 int  gl_bam_ref(const gl_bam* b, int32_t tid, const char** name, int64_t* length, int64_t* n_mapped /* -1: no stats bin */);
 int  gl_bam_decode(gl_bam* b, int32_t tid, int64_t beg, int64_t end, int32_t min_mapq, int32_t threads, int32_t want_format,
                    gl_bam_segments* out, char* err, int64_t err_cap);
+/* BGZF inflate ON THE GPU (inflate.cu): one warp per BGZF member, thousands in flight — the stage the reference's samtools
+ * children (and this library's host feeder) spend their time in.  Block b = d_comp[comp_off[b], comp_off[b+1]) (the whole
+ * member) -> d_out[out_off[b], out_off[b+1]), out_off from the members' ISIZE fields; d_status[b] != 0: malformed or
+ * unsupported member (fall back to zlib).  Device pointers; asynchronous on the ctx stream. */
+int  gl_bgzf_inflate_device(gl_ctx* ctx, const uint8_t* d_comp, const int64_t* d_comp_off, const int64_t* d_out_off, int64_t n_blocks,
+                            uint8_t* d_out, int32_t* d_status);
 /* BAI: per-reference linear index (16 KB tiles) + the 0x924a stats bin (indexcov/types.go:19,45-58),
  * what indexcov takes from biogo's bam.ReadIndex (indexcov/indexcov.go:514). */
 typedef struct gl_bai gl_bai;
