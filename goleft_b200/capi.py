@@ -132,6 +132,7 @@ _proto("gl_bam_close", None, _vp)
 _proto("gl_bam_info", C.c_int, _vp, _i32p, _i32p)
 _proto("gl_bam_ref", C.c_int, _vp, C.c_int32, C.POINTER(C.c_char_p), _i64p, _i64p)
 _proto("gl_bam_decode", C.c_int, _vp, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int64)
+_proto("gl_bam_decode_device", C.c_int, _vp, _vp, C.c_int32, C.c_int32, C.POINTER(_vp), C.POINTER(_vp), _i64p, _vp)
 _proto("gl_bgzf_inflate_device", C.c_int, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp)
 _proto("gl_bai_read", C.c_int, C.c_char_p, C.POINTER(_vp), _vp, C.c_int64)
 _proto("gl_bai_n_refs", C.c_int, _vp, _i32p, _u64p)
@@ -403,6 +404,26 @@ class Bam:
             out["start"] = np.ctypeslib.as_array(C.cast(o.a0, _i32p), (o.n,)).copy()
             out["end"] = np.ctypeslib.as_array(C.cast(o.a1, _i32p), (o.n,)).copy()
         return out
+
+
+def bam_decode_device(ctx: "Ctx", bam: Bam, tid: int, min_mapq: int = 1):
+    """The GPU feeder (BGZF inflate + record parse on the device) -> dict(start, end (copies), stats); GlError(GL_ESTATE) when
+    the reference cannot be done on the device."""
+    o = _BamSegments()
+    ps, pe, n = _vp(), _vp(), C.c_int64(0)
+    rc = lib.gl_bam_decode_device(ctx.h, bam.h, tid, min_mapq, C.byref(ps), C.byref(pe), C.byref(n), C.byref(o))
+    if rc != GL_OK:
+        raise GlError(rc, lib.gl_last_error(ctx.h).decode())
+    out = {"n": n.value, "units": o.units, "max_len": o.max_len, "n_records": o.n_records, "n_pass": o.n_pass, "bytes_in": o.bytes_in,
+           "bytes_out": o.bytes_out, "inflate_s": o.inflate_s, "parse_s": o.parse_s, "wall_s": o.wall_s, "d_start": ps.value, "d_end": pe.value}
+    if n.value:
+        s_, e_ = np.empty(n.value, np.int32), np.empty(n.value, np.int32)
+        ctx._ck(lib.gl_memcpy_d2h(ctx.h, _ptr(s_), ps.value, n.value * 4))
+        ctx._ck(lib.gl_memcpy_d2h(ctx.h, _ptr(e_), pe.value, n.value * 4))
+        out["start"], out["end"] = s_, e_
+    else:
+        out["start"], out["end"] = np.zeros(0, np.int32), np.zeros(0, np.int32)
+    return out
 
 
 def crai_make_sizes(start, span, nbytes) -> np.ndarray:

@@ -74,6 +74,7 @@ struct gl_ctx {
     void* pack_pinned = nullptr; size_t pack_pinned_bytes = 0;   // gl_depth_bed_contig: pinned home of the packed8 words it makes
     gl_buf flush;         // L2 flush scratch
     gl_buf misc;          // small outputs of other subsystems
+    gl_buf bam_comp, bam_out, bam_seg;   // bamgpu.cu: compressed bytes + tables, inflated stream, decoded segments
     gl_buf text_slots, text_blk, text_len, text_out[2];   // depth_text.cu: row slots, block offsets, lengths, compact BED text (depth, callable)
     gl_buf fasta;         // raw FASTA bytes of one record (gl_fasta_load), newlines included
     int64_t fasta_n = 0;

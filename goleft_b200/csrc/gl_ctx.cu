@@ -178,6 +178,7 @@ int gl_ctx_destroy(gl_ctx* ctx) {
     buf_free(ctx->run_tmp_start); buf_free(ctx->run_tmp_class);
     buf_free(ctx->store_s); buf_free(ctx->store_e); buf_free(ctx->packed);
     buf_free(ctx->seg[0]); buf_free(ctx->seg[1]); buf_free(ctx->flush); buf_free(ctx->misc); buf_free(ctx->fasta);
+    buf_free(ctx->bam_comp); buf_free(ctx->bam_out); buf_free(ctx->bam_seg);
     buf_free(ctx->text_slots); buf_free(ctx->text_blk); buf_free(ctx->text_len); buf_free(ctx->text_out[0]); buf_free(ctx->text_out[1]);
     for (int i = 0; i < 2; i++) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);

@@ -42,9 +42,14 @@ public:
     // M/=/X blocks of the records of reference `tid` that pass (flag & 0x704) == 0 && MAPQ >= min_mapq and can overlap
     // [beg, end).  want: 0 = choose (packed8 unless the blocks are long), 8, 32.  Needs the index.
     std::string decode(int tid, int64_t beg, int64_t end, int min_mapq, int threads, int want, ContigSegs& out, DecodeStats* st);
+    int fd() const { return fd_; }
+    int64_t file_size() const { return size_; }
 private:
     int fd_ = -1;
     int64_t size_ = 0;
 };
 
 }  // namespace glhts
+
+// the C ABI's opaque BAM handle (feeder_api.cpp, bamgpu.cu)
+struct gl_bam { glhts::BamFile f; glhts::ContigSegs segs; };

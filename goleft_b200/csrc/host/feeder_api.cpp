@@ -9,7 +9,6 @@
 
 struct gl_segset { glhts::SegmentSet s; };
 struct gl_bai { glhts::BaiIndex b; };
-struct gl_bam { glhts::BamFile f; glhts::ContigSegs segs; };
 
 static void put_err(char* err, int64_t cap, const std::string& m) {
     if (!err || cap <= 0) return;

@@ -45,6 +45,7 @@ extern "C" {
 #define GL_TILE_WIDTH     16384
 
 typedef struct gl_ctx gl_ctx;
+typedef struct gl_bam gl_bam;            /* an open BAM + its index (gl_bam_open) */
 
 /* ---------------------------------------------------------------- context */
 const char* gl_version(void);                       /* "goleft_b200 <semver> sm_100a" */
@@ -285,7 +286,6 @@ void gl_segset_free(gl_segset* s);
  *   format 32 : (a0 = int32 start[n], a1 = int32 end[n]) sorted by start,
  * want_format 0 chooses (packed8 unless the blocks average more than 400 bases: long reads).  The arrays belong to the
  * handle and stay valid until its next gl_bam_decode / gl_bam_close; one handle per decoding thread. */
-typedef struct gl_bam gl_bam;
 typedef struct {
     int32_t format, units, max_len, _pad;
     int64_t n;
@@ -299,6 +299,14 @@ int  gl_bam_info(const gl_bam* b, int32_t* n_refs, int32_t* has_index);
 int  gl_bam_ref(const gl_bam* b, int32_t tid, const char** name, int64_t* length, int64_t* n_mapped /* -1: no stats bin */);
 int  gl_bam_decode(gl_bam* b, int32_t tid, int64_t beg, int64_t end, int32_t min_mapq, int32_t threads, int32_t want_format,
                    gl_bam_segments* out, char* err, int64_t err_cap);
+/* The whole feeder on the GPU for one reference of an indexed BAM: its compressed BGZF range is read into pinned memory and
+ * uploaded, every member is inflated by a warp (gl_bgzf_inflate_device), the records between consecutive linear-index
+ * offsets are walked by one thread each (filter + CIGAR, as gl_bam_decode), and the M/=/X blocks land in ctx-owned device
+ * arrays *d_start / *d_end (*n of them, BAM order; valid until the next call on this ctx) — feed them to
+ * gl_depth_add_segments_device.  Only compressed bytes cross PCIe.  GL_ESTATE: not possible for this reference on the device
+ * (no usable index, a member or record the device code rejects): use gl_bam_decode. */
+int  gl_bam_decode_device(gl_ctx* ctx, gl_bam* b, int32_t tid, int32_t min_mapq, const int32_t** d_start, const int32_t** d_end, int64_t* n,
+                          gl_bam_segments* stats);
 /* BGZF inflate ON THE GPU (inflate.cu): one warp per BGZF member, thousands in flight — the stage the reference's samtools
  * children (and this library's host feeder) spend their time in.  Block b = d_comp[comp_off[b], comp_off[b+1]) (the whole
  * member) -> d_out[out_off[b], out_off[b+1]), out_off from the members' ISIZE fields; d_status[b] != 0: malformed or

@@ -86,3 +86,44 @@ def test_malformed_members_are_flagged(ctx):
     z2[0] = 0
     _, status = ctx.bgzf_inflate(bytes(z2))
     assert status[0] == 1
+
+
+def test_gpu_feeder_equals_generator_and_host_feeder(ctx, tmp_path):
+    """gl_bam_decode_device: inflate + parse + filter + CIGAR walk on the device give exactly the generator's segments in BAM
+    order, for every reference; the depth text from them equals the host-feeder route"""
+    from goleft_b200 import capi
+    sys.path.insert(0, os.path.join(ROOT, "tools", "synth"))
+    import glsynth
+    contigs = [("chrA", 2_500_000, 1), ("chrB", 300_000, 2), ("chrM", 16_569, 24)]
+    bam = str(tmp_path / "g.bam")
+    glsynth.write_bam(bam, contigs, coverage=15.0)
+    b = capi.Bam(bam)
+    for tid, (nm, L, idx) in enumerate(contigs):
+        s, e = glsynth.segments(L, idx, coverage=15.0)
+        d = capi.bam_decode_device(ctx, b, tid)
+        assert d["n"] == s.size and np.array_equal(d["start"], s) and np.array_equal(d["end"], e), nm
+        host = b.decode(tid, want=32)
+        assert d["n_records"] == host["n_records"] and d["n_pass"] == host["n_pass"]
+    # MAPQ threshold and a BAM made by the Python writer (other record layouts: mates, unplaced reads at the end)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bamutil import make_bam_indexed
+    rng = np.random.default_rng(2)
+    refs = [("chrM", 16571), ("chr22", 300001)]
+    recs = []
+    for t, (nm, L) in enumerate(refs):
+        for p0 in np.sort(rng.integers(0, L - 200, 40000)):
+            cig = [[(100, "M")], [(45, "M"), (7, "D"), (55, "M")], [(30, "M"), (2, "I"), (68, "M")], [(12, "S"), (88, "M")], [(20, "M"), (300, "N"), (80, "M")],
+                   [(50, "="), (1, "X"), (49, "=")]][int(rng.integers(0, 6))]
+            recs.append((t, int(p0), int(rng.choice([0, 5, 30, 60])), int(rng.choice([0, 16, 0x400, 0x100, 0x200, 0x800, 4])), cig))
+    recs.append((-1, -1, 0, 4, [(100, "M")]))
+    bam_b, bai_b = make_bam_indexed(refs, recs)
+    p = tmp_path / "p.bam"
+    p.write_bytes(bam_b); (tmp_path / "p.bam.bai").write_bytes(bai_b)
+    b2 = capi.Bam(str(p))
+    for q in (1, 20):
+        old = capi.bam_segments(str(p), q, 2)
+        for t in range(2):
+            d = capi.bam_decode_device(ctx, b2, t, min_mapq=q)
+            es, ee = old["segments"].get(t, (np.zeros(0, np.int32), np.zeros(0, np.int32)))
+            assert np.array_equal(d["start"], es) and np.array_equal(d["end"], ee), (q, t)
+    b.close(); b2.close()
