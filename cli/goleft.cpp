@@ -177,6 +177,7 @@ struct DepthJob {                                   // one contig (.fai mode) or
     std::string hd, ca;                             // .fai mode output
     double decode_s = 0, gpu_s = 0, inflate_s = 0, parse_s = 0;
     long long records = 0, bytes_in = 0, bytes_out = 0;
+    int gpu_fed = 0;                                // passes whose segments came from the GPU feeder
     bool done = false;
 };
 
@@ -197,9 +198,11 @@ struct DepthEngine {
     DepthShared& sh;
     const DepthOpts& o;
     gl_ctx* ctx = nullptr;
-    glhts::BamFile bam;
+    gl_bam gbam;                                            // the library's BAM handle: its BamFile is the host feeder,
+    glhts::BamFile& bam = gbam.f;                           // gl_bam_decode_device runs the feeder on the GPU
     std::map<std::string, int> tid_of;
     glhts::ContigSegs segs;
+    const int32_t* dev_s = nullptr; const int32_t* dev_e = nullptr; int64_t dev_n = -1;   // segments left on the device by the GPU feeder (-1: none)
     std::vector<int64_t> sums; std::vector<int32_t> rstart; std::vector<uint8_t> rclass;
     std::vector<char> tbuf_hd, tbuf_ca;
     // --stats state (depth.go:191-200,246-252): chunks of a contig are parked, one gl_fasta_stats launch for all their rows
@@ -220,11 +223,26 @@ struct DepthEngine {
     }
     ~DepthEngine() { gl_ctx_destroy(ctx); }
 
-    // segments of [beg,end) of a contig into `segs` (packed8 or sorted int32); want: 0 auto, 32 int32
-    void fetch(const std::string& c, long long beg, long long end, int want, DepthJob* job) {
+    // segments of [beg,end) of a contig into `segs` (packed8 or sorted int32); want: 0 auto, 32 int32.
+    // whole = the complete reference is wanted: the GPU feeder (BGZF inflate + record parse on the device, only compressed
+    // bytes over PCIe) takes it when it can; GL_GPU_FEED=0 keeps everything on the host feeder.
+    void fetch(const std::string& c, long long beg, long long end, int want, DepthJob* job, bool whole = false) {
         segs = glhts::ContigSegs();
+        dev_n = -1;
         auto it = tid_of.find(c);
         if (it == tid_of.end()) return;
+        static const bool gpu_feed = [] { const char* e = getenv("GL_GPU_FEED"); return !e || atoi(e) != 0; }();
+        if (whole && gpu_feed && !sh.preload) {
+            gl_bam_segments st;
+            const int rc = gl_bam_decode_device(ctx, &gbam, it->second, o.Q, &dev_s, &dev_e, &dev_n, &st);
+            if (rc == GL_OK) {
+                if (job) { job->decode_s += st.wall_s; job->inflate_s += st.inflate_s; job->parse_s += st.parse_s; job->records += st.n_records;
+                           job->bytes_in += st.bytes_in; job->bytes_out += st.bytes_out; job->gpu_fed++; }
+                return;
+            }
+            dev_n = -1;
+            if (rc != GL_ESTATE) glck(ctx, rc, "gl_bam_decode_device");      // GL_ESTATE: not possible on the device for this reference
+        }
         if (sh.preload) {                                              // unindexed BAM: slices of the preloaded arrays (record order)
             const std::vector<int32_t>& S = sh.preload->start[(size_t)it->second];
             const std::vector<int32_t>& E = sh.preload->end[(size_t)it->second];
@@ -239,6 +257,7 @@ struct DepthEngine {
     }
 
     void add_segments() {
+        if (dev_n >= 0) { if (dev_n > 0) glck(ctx, gl_depth_add_segments_device(ctx, dev_s, dev_e, dev_n), "gl_depth_add_segments_device"); return; }
         if (segs.format == 8 && segs.n_blocks > 0)
             glck(ctx, gl_depth_add_segments_packed8(ctx, segs.anchors.data(), segs.ds.data(), segs.len.data(), segs.n_blocks), "gl_depth_add_segments_packed8");
         else if (segs.format == 32 && segs.n > 0)
@@ -318,10 +337,27 @@ struct DepthEngine {
         const double t_all = now_s();
         for (long long ps = 0; ps < job.len; ps += kMaxPass) {
             const long long pe = std::min(job.len, ps + kMaxPass);
-            fetch(job.chrom, ps, pe, 0, &job);
+            fetch(job.chrom, ps, pe, 0, &job, ps == 0 && pe == job.len);
             const double tg = now_s();
             const bool device_text = !o.stats && job.chrom.size() <= 64;
-            if (device_text) {
+            if (device_text && dev_n >= 0) {                                   // segments already on the device (GPU feeder)
+                const int64_t nwin = (pe - 1) / o.W - ps / o.W + 1;
+                const size_t need_hd = (size_t)gl_depth_text_bound(job.chrom.c_str(), nwin);
+                if (tbuf_hd.size() < need_hd) tbuf_hd.resize(need_hd);
+                if (tbuf_ca.size() < (size_t)(1 << 20)) tbuf_ca.resize(1 << 20);
+                glck(ctx, gl_depth_begin(ctx, ps, pe), "gl_depth_begin");
+                add_segments();
+                glck(ctx, gl_depth_reduce(ctx, o.W, o.mincov, o.maxmean, o.step), "gl_depth_reduce");
+                int64_t hl = 0, cl = 0;
+                int rc = gl_depth_text(ctx, job.chrom.c_str(), tbuf_hd.data(), (int64_t)tbuf_hd.size(), &hl, tbuf_ca.data(), (int64_t)tbuf_ca.size(), &cl);
+                if (rc == GL_ERANGE) {
+                    tbuf_hd.resize((size_t)hl + 16); tbuf_ca.resize((size_t)cl + 16);
+                    rc = gl_depth_text(ctx, job.chrom.c_str(), tbuf_hd.data(), (int64_t)tbuf_hd.size(), &hl, tbuf_ca.data(), (int64_t)tbuf_ca.size(), &cl);
+                }
+                glck(ctx, rc, "gl_depth_text");
+                job.hd.append(tbuf_hd.data(), (size_t)hl);
+                job.ca.append(tbuf_ca.data(), (size_t)cl);
+            } else if (device_text) {
                 const int64_t nwin = (pe - 1) / o.W - ps / o.W + 1;
                 const size_t need_hd = (size_t)gl_depth_text_bound(job.chrom.c_str(), nwin);
                 if (tbuf_hd.size() < need_hd) tbuf_hd.resize(need_hd);
@@ -587,12 +623,12 @@ static int cmd_depth(int argc, char** argv) {
     fclose(fca); fclose(fhd);
     if (sh.fa_map) munmap(const_cast<uint8_t*>(sh.fa_map), sh.fa_len);
     if (timing) {
-        double dec = 0, gpu = 0, inf = 0, par = 0; long long rec = 0, bin = 0, bout = 0;
-        for (const DepthJob& j : jobs) { dec += j.decode_s; gpu += j.gpu_s; inf += j.inflate_s; par += j.parse_s; rec += j.records; bin += j.bytes_in; bout += j.bytes_out; }
+        double dec = 0, gpu = 0, inf = 0, par = 0; long long rec = 0, bin = 0, bout = 0; int fed = 0;
+        for (const DepthJob& j : jobs) { fed += j.gpu_fed; dec += j.decode_s; gpu += j.gpu_s; inf += j.inflate_s; par += j.parse_s; rec += j.records; bin += j.bytes_in; bout += j.bytes_out; }
         fprintf(stderr, "{\"goleft_depth_timing\": {\"wall_s\": %.4f, \"gpus\": %d, \"jobs\": %zu, \"decode_wall_s_sum\": %.4f, \"gpu_call_s_sum\": %.4f, "
                         "\"inflate_thread_s_sum\": %.4f, \"parse_thread_s_sum\": %.4f, "
-                        "\"records\": %lld, \"bgzf_bytes_in\": %lld, \"bgzf_bytes_out\": %lld, \"host_threads\": %d}}\n",
-                now_s() - t_start, G, jobs.size(), dec, gpu, inf, par, rec, bin, bout, glhost_pool_size());
+                        "\"records\": %lld, \"bgzf_bytes_in\": %lld, \"bgzf_bytes_out\": %lld, \"host_threads\": %d, \"gpu_fed_passes\": %d}}\n",
+                now_s() - t_start, G, jobs.size(), dec, gpu, inf, par, rec, bin, bout, glhost_pool_size(), fed);
     }
     return 0;
 }

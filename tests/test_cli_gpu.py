@@ -18,8 +18,8 @@ from oracle import loader as orc  # noqa: E402
 GOLEFT = os.path.join(ROOT, "bin", "goleft")
 
 
-def run(*args, check=True):
-    p = subprocess.run([GOLEFT, *args], capture_output=True, text=True)
+def run(*args, check=True, env=None):
+    p = subprocess.run([GOLEFT, *args], capture_output=True, text=True, env=dict(os.environ, **env) if env else None)
     if check:
         assert p.returncode == 0, p.stderr
     return p
@@ -133,6 +133,13 @@ def test_depth_synthetic_bam_index_seek_and_gpus(tmp_path):
             exp_hd += h; exp_ca += c
     assert open(prefix + ".depth.bed", "rb").read() == exp_hd
     assert open(prefix + ".callable.bed", "rb").read() == exp_ca
+    assert t_all["gpu_fed_passes"] == 3                      # every reference went through the GPU feeder (inflate + parse on the device)
+    # the host feeder (zlib on the pool threads -> packed8 words) gives the same bytes
+    prefix_h = str(tmp_path / "s1h")
+    p = run("depth", "--gpus", "1", "--timing", "-w", "500", "--prefix", prefix_h, "-r", ref, bam, env={"GL_GPU_FEED": "0"})
+    assert json.loads(p.stderr.strip().splitlines()[-1])["goleft_depth_timing"]["gpu_fed_passes"] == 0
+    assert open(prefix_h + ".depth.bed", "rb").read() == exp_hd
+    assert open(prefix_h + ".callable.bed", "rb").read() == exp_ca
     # -c chrM: only chrM's BGZF blocks are read (samtools depth -r gives the reference that, depth.go:116,152)
     prefix2 = str(tmp_path / "s2")
     p = run("depth", "-c", "chrM", "--timing", "-w", "500", "--prefix", prefix2, "-r", ref, bam)
