@@ -726,60 +726,77 @@ __global__ void __launch_bounds__(256) depth_events_kernel(const int* __restrict
     }
 }
 
-// bucket_off[t] = events in tiles < t; carry[t] = (starts - ends) in tiles < t = the depth carried into tile t.  One CTA:
-// every thread owns a run of consecutive tiles (local sums), one block scan of the 1024 run totals, then the run is
-// written out.  Both scans ride in one 64-bit word: events in the high half, net depth (signed) in the low half.
+// bucket_off[t] = events in tiles < t; carry[t] = (starts - ends) in tiles < t = the depth carried into tile t.  One CTA,
+// 4096 tiles per round (coalesced loads, 4 per thread), two warp scans per round.  Both scans ride in one 64-bit word: events
+// in the high half, net depth (signed) in the low half.
 __global__ void __launch_bounds__(1024) depth_evscan_kernel(const int* __restrict__ tile_starts, const int* __restrict__ tile_ends, int num_tiles,
                                                            unsigned* __restrict__ bucket_off, int* __restrict__ carry) {
     __shared__ long long s_w[32];
+    __shared__ long long s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (num_tiles + 1 + 1023) / 1024;                   // entries 0 .. num_tiles (the last one closes the last bucket)
-    const int b = tid * per, e = min(num_tiles + 1, b + per);
-    long long loc = 0;
-    for (int i = b; i < e; i++) {
-        const int st = i < num_tiles ? tile_starts[i] : 0, en = i < num_tiles ? tile_ends[i] : 0;
-        loc += ((long long)(st + en) << 32) + (long long)(st - en);
-    }
-    long long inc = loc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += y; }
-    if (lane == 31) s_w[warp] = inc;
+    if (tid == 0) s_base = 0;
     __syncthreads();
-    long long run = inc - loc;                                       // exclusive prefix of this thread's run
-    for (int k = 0; k < warp; k++) run += s_w[k];
-    for (int i = b; i < e; i++) {
-        const long long lo = (long long)(int)(run & 0xffffffffll);   // low word, sign-extended
-        bucket_off[i] = (unsigned)((run - lo) >> 32);
-        carry[i] = (int)lo;
-        const int st = i < num_tiles ? tile_starts[i] : 0, en = i < num_tiles ? tile_ends[i] : 0;
-        run += ((long long)(st + en) << 32) + (long long)(st - en);
+    for (int base = 0; base <= num_tiles; base += 4096) {
+        long long v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = base + j * 1024 + tid;                     // coalesced: consecutive threads, consecutive tiles
+            const int st = i < num_tiles ? tile_starts[i] : 0, en = i < num_tiles ? tile_ends[i] : 0;
+            v[j] = ((long long)(st + en) << 32) + (long long)(st - en);
+        }
+        // scan order is tile order: segment j (1024 tiles) before segment j+1; inside a segment by thread
+        long long run_before = s_base;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            long long inc = v[j];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += y; }
+            if (lane == 31) s_w[warp] = inc;
+            __syncthreads();
+            long long wv = lane < 32 ? s_w[lane] : 0;                // every warp scans the 32 warp totals
+            long long winc = wv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(kFull, winc, o); if (lane >= o) winc += y; }
+            const long long warp_excl = __shfl_sync(kFull, winc, warp) - __shfl_sync(kFull, wv, warp);
+            const long long seg_total = __shfl_sync(kFull, winc, 31);
+            const long long excl = run_before + warp_excl + inc - v[j];
+            const int i = base + j * 1024 + tid;
+            if (i <= num_tiles) {
+                const long long lo = (long long)(int)(excl & 0xffffffffll);   // low word, sign-extended
+                bucket_off[i] = (unsigned)((excl - lo) >> 32);
+                carry[i] = (int)lo;
+            }
+            run_before += seg_total;
+            __syncthreads();
+        }
+        if (tid == 0) s_base = run_before;
+        __syncthreads();
     }
 }
 
-// K_evtile: one 128-thread CTA per tile (32 bases per thread, the core K_fused8 uses): zero 16 KB, the tile's events
-// into shared memory, tile core
-constexpr int kEvThreads = 128;
-constexpr int kEvWarps = kEvThreads / 32;
-constexpr int kEvBPT = kTile / kEvThreads;
-__global__ void __launch_bounds__(kEvThreads) depth_evtile_kernel(const ScanParams p, const unsigned short* __restrict__ events,
-                                                                  const unsigned* __restrict__ bucket_off, const int* __restrict__ carry) {
+// K_evtile: one CTA per tile: zero 16 KB, the tile's events into shared memory, tile core.  (256 threads x 16 bases: the
+// kernel is not persistent, and with one tile per CTA the 128-thread / 32-base shape of K_fused8 measured 12 % slower here.)
+constexpr int kEvThreads = kScanThreads;
+constexpr int kEvWarps = kWarps;
+__global__ void __launch_bounds__(kEvThreads, 4) depth_evtile_kernel(const ScanParams p, const unsigned short* __restrict__ events,
+                                                                     const unsigned* __restrict__ bucket_off, const int* __restrict__ carry) {
     __shared__ __align__(16) int s_tile[kTile];
     __shared__ __align__(16) int s_depth[kTile];
     __shared__ int s_carry[kEvWarps];
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
 #pragma unroll
-    for (int j = 0; j < kEvBPT / 4; j++) reinterpret_cast<int4*>(s_tile)[tid * (kEvBPT / 4) + j] = make_int4(0, 0, 0, 0);
+    for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);
     if (tid < kEvWarps) s_carry[tid] = tid == 0 ? carry[tile] : 0;
     const unsigned lo = bucket_off[tile], hi = bucket_off[tile + 1];
     __syncthreads();
     for (unsigned i = lo + tid; i < hi; i += kEvThreads) {
         const unsigned ev = events[i];
-        atomicAdd(s_tile + swz_elem_t<kEvBPT>((int)(ev & (kTile - 1))), (ev >> 15) ? -1 : 1);
+        atomicAdd(s_tile + swz_elem((int)(ev & (kTile - 1))), (ev >> 15) ? -1 : 1);
     }
     __syncthreads();
     int acc_max = 0;
-    tile_core<kEvBPT, kEvWarps, false>(p, s_tile, s_depth, s_carry, tile, acc_max);
+    tile_core<16, kEvWarps, false>(p, s_tile, s_depth, s_carry, tile, acc_max);
     flush_max(p, acc_max);
 }
 
