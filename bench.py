@@ -186,14 +186,126 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
-def depthwed_leg(ctx, dist, rank, world, local, S=500, R=6_176_584, n_chunks=8, reps=3):
+def comm_setup(ctx, dist, rank, world):
+    """the library's own NCCL communicator (gl_comm_init) over the ranks torchrun started: rank 0's unique id is broadcast"""
     import torch
-    from goleft_b200 import capi, multigpu
+    from goleft_b200 import capi
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
         uid = torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device="cuda")
     dist.broadcast(uid, src=0)
     ctx.comm_init(bytes(uid.cpu().tolist()), rank, world)
+
+
+def indexcov_cohort_leg(ctx, dist, rank, world, S=2504, T=191_000, reps=3):
+    """BASELINE configs[3]: a 2504-sample 1000G-shaped .bai cohort (T tiles of 16 KB per sample), samples sharded over the
+    ranks: per rank I1 (offset deltas) + I2/I3 (scale + normalise) + I4/I5 (slot histograms, counters) + the
+    "%.3g" tokens of I6 on its samples, device-resident; at N>1 the float32 depths [samples x T] are all-gathered so every
+    rank holds the whole cohort (what I6's rows / I7 need).  Medians of three samples per rank are compared with the oracle."""
+    from goleft_b200 import capi, multigpu
+    lo, hi = multigpu.shard_range(S, rank, world)
+    Sg, width = hi - lo, multigpu.padded_width(S, world)
+    rng = np.random.default_rng(1234)
+    one = np.round(rng.lognormal(np.log(1.6e9), 0.25, T)).astype(np.int64)
+    cn = np.repeat(rng.choice([1.0, 0.5, 1.5, 0.0], size=T // 64 + 1, p=[0.97, 0.01, 0.01, 0.01]), 64)[:T]   # ~1 Mb blocks
+    one = np.round(one * cn).astype(np.int64)
+    def sample_sizes(k):
+        return np.roll(one, (k * 97) % T) + np.int64(k % 1000)
+    # linear-index virtual offsets of the shard: per sample T+1 offsets (prefix sums), uploaded in pieces
+    d_voff = ctx.dev_empty(Sg * (T + 1) * 8)
+    for j in range(Sg):
+        v = np.empty(T + 1, np.uint64)
+        v[0] = 100000
+        np.cumsum(sample_sizes(lo + j), out=v[1:].view(np.int64))
+        v[1:] += np.uint64(100000)
+        capi.lib.gl_memcpy_h2d(ctx.h, d_voff.ptr + j * (T + 1) * 8, v.ctypes.data, v.nbytes)
+    voff_off = ctx.dev_array(np.arange(Sg, dtype=np.int64) * (T + 1))
+    n_intv = ctx.dev_array(np.full(Sg, T + 1, np.int32))
+    size_off = ctx.dev_array(np.arange(Sg, dtype=np.int64) * T)
+    d_sizes = ctx.dev_empty(Sg * T * 8)
+    d_ptr = ctx.dev_array(np.arange(Sg + 1, dtype=np.int64) * T)
+    d_med, d_dep = ctx.dev_empty(Sg * 8), ctx.dev_empty(width * T * 4)
+    d_tok = ctx.dev_empty(Sg * T * 10)
+    n_ref = 24                                                    # 24 reported references of ~T/24 tiles each
+    bounds = np.linspace(0, T, n_ref + 1).astype(np.int64)
+    seg_start = (np.arange(Sg, dtype=np.int64)[None, :] * T + bounds[:-1, None]).reshape(-1)
+    seg_len = np.repeat(np.diff(bounds), Sg)
+    d_ss, d_sl, d_lg = ctx.dev_array(seg_start), ctx.dev_array(seg_len), ctx.dev_array(seg_len)
+    nseg = seg_start.size
+    d_c, d_b = ctx.dev_empty(nseg * 70 * 4), ctx.dev_empty(nseg * 32)
+    d_all = ctx.dev_empty(width * T * 4 * world) if world > 1 else None
+    L = capi.lib
+    def ck(rc):
+        if rc != 0:
+            raise RuntimeError("indexcov leg: rc %d" % rc)
+    t = {"sizes": [], "cohort": [], "counts": [], "tokens": [], "allgather": [], "total": []}
+    for it in range(reps + 1):
+        ctx.flush_l2(); ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        ctx.timer_start()
+        ck(L.gl_indexcov_sizes_batch_device(ctx.h, d_voff.ptr, voff_off.ptr, n_intv.ptr, size_off.ptr, Sg, d_sizes.ptr))
+        a = ctx.timer_stop_ms(); ctx.timer_start()
+        ctx.indexcov_cohort_device(d_sizes, d_ptr, Sg, d_med, d_dep)
+        b = ctx.timer_stop_ms(); ctx.timer_start()
+        ck(L.gl_indexcov_counts_segs_device(ctx.h, d_dep.ptr, d_ss.ptr, d_sl.ptr, d_lg.ptr, nseg, d_c.ptr, d_b.ptr))
+        c = ctx.timer_stop_ms(); ctx.timer_start()
+        ck(L.gl_format_g3_device(ctx.h, d_dep.ptr, Sg * T, d_tok.ptr))
+        d = ctx.timer_stop_ms()
+        g = 0.0
+        if d_all is not None:
+            dist.barrier(); ctx.timer_start()
+            ctx.allgather_device(d_dep, d_all, width * T * 4)
+            g = ctx.timer_stop_ms()
+        if it:
+            for k, v in zip(("sizes", "cohort", "counts", "tokens", "allgather"), (a, b, c, d, g)):
+                t[k].append(v)
+            t["total"].append(a + b + c + d + g)
+    fallbacks = ctx.indexcov_cohort_fallbacks()
+    med = d_med.download(np.float64, Sg)
+    from oracle import loader as orc                              # the checker: three samples of this rank's shard
+    ok = True
+    for j in (0, Sg // 2, Sg - 1):
+        sz = sample_sizes(lo + j)
+        m = float(orc.ic_median(sz))
+        ok = ok and med[j] == m
+        dj = np.empty(T, np.float32)
+        capi.lib.gl_memcpy_d2h(ctx.h, dj.ctypes.data, d_dep.ptr + j * T * 4, T * 4)
+        ok = ok and bool(np.array_equal(dj.view(np.uint32), orc.ic_normalize(sz, m).view(np.uint32)))
+    if d_all is not None:                                         # the gathered matrix: first sample of every rank's block
+        for r in range(world):
+            rlo, _ = multigpu.shard_range(S, r, world)
+            sz = sample_sizes(rlo)
+            dj = np.empty(T, np.float32)
+            capi.lib.gl_memcpy_d2h(ctx.h, dj.ctypes.data, d_all.ptr + r * width * T * 4, T * 4)
+            ok = ok and bool(np.array_equal(dj.view(np.uint32), orc.ic_normalize(sz, float(orc.ic_median(sz))).view(np.uint32)))
+    for bf in (d_voff, voff_off, n_intv, size_off, d_sizes, d_ptr, d_med, d_dep, d_tok, d_ss, d_sl, d_lg, d_c, d_b) + ((d_all,) if d_all is not None else ()):
+        bf.free()
+    means = {k: float(np.mean(v)) for k, v in t.items()}
+    if dist is not None:
+        import torch
+        tt = torch.tensor([means[k] for k in ("sizes", "cohort", "counts", "tokens", "allgather", "total")] + [0.0 if ok else 1.0, float(fallbacks)],
+                          dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        means = dict(zip(("sizes", "cohort", "counts", "tokens", "allgather", "total"), (float(x) for x in tt[:6])))
+        ok, fallbacks = float(tt[6]) == 0.0, int(tt[7])
+    peak, _ = peaks()
+    alg = 12 * Sg * T                                             # SURVEY 8(d): 8 B offsets in + 4 B float out per tile-sample
+    k_ms = means["sizes"] + means["cohort"]
+    return {"samples": S, "tiles_per_sample": T, "samples_per_rank": Sg, "ms": means, "scaling": "strong (2504 samples at every N)",
+            "tile_samples_per_s": S * T / (means["total"] * 1e-3),
+            "roofline_I1_I2_I3": {"alg_bytes_per_rank": alg, "ms": k_ms, "achieved_gbs": alg / (k_ms * 1e-3) / 1e9, "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
+                                  "basis": "12 B per tile-sample (8 B offsets in + 4 B float32 out), ic_sizes_batch_kernel + ic_cohort2_kernel"},
+            "allgather_bytes": width * T * 4 * world if world > 1 else 0,
+            "allgather_busbw_gbs": (width * T * 4 * (world - 1) / (means["allgather"] * 1e-3) / 1e9) if world > 1 and means["allgather"] > 0 else None,
+            "cohort_fallback_samples_max_rank": fallbacks, "bit_exact_vs_oracle": bool(ok),
+            "note": "device-resident, CUDA events, L2 flushed, max over ranks; medians + float32 depths of 3 samples per rank (and of the gathered "
+                    "matrix at N>1) compared bit for bit with the oracle (oracle_indexcov.c)"}
+
+
+def depthwed_leg(ctx, dist, rank, world, local, S=500, R=6_176_584, n_chunks=8, reps=3):
+    import torch
+    from goleft_b200 import capi, multigpu
     lo, hi = multigpu.shard_range(S, rank, world)
     width = multigpu.padded_width(S, world)
     base = ((np.arange(R, dtype=np.int64) * 2654435761) % 97).astype(np.int32)        # depth of (sample s, row r) = base[r] + s
@@ -290,6 +402,85 @@ def depthwed_leg(ctx, dist, rank, world, local, S=500, R=6_176_584, n_chunks=8, 
                                   "(one kernel per rank, CUDA-event time, max over ranks); busbw by the all-gather formula for comparison"},
             "note": "sample-sharded; per rank: depthwed_i32_kernel over 8 row chunks on the compute stream, ncclAllGather of each finished chunk "
                     "on the communication stream (gl_allgather_device_async); times are max over ranks"}
+
+
+def config_legs(ctx, L, nm, n_cpus, timed_dev, timed_host, kernel_times, check):
+    """chr20-sized contig in other shapes, each: resident step (device-timed, per-kernel ms), the drop-in call (int32 host
+    segments -> BED bytes, host-timed), class runs, path taken; the first 10 Mb chunk's bytes are compared with the oracle."""
+    import glsynth
+    from goleft_b200 import capi
+    shapes = [
+        ("cov5_mincov4", dict(coverage=5.0, read_len=150), dict(W=500, mincov=4, maxmean=0)),
+        ("cov30_maxmeandepth40", dict(coverage=30.0, read_len=150), dict(W=500, mincov=4, maxmean=40)),
+        ("cov30_W250_default", dict(coverage=30.0, read_len=150), dict(W=250, mincov=4, maxmean=0)),
+        ("cov30_W1", dict(coverage=30.0, read_len=150), dict(W=1, mincov=4, maxmean=0)),
+        ("longreads_20kb_cov30", dict(coverage=30.0, read_len=20000), dict(W=500, mincov=4, maxmean=0)),
+    ]
+    res = {}
+    for key, gen, par in shapes:
+        if par["W"] == 1:                                    # W=1: one window per base, the text alone is 1.6 GB: resident only, 10 Mb
+            Lc = 10_000_000
+        else:
+            Lc = L
+        h_s, h_e = glsynth.segments(Lc, 19, threads=n_cpus, alloc=ctx.pinned_empty, **gen)
+        n = int(h_s.size)
+        short = gen["read_len"] <= 400
+        n_win = (Lc - 1) // par["W"] + 1
+        if short:
+            qa, qd, ql = capi.pack_segments8(h_s, h_e, threads=0)
+            dv = [ctx.dev_array(a) for a in (qa, qd, ql)]
+            def resident():
+                ctx.depth_begin(0, Lc)
+                ctx.depth_add_segments_packed8_device(dv[0], dv[1], dv[2], qa.size)
+                ctx.depth_reduce(par["W"], par["mincov"], par["maxmean"], STEP)
+        else:
+            dv = [ctx.dev_array(h_s), ctx.dev_array(h_e)]
+            def resident():
+                ctx.depth_begin(0, Lc)
+                ctx.depth_add_segments_device(dv[0], dv[1], n)
+                ctx.depth_reduce(par["W"], par["mincov"], par["maxmean"], STEP)
+        t_res = timed_dev(resident, 5)
+        k_ms, _ = kernel_times(3, resident)
+        path = ctx.depth_last_path()
+        _, n_runs, max_depth = ctx.depth_result_sizes()
+        ent = {"bases": Lc, "segments": n, "read_len": gen["read_len"], "coverage": gen["coverage"], "window": par["W"], "mincov": par["mincov"],
+               "maxmeandepth": par["maxmean"], "runs": int(n_runs), "max_depth": int(max_depth), "path": int(path),
+               "resident": {"ms": t_res, "value": Lc / t_res / 1e3, "kernel_ms": k_ms,
+                            "format": "packed8" if short else "int32 (start,end)"}}
+        if par["W"] > 1:
+            o_hd = ctx.pinned_empty(int(capi.lib.gl_depth_text_bound(nm.encode(), n_win)), np.uint8)
+            o_ca = ctx.pinned_empty(max(1 << 20, 48 * (int(n_runs) + 16)), np.uint8)
+            call = lambda: ctx.depth_bed_contig(nm, Lc, h_s, h_e, par["W"], par["mincov"], par["maxmean"], STEP, out=(o_hd, o_ca), raw=True)
+            t_e2e = timed_host(call, 5)
+            hl, cl = call()
+            ent["e2e_text_int32"] = {"ms": t_e2e, "value": Lc / t_e2e / 1e3, "h2d_bytes": h2d_bytes_of(n), "d2h_bytes": int(hl + cl)}
+            if check:
+                from oracle import loader as orc
+                s_, e_ = sorted_copy(np.array(h_s), np.array(h_e))
+                ce = min(STEP, Lc)
+                hi = int(np.searchsorted(s_, ce, "left"))
+                d = orc.pileup_diff(s_[:hi], e_[:hi], 0, ce)
+                h, c = orc.walk_chunk(nm, 0, ce, par["W"], par["mincov"], par["maxmean"], d)
+                got_hd = bytes(o_hd[:hl])
+                got_ca = bytes(o_ca[:cl])
+                # the first chunk's rows are a prefix of both files (chunk edges are run breaks)
+                ent["first_chunk_bytes_equal_oracle_walker"] = bool(got_hd.startswith(h) and got_ca.startswith(c))
+        for b in dv:
+            b.free()
+        res[key] = ent
+    return res
+
+
+def h2d_bytes_of(nseg, pool_threads=None):
+    """bytes gl_depth_bed_contig moves host->device for nseg int32 segments: fixed-block packed16 (4 B/segment + 4 B per 256)
+    when the library's auto rule takes it (>= 2^20 segments, pool >= 24 threads, GL_BED_PACK unset), else 8 B/segment"""
+    from goleft_b200 import capi
+    if pool_threads is None:
+        pool_threads = int(capi.lib.glhost_pool_size())
+    if os.environ.get("GL_BED_PACK", "-1") in ("-1", "16") and nseg >= (1 << 20) and (pool_threads >= 24 or os.environ.get("GL_BED_PACK") == "16"):
+        nb = (nseg + 255) // 256
+        return nb * (4 + 1024)
+    return 8 * nseg
 
 
 def cli_wallclock(n_cpus):
@@ -475,7 +666,7 @@ def main():
             ok = ok and got[0] == b"".join(hd) and got[1] == b"".join(ca)
             checked.append(w["name"])
         e2e_check = {"contigs": checked, "bytes_equal_oracle_walker": bool(ok),
-                     "inside_timed_region": ["H2D int32 segments (pinned)", "K_index/K_fused/K_gather", "device %.4g row formatter (bed_rows/scan/emit)",
+                     "inside_timed_region": ["host pool: int32 -> fixed-block packed16 (pipelined with the upload)", "H2D packed16 words (pinned)", "depth_unpack16_kernel", "K_index/K_fused/K_gather", "device %.4g row formatter (bed_rows/scan/emit)",
                                              "D2H .depth.bed + .callable.bed bytes (pinned)"],
                      "outside": ["BGZF inflate + BAM record parse (the feeder; see cli_wallclock)"]}
         if not ok:
@@ -578,6 +769,9 @@ def main():
         x_hbm_k, _ = kernel_times(3, one_int32)
         ctx.depth_set_path(0)
         x_e2e_text = timed_host(lambda: ctx.depth_bed_contig(nm, L, w["h_s"], w["h_e"], W, MINCOV, MAXMEAN, STEP, out=(o_hd, o_ca), raw=True), n_x)
+        os.environ["GL_BED_PACK"] = "0"
+        x_e2e_plain = timed_host(lambda: ctx.depth_bed_contig(nm, L, w["h_s"], w["h_e"], W, MINCOV, MAXMEAN, STEP, out=(o_hd, o_ca), raw=True), n_x)
+        del os.environ["GL_BED_PACK"]
         x_e2e_p8 = timed_host(lambda: ctx.depth_bed_contig_packed8(nm, L, h8[0], h8[1], h8[2], W, MINCOV, MAXMEAN, STEP, out=(o_hd, o_ca), raw=True), n_x)
         run_cap = L // 16 + 4096
         o_sum, o_rs, o_rc = ctx.pinned_empty(w["n_win"], np.int64), ctx.pinned_empty(run_cap, np.int32), ctx.pinned_empty(run_cap, np.uint8)
@@ -592,8 +786,11 @@ def main():
                   "hbm_difference_array_path": {"ms": x_hbm, "value": L / x_hbm / 1e3, "kernel_ms": x_hbm_k,
                                                 "note": "the pipeline north_star sketches, on request (gl_depth_set_path(2)): memset + K_scatter "
                                                         "(red.global) + K_super + K_scan + K_gather"},
-                  "e2e_text_int32": {"ms": x_e2e_text, "value": L / x_e2e_text / 1e3, "h2d_bytes": 8 * w["nseg"],
-                                     "call": "gl_depth_bed_contig (what `e2e` times, on this contig alone)"},
+                  "e2e_text_int32": {"ms": x_e2e_text, "value": L / x_e2e_text / 1e3, "h2d_bytes": h2d_bytes_of(w["nseg"]),
+                                     "call": "gl_depth_bed_contig (what `e2e` times, on this contig alone): int32 arrays in, repacked by the host pool to "
+                                             "fixed-block packed16 (4 B/segment) chunk by chunk while the previous chunk is on the wire"},
+                  "e2e_text_int32_plain_upload": {"ms": x_e2e_plain, "value": L / x_e2e_plain / 1e3, "h2d_bytes": 8 * w["nseg"],
+                                                  "call": "the same call with GL_BED_PACK=0: the int32 arrays go over PCIe as they are (8 B/segment)"},
                   "e2e_text_packed8_words": {"ms": x_e2e_p8, "value": L / x_e2e_p8 / 1e3, "h2d_bytes": w["p8_bytes"],
                                              "call": "gl_depth_bed_contig_packed8: the feeder's own packed8 words (what the BAM decoder emits) in, BED bytes out"},
                   "e2e_kernels_only": {"ms": x_k_only, "value": L / x_k_only / 1e3, "h2d_bytes": w["p8_bytes"],
@@ -601,6 +798,12 @@ def main():
                   "host_pack_ms": {"gl_pack_segments8_mt": t_pack, "threads": n_cpus,
                                    "note": "int32 -> packed8 on the host pool; NOT inside e2e (e2e uploads the int32 arrays as they are)"}}
         d_s.free(); d_e.free()
+        # ---- other shapes of the same contig: low coverage (thousands of class runs), maxmeandepth > 0,
+        #      the reference's default W=250 (depth.go:164), long reads (20 kb segments -> the general path)
+        try:
+            extras["configs"] = config_legs(ctx, L, nm, n_cpus, timed_dev, timed_host, kernel_times, rank == 0)
+        except Exception as ex:
+            extras["configs"] = {"error": str(ex)[:300]}
         # ---- the product CLI on a real BAM of the same reads: BGZF inflate + record parse + GPU + text, wall clock
         try:
             extras["cli_wallclock"] = cli_wallclock(n_cpus)
@@ -612,11 +815,24 @@ def main():
     #      windows of int32, sample-sharded; every rank aggregates its columns chunk by chunk and all-gathers each finished chunk
     #      over NVLink on a second stream while the next chunk is aggregated.  Verified on every rank.
     depthwed = None
-    if dist is not None and not args.no_extras:
+    cohort = None
+    if not args.no_extras:
+        comm_ok = dist is not None
+        if dist is not None:
+            try:
+                comm_setup(ctx, dist, rank, world)
+            except Exception as ex:
+                comm_ok, depthwed = False, {"error": "gl_comm_init: " + str(ex)[:300]}
+        if comm_ok:
+            try:
+                depthwed = depthwed_leg(ctx, dist, rank, world, local)
+            except Exception as ex:
+                depthwed = {"error": str(ex)[:300]}
+        # ---- BASELINE configs[3]: the 2504-sample indexcov cohort, samples sharded over the ranks (+ all-gather of the depths at N>1)
         try:
-            depthwed = depthwed_leg(ctx, dist, rank, world, local)
+            cohort = indexcov_cohort_leg(ctx, dist if comm_ok else None, rank, world if comm_ok else 1)
         except Exception as ex:
-            depthwed = {"error": str(ex)[:300]}
+            cohort = {"error": str(ex)[:300]}
 
     per_rank = None
     if dist is not None:
@@ -627,12 +843,12 @@ def main():
         per_rank = [[float(x[0]) / args.steps, float(x[1]) / args.steps] for x in g]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = (float(x) for x in t)
-        cnt = torch.tensor([float(launches), float(nseg), float(n_runs), float(text_bytes[0] + text_bytes[1]), float(8 * nseg)],
+        cnt = torch.tensor([float(launches), float(nseg), float(n_runs), float(text_bytes[0] + text_bytes[1]), float(sum(h2d_bytes_of(w["nseg"]) for w in work))],
                            dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches_all, nseg_all, n_runs_all, d2h_all, h2d_all = (int(x) for x in cnt)
     else:
-        launches_all, nseg_all, n_runs_all, d2h_all, h2d_all = launches, nseg, n_runs, text_bytes[0] + text_bytes[1], 8 * nseg
+        launches_all, nseg_all, n_runs_all, d2h_all, h2d_all = launches, nseg, n_runs, text_bytes[0] + text_bytes[1], sum(h2d_bytes_of(w["nseg"]) for w in work)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -667,7 +883,9 @@ def main():
                           "numa": {"node": node, "cpus": n_cpus}},
                "e2e": {"value": e2e_val, "unit": "Mbases/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                        "ms_per_step": ms_e2e_step, "kernel_ms_rank0": k_ms_e2e,
-                       "call": "gl_depth_bed_contig per contig: int32 (start,end) segments in pinned host memory -> .depth.bed + .callable.bed bytes in pinned host memory"},
+                       "call": "gl_depth_bed_contig per contig: int32 (start,end) segments in pinned host memory -> .depth.bed + .callable.bed bytes in pinned host memory",
+                       "transport": "auto (fixed-block packed16, 4 B/segment, when the rank's host pool has >= 24 threads; else plain int32, 8 B/segment)",
+                       "host_pool_threads": int(capi.lib.glhost_pool_size())},
                "e2e_check": e2e_check,
                "gpu_launches": int(launches_all),
                "roofline": {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src,
@@ -690,6 +908,8 @@ def main():
                "clocks": clocks}
         if depthwed is not None:
             out["depthwed_allgather"] = depthwed
+        if cohort is not None:
+            out["indexcov_cohort"] = cohort
         if per_rank is not None:
             out["per_rank_ms"] = {"resident": [p[0] for p in per_rank], "e2e": [p[1] for p in per_rank]}
         if extras:

@@ -16,6 +16,7 @@
 #include <unistd.h>
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <condition_variable>
 #include <map>
 #include <mutex>
@@ -582,7 +583,8 @@ static int cmd_depth(int argc, char** argv) {
     int n_dev = 0;
     if (gl_device_count(&n_dev) != GL_OK || n_dev < 1) fatal(1, "goleft depth: %s", gl_last_error(nullptr));
     int G = atoi(gpus.c_str());
-    if (G <= 0 || G > n_dev) G = n_dev;
+    const bool oversub = getenv("GL_OVERSUBSCRIBE") != nullptr;               // testing aid: --gpus N workers on fewer devices (worker g -> device g % n_dev)
+    if (G <= 0 || (G > n_dev && !oversub)) G = n_dev;
     G = (int)std::min<size_t>((size_t)G, std::max<size_t>(jobs.size(), 1));
     std::vector<int32_t> gpu_of(jobs.size(), 0);
     {
@@ -592,8 +594,8 @@ static int cmd_depth(int argc, char** argv) {
     }
     auto worker = [&](int g) {
         int node = -1, ncpu = 0;
-        if (G > 1) gl_bind_numa_for_device(g, 0, 1, &node, &ncpu);            // this feeder thread next to its GPU (the pool keeps all cores)
-        DepthEngine eng(sh, g);
+        if (G > 1) gl_bind_numa_for_device(g % n_dev, 0, 1, &node, &ncpu);    // this feeder thread next to its GPU (the pool keeps all cores)
+        DepthEngine eng(sh, g % n_dev);
         for (size_t i = 0; i < jobs.size(); i++) {
             if (gpu_of[i] != g) continue;
             if (bed.empty()) eng.run_contig(jobs[i]); else eng.run_bed_chrom(jobs[i]);
@@ -681,12 +683,13 @@ static double get_cn(const float* d, size_t n) {
 struct IcRef { std::string name; long long len; int id; };
 
 static int cmd_indexcov(int argc, char** argv) {
-    std::string dir, exclude = "^chrEBV$|^NC|_random$|Un_|^HLA\\-|_alt$|hap\\d$", sex = "X,Y", chrom, fai;
+    std::string dir, exclude = "^chrEBV$|^NC|_random$|Un_|^HLA\\-|_alt$|hap\\d$", sex = "X,Y", chrom, fai, gpus = "0";
     bool includegl = false, extranorm = false;
     ArgParser ap;
     ap.prog = "goleft indexcov";
     ap.add("directory", 'd', &dir, true); ap.addb("includegl", 'e', &includegl); ap.add("excludepatt", 0, &exclude);
     ap.add("sex", 'X', &sex); ap.add("chrom", 'c', &chrom); ap.add("fai", 'f', &fai); ap.addb("extranormalize", 'n', &extranorm);
+    ap.add("gpus", 0, &gpus);                       // extension: GPUs to use (0 = every visible one); samples are sharded over them
     ap.parse(argc, argv);
     std::vector<std::string> bams = ap.positional;
     if (bams.empty()) ap.fail("bam is required");
@@ -746,22 +749,28 @@ static int cmd_indexcov(int argc, char** argv) {
     }
 
     ic_mark("read indexes");
-    gl_ctx* ctx = nullptr;
-    if (gl_ctx_create(0, &ctx) != GL_OK) fatal(1, "goleft indexcov: %s", gl_last_error(nullptr));
-    ic_mark("gl_ctx_create");
-    fprintf(stderr, "indexcov: running on %zu indexes\n", S);
+    // ---- GPUs (samples are independent through I5 -> sample-sharded over the GPUs; the rows need every sample
+    //      of a tile, and they are assembled on the host, so the "gather" is each GPU's D2H into its slice of the cohort arrays)
+    int n_dev = 0;
+    if (gl_device_count(&n_dev) != GL_OK || n_dev < 1) fatal(1, "goleft indexcov: %s", gl_last_error(nullptr));
+    int G = atoi(gpus.c_str());
+    const bool oversub = getenv("GL_OVERSUBSCRIBE") != nullptr;               // testing aid: --gpus N shards on fewer devices (shard g -> device g % n_dev)
+    if (G <= 0 || (G > n_dev && !oversub)) G = n_dev;
+    fprintf(stderr, "indexcov: running on %zu indexes\n", bams.size());
 
-    // ---- I1 for the whole cohort in ONE launch (indexcov/types.go:45-82): every sample's linear-index offsets go up once,
-    //      one descriptor per (sample, reference with >= 2 entries); CRAM samples bring host-made pseudo-tile sizes
+    // ---- I1 for the whole cohort (indexcov/types.go:45-82): every sample's linear-index offsets go up once, one descriptor per
+    //      (sample, reference with >= 2 entries); CRAM samples bring host-made pseudo-tile sizes
     std::vector<int64_t> sample_ptr(1, 0);
     std::vector<std::vector<int64_t>> size_ptr(S);                          // per sample: CSR over its refs
     std::vector<uint64_t> mapped(S, 0), unmapped(S, 0);
     std::vector<uint64_t> voff_all;
     std::vector<int64_t> desc_voff, desc_size;
     std::vector<int32_t> desc_n;
-    std::vector<std::pair<int64_t, std::vector<int64_t>>> crai_sizes;       // (offset into the cohort's sizes, values)
+    std::vector<size_t> desc_begin(S + 1, 0), voff_begin(S + 1, 0);         // per sample: its first descriptor / first offset
+    std::vector<std::vector<int64_t>> crai_sizes(S);                        // CRAM samples: the values themselves
     for (size_t i = 0; i < S; i++) {
         const int64_t base = sample_ptr.back();
+        desc_begin[i] = desc_n.size(); voff_begin[i] = voff_all.size();
         if (ends_with(bams[i], ".crai")) {                                  // CRAM: interpolated pseudo-tiles (crai.go:56-127)
             const size_t nr = crai[i].size();
             std::vector<int64_t> sp(nr + 1, 0), all;
@@ -774,7 +783,7 @@ static int cmd_indexcov(int argc, char** argv) {
             }
             if (sp[nr] < 1) fatal(1, "indexcov: no usable chromsomes in bam: %s", bams[i].c_str());
             sample_ptr.push_back(base + sp[nr]);
-            crai_sizes.emplace_back(base, std::move(all));
+            crai_sizes[i] = std::move(all);
             size_ptr[i] = sp;
             continue;
         }
@@ -793,41 +802,19 @@ static int cmd_indexcov(int argc, char** argv) {
         sample_ptr.push_back(base + sp[nr]);
         size_ptr[i] = sp;
     }
+    desc_begin[S] = desc_n.size(); voff_begin[S] = voff_all.size();
     const int64_t total = sample_ptr.back();
-    auto dalloc = [&](size_t bytes) { void* p = nullptr; glck(ctx, gl_dev_alloc(ctx, (int64_t)std::max<size_t>(bytes, 16), &p), "gl_dev_alloc"); return p; };
-    auto up = [&](const void* h, size_t bytes) { void* p = dalloc(bytes); if (bytes) glck(ctx, gl_memcpy_h2d(ctx, p, h, (int64_t)bytes), "gl_memcpy_h2d"); return p; };
-    int64_t* d_sizes = static_cast<int64_t*>(dalloc((size_t)total * 8));
-    if (!desc_n.empty()) {
-        void* d_voff = up(voff_all.data(), voff_all.size() * 8);
-        void* d_dv = up(desc_voff.data(), desc_voff.size() * 8);
-        void* d_dn = up(desc_n.data(), desc_n.size() * 4);
-        void* d_ds = up(desc_size.data(), desc_size.size() * 8);
-        const int rc = gl_indexcov_sizes_batch_device(ctx, static_cast<const uint64_t*>(d_voff), static_cast<const int64_t*>(d_dv),
-                                                      static_cast<const int32_t*>(d_dn), static_cast<const int64_t*>(d_ds), (int64_t)desc_n.size(), d_sizes);
-        if (rc == GL_ERANGE) fatal(2, "panic: expected positive change in vOffset");                 // types.go:75-77
-        glck(ctx, rc, "gl_indexcov_sizes_batch_device");
-        gl_dev_free(ctx, d_voff); gl_dev_free(ctx, d_dv); gl_dev_free(ctx, d_dn); gl_dev_free(ctx, d_ds);
-        std::vector<uint64_t>().swap(voff_all);
+    G = (int)std::min<size_t>((size_t)G, S);
+    // contiguous sample ranges with about total/G tiles each
+    std::vector<size_t> cut((size_t)G + 1, S);
+    cut[0] = 0;
+    for (int g = 1; g < G; g++) {
+        const int64_t want = total / G * g;
+        cut[(size_t)g] = (size_t)(std::lower_bound(sample_ptr.begin(), sample_ptr.end(), want) - sample_ptr.begin());
+        cut[(size_t)g] = std::min(std::max(cut[(size_t)g], cut[(size_t)g - 1]), S);
     }
-    for (auto& cs : crai_sizes) glck(ctx, gl_memcpy_h2d(ctx, d_sizes + cs.first, cs.second.data(), (int64_t)cs.second.size() * 8), "gl_memcpy_h2d");
-    // ---- I2+I3 for the cohort in one kernel, on the resident sizes (indexcov.go:83-151)
-    std::vector<double> med(S);
-    std::vector<float> dep((size_t)total);
-    void* d_sp = up(sample_ptr.data(), sample_ptr.size() * 8);
-    double* d_med = static_cast<double*>(dalloc(S * 8));
-    float* d_dep = static_cast<float*>(dalloc((size_t)total * 4));
-    glck(ctx, gl_indexcov_cohort_device(ctx, d_sizes, static_cast<const int64_t*>(d_sp), (int32_t)S, d_med, d_dep), "gl_indexcov_cohort_device");
-    glck(ctx, gl_memcpy_d2h(ctx, med.data(), d_med, (int64_t)S * 8), "gl_memcpy_d2h");
-    glck(ctx, gl_memcpy_d2h(ctx, dep.data(), d_dep, total * 4), "gl_memcpy_d2h");
-    gl_dev_free(ctx, d_sizes); gl_dev_free(ctx, d_sp); gl_dev_free(ctx, d_med);
-    ic_mark("I1 + I2 + I3 (GPU, + D2H)");
 
     const std::string base = dir + "/" + dir.substr(dir.find_last_of('/') == std::string::npos ? 0 : dir.find_last_of('/') + 1) + "-indexcov";
-    glhts::BgzfWriter bgz(base + ".bed.gz");
-    FILE* roc = fopen((base + ".roc").c_str(), "w");
-    if (!bgz.ok() || !roc) fatal(1, "cannot create outputs in %s", dir.c_str());
-    { std::string h = "#chrom\tstart\tend"; for (auto& n : names) h += "\t" + n; h += "\n"; bgz.write(h.data(), h.size()); }
-
     // the references that are reported (exclude pattern, indexcov.go:637-646)
     std::vector<const IcRef*> kept;
     {
@@ -840,46 +827,135 @@ static int cmd_indexcov(int argc, char** argv) {
             kept.push_back(&ref);
         }
     }
-    // ---- without -n the values never change after I3: the "%.3g" token of EVERY value (I6) and the slot histograms +
-    //      counters of EVERY (reference, sample) pair (I4+I5) come from two launches over the resident depths
+    std::vector<double> med(S);
+    std::vector<float> dep((size_t)total);
     std::vector<uint8_t> tok_all;
     std::vector<int32_t> counts_all;
     std::vector<int64_t> b4_all;
+    if (!extranorm) { tok_all.resize((size_t)total * 10 + 16); counts_all.resize(kept.size() * S * GL_INDEXCOV_SLOTS); b4_all.resize(kept.size() * S * 4); }
+
+    std::vector<gl_ctx*> ctxs((size_t)G, nullptr);
+    // phase A (per GPU, its samples): I1 + I2 + I3 on the device, medians + depths home; the depths stay resident for phase B
+    struct Shard { int64_t* d_sizes = nullptr; float* d_dep = nullptr; int64_t tiles = 0; };
+    std::vector<Shard> shard((size_t)G);
+    auto run_on_gpus = [&](const std::function<void(int)>& fn) {
+        if (G == 1) { fn(0); return; }
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++) th.emplace_back([&, g] { int node = -1, ncpu = 0; gl_bind_numa_for_device(g % n_dev, 0, 1, &node, &ncpu); fn(g); });
+        for (auto& t : th) t.join();
+    };
+    glhost_pool_warm();
+    run_on_gpus([&](int g) {
+        gl_ctx* c = nullptr;
+        if (gl_ctx_create(g % n_dev, &c) != GL_OK) fatal(1, "goleft indexcov: %s", gl_last_error(nullptr));
+        ctxs[(size_t)g] = c;
+        const size_t a = cut[(size_t)g], b = cut[(size_t)g + 1];
+        const int64_t t0 = sample_ptr[a], tiles = sample_ptr[b] - t0;
+        Shard& sd = shard[(size_t)g];
+        sd.tiles = tiles;
+        if (b == a) return;
+        auto dalloc = [&](size_t bytes) { void* p = nullptr; glck(c, gl_dev_alloc(c, (int64_t)std::max<size_t>(bytes, 16), &p), "gl_dev_alloc"); return p; };
+        auto up = [&](const void* h, size_t bytes) { void* p = dalloc(bytes); if (bytes) glck(c, gl_memcpy_h2d(c, p, h, (int64_t)bytes), "gl_memcpy_h2d"); return p; };
+        sd.d_sizes = static_cast<int64_t*>(dalloc((size_t)tiles * 8));
+        const size_t d0 = desc_begin[a], d1 = desc_begin[b], v0 = voff_begin[a], v1 = voff_begin[b];
+        if (d1 > d0) {
+            std::vector<int64_t> dv(desc_voff.begin() + (long)d0, desc_voff.begin() + (long)d1), ds(desc_size.begin() + (long)d0, desc_size.begin() + (long)d1);
+            for (auto& x : dv) x -= (int64_t)v0;
+            for (auto& x : ds) x -= t0;
+            void* d_voff = up(voff_all.data() + v0, (v1 - v0) * 8);
+            void* d_dv = up(dv.data(), dv.size() * 8);
+            void* d_dn = up(desc_n.data() + d0, (d1 - d0) * 4);
+            void* d_ds = up(ds.data(), ds.size() * 8);
+            const int rc = gl_indexcov_sizes_batch_device(c, static_cast<const uint64_t*>(d_voff), static_cast<const int64_t*>(d_dv),
+                                                          static_cast<const int32_t*>(d_dn), static_cast<const int64_t*>(d_ds), (int64_t)(d1 - d0), sd.d_sizes);
+            if (rc == GL_ERANGE) fatal(2, "panic: expected positive change in vOffset");                 // types.go:75-77
+            glck(c, rc, "gl_indexcov_sizes_batch_device");
+            gl_dev_free(c, d_voff); gl_dev_free(c, d_dv); gl_dev_free(c, d_dn); gl_dev_free(c, d_ds);
+        }
+        for (size_t i = a; i < b; i++)
+            if (!crai_sizes[i].empty())
+                glck(c, gl_memcpy_h2d(c, sd.d_sizes + (sample_ptr[i] - t0), crai_sizes[i].data(), (int64_t)crai_sizes[i].size() * 8), "gl_memcpy_h2d");
+        // I2+I3 for the shard in one kernel, on the resident sizes (indexcov.go:83-151)
+        std::vector<int64_t> sp(sample_ptr.begin() + (long)a, sample_ptr.begin() + (long)b + 1);
+        for (auto& x : sp) x -= t0;
+        void* d_sp = up(sp.data(), sp.size() * 8);
+        double* d_med = static_cast<double*>(dalloc((b - a) * 8));
+        sd.d_dep = static_cast<float*>(dalloc((size_t)tiles * 4));
+        glck(c, gl_indexcov_cohort_device(c, sd.d_sizes, static_cast<const int64_t*>(d_sp), (int32_t)(b - a), d_med, sd.d_dep), "gl_indexcov_cohort_device");
+        glck(c, gl_memcpy_d2h(c, med.data() + a, d_med, (int64_t)(b - a) * 8), "gl_memcpy_d2h");
+        glck(c, gl_memcpy_d2h(c, dep.data() + t0, sd.d_dep, tiles * 4), "gl_memcpy_d2h");
+        gl_dev_free(c, sd.d_sizes); gl_dev_free(c, d_sp); gl_dev_free(c, d_med);
+        sd.d_sizes = nullptr;
+    });
+    std::vector<uint64_t>().swap(voff_all);
+    ic_mark("I1 + I2 + I3 (GPU, + D2H)");
+
+    glhts::BgzfWriter bgz(base + ".bed.gz");
+    FILE* roc = fopen((base + ".roc").c_str(), "w");
+    if (!bgz.ok() || !roc) fatal(1, "cannot create outputs in %s", dir.c_str());
+    { std::string h = "#chrom\tstart\tend"; for (auto& n : names) h += "\t" + n; h += "\n"; bgz.write(h.data(), h.size()); }
+
+    // ---- phase B.  Without -n the values never change after I3: the "%.3g" token of EVERY value (I6) and the slot histograms
+    //      + counters of EVERY (reference, sample) pair (I4+I5) come from two launches per GPU over its resident depths.
+    //      `longest` of a reference is over all samples (and needs every median), hence the barrier between the phases.
     if (!extranorm) {
-        tok_all.resize((size_t)total * 10 + 16);
-        uint8_t* d_tok = static_cast<uint8_t*>(dalloc((size_t)total * 10));
-        if (total) glck(ctx, gl_format_g3_device(ctx, d_dep, total, d_tok), "gl_format_g3_device");
-        if (total) glck(ctx, gl_memcpy_d2h(ctx, tok_all.data(), d_tok, total * 10), "gl_memcpy_d2h");
-        gl_dev_free(ctx, d_tok);
-        const size_t nseg = kept.size() * S;
-        std::vector<int64_t> seg_start(nseg, 0), seg_len(nseg, 0), seg_longest(nseg, 0);
-        for (size_t q = 0; q < kept.size(); q++) {
-            int64_t longest = 0;
-            for (size_t k = 0; k < S; k++) {
-                if (kept[q]->id + 1 < (int)size_ptr[k].size() && med[k] != 0) {
-                    seg_start[q * S + k] = sample_ptr[k] + size_ptr[k][kept[q]->id];
-                    seg_len[q * S + k] = size_ptr[k][kept[q]->id + 1] - size_ptr[k][kept[q]->id];
+        const size_t nq = kept.size();
+        std::vector<int64_t> longest_q(nq, 0);
+        for (size_t q = 0; q < nq; q++)
+            for (size_t k = 0; k < S; k++)
+                if (kept[q]->id + 1 < (int)size_ptr[k].size() && med[k] != 0)
+                    longest_q[q] = std::max(longest_q[q], size_ptr[k][kept[q]->id + 1] - size_ptr[k][kept[q]->id]);
+        run_on_gpus([&](int g) {
+            gl_ctx* c = ctxs[(size_t)g];
+            const size_t a = cut[(size_t)g], b = cut[(size_t)g + 1], Sg = b - a;
+            Shard& sd = shard[(size_t)g];
+            if (Sg == 0) return;
+            const int64_t t0 = sample_ptr[a], tiles = sd.tiles;
+            auto dalloc = [&](size_t bytes) { void* p = nullptr; glck(c, gl_dev_alloc(c, (int64_t)std::max<size_t>(bytes, 16), &p), "gl_dev_alloc"); return p; };
+            auto up = [&](const void* h, size_t bytes) { void* p = dalloc(bytes); if (bytes) glck(c, gl_memcpy_h2d(c, p, h, (int64_t)bytes), "gl_memcpy_h2d"); return p; };
+            uint8_t* d_tok = static_cast<uint8_t*>(dalloc((size_t)tiles * 10));
+            if (tiles) glck(c, gl_format_g3_device(c, sd.d_dep, tiles, d_tok), "gl_format_g3_device");
+            if (tiles) glck(c, gl_memcpy_d2h(c, tok_all.data() + (size_t)t0 * 10, d_tok, tiles * 10), "gl_memcpy_d2h");
+            gl_dev_free(c, d_tok);
+            const size_t nseg = nq * Sg;
+            if (nseg) {
+                std::vector<int64_t> seg_start(nseg, 0), seg_len(nseg, 0), seg_longest(nseg, 0);
+                for (size_t q = 0; q < nq; q++)
+                    for (size_t k = a; k < b; k++) {
+                        const size_t j = q * Sg + (k - a);
+                        if (kept[q]->id + 1 < (int)size_ptr[k].size() && med[k] != 0) {
+                            seg_start[j] = sample_ptr[k] - t0 + size_ptr[k][kept[q]->id];
+                            seg_len[j] = size_ptr[k][kept[q]->id + 1] - size_ptr[k][kept[q]->id];
+                        }
+                        seg_longest[j] = longest_q[q];
+                    }
+                void* d_ss = up(seg_start.data(), nseg * 8);
+                void* d_sl = up(seg_len.data(), nseg * 8);
+                void* d_lg = up(seg_longest.data(), nseg * 8);
+                int32_t* d_c = static_cast<int32_t*>(dalloc(nseg * GL_INDEXCOV_SLOTS * 4));
+                int64_t* d_b = static_cast<int64_t*>(dalloc(nseg * 32));
+                glck(c, gl_indexcov_counts_segs_device(c, sd.d_dep, static_cast<const int64_t*>(d_ss), static_cast<const int64_t*>(d_sl),
+                                                       static_cast<const int64_t*>(d_lg), (int32_t)nseg, d_c, d_b), "gl_indexcov_counts_segs_device");
+                if (G == 1) {
+                    glck(c, gl_memcpy_d2h(c, counts_all.data(), d_c, (int64_t)nseg * GL_INDEXCOV_SLOTS * 4), "gl_memcpy_d2h");
+                    glck(c, gl_memcpy_d2h(c, b4_all.data(), d_b, (int64_t)nseg * 32), "gl_memcpy_d2h");
+                } else {                                                         // this GPU's columns of every reference's block
+                    std::vector<int32_t> cc(nseg * GL_INDEXCOV_SLOTS);
+                    std::vector<int64_t> bb(nseg * 4);
+                    glck(c, gl_memcpy_d2h(c, cc.data(), d_c, (int64_t)nseg * GL_INDEXCOV_SLOTS * 4), "gl_memcpy_d2h");
+                    glck(c, gl_memcpy_d2h(c, bb.data(), d_b, (int64_t)nseg * 32), "gl_memcpy_d2h");
+                    for (size_t q = 0; q < nq; q++) {
+                        memcpy(&counts_all[(q * S + a) * GL_INDEXCOV_SLOTS], &cc[q * Sg * GL_INDEXCOV_SLOTS], Sg * GL_INDEXCOV_SLOTS * 4);
+                        memcpy(&b4_all[(q * S + a) * 4], &bb[q * Sg * 4], Sg * 32);
+                    }
                 }
-                longest = std::max(longest, seg_len[q * S + k]);
+                gl_dev_free(c, d_ss); gl_dev_free(c, d_sl); gl_dev_free(c, d_lg); gl_dev_free(c, d_c); gl_dev_free(c, d_b);
             }
-            for (size_t k = 0; k < S; k++) seg_longest[q * S + k] = longest;
-        }
-        counts_all.resize(nseg * GL_INDEXCOV_SLOTS);
-        b4_all.resize(nseg * 4);
-        if (nseg) {
-            void* d_ss = up(seg_start.data(), nseg * 8);
-            void* d_sl = up(seg_len.data(), nseg * 8);
-            void* d_lg = up(seg_longest.data(), nseg * 8);
-            int32_t* d_c = static_cast<int32_t*>(dalloc(nseg * GL_INDEXCOV_SLOTS * 4));
-            int64_t* d_b = static_cast<int64_t*>(dalloc(nseg * 32));
-            glck(ctx, gl_indexcov_counts_segs_device(ctx, d_dep, static_cast<const int64_t*>(d_ss), static_cast<const int64_t*>(d_sl),
-                                                     static_cast<const int64_t*>(d_lg), (int32_t)nseg, d_c, d_b), "gl_indexcov_counts_segs_device");
-            glck(ctx, gl_memcpy_d2h(ctx, counts_all.data(), d_c, (int64_t)nseg * GL_INDEXCOV_SLOTS * 4), "gl_memcpy_d2h");
-            glck(ctx, gl_memcpy_d2h(ctx, b4_all.data(), d_b, (int64_t)nseg * 32), "gl_memcpy_d2h");
-            gl_dev_free(ctx, d_ss); gl_dev_free(ctx, d_sl); gl_dev_free(ctx, d_lg); gl_dev_free(ctx, d_c); gl_dev_free(ctx, d_b);
-        }
+        });
     }
-    gl_dev_free(ctx, d_dep);
+    for (int g = 0; g < G; g++) if (shard[(size_t)g].d_dep) { gl_dev_free(ctxs[(size_t)g], shard[(size_t)g].d_dep); shard[(size_t)g].d_dep = nullptr; }
+    for (int g = 1; g < G; g++) if (ctxs[(size_t)g]) gl_ctx_destroy(ctxs[(size_t)g]);
+    gl_ctx* ctx = ctxs[0];                                                  // -n (I7) runs per reference on GPU 0
     ic_mark("tokens + counts (GPU, + D2H)");
 
     std::map<std::string, std::vector<double>> sexes;

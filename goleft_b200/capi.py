@@ -104,6 +104,7 @@ _proto("gl_indexcov_counts", C.c_int, _vp, _vp, C.c_int64, _vp)
 _proto("gl_indexcov_bins", C.c_int, _vp, _vp, C.c_int64, C.c_int64, _vp)
 _proto("gl_indexcov_counts_batch", C.c_int, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp)
 _proto("gl_indexcov_counts_batch_device", C.c_int, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp)
+_proto("gl_indexcov_counts_segs_device", C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp)
 _proto("gl_indexcov_xnorm", C.c_int, _vp, _vp, _vp, C.c_int32, C.c_int32)
 _proto("gl_format_g3", C.c_int, _vp, _vp, C.c_int64, _vp)
 _proto("gl_format_g3_device", C.c_int, _vp, _vp, C.c_int64, _vp)
@@ -146,6 +147,7 @@ _proto("gl_depth_region_packed16", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_pack_segments8_bound", C.c_int64, C.c_int64)
 _proto("gl_pack_segments8", C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_pack_segments16_fixed_mt", C.c_int, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_pack_segments8_mt", C.c_int, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_depth_add_segments_packed8", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
 _proto("gl_depth_add_segments_packed8_device", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
@@ -299,6 +301,21 @@ def indexsplit_chunks(tile_sum, out_ptr, names, ref_lens, ref_ids, N: int, probl
         return C.string_at(t, n.value)
     finally:
         lib.gl_free_text(t)
+
+
+def pack_segments16_fixed(start: np.ndarray, end: np.ndarray, threads: int = 0, esc_cap: Optional[int] = None):
+    """fixed-block packed16 (gl_pack_segments16_fixed_mt): (anchors, off, len, esc_start, esc_end)"""
+    start, end = _as(start, np.int32), _as(end, np.int32)
+    n = start.size
+    nb = (n + 255) // 256
+    anchors, off, ln = np.empty(nb, np.int32), np.empty(nb * 256, np.uint16), np.empty(nb * 256, np.uint16)
+    cap = n if esc_cap is None else esc_cap
+    es, ee = np.empty(max(cap, 1), np.int32), np.empty(max(cap, 1), np.int32)
+    m = C.c_int64(0)
+    rc = lib.gl_pack_segments16_fixed_mt(_ptr(start), _ptr(end), n, threads, _ptr(anchors), _ptr(off), _ptr(ln), _ptr(es), _ptr(ee), cap, C.byref(m))
+    if rc != 0:
+        raise GlError(rc, "gl_pack_segments16_fixed_mt (needs %d escapes)" % m.value)
+    return anchors, off, ln, es[: m.value].copy(), ee[: m.value].copy()
 
 
 def pack_segments8(start: np.ndarray, end: np.ndarray, threads: Optional[int] = None):

@@ -29,6 +29,8 @@
 #include "gl_common.cuh"
 #include <string.h>
 
+extern "C" int glhost_pool_size(void);          // host/thread_pool.cpp: threads of the library's host pool
+
 namespace {
 
 constexpr int kScanThreads = 256;
@@ -2171,49 +2173,77 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
     GL_CHECK(gl_use(ctx));
     GL_CHECK(bed_args_ok(ctx, rs, re, W, step));
     if (n < 0 || (n > 0 && (!start || !end))) return gl_fail(ctx, GL_EINVAL, "gl_depth_bed_region: bad segments");
-    // How the int32 arrays travel (GL_BED_PACK).  0 (default): as they are — the call is PCIe-bound at 8 B/segment (chr20:
-    // 88 MB, 1.9 ms) and that is still the fastest on the B200 box's host.  16: the host pool repacks them, order-preserving
-    // and without a sort, to packed16 (4 B/segment) in 8 index chunks pipelined with the upload — measured: the repack
-    // costs 1.3 ms on 128 threads (3.4 ms on 32) plus 16 pool dispatches, 2.5-3.3 ms per call at best with a long tail, so
-    // it does not pay.  1: packed8 (2 B/segment, needs a sort: 2-3 ms).  A feeder that emits packed8 itself (gl_bam_decode)
-    // calls gl_depth_bed_region_packed8: 0.65 ms.  tools/e2e_text_probe.py measures all three.
-    static const int force = [] { const char* e = getenv("GL_BED_PACK"); return e ? atoi(e) : 0; }();
-    if (force == 16 && n >= (int64_t(1) << 18)) {
-        const int K = 8;
-        int64_t cap = n / 256 + n / 1024 + 64 * K;                     // blocks: full ones + slack for sparse stretches
-        const size_t bytes = (size_t)cap * (4 + 512 + 512) + 256;
+    // How the int32 arrays travel (GL_BED_PACK; default: auto).  The call is PCIe-bound at 8 B/segment (chr20: 88 MB, 1.9 ms).
+    // 16 / auto: the host pool rewrites them as fixed-block packed16 (gl_pack_segments16_fixed_range_mt: 4 B/segment, the
+    // caller's order, one vectorised streaming pass, no sort, no count pass) in a few block chunks; chunk c+1 is packed while
+    // chunk c is on the wire and unpacked into the segment store by depth_unpack16_kernel.  Auto takes it for >= 2^20
+    // segments when the pool has >= 24 threads (with fewer the pack is slower than the bytes it saves: 8 ranks on one
+    // host share its memory bandwidth).  0: plain int32.  1: packed8 (2 B/segment, needs a sort: 2-3 ms per chr20).
+    // A feeder that emits packed8 itself (gl_bam_decode) calls gl_depth_bed_region_packed8.  tools/e2e_text_probe.py measures all.
+    const char* force_env = getenv("GL_BED_PACK");                      // read per call (tests switch it)
+    const int force = force_env ? atoi(force_env) : -1;
+    if ((force == 16 && n >= 4096) || (force < 0 && n >= (int64_t(1) << 20) && glhost_pool_size() >= 24)) {
+        const int64_t nbk = (n + 255) / 256;
+        const size_t o_off = ((size_t)nbk * 4 + 255) & ~size_t(255), o_len = o_off + (size_t)nbk * 512, bytes = o_len + (size_t)nbk * 512;
         if (ctx->pack_pinned_bytes < bytes) {
             GL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
             if (ctx->pack_pinned) cudaFreeHost(ctx->pack_pinned);
             ctx->pack_pinned = nullptr; ctx->pack_pinned_bytes = 0;
-            cudaError_t e = cudaHostAlloc(&ctx->pack_pinned, bytes, cudaHostAllocDefault);
-            if (e != cudaSuccess) { ctx->pack_pinned = nullptr; cudaGetLastError(); return gl_fail(ctx, GL_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); }
-            ctx->pack_pinned_bytes = bytes;
+            const size_t want = bytes + bytes / 8;
+            cudaError_t e = cudaHostAlloc(&ctx->pack_pinned, want, cudaHostAllocDefault);
+            if (e != cudaSuccess) { ctx->pack_pinned = nullptr; cudaGetLastError(); return gl_fail(ctx, GL_ENOMEM, "cudaHostAlloc(%zu): %s", want, cudaGetErrorString(e)); }
+            ctx->pack_pinned_bytes = want;
         }
-        cap = (int64_t)((ctx->pack_pinned_bytes - 256) / 1028);
-        int32_t* A = static_cast<int32_t*>(ctx->pack_pinned);
-        uint16_t* O = reinterpret_cast<uint16_t*>(A + ((cap + 3) & ~int64_t(3)));
-        uint16_t* Ln = O + (size_t)cap * 256;
+        char* hp = static_cast<char*>(ctx->pack_pinned);
+        int32_t* A = reinterpret_cast<int32_t*>(hp);
+        uint16_t* O = reinterpret_cast<uint16_t*>(hp + o_off);
+        uint16_t* Ln = reinterpret_cast<uint16_t*>(hp + o_len);
         GL_CHECK(gl_depth_begin(ctx, rs, re));
-        GL_CHECK(store_reserve(ctx, (n + n / 4 + 256 * 64 * K)));       // the unpacked slots land here: no regrowth between chunks
-        // ... and the device staging of the packed words is sized once for the largest chunk there can be (a regrowth
-        // between chunks would free a buffer the copy stream is still writing)
-        GL_CHECK(gl_buf_reserve(ctx, ctx->packed, (((size_t)cap * 4 + 255) & ~size_t(255)) + 2 * (((size_t)cap * 512 + 255) & ~size_t(255))));
-        int64_t b_off = 0;
+        GL_CHECK(store_reserve(ctx, nbk * 256 + n / 16 + 8192));         // blocks + room for the escapes: no regrowth between chunks
+        GL_CHECK(gl_buf_reserve(ctx, ctx->packed, bytes));                // device staging, the host buffer's layout
+        char* dp = static_cast<char*>(ctx->packed.p);
+        std::vector<int32_t> es((size_t)(n / 16 + 4096)), ee(es.size());
+        int64_t n_esc = 0;
+        const int K = (int)std::max<int64_t>(1, std::min<int64_t>(8, nbk / 4096));   // >= 1 M segments per chunk
+        // (an earlier call's uploads out of the pinned buffer have finished: every entry point synchronises before it returns;
+        //  the previous call's unpack kernels out of ctx->packed are ordered before ours on ctx->stream via ev_used[0])
+        GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
+        int64_t done_blocks = 0;
+        bool fell_back = false;
         for (int c = 0; c < K; c++) {
-            const int64_t i0 = n * c / K, i1 = n * (c + 1) / K;
-            if (i1 <= i0) continue;
-            int64_t nb = 0;
-            // (an earlier call's uploads out of this buffer have finished: every entry point synchronises before it returns)
-            const int rc = gl_pack_segments16_mt(start + i0, end + i0, i1 - i0, threads, A + b_off, O + b_off * 256, Ln + b_off * 256, cap - b_off, &nb);
-            if (rc == GL_ERANGE) {                                       // very sparse input: the rest goes up as plain int32
-                GL_CHECK(gl_depth_add_segments(ctx, start + i0, end + i0, n - i0));
-                break;
+            const int64_t b0 = nbk * c / K, b1 = nbk * (c + 1) / K;
+            if (b1 <= b0) continue;
+            const int64_t esc_before = n_esc;
+            const int rc = gl_pack_segments16_fixed_range_mt(start, end, n, b0, b1, threads, A, O, Ln, es.data(), ee.data(), (int64_t)es.size(), &n_esc);
+            if (rc == GL_ERANGE) { n_esc = esc_before; fell_back = true; break; }   // (almost) every block escapes: long reads / unsorted input
+            if (rc != GL_OK) return gl_fail(ctx, rc, "gl_pack_segments16_fixed_range_mt failed");
+            GL_CUDA(ctx, cudaMemcpyAsync(dp + (size_t)b0 * 4, A + b0, (size_t)(b1 - b0) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+            GL_CUDA(ctx, cudaMemcpyAsync(dp + o_off + (size_t)b0 * 512, O + b0 * 256, (size_t)(b1 - b0) * 512, cudaMemcpyHostToDevice, ctx->copy_stream));
+            GL_CUDA(ctx, cudaMemcpyAsync(dp + o_len + (size_t)b0 * 512, Ln + b0 * 256, (size_t)(b1 - b0) * 512, cudaMemcpyHostToDevice, ctx->copy_stream));
+            GL_CUDA(ctx, cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
+            GL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));
+            {
+                gl_prof_scope prof(ctx, "depth_unpack16_kernel");
+                depth_unpack16_kernel<<<(unsigned)(b1 - b0), 256, 0, ctx->stream>>>(
+                    reinterpret_cast<const int*>(dp) + b0, reinterpret_cast<const unsigned short*>(dp + o_off) + b0 * 256,
+                    reinterpret_cast<const unsigned short*>(dp + o_len) + b0 * 256, static_cast<int*>(ctx->store_s.p) + b0 * 256,
+                    static_cast<int*>(ctx->store_e.p) + b0 * 256);
             }
-            if (rc != GL_OK) return gl_fail(ctx, rc, "gl_pack_segments16_mt failed");
-            GL_CHECK(gl_depth_add_segments_packed16(ctx, A + b_off, O + b_off * 256, Ln + b_off * 256, nb));
-            b_off += nb;
+            GL_LAUNCHED(ctx, 1);
+            done_blocks = b1;
         }
+        GL_CUDA(ctx, cudaEventRecord(ctx->ev_used[0], ctx->stream));
+        ctx->copies_pending = true;
+        if (done_blocks > 0) {
+            gl_seg_batch bt;
+            bt.off = 0; bt.n = done_blocks * 256;
+            ctx->batches.push_back(bt);
+            ctx->store_n = done_blocks * 256;
+            ctx->g_valid = false; ctx->ev_valid = false; ctx->depth_reduced = false;
+        }
+        if (fell_back)                                                    // the blocks not packed yet go up as plain int32 (another batch)
+            GL_CHECK(gl_depth_add_segments(ctx, start + done_blocks * 256, end + done_blocks * 256, n - done_blocks * 256));
+        if (n_esc > 0) GL_CHECK(gl_depth_add_segments(ctx, es.data(), ee.data(), n_esc));   // segments of the blocks written as empty
         GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, step));
         return gl_depth_text(ctx, chrom, depth_bed, depth_cap, depth_len, callable_bed, callable_cap, callable_len);
     }

@@ -6,6 +6,9 @@
 // does not fit 16 bits from the anchor (sparse regions), and segments longer than 65535 are split (harmless for depth).
 #include <stdint.h>
 #include <string.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include "../../../include/goleft_b200.h"
 
 extern "C" {
@@ -475,4 +478,139 @@ extern "C" int gl_pack_segments16_mt(const int32_t* start, const int32_t* end, i
     if (!(anchors && off && len) || cnt[(size_t)P] > cap_blocks) return GL_ERANGE;
     pool.run(P, [&](int64_t k, int) { pack16_chunk(start, end, lo_of(k), lo_of(k + 1), anchors, off, len, cnt[(size_t)k]); }, T);
     return GL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fixed-block packed16
+// gl_pack_segments16_fixed*: the same device format (256 slots per block, int32 anchor, uint16 off/len) with the block
+// boundaries FIXED: block b holds input segments [256 b, 256 b + 256) in the caller's order, anchor = their lowest start.
+// No count pass, no prefix sum, no data-dependent block edges: one streaming pass (AVX2 when the CPU has it: min/max
+// reduction + subtract + pack over 2 KB that stay in L1), every block independent.  A block whose starts span more than
+// 65535 bases or that holds a segment longer than 65535 (a block straddling a centromere gap; long reads) is written as
+// 256 empty slots and its segments are returned raw in the escape list (a few blocks per contig for short-read data).
+// This is what the one-call int32 entry uses to halve its PCIe bytes: the pack runs at memory speed on the host pool,
+// chunk c+1 is packed while chunk c is on the wire.
+namespace {
+
+inline bool block_scalar(const int32_t* s, const int32_t* e, int cnt, int32_t* anchor, uint16_t* off, uint16_t* len) {
+    int32_t smin = s[0], smax = s[0];
+    uint32_t lmax = 0;
+    for (int i = 0; i < cnt; i++) {
+        smin = s[i] < smin ? s[i] : smin;
+        smax = s[i] > smax ? s[i] : smax;
+        const uint32_t l = e[i] > s[i] ? (uint32_t)e[i] - (uint32_t)s[i] : 0u;
+        lmax = l > lmax ? l : lmax;
+    }
+    *anchor = smin;
+    if ((int64_t)smax - smin > 65535 || lmax > 65535u) return false;
+    for (int i = 0; i < cnt; i++) {
+        off[i] = (uint16_t)(s[i] - smin);
+        len[i] = (uint16_t)(e[i] > s[i] ? e[i] - s[i] : 0);
+    }
+    for (int i = cnt; i < 256; i++) { off[i] = 0; len[i] = 0; }
+    return true;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) inline bool block256_avx2(const int32_t* s, const int32_t* e, int32_t* anchor, uint16_t* off, uint16_t* len) {
+    __m256i vmin = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s)), vmax = vmin, lmax = _mm256_setzero_si256();
+    for (int i = 0; i < 256; i += 8) {
+        const __m256i S = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i));
+        const __m256i E = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(e + i));
+        vmin = _mm256_min_epi32(vmin, S);
+        vmax = _mm256_max_epi32(vmax, S);
+        lmax = _mm256_max_epu32(lmax, _mm256_and_si256(_mm256_sub_epi32(E, S), _mm256_cmpgt_epi32(E, S)));
+    }
+    alignas(32) int32_t a[8], b[8];
+    alignas(32) uint32_t c[8];
+    _mm256_store_si256(reinterpret_cast<__m256i*>(a), vmin);
+    _mm256_store_si256(reinterpret_cast<__m256i*>(b), vmax);
+    _mm256_store_si256(reinterpret_cast<__m256i*>(c), lmax);
+    int32_t smin = a[0], smax = b[0];
+    uint32_t lm = c[0];
+    for (int k = 1; k < 8; k++) { smin = a[k] < smin ? a[k] : smin; smax = b[k] > smax ? b[k] : smax; lm = c[k] > lm ? c[k] : lm; }
+    *anchor = smin;
+    if ((int64_t)smax - smin > 65535 || lm > 65535u) return false;
+    const __m256i A = _mm256_set1_epi32(smin);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(off) | reinterpret_cast<uintptr_t>(len)) & 31) == 0;
+    for (int i = 0; i < 256; i += 16) {
+        const __m256i S0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i)), S1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 8));
+        const __m256i E0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(e + i)), E1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(e + i + 8));
+        const __m256i O = _mm256_permute4x64_epi64(_mm256_packus_epi32(_mm256_sub_epi32(S0, A), _mm256_sub_epi32(S1, A)), 0xD8);
+        const __m256i L0 = _mm256_and_si256(_mm256_sub_epi32(E0, S0), _mm256_cmpgt_epi32(E0, S0));
+        const __m256i L1 = _mm256_and_si256(_mm256_sub_epi32(E1, S1), _mm256_cmpgt_epi32(E1, S1));
+        const __m256i L = _mm256_permute4x64_epi64(_mm256_packus_epi32(L0, L1), 0xD8);
+        if (aligned) {                                  // the output is written once and read by the DMA engine: keep it out of the caches
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(off + i), O);
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(len + i), L);
+        } else {
+            _mm256_storeu_si256(reinterpret_cast<__m256i*>(off + i), O);
+            _mm256_storeu_si256(reinterpret_cast<__m256i*>(len + i), L);
+        }
+    }
+    return true;
+}
+static const bool kHaveAvx2 = __builtin_cpu_supports("avx2");
+#else
+static const bool kHaveAvx2 = false;
+#endif
+
+// blocks [b0, b1) of the input; anchors/off/len are indexed by absolute block; escapes appended to es/ee
+void pack16_fixed_range(const int32_t* start, const int32_t* end, int64_t n, int64_t b0, int64_t b1, int32_t* anchors, uint16_t* off,
+                        uint16_t* len, std::vector<int32_t>& es, std::vector<int32_t>& ee) {
+    for (int64_t b = b0; b < b1; b++) {
+        const int64_t i0 = b * 256;
+        const int cnt = (int)std::min<int64_t>(256, n - i0);
+        bool ok;
+#if defined(__x86_64__)
+        if (cnt == 256 && kHaveAvx2) ok = block256_avx2(start + i0, end + i0, anchors + b, off + i0, len + i0);
+        else
+#endif
+            ok = block_scalar(start + i0, end + i0, cnt, anchors + b, off + i0, len + i0);
+        if (!ok) {
+            memset(off + i0, 0, 512);
+            memset(len + i0, 0, 512);
+            for (int i = 0; i < cnt; i++)
+                if (end[i0 + i] > start[i0 + i]) { es.push_back(start[i0 + i]); ee.push_back(end[i0 + i]); }
+        }
+    }
+#if defined(__x86_64__)
+    if (kHaveAvx2) _mm_sfence();
+#endif
+}
+
+}  // namespace
+
+extern "C" int gl_pack_segments16_fixed_range_mt(const int32_t* start, const int32_t* end, int64_t n, int64_t block_begin, int64_t block_end,
+                                                 int32_t threads, int32_t* anchors, uint16_t* off, uint16_t* len, int32_t* esc_start,
+                                                 int32_t* esc_end, int64_t esc_cap, int64_t* n_esc) {
+    using namespace glhost;
+    const int64_t nbk = (n + 255) / 256;
+    if (n < 0 || block_begin < 0 || block_end < block_begin || block_end > nbk || !n_esc || *n_esc < 0) return GL_EINVAL;
+    if (block_end > block_begin && (!start || !end || !anchors || !off || !len)) return GL_EINVAL;
+    if (block_end == block_begin) return GL_OK;
+    ThreadPool& pool = ThreadPool::global();
+    const int T = threads > 0 ? std::min<int>(threads, pool.size()) : pool.size();
+    const int64_t nb = block_end - block_begin;
+    const int64_t P = std::max<int64_t>(1, std::min<int64_t>((int64_t)T * 2, nb / 64 + 1));   // >= 16 K segments per task, two tasks per thread
+    std::vector<std::vector<int32_t>> es((size_t)P), ee((size_t)P);
+    auto lo_of = [&](int64_t k) { return block_begin + (int64_t)((__int128)nb * k / P); };
+    pool.run(P, [&](int64_t k, int) { pack16_fixed_range(start, end, n, lo_of(k), lo_of(k + 1), anchors, off, len, es[(size_t)k], ee[(size_t)k]); }, T);
+    int64_t m = *n_esc;
+    for (int64_t k = 0; k < P; k++) {
+        const int64_t c = (int64_t)es[(size_t)k].size();
+        if (c == 0) continue;
+        if (m + c > esc_cap || !esc_start || !esc_end) { *n_esc = m + c; return GL_ERANGE; }
+        memcpy(esc_start + m, es[(size_t)k].data(), (size_t)c * 4);
+        memcpy(esc_end + m, ee[(size_t)k].data(), (size_t)c * 4);
+        m += c;
+    }
+    *n_esc = m;
+    return GL_OK;
+}
+
+extern "C" int gl_pack_segments16_fixed_mt(const int32_t* start, const int32_t* end, int64_t n, int32_t threads, int32_t* anchors, uint16_t* off,
+                                           uint16_t* len, int32_t* esc_start, int32_t* esc_end, int64_t esc_cap, int64_t* n_esc) {
+    if (!n_esc) return GL_EINVAL;
+    *n_esc = 0;
+    return gl_pack_segments16_fixed_range_mt(start, end, n, 0, (n + 255) / 256, threads, anchors, off, len, esc_start, esc_end, esc_cap, n_esc);
 }

@@ -125,6 +125,18 @@ int  gl_pack_segments16_mt(const int32_t* start, const int32_t* end, int64_t n, 
                            uint16_t* len, int64_t cap_blocks, int64_t* n_blocks);
 int  gl_depth_add_segments_packed16(gl_ctx* ctx, const int32_t* anchors, const uint16_t* off, const uint16_t* len,
                                     int64_t n_blocks);
+/* The same device format with FIXED block boundaries: block b = input segments [256 b, 256 b + 256) in the caller's order,
+ * anchor = their lowest start; n_blocks = ceil(n / 256) (caller-sized outputs: anchors[n_blocks], off/len[256 n_blocks]).
+ * One streaming pass on the host pool, no sort, no count pass.  A block that cannot be expressed (starts more than 65535
+ * bases apart, or a segment longer than 65535) is written as 256 empty slots and its segments are appended raw to
+ * esc_start/esc_end (*n_esc in/out for the _range form); GL_ERANGE when they exceed esc_cap (*n_esc = needed).  Adding the
+ * blocks (gl_depth_add_segments_packed16) and the escapes (gl_depth_add_segments) gives exactly the input's segments.
+ * This is how gl_depth_bed_region moves decoder-native int32 arrays at 4 B/segment. */
+int  gl_pack_segments16_fixed_mt(const int32_t* start, const int32_t* end, int64_t n, int32_t threads, int32_t* anchors, uint16_t* off,
+                                 uint16_t* len, int32_t* esc_start, int32_t* esc_end, int64_t esc_cap, int64_t* n_esc);
+int  gl_pack_segments16_fixed_range_mt(const int32_t* start, const int32_t* end, int64_t n, int64_t block_begin, int64_t block_end,
+                                       int32_t threads, int32_t* anchors, uint16_t* off, uint16_t* len, int32_t* esc_start,
+                                       int32_t* esc_end, int64_t esc_cap, int64_t* n_esc);
 /* "packed8": a quarter of the bytes, for short-read data.  Blocks of 64 slots: int32 anchor (start of slot 0) +
  * per slot uint8 dstart (start - previous slot's start) and uint8 len (0 = empty/filler).  gl_pack_segments8 puts the
  * segments in start order (depth is order-independent), cuts segments longer than 255 into pieces and bridges gaps

@@ -417,6 +417,39 @@ def test_indexcov_cohort(tmp_path, extranorm):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 3, 7])
+def test_indexcov_cohort_sample_sharded(tmp_path, gpus):
+    """samples shard across the GPUs through I5, the rows gather on the host.  `--gpus N` must give the bytes of
+    `--gpus 1` (GL_OVERSUBSCRIBE lets a one-GPU box run N shards: shard g -> device g % n_dev)."""
+    refs, fai, paths, lin = _cohort_bais(tmp_path)
+    outs = []
+    for g in (1, gpus):
+        out = tmp_path / ("g%d" % g) / "tt"
+        os.makedirs(str(out.parent))
+        run("indexcov", "-d", str(out), "--gpus", str(g), "--fai", fai, *paths, env={"GL_OVERSUBSCRIBE": "1"})
+        outs.append([open(str(out / ("tt-indexcov." + ext)), "rb").read() for ext in ("bed.gz", "roc", "ped")])
+    assert gzip.decompress(outs[0][0]) == gzip.decompress(outs[1][0]) and outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2]
+    assert len(gzip.decompress(outs[1][0]).splitlines()) > 400
+
+
+@pytest.mark.gpu
+def test_depth_gpus_oversubscribed_same_bytes(tmp_path):
+    """`goleft depth --gpus 3` (LPT over three workers, here on however many devices the box has) == `--gpus 1`"""
+    sys.path.insert(0, os.path.join(ROOT, "tools", "synth"))
+    import glsynth
+    contigs = [("chr1", 3_000_000, 1), ("chr2", 2_100_000, 2), ("chr3", 1_000_000, 3), ("chr4", 500_000, 4), ("chrM", 16_569, 24)]
+    bam = str(tmp_path / "synth.bam")
+    glsynth.write_bam(bam, contigs, coverage=8.0)
+    (tmp_path / "g.fa.fai").write_text("".join("%s\t%d\t6\t60\t61\n" % (c[0], c[1]) for c in contigs))
+    got = []
+    for g in (1, 3):
+        prefix = str(tmp_path / ("o%d" % g))
+        run("depth", "--gpus", str(g), "-w", "250", "--prefix", prefix, "-r", str(tmp_path / "g.fa"), bam, env={"GL_OVERSUBSCRIBE": "1"})
+        got.append((open(prefix + ".depth.bed", "rb").read(), open(prefix + ".callable.bed", "rb").read()))
+    assert got[0] == got[1] and got[0][0].count(b"\n") == sum((c[1] - 1) // 250 + 1 for c in contigs)
+
+
+@pytest.mark.gpu
 def test_indexcov_no_usable_chromosomes(tmp_path):
     refs = [("1", 100000)]
     (tmp_path / "g.fa.fai").write_text("1\t100000\t6\t60\t61\n")

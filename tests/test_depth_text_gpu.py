@@ -104,3 +104,50 @@ def test_g4_tokens_equal_printf(ctx):
     for i in range(sums.size):
         mean = 0.0 if sums[i] == 0 else float(sums[i]) / float(lens[i])
         assert got[i] == "c\t%d\t%d\t%s" % (row_s[i], row_e[i], "%.4g" % mean), (i, sums[i], lens[i])
+
+
+@pytest.fixture
+def packed_transport(monkeypatch):
+    """the one-call int32 entry with its fixed-block packed16 transport forced on (auto needs >= 2^20 segments)"""
+    monkeypatch.setenv("GL_BED_PACK", "16")
+    yield
+    monkeypatch.delenv("GL_BED_PACK", raising=False)
+
+
+def test_packed16_transport_same_bytes(ctx, packed_transport):
+    # 5.3 Mb at 30x: a centromere gap (one block straddles it -> escape list), a 200x pile-up, deletion reads whose second
+    # block is out of order, a segment count that is not a multiple of 256, several upload chunks
+    L = 5_300_017
+    s, e = synth.segments(synth.reads(L, contig_index=9))
+    assert s.size % 256 != 0 and s.size > 4096
+    a, o, ln, es, ee = capi.pack_segments16_fixed(s, e)
+    assert es.size > 0                                            # the gap block escaped
+    for W, mincov, maxmean in ((500, 4, 0), (250, 4, 60)):
+        exp = oracle_contig_text("chr9", L, s, e, W, mincov, maxmean)
+        before = ctx.launch_count()
+        got = ctx.depth_bed_contig("chr9", L, s, e, W, mincov, maxmean, step_for(W))
+        assert got[0] == exp[0] and got[1] == exp[1]
+        assert ctx.depth_last_path() == 1                         # unpacked into the store, then the fused int32 path
+        assert ctx.launch_count() - before >= 6                   # + depth_unpack16_kernel
+
+
+def test_packed16_transport_empty_unsorted_and_long_segments(ctx, packed_transport):
+    rng = np.random.default_rng(5)
+    L = 2_000_000
+    # unsorted + empty/reversed segments + negative starts and ends beyond the region
+    s = rng.integers(-200, L + 100, 300_000).astype(np.int32)
+    e = (s + rng.integers(-5, 160, s.size)).astype(np.int32)
+    exp = oracle_contig_text("u", L, s, e, 500, 4, 0)
+    assert ctx.depth_bed_contig("u", L, s, e, 500, 4, 0, 10_000_000) == exp
+    # long reads: every block escapes (segments > 65535 or starts too far apart) -> the call falls back to plain int32
+    s = np.sort(rng.integers(0, L - 100_000, 5000)).astype(np.int32)
+    e = (s + rng.integers(60_000, 100_000, s.size)).astype(np.int32)
+    exp = oracle_contig_text("lr", L, s, e, 500, 4, 0)
+    assert ctx.depth_bed_contig("lr", L, s, e, 500, 4, 0, 10_000_000) == exp
+    # sparse: 20 kb reads 40 kb apart -> most blocks escape but the list fits
+    s = (np.arange(6000, dtype=np.int64) * 300).astype(np.int32)
+    e = (s + 150).astype(np.int32)
+    s[::512] += 70_000                                            # one outlier per second block
+    e[::512] += 70_000
+    exp = oracle_contig_text("sp", L, s, e, 250, 1, 0)
+    assert ctx.depth_bed_contig("sp", L, s, e, 250, 1, 0, 10_000_000) == exp

@@ -374,3 +374,37 @@ def test_pack_segments8_mt_same_pieces():
     u2s, u2e = capi.unpack_segments8(a2, d2, l2)
     assert int((u2e - u2s).sum()) == int((e.astype(np.int64) - s).sum())
     assert np.array_equal(orc.pileup_diff(u2s.astype(np.int32), u2e.astype(np.int32), 0, 1_010_000), orc.pileup_diff(s, e, 0, 1_010_000))
+
+
+def test_pack16_fixed_roundtrip():
+    """host-only: fixed-block packed16 (gl_pack_segments16_fixed_mt) decodes to the input's segments, in order; blocks that do not
+    fit 16 bits come back raw in the escape list"""
+    from goleft_b200 import capi
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 255, 256, 257, 100_000):
+        s = np.sort(rng.integers(0, 3_000_000, n)).astype(np.int32)
+        e = (s + rng.integers(-3, 200, n)).astype(np.int32)
+        if n > 1000:
+            s[5000:5300] += 2_000_000                            # a gap inside a block
+            e[5000:5300] += 2_000_000
+            e[777] = s[777] + 70_000                             # one long segment
+        for thr in (1, 3):
+            a, o, ln, es, ee = capi.pack_segments16_fixed(s, e, threads=thr)
+            nb = (n + 255) // 256
+            assert a.size == nb and o.size == nb * 256
+            S = (np.repeat(a.astype(np.int64), 256) + o)[:n]
+            E = S + ln[:n]
+            escaped = np.repeat(ln.reshape(-1, 256).max(1) == 0, 256)[:n] if n else np.zeros(0, bool)
+            live = e > s
+            keep = ~escaped & live
+            assert np.array_equal(S[keep], s[keep]) and np.array_equal(E[keep], e[keep])
+            assert np.all(ln[:n][~escaped & ~live] == 0)
+            assert np.all(ln[n:] == 0)
+            # a block is escaped only when it has to be ... or holds no live segment at all (then it is empty either way)
+            m = escaped & live
+            assert np.array_equal(es, s[m]) and np.array_equal(ee, e[m])
+            if n > 1000:
+                assert 0 < es.size < 2000
+    with pytest.raises(capi.GlError):
+        s = np.arange(0, 100_000 * 1000, 100_000, dtype=np.int32)
+        capi.pack_segments16_fixed(s, s + 10, esc_cap=10)
