@@ -453,7 +453,10 @@ def config_legs(ctx, L, nm, n_cpus, timed_dev, timed_host, kernel_times, check):
             call = lambda: ctx.depth_bed_contig(nm, Lc, h_s, h_e, par["W"], par["mincov"], par["maxmean"], STEP, out=(o_hd, o_ca), raw=True)
             t_e2e = timed_host(call, 5)
             hl, cl = call()
-            ent["e2e_text_int32"] = {"ms": t_e2e, "value": Lc / t_e2e / 1e3, "h2d_bytes": h2d_bytes_of(n), "d2h_bytes": int(hl + cl)}
+            st = ctx.depth_transport_stats()
+            ent["e2e_text_int32"] = {"ms": t_e2e, "value": Lc / t_e2e / 1e3, "h2d_bytes": st[2], "d2h_bytes": int(hl + cl), "transport": st[0],
+                                     "host_pack_ms": st[1] * 1e3, "depth_path": ctx.depth_last_path(),
+                                     "host_phases_ms": dict(zip(("setup", "pack_and_enqueue_loop", "reduce_text_d2h"), [x * 1e3 for x in ctx.depth_transport_phases()]))}
             if check:
                 from oracle import loader as orc
                 s_, e_ = sorted_copy(np.array(h_s), np.array(h_e))
@@ -469,18 +472,6 @@ def config_legs(ctx, L, nm, n_cpus, timed_dev, timed_host, kernel_times, check):
             b.free()
         res[key] = ent
     return res
-
-
-def h2d_bytes_of(nseg, pool_threads=None):
-    """bytes gl_depth_bed_contig moves host->device for nseg int32 segments: fixed-block packed16 (4 B/segment + 4 B per 256)
-    when the library's auto rule takes it (>= 2^20 segments, pool >= 24 threads, GL_BED_PACK unset), else 8 B/segment"""
-    from goleft_b200 import capi
-    if pool_threads is None:
-        pool_threads = int(capi.lib.glhost_pool_size())
-    if os.environ.get("GL_BED_PACK", "-1") in ("-1", "16") and nseg >= (1 << 20) and (pool_threads >= 24 or os.environ.get("GL_BED_PACK") == "16"):
-        nb = (nseg + 255) // 256
-        return nb * (4 + 1024)
-    return 8 * nseg
 
 
 def cli_wallclock(n_cpus):
@@ -624,13 +615,19 @@ def main():
             ctx.depth_reduce(W, MINCOV, MAXMEAN, STEP)
 
     text_bytes = [0, 0]
+    tr = {"h2d": 0, "pack_s": 0.0, "escaped": 0, "paths": set(), "kinds": set()}
 
     def step_e2e():
         hb = cb = 0
+        h2d, pack_s, esc = 0, 0.0, 0
         for w in work:
             hl, cl = ctx.depth_bed_contig(w["name"], w["L"], w["h_s"], w["h_e"], W, MINCOV, MAXMEAN, STEP, threads=0, out=(o_hd, o_ca), raw=True)
             hb += hl; cb += cl
+            kind, ps, nb, ne = ctx.depth_transport_stats()
+            h2d += nb; pack_s += ps; esc += ne
+            tr["kinds"].add(kind); tr["paths"].add(ctx.depth_last_path())
         text_bytes[0], text_bytes[1] = hb, cb
+        tr["h2d"], tr["pack_s"], tr["escaped"] = h2d, pack_s, esc
 
     # ---- warm-up (also sizes every grow-only buffer)
     for _ in range(args.warmup):
@@ -769,6 +766,7 @@ def main():
         x_hbm_k, _ = kernel_times(3, one_int32)
         ctx.depth_set_path(0)
         x_e2e_text = timed_host(lambda: ctx.depth_bed_contig(nm, L, w["h_s"], w["h_e"], W, MINCOV, MAXMEAN, STEP, out=(o_hd, o_ca), raw=True), n_x)
+        x_e2e_stats = ctx.depth_transport_stats() + (ctx.depth_last_path(), [x * 1e3 for x in ctx.depth_transport_phases()])
         os.environ["GL_BED_PACK"] = "0"
         x_e2e_plain = timed_host(lambda: ctx.depth_bed_contig(nm, L, w["h_s"], w["h_e"], W, MINCOV, MAXMEAN, STEP, out=(o_hd, o_ca), raw=True), n_x)
         del os.environ["GL_BED_PACK"]
@@ -786,7 +784,9 @@ def main():
                   "hbm_difference_array_path": {"ms": x_hbm, "value": L / x_hbm / 1e3, "kernel_ms": x_hbm_k,
                                                 "note": "the pipeline north_star sketches, on request (gl_depth_set_path(2)): memset + K_scatter "
                                                         "(red.global) + K_super + K_scan + K_gather"},
-                  "e2e_text_int32": {"ms": x_e2e_text, "value": L / x_e2e_text / 1e3, "h2d_bytes": h2d_bytes_of(w["nseg"]),
+                  "e2e_text_int32": {"ms": x_e2e_text, "value": L / x_e2e_text / 1e3, "h2d_bytes": x_e2e_stats[2], "transport": x_e2e_stats[0],
+                                     "host_pack_ms": x_e2e_stats[1] * 1e3, "escaped_segments": x_e2e_stats[3], "depth_path": x_e2e_stats[4],
+                                     "host_phases_ms": dict(zip(("setup", "pack_and_enqueue_loop", "reduce_text_d2h"), x_e2e_stats[5])),
                                      "call": "gl_depth_bed_contig (what `e2e` times, on this contig alone): int32 arrays in, repacked by the host pool to "
                                              "fixed-block packed16 (4 B/segment) chunk by chunk while the previous chunk is on the wire"},
                   "e2e_text_int32_plain_upload": {"ms": x_e2e_plain, "value": L / x_e2e_plain / 1e3, "h2d_bytes": 8 * w["nseg"],
@@ -843,12 +843,12 @@ def main():
         per_rank = [[float(x[0]) / args.steps, float(x[1]) / args.steps] for x in g]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = (float(x) for x in t)
-        cnt = torch.tensor([float(launches), float(nseg), float(n_runs), float(text_bytes[0] + text_bytes[1]), float(sum(h2d_bytes_of(w["nseg"]) for w in work))],
+        cnt = torch.tensor([float(launches), float(nseg), float(n_runs), float(text_bytes[0] + text_bytes[1]), float(tr["h2d"])],
                            dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches_all, nseg_all, n_runs_all, d2h_all, h2d_all = (int(x) for x in cnt)
     else:
-        launches_all, nseg_all, n_runs_all, d2h_all, h2d_all = launches, nseg, n_runs, text_bytes[0] + text_bytes[1], sum(h2d_bytes_of(w["nseg"]) for w in work)
+        launches_all, nseg_all, n_runs_all, d2h_all, h2d_all = launches, nseg, n_runs, text_bytes[0] + text_bytes[1], tr["h2d"]
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -885,7 +885,11 @@ def main():
                        "ms_per_step": ms_e2e_step, "kernel_ms_rank0": k_ms_e2e,
                        "call": "gl_depth_bed_contig per contig: int32 (start,end) segments in pinned host memory -> .depth.bed + .callable.bed bytes in pinned host memory",
                        "transport": "auto (fixed-block packed16, 4 B/segment, when the rank's host pool has >= 24 threads; else plain int32, 8 B/segment)",
-                       "host_pool_threads": int(capi.lib.glhost_pool_size())},
+                       "host_pool_threads": int(capi.lib.glhost_pool_size()),
+                       "rank0": {"transport": sorted(tr["kinds"]), "host_pack_ms_per_step": tr["pack_s"] * 1e3, "escaped_segments": tr["escaped"],
+                                 "depth_paths": sorted(tr["paths"]),
+                                 "note": "gl_depth_transport_stats / gl_depth_last_path per contig: transport 16 = fixed-block packed16, 0 = plain int32; "
+                                         "path 1 = fused int32 kernels"}},
                "e2e_check": e2e_check,
                "gpu_launches": int(launches_all),
                "roofline": {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": peak, "peak_source": peak_src,

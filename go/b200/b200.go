@@ -91,16 +91,50 @@ func (c *Ctx) DepthContig(b *Bam, tid int, chrom string, length int, window, min
 	if step < window {
 		step = window
 	}
-	var seg C.gl_bam_segments
-	ebuf := make([]byte, 512)
-	if rc := C.gl_bam_decode(b.h, C.int32_t(tid), 0, C.int64_t(length), C.int32_t(q), 0, 0, &seg, (*C.char)(unsafe.Pointer(&ebuf[0])), 512); rc != C.GL_OK {
-		return nil, nil, fmt.Errorf("goleft_b200: %s", C.GoString((*C.char)(unsafe.Pointer(&ebuf[0]))))
-	}
 	cs := C.CString(chrom)
 	defer C.free(unsafe.Pointer(cs))
 	nWin := (length-1)/window + 1
 	depthBed = make([]byte, int(C.gl_depth_text_bound(cs, C.int64_t(nWin))))
 	callableBed = make([]byte, 1<<20)
+	var seg C.gl_bam_segments
+	// The feeder on the GPU first (BGZF inflate + record parse + filter + CIGAR walk on the device: only compressed bytes
+	// cross PCIe); GL_ESTATE means this reference cannot take that road (no usable index, a member the device inflater
+	// rejects) and the host feeder below decodes it.
+	var dS, dE *C.int32_t
+	var dN C.int64_t
+	if rc := C.gl_bam_decode_device(c.h, b.h, C.int32_t(tid), C.int32_t(q), &dS, &dE, &dN, &seg); rc == C.GL_OK {
+		if e := c.err(C.gl_depth_begin(c.h, 0, C.int64_t(length))); e != nil {
+			return nil, nil, e
+		}
+		if dN > 0 {
+			if e := c.err(C.gl_depth_add_segments_device(c.h, dS, dE, dN)); e != nil {
+				return nil, nil, e
+			}
+		}
+		if e := c.err(C.gl_depth_reduce(c.h, C.int32_t(window), C.int32_t(minCov), C.int32_t(maxMeanDepth), C.int64_t(step))); e != nil {
+			return nil, nil, e
+		}
+		for attempt := 0; attempt < 2; attempt++ {
+			var dl, cl C.int64_t
+			rc := C.gl_depth_text(c.h, cs, (*C.char)(unsafe.Pointer(&depthBed[0])), C.int64_t(len(depthBed)), &dl,
+				(*C.char)(unsafe.Pointer(&callableBed[0])), C.int64_t(len(callableBed)), &cl)
+			if rc == C.GL_ERANGE && attempt == 0 {
+				depthBed = make([]byte, int(dl)+16)
+				callableBed = make([]byte, int(cl)+16)
+				continue
+			}
+			if e := c.err(rc); e != nil {
+				return nil, nil, e
+			}
+			return depthBed[:dl], callableBed[:cl], nil
+		}
+	} else if rc != C.GL_ESTATE {
+		return nil, nil, c.err(rc)
+	}
+	ebuf := make([]byte, 512)
+	if rc := C.gl_bam_decode(b.h, C.int32_t(tid), 0, C.int64_t(length), C.int32_t(q), 0, 0, &seg, (*C.char)(unsafe.Pointer(&ebuf[0])), 512); rc != C.GL_OK {
+		return nil, nil, fmt.Errorf("goleft_b200: %s", C.GoString((*C.char)(unsafe.Pointer(&ebuf[0]))))
+	}
 	for attempt := 0; attempt < 2; attempt++ {
 		var dl, cl C.int64_t
 		var rc C.int

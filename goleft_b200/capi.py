@@ -147,6 +147,8 @@ _proto("gl_depth_region_packed16", C.c_int, _vp, C.c_int64, C.c_int64, _vp, _vp,
        C.c_int32, C.c_int64, _vp, C.c_int64, _i64p, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_pack_segments8_bound", C.c_int64, C.c_int64)
 _proto("gl_pack_segments8", C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _i64p)
+_proto("gl_depth_transport_phases", C.c_int, _vp, C.POINTER(C.c_double))
+_proto("gl_depth_transport_stats", C.c_int, _vp, _i32p, C.POINTER(C.c_double), _i64p, _i64p)
 _proto("gl_pack_segments16_fixed_mt", C.c_int, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_pack_segments8_mt", C.c_int, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, C.c_int64, _i64p)
 _proto("gl_depth_add_segments_packed8", C.c_int, _vp, _vp, _vp, _vp, C.c_int64)
@@ -644,6 +646,17 @@ class Ctx:
         p = C.c_int32(0)
         self._ck(lib.gl_depth_last_path(self.h, C.byref(p)))
         return p.value
+
+    def depth_transport_stats(self):
+        """(transport, host pack seconds, bytes sent host->device, escaped segments) of the last depth_bed_contig call"""
+        t, ps, hb, ne = C.c_int32(0), C.c_double(0), C.c_int64(0), C.c_int64(0)
+        self._ck(lib.gl_depth_transport_stats(self.h, C.byref(t), C.byref(ps), C.byref(hb), C.byref(ne)))
+        return t.value, ps.value, hb.value, ne.value
+
+    def depth_transport_phases(self):
+        ph = (C.c_double * 3)()
+        self._ck(lib.gl_depth_transport_phases(self.h, ph))
+        return [ph[0], ph[1], ph[2]]
 
     def depth_set_path(self, path: int):
         self._ck(lib.gl_depth_set_path(self.h, path))

@@ -28,6 +28,7 @@
 // All arithmetic is integer; results are bit-exact against oracle/oracle_depth.c.
 #include "gl_common.cuh"
 #include <string.h>
+#include <chrono>
 
 extern "C" int glhost_pool_size(void);          // host/thread_pool.cpp: threads of the library's host pool
 
@@ -704,101 +705,153 @@ __global__ void __launch_bounds__(256) depth_events_kernel(const int* __restrict
         warp_tile_add(tile_starts, tS, cS, 1, lane);
         warp_tile_add(tile_ends, tE, cE, 1, lane);
     } else {
+        // two events per live segment; lanes whose event falls in the same tile share one cursor atomic.  Three phases so that
+        // the eight cursor atomics of a thread are in flight together (a phase-per-event loop waits ~1 us for each return):
+        // groups and ranks, then the leaders' atomics, then the shuffles and the 2-byte stores.
+        int pos_[8], t_[8];
+        unsigned grp_[8], base_[8];
+        bool on_[8];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int a = 0, b = 0; bool live = false;
             if (j < cnt) ev_clip(s[j], e[j], rs, re, a, b, live);
-            // two events per live segment; lanes whose event falls in the same tile share one cursor atomic
 #pragma unroll
             for (int which = 0; which < 2; which++) {
-                const int pos = which ? b : a;
-                const int t = pos >> kTileShift;
-                const bool on = live && t < num_tiles;
-                const unsigned grp = __match_any_sync(kFull, on ? t : -1 - lane);   // lanes without an event are alone in their group
-                if (on) {
-                    const int leader = __ffs(grp) - 1;
-                    unsigned base = 0;
-                    if (lane == leader) base = atomicAdd(cursor + t, (unsigned)__popc(grp));
-                    base = __shfl_sync(grp, base, leader);
-                    const unsigned slot = bucket_off[t] + base + (unsigned)__popc(grp & ((1u << lane) - 1u));
-                    events[slot] = (unsigned short)((pos & (kTile - 1)) | (which << 15));
-                }
+                const int k = 2 * j + which;
+                pos_[k] = which ? b : a;
+                t_[k] = pos_[k] >> kTileShift;
+                on_[k] = live && t_[k] < num_tiles;
+                grp_[k] = __match_any_sync(kFull, on_[k] ? t_[k] : -1 - lane);     // lanes without an event are alone in their group
+                base_[k] = 0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (on_[k] && lane == __ffs(grp_[k]) - 1) base_[k] = atomicAdd(cursor + t_[k], (unsigned)__popc(grp_[k]));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned base = __shfl_sync(kFull, base_[k], on_[k] ? __ffs(grp_[k]) - 1 : lane);
+            if (on_[k]) {
+                const unsigned slot = bucket_off[t_[k]] + base + (unsigned)__popc(grp_[k] & ((1u << lane) - 1u));
+                events[slot] = (unsigned short)((pos_[k] & (kTile - 1)) | ((k & 1) << 15));
             }
         }
     }
 }
 
-// bucket_off[t] = events in tiles < t; carry[t] = (starts - ends) in tiles < t = the depth carried into tile t.  One CTA,
-// 4096 tiles per round (coalesced loads, 4 per thread), two warp scans per round.  Both scans ride in one 64-bit word: events
-// in the high half, net depth (signed) in the low half.
+// bucket_off[t] = events in tiles < t; carry[t] = (starts - ends) in tiles < t = the depth carried into tile t.  One CTA; every
+// thread owns a contiguous run of tiles (a multiple of 4: 128-bit loads and stores): thread-local totals, ONE block scan (two
+// barriers in all), then the thread walks its run again (L1 hits) and writes.  Both scans ride in one 64-bit word: events in
+// the high half, net depth (signed) in the low half.  The count arrays are zero-padded to a multiple of 4 entries past
+// num_tiles (ev_layout), and so are the outputs.
 __global__ void __launch_bounds__(1024) depth_evscan_kernel(const int* __restrict__ tile_starts, const int* __restrict__ tile_ends, int num_tiles,
                                                            unsigned* __restrict__ bucket_off, int* __restrict__ carry) {
     __shared__ long long s_w[32];
-    __shared__ long long s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_base = 0;
+    const int T4 = (num_tiles + 2 + 3) & ~3;                        // allocated entries (ev_layout)
+    const int per = ((num_tiles + 1 + 1023) / 1024 + 3) & ~3;       // entries per thread
+    const int i0 = tid * per;
+    long long tot = 0;
+#pragma unroll 4
+    for (int j = 0; j < per; j += 4) {
+        const int i = i0 + j;
+        if (i < T4) {
+            const int4 st = *reinterpret_cast<const int4*>(tile_starts + i), en = *reinterpret_cast<const int4*>(tile_ends + i);
+            tot += ((long long)(st.x + en.x) << 32) + (long long)(st.x - en.x);
+            tot += ((long long)(st.y + en.y) << 32) + (long long)(st.y - en.y);
+            tot += ((long long)(st.z + en.z) << 32) + (long long)(st.z - en.z);
+            tot += ((long long)(st.w + en.w) << 32) + (long long)(st.w - en.w);
+        }
+    }
+    long long inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) s_w[warp] = inc;
     __syncthreads();
-    for (int base = 0; base <= num_tiles; base += 4096) {
-        long long v[4];
+    const long long wv = s_w[lane];                                 // every warp scans the 32 warp totals
+    long long winc = wv;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int i = base + j * 1024 + tid;                     // coalesced: consecutive threads, consecutive tiles
-            const int st = i < num_tiles ? tile_starts[i] : 0, en = i < num_tiles ? tile_ends[i] : 0;
-            v[j] = ((long long)(st + en) << 32) + (long long)(st - en);
-        }
-        // scan order is tile order: segment j (1024 tiles) before segment j+1; inside a segment by thread
-        long long run_before = s_base;
+    for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(kFull, winc, o); if (lane >= o) winc += y; }
+    long long run = __shfl_sync(kFull, winc, warp) - __shfl_sync(kFull, wv, warp) + inc - tot;     // exclusive prefix of this thread's run
+#pragma unroll 2
+    for (int j = 0; j < per; j += 4) {
+        const int i = i0 + j;
+        if (i < T4) {
+            const int4 st = *reinterpret_cast<const int4*>(tile_starts + i), en = *reinterpret_cast<const int4*>(tile_ends + i);
+            const int sv[4] = {st.x, st.y, st.z, st.w}, ev[4] = {en.x, en.y, en.z, en.w};
+            unsigned bo[4];
+            int ca[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            long long inc = v[j];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += y; }
-            if (lane == 31) s_w[warp] = inc;
-            __syncthreads();
-            long long wv = lane < 32 ? s_w[lane] : 0;                // every warp scans the 32 warp totals
-            long long winc = wv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(kFull, winc, o); if (lane >= o) winc += y; }
-            const long long warp_excl = __shfl_sync(kFull, winc, warp) - __shfl_sync(kFull, wv, warp);
-            const long long seg_total = __shfl_sync(kFull, winc, 31);
-            const long long excl = run_before + warp_excl + inc - v[j];
-            const int i = base + j * 1024 + tid;
-            if (i <= num_tiles) {
-                const long long lo = (long long)(int)(excl & 0xffffffffll);   // low word, sign-extended
-                bucket_off[i] = (unsigned)((excl - lo) >> 32);
-                carry[i] = (int)lo;
+            for (int k = 0; k < 4; k++) {
+                const long long lo = (long long)(int)(run & 0xffffffffll);       // low word, sign-extended
+                bo[k] = (unsigned)((run - lo) >> 32);
+                ca[k] = (int)lo;
+                run += ((long long)(sv[k] + ev[k]) << 32) + (long long)(sv[k] - ev[k]);
             }
-            run_before += seg_total;
-            __syncthreads();
+            *reinterpret_cast<uint4*>(bucket_off + i) = make_uint4(bo[0], bo[1], bo[2], bo[3]);
+            *reinterpret_cast<int4*>(carry + i) = make_int4(ca[0], ca[1], ca[2], ca[3]);
         }
-        if (tid == 0) s_base = run_before;
-        __syncthreads();
     }
 }
 
-// K_evtile: one CTA per tile: zero 16 KB, the tile's events into shared memory, tile core.  (256 threads x 16 bases: the
-// kernel is not persistent, and with one tile per CTA the 128-thread / 32-base shape of K_fused8 measured 12 % slower here.)
+// K_evtile: persistent CTAs (tile += gridDim.x), software-pipelined like K_fused8: while tile n runs its core, the first
+// kEvPre * 256 events of tile n+1 are already in flight into registers and so is the bucket range of tile n+2 (round 2's
+// one-CTA-per-tile version stalled 6 issue slots per instruction on those dependent loads).  The core clears the tile as it
+// reads it.  256 threads x 16 bases (the 128 x 32 shape of K_fused8 measured slower here).
 constexpr int kEvThreads = kScanThreads;
 constexpr int kEvWarps = kWarps;
+constexpr int kEvPre = 6;                              // prefetched events per thread: 1536 per tile (a 30x / 150 bp tile holds ~1400)
+
+struct EvRegs { unsigned short e[kEvPre]; };
+
+__device__ __forceinline__ EvRegs evtile_load(const unsigned short* __restrict__ events, unsigned lo, unsigned hi) {
+    EvRegs r;
+#pragma unroll
+    for (int k = 0; k < kEvPre; k++) {
+        const unsigned i = lo + threadIdx.x + (unsigned)k * kEvThreads;
+        r.e[k] = i < hi ? events[i] : (unsigned short)0;                // slots beyond the bucket are skipped by index, not by value
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(kEvThreads, 4) depth_evtile_kernel(const ScanParams p, const unsigned short* __restrict__ events,
                                                                      const unsigned* __restrict__ bucket_off, const int* __restrict__ carry) {
     __shared__ __align__(16) int s_tile[kTile];
     __shared__ __align__(16) int s_depth[kTile];
-    __shared__ int s_carry[kEvWarps];
+    __shared__ int s_carry2[2][kEvWarps];
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
+    const int G = gridDim.x, T = p.num_tiles;
 #pragma unroll
-    for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);
-    if (tid < kEvWarps) s_carry[tid] = tid == 0 ? carry[tile] : 0;
-    const unsigned lo = bucket_off[tile], hi = bucket_off[tile + 1];
-    __syncthreads();
-    for (unsigned i = lo + tid; i < hi; i += kEvThreads) {
-        const unsigned ev = events[i];
-        atomicAdd(s_tile + swz_elem((int)(ev & (kTile - 1))), (ev >> 15) ? -1 : 1);
-    }
+    for (int j = 0; j < 4; j++) reinterpret_cast<int4*>(s_tile)[tid * 4 + j] = make_int4(0, 0, 0, 0);   // later tiles: cleared by the core
+    if (tid < 2 * kEvWarps) (&s_carry2[0][0])[tid] = 0;
+    int tile = blockIdx.x;
+    unsigned lo = 0, hi = 0, lo2 = 0, hi2 = 0;
+    int cin = 0, cin2 = 0;
+    if (tile < T) { lo = bucket_off[tile]; hi = bucket_off[tile + 1]; cin = carry[tile]; }
+    if (tile + G < T) { lo2 = bucket_off[tile + G]; hi2 = bucket_off[tile + G + 1]; cin2 = carry[tile + G]; }
+    EvRegs regs = evtile_load(events, lo, hi);
     __syncthreads();
     int acc_max = 0;
-    tile_core<16, kEvWarps, false>(p, s_tile, s_depth, s_carry, tile, acc_max);
+    for (int it = 0; tile < T; tile += G, it ^= 1) {
+        int* s_carry = s_carry2[it];
+        // an event is (position in the tile | sign << 15)
+#pragma unroll
+        for (int k = 0; k < kEvPre; k++) {
+            const unsigned ev = regs.e[k];
+            if (lo + tid + (unsigned)k * kEvThreads < hi) atomicAdd(s_tile + swz_elem((int)(ev & (kTile - 1))), (ev >> 15) ? -1 : 1);
+        }
+        for (unsigned i = lo + tid + (unsigned)kEvPre * kEvThreads; i < hi; i += kEvThreads) {        // deep tiles only
+            const unsigned ev = events[i];
+            atomicAdd(s_tile + swz_elem((int)(ev & (kTile - 1))), (ev >> 15) ? -1 : 1);
+        }
+        if (tid == 0) s_carry[0] = cin;                     // slots 1.. stay 0 (only slot 0 of either buffer is ever written)
+        __syncthreads();
+        lo = lo2; hi = hi2; cin = cin2;
+        regs = evtile_load(events, lo, hi);                 // next tile's events: in flight during the core
+        lo2 = hi2 = 0; cin2 = 0;
+        if (tile + 2 * G < T) { lo2 = bucket_off[tile + 2 * G]; hi2 = bucket_off[tile + 2 * G + 1]; cin2 = carry[tile + 2 * G]; }
+        tile_core<16, kEvWarps, true>(p, s_tile, s_depth, s_carry, tile, acc_max);
+    }
     flush_max(p, acc_max);
 }
 
@@ -1659,7 +1712,7 @@ int run_reduce(gl_ctx* ctx, int32_t W, int32_t mincov, int32_t maxmean, int64_t 
             const unsigned fused_grid = (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 4);
             if (fused) depth_fused_kernel<<<fused_grid, kScanThreads, 0, ctx->stream>>>(p);
             else if (hbm_diff) depth_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(p);
-            else depth_evtile_kernel<<<(unsigned)tiles, kEvThreads, 0, ctx->stream>>>(p, evl.events, evl.bucket_off, evl.carry);
+            else depth_evtile_kernel<<<(unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 4), kEvThreads, 0, ctx->stream>>>(p, evl.events, evl.bucket_off, evl.carry);
         }
         GL_LAUNCHED(ctx, 1);
         if (do_runs) {
@@ -1968,6 +2021,21 @@ int gl_depth_result_sizes(gl_ctx* ctx, int64_t* n_windows, int64_t* n_runs, int3
     return GL_OK;
 }
 
+int gl_depth_transport_stats(gl_ctx* ctx, int32_t* transport, double* pack_s, int64_t* h2d_bytes, int64_t* n_escaped) {
+    if (!ctx) return GL_EINVAL;
+    if (transport) *transport = ctx->tr_kind;
+    if (pack_s) *pack_s = ctx->tr_pack_s;
+    if (h2d_bytes) *h2d_bytes = ctx->tr_bytes;
+    if (n_escaped) *n_escaped = ctx->tr_esc;
+    return GL_OK;
+}
+
+int gl_depth_transport_phases(gl_ctx* ctx, double phases_s[3]) {
+    if (!ctx || !phases_s) return GL_EINVAL;
+    for (int i = 0; i < 3; i++) phases_s[i] = ctx->tr_phase[i];
+    return GL_OK;
+}
+
 int gl_depth_last_path(gl_ctx* ctx, int32_t* path) {
     if (!ctx || !path) return gl_fail(ctx, GL_EINVAL, "null argument");
     *path = ctx->last_path;
@@ -2183,6 +2251,7 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
     const char* force_env = getenv("GL_BED_PACK");                      // read per call (tests switch it)
     const int force = force_env ? atoi(force_env) : -1;
     if ((force == 16 && n >= 4096) || (force < 0 && n >= (int64_t(1) << 20) && glhost_pool_size() >= 24)) {
+        const auto ph0 = std::chrono::steady_clock::now();
         const int64_t nbk = (n + 255) / 256;
         const size_t o_off = ((size_t)nbk * 4 + 255) & ~size_t(255), o_len = o_off + (size_t)nbk * 512, bytes = o_len + (size_t)nbk * 512;
         if (ctx->pack_pinned_bytes < bytes) {
@@ -2199,10 +2268,20 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
         uint16_t* O = reinterpret_cast<uint16_t*>(hp + o_off);
         uint16_t* Ln = reinterpret_cast<uint16_t*>(hp + o_len);
         GL_CHECK(gl_depth_begin(ctx, rs, re));
-        GL_CHECK(store_reserve(ctx, nbk * 256 + n / 16 + 8192));         // blocks + room for the escapes: no regrowth between chunks
+        GL_CHECK(store_reserve(ctx, nbk * 256 + n / 32 + 65536 + 64));    // blocks + room for the escapes: no regrowth between chunks
         GL_CHECK(gl_buf_reserve(ctx, ctx->packed, bytes));                // device staging, the host buffer's layout
         char* dp = static_cast<char*>(ctx->packed.p);
-        std::vector<int32_t> es((size_t)(n / 16 + 4096)), ee(es.size());
+        // escape list: ctx-owned and grow-only (a fresh zero-filled vector per call cost more page faults than the pack itself)
+        const size_t esc_want = (size_t)(n / 32 + 65536);
+        if (ctx->esc_cap < esc_want) {
+            free(ctx->esc_buf);
+            ctx->esc_buf = static_cast<int32_t*>(malloc(2 * esc_want * sizeof(int32_t)));
+            ctx->esc_cap = ctx->esc_buf ? esc_want : 0;
+            if (!ctx->esc_buf) return gl_fail(ctx, GL_ENOMEM, "malloc(%zu)", 2 * esc_want * sizeof(int32_t));
+        }
+        int32_t* es = ctx->esc_buf;
+        int32_t* ee = ctx->esc_buf + ctx->esc_cap;
+        const int64_t esc_cap = (int64_t)ctx->esc_cap;
         int64_t n_esc = 0;
         const int K = (int)std::max<int64_t>(1, std::min<int64_t>(8, nbk / 4096));   // >= 1 M segments per chunk
         // (an earlier call's uploads out of the pinned buffer have finished: every entry point synchronises before it returns;
@@ -2210,11 +2289,15 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
         GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
         int64_t done_blocks = 0;
         bool fell_back = false;
+        const auto ph1 = std::chrono::steady_clock::now();
+        ctx->tr_kind = 16; ctx->tr_pack_s = 0; ctx->tr_bytes = 0; ctx->tr_esc = 0;
         for (int c = 0; c < K; c++) {
             const int64_t b0 = nbk * c / K, b1 = nbk * (c + 1) / K;
             if (b1 <= b0) continue;
             const int64_t esc_before = n_esc;
-            const int rc = gl_pack_segments16_fixed_range_mt(start, end, n, b0, b1, threads, A, O, Ln, es.data(), ee.data(), (int64_t)es.size(), &n_esc);
+            const auto tp0 = std::chrono::steady_clock::now();
+            const int rc = gl_pack_segments16_fixed_range_mt(start, end, n, b0, b1, threads, A, O, Ln, es, ee, esc_cap, &n_esc);
+            ctx->tr_pack_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count();
             if (rc == GL_ERANGE) { n_esc = esc_before; fell_back = true; break; }   // (almost) every block escapes: long reads / unsorted input
             if (rc != GL_OK) return gl_fail(ctx, rc, "gl_pack_segments16_fixed_range_mt failed");
             GL_CUDA(ctx, cudaMemcpyAsync(dp + (size_t)b0 * 4, A + b0, (size_t)(b1 - b0) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -2231,6 +2314,7 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
             }
             GL_LAUNCHED(ctx, 1);
             done_blocks = b1;
+            ctx->tr_bytes += (b1 - b0) * (4 + 1024);
         }
         GL_CUDA(ctx, cudaEventRecord(ctx->ev_used[0], ctx->stream));
         ctx->copies_pending = true;
@@ -2241,11 +2325,24 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
             ctx->store_n = done_blocks * 256;
             ctx->g_valid = false; ctx->ev_valid = false; ctx->depth_reduced = false;
         }
+        const auto ph2 = std::chrono::steady_clock::now();
+        ctx->tr_esc = n_esc;
+        ctx->tr_bytes += 8 * n_esc + (fell_back ? 8 * (n - done_blocks * 256) : 0);
         if (fell_back)                                                    // the blocks not packed yet go up as plain int32 (another batch)
             GL_CHECK(gl_depth_add_segments(ctx, start + done_blocks * 256, end + done_blocks * 256, n - done_blocks * 256));
-        if (n_esc > 0) GL_CHECK(gl_depth_add_segments(ctx, es.data(), ee.data(), n_esc));   // segments of the blocks written as empty
+        if (n_esc > 0) {
+            // the segments of the blocks written as empty: a batch of their OWN (each batch has its own cell index; appended to the
+            // packed batch they would sit out of order at its end and the fused path would reject the tiles around every gap)
+            ctx->store_n += 4;                                            // a gap in the store keeps gl_depth_add_segments from extending the previous batch
+            GL_CHECK(gl_depth_add_segments(ctx, es, ee, n_esc));
+        }
         GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, step));
-        return gl_depth_text(ctx, chrom, depth_bed, depth_cap, depth_len, callable_bed, callable_cap, callable_len);
+        const int rc_text = gl_depth_text(ctx, chrom, depth_bed, depth_cap, depth_len, callable_bed, callable_cap, callable_len);
+        const auto ph3 = std::chrono::steady_clock::now();
+        ctx->tr_phase[0] = std::chrono::duration<double>(ph1 - ph0).count();
+        ctx->tr_phase[1] = std::chrono::duration<double>(ph2 - ph1).count();
+        ctx->tr_phase[2] = std::chrono::duration<double>(ph3 - ph2).count();
+        return rc_text;
     }
     bool pack = force == 1 && n >= 4096;
     if (pack) {                                       // long segments would be cut into many 255-base pieces: judged on a sample
@@ -2255,6 +2352,7 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
         pack = tot <= 400 * cnt;
     }
     if (!pack) {
+        ctx->tr_kind = 0; ctx->tr_pack_s = 0; ctx->tr_bytes = 8 * n; ctx->tr_esc = 0;
         GL_CHECK(gl_depth_begin(ctx, rs, re));
         GL_CHECK(gl_depth_add_segments(ctx, start, end, n));
         GL_CHECK(gl_depth_reduce(ctx, W, mincov, maxmean, step));

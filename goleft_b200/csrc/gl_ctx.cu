@@ -186,6 +186,7 @@ int gl_ctx_destroy(gl_ctx* ctx) {
         if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);
     }
     if (ctx->pack_pinned) cudaFreeHost(ctx->pack_pinned);
+    free(ctx->esc_buf);
     for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     for (auto e : ctx->ev_chunk) cudaEventDestroy(e);

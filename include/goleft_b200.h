@@ -172,6 +172,12 @@ int  gl_depth_result_sizes(gl_ctx* ctx, int64_t* n_windows, int64_t* n_runs, int
  * int32 copy, no per-segment index), 4 = bucketed events (the general path: any order, any length; two 16-bit events per
  * segment bucketed by 4096-base tile, difference arrays built in shared memory). */
 int  gl_depth_last_path(gl_ctx* ctx, int32_t* path);
+/* How the last gl_depth_bed_region / gl_depth_bed_contig call moved its int32 arrays: transport 0 = as they are (8 B/segment),
+ * 16 = fixed-block packed16 made by the host pool chunk by chunk (4 B/segment); host seconds spent packing (the calling
+ * thread's wall time inside the pool runs), bytes sent host->device, segments that went up raw as escapes. */
+int  gl_depth_transport_stats(gl_ctx* ctx, int32_t* transport, double* pack_s, int64_t* h2d_bytes, int64_t* n_escaped);
+/* host wall-clock phases of the same call: [0] setup (buffers, gl_depth_begin), [1] the pack + enqueue loop, [2] reduce + text + D2H */
+int  gl_depth_transport_phases(gl_ctx* ctx, double phases_s[3]);
 /* 0 = choose automatically (default: packed8 -> fused -> bucketed events), 1 = never the packed8 kernel, 2 = always the HBM
  * difference array, 4 = always bucketed events (tests, comparison runs). */
 int  gl_depth_set_path(gl_ctx* ctx, int32_t path);
