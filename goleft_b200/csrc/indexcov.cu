@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kCohortThreads) ic_cohort_kernel(const long lo
 //     a pathological order — the sample falls back to the range-adaptive select above, so the result is always exact.
 //   A last pass writes float32(float64(size)/med).  Traffic: 2 reads of 8 B + 1 write of 4 B per tile.
 constexpr int kC2Threads = 1024;
+constexpr int kC2Unroll = 8;                         // 8-byte loads in flight per thread in the streaming passes
 constexpr int kC2Sample = 8192;
 constexpr int kC2CandM = 8192;
 constexpr int kC2Cand98 = 4096;
@@ -314,19 +315,30 @@ __global__ void __launch_bounds__(kC2Threads, 1) ic_cohort2_kernel(const long lo
             ok = hiM < lo98;                                                       // brackets must not touch
             long long sum_lo = 0, sum_mid = 0, cnt_above = 0, vmax = 0;
             if (ok) {
-                const long long n_round = (n + kC2Threads - 1) / kC2Threads * kC2Threads;
-                for (long long i = tid; i < n_round; i += kC2Threads) {
-                    const bool live = i < n;
-                    const long long x = live ? v[i] : 0;
-                    const bool inM = live && x >= loM && x <= hiM, in98 = live && x >= lo98 && x <= hi98;
-                    if (live) {
-                        vmax = max(vmax, x);
-                        if (x < loM) sum_lo += x;
-                        else if (x > hiM && x < lo98) sum_mid += x;
-                        else if (x > hi98) cnt_above++;
+                // kC2Unroll loads per thread are issued before any of them is used: one CTA per SM has only 32 warps, and with one
+                // 8-byte load per warp in flight the pass ran at DRAM latency (1 TB/s over the chip), not at bandwidth
+                const long long n_round = (n + kC2Unroll * kC2Threads - 1) / (kC2Unroll * kC2Threads) * (kC2Unroll * kC2Threads);
+                for (long long base = 0; base < n_round; base += kC2Unroll * kC2Threads) {
+                    long long xs[kC2Unroll];
+#pragma unroll
+                    for (int u = 0; u < kC2Unroll; u++) {
+                        const long long i = base + (long long)u * kC2Threads + tid;
+                        xs[u] = i < n ? __ldg(v + i) : 0;
                     }
-                    warp_append(sm.candM, kC2CandM, &s_cnt[0], &s_cnt[2], inM, x);
-                    warp_append(sm.cand98, kC2Cand98, &s_cnt[1], &s_cnt[2], in98, x);
+#pragma unroll
+                    for (int u = 0; u < kC2Unroll; u++) {
+                        const long long x = xs[u];
+                        const bool live = base + (long long)u * kC2Threads + tid < n;
+                        const bool inM = live && x >= loM && x <= hiM, in98 = live && x >= lo98 && x <= hi98;
+                        if (live) {
+                            vmax = max(vmax, x);
+                            if (x < loM) sum_lo += x;
+                            else if (x > hiM && x < lo98) sum_mid += x;
+                            else if (x > hi98) cnt_above++;
+                        }
+                        warp_append(sm.candM, kC2CandM, &s_cnt[0], &s_cnt[2], inM, x);
+                        warp_append(sm.cand98, kC2Cand98, &s_cnt[1], &s_cnt[2], in98, x);
+                    }
                 }
                 sum_lo = block_sum(sum_lo, s_red);
                 sum_mid = block_sum(sum_mid, s_red);
@@ -405,10 +417,20 @@ __global__ void __launch_bounds__(kC2Threads, 1) ic_cohort2_kernel(const long lo
         // depth = float32(float64(o)/median), capped at 50000                    (indexcov.go:129-151)
         if (depth_out) {
             float* out = depth_out + a;
-            for (long long i = tid; i < n; i += kC2Threads) {
-                float d = (med == 0) ? 0.0f : __double2float_rn(__ddiv_rn((double)v[i], dm));
-                if (d > 50000.0f) d = 50000.0f;
-                out[i] = d;
+            for (long long base = 0; base < n; base += kC2Unroll * kC2Threads) {
+                long long xs[kC2Unroll];
+#pragma unroll
+                for (int u = 0; u < kC2Unroll; u++) {
+                    const long long i = base + (long long)u * kC2Threads + tid;
+                    xs[u] = i < n ? __ldg(v + i) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < kC2Unroll; u++) {
+                    const long long i = base + (long long)u * kC2Threads + tid;
+                    float d = (med == 0) ? 0.0f : __double2float_rn(__ddiv_rn((double)xs[u], dm));
+                    if (d > 50000.0f) d = 50000.0f;
+                    if (i < n) out[i] = d;
+                }
             }
         }
         __syncthreads();
@@ -740,13 +762,44 @@ __device__ __forceinline__ unsigned long long scaled_round(unsigned m, int e2, i
     return (unsigned long long)q;
 }
 
+__constant__ unsigned long long c_p10[13] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull,
+                                              1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull};
+
+// the same value in 64-bit arithmetic when everything fits (normalised depths are 1e-3 .. 1e3: k in [0, 5], a power-of-two
+// denominator -> a multiply, a shift and a compare); false: take scaled_round
+__device__ __forceinline__ bool scaled_round_fast(unsigned m, int e2, int k, unsigned long long& N) {
+    if (k >= 0) {
+        if (k > 11 || e2 >= 0 || e2 <= -64) return false;
+        const unsigned long long num = (unsigned long long)m * c_p10[k];            // < 2^24 * 10^11 < 2^61
+        const int sh = -e2;
+        const unsigned long long q = num >> sh, rem = num & ((1ull << sh) - 1ull), half = 1ull << (sh - 1);
+        N = q + ((rem > half || (rem == half && (q & 1ull))) ? 1ull : 0ull);
+        return true;
+    }
+    if (-k > 12) return false;
+    unsigned long long den = c_p10[-k], num = m;
+    if (e2 >= 0) { if (e2 > 39) return false; num <<= e2; }
+    else { const int sh = -e2; if (sh >= 62 || den > (0x3fffffffffffffffull >> sh)) return false; den <<= sh; }
+    const unsigned long long q = num / den, r = num - q * den;                     // den < 2^62: 2 r does not overflow
+    N = q + ((2ull * r > den || (2ull * r == den && (q & 1ull))) ? 1ull : 0ull);
+    return true;
+}
+
+__device__ __forceinline__ unsigned long long scaled_round_any(unsigned m, int e2, int k) {
+    unsigned long long N;
+    return scaled_round_fast(m, e2, k, N) ? N : scaled_round(m, e2, k);
+}
+
+// One value per thread; the 10-byte tokens of a CTA are put together in shared memory and leave as 16-byte stores (a thread
+// writing its own 10 bytes issued ten strided byte stores: the kernel ran at 6 % of HBM bandwidth).
 __global__ void __launch_bounds__(256) fmt_g3_kernel(const float* __restrict__ v, long long n, unsigned char* __restrict__ out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    __shared__ __align__(16) unsigned char s_tok[256 * 10];
+    const long long i0 = (long long)blockIdx.x * 256;
+    const long long i = i0 + threadIdx.x;
     unsigned char t[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) t[k] = 0;
-    const float f = v[i];
+    const float f = i < n ? v[i] : 0.0f;
     const unsigned bits = __float_as_uint(f);
     const bool neg = bits >> 31;
     const unsigned ex = (bits >> 23) & 0xff, frac = bits & 0x7fffff;
@@ -760,15 +813,20 @@ __global__ void __launch_bounds__(256) fmt_g3_kernel(const float* __restrict__ v
     } else {
         const unsigned m = ex ? (frac | 0x800000u) : frac;
         const int e2 = ex ? (int)ex - 150 : -149;
-        int e10 = (int)floor(log10((double)fabsf(f)));
+        // floor(log10 |f|): for normal numbers from the binary exponent E (2^E <= |f| < 2^(E+1)): floor(E log10 2) is the answer or
+        // one less (corrected below by the digits themselves); subnormals take the floating-point estimate
+        int e10 = ex ? (((int)ex - 127) * 78913) >> 18 : (int)floor(log10((double)fabsf(f)));
         if (e10 < -15 || e10 >= 15) {
             len = 0;                                             // host formats it
         } else {
-            unsigned long long N = scaled_round(m, e2, 2 - e10);
-            if (N < 100) { e10--; N = scaled_round(m, e2, 2 - e10); }          // log10 estimate one too high
-            else if (N > 1000) { e10++; N = scaled_round(m, e2, 2 - e10); }    // one too low
-            if (N >= 1000) { N = 100; e10++; }                                 // 999.5.. rounds up to the next decade
-            const int d1 = (int)(N / 100), d2 = (int)(N / 10 % 10), d3 = (int)(N % 10);
+            unsigned long long N = scaled_round_any(m, e2, 2 - e10);
+            if (N < 100) { e10--; N = scaled_round_any(m, e2, 2 - e10); }          // estimate one too high
+            else if (N > 1000) { e10++; N = scaled_round_any(m, e2, 2 - e10); }    // one too low
+            if (N >= 1000) { N = 100; e10++; }                                     // 999.5.. rounds up to the next decade
+            if (e10 < -15 || e10 >= 15) len = 0;
+            else {
+            const unsigned Nu = (unsigned)N;
+            const int d1 = (int)(Nu / 100u), d2 = (int)(Nu / 10u % 10u), d3 = (int)(Nu % 10u);
             const int nd = d3 ? 3 : (d2 ? 2 : 1);                // significant digits after stripping zeros
             const int dig[3] = {d1, d2, d3};
             if (neg) t[len++] = '-';
@@ -792,12 +850,21 @@ __global__ void __launch_bounds__(256) fmt_g3_kernel(const float* __restrict__ v
                 for (int z = 0; z < -e10 - 1; z++) t[len++] = '0';
                 for (int k = 0; k < nd; k++) t[len++] = (unsigned char)('0' + dig[k]);
             }
+            }
         }
     }
     t[9] = (unsigned char)len;
-    unsigned char* o = out + i * 10;
+    unsigned short* st = reinterpret_cast<unsigned short*>(s_tok + threadIdx.x * 10);
 #pragma unroll
-    for (int k = 0; k < 10; k++) o[k] = t[k];
+    for (int k = 0; k < 5; k++) st[k] = (unsigned short)(t[2 * k] | (t[2 * k + 1] << 8));
+    __syncthreads();
+    const long long live = min((long long)256, n - i0);         // tokens of this CTA that exist
+    unsigned char* o = out + i0 * 10;
+    if (live == 256 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        if (threadIdx.x < 160) reinterpret_cast<uint4*>(o)[threadIdx.x] = reinterpret_cast<const uint4*>(s_tok)[threadIdx.x];
+    } else {
+        for (long long j = threadIdx.x; j < live * 10; j += 256) o[j] = s_tok[j];
+    }
 }
 
 // indexsplit (indexsplit/indexsplit.go:92-115): cohort data per 16 KB tile = sum over the samples, IN PATH ORDER, of
