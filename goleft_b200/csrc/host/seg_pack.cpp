@@ -6,6 +6,7 @@
 // does not fit 16 bits from the anchor (sparse regions), and segments longer than 65535 are split (harmless for depth).
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -591,7 +592,10 @@ extern "C" int gl_pack_segments16_fixed_range_mt(const int32_t* start, const int
     ThreadPool& pool = ThreadPool::global();
     const int T = threads > 0 ? std::min<int>(threads, pool.size()) : pool.size();
     const int64_t nb = block_end - block_begin;
-    const int64_t P = std::max<int64_t>(1, std::min<int64_t>((int64_t)T * 2, nb / 64 + 1));   // >= 16 K segments per task, two tasks per thread
+    // tasks: GL_PACK_TASKS_PER_THREAD (default 2) per thread, at least GL_PACK_MIN_BLOCKS (default 64 = 16 K segments) each
+    static const int tpt = [] { const char* e = getenv("GL_PACK_TASKS_PER_THREAD"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+    static const int minb = [] { const char* e = getenv("GL_PACK_MIN_BLOCKS"); const int v = e ? atoi(e) : 64; return v < 1 ? 1 : v; }();
+    const int64_t P = std::max<int64_t>(1, std::min<int64_t>((int64_t)T * tpt, nb / minb + 1));
     std::vector<std::vector<int32_t>> es((size_t)P), ee((size_t)P);
     auto lo_of = [&](int64_t k) { return block_begin + (int64_t)((__int128)nb * k / P); };
     pool.run(P, [&](int64_t k, int) { pack16_fixed_range(start, end, n, lo_of(k), lo_of(k + 1), anchors, off, len, es[(size_t)k], ee[(size_t)k]); }, T);

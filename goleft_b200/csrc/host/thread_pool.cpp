@@ -47,13 +47,15 @@ ThreadPool::~ThreadPool() {
     for (auto& t : workers_) t.join();
 }
 
-void ThreadPool::work(int id) {
-    const std::function<void(int64_t, int)>& fn = *fn_;
-    const int64_t n = n_tasks_;
+void ThreadPool::work(int id, uint32_t generation) {
     for (;;) {
-        const int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
-        if (i >= n) break;
-        fn(i, id);
+        uint64_t cur = job_.load(std::memory_order_acquire);
+        if ((uint32_t)(cur >> 32) != generation) return;                 // this job is over (a later one may be running: not ours)
+        const int64_t i = (int64_t)(cur & 0xffffffffull);
+        if (i >= n_tasks_) return;                                       // n_tasks_ / fn_ were published before job_ (release / acquire)
+        if (!job_.compare_exchange_weak(cur, cur + 1, std::memory_order_acq_rel, std::memory_order_acquire)) continue;
+        (*fn_)(i, id);
+        done_.fetch_add(1, std::memory_order_release);
     }
 }
 
@@ -77,10 +79,7 @@ void ThreadPool::worker_main(int id) {
         if (g == seen) continue;
         seen = g;
         const int limit = (int)(g & ((1u << kLimitBits) - 1));
-        if (id < limit) {
-            work(id);
-            active_.fetch_sub(1, std::memory_order_acq_rel);
-        }
+        if (id < limit) work(id, (uint32_t)(g >> kLimitBits));
     }
 }
 
@@ -90,22 +89,22 @@ void ThreadPool::run(int64_t n_tasks, const std::function<void(int64_t, int)>& f
     int limit = size();
     if (max_threads > 0 && max_threads < limit) limit = max_threads;
     if ((int64_t)limit > n_tasks) limit = (int)n_tasks;
-    if (limit <= 1) {
+    if (limit <= 1 || n_tasks >= (int64_t(1) << 31)) {
         for (int64_t i = 0; i < n_tasks; i++) fn(i, 0);
         return;
     }
+    const uint64_t generation = (gen_.load(std::memory_order_relaxed) >> kLimitBits) + 1;
     fn_ = &fn;
     n_tasks_ = n_tasks;
-    next_.store(0, std::memory_order_relaxed);
-    active_.store(limit - 1, std::memory_order_relaxed);
+    done_.store(0, std::memory_order_relaxed);
+    job_.store((uint64_t)(uint32_t)generation << 32, std::memory_order_release);
     {
         std::lock_guard<std::mutex> lk(mu_);
-        const uint64_t generation = (gen_.load(std::memory_order_relaxed) >> kLimitBits) + 1;
         gen_.store((generation << kLimitBits) | (uint64_t)limit, std::memory_order_release);
     }
     cv_.notify_all();
-    work(0);
-    while (active_.load(std::memory_order_acquire) != 0) GL_CPU_PAUSE();
+    work(0, (uint32_t)generation);
+    while (done_.load(std::memory_order_acquire) != n_tasks) GL_CPU_PAUSE();
     fn_ = nullptr;
 }
 

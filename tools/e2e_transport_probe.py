@@ -58,6 +58,53 @@ def main():
                                                  es.ctypes.data, ee.ctypes.data, es.size, C.byref(m))
             ts.append((time.perf_counter() - t0) * 1e3)
         out["packer_alone_ms"][str(thr)] = {"min": float(np.min(ts)), "median": float(np.median(ts)), "GBps_in": n * 8 / (np.min(ts) * 1e-3) / 1e9}
+    # the packer in 8 block ranges back to back (what the call does), host only ...
+    L = capi.lib
+    L.gl_pack_segments16_fixed_range_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 5 + [C.c_int64, C.POINTER(C.c_int64)]
+
+    def ranges(K, thr=0):
+        m.value = 0
+        t0 = time.perf_counter()
+        per = []
+        for c in range(K):
+            t1 = time.perf_counter()
+            L.gl_pack_segments16_fixed_range_mt(s.ctypes.data, e.ctypes.data, n, nb * c // K, nb * (c + 1) // K, thr, a.ctypes.data, o.ctypes.data,
+                                                ln.ctypes.data, es.ctypes.data, ee.ctypes.data, es.size, C.byref(m))
+            per.append((time.perf_counter() - t1) * 1e3)
+        return (time.perf_counter() - t0) * 1e3, per
+    for thr in (0, 32, 16):
+        out["packer_ranges_host_only_ms_threads_%d" % thr] = {str(K): min(ranges(K, thr)[0] for _ in range(6)) for K in (1, 2, 4, 8, 16)}
+    out["packer_8_ranges_host_only_ms"] = min(ranges(8)[0] for _ in range(8))
+    out["packer_8_ranges_host_only_per_range_ms"] = ranges(8)[1]
+    # ... and the same while an unrelated H2D copy out of pinned memory is running (does the DMA slow the CPU's streaming pass?)
+    try:
+        import torch
+        big = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+        dev = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.Stream()
+        res = []
+        for _ in range(4):
+            with torch.cuda.stream(st):
+                dev.copy_(big, non_blocking=True)
+            t_all, per = ranges(8)
+            busy = not st.query()
+            st.synchronize()
+            res.append({"ms": t_all, "copy_still_running_after": bool(busy), "per_range_ms": per})
+        out["packer_8_ranges_during_h2d_dma"] = res
+        # and the other way round: H2D time of 1 GiB alone and while the packer loops
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(st):
+            ev0.record(st); dev.copy_(big, non_blocking=True); ev1.record(st)
+        st.synchronize()
+        out["h2d_1GiB_alone_ms"] = ev0.elapsed_time(ev1)
+        with torch.cuda.stream(st):
+            ev0.record(st); dev.copy_(big, non_blocking=True); ev1.record(st)
+        while not st.query():
+            ranges(8)
+        st.synchronize()
+        out["h2d_1GiB_while_packing_ms"] = ev0.elapsed_time(ev1)
+    except Exception as ex:
+        out["dma_interference_error"] = str(ex)[:200]
     # plain H2D of the same bytes for scale
     d = ctx.dev_empty(n * 8)
     ts = []
