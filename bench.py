@@ -884,7 +884,7 @@ def main():
                "e2e": {"value": e2e_val, "unit": "Mbases/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                        "ms_per_step": ms_e2e_step, "kernel_ms_rank0": k_ms_e2e,
                        "call": "gl_depth_bed_contig per contig: int32 (start,end) segments in pinned host memory -> .depth.bed + .callable.bed bytes in pinned host memory",
-                       "transport": "auto (fixed-block packed16, 4 B/segment, when the rank's host pool has >= 24 threads; else plain int32, 8 B/segment)",
+                       "transport": "auto (fixed-block packed16, 4 B/segment, packed by 16 pool threads, when the rank's host pool has >= 48 threads; else plain int32, 8 B/segment)",
                        "host_pool_threads": int(capi.lib.glhost_pool_size()),
                        "rank0": {"transport": sorted(tr["kinds"]), "host_pack_ms_per_step": tr["pack_s"] * 1e3, "escaped_segments": tr["escaped"],
                                  "depth_paths": sorted(tr["paths"]),

@@ -705,35 +705,26 @@ __global__ void __launch_bounds__(256) depth_events_kernel(const int* __restrict
         warp_tile_add(tile_starts, tS, cS, 1, lane);
         warp_tile_add(tile_ends, tE, cE, 1, lane);
     } else {
-        // two events per live segment; lanes whose event falls in the same tile share one cursor atomic.  Three phases so that
-        // the eight cursor atomics of a thread are in flight together (a phase-per-event loop waits ~1 us for each return):
-        // groups and ranks, then the leaders' atomics, then the shuffles and the 2-byte stores.
-        int pos_[8], t_[8];
-        unsigned grp_[8], base_[8];
-        bool on_[8];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int a = 0, b = 0; bool live = false;
             if (j < cnt) ev_clip(s[j], e[j], rs, re, a, b, live);
+            // two events per live segment; lanes whose event falls in the same tile share one cursor atomic.  (Issuing the eight
+            // atomics of a thread before the first shuffle was tried: 48 registers instead of 24, 76 us instead of 62.)
 #pragma unroll
             for (int which = 0; which < 2; which++) {
-                const int k = 2 * j + which;
-                pos_[k] = which ? b : a;
-                t_[k] = pos_[k] >> kTileShift;
-                on_[k] = live && t_[k] < num_tiles;
-                grp_[k] = __match_any_sync(kFull, on_[k] ? t_[k] : -1 - lane);     // lanes without an event are alone in their group
-                base_[k] = 0;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (on_[k] && lane == __ffs(grp_[k]) - 1) base_[k] = atomicAdd(cursor + t_[k], (unsigned)__popc(grp_[k]));
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const unsigned base = __shfl_sync(kFull, base_[k], on_[k] ? __ffs(grp_[k]) - 1 : lane);
-            if (on_[k]) {
-                const unsigned slot = bucket_off[t_[k]] + base + (unsigned)__popc(grp_[k] & ((1u << lane) - 1u));
-                events[slot] = (unsigned short)((pos_[k] & (kTile - 1)) | ((k & 1) << 15));
+                const int pos = which ? b : a;
+                const int t = pos >> kTileShift;
+                const bool on = live && t < num_tiles;
+                const unsigned grp = __match_any_sync(kFull, on ? t : -1 - lane);   // lanes without an event are alone in their group
+                if (on) {
+                    const int leader = __ffs(grp) - 1;
+                    unsigned base = 0;
+                    if (lane == leader) base = atomicAdd(cursor + t, (unsigned)__popc(grp));
+                    base = __shfl_sync(grp, base, leader);
+                    const unsigned slot = bucket_off[t] + base + (unsigned)__popc(grp & ((1u << lane) - 1u));
+                    events[slot] = (unsigned short)((pos & (kTile - 1)) | (which << 15));
+                }
             }
         }
     }
@@ -2250,7 +2241,12 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
     // A feeder that emits packed8 itself (gl_bam_decode) calls gl_depth_bed_region_packed8.  tools/e2e_text_probe.py measures all.
     const char* force_env = getenv("GL_BED_PACK");                      // read per call (tests switch it)
     const int force = force_env ? atoi(force_env) : -1;
-    if ((force == 16 && n >= 4096) || (force < 0 && n >= (int64_t(1) << 20) && glhost_pool_size() >= 24)) {
+    if ((force == 16 && n >= 4096) || (force < 0 && n >= (int64_t(1) << 20) && glhost_pool_size() >= 48)) {
+        // The pack is DRAM-bound: 16 threads reach ~80 % of what 64 do.  More is worse on the 2 x 32-core B200 host: when a
+        // burst of 24+ threads starts streaming out of an idle pool, every memory access of the process (and the GPU's DMA)
+        // stalls for 20-100 ms every few calls (tools/e2e_transport_probe.py; none at 16 threads, none when the pool never idles).
+        static const int pack_threads_env = [] { const char* e = getenv("GL_BED_PACK_THREADS"); return e ? atoi(e) : 0; }();
+        const int pack_threads = threads > 0 ? threads : (pack_threads_env > 0 ? pack_threads_env : std::min(glhost_pool_size(), 16));
         const auto ph0 = std::chrono::steady_clock::now();
         const int64_t nbk = (n + 255) / 256;
         const size_t o_off = ((size_t)nbk * 4 + 255) & ~size_t(255), o_len = o_off + (size_t)nbk * 512, bytes = o_len + (size_t)nbk * 512;
@@ -2283,7 +2279,8 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
         int32_t* ee = ctx->esc_buf + ctx->esc_cap;
         const int64_t esc_cap = (int64_t)ctx->esc_cap;
         int64_t n_esc = 0;
-        const int K = (int)std::max<int64_t>(1, std::min<int64_t>(8, nbk / 4096));   // >= 1 M segments per chunk
+        static const int k_max = [] { const char* e = getenv("GL_BED_PACK_CHUNKS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
+        const int K = (int)std::max<int64_t>(1, std::min<int64_t>(k_max, nbk / 4096));   // >= 1 M segments per chunk
         // (an earlier call's uploads out of the pinned buffer have finished: every entry point synchronises before it returns;
         //  the previous call's unpack kernels out of ctx->packed are ordered before ours on ctx->stream via ev_used[0])
         GL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
@@ -2296,7 +2293,7 @@ int gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t rs, int64_t re, 
             if (b1 <= b0) continue;
             const int64_t esc_before = n_esc;
             const auto tp0 = std::chrono::steady_clock::now();
-            const int rc = gl_pack_segments16_fixed_range_mt(start, end, n, b0, b1, threads, A, O, Ln, es, ee, esc_cap, &n_esc);
+            const int rc = gl_pack_segments16_fixed_range_mt(start, end, n, b0, b1, pack_threads, A, O, Ln, es, ee, esc_cap, &n_esc);
             ctx->tr_pack_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count();
             if (rc == GL_ERANGE) { n_esc = esc_before; fell_back = true; break; }   // (almost) every block escapes: long reads / unsorted input
             if (rc != GL_OK) return gl_fail(ctx, rc, "gl_pack_segments16_fixed_range_mt failed");

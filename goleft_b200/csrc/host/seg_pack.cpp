@@ -532,7 +532,8 @@ __attribute__((target("avx2"))) inline bool block256_avx2(const int32_t* s, cons
     *anchor = smin;
     if ((int64_t)smax - smin > 65535 || lm > 65535u) return false;
     const __m256i A = _mm256_set1_epi32(smin);
-    const bool aligned = ((reinterpret_cast<uintptr_t>(off) | reinterpret_cast<uintptr_t>(len)) & 31) == 0;
+    static const bool nt = [] { const char* e = getenv("GL_PACK_NT"); return !e || atoi(e) != 0; }();     // non-temporal stores (default on)
+    const bool aligned = nt && ((reinterpret_cast<uintptr_t>(off) | reinterpret_cast<uintptr_t>(len)) & 31) == 0;
     for (int i = 0; i < 256; i += 16) {
         const __m256i S0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i)), S1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 8));
         const __m256i E0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(e + i)), E1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(e + i + 8));

@@ -23,13 +23,14 @@ public:
     void run(int64_t n_tasks, const std::function<void(int64_t, int)>& fn, int max_threads = 0);
     static ThreadPool& global();                                             // sized by GL_THREADS or hardware_concurrency
     static int default_threads();
+    static constexpr int kSmallGroup = 16;
 
 private:
     void worker_main(int id);
     void work(int id, uint32_t generation);
     std::vector<std::thread> workers_;
     std::mutex mu_;
-    std::condition_variable cv_;
+    std::condition_variable cv_[2];          // workers 1..kSmallGroup-1 sleep on [0], the rest on [1]: a small job does not wake the whole pool
     std::atomic<uint64_t> gen_{0};
     std::atomic<uint64_t> job_{0};          // (generation << 32) | next task index: a worker that arrives late for a finished job cannot claim from the next one by accident
     std::atomic<int64_t> done_{0};          // tasks of the current job that have finished

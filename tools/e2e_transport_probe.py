@@ -19,19 +19,19 @@ import glsynth  # noqa: E402
 def main():
     node, n_cpus = capi.bind_numa_for_device(0, 0, 1)
     ctx = capi.Ctx(0)
-    L = glsynth.CHR20_LEN
+    L = int(os.environ.get("PROBE_LEN", glsynth.CHR20_LEN))
     s, e = glsynth.segments(L, 19, threads=n_cpus, alloc=ctx.pinned_empty)
     n = s.size
     out = {"numa_node": node, "cpus": n_cpus, "pool": int(capi.lib.glhost_pool_size()), "segments": int(n)}
     n_win = (L - 1) // 500 + 1
     o_hd = ctx.pinned_empty(int(capi.lib.gl_depth_text_bound(b"chr20", n_win)), np.uint8)
     o_ca = ctx.pinned_empty(1 << 20, np.uint8)
-    for mode in ("0", "16", "0", "16"):
+    for mode in (() if os.environ.get("PROBE_CALLS_ONLY") == "0" else ("0", "16", "0", "16")):
         os.environ["GL_BED_PACK"] = mode
         for _ in range(3):
             ctx.depth_bed_contig("chr20", L, s, e, 500, 4, 0, 10_000_000, out=(o_hd, o_ca), raw=True)
         ts, ph, pk = [], [], []
-        for _ in range(10):
+        for _ in range(int(os.environ.get("PROBE_REPS", "10"))):
             ctx.flush_l2(); ctx.sync()
             t0 = time.perf_counter()
             ctx.depth_bed_contig("chr20", L, s, e, 500, 4, 0, 10_000_000, out=(o_hd, o_ca), raw=True)
@@ -39,11 +39,21 @@ def main():
             ph.append([x * 1e3 for x in ctx.depth_transport_phases()])
             pk.append(ctx.depth_transport_stats()[1] * 1e3)
         st = ctx.depth_transport_stats()
+        ctx.profile_enable(True); ctx.profile_read()
+        ctx.depth_bed_contig("chr20", L, s, e, 500, 4, 0, 10_000_000, out=(o_hd, o_ca), raw=True)
+        kms = {}
+        for nm, t in ctx.profile_read():
+            kms[nm] = kms.get(nm, 0.0) + t
+        ctx.profile_enable(False)
+        out.setdefault("kernel_ms_GL_BED_PACK_" + mode, []).append(kms)
         out.setdefault("call_ms_GL_BED_PACK_" + mode, []).append(
-            {"median": float(np.median(ts)), "min": float(np.min(ts)), "max": float(np.max(ts)), "path": ctx.depth_last_path(),
+            {"median": float(np.median(ts)), "min": float(np.min(ts)), "max": float(np.max(ts)), "all": [round(x, 2) for x in ts],
+             "phases_all": [[round(y, 2) for y in x] for x in ph], "path": ctx.depth_last_path(),
              "transport": st[0], "h2d_bytes": st[2], "escaped": st[3], "host_pack_ms_median": float(np.median(pk)),
              "phases_ms_median": [float(x) for x in np.median(np.array(ph), axis=0)]})
-    del os.environ["GL_BED_PACK"]
+    os.environ.pop("GL_BED_PACK", None)
+    if os.environ.get("PROBE_CALLS_ONLY") == "1":
+        print(json.dumps(out)); return
     # the packer alone, pinned output
     nb = (n + 255) // 256
     a = ctx.pinned_empty(nb, np.int32); o = ctx.pinned_empty(nb * 256, np.uint16); ln = ctx.pinned_empty(nb * 256, np.uint16)
@@ -83,7 +93,7 @@ def main():
         dev = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
         st = torch.cuda.Stream()
         res = []
-        for _ in range(4):
+        for _ in range(int(os.environ.get("PROBE_DMA_REPS", "4"))):
             with torch.cuda.stream(st):
                 dev.copy_(big, non_blocking=True)
             t_all, per = ranges(8)
