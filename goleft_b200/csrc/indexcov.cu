@@ -194,20 +194,33 @@ struct C2Smem {
     long long cand98[kC2Cand98];
 };
 
-// ascending bitonic sort of a[0..n2), n2 a power of two, by the whole block
+// ascending bitonic sort of a[0..n2), n2 a power of two, by the whole block (blockDim.x a multiple of 32).
+// A compare-exchange at distance j < 256 pairs two elements of the same 256-element chunk: warp w owns the chunks w, w + W, ...
+// and runs all those stages on its own with __syncwarp between them; only the stages with j >= 256 (15 of the 91 for 8192
+// elements) are block-wide.  Every stage visits the n2/2 pairs directly (pair p -> i = p with a zero inserted at bit log2 j).
 __device__ void block_bitonic(long long* a, int n2) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    auto cex = [&](int i, int j, int k) {
+        const int ixj = i | j;
+        const bool up = (i & k) == 0;
+        const long long x = a[i], y = a[ixj];
+        if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+    };
     for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const bool up = (i & k) == 0;
-                    const long long x = a[i], y = a[ixj];
-                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
-                }
-            }
+        int j = k >> 1;
+        for (; j >= 256; j >>= 1) {                          // block-wide stages
+            for (int p = threadIdx.x; p < (n2 >> 1); p += blockDim.x) cex(((p & ~(j - 1)) << 1) | (p & (j - 1)), j, k);
             __syncthreads();
         }
+        // the remaining stages of this k (j = min(k/2, 128) .. 1) stay inside 256-element chunks
+        for (int c = warp; c * 256 < n2; c += W) {
+            const int base = c * 256, m = min(256, n2 - base);             // m < 256 only when n2 < 256
+            for (int jj = j; jj > 0; jj >>= 1) {
+                for (int p = lane; p < (m >> 1); p += 32) cex(base + (((p & ~(jj - 1)) << 1) | (p & (jj - 1))), jj, k);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
     }
 }
 
