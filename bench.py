@@ -551,7 +551,8 @@ def main():
 
     rank, world, local = dist_env()
     dist = None
-    os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
+    # stdout is the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/WARN/INFO, so leave it unset
+    # unless the caller set it
     from goleft_b200 import capi
     import glsynth
     if capi.device_count() < 1:

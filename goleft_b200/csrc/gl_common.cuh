@@ -72,6 +72,7 @@ struct gl_ctx {
     void* pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;
     void* pack_pinned = nullptr; size_t pack_pinned_bytes = 0;   // gl_depth_bed_contig: pinned home of the packed8 words it makes
+    bool cohort_attr_set = false;                                // ic_cohort2_kernel's dynamic shared-memory limit raised on this ctx's device
     double tr_phase[3] = {0, 0, 0};
     int tr_kind = 0; double tr_pack_s = 0; int64_t tr_bytes = 0, tr_esc = 0;   // gl_depth_transport_stats
     int32_t* esc_buf = nullptr; size_t esc_cap = 0;              // ... and of the raw segments of blocks that do not fit packed16 (2 x esc_cap ints, malloc)

@@ -958,10 +958,9 @@ int gl_indexcov_cohort_device(gl_ctx* ctx, const int64_t* d_sizes, const int64_t
                                                                           reinterpret_cast<const long long*>(d_sample_ptr), S,
                                                                           d_medians, d_depth_out);
     } else {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!ctx->cohort_attr_set) {                          // per device (a function attribute belongs to the device it was set on)
             GL_CUDA(ctx, cudaFuncSetAttribute(ic_cohort2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(C2Smem)));
-            attr_set = true;
+            ctx->cohort_attr_set = true;
         }
         GL_CHECK(gl_buf_reserve(ctx, ctx->misc, 64));
         GL_CUDA(ctx, cudaMemsetAsync(ctx->misc.p, 0, 4, ctx->stream));
