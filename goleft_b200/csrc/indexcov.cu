@@ -829,14 +829,14 @@ __global__ void __launch_bounds__(256) fmt_g3_kernel(const float* __restrict__ v
         // floor(log10 |f|): for normal numbers from the binary exponent E (2^E <= |f| < 2^(E+1)): floor(E log10 2) is the answer or
         // one less (corrected below by the digits themselves); subnormals take the floating-point estimate
         int e10 = ex ? (((int)ex - 127) * 78913) >> 18 : (int)floor(log10((double)fabsf(f)));
-        if (e10 < -15 || e10 >= 15) {
+        if (e10 < -16 || e10 >= 15) {
             len = 0;                                             // host formats it
         } else {
             unsigned long long N = scaled_round_any(m, e2, 2 - e10);
             if (N < 100) { e10--; N = scaled_round_any(m, e2, 2 - e10); }          // estimate one too high
             else if (N > 1000) { e10++; N = scaled_round_any(m, e2, 2 - e10); }    // one too low
             if (N >= 1000) { N = 100; e10++; }                                     // 999.5.. rounds up to the next decade
-            if (e10 < -15 || e10 >= 15) len = 0;
+            if (e10 < -15) len = 0;                              // below 1e-15 after all: the host's
             else {
             const unsigned Nu = (unsigned)N;
             const int d1 = (int)(Nu / 100u), d2 = (int)(Nu / 10u % 10u), d3 = (int)(Nu % 10u);
