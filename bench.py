@@ -13,9 +13,13 @@ contigs; time = max over ranks; value = genome bases / that time.
 value : the rank's contigs already resident in HBM in the engine's segment format (packed8); per step, per contig:
         gl_depth_begin / add_segments_packed8_device / gl_depth_reduce (window sums + class runs stay on the device).
 e2e   : the drop-in call, per contig: gl_depth_bed_contig — decoder-native int32 (start,end) segments in PINNED HOST
-        memory in, finished .depth.bed + .callable.bed BYTES out in pinned host memory.  H2D of the segments, every
-        kernel, the device %.4g row formatter and the D2H of the text are inside the timed region, every step.  This is
-        the work the reference arm is charged for (per-base counting + window/class walk + BED text).
+        memory in, finished .depth.bed + .callable.bed BYTES out in pinned host memory.  The host repack to fixed-block
+        packed16 (when the rank owns >= 48 host threads), the H2D, every kernel, the device %.4g row formatter and the D2H
+        of the text are inside the timed region, every step.  Two gl_ctx lanes per GPU (one host thread each) take the
+        rank's contigs; every call is the synchronous call.  This is the work the reference arm is charged for (per-base
+        counting + window/class walk + BED text).
+extras (N=1): chr20 through every path, other shapes of chr20 (5x, maxmeandepth, W=250, W=1, long reads), the CLI on a BAM;
+        every N: the 2504-sample indexcov cohort (configs[3]); N>1: the 500 x 6.18 M depthwed matrix (configs[4]).
 roofline / cpu_baseline : DESIGN.md §3.
 """
 import argparse
