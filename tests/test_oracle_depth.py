@@ -408,3 +408,45 @@ def test_pack16_fixed_roundtrip():
     with pytest.raises(capi.GlError):
         s = np.arange(0, 100_000 * 1000, 100_000, dtype=np.int32)
         capi.pack_segments16_fixed(s, s + 10, esc_cap=10)
+
+
+def test_host_pool_small_jobs_and_thread_limits():
+    """host-only: the library's thread pool (a job is complete when its TASKS are done; workers that sat out a job sleep; a
+    small job wakes only the first 16 workers) under back-to-back small jobs with changing thread limits, over-subscribed on
+    purpose (GL_THREADS=40): every range call of the fixed-block packer must give the single-threaded bytes."""
+    import os
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import ctypes as C, sys, time
+import numpy as np
+sys.path.insert(0, %r)
+from goleft_b200 import capi
+rng = np.random.default_rng(5)
+n = 3_000_001
+s = np.sort(rng.integers(0, 40_000_000, n)).astype(np.int32)
+e = (s + rng.integers(1, 200, n)).astype(np.int32)
+ref = capi.pack_segments16_fixed(s, e, threads=1)
+nb = (n + 255) // 256
+a = np.zeros(nb, np.int32); o = np.zeros(nb * 256, np.uint16); l = np.zeros(nb * 256, np.uint16)
+es = np.zeros(n, np.int32); ee = np.zeros(n, np.int32)
+m = C.c_int64(0)
+L = capi.lib
+L.gl_pack_segments16_fixed_range_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 5 + [C.c_int64, C.POINTER(C.c_int64)]
+assert L.glhost_pool_size() == 40
+for rep in range(120):
+    K = 1 + rep %% 23
+    thr = [0, 16, 3, 40, 8, 17, 1][rep %% 7]
+    a[:] = 0; o[:] = 0; l[:] = 0; m.value = 0
+    for c in range(K):
+        rc = L.gl_pack_segments16_fixed_range_mt(s.ctypes.data, e.ctypes.data, n, nb * c // K, nb * (c + 1) // K, thr, a.ctypes.data, o.ctypes.data,
+                                                 l.ctypes.data, es.ctypes.data, ee.ctypes.data, n, C.byref(m))
+        assert rc == 0
+    if rep %% 10 == 0:
+        time.sleep(0.005)                       # let the workers fall asleep: the next job has to wake them
+    assert np.array_equal(a, ref[0]) and np.array_equal(o, ref[1]) and np.array_equal(l, ref[2]) and np.array_equal(es[:m.value], ref[3]), rep
+print("ok")
+''' % ROOT
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, GL_THREADS="40"), timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith("ok"), p.stderr[-2000:]
