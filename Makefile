@@ -60,12 +60,6 @@ synth: tools/synth/libglsynth.so
 tools/synth/libglsynth.so: tools/synth/glsynth.c tools/synth/bamsynth.c tools/synth/glsynth_core.h
 	$(CC) -O2 -fPIC -shared -Wall -o $@ tools/synth/glsynth.c tools/synth/bamsynth.c -lpthread -lz
 
-# A/B build of the depth kernels with the branch-free segment application (GL_BRANCHFREE_APPLY=1): same library otherwise
-exp: $(LIB)
-	@mkdir -p $(BUILD)
-	$(NVCC) $(NVFLAGS) -DGL_BRANCHFREE_APPLY=1 -I$(NCCL_INC) -c $(CSRC)/depth.cu -o $(BUILD)/depth_exp.o 2> $(BUILD)/depth_exp.ptxas.log
-	$(NVCC) $(ARCH) -shared -o goleft_b200/libgoleft_b200_exp.so $(BUILD)/depth_exp.o $(filter-out $(BUILD)/depth.o,$(CU_OBJS)) $(CPP_OBJS) -lz -lpthread -ldl
-
 clean:
 	rm -rf $(BUILD) $(LIB) bin oracle/_build tools/synth/libglsynth.so
 

@@ -15,6 +15,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <functional>
 #include <condition_variable>
@@ -845,10 +846,15 @@ static int cmd_indexcov(int argc, char** argv) {
         for (auto& t : th) t.join();
     };
     glhost_pool_warm();
+    ic_mark("host arrays");
+    std::vector<std::array<double, 4>> gpu_t((size_t)G);                     // per GPU: ctx, upload + I1, I2 + I3, D2H
     run_on_gpus([&](int g) {
         gl_ctx* c = nullptr;
+        double tg0 = now_s();
         if (gl_ctx_create(g % n_dev, &c) != GL_OK) fatal(1, "goleft indexcov: %s", gl_last_error(nullptr));
         ctxs[(size_t)g] = c;
+        gpu_t[(size_t)g] = {now_s() - tg0, 0, 0, 0};
+        tg0 = now_s();
         const size_t a = cut[(size_t)g], b = cut[(size_t)g + 1];
         const int64_t t0 = sample_ptr[a], tiles = sample_ptr[b] - t0;
         Shard& sd = shard[(size_t)g];
@@ -875,6 +881,8 @@ static int cmd_indexcov(int argc, char** argv) {
         for (size_t i = a; i < b; i++)
             if (!crai_sizes[i].empty())
                 glck(c, gl_memcpy_h2d(c, sd.d_sizes + (sample_ptr[i] - t0), crai_sizes[i].data(), (int64_t)crai_sizes[i].size() * 8), "gl_memcpy_h2d");
+        glck(c, gl_sync(c), "gl_sync");
+        gpu_t[(size_t)g][1] = now_s() - tg0; tg0 = now_s();
         // I2+I3 for the shard in one kernel, on the resident sizes (indexcov.go:83-151)
         std::vector<int64_t> sp(sample_ptr.begin() + (long)a, sample_ptr.begin() + (long)b + 1);
         for (auto& x : sp) x -= t0;
@@ -882,12 +890,19 @@ static int cmd_indexcov(int argc, char** argv) {
         double* d_med = static_cast<double*>(dalloc((b - a) * 8));
         sd.d_dep = static_cast<float*>(dalloc((size_t)tiles * 4));
         glck(c, gl_indexcov_cohort_device(c, sd.d_sizes, static_cast<const int64_t*>(d_sp), (int32_t)(b - a), d_med, sd.d_dep), "gl_indexcov_cohort_device");
+        glck(c, gl_sync(c), "gl_sync");
+        gpu_t[(size_t)g][2] = now_s() - tg0; tg0 = now_s();
         glck(c, gl_memcpy_d2h(c, med.data() + a, d_med, (int64_t)(b - a) * 8), "gl_memcpy_d2h");
         glck(c, gl_memcpy_d2h(c, dep.data() + t0, sd.d_dep, tiles * 4), "gl_memcpy_d2h");
+        gpu_t[(size_t)g][3] = now_s() - tg0;
         gl_dev_free(c, sd.d_sizes); gl_dev_free(c, d_sp); gl_dev_free(c, d_med);
         sd.d_sizes = nullptr;
     });
     std::vector<uint64_t>().swap(voff_all);
+    if (ic_timing)
+        for (int g = 0; g < G; g++)
+            fprintf(stderr, "[indexcov timing]   gpu %d: gl_ctx_create %.3f s, upload + I1 %.3f s, I2 + I3 %.3f s, D2H %.3f s\n", g, gpu_t[(size_t)g][0],
+                    gpu_t[(size_t)g][1], gpu_t[(size_t)g][2], gpu_t[(size_t)g][3]);
     ic_mark("I1 + I2 + I3 (GPU, + D2H)");
 
     glhts::BgzfWriter bgz(base + ".bed.gz");

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# GOLEFT_B200_LIB: another build of the same library (the Makefile's `exp` A/B target); tests and bench use the default
+# GOLEFT_B200_LIB: another build of the same library (A/B runs); tests and bench use the default
 LIB_PATH = os.environ.get("GOLEFT_B200_LIB") or os.path.join(_HERE, "libgoleft_b200.so")
 
 GL_OK, GL_EINVAL, GL_ECUDA, GL_ENOMEM, GL_ESTATE, GL_ERANGE, GL_ENCCL = 0, -1, -2, -3, -4, -5, -6

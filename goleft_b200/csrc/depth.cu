@@ -893,17 +893,6 @@ __device__ __forceinline__ bool fused_out_of_order(const SegRange& g) {
 // one segment into the tile [t0,t1): +1/-1 in shared memory, or +1 carried in when it covers base t0-1
 // Region clipping: rs <= t0 and t1 <= re, so only tile 0 can see starts below rs (they count from its first base)
 // and an end beyond re only lands in the masked tail of the last tile: neither needs an explicit clip.
-#if GL_BRANCHFREE_APPLY
-__device__ __forceinline__ void fused_apply(int* s_tile, int t0, int t1, bool first_tile, int s, int e, int& carry) {
-    const int sc = first_tile ? max(s, t0) : s;                         // t0 == rs on the first tile
-    const bool live = (sc < e) & (sc < t1) & (e >= t0);
-    const int ra = sc - t0, rb = e - t0;                                // live: ra < 4096 and rb >= 0
-    const int pa = live ? ra : (int)threadIdx.x, pb = live ? rb : (int)threadIdx.x;   // the others add zeros at addresses of their own
-    atomicAdd(s_tile + swz_elem(pa & (kTile - 1)), (live & (ra >= 0)) ? 1 : 0);
-    carry += (live & (ra < 0)) ? 1 : 0;                                 // covers base t0-1: carried in
-    atomicAdd(s_tile + swz_elem(pb & (kTile - 1)), (live & (rb < kTile)) ? -1 : 0);
-}
-#else
 __device__ __forceinline__ void fused_apply(int* s_tile, int t0, int t1, bool first_tile, int s, int e, int& carry) {
     const int sc = first_tile ? max(s, t0) : s;                         // t0 == rs on the first tile
     if (sc < e && sc < t1 && e >= t0) {
@@ -912,7 +901,6 @@ __device__ __forceinline__ void fused_apply(int* s_tile, int t0, int t1, bool fi
         if (e - t0 < kTile) atomicAdd(s_tile + swz_elem(e - t0), -1);
     }
 }
-#endif
 
 __global__ void __launch_bounds__(kScanThreads, 4) depth_fused_kernel(const ScanParams p) {
     __shared__ __align__(16) int s_tile[kTile];
@@ -1069,14 +1057,13 @@ constexpr int kF8BlocksPerPass = kF8Threads / 16;   // a block is 16 lanes x 4 s
 //   it covers base t0-1 or ends exactly at t0 — then its -1 lands on base 0 and cancels the carry);  -1 at b when inside.
 // A start before the region (first tile) is a carry like any other: the region's first base starts a run regardless, so
 // the depth "before" it is never looked at.  Starts / ends beyond the region end fall in the masked tail of the last tile.
-#ifndef GL_BRANCHFREE_APPLY
-#define GL_BRANCHFREE_APPLY 0
-#endif
-#if GL_BRANCHFREE_APPLY
 // `if (p) atomicAdd(smem, v)` compiles to a divergent region per atomic (BSSY / BRA / address math / ATOMS / BSYNC, ~15
 // instructions; ptxas does the same to a predicated `red.shared`).  Adding ZERO at an always-valid address instead keeps the
 // warp converged: the position is masked into the tile, the value is the predicate (+1 / -1 or 0), the atomic is
-// unconditional — 7 instructions per event, and the eight atomics of a thread interleave freely.
+// unconditional — 7 instructions per event, and the eight atomics of a thread interleave freely.  A/B on the B200 (same box,
+// same run): K_fused8 84.3 -> 80.6 us on chr20 30x, 173.9 -> 168.2 us at 5x, 145.9 -> 140.4 us with maxmeandepth.  (The same
+// change made K_fused 2 % slower — a quarter of its 1024 register slots per tile are idle and would add zeros — so it keeps
+// the branches.)
 __device__ __forceinline__ void fused_apply32(int* s_tile, int a, int len, int& carry) {
     const int b = a + len;
     const bool live = len != 0;                             // 0 = filler / empty slot
@@ -1086,15 +1073,6 @@ __device__ __forceinline__ void fused_apply32(int* s_tile, int a, int len, int& 
     carry += (live & (a < 0) & (b >= 0)) ? 1 : 0;
     atomicAdd(s_tile + swz_elem_t<kF8BPT>(b & (kTile - 1)), vb);
 }
-#else
-__device__ __forceinline__ void fused_apply32(int* s_tile, int a, int len, int& carry) {
-    if (len == 0) return;                                   // filler / empty slot
-    const int b = a + len;
-    if ((unsigned)a < (unsigned)kTile) atomicAdd(s_tile + swz_elem_t<kF8BPT>(a), 1);
-    else if (a < 0 && b >= 0) carry++;
-    if ((unsigned)b < (unsigned)kTile) atomicAdd(s_tile + swz_elem_t<kF8BPT>(b), -1);
-}
-#endif
 
 // thread (tid) takes slots 4*(tid&15)..+3 of block lo + (tid>>4) + 8*pass
 __device__ __forceinline__ P8Regs fused8_load(const ScanParams& p, int lo, int hi, int pass) {
@@ -1117,14 +1095,9 @@ __device__ __forceinline__ void fused8_apply(const P8Regs& r, int* s_tile, int t
         const int v = __shfl_up_sync(kFull, inc, o, 16);
         if (sub >= o) inc += v;
     }
-#if GL_BRANCHFREE_APPLY
     if (__ballot_sync(kFull, r.l != 0) == 0) return;        // no live slot in the whole warp (warp-uniform: no divergence)
     // tile-relative start of the slot before this thread's first; a thread without a live slot adds zeros at addresses of its own
     const int base = r.l != 0 ? r.anchor + inc - d3 - t0 : (int)threadIdx.x;
-#else
-    if (r.l == 0) return;                                   // four empty slots (or no block): nothing to add
-    const int base = r.anchor + inc - d3 - t0;              // tile-relative start of the slot before this thread's first
-#endif
     fused_apply32(s_tile, base + d0, (int)(r.l & 0xff), carry);
     fused_apply32(s_tile, base + d1, (int)((r.l >> 8) & 0xff), carry);
     fused_apply32(s_tile, base + d2, (int)((r.l >> 16) & 0xff), carry);
