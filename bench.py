@@ -555,8 +555,7 @@ def main():
 
     rank, world, local = dist_env()
     dist = None
-    # stdout is the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/WARN/INFO, so leave it unset
-    # unless the caller set it
+    os.environ.setdefault("NCCL_DEBUG", "WARN")          # as in round 1: NCCL's one-line version banner precedes the JSON line (the last line of stdout)
     from goleft_b200 import capi
     import glsynth
     if capi.device_count() < 1:
