@@ -521,8 +521,32 @@ def cli_wallclock(n_cpus):
         dall = b.decode(0, threads=0)
         b.close()
         hd_bytes = os.path.getsize(os.path.join(tmp, "out.depth.bed"))
+        # BED mode (depth.go:103-120: one samtools child per line in the reference): an exome-shaped BED, chr20's share of ~200 k
+        # targets = 4,200 lines of 120-400 bp; here one pass over the span they cover + gl_depth_interval_sums for the edge windows
+        bed_leg = None
+        try:
+            rng = np.random.default_rng(20)
+            starts = np.sort(rng.integers(100_000, glsynth.CHR20_LEN - 1000, 4200))
+            lens = rng.integers(120, 400, starts.size)
+            with open(os.path.join(tmp, "exome.bed"), "w") as fh:
+                for a_, l_ in zip(starts, lens):
+                    fh.write("chr20\t%d\t%d\n" % (a_, a_ + l_))
+            wb, tb = [], None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                pb = subprocess.run([exe, "depth", "--timing", "-w", "250", "--bed", os.path.join(tmp, "exome.bed"), "--prefix", os.path.join(tmp, "ex"),
+                                     "-r", os.path.join(tmp, "ref.fa"), bam], capture_output=True, text=True)
+                wb.append(time.perf_counter() - t0)
+                if pb.returncode != 0:
+                    raise RuntimeError(pb.stderr[-300:])
+                tb = json.loads(pb.stderr.strip().splitlines()[-1])["goleft_depth_timing"]
+            bed_leg = {"lines": int(starts.size), "window": 250, "process_wall_s_all": wb, "in_process": tb,
+                       "depth_bed_rows": sum(1 for _ in open(os.path.join(tmp, "ex.depth.bed"))),
+                       "note": "goleft depth --bed on the same chr20 BAM: the reference would start 4,200 samtools children"}
+        except Exception as ex:
+            bed_leg = {"error": str(ex)[:300]}
         return {"bam_bytes": os.path.getsize(bam), "bam_write_s": t_write, "process_wall_s": min(walls), "process_wall_s_all": walls,
-                "in_process": tim, "depth_bed_bytes": hd_bytes,
+                "in_process": tim, "depth_bed_bytes": hd_bytes, "bed_mode_exome": bed_leg,
                 "value": glsynth.CHR20_LEN / min(walls) / 1e6, "unit": "Mbases/s",
                 "gpu_feeder": {"steady_state_call": dev,
                                "note": "gl_bam_decode_device on the chr20 BAM, third call: parallel pread of the compressed range, H2D, bgzf_inflate_kernel "

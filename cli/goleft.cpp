@@ -744,21 +744,25 @@ static int cmd_indexcov(int argc, char** argv) {
     std::vector<std::string> names(S);
     std::vector<glhts::BaiIndex> idx(S);
     std::vector<std::vector<glhts::CraiSlices>> crai(S);
-    for (size_t i = 0; i < S; i++) {
+    // the reference reads the indexes on 8 goroutines (indexcov.go:417-434); here every pool thread takes files.  The first
+    // error in INPUT order is the one reported, whatever thread met it.
+    std::vector<std::string> read_err(S);
+    glhost::ThreadPool::global().run((int64_t)S, [&](int64_t ii, int) {
+        const size_t i = (size_t)ii;
         const std::string& b = bams[i];
         if (ends_with(b, ".crai")) {                                       // indexcov.go:474-496
-            std::string e = glhts::crai_read(b, crai[i]);
-            if (!e.empty()) fatal(1, "%s", e.c_str());
+            read_err[i] = glhts::crai_read(b, crai[i]);
             names[i] = short_name(b, true, nullptr);
-            continue;
+            return;
         }
         std::string p = ends_with(b, ".bai") ? b : b + ".bai";
         if (!file_exists(p)) p = b.substr(0, b.size() - 4) + (ends_with(b, ".bai") ? "" : ".bai");
-        std::string e = glhts::bai_read(p, idx[i]);
-        if (!e.empty()) fatal(1, "%s", e.c_str());
+        read_err[i] = glhts::bai_read(p, idx[i]);
+        if (!read_err[i].empty()) return;
         if (ends_with(b, ".bai")) names[i] = short_name(b, true, nullptr);
-        else { glhts::BamHeader h; std::string he = glhts::bam_read_header(b, h); if (!he.empty()) fatal(1, "%s", he.c_str()); names[i] = short_name(b, false, &h); }
-    }
+        else { glhts::BamHeader h; read_err[i] = glhts::bam_read_header(b, h); if (read_err[i].empty()) names[i] = short_name(b, false, &h); }
+    });
+    for (size_t i = 0; i < S; i++) if (!read_err[i].empty()) fatal(1, "%s", read_err[i].c_str());
 
     ic_mark("read indexes");
     // ---- GPUs (samples are independent through I5 -> sample-sharded over the GPUs; the rows need every sample
