@@ -233,8 +233,10 @@ int  gl_depth_format_rows(gl_ctx* ctx, const char* chrom, const int32_t* row_s, 
                           int64_t n, char* out, int64_t cap, int64_t* len);
 /* One contig end to end, the call `goleft depth` makes per reference sequence in .fai mode (depth.go:129-159 + the
  * callback 238-364 for each of its chunks, concatenated in order): host segments in -> BED bytes out.  step = the chunk
- * length (depth.go:132: a multiple of W).  Short-read input is packed to packed8 on `threads` host threads (0 = all)
- * and streamed up while the first tiles reduce; long segments go up as int32.  Everything is inside the call. */
+ * length (depth.go:132: a multiple of W).  The int32 arrays go over PCIe as fixed-block packed16 (4 B/segment), rewritten
+ * chunk by chunk by the library's host pool (`threads` of it, 0 = the default 16) while the previous chunk is on the wire,
+ * when there are >= 2^20 segments and the pool has >= 48 threads; otherwise, and for long reads, as they are (GL_BED_PACK,
+ * gl_depth_transport_stats).  Everything is inside the call; it is synchronous. */
 /* The same for [region_start, region_end) of a contig: region_start must be a multiple of step (whole chunks), so that
  * contigs longer than 2^30-1 bases, or one GPU's share of a contig, can be done in pieces whose texts concatenate. */
 int  gl_depth_bed_region(gl_ctx* ctx, const char* chrom, int64_t region_start, int64_t region_end, const int32_t* start, const int32_t* end,
